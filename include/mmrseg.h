@@ -1,0 +1,266 @@
+/*
+ * mmrseg.h — C-ABI of libmmrseg.so: the sm_100a kernels behind the segmentation
+ * train / infer step of AliakbarMzadeh/MMR_semantic-segmentation_v1.
+ *
+ * The reference has no FFI: its "operator interface" for this path is the set of
+ * Python call sites listed below.  Every entry point names the
+ * reference call it replaces.  Conventions:
+ *   - plain pointers and sizes, no torch types; all device pointers are caller-owned;
+ *   - every launch is asynchronous on the given CUDA stream (a cudaStream_t passed as
+ *     void*); nothing here synchronises or allocates on the launch path (plan creation
+ *     allocates its small descriptor tables once);
+ *   - return 0 on success, a negative code on error; mmr_last_error() gives the
+ *     message (thread-local);
+ *   - activations are NHWC bf16 inside the path, logits / dlogits are NCHW fp32 at the
+ *     boundary (what `model(x)` returns in the reference), labels are int64.
+ */
+#ifndef MMRSEG_H
+#define MMRSEG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mmr_stream_t; /* cudaStream_t */
+
+const char* mmr_last_error(void);
+int mmr_abi_version(void);
+/* 1 if a CUDA device with compute capability 10.x is usable in this process. */
+int mmr_device_ok(void);
+
+/* ------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 (fprop and dgrad share it).
+ * Replaces: nn.Conv2d forward/backward-data as issued by smp Conv2dReLU / torchvision
+ * BasicBlock / SegmentationHead inside `seg = model(img)` (SU/ModelTraining.py:589,
+ * SU/ModelEval.py:419, ED/Main_MMR_SegModel.py:697) and `loss.backward()`
+ * (SU/ModelTraining.py:614, ED/Main_MMR_SegModel.py:715), including the
+ * F.interpolate(nearest x2) + torch.cat of smp DecoderBlock.forward, which become
+ * K-segments of the gather (no upsampled / concatenated tensor is materialised).
+ *
+ * One output tile = 128 pixels (box_w x box_h x box_n) x bn channels.  The reduction is a
+ * list of K-steps; K-step i multiplies a [128 x bk] activation box, fetched by TMA from
+ * source `src` at channel c0 and spatial origin (ax*gx0+bx, ay*gy0+by) of the tile, by the
+ * [bn x bk] weight block at column wk of the K-major weight matrix.  Up to 4 pixel
+ * classes (output parities) each own a K-step range, which is how nearest-x2 gathers and
+ * stride-2 transposed gathers are expressed without replication or zero-insertion.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* ptr; /* bf16 NHWC */
+  int32_t C, W, H, N;
+  int32_t es; /* TMA element stride along W and H (1 or 2) */
+} MmrSrc;
+
+typedef struct {
+  int32_t src, c0, ax, bx, ay, by, wk, pad_;
+} MmrKStep;
+
+typedef struct {
+  int32_t kbegin, kcount, oy_add, ox_add;
+} MmrConvClass;
+
+typedef struct {
+  void* ptr;    /* destination tensor base (bf16 NHWC, or fp32 NCHW in out_mode 1) */
+  int32_t ldc;  /* channels of the destination tensor */
+  int32_t coff; /* first destination channel written by this N-tile */
+} MmrOutSeg;
+
+enum { MMR_OUT_BF16_NHWC = 0, MMR_OUT_F32_NCHW = 1 };
+
+typedef struct {
+  int32_t nsrc;
+  MmrSrc src[6];
+  const void* weights; /* bf16 [w_rows][w_cols], K contiguous */
+  int32_t w_rows, w_cols;
+  int32_t bk; /* channels per K-step: 64, 32 or 16 */
+  int32_t bn; /* output channels per tile: multiple of 16, <= 256 */
+  int32_t box_w, box_h, box_n; /* box_w*box_h*box_n == 128 */
+  int32_t ncls;
+  MmrConvClass cls[4];
+  int32_t nksteps;
+  const MmrKStep* ksteps; /* host array */
+  int32_t n_tiles_n;
+  const MmrOutSeg* outsegs; /* host array, one per N-tile */
+  int32_t gx_count, gy_count, n_img; /* extent of the tile grid (per class) */
+  int32_t oy_mul, ox_mul;            /* output y = oy_mul*gy + oy_add */
+  int32_t Hout, Wout;                /* spatial size of the destination tensors */
+  int32_t cout_total;                /* valid output channels (masks the last N-tile) */
+  const float* scale;                /* per output channel, may be NULL (=1) */
+  const float* bias;                 /* per output channel, may be NULL (=0) */
+  const void* residual;              /* bf16 NHWC, added before ReLU, may be NULL */
+  int32_t res_ldc;
+  int32_t relu;
+  int32_t out_mode;
+} MmrConvDesc;
+
+int mmr_conv_plan_create(const MmrConvDesc* desc, void** plan);
+/* impl: 0 = tcgen05/TMA kernel (the product path); 1 = scalar CUDA-core kernel reading the
+ * same K-step tables (test aid for bisecting table bugs from tensor-core bugs). */
+int mmr_conv_plan_run(void* plan, int impl, mmr_stream_t stream);
+int mmr_conv_plan_destroy(void* plan);
+
+/* ------------------------------------------------------------------------------------
+ * Weight gradient on tcgen05: dW[co][chunk cols] = sum over pixels dz[p][co] * x[p'][ci],
+ * both operands pixel-major (MN-major UMMA).  Replaces the weight-gradient half of
+ * `loss.backward()` for every nn.Conv2d on the path.
+ * A "chunk" is (source, channel offset, tap); per pixel class it carries the spatial shift
+ * of its activation box.  Output: fp32 partial sums [n_split][m_rows][n_chunks*chunk_ch].
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t src, c0;
+  int32_t ax[4], bx[4], ay[4], by[4]; /* per pixel class */
+} MmrWgChunk;
+
+typedef struct {
+  MmrSrc dz; /* gradient wrt the conv output, bf16 NHWC; es = traversal stride of a class grid */
+  int32_t dz_ax, dz_ay;     /* dz box origin = dz_ax*gx0 + dz_bx[cls] */
+  int32_t dz_bx[4], dz_by[4];
+  int32_t nsrc;
+  MmrSrc src[6];
+  int32_t ncls;
+  int32_t nchunks;
+  const MmrWgChunk* chunks; /* host array */
+  int32_t chunk_ch;         /* channels per chunk: 64, 32 or 16 */
+  int32_t cout;             /* valid rows (<= 128 per M-tile) */
+  int32_t kp_w, kp_h;       /* pixel box of one K-step: kp_w*kp_h == 32 */
+  int32_t gx_count, gy_count, n_img;
+  int32_t n_split;          /* split-K factor over the pixel tiles */
+  float* partial;           /* fp32 [n_split][cout_pad][nchunks*chunk_ch] */
+  int32_t cout_pad;
+} MmrWgradDesc;
+
+int mmr_wgrad_plan_create(const MmrWgradDesc* desc, void** plan);
+int mmr_wgrad_plan_run(void* plan, int impl, mmr_stream_t stream);
+int mmr_wgrad_plan_destroy(void* plan);
+
+/* Sum the split-K partials and scatter into the OIHW fp32 gradient of the parameter
+ * (`param.grad` in the reference's optimizer, SU/ModelTraining.py:366,617).
+ * partial column index = (tap*cin + ci) ; dst index = ((co*cin + ci)*taps + tap).
+ * accumulate != 0 adds into dst (gradient accumulation, ED/Main_MMR_SegModel.py:718). */
+int mmr_wgrad_reduce(const float* partial, int n_split, int cout, int cout_pad, int cin, int taps,
+                     int ncols_pad, float* dst_oihw, int accumulate, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Layout / packing kernels at the boundary of the path.
+ * ------------------------------------------------------------------------------------ */
+/* NCHW fp32 image -> im2col rows for the 7x7 stride-2 pad-3 stem (encoder.conv1), bf16
+ * [N*Ho*Wo][kpad], column = (ky*7+kx)*3 + c, zero padded to kpad.  Optionally applies
+ * (x-mean[c])/std[c] first (utils.normalize, SU/utils.py:480-519) when mean != NULL. */
+int mmr_stem_im2col(const float* x, int N, int H, int W, void* out, int kpad, const float* mean,
+                    const float* std_, mmr_stream_t stream);
+/* NCHW fp32 -> NHWC bf16 with channel padding to cpad (zeros). */
+int mmr_pack_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, void* out,
+                                   int cpad, mmr_stream_t stream);
+/* NHWC bf16 -> NCHW fp32 (first C of ldc channels). */
+int mmr_unpack_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int ldc, int H, int W,
+                                     float* out, mmr_stream_t stream);
+/* OIHW fp32 master weights -> bf16 GEMM layouts:
+ *   fwd  [O][kh*kw][I]  (row stride ldf >= kh*kw*I)   and, if dgrad != NULL,
+ *   dgrad [I][kh*kw][O] (row stride ldd >= kh*kw*O). */
+int mmr_repack_weights(const float* w_oihw, int O, int I, int taps, void* fwd, int ldf,
+                       void* dgrad, int ldd, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * BatchNorm2d (+ residual add + ReLU), training and eval; replaces nn.BatchNorm2d / ReLU
+ * / the BasicBlock residual add inside model(img) and their backward.
+ * ------------------------------------------------------------------------------------ */
+/* Per-channel sum and sum of squares of z [P][C] bf16 -> double partial[nblk][2][C]. */
+int mmr_bn_stats(const void* z, int64_t P, int C, double* partial, int nblk, mmr_stream_t stream);
+/* partial -> mean/invstd, scale = gamma*invstd, shift = beta - mean*scale; running stats
+ * updated with `momentum` (unbiased variance), num_batches_tracked += 1. */
+int mmr_bn_finalize(const double* partial, int nblk, int64_t P, int C, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean,
+                    float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
+                    float* scale, float* shift, mmr_stream_t stream);
+/* a = [relu](z*scale + shift [+ residual]) ; all NHWC bf16, [P][C]. */
+int mmr_bn_apply(const void* z, int64_t P, int C, const float* scale, const float* shift,
+                 const void* residual, int relu, void* out, mmr_stream_t stream);
+
+/* A gradient of an activation is the sum of several contribution tensors (one per
+ * consumer).  pool2 != 0: the contribution lives at twice the resolution and is 2x2
+ * sum-pooled on the fly (backward of nearest x2 upsampling). */
+typedef struct {
+  const void* ptr; /* bf16 NHWC */
+  int32_t pool2;
+} MmrContrib;
+
+/* g = mask * sum(contribs), mask = (act > 0) if act != NULL; writes g (bf16) and the
+ * per-channel double partial sums of g and g*xhat, xhat = (z-mean)*invstd. */
+int mmr_bn_bwd_reduce(const MmrContrib* contribs, int ncontrib, const void* act, const void* z,
+                      const float* mean, const float* invstd, int N, int H, int W, int C, void* g,
+                      double* partial, int nblk, mmr_stream_t stream);
+/* partial -> dgamma, dbeta (fp32, accumulate flag) and the coefficients used by apply. */
+int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, int C, const float* gamma,
+                        const float* invstd, float* dgamma, float* dbeta, int accumulate,
+                        float* coef /* [3][C] */, mmr_stream_t stream);
+/* dz = coefA*g + coefB*xhat + coefC, bf16. */
+int mmr_bn_bwd_apply(const void* g, const void* z, const float* mean, const float* invstd,
+                     const float* coef, int64_t P, int C, void* dz, mmr_stream_t stream);
+/* g = mask * sum(contribs) only (layers without BN), plus optional per-channel sum (bias
+ * gradient) as double partials. */
+int mmr_grad_gather(const MmrContrib* contribs, int ncontrib, const void* act, int N, int H, int W,
+                    int C, void* g, double* partial, int nblk, mmr_stream_t stream);
+
+/* MaxPool2d(3, stride 2, pad 1) on NHWC bf16; idx = window position 0..8 of the first
+ * maximum (torch tie rule).  Replaces encoder.maxpool. */
+int mmr_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, uint8_t* idx,
+                         mmr_stream_t stream);
+int mmr_maxpool3x3s2_bwd(const MmrContrib* contribs, int ncontrib, const uint8_t* idx, int N,
+                         int H, int W, int C, void* gin, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Loss: softmax + soft-Dice + cross-entropy, forward and backward.
+ * Replaces dice_loss / DiceLoss.forward (SU/dice_loss.py:37-161,241-259) +
+ * nn.CrossEntropyLoss (SU/ModelTraining.py:360,601) combined as w*dice + (1-w)*ce
+ * (SU/ModelTraining.py:600-603), and monai DiceCELoss(softmax=True)
+ * (ED/Main_MMR_SegModel.py:578,709) through its smoothing constants.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  float dice_eps_nr, dice_eps_dr; /* 1.0/1.0 (SU) or 1e-5/1e-5 (monai) */
+  float onehot_eps;               /* 1e-6: kornia one_hot adds eps everywhere; 0 for monai */
+  float w_dice, w_ce;
+  int32_t dice_channels;   /* leading channels entering the dice term (ignore_index slice) */
+  int64_t ce_ignore_index; /* labels equal to this are skipped by CE (-100 = torch default) */
+} MmrLossParams;
+
+/* workspace: doubles, size mmr_dice_ce_workspace_doubles(N, C, blocks). Outputs:
+ * out[0] = total loss, out[1] = dice term, out[2] = ce term (fp32). */
+int64_t mmr_dice_ce_workspace_doubles(int N, int C, int nblk);
+int mmr_dice_ce_fwd(const float* logits, const int64_t* labels, int N, int C, int H, int W,
+                    const MmrLossParams* p, double* workspace, int nblk, float* out,
+                    mmr_stream_t stream);
+/* dlogits (fp32 NCHW) = grad_scale * dLoss/dlogits, using the sums left in workspace. */
+int mmr_dice_ce_bwd(const float* logits, const int64_t* labels, int N, int C, int H, int W,
+                    const MmrLossParams* p, const double* workspace, float grad_scale,
+                    float* dlogits, mmr_stream_t stream);
+/* fp32 NCHW dlogits -> bf16 NHWC padded to cpad channels + per-class sums (head bias grad). */
+int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int W, void* out, int cpad,
+                       float* dbias, int accumulate, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Metric: argmax -> per-image confusion matrix, integer and bit-exact.
+ * Replaces torch.argmax + Evaluate.addBatch (SU/utils.py:82-138) and smp get_stats
+ * (ED/Main_MMR_SegModel.py:634-639,1323-1325): cm[n][g][p] += #{label==g & pred==p}.
+ * Labels outside [0,C) (ignore_index) are skipped.  pred_out (int64 [N][H][W]) optional.
+ * ------------------------------------------------------------------------------------ */
+int mmr_confusion_from_logits(const float* logits, const int64_t* labels, int N, int C, int H,
+                              int W, int64_t* cm /* [N][C][C], accumulated */, int64_t* pred_out,
+                              mmr_stream_t stream);
+int mmr_confusion_from_preds(const int64_t* preds, const int64_t* labels, int N, int C,
+                             int64_t npix_per_image, int64_t* cm, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Optimiser: Adam / AdamW over one flat fp32 buffer.  Replaces optim.Adam(...).step()
+ * (SU/ModelTraining.py:366,617) and AdamW (ED/Main_MMR_SegModel.py:878-880).
+ * mode 0: L2 (g += wd*p), mode 1: decoupled (AdamW).  bc1 = 1-b1^t, bc2 = 1-b2^t.
+ * grad_scale multiplies g first (1/world_size for DDP, or the clip coefficient).
+ * ------------------------------------------------------------------------------------ */
+int mmr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1,
+                  float b2, float eps, float wd, float bc1, float bc2, int mode, float grad_scale,
+                  mmr_stream_t stream);
+/* sum of squares of g (double out[0] accumulated) for clip_grad_norm_. */
+int mmr_sumsq(const float* g, int64_t n, double* out, mmr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMRSEG_H */

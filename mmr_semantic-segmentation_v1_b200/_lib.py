@@ -1,0 +1,154 @@
+"""ctypes binding of libmmrseg.so (the C-ABI declared in include/mmrseg.h).
+
+There is no CPU fallback: if the shared library is missing this module raises, and every
+launch wrapper raises `MmrError` carrying `mmr_last_error()` when a call fails.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmmrseg.so")
+
+
+class MmrError(RuntimeError):
+    pass
+
+
+class MmrSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
+                ("N", C.c_int32), ("es", C.c_int32)]
+
+
+class MmrKStep(C.Structure):
+    _fields_ = [("src", C.c_int32), ("c0", C.c_int32), ("ax", C.c_int32), ("bx", C.c_int32),
+                ("ay", C.c_int32), ("by", C.c_int32), ("wk", C.c_int32), ("pad_", C.c_int32)]
+
+
+class MmrConvClass(C.Structure):
+    _fields_ = [("kbegin", C.c_int32), ("kcount", C.c_int32), ("oy_add", C.c_int32),
+                ("ox_add", C.c_int32)]
+
+
+class MmrOutSeg(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ldc", C.c_int32), ("coff", C.c_int32)]
+
+
+class MmrConvDesc(C.Structure):
+    _fields_ = [
+        ("nsrc", C.c_int32), ("src", MmrSrc * 6),
+        ("weights", C.c_void_p), ("w_rows", C.c_int32), ("w_cols", C.c_int32),
+        ("bk", C.c_int32), ("bn", C.c_int32),
+        ("box_w", C.c_int32), ("box_h", C.c_int32), ("box_n", C.c_int32),
+        ("ncls", C.c_int32), ("cls", MmrConvClass * 4),
+        ("nksteps", C.c_int32), ("ksteps", C.POINTER(MmrKStep)),
+        ("n_tiles_n", C.c_int32), ("outsegs", C.POINTER(MmrOutSeg)),
+        ("gx_count", C.c_int32), ("gy_count", C.c_int32), ("n_img", C.c_int32),
+        ("oy_mul", C.c_int32), ("ox_mul", C.c_int32),
+        ("Hout", C.c_int32), ("Wout", C.c_int32),
+        ("cout_total", C.c_int32),
+        ("scale", C.c_void_p), ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("res_ldc", C.c_int32),
+        ("relu", C.c_int32), ("out_mode", C.c_int32),
+    ]
+
+
+class MmrWgChunk(C.Structure):
+    _fields_ = [("src", C.c_int32), ("c0", C.c_int32), ("ax", C.c_int32 * 4),
+                ("bx", C.c_int32 * 4), ("ay", C.c_int32 * 4), ("by", C.c_int32 * 4)]
+
+
+class MmrWgradDesc(C.Structure):
+    _fields_ = [
+        ("dz", MmrSrc), ("dz_ax", C.c_int32), ("dz_ay", C.c_int32),
+        ("dz_bx", C.c_int32 * 4), ("dz_by", C.c_int32 * 4),
+        ("nsrc", C.c_int32), ("src", MmrSrc * 6),
+        ("ncls", C.c_int32),
+        ("nchunks", C.c_int32), ("chunks", C.POINTER(MmrWgChunk)),
+        ("chunk_ch", C.c_int32), ("cout", C.c_int32),
+        ("kp_w", C.c_int32), ("kp_h", C.c_int32),
+        ("gx_count", C.c_int32), ("gy_count", C.c_int32), ("n_img", C.c_int32),
+        ("n_split", C.c_int32), ("partial", C.c_void_p), ("cout_pad", C.c_int32),
+    ]
+
+
+class MmrContrib(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("pool2", C.c_int32)]
+
+
+class MmrLossParams(C.Structure):
+    _fields_ = [("dice_eps_nr", C.c_float), ("dice_eps_dr", C.c_float), ("onehot_eps", C.c_float),
+                ("w_dice", C.c_float), ("w_ce", C.c_float), ("dice_channels", C.c_int32),
+                ("ce_ignore_index", C.c_int64)]
+
+
+MMR_OUT_BF16_NHWC = 0
+MMR_OUT_F32_NCHW = 1
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/mmrseg.h declares.
+SIGNATURES = {
+    "mmr_last_error": (C.c_char_p, []),
+    "mmr_abi_version": (_i, []),
+    "mmr_device_ok": (_i, []),
+    "mmr_conv_plan_create": (_i, [C.POINTER(MmrConvDesc), C.POINTER(_vp)]),
+    "mmr_conv_plan_run": (_i, [_vp, _i, _vp]),
+    "mmr_conv_plan_destroy": (_i, [_vp]),
+    "mmr_wgrad_plan_create": (_i, [C.POINTER(MmrWgradDesc), C.POINTER(_vp)]),
+    "mmr_wgrad_plan_run": (_i, [_vp, _i, _vp]),
+    "mmr_wgrad_plan_destroy": (_i, [_vp]),
+    "mmr_wgrad_reduce": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "mmr_stem_im2col": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "mmr_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "mmr_unpack_nhwc_bf16_to_nchw_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_repack_weights": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
+    "mmr_bn_stats": (_i, [_vp, _i64, _i, _vp, _i, _vp]),
+    "mmr_bn_finalize": (_i, [_vp, _i, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp, _vp]),
+    "mmr_bn_apply": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    "mmr_bn_bwd_reduce": (_i, [C.POINTER(MmrContrib), _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
+                               _vp, _i, _vp]),
+    "mmr_bn_bwd_finalize": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "mmr_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "mmr_grad_gather": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "mmr_maxpool3x3s2_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mmr_maxpool3x3s2_bwd": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_dice_ce_workspace_doubles": (_i64, [_i, _i, _i]),
+    "mmr_dice_ce_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(MmrLossParams), _vp, _i, _vp,
+                             _vp]),
+    "mmr_dice_ce_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(MmrLossParams), _vp, _f, _vp,
+                             _vp]),
+    "mmr_head_grad_prep": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
+    "mmr_confusion_from_logits": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mmr_confusion_from_preds": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
+    "mmr_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "mmr_sumsq": (_i, [_vp, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libmmrseg.so once.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MmrError(
+                "libmmrseg.so not found at %s: build it with `python __graft_entry__.py` "
+                "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MmrError(lib().mmr_last_error().decode(errors="replace"))
+
+
+def device_ok():
+    return bool(lib().mmr_device_ok())

@@ -1,0 +1,242 @@
+"""Host-side geometry for the tcgen05 implicit-GEMM convolution (csrc/conv_gemm.cu).
+
+Turns "conv k x k / stride s / pad p over the channel-concatenation of sources, some of
+them nearest-x2 upsampled" (smp DecoderBlock.forward: F.interpolate(scale_factor=2,
+mode='nearest') -> torch.cat -> Conv2dReLU; torchvision BasicBlock convs) into the K-step
+tables of include/mmrseg.h.  Nothing is replicated or concatenated in memory: an
+upsampled source is read at (y>>1, x>>1) by splitting the output pixels into their four
+parities, for which the gather is a plain shifted box.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (MMR_OUT_BF16_NHWC, MMR_OUT_F32_NCHW, MmrConvClass, MmrConvDesc, MmrKStep,
+                   MmrOutSeg, MmrSrc)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def choose_box(gx, gy, n):
+    """Pick (box_w, box_h, box_n) with product 128 minimising padded pixels."""
+    best = None
+    for bw in (16, 8, 32, 4, 64, 2, 128, 1):
+        for bh in (8, 16, 4, 32, 2, 64, 1, 128):
+            if 128 % (bw * bh) or bw * bh > 128:
+                continue
+            bn = 128 // (bw * bh)
+            waste = (-(-gx // bw) * bw) * (-(-gy // bh) * bh) * (-(-n // bn) * bn)
+            # prefer wider rows (contiguous NHWC runs) then squarer boxes on ties
+            key = (waste, 0 if bw >= 8 else 1, abs(bw - 2 * bh))
+            if best is None or key < best[0]:
+                best = (key, (bw, bh, bn))
+    return best[1]
+
+
+def pick_bk(channels):
+    """Largest K-step width (64/32/16) dividing every segment's channel count."""
+    for bk in (64, 32, 16):
+        if all(c % bk == 0 for c in channels):
+            return bk
+    raise ValueError("channel counts %r need a common divisor of 16" % (channels,))
+
+
+def pick_bn(sizes, cap=128):
+    for bn in (256, 128, 64, 32, 16):
+        if bn <= cap and all(s % bn == 0 for s in sizes):
+            return bn
+    return 16
+
+
+class ConvPlan:
+    """Owns one mmr_conv_plan (tensor maps + device tables) and the tensors it points at."""
+
+    def __init__(self, desc, keep):
+        self._keep = keep  # python refs that must outlive the plan (tensors, tables)
+        self.desc = desc
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mmr_conv_plan_create(C.byref(desc), C.byref(h)))
+        self.handle = h
+        self.flops = 0
+
+    def run(self, stream=None, impl=0):
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(_lib.lib().mmr_conv_plan_run(self.handle, impl, C.c_void_p(s)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().mmr_conv_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _make_desc(srcs, ksteps_per_cls, cls_meta, weights, bk, bn, out_segs, grid, n_img, o_mul,
+               Hout, Wout, cout_total, scale, bias, residual, relu, out_mode, box=None):
+    d = MmrConvDesc()
+    d.nsrc = len(srcs)
+    for i, (t, es) in enumerate(srcs):
+        N, H, W, Cc = t.shape
+        d.src[i] = MmrSrc(t.data_ptr(), Cc, W, H, N, es)
+    d.weights = weights.data_ptr()
+    d.w_rows, d.w_cols = weights.shape
+    d.bk, d.bn = bk, bn
+    gx, gy = grid
+    bw, bh, bnimg = box if box is not None else choose_box(gx, gy, n_img)
+    d.box_w, d.box_h, d.box_n = bw, bh, bnimg
+    flat = []
+    d.ncls = len(ksteps_per_cls)
+    for ci, ks in enumerate(ksteps_per_cls):
+        oy_add, ox_add = cls_meta[ci]
+        d.cls[ci] = MmrConvClass(len(flat), len(ks), oy_add, ox_add)
+        flat.extend(ks)
+    arr = (MmrKStep * max(1, len(flat)))(*flat)
+    d.nksteps = len(flat)
+    d.ksteps = C.cast(arr, C.POINTER(MmrKStep))
+    segs = (MmrOutSeg * len(out_segs))(*[MmrOutSeg(t.data_ptr(), ldc, coff)
+                                         for (t, ldc, coff) in out_segs])
+    d.n_tiles_n = len(out_segs)
+    d.outsegs = C.cast(segs, C.POINTER(MmrOutSeg))
+    d.gx_count, d.gy_count, d.n_img = gx, gy, n_img
+    d.oy_mul, d.ox_mul = o_mul
+    d.Hout, d.Wout = Hout, Wout
+    d.cout_total = cout_total
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.res_ldc = residual.shape[-1] if residual is not None else 0
+    d.relu = int(bool(relu))
+    d.out_mode = out_mode
+    keep = [arr, segs, [t for t, _ in srcs], weights, [t for t, _, _ in out_segs], scale, bias,
+            residual]
+    return d, keep
+
+
+def build_fprop(sources, weights, ksize, stride, pad, out, *, scale=None, bias=None, residual=None,
+                relu=False, out_mode=MMR_OUT_BF16_NHWC, cout=None, bn=None, box=None):
+    """Forward conv.  sources: list of (tensor [N,Hs,Ws,Cs] bf16, up in {1,2}) in concat order.
+    weights: bf16 [Cout_rows][taps*Cin_total], column = (ky*k+kx)*Cin_total + ci.
+    out: bf16 [N,Ho,Wo,Cout] (or fp32 [N,Cout,Ho,Wo] when out_mode is F32_NCHW)."""
+    N = sources[0][0].shape[0]
+    Hin = sources[0][0].shape[1] * sources[0][1]
+    Win = sources[0][0].shape[2] * sources[0][1]
+    for t, up in sources:
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+        assert (t.shape[1] * up, t.shape[2] * up) == (Hin, Win), "sources disagree on resolution"
+    Ho = (Hin + 2 * pad - ksize) // stride + 1
+    Wo = (Win + 2 * pad - ksize) // stride + 1
+    cin_total = sum(t.shape[3] for t, _ in sources)
+    assert weights.shape[1] == ksize * ksize * cin_total, (weights.shape, ksize, cin_total)
+    if out_mode == MMR_OUT_F32_NCHW:
+        cout = out.shape[1] if cout is None else cout
+        assert tuple(out.shape) == (N, out.shape[1], Ho, Wo)
+        ldc = out.shape[1]
+    else:
+        cout = out.shape[3] if cout is None else cout
+        assert tuple(out.shape[:3]) == (N, Ho, Wo)
+        ldc = out.shape[3]
+    bk = pick_bk([t.shape[3] for t, _ in sources])
+    if bn is None:
+        bn = min(128, -(-cout // 16) * 16)
+    n_tiles = -(-cout // bn)
+    out_segs = [(out, ldc, i * bn) for i in range(n_tiles)]
+    any_up = any(up == 2 for _, up in sources)
+    assert stride in (1, 2)
+    assert not (any_up and stride != 1), "upsampled sources only with stride 1"
+
+    def ksteps_for(py, px):
+        ks = []
+        seg_off = 0
+        for si, (t, up) in enumerate(sources):
+            Cs = t.shape[3]
+            for c0 in range(0, Cs, bk):
+                for ky in range(ksize):
+                    for kx in range(ksize):
+                        wk = (ky * ksize + kx) * cin_total + seg_off + c0
+                        if any_up:
+                            if up == 2:
+                                ax = ay = 1
+                                by = (py + ky - pad) >> 1
+                                bx = (px + kx - pad) >> 1
+                            else:
+                                ax = ay = 2
+                                by = py + ky - pad
+                                bx = px + kx - pad
+                        else:
+                            ax = ay = stride
+                            by = ky - pad
+                            bx = kx - pad
+                        ks.append(MmrKStep(si, c0, ax, bx, ay, by, wk, 0))
+            seg_off += Cs
+        return ks
+
+    if any_up:
+        assert Ho % 2 == 0 and Wo % 2 == 0
+        classes = [(py, px) for py in (0, 1) for px in (0, 1)]
+        ksteps = [ksteps_for(py, px) for py, px in classes]
+        srcs = [(t, 1 if up == 2 else 2) for t, up in sources]
+        grid, o_mul = (Wo // 2, Ho // 2), (2, 2)
+    else:
+        classes = [(0, 0)]
+        ksteps = [ksteps_for(0, 0)]
+        srcs = [(t, stride) for t, _ in sources]
+        grid, o_mul = (Wo, Ho), (1, 1)
+    d, keep = _make_desc(srcs, ksteps, classes, weights, bk, bn, out_segs, grid, N, o_mul, Ho, Wo,
+                         cout, scale, bias, residual, relu, out_mode, box)
+    plan = ConvPlan(d, keep)
+    plan.flops = 2 * N * Ho * Wo * cout * ksize * ksize * cin_total
+    return plan
+
+
+def build_dgrad(dz, weights_d, ksize, stride, pad, in_hw, grads, *, bn=None, box=None):
+    """Data gradient.  dz: [N,Ho,Wo,Cout] bf16.  weights_d: bf16 [Cin_total][taps*Cout],
+    column = (ky*k+kx)*Cout + co.  in_hw: (Hin, Win) of the (virtually concatenated) conv
+    input.  grads: list of (tensor [N,Hin,Win,Cs] bf16) in concat order — one per source;
+    for an upsampled source the tensor is still at (Hin, Win) and its consumer 2x2-pools it."""
+    N, Ho, Wo, Cout = dz.shape
+    Hin, Win = in_hw
+    assert dz.dtype == torch.bfloat16 and dz.is_contiguous()
+    cin_total = sum(g.shape[3] for g in grads)
+    assert tuple(weights_d.shape) == (cin_total, ksize * ksize * Cout), (weights_d.shape,)
+    bk = pick_bk([Cout])
+    sizes = [g.shape[3] for g in grads]
+    if bn is None:
+        bn = pick_bn(sizes)
+    out_segs = []
+    for g in grads:
+        assert tuple(g.shape[:3]) == (N, Hin, Win)
+        for c in range(0, g.shape[3], bn):
+            out_segs.append((g, g.shape[3], c))
+
+    def ksteps_for(py, px):
+        ks = []
+        for c0 in range(0, Cout, bk):
+            for ky in range(ksize):
+                for kx in range(ksize):
+                    wk = (ky * ksize + kx) * Cout + c0
+                    if stride == 1:
+                        ks.append(MmrKStep(0, c0, 1, pad - kx, 1, pad - ky, wk, 0))
+                    else:
+                        ty, tx = py + pad - ky, px + pad - kx
+                        if ty % 2 or tx % 2:
+                            continue
+                        ks.append(MmrKStep(0, c0, 1, tx // 2, 1, ty // 2, wk, 0))
+        return ks
+
+    if stride == 1:
+        classes, ksteps = [(0, 0)], [ksteps_for(0, 0)]
+        grid, o_mul = (Win, Hin), (1, 1)
+    else:
+        assert stride == 2 and Hin % 2 == 0 and Win % 2 == 0
+        classes = [(py, px) for py in (0, 1) for px in (0, 1)]
+        ksteps = [ksteps_for(py, px) for py, px in classes]
+        grid, o_mul = (Win // 2, Hin // 2), (2, 2)
+    d, keep = _make_desc([(dz, 1)], ksteps, classes, weights_d, bk, bn, out_segs, grid, N, o_mul,
+                         Hin, Win, cin_total, None, None, None, False, MMR_OUT_BF16_NHWC, box)
+    plan = ConvPlan(d, keep)
+    plan.flops = 2 * N * Ho * Wo * Cout * ksize * ksize * cin_total
+    return plan

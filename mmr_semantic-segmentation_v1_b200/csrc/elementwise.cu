@@ -1,0 +1,655 @@
+// HBM-bound kernels of the path: layout packing, BatchNorm (+residual +ReLU) forward and
+// backward, gradient gathering across the dense skip fan-out (with the 2x2 sum-pool that is
+// the backward of nearest-x2 upsampling), and the ResNet stem max-pool.
+// All activations are NHWC bf16; every thread moves 16 bytes (8 channels) per access.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmr {
+
+constexpr int kEwThreads = 256;
+constexpr int kMaxContrib = 8;
+
+struct ContribList {
+  const __nv_bfloat16* ptr[kMaxContrib];
+  int pool2[kMaxContrib];
+  int n;
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// Sum of all contributions at pixel (n,y,x), channels [c, c+8).
+__device__ __forceinline__ void gather8(const ContribList& cl, int n, int y, int x, int c, int H,
+                                        int W, int C, float (&g)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  for (int i = 0; i < cl.n; ++i) {
+    float v[8];
+    if (!cl.pool2[i]) {
+      load8(cl.ptr[i] + (((size_t)n * H + y) * W + x) * C + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += v[j];
+    } else {
+      const int H2 = 2 * H, W2 = 2 * W;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          load8(cl.ptr[i] + (((size_t)n * H2 + 2 * y + dy) * W2 + 2 * x + dx) * C + c, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += v[j];
+        }
+    }
+  }
+}
+
+static int fill_contribs(ContribList& cl, const MmrContrib* contribs, int n) {
+  MMR_REQUIRE(n >= 0 && n <= kMaxContrib, "at most %d gradient contributions, got %d", kMaxContrib, n);
+  cl.n = n;
+  for (int i = 0; i < kMaxContrib; ++i) {
+    cl.ptr[i] = i < n ? reinterpret_cast<const __nv_bfloat16*>(contribs[i].ptr) : nullptr;
+    cl.pool2[i] = i < n ? contribs[i].pool2 : 0;
+  }
+  return 0;
+}
+
+static int ew_blocks(int64_t work_items, int cap_mult = 8) {
+  int64_t b = (work_items + kEwThreads - 1) / kEwThreads;
+  const int64_t cap = (int64_t)num_sms() * cap_mult;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------ packing
+__global__ void stem_im2col_kernel(const float* __restrict__ x, int N, int H, int W, int Ho, int Wo,
+                                   __nv_bfloat16* __restrict__ out, int kpad,
+                                   const float* __restrict__ mean, const float* __restrict__ std_) {
+  const int groups = kpad / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((int64_t)Wo * Ho));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int c = k / 49, r = k % 49, ky = r / 7, kx = r % 7;
+        const int iy = 2 * oy + ky - 3, ix = 2 * ox + kx - 3;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          val = __ldg(x + (((size_t)n * 3 + c) * H + iy) * W + ix);
+          if (mean) val = (val - __ldg(mean + c)) / __ldg(std_ + c);
+        }
+      }
+      v[j] = val;
+    }
+    store8(out + pix * kpad + g * 8, v);
+  }
+}
+
+__global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C, int H, int W,
+                                 __nv_bfloat16* __restrict__ out, int cpad) {
+  const int groups = cpad / 8;
+  const int64_t hw = (int64_t)H * W;
+  const int64_t total = (int64_t)N * hw * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // pixel index fastest so that the strided NCHW reads coalesce across the warp
+    const int64_t p = i % hw;
+    const int g = (int)((i / hw) % groups);
+    const int n = (int)(i / (hw * groups));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      v[j] = c < C ? __ldg(x + ((size_t)n * C + c) * hw + p) : 0.f;
+    }
+    store8(out + ((size_t)n * hw + p) * cpad + g * 8, v);
+  }
+}
+
+__global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int N, int C, int ldc, int H,
+                                   int W, float* __restrict__ out) {
+  const int64_t hw = (int64_t)H * W;
+  const int64_t total = (int64_t)N * C * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i % hw;
+    const int c = (int)((i / hw) % C);
+    const int n = (int)(i / (hw * C));
+    out[i] = __bfloat162float(x[((size_t)n * hw + p) * ldc + c]);
+  }
+}
+
+__global__ void repack_weights_kernel(const float* __restrict__ w, int O, int I, int taps,
+                                      __nv_bfloat16* __restrict__ fwd, int ldf,
+                                      __nv_bfloat16* __restrict__ dgrad, int ldd) {
+  const int64_t total = (int64_t)O * I * taps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const int ci = (int)((i / taps) % I);
+    const int o = (int)(i / ((int64_t)taps * I));
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    if (fwd) fwd[(size_t)o * ldf + (size_t)t * I + ci] = v;
+    if (dgrad) dgrad[(size_t)ci * ldd + (size_t)t * O + o] = v;
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm forward
+// Thread layout for [P][C] reductions: tpc = C/8 threads span one pixel row, the block's
+// 256/tpc thread-rows stride over pixels.  Per-thread fp32 partial sums are flushed to double
+// every 16 rows; block partials are written (not atomically added) so results are
+// deterministic.
+template <int MODE>  // 0: stats of z ; 1: bn backward reduce ; 2: plain gradient gather
+__global__ void __launch_bounds__(kEwThreads)
+reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, int C, double* __restrict__ partial,
+                   ContribList cl, const __nv_bfloat16* __restrict__ act,
+                   const float* __restrict__ mean, const float* __restrict__ invstd, int H, int W,
+                   __nv_bfloat16* __restrict__ gout) {
+  const int tpc = C / 8;
+  const int rows_per_iter = kEwThreads / tpc;
+  const int cg = threadIdx.x % tpc;
+  const int rl = threadIdx.x / tpc;
+  const int c = cg * 8;
+  double d1[8], d2[8];
+  float f1[8], f2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d1[j] = d2[j] = 0.0, f1[j] = f2[j] = 0.f;
+  float mu[8], is[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mu[j] = __ldg(mean + c + j), is[j] = __ldg(invstd + c + j);
+  }
+  int since_flush = 0;
+  for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rl; r < P;
+       r += (int64_t)gridDim.x * rows_per_iter) {
+    if (MODE == 0) {
+      float v[8];
+      load8(z + r * C + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f1[j] += v[j], f2[j] += v[j] * v[j];
+    } else {
+      const int x = (int)(r % W);
+      const int y = (int)((r / W) % H);
+      const int n = (int)(r / ((int64_t)W * H));
+      float g[8];
+      gather8(cl, n, y, x, c, H, W, C, g);
+      if (act) {
+        float a[8];
+        load8(act + r * C + c, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+      }
+      store8(gout + r * C + c, g);
+      if (MODE == 1) {
+        float zz[8];
+        load8(z + r * C + c, zz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f1[j] += g[j], f2[j] += g[j] * ((zz[j] - mu[j]) * is[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f1[j] += g[j];
+      }
+    }
+    if (++since_flush == 16) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d1[j] += f1[j], d2[j] += f2[j], f1[j] = f2[j] = 0.f;
+      since_flush = 0;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d1[j] += f1[j], d2[j] += f2[j];
+  if (partial == nullptr) return;
+  __shared__ double sh[kEwThreads * 2];  // reused per channel j
+  for (int j = 0; j < 8; ++j) {
+    sh[threadIdx.x] = d1[j];
+    sh[kEwThreads + threadIdx.x] = d2[j];
+    __syncthreads();
+    if (rl == 0) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int k = 0; k < rows_per_iter; ++k) {
+        s1 += sh[k * tpc + cg];
+        s2 += sh[kEwThreads + k * tpc + cg];
+      }
+      partial[((size_t)blockIdx.x * 2 + 0) * C + c + j] = s1;
+      partial[((size_t)blockIdx.x * 2 + 1) * C + c + j] = s2;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* running_mean,
+                                   float* running_var, int64_t* nbt, float* mean, float* invstd,
+                                   float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) nbt[0] += 1;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s1 += partial[((size_t)b * 2 + 0) * C + c];
+    s2 += partial[((size_t)b * 2 + 1) * C + c];
+  }
+  const double m = s1 / (double)P;
+  double var = s2 / (double)P - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean[c] = (float)m;
+  invstd[c] = is;
+  scale[c] = g * is;
+  shift[c] = b - (float)m * g * is;
+  if (running_mean) {
+    const double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, int C,
+                                const float* __restrict__ scale, const float* __restrict__ shift,
+                                const __nv_bfloat16* __restrict__ residual, int relu,
+                                __nv_bfloat16* __restrict__ out) {
+  const int groups = C / 8;
+  const int64_t total = P * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    float v[8];
+    load8(z + i * 8, v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c));
+    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
+    if (residual) {
+      float r[8];
+      load8(residual + i * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    store8(out + i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm backward
+// With g = dL/d(bn output) already masked by ReLU, xhat = (z-mean)*invstd, M = N*H*W:
+//   dgamma = sum g*xhat,  dbeta = sum g,
+//   dz = gamma*invstd * (g - dbeta/M - xhat*dgamma/M) = coefA*g + coefB*xhat + coefC.
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P,
+                                       int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ invstd, float* dgamma,
+                                       float* dbeta, int accumulate, float* coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s1 += partial[((size_t)b * 2 + 0) * C + c];
+    s2 += partial[((size_t)b * 2 + 1) * C + c];
+  }
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
+  const double gi = (double)(gamma ? gamma[c] : 1.f) * (double)invstd[c];
+  coef[c] = (float)gi;
+  coef[C + c] = (float)(-gi * s2 / (double)P);
+  coef[2 * C + c] = (float)(-gi * s1 / (double)P);
+}
+
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g,
+                                    const __nv_bfloat16* __restrict__ z,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ coef, int64_t P, int C,
+                                    __nv_bfloat16* __restrict__ dz) {
+  const int groups = C / 8;
+  const int64_t total = P * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    float gv[8], zv[8], o[8];
+    load8(g + i * 8, gv);
+    load8(z + i * 8, zv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (zv[j] - __ldg(mean + c + j)) * __ldg(invstd + c + j);
+      o[j] = __ldg(coef + c + j) * gv[j] + __ldg(coef + C + c + j) * xh + __ldg(coef + 2 * C + c + j);
+    }
+    store8(dz + i * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------ max-pool 3x3 s2 p1
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int groups = C / 8;
+  const int64_t total = (int64_t)N * Ho * Wo * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    const int64_t pix = i / groups;
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((int64_t)Wo * Ho));
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY, bi[j] = 0;
+    bool first = true;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        load8(x + (((size_t)n * H + iy) * W + ix) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // torch: first maximum in window scan order wins; NaN propagates
+          if (first || v[j] > best[j] || v[j] != v[j]) best[j] = v[j], bi[j] = ky * 3 + kx;
+        }
+        first = false;
+      }
+    }
+    store8(out + pix * C + c, best);
+    uint2 packed;
+    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + pix * C + c) = packed;
+  }
+}
+
+// gin[n,y,x,c] = sum over the (<=4) windows containing (y,x) whose recorded argmax is (y,x).
+__global__ void maxpool_bwd_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N, int H,
+                                   int W, int C, __nv_bfloat16* __restrict__ gin) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int groups = C / 8;
+  const int64_t total = (int64_t)N * H * W * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    const int64_t pix = i / groups;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Wo) continue;
+        const size_t opix = ((size_t)n * Ho + oy) * Wo + ox;
+        const uint2 packed = *reinterpret_cast<const uint2*>(idx + opix * C + c);
+        float g[8];
+        gather8(cl, n, oy, ox, c, Ho, Wo, C, g);
+        const int want = ky * 3 + kx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t word = j < 4 ? packed.x : packed.y;
+          const int id = (int)((word >> (8 * (j & 3))) & 0xFF);
+          if (id == want) acc[j] += g[j];
+        }
+      }
+    }
+    store8(gin + pix * C + c, acc);
+  }
+}
+
+// ------------------------------------------------------------------ head gradient prep
+// dlogits fp32 NCHW -> bf16 NHWC (cpad channels, zero padded); per-class sums -> dbias.
+__global__ void head_grad_prep_kernel(const float* __restrict__ dl, int N, int C, int H, int W,
+                                      __nv_bfloat16* __restrict__ out, int cpad,
+                                      double* __restrict__ partial) {
+  const int64_t hw = (int64_t)H * W;
+  const int64_t total = (int64_t)N * hw;
+  double acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i % hw;
+    const int n = (int)(i / hw);
+    for (int g = 0; g < cpad / 8; ++g) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        v[j] = c < C ? __ldg(dl + ((size_t)n * C + c) * hw + p) : 0.f;
+        if (g < 2) acc[(g * 8 + j) & 15] += v[j];
+      }
+      store8(out + (size_t)i * cpad + g * 8, v);
+    }
+  }
+  if (partial == nullptr) return;
+  __shared__ double sh[kEwThreads];
+  for (int j = 0; j < 16 && j < C; ++j) {
+    sh[threadIdx.x] = acc[j];
+    __syncthreads();
+    for (int s = kEwThreads / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * 16 + j] = sh[0];
+    __syncthreads();
+  }
+}
+
+__global__ void head_bias_finalize_kernel(const double* __restrict__ partial, int nblk, int C,
+                                          float* dbias, int accumulate) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * 16 + c];
+  dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)s;
+}
+
+static double* g_head_ws = nullptr;  // small persistent workspace for head_grad_prep partials
+static const int kHeadBlocks = 592;
+
+}  // namespace mmr
+
+using namespace mmr;
+
+extern "C" int mmr_stem_im2col(const float* x, int N, int H, int W, void* out, int kpad,
+                               const float* mean, const float* std_, mmr_stream_t stream) {
+  MMR_REQUIRE(kpad % 8 == 0 && kpad >= 152, "kpad must be a multiple of 8 and >= 152, got %d", kpad);
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (kpad / 8);
+  stem_im2col_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
+      x, N, H, W, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out), kpad, mean, std_);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_pack_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, void* out,
+                                              int cpad, mmr_stream_t stream) {
+  MMR_REQUIRE(cpad % 8 == 0 && cpad >= C, "cpad must be a multiple of 8 and >= C");
+  const int64_t total = (int64_t)N * H * W * (cpad / 8);
+  pack_nchw_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
+      x, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), cpad);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_unpack_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int ldc, int H, int W,
+                                                float* out, mmr_stream_t stream) {
+  const int64_t total = (int64_t)N * C * H * W;
+  unpack_nhwc_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), N, C, ldc, H, W, out);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_repack_weights(const float* w, int O, int I, int taps, void* fwd, int ldf,
+                                  void* dgrad, int ldd, mmr_stream_t stream) {
+  MMR_REQUIRE(!fwd || ldf >= taps * I, "forward row stride too small");
+  MMR_REQUIRE(!dgrad || ldd >= taps * O, "dgrad row stride too small");
+  const int64_t total = (int64_t)O * I * taps;
+  repack_weights_kernel<<<ew_blocks(total, 4), kEwThreads, 0, as_stream(stream)>>>(
+      w, O, I, taps, reinterpret_cast<__nv_bfloat16*>(fwd), ldf,
+      reinterpret_cast<__nv_bfloat16*>(dgrad), ldd);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static int check_rows_layout(int C) {
+  MMR_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048 && (kEwThreads % (C / 8)) == 0,
+              "channel count %d unsupported by the row-reduction layout (need C/8 | 256)", C);
+  return 0;
+}
+
+extern "C" int mmr_bn_stats(const void* z, int64_t P, int C, double* partial, int nblk,
+                            mmr_stream_t stream) {
+  if (check_rows_layout(C)) return -1;
+  ContribList cl;
+  fill_contribs(cl, nullptr, 0);
+  reduce_rows_kernel<0><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(z), P, C, partial, cl, nullptr, nullptr, nullptr, 1, 1,
+      nullptr);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_bn_finalize(const double* partial, int nblk, int64_t P, int C, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean,
+                               float* running_var, int64_t* nbt, float* mean, float* invstd,
+                               float* scale, float* shift, mmr_stream_t stream) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
+      partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd,
+      scale, shift);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_bn_apply(const void* z, int64_t P, int C, const float* scale, const float* shift,
+                            const void* residual, int relu, void* out, mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  bn_apply_kernel<<<ew_blocks(P * (C / 8), 16), kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
+      reinterpret_cast<const __nv_bfloat16*>(residual), relu, reinterpret_cast<__nv_bfloat16*>(out));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_bn_bwd_reduce(const MmrContrib* contribs, int ncontrib, const void* act,
+                                 const void* z, const float* mean, const float* invstd, int N, int H,
+                                 int W, int C, void* g, double* partial, int nblk,
+                                 mmr_stream_t stream) {
+  if (check_rows_layout(C)) return -1;
+  ContribList cl;
+  if (fill_contribs(cl, contribs, ncontrib)) return -1;
+  reduce_rows_kernel<1><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(z), (int64_t)N * H * W, C, partial, cl,
+      reinterpret_cast<const __nv_bfloat16*>(act), mean, invstd, H, W,
+      reinterpret_cast<__nv_bfloat16*>(g));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, int C,
+                                   const float* gamma, const float* invstd, float* dgamma,
+                                   float* dbeta, int accumulate, float* coef, mmr_stream_t stream) {
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
+      partial, nblk, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_bn_bwd_apply(const void* g, const void* z, const float* mean, const float* invstd,
+                                const float* coef, int64_t P, int C, void* dz, mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  bn_bwd_apply_kernel<<<ew_blocks(P * (C / 8), 16), kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean,
+      invstd, coef, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_grad_gather(const MmrContrib* contribs, int ncontrib, const void* act, int N,
+                               int H, int W, int C, void* g, double* partial, int nblk,
+                               mmr_stream_t stream) {
+  if (check_rows_layout(C)) return -1;
+  ContribList cl;
+  if (fill_contribs(cl, contribs, ncontrib)) return -1;
+  reduce_rows_kernel<2><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
+      nullptr, (int64_t)N * H * W, C, partial, cl, reinterpret_cast<const __nv_bfloat16*>(act),
+      nullptr, nullptr, H, W, reinterpret_cast<__nv_bfloat16*>(g));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out,
+                                    uint8_t* idx, mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out),
+      idx);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_maxpool3x3s2_bwd(const MmrContrib* contribs, int ncontrib, const uint8_t* idx,
+                                    int N, int H, int W, int C, void* gin, mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  ContribList cl;
+  if (fill_contribs(cl, contribs, ncontrib)) return -1;
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
+      cl, idx, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int W, void* out,
+                                  int cpad, float* dbias, int accumulate, mmr_stream_t stream) {
+  MMR_REQUIRE(cpad % 8 == 0 && cpad >= C && C <= 16, "head_grad_prep: need C <= 16 <= cpad (mult of 8)");
+  if (dbias && g_head_ws == nullptr) {
+    MMR_CUDA_CHECK(cudaMalloc(&g_head_ws, sizeof(double) * 16 * kHeadBlocks));
+  }
+  head_grad_prep_kernel<<<kHeadBlocks, kEwThreads, 0, as_stream(stream)>>>(
+      dlogits, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), cpad, dbias ? g_head_ws : nullptr);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  if (dbias) {
+    head_bias_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(g_head_ws, kHeadBlocks, C, dbias,
+                                                               accumulate);
+    MMR_CUDA_CHECK(cudaGetLastError());
+  }
+  return 0;
+}

@@ -1,0 +1,148 @@
+// Optimiser-side kernels: Adam / AdamW over the flat fp32 parameter buffer, gradient
+// norm, and the split-K reduction that turns wgrad partials into OIHW fp32 gradients.
+// All HBM-bound (Adam: 28 B/param).
+#include "common.h"
+
+namespace mmr {
+
+constexpr int kOptThreads = 256;
+
+// torch.optim.Adam (SU/ModelTraining.py:366: lr, weight_decay -> L2 added to the gradient)
+// and AdamW (ED/Main_MMR_SegModel.py:878-880: decoupled decay), single-tensor formulas:
+//   g = g*grad_scale (+ wd*p for Adam);  p *= (1 - lr*wd) for AdamW
+//   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g
+//   p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(kOptThreads)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+            float bc1, float bc2, int mode, float grad_scale) {
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = reinterpret_cast<float*>(&pp);
+    const float* ga = reinterpret_cast<const float*>(&gg);
+    float* ma = reinterpret_cast<float*>(&mm);
+    float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gr = ga[j] * grad_scale;
+      if (mode == 0)
+        gr += wd * pa[j];
+      else
+        pa[j] *= (1.f - lr * wd);
+      ma[j] = b1 * ma[j] + (1.f - b1) * gr;
+      va[j] = b2 * va[j] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(va[j]) * inv_sqrt_bc2 + eps;
+      pa[j] -= step_size * (ma[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gr = g[i] * grad_scale;
+    float pv = p[i];
+    if (mode == 0)
+      gr += wd * pv;
+    else
+      pv *= (1.f - lr * wd);
+    const float mv = b1 * m[i] + (1.f - b1) * gr;
+    const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mv;
+    v[i] = vv;
+    p[i] = pv - step_size * (mv / (sqrtf(vv) * inv_sqrt_bc2 + eps));
+  }
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __ldg(g + i);
+    acc += (double)x * (double)x;
+  }
+  __shared__ double sh[kOptThreads];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = kOptThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, sh[0]);
+}
+
+// partial: [n_split][cout_pad][ncols_pad], column = tap*cin_pad + ci, cin_pad = ncols_pad/taps.
+// dst: OIHW fp32, index (co*cin + ci)*taps + tap.
+__global__ void __launch_bounds__(kOptThreads)
+wgrad_reduce_kernel(const float* __restrict__ partial, int n_split, int cout, int cout_pad, int cin,
+                    int taps, int ncols_pad, float* __restrict__ dst, int accumulate) {
+  const int cin_pad = ncols_pad / taps;
+  const int64_t total = (int64_t)cout * cin * taps;
+  const size_t split_stride = (size_t)cout_pad * ncols_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // iterate in partial-column order so the reads coalesce
+    const int ci = (int)(i % cin);
+    const int tap = (int)((i / cin) % taps);
+    const int co = (int)(i / ((int64_t)cin * taps));
+    const size_t src = (size_t)co * ncols_pad + (size_t)tap * cin_pad + ci;
+    float s = 0.f;
+    for (int k = 0; k < n_split; ++k) s += __ldg(partial + k * split_stride + src);
+    const size_t d = ((size_t)co * cin + ci) * taps + tap;
+    dst[d] = accumulate ? dst[d] + s : s;
+  }
+}
+
+}  // namespace mmr
+
+using namespace mmr;
+
+extern "C" int mmr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                             float b1, float b2, float eps, float wd, float bc1, float bc2, int mode,
+                             float grad_scale, mmr_stream_t stream) {
+  MMR_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+               reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
+              "adam buffers must be 16-byte aligned");
+  int64_t blocks = (n / 4 + kOptThreads - 1) / kOptThreads;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<(int)blocks, kOptThreads, 0, as_stream(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, wd,
+                                                                  bc1, bc2, mode, grad_scale);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_sumsq(const float* g, int64_t n, double* out, mmr_stream_t stream) {
+  int64_t blocks = (n + kOptThreads * 4 - 1) / (kOptThreads * 4);
+  const int64_t cap = (int64_t)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<(int)blocks, kOptThreads, 0, as_stream(stream)>>>(g, n, out);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_wgrad_reduce(const float* partial, int n_split, int cout, int cout_pad, int cin,
+                                int taps, int ncols_pad, float* dst_oihw, int accumulate,
+                                mmr_stream_t stream) {
+  MMR_REQUIRE(ncols_pad % taps == 0 && ncols_pad / taps >= cin, "wgrad_reduce: bad column layout");
+  const int64_t total = (int64_t)cout * cin * taps;
+  int64_t blocks = (total + kOptThreads - 1) / kOptThreads;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  wgrad_reduce_kernel<<<(int)blocks, kOptThreads, 0, as_stream(stream)>>>(
+      partial, n_split, cout, cout_pad, cin, taps, ncols_pad, dst_oihw, accumulate);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
