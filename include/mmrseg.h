@@ -99,45 +99,52 @@ int mmr_conv_plan_run(void* plan, int impl, mmr_stream_t stream);
 int mmr_conv_plan_destroy(void* plan);
 
 /* ------------------------------------------------------------------------------------
- * Weight gradient on tcgen05: dW[co][chunk cols] = sum over pixels dz[p][co] * x[p'][ci],
- * both operands pixel-major (MN-major UMMA).  Replaces the weight-gradient half of
- * `loss.backward()` for every nn.Conv2d on the path.
- * A "chunk" is (source, channel offset, tap); per pixel class it carries the spatial shift
- * of its activation box.  Output: fp32 partial sums [n_split][m_rows][n_chunks*chunk_ch].
+ * Weight gradient on tcgen05.  Replaces the weight-gradient half of `loss.backward()`
+ * (SU/ModelTraining.py:614, ED/Main_MMR_SegModel.py:715) for every nn.Conv2d on the path.
+ *
+ *   dWt[(chunk, ch)][co] = sum over pixels  x[chunk.src][pixel + shift(chunk)][chunk.c0 + ch] * dz[pixel][co]
+ *
+ * Both operands are pixel-major in memory (NHWC), i.e. MN-major UMMA operands: a K-step is a
+ * box of kp_w*kp_h*kp_n = 32 pixels; the M side stacks 128/chunk_ch activation chunks (a
+ * chunk = source, channel offset, filter tap), the N side is the conv's output channels.  A
+ * CTA keeps up to 512/cout accumulator tiles in TMEM so one dz box is reused by all of them.
+ * The pixel range is split n_split ways (split-K); fp32 partials are then summed in a fixed
+ * order (deterministic) and scattered into the OIHW fp32 gradient.
+ * Up to 4 pixel classes (output parities) carry per-class box shifts, as in the forward plan.
  * ------------------------------------------------------------------------------------ */
 typedef struct {
-  int32_t src, c0;
-  int32_t ax[4], bx[4], ay[4], by[4]; /* per pixel class */
+  int32_t src, c0;      /* source tensor, first channel of the chunk */
+  int32_t a;            /* box origin = a*g0 + b[cls] along x and y */
+  int32_t bx[4], by[4]; /* per pixel class */
+  int32_t dst_ci;       /* input-channel index of channel 0 of the chunk in the OIHW gradient */
+  int32_t dst_tap;      /* filter tap (ky*kw + kx); -1 marks a padding chunk (discarded) */
 } MmrWgChunk;
 
 typedef struct {
-  MmrSrc dz; /* gradient wrt the conv output, bf16 NHWC; es = traversal stride of a class grid */
-  int32_t dz_ax, dz_ay;     /* dz box origin = dz_ax*gx0 + dz_bx[cls] */
+  MmrSrc dz; /* gradient wrt the conv output, bf16 NHWC (C = padded channel count) */
+  int32_t dz_a;
   int32_t dz_bx[4], dz_by[4];
   int32_t nsrc;
   MmrSrc src[6];
   int32_t ncls;
-  int32_t nchunks;
+  int32_t nchunks;          /* multiple of 128/chunk_ch */
   const MmrWgChunk* chunks; /* host array */
   int32_t chunk_ch;         /* channels per chunk: 64, 32 or 16 */
-  int32_t cout;             /* valid rows (<= 128 per M-tile) */
-  int32_t kp_w, kp_h;       /* pixel box of one K-step: kp_w*kp_h == 32 */
+  int32_t cout_gemm;        /* N of the GEMM: dz channels used, multiple of 16 */
+  int32_t kp_w, kp_h, kp_n; /* pixel box of one K-step, product 32 */
   int32_t gx_count, gy_count, n_img;
-  int32_t n_split;          /* split-K factor over the pixel tiles */
-  float* partial;           /* fp32 [n_split][cout_pad][nchunks*chunk_ch] */
-  int32_t cout_pad;
+  int32_t n_split;
+  float* partial; /* fp32 [n_split][nchunks*chunk_ch][cout_gemm] */
+  float* dst;     /* OIHW fp32 gradient [dst_cout][dst_cin][dst_taps] */
+  int32_t dst_cout, dst_cin, dst_taps;
+  int32_t chunk_valid_ch; /* leading channels of each chunk that exist in dst (<= chunk_ch) */
 } MmrWgradDesc;
 
 int mmr_wgrad_plan_create(const MmrWgradDesc* desc, void** plan);
-int mmr_wgrad_plan_run(void* plan, int impl, mmr_stream_t stream);
-int mmr_wgrad_plan_destroy(void* plan);
-
-/* Sum the split-K partials and scatter into the OIHW fp32 gradient of the parameter
- * (`param.grad` in the reference's optimizer, SU/ModelTraining.py:366,617).
- * partial column index = (tap*cin + ci) ; dst index = ((co*cin + ci)*taps + tap).
+/* impl: 0 = tcgen05 kernel, 1 = scalar CUDA-core kernel on the same tables (test aid).
  * accumulate != 0 adds into dst (gradient accumulation, ED/Main_MMR_SegModel.py:718). */
-int mmr_wgrad_reduce(const float* partial, int n_split, int cout, int cout_pad, int cin, int taps,
-                     int ncols_pad, float* dst_oihw, int accumulate, mmr_stream_t stream);
+int mmr_wgrad_plan_run(void* plan, int impl, int accumulate, mmr_stream_t stream);
+int mmr_wgrad_plan_destroy(void* plan);
 
 /* ------------------------------------------------------------------------------------
  * Layout / packing kernels at the boundary of the path.

@@ -53,21 +53,22 @@ class MmrConvDesc(C.Structure):
 
 
 class MmrWgChunk(C.Structure):
-    _fields_ = [("src", C.c_int32), ("c0", C.c_int32), ("ax", C.c_int32 * 4),
-                ("bx", C.c_int32 * 4), ("ay", C.c_int32 * 4), ("by", C.c_int32 * 4)]
+    _fields_ = [("src", C.c_int32), ("c0", C.c_int32), ("a", C.c_int32), ("bx", C.c_int32 * 4),
+                ("by", C.c_int32 * 4), ("dst_ci", C.c_int32), ("dst_tap", C.c_int32)]
 
 
 class MmrWgradDesc(C.Structure):
     _fields_ = [
-        ("dz", MmrSrc), ("dz_ax", C.c_int32), ("dz_ay", C.c_int32),
-        ("dz_bx", C.c_int32 * 4), ("dz_by", C.c_int32 * 4),
+        ("dz", MmrSrc), ("dz_a", C.c_int32), ("dz_bx", C.c_int32 * 4), ("dz_by", C.c_int32 * 4),
         ("nsrc", C.c_int32), ("src", MmrSrc * 6),
         ("ncls", C.c_int32),
         ("nchunks", C.c_int32), ("chunks", C.POINTER(MmrWgChunk)),
-        ("chunk_ch", C.c_int32), ("cout", C.c_int32),
-        ("kp_w", C.c_int32), ("kp_h", C.c_int32),
+        ("chunk_ch", C.c_int32), ("cout_gemm", C.c_int32),
+        ("kp_w", C.c_int32), ("kp_h", C.c_int32), ("kp_n", C.c_int32),
         ("gx_count", C.c_int32), ("gy_count", C.c_int32), ("n_img", C.c_int32),
-        ("n_split", C.c_int32), ("partial", C.c_void_p), ("cout_pad", C.c_int32),
+        ("n_split", C.c_int32), ("partial", C.c_void_p), ("dst", C.c_void_p),
+        ("dst_cout", C.c_int32), ("dst_cin", C.c_int32), ("dst_taps", C.c_int32),
+        ("chunk_valid_ch", C.c_int32),
     ]
 
 
@@ -95,9 +96,8 @@ SIGNATURES = {
     "mmr_conv_plan_run": (_i, [_vp, _i, _vp]),
     "mmr_conv_plan_destroy": (_i, [_vp]),
     "mmr_wgrad_plan_create": (_i, [C.POINTER(MmrWgradDesc), C.POINTER(_vp)]),
-    "mmr_wgrad_plan_run": (_i, [_vp, _i, _vp]),
+    "mmr_wgrad_plan_run": (_i, [_vp, _i, _i, _vp]),
     "mmr_wgrad_plan_destroy": (_i, [_vp]),
-    "mmr_wgrad_reduce": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "mmr_stem_im2col": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "mmr_unpack_nhwc_bf16_to_nchw_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -240,3 +240,141 @@ def build_dgrad(dz, weights_d, ksize, stride, pad, in_hw, grads, *, bn=None, box
     plan = ConvPlan(d, keep)
     plan.flops = 2 * N * Ho * Wo * Cout * ksize * ksize * cin_total
     return plan
+
+
+def choose_pixbox(gx, gy, n, total=32):
+    """(w, h, n) box with product `total` minimising padded pixels (wgrad K-step)."""
+    best = None
+    for bw in (8, 16, 4, 32, 2, 1):
+        for bh in (4, 8, 2, 16, 1, 32):
+            if bw * bh > total or total % (bw * bh):
+                continue
+            bn = total // (bw * bh)
+            waste = (-(-gx // bw) * bw) * (-(-gy // bh) * bh) * (-(-n // bn) * bn)
+            key = (waste, 0 if bw >= 8 else 1, bn)
+            if best is None or key < best[0]:
+                best = (key, (bw, bh, bn))
+    return best[1]
+
+
+class WgradPlan:
+    def __init__(self, desc, keep):
+        self._keep = keep
+        self.desc = desc
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mmr_wgrad_plan_create(C.byref(desc), C.byref(h)))
+        self.handle = h
+        self.flops = 0
+
+    def run(self, stream=None, impl=0, accumulate=False):
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(_lib.lib().mmr_wgrad_plan_run(self.handle, impl, int(accumulate), C.c_void_p(s)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().mmr_wgrad_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def build_wgrad(dz, sources, ksize, stride, pad, dst, *, cout_gemm=None, dst_cin=None, n_sms=148,
+                n_split=None):
+    """Weight gradient.  dz: [N,Ho,Wo,Cz] bf16 (Cz >= cout_gemm).  sources: as in build_fprop.
+    dst: fp32 OIHW gradient [Cout][Cin_total][k][k] (written or accumulated at run time)."""
+    from ._lib import MmrWgChunk, MmrWgradDesc
+    N, Ho, Wo, Cz = dz.shape
+    assert dz.dtype == torch.bfloat16 and dz.is_contiguous()
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    cout = dst.shape[0]
+    taps = ksize * ksize
+    cin_total = sum(t.shape[3] for t, _ in sources)
+    if dst_cin is None:
+        dst_cin = dst.shape[1]
+    assert dst.numel() == cout * dst_cin * taps
+    if cout_gemm is None:
+        cout_gemm = Cz
+    chunk_ch = pick_bk([t.shape[3] for t, _ in sources])
+    cpm = 128 // chunk_ch
+    any_up = any(up == 2 for _, up in sources)
+    assert not (any_up and stride != 1)
+    classes = [(py, px) for py in (0, 1) for px in (0, 1)] if any_up else [(0, 0)]
+    chunks = []
+    seg_off = 0
+    for si, (t, up) in enumerate(sources):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+        for c0 in range(0, t.shape[3], chunk_ch):
+            for ky in range(ksize):
+                for kx in range(ksize):
+                    ch = MmrWgChunk()
+                    ch.src, ch.c0 = si, c0
+                    for ci, (py, px) in enumerate(classes):
+                        if any_up:
+                            if up == 2:
+                                ch.a = 1
+                                ch.by[ci] = (py + ky - pad) >> 1
+                                ch.bx[ci] = (px + kx - pad) >> 1
+                            else:
+                                ch.a = 2
+                                ch.by[ci] = py + ky - pad
+                                ch.bx[ci] = px + kx - pad
+                        else:
+                            ch.a = stride
+                            ch.by[ci] = ky - pad
+                            ch.bx[ci] = kx - pad
+                    ch.dst_ci = seg_off + c0
+                    ch.dst_tap = ky * ksize + kx
+                    chunks.append(ch)
+        seg_off += t.shape[3]
+    while len(chunks) % cpm:
+        pad_ch = MmrWgChunk()
+        C.memmove(C.byref(pad_ch), C.byref(chunks[0]), C.sizeof(MmrWgChunk))
+        pad_ch.dst_tap = -1
+        chunks.append(pad_ch)
+    arr = (MmrWgChunk * len(chunks))(*chunks)
+
+    d = MmrWgradDesc()
+    if any_up:
+        gx, gy = Wo // 2, Ho // 2
+        d.dz = MmrSrc(dz.data_ptr(), Cz, Wo, Ho, N, 2)
+        d.dz_a = 2
+        for ci, (py, px) in enumerate(classes):
+            d.dz_bx[ci], d.dz_by[ci] = px, py
+        srcs = [(t, 1 if up == 2 else 2) for t, up in sources]
+    else:
+        gx, gy = Wo, Ho
+        d.dz = MmrSrc(dz.data_ptr(), Cz, Wo, Ho, N, 1)
+        d.dz_a = 1
+        srcs = [(t, stride) for t, _ in sources]
+    d.nsrc = len(srcs)
+    for i, (t, es) in enumerate(srcs):
+        n_, h_, w_, c_ = t.shape
+        d.src[i] = MmrSrc(t.data_ptr(), c_, w_, h_, n_, es)
+    d.ncls = len(classes)
+    d.nchunks = len(chunks)
+    d.chunks = C.cast(arr, C.POINTER(MmrWgChunk))
+    d.chunk_ch = chunk_ch
+    d.cout_gemm = cout_gemm
+    d.kp_w, d.kp_h, d.kp_n = choose_pixbox(gx, gy, N)
+    d.gx_count, d.gy_count, d.n_img = gx, gy, N
+    ksteps = (-(-gx // d.kp_w)) * (-(-gy // d.kp_h)) * (-(-N // d.kp_n)) * len(classes)
+    nt_cols = min(256, cout_gemm)
+    n_ntiles = cout_gemm // nt_cols
+    n_mtiles = len(chunks) // cpm
+    max_mt = min(8, 512 // nt_cols)
+    n_groups = -(-n_mtiles // max_mt)
+    if n_split is None:
+        n_split = max(1, n_sms // (n_groups * n_ntiles))
+        n_split = max(1, min(n_split, ksteps // 4))
+    n_split = max(1, min(n_split, ksteps))
+    d.n_split = n_split
+    partial = torch.empty((n_split, n_mtiles * 128, cout_gemm), device=dz.device, dtype=torch.float32)
+    d.partial = partial.data_ptr()
+    d.dst = dst.data_ptr()
+    d.dst_cout, d.dst_cin, d.dst_taps = cout, dst_cin, taps
+    d.chunk_valid_ch = chunk_ch
+    plan = WgradPlan(d, [arr, partial, dz, dst, [t for t, _ in sources]])
+    plan.flops = 2 * N * Ho * Wo * cout * taps * cin_total
+    plan.n_ctas = n_groups * n_ntiles * n_split
+    return plan

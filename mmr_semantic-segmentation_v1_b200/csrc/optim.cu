@@ -1,5 +1,5 @@
-// Optimiser-side kernels: Adam / AdamW over the flat fp32 parameter buffer, gradient
-// norm, and the split-K reduction that turns wgrad partials into OIHW fp32 gradients.
+// Optimiser-side kernels: Adam / AdamW over the flat fp32 parameter buffer and the gradient
+// norm.
 // All HBM-bound (Adam: 28 B/param).
 #include "common.h"
 
@@ -80,28 +80,6 @@ sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
   if (threadIdx.x == 0) atomicAdd(out, sh[0]);
 }
 
-// partial: [n_split][cout_pad][ncols_pad], column = tap*cin_pad + ci, cin_pad = ncols_pad/taps.
-// dst: OIHW fp32, index (co*cin + ci)*taps + tap.
-__global__ void __launch_bounds__(kOptThreads)
-wgrad_reduce_kernel(const float* __restrict__ partial, int n_split, int cout, int cout_pad, int cin,
-                    int taps, int ncols_pad, float* __restrict__ dst, int accumulate) {
-  const int cin_pad = ncols_pad / taps;
-  const int64_t total = (int64_t)cout * cin * taps;
-  const size_t split_stride = (size_t)cout_pad * ncols_pad;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    // iterate in partial-column order so the reads coalesce
-    const int ci = (int)(i % cin);
-    const int tap = (int)((i / cin) % taps);
-    const int co = (int)(i / ((int64_t)cin * taps));
-    const size_t src = (size_t)co * ncols_pad + (size_t)tap * cin_pad + ci;
-    float s = 0.f;
-    for (int k = 0; k < n_split; ++k) s += __ldg(partial + k * split_stride + src);
-    const size_t d = ((size_t)co * cin + ci) * taps + tap;
-    dst[d] = accumulate ? dst[d] + s : s;
-  }
-}
-
 }  // namespace mmr
 
 using namespace mmr;
@@ -128,21 +106,6 @@ extern "C" int mmr_sumsq(const float* g, int64_t n, double* out, mmr_stream_t st
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   sumsq_kernel<<<(int)blocks, kOptThreads, 0, as_stream(stream)>>>(g, n, out);
-  MMR_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int mmr_wgrad_reduce(const float* partial, int n_split, int cout, int cout_pad, int cin,
-                                int taps, int ncols_pad, float* dst_oihw, int accumulate,
-                                mmr_stream_t stream) {
-  MMR_REQUIRE(ncols_pad % taps == 0 && ncols_pad / taps >= cin, "wgrad_reduce: bad column layout");
-  const int64_t total = (int64_t)cout * cin * taps;
-  int64_t blocks = (total + kOptThreads - 1) / kOptThreads;
-  const int64_t cap = (int64_t)num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  wgrad_reduce_kernel<<<(int)blocks, kOptThreads, 0, as_stream(stream)>>>(
-      partial, n_split, cout, cout_pad, cin, taps, ncols_pad, dst_oihw, accumulate);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
