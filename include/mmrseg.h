@@ -162,9 +162,9 @@ int mmr_unpack_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int ldc, int H
                                      float* out, mmr_stream_t stream);
 /* OIHW fp32 master weights -> bf16 GEMM layouts:
  *   fwd  [O][kh*kw][I]  (row stride ldf >= kh*kw*I)   and, if dgrad != NULL,
- *   dgrad [I][kh*kw][O] (row stride ldd >= kh*kw*O). */
+ *   dgrad [I][kh*kw][o_pad] (row stride ldd >= kh*kw*o_pad; o_pad >= O, pad columns untouched). */
 int mmr_repack_weights(const float* w_oihw, int O, int I, int taps, void* fwd, int ldf,
-                       void* dgrad, int ldd, mmr_stream_t stream);
+                       void* dgrad, int ldd, int o_pad, mmr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * BatchNorm2d (+ residual add + ReLU), training and eval; replaces nn.BatchNorm2d / ReLU
@@ -207,6 +207,10 @@ int mmr_bn_bwd_apply(const void* g, const void* z, const float* mean, const floa
 int mmr_grad_gather(const MmrContrib* contribs, int ncontrib, const void* act, int N, int H, int W,
                     int C, void* g, double* partial, int nblk, mmr_stream_t stream);
 
+/* dbias[c] (+)= sum over blocks of the per-channel sums mmr_grad_gather left in partial. */
+int mmr_bias_grad_finalize(const double* partial, int nblk, int C, float* dbias, int accumulate,
+                           mmr_stream_t stream);
+
 /* MaxPool2d(3, stride 2, pad 1) on NHWC bf16; idx = window position 0..8 of the first
  * maximum (torch tie rule).  Replaces encoder.maxpool. */
 int mmr_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, uint8_t* idx,
@@ -235,10 +239,12 @@ int64_t mmr_dice_ce_workspace_doubles(int N, int C, int nblk);
 int mmr_dice_ce_fwd(const float* logits, const int64_t* labels, int N, int C, int H, int W,
                     const MmrLossParams* p, double* workspace, int nblk, float* out,
                     mmr_stream_t stream);
-/* dlogits (fp32 NCHW) = grad_scale * dLoss/dlogits, using the sums left in workspace. */
+/* dlogits (fp32 NCHW) = grad_scale * [*grad_scale_dev] * dLoss/dlogits, using the sums left in
+ * workspace.  grad_scale_dev (device scalar, may be NULL) carries autograd's upstream gradient
+ * without a host synchronisation. */
 int mmr_dice_ce_bwd(const float* logits, const int64_t* labels, int N, int C, int H, int W,
                     const MmrLossParams* p, const double* workspace, float grad_scale,
-                    float* dlogits, mmr_stream_t stream);
+                    const float* grad_scale_dev, float* dlogits, mmr_stream_t stream);
 /* fp32 NCHW dlogits -> bf16 NHWC padded to cpad channels + per-class sums (head bias grad). */
 int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int W, void* out, int cpad,
                        float* dbias, int accumulate, mmr_stream_t stream);
@@ -252,8 +258,15 @@ int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int W, void* o
 int mmr_confusion_from_logits(const float* logits, const int64_t* labels, int N, int C, int H,
                               int W, int64_t* cm /* [N][C][C], accumulated */, int64_t* pred_out,
                               mmr_stream_t stream);
+/* ignore_index: labels equal to it are skipped too (smp get_stats ignore_index). */
 int mmr_confusion_from_preds(const int64_t* preds, const int64_t* labels, int N, int C,
-                             int64_t npix_per_image, int64_t* cm, mmr_stream_t stream);
+                             int64_t npix_per_image, int64_t ignore_index, int64_t* cm,
+                             mmr_stream_t stream);
+/* One-hot map [N][C][H][W] (fp32 when is_float, else int64) -> labels [N][H][W] int64 (first
+ * maximal channel).  The reference passes one-hot ground truth to Evaluate.addBatch
+ * (SU/ModelTraining.py:725,757) and to DiceCELoss (ED/Main_MMR_SegModel.py:700-709). */
+int mmr_onehot_to_labels(const void* onehot, int is_float, int N, int C, int H, int W,
+                         int64_t* labels, mmr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Optimiser: Adam / AdamW over one flat fp32 buffer.  Replaces optim.Adam(...).step()

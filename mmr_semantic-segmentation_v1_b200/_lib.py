@@ -101,7 +101,7 @@ SIGNATURES = {
     "mmr_stem_im2col": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "mmr_unpack_nhwc_bf16_to_nchw_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
-    "mmr_repack_weights": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
+    "mmr_repack_weights": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "mmr_bn_stats": (_i, [_vp, _i64, _i, _vp, _i, _vp]),
     "mmr_bn_finalize": (_i, [_vp, _i, _i64, _i, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, _vp]),
@@ -111,16 +111,18 @@ SIGNATURES = {
     "mmr_bn_bwd_finalize": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "mmr_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "mmr_grad_gather": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "mmr_bias_grad_finalize": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "mmr_maxpool3x3s2_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mmr_maxpool3x3s2_bwd": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mmr_dice_ce_workspace_doubles": (_i64, [_i, _i, _i]),
     "mmr_dice_ce_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(MmrLossParams), _vp, _i, _vp,
                              _vp]),
     "mmr_dice_ce_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(MmrLossParams), _vp, _f, _vp,
-                             _vp]),
+                             _vp, _vp]),
     "mmr_head_grad_prep": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "mmr_confusion_from_logits": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "mmr_confusion_from_preds": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp]),
+    "mmr_confusion_from_preds": (_i, [_vp, _vp, _i, _i, _i64, _i64, _vp, _vp]),
+    "mmr_onehot_to_labels": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "mmr_sumsq": (_i, [_vp, _i64, _vp, _vp]),
 }

@@ -280,7 +280,7 @@ class WgradPlan:
 
 
 def build_wgrad(dz, sources, ksize, stride, pad, dst, *, cout_gemm=None, dst_cin=None, n_sms=148,
-                n_split=None):
+                n_split=None, partial=None):
     """Weight gradient.  dz: [N,Ho,Wo,Cz] bf16 (Cz >= cout_gemm).  sources: as in build_fprop.
     dst: fp32 OIHW gradient [Cout][Cin_total][k][k] (written or accumulated at run time)."""
     from ._lib import MmrWgChunk, MmrWgradDesc
@@ -368,8 +368,13 @@ def build_wgrad(dz, sources, ksize, stride, pad, dst, *, cout_gemm=None, dst_cin
         n_split = max(1, n_sms // (n_groups * n_ntiles))
         n_split = max(1, min(n_split, ksteps // 4))
     n_split = max(1, min(n_split, ksteps))
+    per_split = n_mtiles * 128 * cout_gemm
+    if partial is None:
+        partial = torch.empty((n_split * per_split,), device=dz.device, dtype=torch.float32)
+    else:  # shared scratch: shrink the split factor until the partials fit
+        assert partial.dtype == torch.float32 and partial.numel() >= per_split
+        n_split = min(n_split, partial.numel() // per_split)
     d.n_split = n_split
-    partial = torch.empty((n_split, n_mtiles * 128, cout_gemm), device=dz.device, dtype=torch.float32)
     d.partial = partial.data_ptr()
     d.dst = dst.data_ptr()
     d.dst_cout, d.dst_cin, d.dst_taps = cout, dst_cin, taps

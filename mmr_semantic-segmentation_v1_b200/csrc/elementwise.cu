@@ -146,7 +146,7 @@ __global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int N, i
 
 __global__ void repack_weights_kernel(const float* __restrict__ w, int O, int I, int taps,
                                       __nv_bfloat16* __restrict__ fwd, int ldf,
-                                      __nv_bfloat16* __restrict__ dgrad, int ldd) {
+                                      __nv_bfloat16* __restrict__ dgrad, int ldd, int o_pad) {
   const int64_t total = (int64_t)O * I * taps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -155,7 +155,7 @@ __global__ void repack_weights_kernel(const float* __restrict__ w, int O, int I,
     const int o = (int)(i / ((int64_t)taps * I));
     const __nv_bfloat16 v = __float2bfloat16(w[i]);
     if (fwd) fwd[(size_t)o * ldf + (size_t)t * I + ci] = v;
-    if (dgrad) dgrad[(size_t)ci * ldd + (size_t)t * O + o] = v;
+    if (dgrad) dgrad[(size_t)ci * ldd + (size_t)t * o_pad + o] = v;
   }
 }
 
@@ -516,13 +516,13 @@ extern "C" int mmr_unpack_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int
 }
 
 extern "C" int mmr_repack_weights(const float* w, int O, int I, int taps, void* fwd, int ldf,
-                                  void* dgrad, int ldd, mmr_stream_t stream) {
+                                  void* dgrad, int ldd, int o_pad, mmr_stream_t stream) {
   MMR_REQUIRE(!fwd || ldf >= taps * I, "forward row stride too small");
-  MMR_REQUIRE(!dgrad || ldd >= taps * O, "dgrad row stride too small");
+  MMR_REQUIRE(!dgrad || (o_pad >= O && ldd >= taps * o_pad), "dgrad row stride too small");
   const int64_t total = (int64_t)O * I * taps;
   repack_weights_kernel<<<ew_blocks(total, 4), kEwThreads, 0, as_stream(stream)>>>(
       w, O, I, taps, reinterpret_cast<__nv_bfloat16*>(fwd), ldf,
-      reinterpret_cast<__nv_bfloat16*>(dgrad), ldd);
+      reinterpret_cast<__nv_bfloat16*>(dgrad), ldd, o_pad);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -609,6 +609,24 @@ extern "C" int mmr_grad_gather(const MmrContrib* contribs, int ncontrib, const v
   reduce_rows_kernel<2><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
       nullptr, (int64_t)N * H * W, C, partial, cl, reinterpret_cast<const __nv_bfloat16*>(act),
       nullptr, nullptr, H, W, reinterpret_cast<__nv_bfloat16*>(g));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Bias gradient of a conv without BatchNorm: column sums left by mmr_grad_gather.
+__global__ void bias_grad_finalize_kernel(const double* __restrict__ partial, int nblk, int C,
+                                          float* dbias, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[((size_t)b * 2 + 0) * C + c];
+  dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)s;
+}
+
+extern "C" int mmr_bias_grad_finalize(const double* partial, int nblk, int C, float* dbias,
+                                      int accumulate, mmr_stream_t stream) {
+  bias_grad_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(partial, nblk, C, dbias,
+                                                                            accumulate);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -160,7 +160,9 @@ template <int CP>
 __global__ void __launch_bounds__(kLossThreads)
 dice_ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int N, int C,
                    int64_t HW, MmrLossParams prm, const double* __restrict__ ws,
-                   float grad_scale, float* __restrict__ dlogits) {
+                   float grad_scale, const float* __restrict__ grad_scale_dev,
+                   float* __restrict__ dlogits) {
+  if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);
   const int n = blockIdx.y;
   const double* red = ws;
   const double* tail = red + (size_t)N * C * 3;
@@ -259,9 +261,27 @@ confusion_logits_kernel(const float* __restrict__ logits, const int64_t* __restr
   }
 }
 
+// labels[n][i] = first channel holding the maximum of a one-hot map (torch.argmax rule).
+template <typename T>
+__global__ void __launch_bounds__(kLossThreads)
+onehot_to_labels_kernel(const T* __restrict__ oh, int C, int64_t HW, int64_t* __restrict__ labels) {
+  const int n = blockIdx.y;
+  const T* src = oh + (size_t)n * C * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    T best = src[i];
+    int arg = 0;
+    for (int c = 1; c < C; ++c) {
+      const T v = src[(size_t)c * HW + i];
+      if (v > best) best = v, arg = c;
+    }
+    labels[(size_t)n * HW + i] = arg;
+  }
+}
+
 __global__ void __launch_bounds__(kLossThreads)
 confusion_preds_kernel(const int64_t* __restrict__ preds, const int64_t* __restrict__ labels, int C,
-                       int64_t HW, unsigned long long* __restrict__ cm) {
+                       int64_t HW, int64_t ignore_index, unsigned long long* __restrict__ cm) {
   __shared__ unsigned int hist[kMaxClasses * kMaxClasses];
   for (int k = threadIdx.x; k < C * C; k += blockDim.x) hist[k] = 0u;
   __syncthreads();
@@ -269,7 +289,8 @@ confusion_preds_kernel(const int64_t* __restrict__ preds, const int64_t* __restr
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = __ldg(preds + (size_t)n * HW + i), t = __ldg(labels + (size_t)n * HW + i);
-    if (t >= 0 && t < C && p >= 0 && p < C) atomicAdd(&hist[(int)t * C + (int)p], 1u);
+    if (t != ignore_index && t >= 0 && t < C && p >= 0 && p < C)
+      atomicAdd(&hist[(int)t * C + (int)p], 1u);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < C * C; k += blockDim.x)
@@ -320,12 +341,12 @@ extern "C" int mmr_dice_ce_fwd(const float* logits, const int64_t* labels, int N
 
 extern "C" int mmr_dice_ce_bwd(const float* logits, const int64_t* labels, int N, int C, int H, int W,
                                const MmrLossParams* p, const double* workspace, float grad_scale,
-                               float* dlogits, mmr_stream_t stream) {
+                               const float* grad_scale_dev, float* dlogits, mmr_stream_t stream) {
   MMR_REQUIRE(C >= 1 && C <= kMaxClasses, "classes must be in [1,%d], got %d", kMaxClasses, C);
   const int64_t HW = (int64_t)H * W;
   dim3 grid(blocks_per_image(HW, N), N);
   DISPATCH_CP(C, (dice_ce_bwd_kernel<CP><<<grid, kLossThreads, 0, as_stream(stream)>>>(
-                     logits, labels, N, C, HW, *p, workspace, grad_scale, dlogits)));
+                     logits, labels, N, C, HW, *p, workspace, grad_scale, grad_scale_dev, dlogits)));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -343,12 +364,27 @@ extern "C" int mmr_confusion_from_logits(const float* logits, const int64_t* lab
   return 0;
 }
 
+extern "C" int mmr_onehot_to_labels(const void* onehot, int is_float, int N, int C, int H, int W,
+                                    int64_t* labels, mmr_stream_t stream) {
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid(blocks_per_image(HW, N), N);
+  if (is_float)
+    onehot_to_labels_kernel<float><<<grid, kLossThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float*>(onehot), C, HW, labels);
+  else
+    onehot_to_labels_kernel<int64_t><<<grid, kLossThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const int64_t*>(onehot), C, HW, labels);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int mmr_confusion_from_preds(const int64_t* preds, const int64_t* labels, int N, int C,
-                                        int64_t npix, int64_t* cm, mmr_stream_t stream) {
+                                        int64_t npix, int64_t ignore_index, int64_t* cm,
+                                        mmr_stream_t stream) {
   MMR_REQUIRE(C >= 1 && C <= kMaxClasses, "classes must be in [1,%d], got %d", kMaxClasses, C);
   dim3 grid(blocks_per_image(npix, N), N);
   confusion_preds_kernel<<<grid, kLossThreads, 0, as_stream(stream)>>>(
-      preds, labels, C, npix, reinterpret_cast<unsigned long long*>(cm));
+      preds, labels, C, npix, ignore_index, reinterpret_cast<unsigned long long*>(cm));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

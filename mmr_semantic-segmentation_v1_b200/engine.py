@@ -1,0 +1,523 @@
+"""Static execution plan of one network: every buffer, tensor map and launch argument is fixed
+at build time for a given (batch, height, width); running a step is replaying lists of C-ABI
+launches on one CUDA stream (capturable in a CUDA graph, no allocation, no host sync).
+
+Forward (training):  conv (tcgen05, raw bf16 output z) -> batch statistics -> y = relu(z*scale +
+shift [+ residual]).  Forward (eval): BatchNorm folded into the conv epilogue, one launch per conv.
+Backward: per unit  g = relu-mask * sum(consumer contributions)  (+ BN reductions) -> dz -> wgrad
+(fp32 OIHW into the flat gradient buffer) and dgrad (one bf16 tensor per source; a nearest-x2
+source receives it at the conv's resolution and its own gather 2x2-pools it).
+
+Replaces the autograd graph PyTorch builds for `seg = model(img)` / `loss.backward()`
+(SU/ModelTraining.py:589,614; ED/Main_MMR_SegModel.py:697,715).
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib, convplan
+from ._lib import MMR_OUT_BF16_NHWC, MMR_OUT_F32_NCHW, MmrContrib
+
+STEM_KPAD = 160  # 7*7*3 = 147 im2col columns padded to a multiple of 32
+BN_BLOCKS = 592  # CTAs of the per-channel reductions (4 per SM)
+WG_PARTIAL_FLOATS = 48 * 1024 * 1024  # 192 MB of fp32 split-K partials
+
+
+class _Act:
+    def __init__(self, name, shape, needs_grad=True):
+        self.name, self.shape, self.needs_grad = name, shape, needs_grad
+        self.buf = None
+        self.contribs = []   # (buffer key, pool2) filled while building the backward plan
+        self.producer = None
+
+
+class _Arena:
+    """Liveness-planned scratch for backward temporaries (g, dz, per-source data gradients)."""
+
+    def __init__(self):
+        self.req = []  # (key, nbytes, t_alloc, t_free)
+
+    def request(self, key, nbytes, t_alloc, t_free):
+        if os.environ.get("MMR_NO_ARENA_REUSE"):
+            t_free = 1 << 30
+        self.req.append((key, (nbytes + 1023) // 1024 * 1024, t_alloc, t_free))
+
+    def plan(self):
+        free, live, offsets, top = [], [], {}, 0
+        for key, nbytes, t0, t1 in sorted(self.req, key=lambda r: r[2]):
+            for item in [l for l in live if l[0] < t0]:
+                live.remove(item)
+                free.append((item[1], item[2]))
+            free.sort()
+            merged = []
+            for off, sz in free:
+                if merged and merged[-1][0] + merged[-1][1] == off:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + sz)
+                else:
+                    merged.append((off, sz))
+            free = merged
+            if free and free[-1][0] + free[-1][1] == top:   # trailing hole: give it back
+                top = free[-1][0]
+                free.pop()
+            got = None
+            for i, (off, sz) in enumerate(free):
+                if sz >= nbytes:
+                    got = off
+                    if sz > nbytes:
+                        free[i] = (off + nbytes, sz - nbytes)
+                    else:
+                        free.pop(i)
+                    break
+            if got is None:
+                got = top
+                top += nbytes
+            offsets[key] = got
+            live.append((t1, got, nbytes))
+            self.peak = max(getattr(self, "peak", 0), top)
+        return offsets, getattr(self, "peak", 0)
+
+
+class Engine:
+    def __init__(self, ops, params, grads, N, H, W, device, training=True, n_sms=None):
+        """params: name -> fp32 tensor (weights, biases, BN affine and running buffers);
+        grads: name -> fp32 tensor receiving the gradient of the parameter of that name."""
+        self.lib = _lib.lib()
+        if not _lib.device_ok():
+            raise _lib.MmrError("mmrseg_b200 needs a CUDA device of compute capability 10.x "
+                                "(B200); there is no CPU or PyTorch fallback")
+        self.ops, self.P, self.G = ops, params, grads
+        self.N, self.H, self.W = N, H, W
+        self.dev = device
+        self.training = training
+        self.n_sms = n_sms or torch.cuda.get_device_properties(device).multi_processor_count
+        self.keep = []
+        self.acts = {}
+        self.units = []
+        self.fwd_calls = []
+        self.repack_calls = []
+        self._w_versions = None
+        self.bwd_calls = {False: [], True: []}
+        self.conv_flops_fwd = 0
+        self.conv_flops_bwd = 0
+        self.n_launch_fwd = 0
+        self.n_launch_bwd = 0
+        self.weights_dirty = True
+        self.param_ready_hooks = []  # (index in bwd call list, [param names]) for DDP overlap
+        self.x_in = torch.empty((N, 3, H, W), device=device, dtype=torch.float32)
+        self.bn_partial = torch.empty((BN_BLOCKS * 2 * 512,), device=device, dtype=torch.float64)
+        # split-K partials of the weight-gradient GEMMs: one buffer, used by one layer at a time
+        self.wg_partial = torch.empty((WG_PARTIAL_FLOATS,), device=device, dtype=torch.float32) \
+            if training else None
+        self._build_forward()
+        if training:
+            self._build_backward()
+
+    # ------------------------------------------------------------------ helpers
+    def _bf16(self, *shape, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(shape, device=self.dev, dtype=torch.bfloat16)
+
+    def _f32(self, *shape, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(shape, device=self.dev, dtype=torch.float32)
+
+    def _rec(self, calls, fname, *args):
+        conv = []
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                self.keep.append(a)
+                conv.append(C.c_void_p(a.data_ptr()))
+            else:
+                conv.append(a)
+        calls.append((getattr(self.lib, fname), tuple(conv)))
+
+    def _nblk(self, P, Cc):
+        rows_per_iter = 256 // (Cc // 8)
+        return int(max(1, min(BN_BLOCKS, -(-P // (rows_per_iter * 4)))))
+
+    # ------------------------------------------------------------------ forward plan
+    def _build_forward(self):
+        N, H, W = self.N, self.H, self.W
+        fc = self.fwd_calls
+        self.acts["image"] = _Act("image", (N, H, W, 3), needs_grad=False)
+        for op in self.ops:
+            kind = op["op"]
+            if kind == "stem":
+                self._fwd_stem(op)
+            elif kind == "maxpool":
+                src = self.acts[op["in"]]
+                n, h, w, c = src.shape
+                out = _Act(op["out"], (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c))
+                out.buf = self._bf16(*out.shape)
+                out.idx = torch.empty(out.shape, device=self.dev, dtype=torch.uint8)
+                out.producer = {"kind": "maxpool", "src": src, "out": out}
+                self.acts[op["out"]] = out
+                self.units.append(out.producer)
+                self._rec(fc, "mmr_maxpool3x3s2_fwd", src.buf, n, h, w, c, out.buf, out.idx)
+            elif kind in ("conv", "head"):
+                self._fwd_conv(op)
+            elif kind == "input":    # test seam: an activation fed from outside (bf16 NHWC)
+                h, w, c = op["shape"]
+                act = _Act(op["out"], (N, h, w, c))
+                act.buf = self._bf16(N, h, w, c, zero=True)
+                act.producer = {"kind": "input", "out": act, "grad": self._bf16(N, h, w, c, zero=True)}
+                self.acts[op["out"]] = act
+                self.units.append(act.producer)
+            elif kind == "output":   # test seam: an activation whose gradient is seeded from outside
+                act = self.acts[op["in"]]
+                self.out_seeds = getattr(self, "out_seeds", {})
+                self.out_seeds[op["in"]] = self._bf16(*act.shape, zero=True)
+            else:
+                raise ValueError("unknown op %r" % kind)
+        self.n_launch_fwd = len(fc) + len(self.repack_calls)
+
+    def _bn_state(self, unit, bn_name, Cc):
+        st = self._f32(7, Cc)  # mean, invstd, scale, shift, coefA, coefB, coefC
+        unit.update(bn=bn_name, mean=st[0], invstd=st[1], scale=st[2], shift=st[3], coef=st[4:7])
+        self.keep.append(st)
+
+    def _fwd_bn_train(self, unit, z, out, residual, relu):
+        fc = self.fwd_calls
+        bn = unit["bn"]
+        Cc = z.shape[-1]
+        Pn = z.numel() // Cc
+        nblk = self._nblk(Pn, Cc)
+        self._rec(fc, "mmr_bn_stats", z, Pn, Cc, self.bn_partial, nblk)
+        self._rec(fc, "mmr_bn_finalize", self.bn_partial, nblk, Pn, Cc, self.P[bn + ".weight"],
+                  self.P[bn + ".bias"], C.c_float(1e-5), C.c_float(0.1), self.P[bn + ".running_mean"],
+                  self.P[bn + ".running_var"], self.P[bn + ".num_batches_tracked"], unit["mean"],
+                  unit["invstd"], unit["scale"], unit["shift"])
+        self._rec(fc, "mmr_bn_apply", z, Pn, Cc, unit["scale"], unit["shift"], residual, int(relu), out)
+
+    def _fwd_stem(self, op):
+        N, H, W = self.N, self.H, self.W
+        Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        Pn = N * Ho * Wo
+        fc = self.fwd_calls
+        w = self.P[op["conv"] + ".weight"]
+        cout = w.shape[0]
+        unit = {"kind": "stem", "op": op, "cout": cout}
+        unit["mat"] = self._bf16(1, 1, Pn, STEM_KPAD)
+        unit["wf"] = self._bf16(cout, STEM_KPAD, zero=True)
+        out = _Act(op["out"], (N, Ho, Wo, cout))
+        out.buf = self._bf16(*out.shape)
+        out.producer = unit
+        unit["out"] = out
+        self._rec(fc, "mmr_stem_im2col", self.x_in, N, H, W, unit["mat"], STEM_KPAD, None, None)
+        self._rec(self.repack_calls, "mmr_repack_weights", w, cout, 147, 1, unit["wf"], STEM_KPAD, None, 0, 0)
+        if self.training:
+            unit["z"] = self._bf16(N, Ho, Wo, cout)
+            self._bn_state(unit, op["bn"], cout)
+            plan = convplan.build_fprop([(unit["mat"], 1)], unit["wf"], 1, 1, 0, unit["z"].view(1, 1, Pn, cout))
+            fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+            self._fwd_bn_train(unit, unit["z"], out.buf, None, True)
+        else:
+            self._fold(unit, op["bn"], cout)
+            plan = convplan.build_fprop([(unit["mat"], 1)], unit["wf"], 1, 1, 0, out.buf.view(1, 1, Pn, cout),
+                                        scale=unit["scale"], bias=unit["shift"], relu=True)
+            fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+        plan.flops = 2 * Pn * cout * 147
+        self.conv_flops_fwd += plan.flops
+        unit["fplan"] = plan
+        self.acts[op["out"]] = out
+        self.units.append(unit)
+
+    def _fold(self, unit, bn_name, Cc):
+        """Eval mode: scale/shift from the running statistics, refreshed by `refresh_folded`."""
+        st = self._f32(2, Cc)
+        unit.update(bn=bn_name, scale=st[0], shift=st[1])
+        self.keep.append(st)
+        self.folded = getattr(self, "folded", [])
+        self.folded.append(unit)
+
+    def refresh_folded(self):
+        units = getattr(self, "folded", [])
+        ver = tuple(self.P[u["bn"] + sfx]._version for u in units
+                    for sfx in (".weight", ".bias", ".running_mean", ".running_var"))
+        if ver == getattr(self, "_fold_versions", None):
+            return
+        self._fold_versions = ver
+        for u in units:
+            bn = u["bn"]
+            inv = torch.rsqrt(self.P[bn + ".running_var"].float() + 1e-5)
+            sc = self.P[bn + ".weight"].float() * inv
+            u["scale"].copy_(sc)
+            u["shift"].copy_(self.P[bn + ".bias"].float() - self.P[bn + ".running_mean"].float() * sc)
+
+    def _fwd_conv(self, op):
+        fc = self.fwd_calls
+        head = op["op"] == "head"
+        k = op["k"]
+        s = 1 if head else op["s"]
+        pad = k // 2
+        srcs = [(self.acts[name], up) for name, up in op["src"]]
+        n, h0, w0, _ = srcs[0][0].shape
+        Hin, Win = h0 * srcs[0][1], w0 * srcs[0][1]
+        Ho, Wo = (Hin + 2 * pad - k) // s + 1, (Win + 2 * pad - k) // s + 1
+        w = self.P[op["conv"] + ".weight"]
+        cout, cin = w.shape[0], w.shape[1]
+        assert cin == sum(a.shape[3] for a, _ in srcs), (op["conv"], cin)
+        cpad = -(-cout // 16) * 16
+        taps = k * k
+        unit = {"kind": "head" if head else "conv", "op": op, "cout": cout, "cpad": cpad, "k": k, "s": s,
+                "pad": pad, "srcs": srcs, "in_hw": (Hin, Win)}
+        unit["wf"] = self._bf16(cpad, taps * cin, zero=True)
+        unit["wd"] = self._bf16(cin, taps * cpad, zero=True) if self.training else None
+        self._rec(self.repack_calls, "mmr_repack_weights", w, cout, cin, taps, unit["wf"], taps * cin,
+                  unit["wd"], taps * cpad, cpad)
+        sources = [(a.buf, up) for a, up in srcs]
+        res = self.acts[op["res"]] if (not head and op.get("res")) else None
+        unit["res"] = res
+        if head:
+            out = _Act(op["out"], (n, Ho, Wo, cout))
+            out.buf = self._f32(n, cout, Ho, Wo)  # NCHW fp32 logits
+            plan = convplan.build_fprop(sources, unit["wf"], k, 1, pad, out.buf, bias=self.P[op["conv"] + ".bias"],
+                                        out_mode=MMR_OUT_F32_NCHW, cout=cout, bn=cpad)
+            fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+        else:
+            out = _Act(op["out"], (n, Ho, Wo, cout))
+            out.buf = self._bf16(*out.shape)
+            bias = self.P[op["conv"] + ".bias"] if op.get("bias") else None
+            if op.get("bn") and self.training:
+                unit["z"] = self._bf16(*out.shape)
+                self._bn_state(unit, op["bn"], cout)
+                plan = convplan.build_fprop(sources, unit["wf"], k, s, pad, unit["z"], bias=bias)
+                fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+                self._fwd_bn_train(unit, unit["z"], out.buf, res.buf if res else None, op["relu"])
+            else:
+                scale = shift = None
+                if op.get("bn"):
+                    self._fold(unit, op["bn"], cout)
+                    scale, shift = unit["scale"], unit["shift"]
+                    assert bias is None
+                else:
+                    shift = bias
+                plan = convplan.build_fprop(sources, unit["wf"], k, s, pad, out.buf, scale=scale, bias=shift,
+                                            residual=res.buf if res else None, relu=op["relu"])
+                fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+        plan.flops = 2 * n * Ho * Wo * cout * taps * cin
+        self.conv_flops_fwd += plan.flops
+        unit["fplan"] = plan
+        unit["out"] = out
+        out.producer = unit
+        self.acts[op["out"]] = out
+        self.units.append(unit)
+
+    # ------------------------------------------------------------------ backward plan
+    def _build_backward(self):
+        order = list(reversed(self.units))
+        t_of = {id(u): t for t, u in enumerate(order)}
+        arena = _Arena()
+        bpe = 2
+
+        def nbytes(shape):
+            n = bpe
+            for d in shape:
+                n *= d
+            return n
+
+        # 1. liveness of every temporary
+        for t, u in enumerate(order):
+            kind = u["kind"]
+            if kind == "input":
+                continue
+            if kind == "maxpool":
+                src = u["src"]
+                if src.needs_grad:
+                    arena.request(("gin", id(u)), nbytes(src.shape), t, t_of[id(src.producer)])
+                continue
+            out = u["out"]
+            oshape = out.shape[:3] + (u.get("cpad", u["cout"]),)
+            t_g = t
+            if u.get("res") is not None and u["res"].needs_grad and u["res"].producer is not None:
+                t_g = t_of[id(u["res"].producer)]
+            arena.request(("g", id(u)), nbytes(oshape), t, t_g)
+            if u.get("bn"):
+                arena.request(("dz", id(u)), nbytes(oshape), t, t)
+            if kind == "stem":
+                continue
+            Hin, Win = u["in_hw"]
+            for si, (a, up) in enumerate(u["srcs"]):
+                if a.needs_grad and a.producer is not None:
+                    arena.request(("dx", id(u), si), nbytes((a.shape[0], Hin, Win, a.shape[3])), t,
+                                  t_of[id(a.producer)])
+        offsets, peak = arena.plan()
+        self.arena_bytes = peak
+        self.arena = torch.empty((max(peak, 1024),), device=self.dev, dtype=torch.uint8)
+
+        def view(key, shape):
+            off = offsets[key]
+            return self.arena[off:off + nbytes(shape)].view(torch.bfloat16).view(shape)
+
+        # 2. emit launches in backward order; contributions are registered as we go
+        for acc in (False, True):
+            for a in self.acts.values():
+                a.contribs = []
+            for name, seed in getattr(self, "out_seeds", {}).items():
+                self.acts[name].contribs.append((seed, 0))
+            calls = self.bwd_calls[acc]
+            for t, u in enumerate(order):
+                self._bwd_unit(u, calls, view, int(acc), record_hooks=not acc)
+        self.n_launch_bwd = len(self.bwd_calls[False])
+
+    def _contrib_array(self, act):
+        arr = (MmrContrib * max(1, len(act.contribs)))()
+        for i, (buf, pool2) in enumerate(act.contribs):
+            arr[i].ptr = buf.data_ptr()
+            arr[i].pool2 = pool2
+            self.keep.append(buf)
+        self.keep.append(arr)
+        return arr, len(act.contribs)
+
+    def _bwd_unit(self, u, calls, view, acc, record_hooks):
+        kind = u["kind"]
+        if kind == "input":
+            out = u["out"]
+            n, h, w, c = out.shape
+            arr, cnt = self._contrib_array(out)
+            self._rec(calls, "mmr_grad_gather", arr, cnt, None, n, h, w, c, u["grad"], None, self._nblk(n * h * w, c))
+            return
+        if kind == "maxpool":
+            src, out = u["src"], u["out"]
+            if not src.needs_grad:
+                return
+            n, h, w, c = src.shape
+            gin = view(("gin", id(u)), src.shape)
+            arr, cnt = self._contrib_array(out)
+            self._rec(calls, "mmr_maxpool3x3s2_bwd", arr, cnt, out.idx, n, h, w, c, gin)
+            src.contribs.append((gin, 0))
+            return
+        out = u["out"]
+        n, ho, wo, _ = out.shape
+        cpad = u.get("cpad", u["cout"])
+        oshape = (n, ho, wo, cpad)
+        Pn = n * ho * wo
+        conv = u["op"]["conv"]
+        g = view(("g", id(u)), oshape)
+        if kind == "head":
+            # the loss leaves fp32 NCHW dlogits in u["dlogits"]; convert + bias gradient
+            if "dlogits" not in u:
+                u["dlogits"] = self._f32(n, u["cout"], ho, wo)
+            self._rec(calls, "mmr_head_grad_prep", u["dlogits"], n, u["cout"], ho, wo, g, cpad,
+                      self.G[conv + ".bias"], acc)
+            dz = g
+        else:
+            arr, cnt = self._contrib_array(out)
+            relu_act = out.buf if u["op"]["relu"] else None
+            Cc = u["cout"]
+            nblk = self._nblk(Pn, Cc)
+            if u.get("bn"):
+                bn = u["bn"]
+                dz = view(("dz", id(u)), oshape)
+                self._rec(calls, "mmr_bn_bwd_reduce", arr, cnt, relu_act, u["z"], u["mean"], u["invstd"], n,
+                          ho, wo, Cc, g, self.bn_partial, nblk)
+                self._rec(calls, "mmr_bn_bwd_finalize", self.bn_partial, nblk, Pn, Cc, self.P[bn + ".weight"],
+                          u["invstd"], self.G[bn + ".weight"], self.G[bn + ".bias"], acc, u["coef"])
+                self._rec(calls, "mmr_bn_bwd_apply", g, u["z"], u["mean"], u["invstd"], u["coef"], Pn, Cc, dz)
+            else:
+                has_bias = u["op"].get("bias")
+                self._rec(calls, "mmr_grad_gather", arr, cnt, relu_act, n, ho, wo, Cc, g,
+                          self.bn_partial if has_bias else None, nblk)
+                if has_bias:
+                    self._rec(calls, "mmr_bias_grad_finalize", self.bn_partial, nblk, Cc,
+                              self.G[conv + ".bias"], acc)
+                dz = g
+            if u.get("res") is not None and u["res"].needs_grad:
+                u["res"].contribs.append((g, 0))
+        # weight gradient
+        gw = self.G[conv + ".weight"]
+        wplan = u.get("wplan")
+        if wplan is None:
+            if kind == "stem":
+                wplan = convplan.build_wgrad(dz.view(1, 1, Pn, cpad), [(u["mat"], 1)], 1, 1, 0,
+                                             gw.view(gw.shape[0], 147, 1, 1), n_sms=self.n_sms,
+                                             partial=self.wg_partial)
+                wplan.flops = 2 * Pn * u["cout"] * 147
+            else:
+                sources = [(a.buf, up) for a, up in u["srcs"]]
+                wplan = convplan.build_wgrad(dz, sources, u["k"], u["s"], u["pad"], gw, cout_gemm=cpad,
+                                             n_sms=self.n_sms, partial=self.wg_partial)
+            u["wplan"] = wplan
+        calls.append((self.lib.mmr_wgrad_plan_run, (wplan.handle, 0, acc)))
+        if record_hooks:
+            self.conv_flops_bwd += wplan.flops
+            names = [conv + ".weight"]
+            if u.get("bn"):
+                names += [u["bn"] + ".weight", u["bn"] + ".bias"]
+            if kind == "head" or u["op"].get("bias"):
+                names.append(conv + ".bias")
+            self.param_ready_hooks.append((len(calls), names))
+        if kind == "stem":
+            return
+        # data gradient, one tensor per source that needs it
+        need = [a.needs_grad and a.producer is not None for a, _ in u["srcs"]]
+        if not any(need):
+            return
+        Hin, Win = u["in_hw"]
+        grads = []
+        for si, (a, up) in enumerate(u["srcs"]):
+            shape = (a.shape[0], Hin, Win, a.shape[3])
+            if need[si]:
+                grads.append(view(("dx", id(u), si), shape))
+            else:
+                grads.append(None)
+        if not all(need):
+            raise NotImplementedError("mixed grad / no-grad sources in one conv")
+        dplan = u.get("dplan")
+        if dplan is None:
+            dplan = u["dplan"] = convplan.build_dgrad(dz, u["wd"], u["k"], u["s"], u["pad"], (Hin, Win), grads)
+        calls.append((self.lib.mmr_conv_plan_run, (dplan.handle, 0)))
+        if record_hooks:
+            self.conv_flops_bwd += dplan.flops
+        for si, (a, up) in enumerate(u["srcs"]):
+            a.contribs.append((grads[si], 1 if up == 2 else 0))
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, calls, stream, lo=0, hi=None):
+        s = C.c_void_p(stream)
+        err = 0
+        for fn, args in (calls[lo:hi] if (lo or hi is not None) else calls):
+            err |= fn(*args, s)
+        if err:
+            raise _lib.MmrError(self.lib.mmr_last_error().decode(errors="replace"))
+
+    def forward(self, x=None, stream=None):
+        """x: fp32 NCHW [N,3,H,W] on the device (copied into the plan's input buffer)."""
+        if x is not None:
+            self.x_in.copy_(x, non_blocking=True)
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        if self.training:
+            self._run(self.repack_calls, st)  # the optimiser rewrites the fp32 masters every step
+        else:
+            self.refresh_folded()
+            ver = tuple(t._version for t in self.P.values())
+            if ver != self._w_versions or self.weights_dirty:
+                self._run(self.repack_calls, st)
+                self._w_versions, self.weights_dirty = ver, False
+        self._run(self.fwd_calls, st)
+        return self.acts["logits"].buf if "logits" in self.acts else None
+
+    def head_units(self):
+        return [u for u in self.units if u["kind"] == "head"]
+
+    def backward(self, dlogits=None, accumulate=False, stream=None, on_ready=None):
+        """dlogits: fp32 NCHW gradient of the main head (copied in), or None when a loss kernel
+        already wrote into `dlogits_buffer()`.  on_ready(param_names) is called (host side, in
+        launch order) after the launches that complete those parameters' gradients."""
+        if dlogits is not None:
+            self.head_units()[0]["dlogits"].copy_(dlogits, non_blocking=True)
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        calls = self.bwd_calls[bool(accumulate)]
+        if on_ready is None:
+            self._run(calls, st)
+            return
+        lo = 0
+        for hi, names in self.param_ready_hooks:
+            self._run(calls, st, lo, hi)
+            on_ready(names)
+            lo = hi
+        self._run(calls, st, lo, len(calls))
+
+    def dlogits_buffer(self, which=0):
+        return self.head_units()[which]["dlogits"]

@@ -1,0 +1,111 @@
+"""Static dataflow graphs of the networks on the hot path.
+
+A graph is a list of op dicts in forward execution order.  Tensor names are strings; every
+op writes exactly one tensor.  Parameter names are `state_dict` prefixes of the reference
+models, so the engine can bind the reference's own parameter tensors.
+
+  {'op': 'stem',    'out', 'conv', 'bn'}                         7x7 s2 p3 conv + BN + ReLU on the image
+  {'op': 'stem3',   'out', 'conv', 'cout', 'relu'}               3x3 s1 p1 conv(+bias)+ReLU on the image
+  {'op': 'maxpool', 'in', 'out'}                                  3x3 s2 p1
+  {'op': 'conv',    'out', 'conv', 'src': [(tensor, up)], 'k', 's', 'cout',
+                    'bn': name|None, 'bias': bool, 'relu': bool, 'res': tensor|None}
+  {'op': 'head',    'out', 'conv', 'src': [(tensor, 1)], 'k', 'cout'}   conv + bias -> fp32 NCHW logits
+
+U-Net++ follows smp's UnetPlusPlusDecoder.forward order (call sites
+SU/ModelTraining.py:247-254, ED/Main_MMR_SegModel.py:589); the encoder is the torchvision
+BasicBlock ResNet that smp wraps.
+"""
+
+RESNET_LAYERS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+DECODER_CHANNELS = (256, 128, 64, 32, 16)
+
+
+def resnet_encoder_ops(prefix, layers, ops):
+    """Appends stem, maxpool and the four BasicBlock stages; returns the feature names
+    [stem, layer1, layer2, layer3, layer4] and their channel counts."""
+    ops.append({"op": "stem", "out": "f_stem", "conv": prefix + "conv1", "bn": prefix + "bn1", "relu": True})
+    ops.append({"op": "maxpool", "in": "f_stem", "out": "pool"})
+    x, cin = "pool", 64
+    feats, chans = ["f_stem"], [64]
+    for li, (nblk, cout) in enumerate(zip(layers, (64, 128, 256, 512)), start=1):
+        for bi in range(nblk):
+            s = 2 if (bi == 0 and li > 1) else 1
+            base = "%slayer%d.%d." % (prefix, li, bi)
+            t1 = base + "t1"
+            ops.append({"op": "conv", "out": t1, "conv": base + "conv1", "src": [(x, 1)], "k": 3, "s": s,
+                        "cout": cout, "bn": base + "bn1", "bias": False, "relu": True, "res": None})
+            idn = x
+            if s != 1 or cin != cout:
+                idn = base + "idn"
+                ops.append({"op": "conv", "out": idn, "conv": base + "downsample.0", "src": [(x, 1)],
+                            "k": 1, "s": s, "cout": cout, "bn": base + "downsample.1", "bias": False,
+                            "relu": False, "res": None})
+            out = base + "out"
+            ops.append({"op": "conv", "out": out, "conv": base + "conv2", "src": [(t1, 1)], "k": 3,
+                        "s": 1, "cout": cout, "bn": base + "bn2", "bias": False, "relu": True,
+                        "res": idn})
+            x, cin = out, cout
+        feats.append(x)
+        chans.append(cout)
+    return feats, chans
+
+
+def decoder_block_specs(encoder_channels, decoder_channels=DECODER_CHANNELS):
+    """Block name -> (in, skip, out) channels (smp UnetPlusPlusDecoder.__init__)."""
+    enc = list(encoder_channels[1:])[::-1]
+    in_ch = [enc[0]] + list(decoder_channels[:-1])
+    skip_ch = list(enc[1:]) + [0]
+    out_ch = list(decoder_channels)
+    specs = {}
+    for layer_idx in range(len(in_ch) - 1):
+        for depth_idx in range(layer_idx + 1):
+            if depth_idx == 0:
+                spec = (in_ch[layer_idx], skip_ch[layer_idx] * (layer_idx + 1), out_ch[layer_idx])
+            else:
+                spec = (skip_ch[layer_idx - 1], skip_ch[layer_idx] * (layer_idx + 1 - depth_idx),
+                        skip_ch[layer_idx])
+            specs["x_%d_%d" % (depth_idx, layer_idx)] = spec
+    specs["x_0_%d" % (len(in_ch) - 1)] = (in_ch[-1], 0, out_ch[-1])
+    return specs
+
+
+def decoder_schedule(depth=4):
+    """(block, x source, [skip sources]) in smp's execution order; 'f<k>' is the k-th feature of
+    the reversed encoder pyramid (f0 deepest)."""
+    sched = []
+    for layer_idx in range(depth):
+        for depth_idx in range(depth - layer_idx):
+            if layer_idx == 0:
+                sched.append(("x_%d_%d" % (depth_idx, depth_idx), "f%d" % depth_idx,
+                              ["f%d" % (depth_idx + 1)]))
+            else:
+                L = depth_idx + layer_idx
+                skips = ["x_%d_%d" % (i, L) for i in range(depth_idx + 1, L + 1)] + ["f%d" % (L + 1)]
+                sched.append(("x_%d_%d" % (depth_idx, L), "x_%d_%d" % (depth_idx, L - 1), skips))
+    sched.append(("x_0_%d" % depth, "x_0_%d" % (depth - 1), []))
+    return sched
+
+
+def unetpp_graph(encoder_name="resnet18", classes=2, deep_supervision=False):
+    ops = []
+    feats, chans = resnet_encoder_ops("encoder.", RESNET_LAYERS[encoder_name], ops)
+    rev = feats[::-1]  # f0 = layer4 ... f4 = stem
+    specs = decoder_block_specs([3] + chans)
+    name_of = lambda s: rev[int(s[1:])] if s[0] == "f" else s
+    for blk, xsrc, skips in decoder_schedule(4):
+        cin, cskip, cout = specs[blk]
+        src = [(name_of(xsrc), 2)] + [(name_of(s), 1) for s in skips]
+        base = "decoder.blocks.%s." % blk
+        ops.append({"op": "conv", "out": blk + ".mid", "conv": base + "conv1.0", "src": src, "k": 3,
+                    "s": 1, "cout": cout, "bn": base + "conv1.1", "bias": False, "relu": True,
+                    "res": None})
+        ops.append({"op": "conv", "out": blk, "conv": base + "conv2.0", "src": [(blk + ".mid", 1)],
+                    "k": 3, "s": 1, "cout": cout, "bn": base + "conv2.1", "bias": False, "relu": True,
+                    "res": None})
+    ops.append({"op": "head", "out": "logits", "conv": "segmentation_head.0", "src": [("x_0_4", 1)],
+                "k": 3, "cout": classes})
+    if deep_supervision:
+        for node in ("x_0_3", "x_0_2", "x_0_1"):
+            ops.append({"op": "head", "out": "logits." + node, "conv": "ds_heads." + node,
+                        "src": [(node, 1)], "k": 3, "cout": classes})
+    return ops

@@ -1,0 +1,160 @@
+"""Metric seam of the reference on the integer confusion-matrix kernel (csrc/loss_metric.cu).
+
+    Evaluate(key, use_gpu).addBatch / getIoU / getPRF1 / reset      SU/utils.py:31-181
+    dice(im1, im2, empty_score)                                      SU/utils.py:523-576
+    get_stats(..., mode='multiclass') / iou_score                    smp.metrics, as called at
+                                             ED/Main_MMR_SegModel.py:634-639, 1323-1325
+
+Counting is int64 on the device (argmax with torch's first-maximum rule, shared-memory integer
+atomics, bit-exact); the reference counts in float32 and is exact only below 2^24 per class and
+call.  Ratios are float64 as in the reference.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .losses import onehot_to_labels, _stream
+
+
+def confusion_matrix(logits, labels, cm=None, return_pred=False):
+    """cm[n][g][p] += #{label == g and argmax(logits) == p}; logits fp32 [N,C,H,W]."""
+    if not logits.is_cuda:
+        raise _lib.MmrError("metric kernels run on a B200 only (input on %s); there is no CPU fallback"
+                            % logits.device)
+    logits = logits.contiguous()
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    n, c, h, w = logits.shape
+    if cm is None:
+        cm = torch.zeros((n, c, c), device=logits.device, dtype=torch.int64)
+    pred = torch.empty((n, h, w), device=logits.device, dtype=torch.int64) if return_pred else None
+    _lib.check(_lib.lib().mmr_confusion_from_logits(
+        logits.data_ptr(), labels.contiguous().data_ptr(), n, c, h, w, cm.data_ptr(),
+        pred.data_ptr() if pred is not None else None, _stream()))
+    return (cm, pred) if return_pred else cm
+
+
+def confusion_matrix_from_preds(preds, labels, num_classes, ignore_index=None, cm=None):
+    preds = preds.contiguous().long()
+    labels = labels.contiguous().long()
+    n = preds.shape[0]
+    npix = preds.numel() // n
+    if cm is None:
+        cm = torch.zeros((n, num_classes, num_classes), device=preds.device, dtype=torch.int64)
+    ign = -(2 ** 62) if ignore_index is None else int(ignore_index)
+    _lib.check(_lib.lib().mmr_confusion_from_preds(preds.data_ptr(), labels.data_ptr(), n, num_classes,
+                                                   npix, ign, cm.data_ptr(), _stream()))
+    return cm
+
+
+class Evaluate:
+    """`utils.Evaluate`: accumulates tp / fp / fn per class over batches."""
+
+    def __init__(self, key, use_gpu):
+        self.num_classes = len(key)
+        self.key = key
+        self.use_gpu = use_gpu
+        self.reset()
+
+    def reset(self):
+        self._cm = None
+
+    def addBatch(self, seg, gt, args):
+        if getattr(args, "dataset", None) == "synapse":
+            seg = seg[:, 0:21, :, :]
+            gt = gt[:, 0:21, :, :]
+        labels = onehot_to_labels(gt)
+        n, c = seg.shape[0], seg.shape[1]
+        cm = confusion_matrix(seg, labels)
+        cm = cm.sum(0)
+        self._cm = cm if self._cm is None else self._cm + cm
+
+    def confusion(self):
+        """int64 [C,C] on the device: rows ground truth, columns prediction."""
+        return self._cm
+
+    def _tpfpfn(self):
+        if self._cm is None:
+            return 0, 0, 0
+        cm = self._cm.cpu()
+        tp = cm.diagonal().double()
+        return tp, cm.sum(0).double() - tp, cm.sum(1).double() - tp
+
+    @property
+    def tp(self):
+        return self._tpfpfn()[0]
+
+    @property
+    def fp(self):
+        return self._tpfpfn()[1]
+
+    @property
+    def fn(self):
+        return self._tpfpfn()[2]
+
+    def getIoU(self):
+        tp, fp, fn = self._tpfpfn()
+        return tp / (tp + fp + fn + 1e-15)
+
+    def getPRF1(self):
+        tp, fp, fn = self._tpfpfn()
+        epsilon = 1e-15
+        precision = tp / (tp + fp + epsilon)
+        recall = tp / (tp + fn + epsilon)
+        f1 = (2 * precision * recall) / (precision + recall + epsilon)
+        return precision, recall, f1
+
+
+def dice(im1, im2, empty_score=1.0):
+    """`utils.dice` on device tensors: 2|A and B| / (|A| + |B|) of the boolean masks."""
+    a = torch.as_tensor(im1)
+    b = torch.as_tensor(im2)
+    if a.shape != b.shape:
+        raise ValueError("Shape mismatch: im1 and im2 must have the same shape.")
+    a = (a != 0).reshape(1, -1).long()
+    b = (b != 0).reshape(1, -1).long()
+    cm = confusion_matrix_from_preds(a, b, 2).cpu()[0]
+    im_sum = int(cm[1].sum() + cm[:, 1].sum())
+    if im_sum == 0:
+        return empty_score
+    return 2.0 * int(cm[1, 1]) / im_sum
+
+
+def get_stats(output, target, mode="multiclass", ignore_index=None, threshold=None, num_classes=None):
+    """smp.metrics.get_stats for mode='multiclass': (tp, fp, fn, tn), each int64 [N, C]."""
+    if mode != "multiclass":
+        raise NotImplementedError("only mode='multiclass' (the reference's) is built")
+    if num_classes is None:
+        raise ValueError("``num_classes`` attribute should be not ``None`` for 'multiclass' mode.")
+    if output.shape != target.shape:
+        raise ValueError("Dimensions should match, but ``output`` shape is not equal to ``target`` "
+                         "shape, %s != %s" % (tuple(output.shape), tuple(target.shape)))
+    n = output.shape[0]
+    npix = output.numel() // n
+    cm = confusion_matrix_from_preds(output.reshape(n, -1), target.reshape(n, -1), num_classes,
+                                     ignore_index)
+    tp = cm.diagonal(dim1=1, dim2=2)
+    fp = cm.sum(1) - tp
+    fn = cm.sum(2) - tp
+    # smp: tn = numel - tp - fp - fn - (number of ignored pixels of the image)
+    counted = cm.sum((1, 2))
+    tn = counted[:, None] - tp - fp - fn
+    if ignore_index is None:
+        tn = npix - tp - fp - fn
+    return tp.contiguous(), fp.contiguous(), fn.contiguous(), tn.contiguous()
+
+
+def iou_score(tp, fp, fn, tn, reduction=None, class_weights=None, zero_division=1.0):
+    """smp.metrics.iou_score: tp/(tp+fp+fn), NaN -> zero_division; reductions none / macro / micro."""
+    def score(a, b, c):
+        s = a / (a + b + c)
+        return torch.where(torch.isnan(s), torch.full_like(s, float(zero_division)), s)
+    tp, fp, fn = tp.float(), fp.float(), fn.float()
+    if reduction in (None, "none"):
+        return score(tp, fp, fn)
+    if reduction == "macro":
+        return score(tp.sum(0), fp.sum(0), fn.sum(0)).mean()
+    if reduction == "micro":
+        return score(tp.sum(), fp.sum(), fn.sum())
+    raise NotImplementedError("reduction %r" % (reduction,))

@@ -1,0 +1,255 @@
+"""Drop-in model classes for the reference's model-construction seam.
+
+    smp.UnetPlusPlus(encoder_name=..., encoder_weights=..., in_channels=3, classes=C)
+        SU/ModelTraining.py:247-254, SU/ModelEval.py:331-337
+    smp.create_model(arch="UnetPlusPlus", encoder_name=..., ...)
+        ED/Main_MMR_SegModel.py:589 (config['model'], ED/common_utils.py:235-241)
+
+The modules below are parameter containers with smp's module tree, so `state_dict()` keys and
+shapes are byte-compatible with the reference's checkpoints; `forward` never calls a torch.nn
+layer: it replays the static plan of `engine.Engine` (hand-written sm_100a kernels through the
+C-ABI of include/mmrseg.h).  There is no CPU or eager-PyTorch fallback: calling the model with a
+CPU tensor raises.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, graph
+from .engine import Engine
+
+
+# ------------------------------------------------------------------ parameter containers
+def _conv(cin, cout, k, stride=1, bias=False):
+    return nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2, bias=bias)
+
+
+class _BasicBlock(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = _conv(cin, cout, 3, stride)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = _conv(cout, cout, 3)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(_conv(cin, cout, 1, stride), nn.BatchNorm2d(cout))
+
+
+class _ResNetEncoder(nn.Module):
+    """torchvision-layout ResNet (BasicBlock) without avgpool/fc, as smp's ResNetEncoder."""
+
+    def __init__(self, name):
+        super().__init__()
+        layers = graph.RESNET_LAYERS[name]
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        cin = 64
+        for li, (n, cout) in enumerate(zip(layers, (64, 128, 256, 512)), start=1):
+            blocks = []
+            for bi in range(n):
+                blocks.append(_BasicBlock(cin, cout, 2 if (bi == 0 and li > 1) else 1))
+                cin = cout
+            setattr(self, "layer%d" % li, nn.Sequential(*blocks))
+        for m in self.modules():  # torchvision's default initialisation
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+
+class _Conv2dReLU(nn.Sequential):
+    def __init__(self, cin, cout):
+        super().__init__(_conv(cin, cout, 3), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class _DecoderBlock(nn.Module):
+    def __init__(self, cin, cskip, cout):
+        super().__init__()
+        self.conv1 = _Conv2dReLU(cin + cskip, cout)
+        self.attention1 = nn.Identity()
+        self.conv2 = _Conv2dReLU(cout, cout)
+        self.attention2 = nn.Identity()
+
+
+class _Decoder(nn.Module):
+    def __init__(self, encoder_channels):
+        super().__init__()
+        self.blocks = nn.ModuleDict({name: _DecoderBlock(i, s, o) for name, (i, s, o) in
+                                     graph.decoder_block_specs(encoder_channels).items()})
+        for m in self.modules():  # smp initialize_decoder
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+
+# ------------------------------------------------------------------ autograd bridge
+class _PlanFunction(torch.autograd.Function):
+    """logits = plan(x); backward replays the plan's backward and leaves parameter gradients in
+    the model's flat gradient buffer (exposed as each parameter's .grad)."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        eng = model._engine_for(x, training=True)
+        ctx.model, ctx.eng = model, eng
+        return eng.forward(x).detach()  # a fresh tensor object over the plan's logits buffer
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model, eng = ctx.model, ctx.eng
+        accumulate = model._grads_live()
+        eng.backward(dlogits.contiguous(), accumulate=accumulate, on_ready=model._on_grads_ready)
+        model._publish_grads()
+        if model._after_backward is not None:
+            model._after_backward()
+        return (None, None) + (None,) * len(model._flat_names)
+
+
+class _PlanModel(nn.Module):
+    """Shared machinery: flat fp32 parameter / gradient buffers, plan cache, autograd bridge."""
+
+    def _graph(self):
+        raise NotImplementedError
+
+    def __init__(self):
+        super().__init__()
+        self._engines = {}
+        self._flat = None
+        self._on_grads_ready = None  # DDP installs callbacks here
+        self._after_backward = None
+
+    # ---- flat parameter storage ------------------------------------------------------------
+    def _flatten(self, device):
+        """Re-home every parameter into one fp32 buffer (so Adam and the gradient all-reduce are
+        single launches) and create the matching flat gradient buffer."""
+        named = list(self.named_parameters())
+        offs, total = [], 0
+        for _, p in named:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(total, device=device, dtype=torch.float32)
+        gflat = torch.zeros(total, device=device, dtype=torch.float32)
+        views = {}
+        for (name, p), off in zip(named, offs):
+            v = flat[off:off + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            views[name] = gflat[off:off + p.numel()].view(p.shape)
+        self._flat, self._gflat, self._gviews = flat, gflat, views
+        self._flat_names = [n for n, _ in named]
+        self._flat_offsets = dict(zip(self._flat_names, offs))
+        self._flat_ptrs = [p.data_ptr() for _, p in named]
+        self._engines = {}
+
+    def _ensure_flat(self, device):
+        ptrs = [p.data_ptr() for p in self.parameters()]
+        if self._flat is None or ptrs != self._flat_ptrs or self._flat.device != device:
+            for p in self.parameters():
+                if p.dtype != torch.float32:
+                    raise _lib.MmrError("parameters must stay fp32 masters (the kernels compute in "
+                                        "bf16 with fp32 accumulate on their own); got %s" % p.dtype)
+            self._flatten(device)
+
+    def flat_parameters(self):
+        return self._flat, self._gflat
+
+    def _grads_live(self):
+        """True when every .grad is still our view (gradient accumulation step)."""
+        live = [p.grad is not None for p in self.parameters()]
+        if not any(live):
+            return False
+        if all(live) and all(p.grad.data_ptr() == self._gviews[n].data_ptr()
+                             for n, p in self.named_parameters()):
+            return True
+        raise _lib.MmrError("parameter .grad tensors were replaced; call zero_grad(set_to_none=True) "
+                            "(or leave them untouched) between backward passes")
+
+    def _publish_grads(self):
+        for n, p in self.named_parameters():
+            if p.grad is None:
+                p.grad = self._gviews[n]
+
+    # ---- plan cache ------------------------------------------------------------------------
+    def _engine_for(self, x, training):
+        if not x.is_cuda:
+            raise _lib.MmrError("mmrseg_b200 models run on a B200 only: input is on %s and there is "
+                                "no CPU fallback" % x.device)
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected input of shape [N, 3, H, W], got %s" % (tuple(x.shape),))
+        n, _, h, w = x.shape
+        if h % 32 or w % 32:
+            raise RuntimeError("Wrong input shape height=%d, width=%d. Expected image height and width "
+                               "divisible by 32." % (h, w))
+        self._ensure_flat(x.device)
+        key = (n, h, w, bool(training))
+        eng = self._engines.get(key)
+        if eng is None:
+            tensors = dict(self.named_parameters())
+            tensors.update(dict(self.named_buffers()))
+            params = {k: v.data for k, v in tensors.items()}
+            eng = Engine(self._graph(), params, self._gviews, n, h, w, x.device, training=training)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, x):
+        x = x.float() if x.dtype != torch.float32 else x
+        if self.training and torch.is_grad_enabled():
+            self._ensure_flat(x.device)
+            return _PlanFunction.apply(self, x.contiguous(), *self.parameters())
+        eng = self._engine_for(x, training=self.training)
+        return eng.forward(x.contiguous())
+
+
+class UnetPlusPlus(_PlanModel):
+    """`smp.UnetPlusPlus` with the reference's arguments.  `encoder_weights` other than None
+    would need a download; BASELINE configs are random-init, checkpoints load through
+    `load_state_dict`."""
+
+    def __init__(self, encoder_name="resnet18", encoder_depth=5, encoder_weights=None,
+                 decoder_use_batchnorm=True, decoder_channels=(256, 128, 64, 32, 16),
+                 decoder_attention_type=None, in_channels=3, classes=1, activation=None,
+                 aux_params=None, deep_supervision=False):
+        super().__init__()
+        if encoder_name not in graph.RESNET_LAYERS:
+            raise KeyError("encoder %r is not built; available: %s" % (encoder_name, list(graph.RESNET_LAYERS)))
+        if (encoder_depth != 5 or tuple(decoder_channels) != graph.DECODER_CHANNELS or in_channels != 3
+                or decoder_attention_type is not None or not decoder_use_batchnorm
+                or activation is not None or aux_params is not None):
+            raise NotImplementedError("only the configuration the reference uses is built: depth 5, "
+                                      "decoder (256,128,64,32,16) with batch-norm, 3 input channels")
+        if encoder_weights is not None:
+            raise ValueError("pretrained encoder weights need a download; pass encoder_weights=None and "
+                             "load a checkpoint with load_state_dict")
+        self.encoder_name, self.classes, self.deep_supervision = encoder_name, classes, deep_supervision
+        self.encoder = _ResNetEncoder(encoder_name)
+        self.decoder = _Decoder((3, 64, 64, 128, 256, 512))
+        head = _conv(16, classes, 3, bias=True)
+        nn.init.xavier_uniform_(head.weight)
+        nn.init.constant_(head.bias, 0)
+        self.segmentation_head = nn.Sequential(head, nn.Identity(), nn.Identity())
+        if deep_supervision:
+            self.ds_heads = nn.ModuleDict({"x_0_1": _conv(128, classes, 3, bias=True),
+                                           "x_0_2": _conv(64, classes, 3, bias=True),
+                                           "x_0_3": _conv(32, classes, 3, bias=True)})
+            for m in self.ds_heads.values():
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.constant_(m.bias, 0)
+
+    def _graph(self):
+        return graph.unetpp_graph(self.encoder_name, self.classes, self.deep_supervision)
+
+
+def create_model(arch="UnetPlusPlus", encoder_name="resnet18", encoder_weights=None, in_channels=3,
+                 classes=1, **kwargs):
+    """`smp.create_model(**config['model'])` (ED/Main_MMR_SegModel.py:589)."""
+    if arch.lower() != "unetplusplus":
+        raise KeyError("architecture %r is not built; available: ['UnetPlusPlus']" % arch)
+    return UnetPlusPlus(encoder_name=encoder_name, encoder_weights=encoder_weights,
+                        in_channels=in_channels, classes=classes, **kwargs)

@@ -1,0 +1,100 @@
+"""Batch-sharded data-parallel training: one process per GPU, gradients all-reduced with NCCL
+over NVLink in buckets that start while the backward plan is still running.
+
+The reference is single-process; semantics follow torch DDP defaults: per-replica
+BatchNorm statistics, loss mean per replica, gradients averaged over ranks, parameters
+broadcast from rank 0 at construction.
+"""
+import torch
+import torch.distributed as dist
+
+
+class DistributedDataParallel(torch.nn.Module):
+    def __init__(self, module, bucket_mb=8.0, process_group=None):
+        super().__init__()
+        self.module = module
+        self.pg = process_group
+        self.bucket_elems = int(bucket_mb * 1024 * 1024 / 4)
+        self.world = dist.get_world_size(self.pg) if dist.is_initialized() else 1
+        self._buckets = None
+        self._side = None
+        module._on_grads_ready = self._ready
+        module._after_backward = self._finish
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+    # ---- bucket plan: contiguous slices of the flat gradient buffer, closed in backward order
+    def plan_buckets(self, names, offsets, sizes, total):
+        """names in flat order; returns [(lo, hi, set(names))] covering [0,total)."""
+        buckets, hi, cur = [], total, set()
+        for name in reversed(names):
+            cur.add(name)
+            lo = offsets[name]
+            if hi - lo >= self.bucket_elems:
+                buckets.append((lo, hi, cur))
+                hi, cur = lo, set()
+        if cur:
+            buckets.append((0, hi, cur))
+        return buckets
+
+    def _setup(self):
+        m = self.module
+        names = m._flat_names
+        sizes = {n: p.numel() for n, p in m.named_parameters()}
+        self._buckets = self.plan_buckets(names, m._flat_offsets, sizes, m._gflat.numel())
+        self._pending = None
+        self._side = torch.cuda.Stream(device=m._gflat.device) if m._gflat.is_cuda else None
+        self._works = []
+        # broadcast_parameters: rank 0's weights and BN buffers
+        if self.world > 1:
+            dist.broadcast(m._flat, 0, group=self.pg)
+            for b in m.buffers():
+                dist.broadcast(b, 0, group=self.pg)
+
+    def sync_parameters(self):
+        """Call once after the model is on its device and flattened."""
+        if self._buckets is None:
+            self._setup()
+
+    def _ready(self, names):
+        if self._buckets is None:
+            self._setup()
+        if self._pending is None:
+            self._pending = [set(b[2]) for b in self._buckets]
+        for i, pend in enumerate(self._pending):
+            if not pend:
+                continue
+            pend.difference_update(names)
+            if not pend:
+                self._launch(i)
+
+    def _launch(self, i):
+        lo, hi, _ = self._buckets[i]
+        g = self.module._gflat[lo:hi]
+        if self.world == 1:
+            return
+        if self._side is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                self._works.append(dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+        else:  # gloo (CPU tests): no AVG
+            w = dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self._works.append((w, g))
+
+    def _finish(self):
+        if self._pending is not None:
+            for i, pend in enumerate(self._pending):
+                if pend:  # parameters that received no gradient callback: reduce anyway
+                    self._launch(i)
+        for w in self._works:
+            if isinstance(w, tuple):
+                w[0].wait()
+                w[1].div_(self.world)
+            else:
+                w.wait()
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        self._works, self._pending = [], None

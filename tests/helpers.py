@@ -1,0 +1,75 @@
+"""Shared test helpers: synthetic inputs, oracle/candidate model pairs, and the
+mask-matched ReLU that lets an fp32 oracle back-propagate through the same ReLU sign pattern as
+the bf16 plan engine."""
+import torch
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def synthetic_batch(n, classes, h, w, seed=6210):
+    """frames: rand in [0,1] normalised with the ImageNet mean/std the reference uses
+    (SU/ModelTraining.py:300-301); labels: randint(0, classes)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand((n, 3, h, w), generator=g)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    return (u - mean) / std, torch.randint(0, classes, (n, h, w), generator=g)
+
+
+def model_pair(classes, encoder="resnet18", seed=6210, randomize_bn=True):
+    """(oracle fp32 CPU model, plan model on cuda) with identical weights."""
+    from oracle.unetpp import UnetPlusPlus as OracleNet
+    from mmrseg_b200.models import UnetPlusPlus
+    torch.manual_seed(seed)
+    ref = OracleNet(encoder, None, 3, classes)
+    if randomize_bn:
+        g = torch.Generator().manual_seed(seed + 1)
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.data.uniform_(0.5, 1.5, generator=g)
+                m.bias.data.normal_(0, 0.2, generator=g)
+                m.running_mean.normal_(0, 0.2, generator=g)
+                m.running_var.uniform_(0.5, 1.5, generator=g)
+    net = UnetPlusPlus(encoder, classes=classes)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    return ref, net.cuda()
+
+
+class _MaskedReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask):
+        ctx.save_for_backward(mask)
+        return torch.relu(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * mask, None
+
+
+class ReLUWithMasks(torch.nn.Module):
+    """ReLU whose backward uses externally supplied masks, consumed in call order."""
+
+    def __init__(self, masks):
+        super().__init__()
+        self.masks = list(masks)
+
+    def forward(self, x):
+        return _MaskedReLU.apply(x, self.masks.pop(0))
+
+
+def install_engine_masks(ref, eng):
+    """Make the oracle U-Net++ back-propagate through the ReLU sign pattern of the engine's stored
+    activations (a forward error eps flips ~0.8*eps of the masks, which alone moves fp32 gradients
+    by sqrt(0.8*eps) per layer; matching the masks isolates the arithmetic of the kernels)."""
+    m = lambda name: (eng.acts[name].buf.float().permute(0, 3, 1, 2).cpu() > 0).float()
+    ref.encoder.relu = ReLUWithMasks([m("f_stem")])
+    for li in range(1, 5):
+        for bi, blk in enumerate(getattr(ref.encoder, "layer%d" % li)):
+            base = "encoder.layer%d.%d." % (li, bi)
+            blk.relu = ReLUWithMasks([m(base + "t1"), m(base + "out")])
+    for name, blk in ref.decoder.blocks.items():
+        blk.conv1[2] = ReLUWithMasks([m(name + ".mid")])
+        blk.conv2[2] = ReLUWithMasks([m(name)])

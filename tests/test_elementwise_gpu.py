@@ -1,0 +1,172 @@
+"""HBM-bound kernels (csrc/elementwise.cu) against torch fp32 references on the same bf16 inputs:
+BatchNorm forward/backward, gradient gathering with the 2x2 sum-pool of nearest-x2 upsampling,
+max-pool, packing."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from mmrseg_b200 import _lib
+    return _lib
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2)
+
+
+def _contribs(items):
+    from mmrseg_b200._lib import MmrContrib
+    arr = (MmrContrib * len(items))()
+    for i, (t, pool2) in enumerate(items):
+        arr[i].ptr = t.data_ptr()
+        arr[i].pool2 = pool2
+    return arr
+
+
+@pytest.mark.parametrize("shape", [(4, 16, 16, 64), (2, 32, 32, 16), (3, 8, 8, 512), (2, 24, 40, 128)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_bn_forward_backward(shape, with_res):
+    L = _lib()
+    lib = L.lib()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    n, h, w, c = shape
+    P = n * h * w
+    z = (torch.randn(shape, generator=gen, device="cuda") * 1.7 + 0.3).to(torch.bfloat16)
+    res = torch.randn(shape, generator=gen, device="cuda").to(torch.bfloat16) if with_res else None
+    gamma = torch.rand(c, generator=gen, device="cuda") + 0.5
+    beta = torch.randn(c, generator=gen, device="cuda") * 0.2
+    rm = torch.randn(c, generator=gen, device="cuda") * 0.1
+    rv = torch.rand(c, generator=gen, device="cuda") + 0.5
+    nbt = torch.zeros((), device="cuda", dtype=torch.int64)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    nblk = 37
+    partial = torch.empty((nblk * 2 * c,), device="cuda", dtype=torch.float64)
+    st = torch.empty((7, c), device="cuda")
+    out = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mmr_bn_stats(_p(z), P, c, _p(partial), nblk, _s()))
+    L.check(lib.mmr_bn_finalize(_p(partial), nblk, P, c, _p(gamma), _p(beta), 1e-5, 0.1, _p(rm), _p(rv),
+                                _p(nbt), _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), _s()))
+    L.check(lib.mmr_bn_apply(_p(z), P, c, _p(st[2]), _p(st[3]), _p(res), 1, _p(out), _s()))
+    # reference
+    zf = _nchw(z).clone().requires_grad_(True)
+    gl = gamma.clone().requires_grad_(True)
+    bl = beta.clone().requires_grad_(True)
+    y = F.batch_norm(zf, rm_ref, rv_ref, gl, bl, True, 0.1, 1e-5)
+    resf = _nchw(res).clone().requires_grad_(True) if with_res else None
+    yr = torch.relu(y + resf) if with_res else torch.relu(y)
+    torch.cuda.synchronize()
+    assert (_nchw(out) - yr).abs().max().item() <= 0.03
+    assert torch.allclose(rm, rm_ref, atol=1e-5) and torch.allclose(rv, rv_ref, rtol=1e-4, atol=1e-5)
+    assert int(nbt) == 1
+    # backward: two contributions
+    g1 = torch.randn(shape, generator=gen, device="cuda").to(torch.bfloat16)
+    g2 = torch.randn(shape, generator=gen, device="cuda").to(torch.bfloat16)
+    yr.backward(_nchw(g1) + _nchw(g2))
+    g = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+    dz = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+    dgamma = torch.empty(c, device="cuda")
+    dbeta = torch.empty(c, device="cuda")
+    arr = _contribs([(g1, 0), (g2, 0)])
+    L.check(lib.mmr_bn_bwd_reduce(arr, 2, _p(out), _p(z), _p(st[0]), _p(st[1]), n, h, w, c, _p(g),
+                                  _p(partial), nblk, _s()))
+    L.check(lib.mmr_bn_bwd_finalize(_p(partial), nblk, P, c, _p(gamma), _p(st[1]), _p(dgamma), _p(dbeta), 0,
+                                    _p(st[4]), _s()))
+    L.check(lib.mmr_bn_bwd_apply(_p(g), _p(z), _p(st[0]), _p(st[1]), _p(st[4]), P, c, _p(dz), _s()))
+    torch.cuda.synchronize()
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    assert rel(dgamma, gl.grad) < 5e-3, rel(dgamma, gl.grad)
+    assert rel(dbeta, bl.grad) < 5e-3
+    assert rel(_nchw(dz), zf.grad) < 1e-2, rel(_nchw(dz), zf.grad)
+    if with_res:
+        assert rel(_nchw(g), resf.grad) < 1e-2
+
+
+def test_grad_gather_pool2_and_mask():
+    L = _lib()
+    lib = L.lib()
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    n, h, w, c = 2, 8, 12, 64
+    a = torch.randn((n, h, w, c), generator=gen, device="cuda").to(torch.bfloat16)
+    g_same = torch.randn((n, h, w, c), generator=gen, device="cuda").to(torch.bfloat16)
+    g_up = torch.randn((n, 2 * h, 2 * w, c), generator=gen, device="cuda").to(torch.bfloat16)
+    out = torch.empty((n, h, w, c), device="cuda", dtype=torch.bfloat16)
+    nblk = 11
+    partial = torch.empty((nblk * 2 * c,), device="cuda", dtype=torch.float64)
+    arr = _contribs([(g_same, 0), (g_up, 1)])
+    L.check(lib.mmr_grad_gather(arr, 2, _p(a), n, h, w, c, _p(out), _p(partial), nblk, _s()))
+    torch.cuda.synchronize()
+    want = _nchw(g_same) + F.avg_pool2d(_nchw(g_up), 2) * 4
+    want = want * (_nchw(a) > 0)
+    assert (_nchw(out) - want).abs().max().item() <= 0.05
+    sums = partial.view(nblk, 2, c)[:, 0].sum(0)
+    assert torch.allclose(sums.float(), want.sum((0, 2, 3)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 14, 10, 64)])
+def test_maxpool(shape):
+    L = _lib()
+    lib = L.lib()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    n, h, w, c = shape
+    x = torch.randn(shape, generator=gen, device="cuda").to(torch.bfloat16)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty((n, ho, wo, c), device="cuda", dtype=torch.bfloat16)
+    idx = torch.empty((n, ho, wo, c), device="cuda", dtype=torch.uint8)
+    L.check(lib.mmr_maxpool3x3s2_fwd(_p(x), n, h, w, c, _p(out), _p(idx), _s()))
+    xf = _nchw(x).clone().requires_grad_(True)
+    y = F.max_pool2d(xf, 3, 2, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(_nchw(out), y.detach())
+    g = torch.randn((n, ho, wo, c), generator=gen, device="cuda").to(torch.bfloat16)
+    y.backward(_nchw(g))
+    gin = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+    arr = _contribs([(g, 0)])
+    L.check(lib.mmr_maxpool3x3s2_bwd(arr, 1, _p(idx), n, h, w, c, _p(gin), _s()))
+    torch.cuda.synchronize()
+    assert (_nchw(gin) - xf.grad).abs().max().item() <= 0.03
+
+
+def test_pack_unpack_im2col_headprep():
+    L = _lib()
+    lib = L.lib()
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    n, h, w = 2, 32, 64
+    x = torch.randn((n, 3, h, w), generator=gen, device="cuda")
+    packed = torch.empty((n, h, w, 8), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mmr_pack_nchw_f32_to_nhwc_bf16(_p(x), n, 3, h, w, _p(packed), 8, _s()))
+    back = torch.empty((n, 3, h, w), device="cuda")
+    L.check(lib.mmr_unpack_nhwc_bf16_to_nchw_f32(_p(packed), n, 3, 8, h, w, _p(back), _s()))
+    torch.cuda.synchronize()
+    assert torch.equal(back, x.to(torch.bfloat16).float())
+    assert packed[..., 3:].abs().max().item() == 0
+    # im2col of the 7x7 s2 p3 stem == unfold
+    ho, wo = h // 2, w // 2
+    mat = torch.empty((n * ho * wo, 160), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mmr_stem_im2col(_p(x), n, h, w, _p(mat), 160, None, None, _s()))
+    torch.cuda.synchronize()
+    cols = F.unfold(x, 7, padding=3, stride=2)  # [n, 147, ho*wo], row = c*49 + ky*7 + kx
+    want = cols.permute(0, 2, 1).reshape(n * ho * wo, 147).to(torch.bfloat16)
+    assert torch.equal(mat[:, :147], want)
+    assert mat[:, 147:].abs().max().item() == 0
+    # head gradient prep
+    dl = torch.randn((n, 2, h, w), generator=gen, device="cuda")
+    g = torch.empty((n, h, w, 16), device="cuda", dtype=torch.bfloat16)
+    db = torch.empty(2, device="cuda")
+    L.check(lib.mmr_head_grad_prep(_p(dl), n, 2, h, w, _p(g), 16, _p(db), 0, _s()))
+    torch.cuda.synchronize()
+    assert torch.equal(g[..., :2].float().permute(0, 3, 1, 2), dl.to(torch.bfloat16).float())
+    assert g[..., 2:].abs().max().item() == 0
+    assert torch.allclose(db, dl.sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
