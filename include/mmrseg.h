@@ -258,10 +258,13 @@ int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int W, void* o
 int mmr_confusion_from_logits(const float* logits, const int64_t* labels, int N, int C, int H,
                               int W, int64_t* cm /* [N][C][C], accumulated */, int64_t* pred_out,
                               mmr_stream_t stream);
-/* ignore_index: labels equal to it are skipped too (smp get_stats ignore_index). */
+/* ignore_index: labels equal to it are skipped (smp get_stats ignore_index).  overflow_bin != 0:
+ * cm is [N][C+1][C+1] and bin C collects out-of-range predictions / labels (smp counts a pixel
+ * whose prediction is out of range as a false negative of its label); otherwise such pixels
+ * are skipped and cm is [N][C][C]. */
 int mmr_confusion_from_preds(const int64_t* preds, const int64_t* labels, int N, int C,
-                             int64_t npix_per_image, int64_t ignore_index, int64_t* cm,
-                             mmr_stream_t stream);
+                             int64_t npix_per_image, int64_t ignore_index, int overflow_bin,
+                             int64_t* cm, mmr_stream_t stream);
 /* One-hot map [N][C][H][W] (fp32 when is_float, else int64) -> labels [N][H][W] int64 (first
  * maximal channel).  The reference passes one-hot ground truth to Evaluate.addBatch
  * (SU/ModelTraining.py:725,757) and to DiceCELoss (ED/Main_MMR_SegModel.py:700-709). */

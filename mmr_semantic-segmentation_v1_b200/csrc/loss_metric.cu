@@ -279,22 +279,33 @@ onehot_to_labels_kernel(const T* __restrict__ oh, int C, int64_t HW, int64_t* __
   }
 }
 
+// overflow != 0: one extra bin (index C) collects out-of-range predictions / labels, so that
+// row and column sums are the plain histograms smp's get_stats uses; cm is then (C+1) x (C+1).
 __global__ void __launch_bounds__(kLossThreads)
 confusion_preds_kernel(const int64_t* __restrict__ preds, const int64_t* __restrict__ labels, int C,
-                       int64_t HW, int64_t ignore_index, unsigned long long* __restrict__ cm) {
-  __shared__ unsigned int hist[kMaxClasses * kMaxClasses];
-  for (int k = threadIdx.x; k < C * C; k += blockDim.x) hist[k] = 0u;
+                       int64_t HW, int64_t ignore_index, int overflow,
+                       unsigned long long* __restrict__ cm) {
+  __shared__ unsigned int hist[(kMaxClasses + 1) * (kMaxClasses + 1)];
+  const int Cb = C + (overflow ? 1 : 0);
+  for (int k = threadIdx.x; k < Cb * Cb; k += blockDim.x) hist[k] = 0u;
   __syncthreads();
   const int n = blockIdx.y;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = __ldg(preds + (size_t)n * HW + i), t = __ldg(labels + (size_t)n * HW + i);
-    if (t != ignore_index && t >= 0 && t < C && p >= 0 && p < C)
-      atomicAdd(&hist[(int)t * C + (int)p], 1u);
+    int64_t p = __ldg(preds + (size_t)n * HW + i), t = __ldg(labels + (size_t)n * HW + i);
+    if (t == ignore_index) continue;
+    const bool t_ok = t >= 0 && t < C, p_ok = p >= 0 && p < C;
+    if (overflow) {
+      if (!t_ok) t = C;
+      if (!p_ok) p = C;
+    } else if (!t_ok || !p_ok) {
+      continue;
+    }
+    atomicAdd(&hist[(int)t * Cb + (int)p], 1u);
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < C * C; k += blockDim.x)
-    if (hist[k]) atomicAdd(&cm[(size_t)n * C * C + k], (unsigned long long)hist[k]);
+  for (int k = threadIdx.x; k < Cb * Cb; k += blockDim.x)
+    if (hist[k]) atomicAdd(&cm[(size_t)n * Cb * Cb + k], (unsigned long long)hist[k]);
 }
 
 static int blocks_per_image(int64_t HW, int N) {
@@ -379,12 +390,12 @@ extern "C" int mmr_onehot_to_labels(const void* onehot, int is_float, int N, int
 }
 
 extern "C" int mmr_confusion_from_preds(const int64_t* preds, const int64_t* labels, int N, int C,
-                                        int64_t npix, int64_t ignore_index, int64_t* cm,
-                                        mmr_stream_t stream) {
+                                        int64_t npix, int64_t ignore_index, int overflow_bin,
+                                        int64_t* cm, mmr_stream_t stream) {
   MMR_REQUIRE(C >= 1 && C <= kMaxClasses, "classes must be in [1,%d], got %d", kMaxClasses, C);
   dim3 grid(blocks_per_image(npix, N), N);
   confusion_preds_kernel<<<grid, kLossThreads, 0, as_stream(stream)>>>(
-      preds, labels, C, npix, ignore_index, reinterpret_cast<unsigned long long*>(cm));
+      preds, labels, C, npix, ignore_index, overflow_bin, reinterpret_cast<unsigned long long*>(cm));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -35,16 +35,20 @@ def confusion_matrix(logits, labels, cm=None, return_pred=False):
     return (cm, pred) if return_pred else cm
 
 
-def confusion_matrix_from_preds(preds, labels, num_classes, ignore_index=None, cm=None):
+def confusion_matrix_from_preds(preds, labels, num_classes, ignore_index=None, cm=None, overflow_bin=False):
+    if not preds.is_cuda:
+        raise _lib.MmrError("metric kernels run on a B200 only (input on %s); there is no CPU fallback"
+                            % preds.device)
     preds = preds.contiguous().long()
     labels = labels.contiguous().long()
     n = preds.shape[0]
     npix = preds.numel() // n
+    cb = num_classes + (1 if overflow_bin else 0)
     if cm is None:
-        cm = torch.zeros((n, num_classes, num_classes), device=preds.device, dtype=torch.int64)
+        cm = torch.zeros((n, cb, cb), device=preds.device, dtype=torch.int64)
     ign = -(2 ** 62) if ignore_index is None else int(ignore_index)
     _lib.check(_lib.lib().mmr_confusion_from_preds(preds.data_ptr(), labels.data_ptr(), n, num_classes,
-                                                   npix, ign, cm.data_ptr(), _stream()))
+                                                   npix, ign, int(overflow_bin), cm.data_ptr(), _stream()))
     return cm
 
 
@@ -133,15 +137,13 @@ def get_stats(output, target, mode="multiclass", ignore_index=None, threshold=No
     n = output.shape[0]
     npix = output.numel() // n
     cm = confusion_matrix_from_preds(output.reshape(n, -1), target.reshape(n, -1), num_classes,
-                                     ignore_index)
-    tp = cm.diagonal(dim1=1, dim2=2)
-    fp = cm.sum(1) - tp
-    fn = cm.sum(2) - tp
-    # smp: tn = numel - tp - fp - fn - (number of ignored pixels of the image)
-    counted = cm.sum((1, 2))
-    tn = counted[:, None] - tp - fp - fn
-    if ignore_index is None:
-        tn = npix - tp - fp - fn
+                                     ignore_index, overflow_bin=True)
+    c = num_classes
+    tp = cm[:, :c, :c].diagonal(dim1=1, dim2=2)
+    fp = cm.sum(1)[:, :c] - tp          # histogram of the predictions - tp
+    fn = cm.sum(2)[:, :c] - tp          # histogram of the labels - tp
+    # smp: tn = numel - tp - fp - fn - ignored;  numel - ignored = every pixel the kernel counted
+    tn = cm.sum((1, 2))[:, None] - tp - fp - fn
     return tp.contiguous(), fp.contiguous(), fn.contiguous(), tn.contiguous()
 
 

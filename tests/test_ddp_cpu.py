@@ -1,0 +1,59 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes run the bucketed gradient all-reduce of
+parallel.DistributedDataParallel on a stand-in model (flat gradient buffer + readiness callbacks
+in backward order) and must end with the rank-mean in every bucket."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class _FakePlanModel(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Parameter(torch.zeros(1000))
+        self.b = torch.nn.Parameter(torch.zeros(3000))
+        self.c = torch.nn.Parameter(torch.zeros(10))
+        self._on_grads_ready = None
+        self._after_backward = None
+        names = ["a", "b", "c"]
+        offs, tot = {}, 0
+        for n in names:
+            offs[n] = tot
+            tot += (getattr(self, n).numel() + 3) // 4 * 4
+        self._flat = torch.zeros(tot)
+        self._gflat = torch.zeros(tot)
+        self._flat_names, self._flat_offsets = names, offs
+
+
+def _worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmrseg_b200.parallel import DistributedDataParallel
+    m = _FakePlanModel()
+    m._flat.fill_(float(rank + 1))
+    ddp = DistributedDataParallel(m, bucket_mb=0.008)      # ~2k floats per bucket -> several buckets
+    ddp.sync_parameters()
+    assert torch.all(m._flat == 1.0)                        # rank 0's parameters everywhere
+    assert len(ddp._buckets) >= 2
+    covered = sorted((lo, hi) for lo, hi, _ in ddp._buckets)
+    assert covered[0][0] == 0 and covered[-1][1] == m._gflat.numel()
+    assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+    for step in range(2):
+        m._gflat.copy_(torch.arange(m._gflat.numel(), dtype=torch.float32) * (rank + 1))
+        for names in (["c"], ["b"], ["a"]):                 # backward order: last parameter first
+            m._on_grads_ready(names)
+        m._after_backward()
+        want = torch.arange(m._gflat.numel(), dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+        assert torch.allclose(m._gflat, want), (rank, step)
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
