@@ -242,19 +242,43 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, int C, double
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P, int C,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float eps, float momentum, float* running_mean,
-                                   float* running_var, int64_t* nbt, float* mean, float* invstd,
-                                   float* scale, float* shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt) nbt[0] += 1;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s1 += partial[((size_t)b * 2 + 0) * C + c];
-    s2 += partial[((size_t)b * 2 + 1) * C + c];
+// Sum partial[b][which][c] over the nblk blocks for 8 consecutive channels per CTA: 256 threads =
+// 8 channels x 32 block-lanes, tree-combined in shared memory in a fixed order (deterministic).
+__device__ __forceinline__ void reduce_partials8(const double* __restrict__ partial, int nblk, int C,
+                                                 int c0, double& s1, double& s2) {
+  __shared__ double sh[2][32][8];
+  const int j = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c = c0 + j;
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C)
+    for (int b = lane; b < nblk; b += 32) {
+      a1 += partial[((size_t)b * 2 + 0) * C + c];
+      a2 += partial[((size_t)b * 2 + 1) * C + c];
+    }
+  sh[0][lane][j] = a1;
+  sh[1][lane][j] = a2;
+  __syncthreads();
+  for (int s = 16; s > 0; s >>= 1) {
+    if (lane < s) {
+      sh[0][lane][j] += sh[0][lane + s][j];
+      sh[1][lane][j] += sh[1][lane + s][j];
+    }
+    __syncthreads();
   }
+  s1 = sh[0][0][j];
+  s2 = sh[1][0][j];
+}
+
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P, int C,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float momentum, float* running_mean, float* running_var, int64_t* nbt, float* mean,
+                   float* invstd, float* scale, float* shift) {
+  double s1, s2;
+  reduce_partials8(partial, nblk, C, blockIdx.x * 8, s1, s2);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) nbt[0] += 1;
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7);
+  if ((threadIdx.x >> 3) != 0 || c >= C) return;
   const double m = s1 / (double)P;
   double var = s2 / (double)P - m * m;
   if (var < 0.0) var = 0.0;
@@ -308,17 +332,14 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, 
 // With g = dL/d(bn output) already masked by ReLU, xhat = (z-mean)*invstd, M = N*H*W:
 //   dgamma = sum g*xhat,  dbeta = sum g,
 //   dz = gamma*invstd * (g - dbeta/M - xhat*dgamma/M) = coefA*g + coefB*xhat + coefC.
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P,
-                                       int C, const float* __restrict__ gamma,
-                                       const float* __restrict__ invstd, float* dgamma,
-                                       float* dbeta, int accumulate, float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s1 += partial[((size_t)b * 2 + 0) * C + c];
-    s2 += partial[((size_t)b * 2 + 1) * C + c];
-  }
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P, int C,
+                       const float* __restrict__ gamma, const float* __restrict__ invstd, float* dgamma,
+                       float* dbeta, int accumulate, float* coef) {
+  double s1, s2;
+  reduce_partials8(partial, nblk, C, blockIdx.x * 8, s1, s2);
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7);
+  if ((threadIdx.x >> 3) != 0 || c >= C) return;
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
   const double gi = (double)(gamma ? gamma[c] : 1.f) * (double)invstd[c];
@@ -549,7 +570,7 @@ extern "C" int mmr_bn_finalize(const double* partial, int nblk, int64_t P, int C
                                const float* beta, float eps, float momentum, float* running_mean,
                                float* running_var, int64_t* nbt, float* mean, float* invstd,
                                float* scale, float* shift, mmr_stream_t stream) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(
       partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd,
       scale, shift);
   MMR_CUDA_CHECK(cudaGetLastError());
@@ -584,7 +605,7 @@ extern "C" int mmr_bn_bwd_reduce(const MmrContrib* contribs, int ncontrib, const
 extern "C" int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, int C,
                                    const float* gamma, const float* invstd, float* dgamma,
                                    float* dbeta, int accumulate, float* coef, mmr_stream_t stream) {
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(
       partial, nblk, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -616,17 +637,17 @@ extern "C" int mmr_grad_gather(const MmrContrib* contribs, int ncontrib, const v
 // Bias gradient of a conv without BatchNorm: column sums left by mmr_grad_gather.
 __global__ void bias_grad_finalize_kernel(const double* __restrict__ partial, int nblk, int C,
                                           float* dbias, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[((size_t)b * 2 + 0) * C + c];
-  dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)s;
+  double s1, s2;
+  reduce_partials8(partial, nblk, C, blockIdx.x * 8, s1, s2);
+  const int c = blockIdx.x * 8 + (threadIdx.x & 7);
+  if ((threadIdx.x >> 3) != 0 || c >= C) return;
+  dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)s1;
 }
 
 extern "C" int mmr_bias_grad_finalize(const double* partial, int nblk, int C, float* dbias,
                                       int accumulate, mmr_stream_t stream) {
-  bias_grad_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(partial, nblk, C, dbias,
-                                                                            accumulate);
+  bias_grad_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(partial, nblk, C, dbias,
+                                                                         accumulate);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

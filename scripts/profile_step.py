@@ -1,0 +1,29 @@
+"""One process, three U-Net++ train steps at the bench configuration (batch 16 @ 512x512): the
+command that the ncu launch list / full capture under profiles/ are taken from."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from mmrseg_b200.losses import DiceCrossEntropyLoss
+from mmrseg_b200.models import UnetPlusPlus
+from mmrseg_b200.optim import FusedAdam
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else bench.BATCH_PER_GPU
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+torch.manual_seed(6210)
+model = UnetPlusPlus("resnet18", classes=bench.CLASSES).cuda().train()
+crit = DiceCrossEntropyLoss(0.5)
+opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+x, y = bench.synthetic(n)
+x, y = x.cuda(), y.cuda()
+for i in range(steps):
+    for p in model.parameters():
+        p.grad = None
+    loss = crit(model(x), y)
+    loss.backward()
+    opt.step()
+torch.cuda.synchronize()
+eng = list(model._engines.values())[0]
+print("loss", float(loss), "launch calls fwd/bwd", len(eng.fwd_calls), len(eng.bwd_calls[False]))
