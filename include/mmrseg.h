@@ -99,6 +99,57 @@ int mmr_conv_plan_run(void* plan, int impl, mmr_stream_t stream);
 int mmr_conv_plan_destroy(void* plan);
 
 /* ------------------------------------------------------------------------------------
+ * 3x3 / stride 1 / pad 1 convolution, second kernel generation (csrc/conv_halo.cu): one halo
+ * tile per channel chunk feeds all nine filter taps as shifted shared-memory views, one weight
+ * slot is shared by the tx M-tiles (16 rows x 8 pixels each) of a macro tile, nearest-x2 sources
+ * are replicated by zero-stride TMA dimensions.  Same call sites as mmr_conv_plan_* above: the
+ * Conv2dReLU / BasicBlock / SegmentationHead convolutions of `seg = model(img)` and the
+ * data-gradient half of `loss.backward()`; stride-2, 1x1 and 7x7 convolutions stay on
+ * mmr_conv_plan_*.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* ptr; /* bf16 NHWC, stored resolution (half of the conv's when up == 2) */
+  int32_t C, W, H, N;
+  int32_t up; /* 1, or 2 = nearest x2 (smp DecoderBlock F.interpolate) */
+} MmrHaloSrc;
+
+typedef struct {
+  int32_t nsrc;
+  MmrHaloSrc src[6];   /* channel-concatenated in this order (torch.cat of DecoderBlock.forward) */
+  int32_t N, H, W;     /* resolution of the convolution (= output) */
+  const void* weights; /* bf16, packed by mmr_pack_weights_halo */
+  int32_t cb;          /* channels per K chunk: 64, 32 or 16; divides every source's C */
+  int32_t bn;          /* output channels per N tile: 16/32/64/128/192/256 */
+  int32_t n_ntiles;
+  int32_t tx;          /* M-tiles per macro tile: 1, 2 or 4 */
+  int32_t tps;         /* filter taps per weight slot: 1, 3 or 9; tps*bn <= 256 */
+  int32_t halo_stages, w_slots, acc_bufs, out_stages; /* shared-memory / TMEM pipeline depths */
+  int32_t ngroups;     /* n_ntiles * bn/min(bn,64) store groups (bf16 NHWC mode) */
+  const MmrOutSeg* groups; /* host array: destination tensor, its channel count, first channel */
+  int32_t cout_total;  /* valid output channels */
+  const float* scale;  /* per output channel, may be NULL */
+  const float* bias;
+  const void* residual; /* bf16 NHWC [N][H][W][res_ldc], indexed by output channel, may be NULL */
+  int32_t res_ldc, relu;
+  int32_t out_mode;    /* MMR_OUT_BF16_NHWC, or MMR_OUT_F32_NCHW into out_f32 (one N tile) */
+  void* out_f32;
+  int32_t out_ldc;
+  /* optional [8][2][stats_ld] doubles, ACCUMULATED: per-channel sum and sum of squares of the
+   * stored bf16 outputs (BatchNorm batch statistics); consumed by mmr_bn_finalize(nblk = 8). */
+  double* stats;
+  int32_t stats_ld;
+} MmrHaloConvDesc;
+
+int mmr_halo_conv_plan_create(const MmrHaloConvDesc* desc, void** plan);
+int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream);
+int mmr_halo_conv_plan_destroy(void* plan);
+/* OIHW fp32 3x3 master weights -> bf16 [n_ntiles][nchunks][9][bn][cb].  mode 0 (fprop): rows are
+ * output channels, columns input channels; mode 1 (dgrad): rows are input channels, columns output
+ * channels, taps mirrored.  Out-of-range rows / columns are zero. */
+int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode, int cb, int bn, int n_ntiles,
+                          int nchunks, void* out, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Weight gradient on tcgen05.  Replaces the weight-gradient half of `loss.backward()`
  * (SU/ModelTraining.py:614, ED/Main_MMR_SegModel.py:715) for every nn.Conv2d on the path.
  *

@@ -52,6 +52,28 @@ class MmrConvDesc(C.Structure):
     ]
 
 
+class MmrHaloSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
+                ("N", C.c_int32), ("up", C.c_int32)]
+
+
+class MmrHaloConvDesc(C.Structure):
+    _fields_ = [
+        ("nsrc", C.c_int32), ("src", MmrHaloSrc * 6),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("weights", C.c_void_p), ("cb", C.c_int32), ("bn", C.c_int32), ("n_ntiles", C.c_int32),
+        ("tx", C.c_int32), ("tps", C.c_int32),
+        ("halo_stages", C.c_int32), ("w_slots", C.c_int32), ("acc_bufs", C.c_int32),
+        ("out_stages", C.c_int32),
+        ("ngroups", C.c_int32), ("groups", C.POINTER(MmrOutSeg)),
+        ("cout_total", C.c_int32),
+        ("scale", C.c_void_p), ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("res_ldc", C.c_int32), ("relu", C.c_int32),
+        ("out_mode", C.c_int32), ("out_f32", C.c_void_p), ("out_ldc", C.c_int32),
+        ("stats", C.c_void_p), ("stats_ld", C.c_int32),
+    ]
+
+
 class MmrWgChunk(C.Structure):
     _fields_ = [("src", C.c_int32), ("c0", C.c_int32), ("a", C.c_int32), ("bx", C.c_int32 * 4),
                 ("by", C.c_int32 * 4), ("dst_ci", C.c_int32), ("dst_tap", C.c_int32)]
@@ -95,6 +117,10 @@ SIGNATURES = {
     "mmr_conv_plan_create": (_i, [C.POINTER(MmrConvDesc), C.POINTER(_vp)]),
     "mmr_conv_plan_run": (_i, [_vp, _i, _vp]),
     "mmr_conv_plan_destroy": (_i, [_vp]),
+    "mmr_halo_conv_plan_create": (_i, [C.POINTER(MmrHaloConvDesc), C.POINTER(_vp)]),
+    "mmr_halo_conv_plan_run": (_i, [_vp, _vp]),
+    "mmr_halo_conv_plan_destroy": (_i, [_vp]),
+    "mmr_pack_weights_halo": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_wgrad_plan_create": (_i, [C.POINTER(MmrWgradDesc), C.POINTER(_vp)]),
     "mmr_wgrad_plan_run": (_i, [_vp, _i, _i, _vp]),
     "mmr_wgrad_plan_destroy": (_i, [_vp]),

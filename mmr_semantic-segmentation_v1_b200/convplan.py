@@ -383,3 +383,225 @@ def build_wgrad(dz, sources, ksize, stride, pad, dst, *, cout_gemm=None, dst_cin
     plan.flops = 2 * N * Ho * Wo * cout * taps * cin_total
     plan.n_ctas = n_groups * n_ntiles * n_split
     return plan
+
+
+# ------------------------------------------------------------------------------------------
+# Second kernel generation (csrc/conv_halo.cu): 3x3 / stride 1 / pad 1 convolutions.
+# ------------------------------------------------------------------------------------------
+HALO_SMEM = 227 * 1024 - 256
+
+
+def _mma_clk(bn):
+    """Cycles of one M=128 x bn x K=16 SS-mode tcgen05.mma: tensor-pipe floor bn/2, or the shared
+    memory operand read (4 KB of A + bn*32 B of B at 128 B/clk) — measured, scripts/probe/probe3.cu."""
+    return max(bn / 2.0, (4096 + bn * 32) / 128.0)
+
+
+def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, seg_sizes=None, force=None):
+    """Pick (bn, tx, tps, pipeline depths) for a halo-kernel plan: minimise the modelled time of the
+    whole layer (MMA issue under the shared-memory operand limit, L2 -> shared traffic, exposed
+    epilogue, wave quantisation over the SMs) subject to 227 KB of shared memory and 512 TMEM columns.
+    seg_sizes: channel counts of the destination tensors in concat order (dgrad); an N tile's store
+    groups must not straddle them."""
+    cpad = -(-cout // 16) * 16
+    seg_sizes = seg_sizes or [cpad]
+    best = None
+    for bn in (256, 192, 160, 128, 96, 64, 32, 16):
+        if bn > cpad or cpad % bn:
+            continue
+        sg = 64 if bn % 64 == 0 else (32 if bn % 32 == 0 else 16)
+        if any(s % sg for s in seg_sizes):
+            continue
+        n_nt = cpad // bn
+        gpn = bn // sg
+        if n_nt * gpn > 16:
+            continue
+        for tx in (4, 2, 1):
+            if tx > 1 and 8 * tx > -(-W // 8) * 8:
+                continue
+            pitch = 8 * tx + (4 if any_up else 2)
+            halo_stage = -(-(18 * pitch * cb * 2) // 1024) * 1024
+            for acc_bufs in (2, 1):
+                if acc_bufs * tx * bn > 512:
+                    continue
+                for tps in (9, 3, 1):
+                    if tps * bn > 256:
+                        continue
+                    w_slot = -(-(tps * bn * cb * 2) // 1024) * 1024
+                    for out_stages in ((2, 1) if bf16_out else (0,)):
+                        out_stage = 128 * sg * 2
+                        for halo_stages in (3, 2):
+                            rest = HALO_SMEM - halo_stages * halo_stage - out_stages * out_stage
+                            w_slots = min(8, rest // w_slot)
+                            if w_slots < 2:
+                                continue
+                            cfg = dict(bn=bn, sg=sg, n_ntiles=n_nt, tx=tx, tps=tps, acc_bufs=acc_bufs,
+                                       halo_stages=halo_stages, w_slots=w_slots, out_stages=out_stages)
+                            if force and any(cfg[k] != v for k, v in force.items()):
+                                continue
+                            items = N * (-(-H // 16)) * (-(-W // (8 * tx))) * n_nt
+                            mma = tx * nchunks * 9 * (cb // 16) * _mma_clk(bn)
+                            traffic = nchunks * (18 * pitch * cb * 2 + 9 * bn * cb * 2) / 60.0
+                            epi = tx * gpn * 450.0
+                            per_item = max(mma, traffic) + (epi if acc_bufs == 1 else 0.0)
+                            per_item = max(per_item, epi)
+                            # pipeline depth penalties: a shallow weight ring stalls the issuer
+                            if w_slots * tps < 3:
+                                per_item *= 1.15
+                            if halo_stages < 3 and nchunks > 1:
+                                per_item *= 1.03
+                            if out_stages == 1:
+                                per_item *= 1.02
+                            total = -(-items // n_sms) * per_item
+                            key = (total, -tx, -w_slots)
+                            if best is None or key < best[0]:
+                                best = (key, cfg)
+    if best is None:
+        raise ValueError("no halo-kernel configuration for cout=%d cb=%d" % (cout, cb))
+    cfg = best[1]
+    cfg.update(cb=cb, nchunks=nchunks, cpad=cpad)
+    return cfg
+
+
+def halo_supported(sources, ksize, stride, pad):
+    """3x3 / stride 1 / pad 1; an upsampled source additionally needs H % 16 == 0 (its 16 interior
+    halo rows come from a tensor map that merges batch and rows)."""
+    if not (ksize == 3 and stride == 1 and pad == 1):
+        return False
+    H = sources[0][0].shape[1] * sources[0][1]
+    if any(up == 2 for _, up in sources) and H % 16:
+        return False
+    return all(t.shape[3] % 16 == 0 for t, _ in sources)
+
+
+def halo_packed_weights_numel(cfg):
+    return cfg["n_ntiles"] * cfg["nchunks"] * 9 * cfg["bn"] * cfg["cb"]
+
+
+class HaloPlan:
+    def __init__(self, desc, keep):
+        self._keep = keep
+        self.desc = desc
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mmr_halo_conv_plan_create(C.byref(desc), C.byref(h)))
+        self.handle = h
+        self.flops = 0
+
+    def run(self, stream=None, impl=0):
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(_lib.lib().mmr_halo_conv_plan_run(self.handle, C.c_void_p(s)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().mmr_halo_conv_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def pack_weights_halo(w_oihw, cfg, mode, out=None, stream=None):
+    """fp32 OIHW 3x3 weights -> the packed bf16 layout of cfg (mode 0 fprop, 1 dgrad)."""
+    O, I = w_oihw.shape[0], w_oihw.shape[1]
+    assert w_oihw.dtype == torch.float32 and w_oihw.is_contiguous() and tuple(w_oihw.shape[2:]) == (3, 3)
+    if out is None:
+        out = torch.empty((halo_packed_weights_numel(cfg),), device=w_oihw.device, dtype=torch.bfloat16)
+    s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    _lib.check(_lib.lib().mmr_pack_weights_halo(C.c_void_p(w_oihw.data_ptr()), O, I, mode, cfg["cb"], cfg["bn"],
+                                                cfg["n_ntiles"], cfg["nchunks"], C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(s)))
+    return out
+
+
+def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=None, residual=None,
+               relu=False, out_f32=None, stats=None, stats_ld=0):
+    """sources: [(tensor [N,Hs,Ws,Cs] bf16, up)], packed: bf16 weights from pack_weights_halo,
+    groups: [(dst tensor [N,H,W,ldc] bf16, coff)] one per store group of cfg['sg'] channels (bf16 NHWC
+    mode), or out_f32 = fp32 [N,C,H,W] (head logits)."""
+    from ._lib import MmrHaloConvDesc, MmrHaloSrc
+    d = MmrHaloConvDesc()
+    d.nsrc = len(sources)
+    for i, (t, up) in enumerate(sources):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+        n_, h_, w_, c_ = t.shape
+        assert (n_, h_ * up, w_ * up) == (N, H, W), (t.shape, up, N, H, W)
+        d.src[i] = MmrHaloSrc(t.data_ptr(), c_, w_, h_, n_, up)
+    d.N, d.H, d.W = N, H, W
+    assert packed.numel() == halo_packed_weights_numel(cfg)
+    d.weights = packed.data_ptr()
+    d.cb, d.bn, d.n_ntiles = cfg["cb"], cfg["bn"], cfg["n_ntiles"]
+    d.tx, d.tps = cfg["tx"], cfg["tps"]
+    d.halo_stages, d.w_slots, d.acc_bufs = cfg["halo_stages"], cfg["w_slots"], cfg["acc_bufs"]
+    d.out_stages = max(1, cfg["out_stages"])
+    keep = [sources, packed, scale, bias, residual, stats]
+    if out_f32 is None:
+        segs = (MmrOutSeg * len(groups))(*[MmrOutSeg(t.data_ptr(), t.shape[3], coff) for t, coff in groups])
+        for t, _ in groups:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape[:3]) == (N, H, W)
+        d.ngroups = len(groups)
+        d.groups = C.cast(segs, C.POINTER(MmrOutSeg))
+        d.out_mode = MMR_OUT_BF16_NHWC
+        keep += [segs, [t for t, _ in groups]]
+    else:
+        assert out_f32.dtype == torch.float32 and tuple(out_f32.shape) == (N, out_f32.shape[1], H, W)
+        d.out_mode = MMR_OUT_F32_NCHW
+        d.out_f32 = out_f32.data_ptr()
+        d.out_ldc = out_f32.shape[1]
+        keep.append(out_f32)
+    d.cout_total = cout
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.res_ldc = residual.shape[-1] if residual is not None else 0
+    d.relu = int(bool(relu))
+    d.stats = stats.data_ptr() if stats is not None else None
+    d.stats_ld = stats_ld
+    plan = HaloPlan(d, keep)
+    plan.cfg = cfg
+    return plan
+
+
+def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=None, relu=False,
+                     out_f32=None, stats=None, stats_ld=0, force=None, packed=None):
+    """Forward 3x3 s1 p1 conv over the concatenation of `sources` (see build_fprop)."""
+    N = sources[0][0].shape[0]
+    H = sources[0][0].shape[1] * sources[0][1]
+    W = sources[0][0].shape[2] * sources[0][1]
+    cout, cin = w_oihw.shape[0], w_oihw.shape[1]
+    assert cin == sum(t.shape[3] for t, _ in sources)
+    cb = pick_bk([t.shape[3] for t, _ in sources])
+    any_up = any(up == 2 for _, up in sources)
+    cfg = halo_config(H, W, N, cb, cin // cb, cout, any_up, bf16_out=out_f32 is None, force=force)
+    if packed is None:
+        packed = pack_weights_halo(w_oihw, cfg, 0)
+    groups = None
+    if out_f32 is None:
+        assert out.shape[3] >= cfg["cpad"]
+        groups = [(out, g * cfg["sg"]) for g in range(cfg["cpad"] // cfg["sg"])]
+    plan = build_halo(cfg, sources, packed, groups, N, H, W, cout, scale=scale, bias=bias, residual=residual,
+                      relu=relu, out_f32=out_f32, stats=stats, stats_ld=stats_ld)
+    plan.flops = 2 * N * H * W * cout * 9 * cin
+    plan.packed = packed
+    return plan
+
+
+def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None):
+    """Data gradient of a 3x3 s1 p1 conv: dz [N,H,W,Cz] bf16 (Cz = Cout padded to 16), grads = one bf16
+    tensor [N,H,W,Cs] per source in concat order."""
+    N, H, W, Cz = dz.shape
+    cout, cin = w_oihw.shape[0], w_oihw.shape[1]
+    assert Cz >= cout and Cz % 16 == 0
+    sizes = [g.shape[3] for g in grads]
+    assert sum(sizes) == cin
+    cb = pick_bk([Cz])
+    cfg = halo_config(H, W, N, cb, Cz // cb, cin, False, seg_sizes=sizes, force=force)
+    if packed is None:
+        packed = pack_weights_halo(w_oihw, cfg, 1)
+    groups = []
+    for g in grads:
+        for c in range(0, g.shape[3], cfg["sg"]):
+            groups.append((g, c))
+    plan = build_halo(cfg, [(dz, 1)], packed, groups, N, H, W, cin)
+    plan.flops = 2 * N * H * W * cout * 9 * cin
+    plan.packed = packed
+    return plan

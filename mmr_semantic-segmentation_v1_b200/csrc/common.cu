@@ -59,6 +59,8 @@ static CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
   return CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
+void* get_encode_tiled() { return reinterpret_cast<void*>(get_encode()); }
+
 int encode_act_map(CUtensorMap* out, const MmrSrc& s, int box_c, int box_w, int box_h, int box_n) {
   EncodeTiledFn enc = get_encode();
   MMR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");

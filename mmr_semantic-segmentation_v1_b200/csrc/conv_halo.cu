@@ -1,0 +1,719 @@
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on tcgen05, second kernel generation.
+//
+// What bounds the first generation (conv_gemm.cu) is L2 -> shared-memory traffic: every filter tap
+// re-fetches its activation box and every tile re-fetches its weights.  Here one halo tile
+// (18 rows x (8*TX+2) pixels x one channel chunk) is fetched ONCE per chunk and the nine taps
+// are issued as nine shifted K-major views of it: with SWIZZLE_128B/64B/32B the hardware swizzle is
+// a function of the absolute shared-memory address, so an operand may start at any row of the halo
+// and use any row-group stride (scripts/probe/umma_shift_probe.cu, probe2.cu).  One weight slot is
+// shared by the TX M-tiles of the macro tile.
+//
+//   M tile  = 16 rows x 8 pixels of the output (one 8-pixel row segment per UMMA 8-row group,
+//             row-group stride = halo pitch), TX of them side by side form the macro tile;
+//   N tile  = bn output channels;   K = chunks of cb channels (cb*2 = 128/64/32-byte rows) x 9 taps.
+//
+// A nearest-x2 upsampled source is replicated by the TMA engine itself: tensor maps with byte
+// stride 0 on two extra dimensions (C, dupx, Wl, dupy, rows) land the upsampled halo in shared
+// memory, so the concatenated / upsampled input of smp's DecoderBlock never exists in HBM.
+//
+// Warp roles (one persistent CTA per SM, 256 threads):
+//   warp 0  halo producer (TMA)          warp 1  MMA issuer (one elected lane)
+//   warp 2  TMEM allocator               warp 3  weight producer (TMA)
+//   warps 4-7  epilogue: tcgen05.ld -> scale/bias/residual/ReLU -> bf16 -> swizzled staging tile in
+//              shared memory -> TMA store; per-channel sum / sum of squares of the stored values
+//              (BatchNorm batch statistics) are taken from the staging tile on the way.
+// Accumulators are double-buffered in TMEM when 2*TX*bn <= 512 columns.
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmr {
+
+constexpr int kHaloThreads = 256;
+constexpr int kMaxChunks = 16;
+constexpr int kMaxGroups = 16;
+constexpr int kStatSlots = 8;
+
+struct HaloChunk {
+  int32_t map, map_edge, c0, up;
+};
+
+struct HaloParams {
+  const CUtensorMap* maps;  // device: [source maps ...][weight map][store-group maps ...]
+  HaloChunk chunk[kMaxChunks];
+  int32_t group_coff[kMaxGroups];
+  int nchunks, wmap, smap0;
+  int H, W, N;
+  int TX, tiles_x, tiles_y, n_ntiles, total_items;
+  int rowbytes, KS;
+  int bn, sg, gpn;  // store group = sg channels, gpn groups per N tile
+  int tps, nslots;  // taps per weight slot, slots per chunk
+  int halo_stages, w_slots, acc_bufs, out_stages;
+  uint32_t halo_stage_bytes, w_slot_bytes, out_stage_bytes, w_tx_bytes;
+  uint32_t halo_tx_bytes[2];
+  int pitch[2];
+  uint32_t tmem_cols;
+  const float* scale;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int res_ldc, relu, out_mode;
+  float* out_f32;
+  int out_ldc, cout_total;
+  double* stats;
+  int stats_ld;
+};
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const void* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* map, const void* src, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Shared-memory matrix descriptor split in two words so that the issue loop only adds to the low
+// one: hi = stride-dim offset | version 1 | swizzle; lo = (address >> 4) | LBO field 1.
+__device__ __forceinline__ uint32_t desc_hi32(uint32_t sbo_bytes, uint32_t swz) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
+}
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                          uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\ntcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_lohi_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, 1, 0;\nmov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\ntcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
+      : "memory");
+}
+// All MMAs of one filter tap: TX accumulators x KS 16-channel steps against one weight block.
+template <int KS>
+__device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t a_tap, uint32_t a_hi, uint32_t b_tap,
+                                          uint32_t b_hi, uint32_t idesc, int TX, uint32_t tile_step,
+                                          uint32_t bn, uint32_t first_acc) {
+  uint32_t d = d0, a = a_tap;
+  for (int i = 0; i < TX; ++i, d += bn, a += tile_step) {
+    umma_lohi(d, a, a_hi, b_tap, b_hi, idesc, first_acc);
+#pragma unroll
+    for (int k = 1; k < KS; ++k) umma_lohi_acc(d, a + 2 * k, a_hi, b_tap + 2 * k, b_hi, idesc);
+  }
+}
+
+// XOR applied to the 16-byte chunk index of staging row r (matches TMA SWIZZLE_{128,64,32}B).
+__device__ __forceinline__ uint32_t row_xor(uint32_t r, int rowbytes) {
+  return rowbytes == 128 ? (r & 7u) : (rowbytes == 64 ? ((r >> 1) & 3u) : ((r >> 2) & 1u));
+}
+
+struct ItemCoord {
+  int nt, x0, y0, n;
+};
+__device__ __forceinline__ ItemCoord decode_item(const HaloParams& p, int item) {
+  ItemCoord c;
+  c.nt = item % p.n_ntiles;
+  int t = item / p.n_ntiles;
+  const int tx = t % p.tiles_x;
+  t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  c.n = t / p.tiles_y;
+  c.x0 = tx * 8 * p.TX;
+  c.y0 = ty * 16;
+  return c;
+}
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* halo_base = smem;
+  uint8_t* w_base = halo_base + (size_t)p.halo_stages * p.halo_stage_bytes;
+  uint8_t* out_base = w_base + (size_t)p.w_slots * p.w_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_base + (size_t)p.out_stages * p.out_stage_bytes);
+  uint64_t* halo_full = bars;
+  uint64_t* halo_empty = bars + 4;
+  uint64_t* w_full = bars + 8;
+  uint64_t* w_empty = bars + 16;
+  uint64_t* tmem_full = bars + 24;
+  uint64_t* tmem_empty = bars + 26;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 28);
+
+  // warp index through a shuffle: tells the compiler it is warp-uniform, which keeps the role
+  // loops (descriptor arithmetic, barrier indices) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();  // swizzled operands need the 1024-byte alignment
+    for (int s = 0; s < p.halo_stages; ++s) {
+      mbar_init(&halo_full[s], 1);
+      mbar_init(&halo_empty[s], 1);
+    }
+    for (int s = 0; s < p.w_slots; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- halo producer
+    int hs = 0;
+    uint32_t hph = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const ItemCoord ic = decode_item(p, item);
+      for (int c = 0; c < p.nchunks; ++c) {
+        mbar_wait(&halo_empty[hs], hph ^ 1);
+        if (elect_one()) {
+          const HaloChunk ch = p.chunk[c];
+          uint8_t* dst = halo_base + (size_t)hs * p.halo_stage_bytes;
+          if (!ch.up) {
+            mbar_arrive_expect_tx(&halo_full[hs], p.halo_tx_bytes[0]);
+            tma_load_4d(dst, &p.maps[ch.map], &halo_full[hs], ch.c0, ic.x0 - 1, ic.y0 - 1, ic.n);
+          } else {
+            // halo row 0 = upsampled row y0-1, rows 1..16 = y0..y0+15, row 17 = y0+16;
+            // halo column 0 = upsampled column x0-2 (even, so the pair replication lines up).
+            const int xl = (ic.x0 >> 1) - 1, yl = ic.y0 >> 1;
+            const uint32_t rowb = (uint32_t)p.pitch[1] * p.rowbytes;
+            mbar_arrive_expect_tx(&halo_full[hs], p.halo_tx_bytes[1]);
+            tma_load_5d(dst, &p.maps[ch.map_edge], &halo_full[hs], ch.c0, 0, xl, yl - 1, ic.n);
+            tma_load_5d(dst + rowb, &p.maps[ch.map], &halo_full[hs], ch.c0, 0, xl, 0,
+                        ic.n * (p.H >> 1) + yl);
+            tma_load_5d(dst + 17 * rowb, &p.maps[ch.map_edge], &halo_full[hs], ch.c0, 0, xl, yl + 8,
+                        ic.n);
+          }
+        }
+        __syncwarp();
+        if (++hs == p.halo_stages) {
+          hs = 0;
+          hph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------------------------------------------------------- weight producer
+    int ws = 0;
+    uint32_t wph = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int nt = item % p.n_ntiles;
+      int row = nt * p.nchunks * 9 * p.bn;
+      for (int c = 0; c < p.nchunks; ++c) {
+        for (int s = 0; s < p.nslots; ++s) {
+          mbar_wait(&w_empty[ws], wph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&w_full[ws], p.w_tx_bytes);
+            tma_load_2d(w_base + (size_t)ws * p.w_slot_bytes, &p.maps[p.wmap], &w_full[ws], 0, row);
+          }
+          __syncwarp();
+          row += p.tps * p.bn;
+          if (++ws == p.w_slots) {
+            ws = 0;
+            wph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, p.bn, 0, 0);
+    const uint32_t rb = (uint32_t)p.rowbytes;
+    const uint32_t swz = swizzle_code(p.rowbytes);
+    const uint32_t hiB = desc_hi32(8 * rb, swz);
+    const uint32_t halo0 = smem_u32(halo_base), w0 = smem_u32(w_base);
+    const uint32_t tile_step = (8 * rb) >> 4;  // next M-tile of the macro tile: 8 pixels to the right
+    const uint32_t tap_bytes = (uint32_t)p.bn * rb;
+    int hs = 0, ws = 0, it = 0;
+    uint32_t hph = 0, wph = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      const int buf = it % p.acc_bufs;
+      const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
+      mbar_wait(&tmem_empty[buf], par ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * p.TX * p.bn);
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int up = p.chunk[c].up;
+        const uint32_t pitch = (uint32_t)p.pitch[up];
+        const uint32_t hiA = desc_hi32(pitch * rb, swz);
+        mbar_wait(&halo_full[hs], hph);
+        tc_fence_after();
+        const uint32_t a_stage = ((halo0 + (uint32_t)hs * p.halo_stage_bytes + (up ? rb : 0u)) >> 4) | 0x10000u;
+        int tap = 0;
+        for (int s = 0; s < p.nslots; ++s) {
+          mbar_wait(&w_full[ws], wph);
+          tc_fence_after();
+          const uint32_t b_slot = ((w0 + (uint32_t)ws * p.w_slot_bytes) >> 4) | 0x10000u;
+          for (int tt = 0; tt < p.tps; ++tt, ++tap) {
+            const uint32_t ky = (uint32_t)tap / 3u, kx = (uint32_t)tap - 3u * ky;
+            const uint32_t a_tap = a_stage + (((ky * pitch + kx) * rb) >> 4);
+            const uint32_t b_tap = b_slot + (((uint32_t)tt * tap_bytes) >> 4);
+            const uint32_t first_acc = (uint32_t)((c | tap) != 0);
+            if (elect_one()) {
+              if (p.KS == 4)
+                issue_tap<4>(d0, a_tap, hiA, b_tap, hiB, idesc, p.TX, tile_step, (uint32_t)p.bn, first_acc);
+              else if (p.KS == 2)
+                issue_tap<2>(d0, a_tap, hiA, b_tap, hiB, idesc, p.TX, tile_step, (uint32_t)p.bn, first_acc);
+              else
+                issue_tap<1>(d0, a_tap, hiA, b_tap, hiB, idesc, p.TX, tile_step, (uint32_t)p.bn, first_acc);
+            }
+          }
+          __syncwarp();
+          if (elect_one()) umma_commit(&w_empty[ws]);
+          if (++ws == p.w_slots) {
+            ws = 0;
+            wph ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit(&halo_empty[hs]);
+        if (++hs == p.halo_stages) {
+          hs = 0;
+          hph ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&tmem_full[buf]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp - 4;
+    const int m = q * 32 + lane;  // accumulator row = pixel (h, w) of the M tile
+    const int h = m >> 3, w = m & 7;
+    const int orb = p.sg * 2;  // staging row bytes
+    const uint32_t xr = row_xor((uint32_t)m, orb);
+    const int npairs = p.sg >> 1;
+    const int pr = m % npairs, rg = m / npairs, nrg = 128 / npairs;
+    const int slot = blockIdx.x & (kStatSlots - 1);
+    int it = 0, gcount = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      const ItemCoord ic = decode_item(p, item);
+      const int buf = it % p.acc_bufs;
+      const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
+      mbar_wait(&tmem_full[buf], par);
+      tc_fence_after();
+      const int y = ic.y0 + h;
+      for (int g = 0; g < p.gpn; ++g) {
+        const int ch0 = ic.nt * p.bn + g * p.sg;
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+        for (int i = 0; i < p.TX; ++i) {
+          const int x = ic.x0 + 8 * i + w;
+          const bool valid = y < p.H && x < p.W;
+          const size_t pix = ((size_t)ic.n * p.H + y) * p.W + x;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                 (uint32_t)(buf * p.TX * p.bn + i * p.bn + g * p.sg);
+          uint8_t* stage = out_base;
+          if (p.out_mode == MMR_OUT_BF16_NHWC) stage += (size_t)(gcount % p.out_stages) * p.out_stage_bytes;
+          if (p.out_mode == MMR_OUT_BF16_NHWC && p.out_stages == 1 && gcount > 0) {
+            if (m == 0) bulk_wait_read0();
+            epi_bar();
+          }
+          const bool last = (g == p.gpn - 1) && (i == p.TX - 1);
+          for (int c0 = 0; c0 < p.sg; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+            if (last && c0 + 16 >= p.sg) {
+              // every TMEM read of this item is done: hand the accumulators back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            }
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.scale) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= __ldg(p.scale + min(ch0 + c0 + j, p.cout_total - 1));
+            }
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + min(ch0 + c0 + j, p.cout_total - 1));
+            }
+            if (p.residual && valid) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_ldc + ch0 + c0);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 f = unpack_bf16x2(rr[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.out_mode == MMR_OUT_BF16_NHWC) {
+              uint4 o0, o1;
+              if (valid) {
+                o0.x = pack_bf16x2(v[0], v[1]);
+                o0.y = pack_bf16x2(v[2], v[3]);
+                o0.z = pack_bf16x2(v[4], v[5]);
+                o0.w = pack_bf16x2(v[6], v[7]);
+                o1.x = pack_bf16x2(v[8], v[9]);
+                o1.y = pack_bf16x2(v[10], v[11]);
+                o1.z = pack_bf16x2(v[12], v[13]);
+                o1.w = pack_bf16x2(v[14], v[15]);
+              } else {
+                o0 = make_uint4(0, 0, 0, 0);
+                o1 = o0;
+              }
+              uint8_t* rowp = stage + (size_t)m * orb;
+              const uint32_t j0 = (uint32_t)c0 >> 3;
+              *reinterpret_cast<uint4*>(rowp + ((j0 ^ xr) << 4)) = o0;
+              *reinterpret_cast<uint4*>(rowp + (((j0 + 1) ^ xr) << 4)) = o1;
+            } else if (valid) {
+              const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int ch = ch0 + c0 + j;
+                if (ch < p.cout_total)
+                  p.out_f32[((size_t)ic.n * p.out_ldc + ch) * hw + (size_t)y * p.W + x] = v[j];
+              }
+            }
+          }
+          if (p.out_mode == MMR_OUT_BF16_NHWC) {
+            if (p.out_stages > 1 && m == 0) bulk_wait_read0();  // the other staging buffer is free again
+            fence_proxy_async_smem();
+            epi_bar();
+            if (m == 0) {
+              const int gi = ic.nt * p.gpn + g;
+              tma_store_4d(&p.maps[p.smap0 + gi], stage, p.group_coff[gi], ic.x0 + 8 * i, ic.y0, ic.n);
+              bulk_commit();
+            }
+            if (p.stats) {
+              for (int k = 0; k < npairs; ++k) {
+                const uint32_t r = (uint32_t)(rg + k * nrg);
+                const uint32_t off = r * orb + ((((uint32_t)pr >> 2) ^ row_xor(r, orb)) << 4) + ((uint32_t)pr & 3u) * 4u;
+                const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(stage + off));
+                s1a += f.x;
+                s1b += f.y;
+                s2a += f.x * f.x;
+                s2b += f.y * f.y;
+              }
+            }
+            ++gcount;
+          }
+        }
+        if (p.stats) {
+          const int ch = ch0 + 2 * pr;
+          if (ch < p.cout_total) {
+            double* s = p.stats + (size_t)slot * 2 * p.stats_ld;
+            atomicAdd(s + ch, (double)s1a);
+            atomicAdd(s + p.stats_ld + ch, (double)s2a);
+            if (ch + 1 < p.cout_total) {
+              atomicAdd(s + ch + 1, (double)s1b);
+              atomicAdd(s + p.stats_ld + ch + 1, (double)s2b);
+            }
+          }
+        }
+      }
+    }
+    if (p.out_mode == MMR_OUT_BF16_NHWC && m == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------ weight packing
+// out[((nt*nchunks + c)*9 + tap)*bn + r][k], bf16.  mode 0 (fprop): N index = output channel,
+// K index = concatenated input channel, filter tap as is.  mode 1 (dgrad): N index = input channel,
+// K index = output channel, tap mirrored (the data gradient correlates dz with the flipped filter).
+__global__ void pack_weights_halo_kernel(const float* __restrict__ w, int O, int I, int mode, int cb, int bn,
+                                         int n_ntiles, int nchunks, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)n_ntiles * nchunks * 9 * bn * cb;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    const int k = (int)(t % cb);
+    t /= cb;
+    const int r = (int)(t % bn);
+    t /= bn;
+    const int tap = (int)(t % 9);
+    t /= 9;
+    const int c = (int)(t % nchunks);
+    const int nt = (int)(t / nchunks);
+    const int nidx = nt * bn + r, kidx = c * cb + k;
+    float v = 0.f;
+    if (mode == 0) {
+      if (nidx < O && kidx < I) v = w[((size_t)nidx * I + kidx) * 9 + tap];
+    } else {
+      if (kidx < O && nidx < I) v = w[((size_t)kidx * I + nidx) * 9 + (8 - tap)];
+    }
+    out[idx] = __float2bfloat16(v);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+void* get_encode_tiled();  // common.cu
+
+static int encode_generic(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dims,
+                          const cuuint64_t* strides, const cuuint32_t* box, int inner_bytes, const char* what) {
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(get_encode_tiled());
+  MMR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  MMR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: base must be 16-byte aligned", what);
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                    : CU_TENSOR_MAP_SWIZZLE_32B;
+  for (int i = 0; i < rank; ++i) MMR_REQUIRE(box[i] >= 1 && box[i] <= 256, "%s: box dim %d = %u", what, i, box[i]);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s, rank %d) -> CUresult %d", what, rank, (int)r);
+  return 0;
+}
+
+struct HaloPlan {
+  HaloParams prm;
+  void* dev_blob = nullptr;
+  size_t smem_bytes = 0;
+  int grid = 0;
+};
+
+}  // namespace mmr
+
+using namespace mmr;
+
+extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_plan) {
+  MMR_REQUIRE(d && out_plan, "null argument");
+  MMR_REQUIRE(d->nsrc >= 1 && d->nsrc <= 6, "nsrc must be 1..6, got %d", d->nsrc);
+  MMR_REQUIRE(d->cb == 64 || d->cb == 32 || d->cb == 16, "cb must be 16/32/64, got %d", d->cb);
+  MMR_REQUIRE(d->bn >= 16 && d->bn <= 256 && d->bn % 16 == 0, "bn must be a multiple of 16 in [16,256], got %d",
+              d->bn);
+  MMR_REQUIRE(d->tx == 1 || d->tx == 2 || d->tx == 4, "tx must be 1, 2 or 4, got %d", d->tx);
+  MMR_REQUIRE(d->tps == 1 || d->tps == 3 || d->tps == 9, "tps must be 1, 3 or 9, got %d", d->tps);
+  MMR_REQUIRE(d->tps * d->bn <= 256, "tps*bn must be <= 256 (TMA box rows)");
+  MMR_REQUIRE(d->acc_bufs == 1 || d->acc_bufs == 2, "acc_bufs must be 1 or 2");
+  MMR_REQUIRE(d->acc_bufs * d->tx * d->bn <= 512, "accumulators exceed 512 TMEM columns");
+  MMR_REQUIRE(d->halo_stages >= 1 && d->halo_stages <= 4, "halo_stages must be 1..4");
+  MMR_REQUIRE(d->w_slots >= 1 && d->w_slots <= 8, "w_slots must be 1..8");
+  MMR_REQUIRE(d->out_stages >= 1 && d->out_stages <= 2, "out_stages must be 1 or 2");
+  MMR_REQUIRE(d->n_ntiles >= 1, "need at least one N tile");
+
+  HaloPlan* pl = new HaloPlan();
+  HaloParams& p = pl->prm;
+  memset(&p, 0, sizeof(p));
+  const int rb = d->cb * 2;
+  p.rowbytes = rb;
+  p.KS = rb / 32;
+  p.H = d->H;
+  p.W = d->W;
+  p.N = d->N;
+  p.TX = d->tx;
+  p.bn = d->bn;
+  p.sg = d->bn < 64 ? d->bn : 64;
+  p.gpn = d->bn / p.sg;
+  MMR_REQUIRE(d->bn % p.sg == 0, "bn must be <= 64 or a multiple of 64");
+  p.tps = d->tps;
+  p.nslots = 9 / d->tps;
+  p.n_ntiles = d->n_ntiles;
+  p.tiles_x = (d->W + 8 * d->tx - 1) / (8 * d->tx);
+  p.tiles_y = (d->H + 15) / 16;
+  p.total_items = p.tiles_x * p.tiles_y * d->N * d->n_ntiles;
+  p.halo_stages = d->halo_stages;
+  p.w_slots = d->w_slots;
+  p.acc_bufs = d->acc_bufs;
+  p.out_stages = d->out_stages;
+  p.pitch[0] = 8 * d->tx + 2;
+  p.pitch[1] = 8 * d->tx + 4;
+
+  std::vector<CUtensorMap> maps;
+  int nchunks = 0;
+  bool any_up = false;
+  for (int si = 0; si < d->nsrc; ++si) {
+    const MmrHaloSrc& s = d->src[si];
+    MMR_REQUIRE(s.C % d->cb == 0, "source %d: %d channels are not a multiple of the chunk %d", si, s.C, d->cb);
+    MMR_REQUIRE(s.N == d->N, "source %d: batch mismatch", si);
+    int mi, me = -1;
+    if (s.up == 1) {
+      MMR_REQUIRE(s.H == d->H && s.W == d->W, "source %d: resolution mismatch", si);
+      cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.N};
+      cuuint64_t str[3] = {(cuuint64_t)s.C * 2, (cuuint64_t)s.C * 2 * s.W, (cuuint64_t)s.C * 2 * s.W * s.H};
+      cuuint32_t box[4] = {(cuuint32_t)d->cb, (cuuint32_t)p.pitch[0], 18, 1};
+      maps.emplace_back();
+      mi = (int)maps.size() - 1;
+      if (encode_generic(&maps[mi], s.ptr, 4, dims, str, box, rb, "halo source")) { delete pl; return -1; }
+    } else {
+      MMR_REQUIRE(s.up == 2, "source %d: up must be 1 or 2", si);
+      MMR_REQUIRE(s.H * 2 == d->H && s.W * 2 == d->W, "source %d: upsampled resolution mismatch", si);
+      MMR_REQUIRE(d->H % 16 == 0, "nearest-x2 sources need H %% 16 == 0 (got %d)", d->H);
+      any_up = true;
+      const cuuint32_t bw = (cuuint32_t)(4 * d->tx + 2);
+      {  // 16 interior rows: (C, dupx, Wl, dupy, N*Hl), replication through zero strides
+        cuuint64_t dims[5] = {(cuuint64_t)s.C, 2, (cuuint64_t)s.W, 2, (cuuint64_t)s.N * s.H};
+        cuuint64_t str[4] = {0, (cuuint64_t)s.C * 2, 0, (cuuint64_t)s.C * 2 * s.W};
+        cuuint32_t box[5] = {(cuuint32_t)d->cb, 2, bw, 2, 8};
+        maps.emplace_back();
+        mi = (int)maps.size() - 1;
+        if (encode_generic(&maps[mi], s.ptr, 5, dims, str, box, rb, "upsampled halo body")) { delete pl; return -1; }
+      }
+      {  // top / bottom halo row: (C, dupx, Wl, Hl, N) keeps the per-image zero fill
+        cuuint64_t dims[5] = {(cuuint64_t)s.C, 2, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.N};
+        cuuint64_t str[4] = {0, (cuuint64_t)s.C * 2, (cuuint64_t)s.C * 2 * s.W, (cuuint64_t)s.C * 2 * s.W * s.H};
+        cuuint32_t box[5] = {(cuuint32_t)d->cb, 2, bw, 1, 1};
+        maps.emplace_back();
+        me = (int)maps.size() - 1;
+        if (encode_generic(&maps[me], s.ptr, 5, dims, str, box, rb, "upsampled halo edge")) { delete pl; return -1; }
+      }
+    }
+    for (int c0 = 0; c0 < s.C; c0 += d->cb) {
+      MMR_REQUIRE(nchunks < kMaxChunks, "more than %d channel chunks", kMaxChunks);
+      p.chunk[nchunks++] = HaloChunk{mi, me, c0, s.up == 2 ? 1 : 0};
+    }
+  }
+  p.nchunks = nchunks;
+  {
+    const int64_t rows = (int64_t)d->n_ntiles * nchunks * 9 * d->bn;
+    cuuint64_t dims[2] = {(cuuint64_t)d->cb, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)rb};
+    cuuint32_t box[2] = {(cuuint32_t)d->cb, (cuuint32_t)(d->tps * d->bn)};
+    maps.emplace_back();
+    p.wmap = (int)maps.size() - 1;
+    if (encode_generic(&maps[p.wmap], d->weights, 2, dims, str, box, rb, "packed weights")) { delete pl; return -1; }
+  }
+  p.smap0 = (int)maps.size();
+  p.out_mode = d->out_mode;
+  if (d->out_mode == MMR_OUT_BF16_NHWC) {
+    const int ng = d->n_ntiles * p.gpn;
+    MMR_REQUIRE(d->ngroups == ng && d->groups, "expected %d store groups, got %d", ng, d->ngroups);
+    MMR_REQUIRE(ng <= kMaxGroups, "more than %d store groups", kMaxGroups);
+    for (int g = 0; g < ng; ++g) {
+      const MmrOutSeg& og = d->groups[g];
+      MMR_REQUIRE(og.ldc % 8 == 0 && og.coff % 8 == 0 && og.coff + p.sg <= og.ldc,
+                  "store group %d: channels [%d, %d) do not fit a tensor of %d channels", g, og.coff,
+                  og.coff + p.sg, og.ldc);
+      cuuint64_t dims[4] = {(cuuint64_t)og.ldc, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+      cuuint64_t str[3] = {(cuuint64_t)og.ldc * 2, (cuuint64_t)og.ldc * 2 * d->W,
+                           (cuuint64_t)og.ldc * 2 * d->W * d->H};
+      cuuint32_t box[4] = {(cuuint32_t)p.sg, 8, 16, 1};
+      maps.emplace_back();
+      if (encode_generic(&maps.back(), og.ptr, 4, dims, str, box, p.sg * 2, "store group")) { delete pl; return -1; }
+      p.group_coff[g] = og.coff;
+    }
+  } else {
+    MMR_REQUIRE(d->out_f32 != nullptr && d->n_ntiles == 1, "fp32 NCHW output needs out_f32 and one N tile");
+    MMR_REQUIRE(d->stats == nullptr, "statistics need the bf16 NHWC output mode");
+  }
+  p.halo_tx_bytes[0] = (uint32_t)(18 * p.pitch[0] * rb);
+  p.halo_tx_bytes[1] = (uint32_t)(18 * p.pitch[1] * rb);
+  const uint32_t halo_bytes = p.halo_tx_bytes[any_up ? 1 : 0];
+  p.halo_stage_bytes = (halo_bytes + 1023) / 1024 * 1024;
+  p.w_tx_bytes = (uint32_t)(d->tps * d->bn * rb);
+  p.w_slot_bytes = (p.w_tx_bytes + 1023) / 1024 * 1024;
+  p.out_stage_bytes = d->out_mode == MMR_OUT_BF16_NHWC ? (uint32_t)((128 * p.sg * 2 + 1023) / 1024 * 1024) : 0;
+  if (d->out_mode != MMR_OUT_BF16_NHWC) p.out_stages = 0;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(d->acc_bufs * d->tx * d->bn)) cols <<= 1;
+  p.tmem_cols = cols;
+  size_t smem = (size_t)p.halo_stages * p.halo_stage_bytes + (size_t)p.w_slots * p.w_slot_bytes +
+                (size_t)p.out_stages * p.out_stage_bytes + 256;
+  MMR_REQUIRE(smem <= 227 * 1024, "shared memory plan needs %zu bytes (> 227 KB)", smem);
+  if (smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM: the TMEM allocation assumes it
+  pl->smem_bytes = smem;
+  p.scale = d->scale;
+  p.bias = d->bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  p.res_ldc = d->res_ldc;
+  p.relu = d->relu;
+  p.out_f32 = reinterpret_cast<float*>(d->out_f32);
+  p.out_ldc = d->out_ldc;
+  p.cout_total = d->cout_total;
+  p.stats = d->stats;
+  p.stats_ld = d->stats_ld;
+
+  const size_t maps_bytes = maps.size() * sizeof(CUtensorMap);
+  cudaError_t e = cudaMalloc(&pl->dev_blob, maps_bytes);
+  if (e != cudaSuccess) {
+    delete pl;
+    return fail("cudaMalloc(%zu) failed: %s", maps_bytes, cudaGetErrorString(e));
+  }
+  e = cudaMemcpy(pl->dev_blob, maps.data(), maps_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(pl->dev_blob);
+    delete pl;
+    return fail("cudaMemcpy failed: %s", cudaGetErrorString(e));
+  }
+  p.maps = reinterpret_cast<const CUtensorMap*>(pl->dev_blob);
+  const int sms = num_sms();
+  pl->grid = p.total_items < sms ? p.total_items : sms;
+  e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e != cudaSuccess) cudaGetLastError();  // tolerated on non-sm_100 devices; the launch will report
+  *out_plan = pl;
+  return 0;
+}
+
+extern "C" int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream) {
+  MMR_REQUIRE(plan, "null plan");
+  HaloPlan* pl = reinterpret_cast<HaloPlan*>(plan);
+  if (pl->prm.total_items == 0) return 0;
+  conv_halo_kernel<<<pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream)>>>(pl->prm);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_halo_conv_plan_destroy(void* plan) {
+  if (!plan) return 0;
+  HaloPlan* pl = reinterpret_cast<HaloPlan*>(plan);
+  if (pl->dev_blob) cudaFree(pl->dev_blob);
+  delete pl;
+  return 0;
+}
+
+extern "C" int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode, int cb, int bn, int n_ntiles,
+                                     int nchunks, void* out, mmr_stream_t stream) {
+  MMR_REQUIRE(w_oihw && out, "null argument");
+  MMR_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (fprop) or 1 (dgrad)");
+  const int64_t total = (int64_t)n_ntiles * nchunks * 9 * bn * cb;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  pack_weights_halo_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(
+      w_oihw, O, I, mode, cb, bn, n_ntiles, nchunks, reinterpret_cast<__nv_bfloat16*>(out));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,167 @@
+"""Halo-tile tcgen05 convolution (csrc/conv_halo.cu) against torch.nn.functional.conv2d.
+
+Same comparison as tests/test_conv_gpu.py: F.conv2d in fp32 on the same bf16-rounded operands, so
+what is left is accumulation order and the bf16 rounding of the stored output: tolerance 4e-3 x 8 of
+the output RMS for forward / data-gradient tensors.  BatchNorm statistics taken in the epilogue are
+compared with the sums of the stored bf16 tensor in float64: 1e-5 relative (fp32 partial sums over at
+most a few thousand values, then double atomics).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda") * scale).to(torch.bfloat16)
+
+
+def _ref_conv(sources, w):
+    xs = []
+    for t, up in sources:
+        x = t.float().permute(0, 3, 1, 2)
+        if up == 2:
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+        xs.append(x)
+    return F.conv2d(torch.cat(xs, 1), w.to(torch.bfloat16).float(), None, 1, 1)
+
+
+def _check(out_nhwc, ref_nchw, tol=4e-3):
+    got = out_nhwc.float().permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    err = (got - ref_nchw).abs().max().item()
+    rms = ref_nchw.pow(2).mean().sqrt().item()
+    assert err <= tol * max(rms, 1e-6) * 8, (err, rms)
+
+
+FPROP_CASES = [
+    # (N, H, W, [(C, up)], Cout, force)
+    (2, 16, 16, [(64, 1)], 64, None),
+    (2, 32, 32, [(64, 1)], 64, dict(tx=4)),
+    (2, 32, 32, [(64, 1)], 64, dict(tx=2, acc_bufs=1)),
+    (2, 32, 32, [(64, 1)], 64, dict(tx=1, out_stages=1)),
+    (2, 32, 32, [(64, 1)], 64, dict(tx=2, tps=3)),
+    (2, 16, 16, [(64, 1)], 128, None),
+    (1, 32, 32, [(128, 1)], 256, None),
+    (1, 16, 16, [(512, 1)], 512, None),
+    (1, 32, 32, [(32, 1)], 32, None),
+    (1, 32, 32, [(16, 1)], 16, None),
+    (1, 32, 64, [(16, 1)], 16, dict(tx=4)),
+    (2, 32, 32, [(128, 2), (64, 1)], 64, None),
+    (1, 32, 32, [(64, 2), (64, 1), (64, 1)], 64, dict(tx=4)),
+    (1, 32, 32, [(64, 2), (64, 1), (64, 1)], 64, dict(tx=1)),
+    (2, 64, 64, [(64, 2), (64, 1), (64, 1), (64, 1), (64, 1)], 32, None),
+    (3, 24, 40, [(64, 1)], 64, None),        # ragged tiles in both directions
+    (1, 40, 24, [(64, 1)], 64, dict(tx=2)),
+    (2, 8, 8, [(512, 1)], 512, None),        # image smaller than one tile
+    (1, 64, 64, [(32, 2)], 16, None),
+    (1, 32, 48, [(64, 2)], 64, dict(tx=4)),  # upsampled source, ragged in x
+]
+
+
+@pytest.mark.parametrize("case", FPROP_CASES)
+def test_fprop_matches_conv2d(case):
+    from mmrseg_b200 import convplan
+    N, H, W, srcs, Cout, force = case
+    gen = torch.Generator(device="cuda").manual_seed(6210)
+    sources = [(_mk((N, H // up, W // up, C), gen), up) for C, up in srcs]
+    cin = sum(c for c, _ in srcs)
+    w = torch.randn((Cout, cin, 3, 3), generator=gen, device="cuda") * (1.0 / (cin * 9) ** 0.5)
+    out = torch.full((N, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    plan = convplan.build_fprop_halo(sources, w, out, force=force)
+    plan.run()
+    torch.cuda.synchronize()
+    _check(out, _ref_conv(sources, w))
+    # a second launch on the same plan (persistent state must be clean)
+    out.fill_(float("nan"))
+    plan.run()
+    torch.cuda.synchronize()
+    _check(out, _ref_conv(sources, w))
+
+
+def test_fprop_epilogue_scale_bias_residual_relu():
+    from mmrseg_b200 import convplan
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    N, H, W, C, Cout = 2, 32, 32, 64, 128
+    x = _mk((N, H, W, C), gen)
+    w = torch.randn((Cout, C, 3, 3), generator=gen, device="cuda") / 24
+    scale = torch.rand(Cout, generator=gen, device="cuda") + 0.5
+    bias = torch.randn(Cout, generator=gen, device="cuda")
+    res = _mk((N, H, W, Cout), gen)
+    out = torch.empty((N, H, W, Cout), device="cuda", dtype=torch.bfloat16)
+    plan = convplan.build_fprop_halo([(x, 1)], w, out, scale=scale, bias=bias, residual=res, relu=True)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = _ref_conv([(x, 1)], w) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    ref = torch.relu(ref + res.float().permute(0, 3, 1, 2))
+    _check(out, ref)
+
+
+def test_head_f32_nchw_output():
+    from mmrseg_b200 import convplan
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    N, H, W, C, classes = 2, 32, 40, 16, 2
+    x = _mk((N, H, W, C), gen)
+    w = torch.randn((classes, C, 3, 3), generator=gen, device="cuda") / 12
+    b = torch.randn(classes, generator=gen, device="cuda")
+    out = torch.full((N, classes, H, W), float("nan"), device="cuda")
+    plan = convplan.build_fprop_halo([(x, 1)], w, None, bias=b, out_f32=out)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = _ref_conv([(x, 1)], w) + b.view(1, -1, 1, 1)
+    err = (out - ref).abs().max().item()
+    assert err < 1e-3, err
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (3, 24, 40, 64, 128), (2, 32, 32, 16, 16),
+                                   (2, 32, 32, 32, 32)])
+def test_batchnorm_statistics_from_epilogue(shape):
+    from mmrseg_b200 import convplan
+    N, H, W, C, Cout = shape
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x = _mk((N, H, W, C), gen)
+    w = torch.randn((Cout, C, 3, 3), generator=gen, device="cuda") / (9 * C) ** 0.5
+    out = torch.empty((N, H, W, Cout), device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros((8, 2, Cout), device="cuda", dtype=torch.float64)
+    plan = convplan.build_fprop_halo([(x, 1)], w, out, stats=stats, stats_ld=Cout)
+    plan.run()
+    torch.cuda.synchronize()
+    z = out.double().reshape(-1, Cout)
+    got = stats.sum(0)
+    assert torch.allclose(got[0], z.sum(0), rtol=1e-5, atol=1e-5 * z.abs().sum(0).max().item())
+    assert torch.allclose(got[1], (z * z).sum(0), rtol=1e-5)
+
+
+DGRAD_CASES = [
+    # (N, H, W, [Cs per source], Cout, force)
+    (2, 32, 32, [64], 64, None),
+    (2, 32, 32, [64, 64, 128], 64, None),
+    (1, 32, 32, [64, 64, 64, 64, 64], 32, None),
+    (2, 16, 16, [128], 256, None),
+    (1, 64, 64, [32], 16, None),
+    (1, 32, 32, [16], 16, None),
+    (3, 24, 40, [64, 64], 64, None),
+    (2, 32, 32, [64, 64], 64, dict(bn=128)),
+    (2, 32, 32, [64, 64], 64, dict(bn=64, tx=4)),
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_dgrad_matches_autograd(case):
+    from mmrseg_b200 import convplan
+    N, H, W, sizes, Cout, force = case
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    cin = sum(sizes)
+    cz = -(-Cout // 16) * 16
+    dz = torch.zeros((N, H, W, cz), device="cuda", dtype=torch.bfloat16)
+    dz[..., :Cout] = _mk((N, H, W, Cout), gen)
+    w = torch.randn((Cout, cin, 3, 3), generator=gen, device="cuda") * (1.0 / (Cout * 9) ** 0.5)
+    grads = [torch.full((N, H, W, c), float("nan"), device="cuda", dtype=torch.bfloat16) for c in sizes]
+    plan = convplan.build_dgrad_halo(dz, w, grads, force=force)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((N, cin, H, W), w.to(torch.bfloat16).float(),
+                                     dz[..., :Cout].float().permute(0, 3, 1, 2), stride=1, padding=1)
+    got = torch.cat(grads, 3)
+    _check(got, ref)
