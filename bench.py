@@ -144,13 +144,14 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- our arm
 def kernels_per_call(lib, fn):
-    two = (lib.mmr_wgrad_plan_run, lib.mmr_head_grad_prep)
+    two = (lib.mmr_wgrad_plan_run, lib.mmr_wgrad_halo_plan_run, lib.mmr_head_grad_prep)
     return 2 if any(fn is f for f in two) else 1
 
 
 def conv_kernel_time(eng, n_iter=3):
-    """CUDA-event time of every conv_gemm_tc_kernel launch (fprop + dgrad) of one step, on the
-    launching stream; returns (ms per step spent in that kernel, launches per step)."""
+    """CUDA-event time of every implicit-GEMM conv launch (fprop + dgrad: conv_halo_kernel for the 3x3
+    stride-1 layers, conv_gemm_tc_kernel for the strided / 1x1 / stem ones) of one step, on the
+    launching stream; returns (ms per step spent in those kernels, launches per step)."""
     lib = eng.lib
     stream = torch.cuda.current_stream()
     s = stream.cuda_stream
@@ -161,7 +162,7 @@ def conv_kernel_time(eng, n_iter=3):
         evs = []
         for calls in (eng.repack_calls, eng.fwd_calls, eng.bwd_calls[False]):
             for fn, a in calls:
-                if fn is lib.mmr_conv_plan_run:
+                if fn is lib.mmr_conv_plan_run or fn is lib.mmr_halo_conv_plan_run:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(stream)
                     fn(*a, sp)
@@ -286,7 +287,7 @@ def run_ours(args):
             "e2e": {"value": world * n * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "conv_gemm_tc_kernel (all fprop + dgrad launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel + conv_gemm_tc_kernel (all fprop + dgrad launches of a step)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                          "traffic": traffic, "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
                          "algorithmic_tflop_per_step": conv_flops / 1e12, "peak_source": pk["src"]},

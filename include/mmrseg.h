@@ -119,12 +119,13 @@ typedef struct {
   int32_t N, H, W;     /* resolution of the convolution (= output) */
   const void* weights; /* bf16, packed by mmr_pack_weights_halo */
   int32_t cb;          /* channels per K chunk: 64, 32 or 16; divides every source's C */
-  int32_t bn;          /* output channels per N tile: 16/32/64/128/192/256 */
+  int32_t bn;          /* output channels per N tile: multiple of 16, <= 256 */
+  int32_t sg;          /* channels per store group (one TMA store): 16, 32 or 64, divides bn */
   int32_t n_ntiles;
   int32_t tx;          /* M-tiles per macro tile: 1, 2 or 4 */
   int32_t tps;         /* filter taps per weight slot: 1, 3 or 9; tps*bn <= 256 */
   int32_t halo_stages, w_slots, acc_bufs, out_stages; /* shared-memory / TMEM pipeline depths */
-  int32_t ngroups;     /* n_ntiles * bn/min(bn,64) store groups (bf16 NHWC mode) */
+  int32_t ngroups;     /* n_ntiles * bn/sg store groups (bf16 NHWC mode) */
   const MmrOutSeg* groups; /* host array: destination tensor, its channel count, first channel */
   int32_t cout_total;  /* valid output channels */
   const float* scale;  /* per output channel, may be NULL */
@@ -196,6 +197,35 @@ int mmr_wgrad_plan_create(const MmrWgradDesc* desc, void** plan);
  * accumulate != 0 adds into dst (gradient accumulation, ED/Main_MMR_SegModel.py:718). */
 int mmr_wgrad_plan_run(void* plan, int impl, int accumulate, mmr_stream_t stream);
 int mmr_wgrad_plan_destroy(void* plan);
+
+/* ------------------------------------------------------------------------------------
+ * Weight gradient of a 3x3 / stride 1 / pad 1 convolution, second kernel generation
+ * (csrc/conv_wgrad_halo.cu): the nine shifted activation boxes of a pixel tile are views of one
+ * halo tile; a CTA owns (channel chunk, bn-wide output-channel slice) x a split of the pixel macro
+ * tiles; partials [nchunks*cout_gemm/bn][n_split][A*128][bn] fp32 (A = 5 for cb 64, else 3) are
+ * summed in split order and scattered to the OIHW fp32 gradient.  Same call site as
+ * mmr_wgrad_plan_*: the weight-gradient half of `loss.backward()`.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  MmrHaloSrc dz; /* bf16 NHWC gradient wrt the conv output, C >= cout_gemm, up = 1 */
+  int32_t nsrc;
+  MmrHaloSrc src[6];
+  int32_t N, H, W;
+  int32_t cb;        /* channels per chunk: 64/32/16, divides every source's C */
+  int32_t bn;        /* output channels per CTA slice: 64/32/16 */
+  int32_t cout_gemm; /* dz channels used, multiple of bn */
+  int32_t tx;        /* pixel tiles (16 rows x 8 pixels) per macro tile: 1, 2 or 4 */
+  int32_t n_split;
+  float* partial;    /* mmr_wgrad_halo_partial_floats(...) floats */
+  float* dst;        /* OIHW fp32 [dst_cout][dst_cin][3][3] */
+  int32_t dst_cout, dst_cin;
+} MmrWgradHaloDesc;
+
+int64_t mmr_wgrad_halo_partial_floats(int nchunks, int cb, int bn, int n_ntiles, int n_split);
+int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* desc, void** plan);
+/* accumulate != 0 adds into dst (gradient accumulation). */
+int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t stream);
+int mmr_wgrad_halo_plan_destroy(void* plan);
 
 /* ------------------------------------------------------------------------------------
  * Layout / packing kernels at the boundary of the path.
@@ -331,6 +361,9 @@ int mmr_onehot_to_labels(const void* onehot, int is_float, int N, int C, int H, 
 int mmr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1,
                   float b2, float eps, float wd, float bc1, float bc2, int mode, float grad_scale,
                   mmr_stream_t stream);
+/* cudaMemsetAsync(ptr, 0, nbytes) on the stream: re-arms accumulated buffers (statistics slots of
+ * mmr_halo_conv_plan_*, split-K partials) inside a replayed launch list. */
+int mmr_zero_async(void* ptr, int64_t nbytes, mmr_stream_t stream);
 /* sum of squares of g (double out[0] accumulated) for clip_grad_norm_. */
 int mmr_sumsq(const float* g, int64_t n, double* out, mmr_stream_t stream);
 

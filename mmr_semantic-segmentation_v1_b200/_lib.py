@@ -61,7 +61,7 @@ class MmrHaloConvDesc(C.Structure):
     _fields_ = [
         ("nsrc", C.c_int32), ("src", MmrHaloSrc * 6),
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-        ("weights", C.c_void_p), ("cb", C.c_int32), ("bn", C.c_int32), ("n_ntiles", C.c_int32),
+        ("weights", C.c_void_p), ("cb", C.c_int32), ("bn", C.c_int32), ("sg", C.c_int32), ("n_ntiles", C.c_int32),
         ("tx", C.c_int32), ("tps", C.c_int32),
         ("halo_stages", C.c_int32), ("w_slots", C.c_int32), ("acc_bufs", C.c_int32),
         ("out_stages", C.c_int32),
@@ -71,6 +71,16 @@ class MmrHaloConvDesc(C.Structure):
         ("residual", C.c_void_p), ("res_ldc", C.c_int32), ("relu", C.c_int32),
         ("out_mode", C.c_int32), ("out_f32", C.c_void_p), ("out_ldc", C.c_int32),
         ("stats", C.c_void_p), ("stats_ld", C.c_int32),
+    ]
+
+
+class MmrWgradHaloDesc(C.Structure):
+    _fields_ = [
+        ("dz", MmrHaloSrc), ("nsrc", C.c_int32), ("src", MmrHaloSrc * 6),
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("cb", C.c_int32), ("bn", C.c_int32), ("cout_gemm", C.c_int32), ("tx", C.c_int32),
+        ("n_split", C.c_int32), ("partial", C.c_void_p), ("dst", C.c_void_p),
+        ("dst_cout", C.c_int32), ("dst_cin", C.c_int32),
     ]
 
 
@@ -121,6 +131,10 @@ SIGNATURES = {
     "mmr_halo_conv_plan_run": (_i, [_vp, _vp]),
     "mmr_halo_conv_plan_destroy": (_i, [_vp]),
     "mmr_pack_weights_halo": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_wgrad_halo_partial_floats": (_i64, [_i, _i, _i, _i, _i]),
+    "mmr_wgrad_halo_plan_create": (_i, [C.POINTER(MmrWgradHaloDesc), C.POINTER(_vp)]),
+    "mmr_wgrad_halo_plan_run": (_i, [_vp, _i, _vp]),
+    "mmr_wgrad_halo_plan_destroy": (_i, [_vp]),
     "mmr_wgrad_plan_create": (_i, [C.POINTER(MmrWgradDesc), C.POINTER(_vp)]),
     "mmr_wgrad_plan_run": (_i, [_vp, _i, _i, _vp]),
     "mmr_wgrad_plan_destroy": (_i, [_vp]),
@@ -150,6 +164,7 @@ SIGNATURES = {
     "mmr_confusion_from_preds": (_i, [_vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp]),
     "mmr_onehot_to_labels": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "mmr_zero_async": (_i, [_vp, _i64, _vp]),
     "mmr_sumsq": (_i, [_vp, _i64, _vp, _vp]),
 }
 

@@ -440,18 +440,20 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
                             if force and any(cfg[k] != v for k, v in force.items()):
                                 continue
                             items = N * (-(-H // 16)) * (-(-W // (8 * tx))) * n_nt
-                            mma = tx * nchunks * 9 * (cb // 16) * _mma_clk(bn)
-                            traffic = nchunks * (18 * pitch * cb * 2 + 9 * bn * cb * 2) / 60.0
-                            epi = tx * gpn * 450.0
-                            per_item = max(mma, traffic) + (epi if acc_bufs == 1 else 0.0)
+                            # issue time of the MMAs, plus the waits of the issuer on a chunk / item boundary
+                            mma = tx * nchunks * 9 * (cb // 16) * _mma_clk(bn) + nchunks * (150 + (9 // tps) * 120) + 600
+                            # one elected lane issues every TMA of a ring: ~360 clk per operation
+                            # (scripts/probe/probe4.cu), so few large weight slots beat many small ones
+                            wprod = nchunks * (9 // tps) * 360
+                            hprod = nchunks * (3 if any_up else 1) * 400
+                            traffic = nchunks * (18 * pitch * cb * 2 + 9 * bn * cb * 2) / 70.0
+                            epi = tx * gpn * (450.0 if sg == 64 else 700.0)
+                            per_item = max(mma, wprod, hprod, traffic) + (epi if acc_bufs == 1 else 0.0)
                             per_item = max(per_item, epi)
-                            # pipeline depth penalties: a shallow weight ring stalls the issuer
                             if w_slots * tps < 3:
                                 per_item *= 1.15
-                            if halo_stages < 3 and nchunks > 1:
-                                per_item *= 1.03
                             if out_stages == 1:
-                                per_item *= 1.02
+                                per_item *= 1.01
                             total = -(-items // n_sms) * per_item
                             key = (total, -tx, -w_slots)
                             if best is None or key < best[0]:
@@ -529,7 +531,7 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     d.N, d.H, d.W = N, H, W
     assert packed.numel() == halo_packed_weights_numel(cfg)
     d.weights = packed.data_ptr()
-    d.cb, d.bn, d.n_ntiles = cfg["cb"], cfg["bn"], cfg["n_ntiles"]
+    d.cb, d.bn, d.sg, d.n_ntiles = cfg["cb"], cfg["bn"], cfg["sg"], cfg["n_ntiles"]
     d.tx, d.tps = cfg["tx"], cfg["tps"]
     d.halo_stages, d.w_slots, d.acc_bufs = cfg["halo_stages"], cfg["w_slots"], cfg["acc_bufs"]
     d.out_stages = max(1, cfg["out_stages"])
@@ -561,17 +563,26 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     return plan
 
 
+def fprop_halo_cfg(sources, cout, bf16_out=True, force=None):
+    N = sources[0][0].shape[0]
+    H = sources[0][0].shape[1] * sources[0][1]
+    W = sources[0][0].shape[2] * sources[0][1]
+    cin = sum(t.shape[3] for t, _ in sources)
+    cb = pick_bk([t.shape[3] for t, _ in sources])
+    any_up = any(up == 2 for _, up in sources)
+    return halo_config(H, W, N, cb, cin // cb, cout, any_up, bf16_out=bf16_out, force=force)
+
+
 def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=None, relu=False,
-                     out_f32=None, stats=None, stats_ld=0, force=None, packed=None):
+                     out_f32=None, stats=None, stats_ld=0, force=None, packed=None, cfg=None):
     """Forward 3x3 s1 p1 conv over the concatenation of `sources` (see build_fprop)."""
     N = sources[0][0].shape[0]
     H = sources[0][0].shape[1] * sources[0][1]
     W = sources[0][0].shape[2] * sources[0][1]
     cout, cin = w_oihw.shape[0], w_oihw.shape[1]
     assert cin == sum(t.shape[3] for t, _ in sources)
-    cb = pick_bk([t.shape[3] for t, _ in sources])
-    any_up = any(up == 2 for _, up in sources)
-    cfg = halo_config(H, W, N, cb, cin // cb, cout, any_up, bf16_out=out_f32 is None, force=force)
+    if cfg is None:
+        cfg = fprop_halo_cfg(sources, cout, out_f32 is None, force)
     if packed is None:
         packed = pack_weights_halo(w_oihw, cfg, 0)
     groups = None
@@ -585,7 +596,13 @@ def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=No
     return plan
 
 
-def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None):
+def dgrad_halo_cfg(dz_shape, sizes, force=None):
+    N, H, W, Cz = dz_shape
+    cb = pick_bk([Cz])
+    return halo_config(H, W, N, cb, Cz // cb, sum(sizes), False, seg_sizes=list(sizes), force=force)
+
+
+def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None, cfg=None):
     """Data gradient of a 3x3 s1 p1 conv: dz [N,H,W,Cz] bf16 (Cz = Cout padded to 16), grads = one bf16
     tensor [N,H,W,Cs] per source in concat order."""
     N, H, W, Cz = dz.shape
@@ -593,8 +610,8 @@ def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None):
     assert Cz >= cout and Cz % 16 == 0
     sizes = [g.shape[3] for g in grads]
     assert sum(sizes) == cin
-    cb = pick_bk([Cz])
-    cfg = halo_config(H, W, N, cb, Cz // cb, cin, False, seg_sizes=sizes, force=force)
+    if cfg is None:
+        cfg = dgrad_halo_cfg(dz.shape, sizes, force)
     if packed is None:
         packed = pack_weights_halo(w_oihw, cfg, 1)
     groups = []
@@ -604,4 +621,107 @@ def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None):
     plan = build_halo(cfg, [(dz, 1)], packed, groups, N, H, W, cin)
     plan.flops = 2 * N * H * W * cout * 9 * cin
     plan.packed = packed
+    return plan
+
+
+class WgradHaloPlan:
+    def __init__(self, desc, keep):
+        self._keep = keep
+        self.desc = desc
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mmr_wgrad_halo_plan_create(C.byref(desc), C.byref(h)))
+        self.handle = h
+        self.flops = 0
+
+    def run(self, stream=None, accumulate=False):
+        s = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(_lib.lib().mmr_wgrad_halo_plan_run(self.handle, int(accumulate), C.c_void_p(s)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().mmr_wgrad_halo_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=None, max_partial=None):
+    """(bn, tx, n_split) of a halo weight-gradient plan: slices = nchunks * cout_gemm/bn CTAs wide,
+    split-K so that about two waves of CTAs cover the SMs, tx as large as shared memory allows while
+    keeping at least 3 pipeline stages."""
+    bn = 64 if cout_gemm % 64 == 0 else (32 if cout_gemm % 32 == 0 else 16)
+    n_nt = cout_gemm // bn
+    A = 5 if cb == 64 else 3
+    best = None
+    for tx in (4, 2, 1):
+        if tx > 1 and 8 * tx > -(-W // 8) * 8:
+            continue
+        pitch = 8 * tx + (4 if any_up else 2)
+        stage = -(-(18 * pitch * cb * 2 + 1024) // 1024) * 1024 + -(-(16 * 8 * tx * bn * 2) // 1024) * 1024
+        stages = min(6, (224 * 1024) // stage)
+        if stages < 2:
+            continue
+        tiles = N * (-(-H // 16)) * (-(-W // (8 * tx)))
+        slices = nchunks * n_nt
+        n_split = max(1, min(tiles, round(2 * n_sms / slices))) if slices < 2 * n_sms else 1
+        cfg = dict(bn=bn, tx=tx, n_split=n_split, stages=stages)
+        if force and any(cfg.get(k, v) != v for k, v in force.items() if k != "n_split"):
+            continue
+        if force and "n_split" in force:
+            cfg["n_split"] = n_split = max(1, min(tiles, force["n_split"]))
+        # per-stage issue time vs. the ~2-4 TMA operations one lane issues per stage
+        mma = tx * 8 * A * _mma_clk(bn)
+        prod = (4 if any_up else 2) * 380
+        per_tile = max(mma, prod) / tx
+        waves = -(-(slices * n_split) // n_sms)
+        total = waves * (-(-tiles // n_split)) * tx * per_tile * (1.0 if stages >= 3 else 1.1)
+        key = (total, -tx)
+        if best is None or key < best[0]:
+            best = (key, cfg)
+    if best is None:
+        raise ValueError("no halo wgrad configuration")
+    cfg = best[1]
+    cfg.update(cb=cb, nchunks=nchunks, n_ntiles=n_nt, A=A)
+    if max_partial is not None:
+        per_split = nchunks * n_nt * A * 128 * bn
+        cfg["n_split"] = max(1, min(cfg["n_split"], max_partial // per_split))
+    return cfg
+
+
+def build_wgrad_halo(dz, sources, dst, *, cout_gemm=None, force=None, partial=None, n_sms=148):
+    """Weight gradient of a 3x3 s1 p1 conv.  dz: [N,H,W,Cz] bf16; sources as in build_fprop_halo;
+    dst: fp32 OIHW [Cout][Cin_total][3][3]."""
+    from ._lib import MmrHaloSrc, MmrWgradHaloDesc
+    N, H, W, Cz = dz.shape
+    assert dz.dtype == torch.bfloat16 and dz.is_contiguous()
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape[2:]) == (3, 3)
+    cout, cin = dst.shape[0], dst.shape[1]
+    assert cin == sum(t.shape[3] for t, _ in sources)
+    if cout_gemm is None:
+        cout_gemm = Cz
+    cb = pick_bk([t.shape[3] for t, _ in sources])
+    any_up = any(up == 2 for _, up in sources)
+    cfg = wgrad_halo_config(H, W, N, cb, cin // cb, cout_gemm, any_up, n_sms=n_sms, force=force,
+                            max_partial=partial.numel() if partial is not None else None)
+    need = cfg["nchunks"] * cfg["n_ntiles"] * cfg["n_split"] * cfg["A"] * 128 * cfg["bn"]
+    if partial is None:
+        partial = torch.empty((need,), device=dz.device, dtype=torch.float32)
+    assert partial.dtype == torch.float32 and partial.numel() >= need
+    d = MmrWgradHaloDesc()
+    d.dz = MmrHaloSrc(dz.data_ptr(), Cz, W, H, N, 1)
+    d.nsrc = len(sources)
+    for i, (t, up) in enumerate(sources):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+        n_, h_, w_, c_ = t.shape
+        assert (n_, h_ * up, w_ * up) == (N, H, W)
+        d.src[i] = MmrHaloSrc(t.data_ptr(), c_, w_, h_, n_, up)
+    d.N, d.H, d.W = N, H, W
+    d.cb, d.bn, d.cout_gemm, d.tx, d.n_split = cb, cfg["bn"], cout_gemm, cfg["tx"], cfg["n_split"]
+    d.partial = partial.data_ptr()
+    d.dst = dst.data_ptr()
+    d.dst_cout, d.dst_cin = cout, cin
+    plan = WgradHaloPlan(d, [dz, sources, dst, partial])
+    plan.cfg = cfg
+    plan.flops = 2 * N * H * W * cout * 9 * cin
     return plan

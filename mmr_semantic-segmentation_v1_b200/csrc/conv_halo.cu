@@ -545,9 +545,10 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.N = d->N;
   p.TX = d->tx;
   p.bn = d->bn;
-  p.sg = d->bn < 64 ? d->bn : 64;
+  MMR_REQUIRE((d->sg == 16 || d->sg == 32 || d->sg == 64) && d->bn % d->sg == 0,
+              "sg must be 16/32/64 and divide bn (sg %d, bn %d)", d->sg, d->bn);
+  p.sg = d->sg;
   p.gpn = d->bn / p.sg;
-  MMR_REQUIRE(d->bn % p.sg == 0, "bn must be <= 64 or a multiple of 64");
   p.tps = d->tps;
   p.nslots = 9 / d->tps;
   p.n_ntiles = d->n_ntiles;

@@ -1,0 +1,455 @@
+// Weight gradient of a 3x3 / stride 1 / pad 1 convolution on tcgen05, second kernel generation.
+//
+//   dW[co][ci][ky][kx] = sum over pixels  x[pixel + (ky-1, kx-1)][ci] * dz[pixel][co]
+//
+// As in conv_wgrad.cu both operands are pixel-major in memory (NHWC), i.e. MN-major UMMA operands,
+// and the reduction runs over pixels.  What is new: the nine shifted activation boxes of a pixel
+// tile are nine views of ONE halo tile (18 rows x (8*TX+2) pixels x one channel chunk) fetched by a
+// single TMA box — the first generation issued one small TMA per tap and was bound by the rate at
+// which one thread can issue them.  An M tile of 128 accumulator rows stacks 128/cb views:
+//   cb = 64:  two taps per M tile (second atom = first + LBO), 5 M tiles, the last one half used;
+//   cb = 32 / 16:  one M tile per filter row ky, atoms at 1-pixel steps (kx = 0,1,2 used).
+// A CTA owns one (channel chunk, 64-wide output-channel slice) and a range of pixel macro tiles
+// (split-K); fp32 partials are then summed in split order (deterministic) and scattered to OIHW.
+// Nearest-x2 sources use the zero-stride replicating tensor maps of conv_halo.cu.
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mmr {
+
+constexpr int kWhThreads = 256;
+constexpr int kWhMaxChunks = 16;
+constexpr int kWhMaxStages = 6;
+constexpr int kWhMaxAcc = 5;
+
+struct WhChunk {
+  int32_t map, map_edge, c0, up, ci0;
+};
+
+struct WhParams {
+  const CUtensorMap* maps;  // device: [activation maps ...][dz map]
+  WhChunk chunk[kWhMaxChunks];
+  int nchunks, dzmap;
+  int H, W, N, TX, tiles_x, tiles_y, total_tiles;
+  int cb, xrb, bn, zrb, n_ntiles, A;
+  int n_split, stages;
+  int pitch[2];
+  uint32_t x_tx_bytes[2], x_stage_bytes, z_tx_bytes, stage_bytes, tmem_cols;
+  float* partial;  // [slice][split][A*128][bn]
+  float* dst;
+  int dst_cout, dst_cin;
+};
+
+__device__ __forceinline__ bool wh_elect() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void wh_tma_load_5d(void* dst, const void* map, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void wh_umma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\ntcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t wh_desc_hi(uint32_t sbo_bytes, uint32_t swz) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
+}
+
+// View of accumulator a inside the halo tile: pixel offset of its first atom and the byte distance to
+// the next atom along M (the LBO of the MN-major descriptor).
+__device__ __forceinline__ void wh_view(int cb, int a, int pitch, int& voff_px, int& lbo_px) {
+  if (cb == 64) {
+    const int t0 = 2 * a, t1 = t0 + 1;
+    const int o0 = (t0 / 3) * pitch + (t0 % 3);
+    const int o1 = t1 < 9 ? (t1 / 3) * pitch + (t1 % 3) : o0 + 1;  // tap 9 does not exist: rows discarded
+    voff_px = o0;
+    lbo_px = o1 - o0;
+  } else {
+    voff_px = a * pitch;
+    lbo_px = 1;
+  }
+}
+
+__global__ void __launch_bounds__(kWhThreads, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWhMaxStages;
+  uint64_t* tmem_full = bars + 2 * kWhMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kWhMaxStages + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int slice = blockIdx.x;
+  const int c = slice / p.n_ntiles, nt = slice % p.n_ntiles;
+  const int split = blockIdx.y;
+  const int k_begin = (int)(((long long)p.total_tiles * split) / p.n_split);
+  const int k_end = (int)(((long long)p.total_tiles * (split + 1)) / p.n_split);
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  const WhChunk ch = p.chunk[c];
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    int tx = k_begin % p.tiles_x, t = k_begin / p.tiles_x;
+    int ty = t % p.tiles_y, n = t / p.tiles_y;
+    for (int it = k_begin; it < k_end; ++it) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (wh_elect()) {
+        uint8_t* sx = smem + (size_t)stage * p.stage_bytes;
+        uint8_t* sz = sx + p.x_stage_bytes;
+        const int x0 = tx * 8 * p.TX, y0 = ty * 16;
+        mbar_arrive_expect_tx(&full[stage], p.x_tx_bytes[ch.up] + p.z_tx_bytes);
+        tma_load_4d(sz, &p.maps[p.dzmap], &full[stage], nt * p.bn, x0, y0, n);
+        if (!ch.up) {
+          tma_load_4d(sx, &p.maps[ch.map], &full[stage], ch.c0, x0 - 1, y0 - 1, n);
+        } else {
+          const int xl = (x0 >> 1) - 1, yl = y0 >> 1;
+          const uint32_t rowb = (uint32_t)p.pitch[1] * p.xrb;
+          wh_tma_load_5d(sx, &p.maps[ch.map_edge], &full[stage], ch.c0, 0, xl, yl - 1, n);
+          wh_tma_load_5d(sx + rowb, &p.maps[ch.map], &full[stage], ch.c0, 0, xl, 0, n * (p.H >> 1) + yl);
+          wh_tma_load_5d(sx + 17 * rowb, &p.maps[ch.map_edge], &full[stage], ch.c0, 0, xl, yl + 8, n);
+        }
+      }
+      __syncwarp();
+      if (++tx == p.tiles_x) {
+        tx = 0;
+        if (++ty == p.tiles_y) {
+          ty = 0;
+          ++n;
+        }
+      }
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, p.bn, 1, 1);  // both operands MN-major
+    const uint32_t xrb = (uint32_t)p.xrb, zrb = (uint32_t)p.zrb;
+    const uint32_t pitch = (uint32_t)p.pitch[ch.up];
+    const uint32_t hiA = wh_desc_hi(pitch * xrb, swizzle_code(p.xrb));
+    const uint32_t hiB = wh_desc_hi((uint32_t)(8 * p.TX) * zrb, swizzle_code(p.zrb));
+    uint32_t a_const[kWhMaxAcc];
+#pragma unroll
+    for (int a = 0; a < kWhMaxAcc; ++a) {
+      int voff, lbo;
+      wh_view(p.cb, a, (int)pitch, voff, lbo);
+      a_const[a] = (((uint32_t)voff * xrb) >> 4) + ((((uint32_t)lbo * xrb) >> 4) << 16);
+    }
+    const uint32_t smem0 = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = k_begin; it < k_end; ++it) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t x_base = smem0 + (uint32_t)stage * p.stage_bytes + (ch.up ? xrb : 0u);
+      const uint32_t z_base = smem0 + (uint32_t)stage * p.stage_bytes + p.x_stage_bytes;
+      if (wh_elect()) {
+        for (int i = 0; i < p.TX; ++i) {
+#pragma unroll 2
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t a_k = (x_base + ((uint32_t)(2 * kk) * pitch + 8u * i) * xrb) >> 4;
+            const uint32_t b_k = ((z_base + ((uint32_t)(2 * kk * 8 * p.TX) + 8u * i) * zrb) >> 4) | 0x10000u;
+            const uint32_t acc = (uint32_t)(it != k_begin || i != 0 || kk != 0);
+#pragma unroll
+            for (int a = 0; a < kWhMaxAcc; ++a)
+              if (a < p.A) wh_umma(tmem_base + (uint32_t)(a * p.bn), a_k + a_const[a], hiA, b_k, hiB, idesc, acc);
+          }
+        }
+      }
+      __syncwarp();
+      if (wh_elect()) umma_commit(&empty[stage]);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (wh_elect()) {
+      if (k_end > k_begin)
+        umma_commit(tmem_full);
+      else
+        mbar_arrive(tmem_full);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: fp32 partials
+    const int q = warp - 4;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* base = p.partial + ((size_t)slice * p.n_split + split) * (size_t)(p.A * 128) * p.bn;
+    for (int a = 0; a < p.A; ++a) {
+      float* dst = base + ((size_t)a * 128 + q * 32 + lane) * p.bn;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.bn);
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        if (k_end > k_begin) {
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Sum the split-K partials in split order and scatter into OIHW fp32 (dst[co][ci][tap]).
+__global__ void __launch_bounds__(256)
+wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
+  const size_t per_slice = (size_t)p.A * 128 * p.bn;
+  const size_t total = per_slice * p.nchunks * p.n_ntiles;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % p.bn);
+    size_t t = idx / p.bn;
+    const int r = (int)(t % 128);
+    t /= 128;
+    const int a = (int)(t % p.A);
+    const int slice = (int)(t / p.A);
+    const int c = slice / p.n_ntiles, nt = slice % p.n_ntiles;
+    int tap, chn;
+    if (p.cb == 64) {
+      tap = 2 * a + (r >> 6);
+      chn = r & 63;
+    } else {
+      const int kx = r / p.cb;
+      tap = kx < 3 ? 3 * a + kx : 9;
+      chn = r % p.cb;
+    }
+    const int co = nt * p.bn + n, ci = p.chunk[c].ci0 + chn;
+    if (tap >= 9 || co >= p.dst_cout || ci >= p.dst_cin) continue;
+    const float* src = p.partial + (size_t)slice * p.n_split * per_slice + (idx - (size_t)slice * per_slice);
+    float s = 0.f;
+    for (int k = 0; k < p.n_split; ++k) s += __ldg(src + (size_t)k * per_slice);
+    float* d = p.dst + ((size_t)co * p.dst_cin + ci) * 9 + tap;
+    *d = accumulate ? *d + s : s;
+  }
+}
+
+typedef CUresult (*WhEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+void* get_encode_tiled();  // common.cu
+
+static int wh_encode(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box, int inner_bytes, const char* what) {
+  WhEncodeTiledFn enc = reinterpret_cast<WhEncodeTiledFn>(get_encode_tiled());
+  MMR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  MMR_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "%s: base must be 16-byte aligned", what);
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                    : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MMR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s, rank %d) -> CUresult %d", what, rank, (int)r);
+  return 0;
+}
+
+struct WhPlan {
+  WhParams prm;
+  void* dev_blob = nullptr;
+  size_t smem_bytes = 0;
+};
+
+}  // namespace mmr
+
+using namespace mmr;
+
+extern "C" int64_t mmr_wgrad_halo_partial_floats(int nchunks, int cb, int bn, int n_ntiles, int n_split) {
+  const int A = cb == 64 ? 5 : 3;
+  return (int64_t)nchunks * n_ntiles * n_split * A * 128 * bn;
+}
+
+extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_plan) {
+  MMR_REQUIRE(d && out_plan, "null argument");
+  MMR_REQUIRE(d->nsrc >= 1 && d->nsrc <= 6, "nsrc must be 1..6, got %d", d->nsrc);
+  MMR_REQUIRE(d->cb == 64 || d->cb == 32 || d->cb == 16, "cb must be 16/32/64, got %d", d->cb);
+  MMR_REQUIRE(d->bn == 64 || d->bn == 32 || d->bn == 16, "bn must be 16/32/64, got %d", d->bn);
+  MMR_REQUIRE(d->cout_gemm % d->bn == 0 && d->dz.C >= d->cout_gemm, "cout_gemm %d must be a multiple of bn %d and fit dz (%d)",
+              d->cout_gemm, d->bn, d->dz.C);
+  MMR_REQUIRE(d->tx == 1 || d->tx == 2 || d->tx == 4, "tx must be 1, 2 or 4");
+  MMR_REQUIRE(d->dz.up == 1 && d->dz.H == d->H && d->dz.W == d->W && d->dz.N == d->N, "dz resolution mismatch");
+  MMR_REQUIRE(d->partial && d->dst, "null output");
+  WhPlan* pl = new WhPlan();
+  WhParams& p = pl->prm;
+  memset(&p, 0, sizeof(p));
+  p.H = d->H;
+  p.W = d->W;
+  p.N = d->N;
+  p.TX = d->tx;
+  p.cb = d->cb;
+  p.xrb = d->cb * 2;
+  p.bn = d->bn;
+  p.zrb = d->bn * 2;
+  p.n_ntiles = d->cout_gemm / d->bn;
+  p.A = d->cb == 64 ? 5 : 3;
+  p.tiles_x = (d->W + 8 * d->tx - 1) / (8 * d->tx);
+  p.tiles_y = (d->H + 15) / 16;
+  p.total_tiles = p.tiles_x * p.tiles_y * d->N;
+  p.pitch[0] = 8 * d->tx + 2;
+  p.pitch[1] = 8 * d->tx + 4;
+
+  std::vector<CUtensorMap> maps;
+  int nchunks = 0, ci0 = 0;
+  bool any_up = false;
+  for (int si = 0; si < d->nsrc; ++si) {
+    const MmrHaloSrc& s = d->src[si];
+    MMR_REQUIRE(s.C % d->cb == 0, "source %d: %d channels are not a multiple of the chunk %d", si, s.C, d->cb);
+    MMR_REQUIRE(s.N == d->N, "source %d: batch mismatch", si);
+    int mi, me = -1;
+    if (s.up == 1) {
+      MMR_REQUIRE(s.H == d->H && s.W == d->W, "source %d: resolution mismatch", si);
+      cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.N};
+      cuuint64_t str[3] = {(cuuint64_t)s.C * 2, (cuuint64_t)s.C * 2 * s.W, (cuuint64_t)s.C * 2 * s.W * s.H};
+      cuuint32_t box[4] = {(cuuint32_t)d->cb, (cuuint32_t)p.pitch[0], 18, 1};
+      maps.emplace_back();
+      mi = (int)maps.size() - 1;
+      if (wh_encode(&maps[mi], s.ptr, 4, dims, str, box, p.xrb, "wgrad halo source")) { delete pl; return -1; }
+    } else {
+      MMR_REQUIRE(s.up == 2 && s.H * 2 == d->H && s.W * 2 == d->W, "source %d: upsampled resolution mismatch", si);
+      MMR_REQUIRE(d->H % 16 == 0, "nearest-x2 sources need H %% 16 == 0 (got %d)", d->H);
+      any_up = true;
+      const cuuint32_t bw = (cuuint32_t)(4 * d->tx + 2);
+      {
+        cuuint64_t dims[5] = {(cuuint64_t)s.C, 2, (cuuint64_t)s.W, 2, (cuuint64_t)s.N * s.H};
+        cuuint64_t str[4] = {0, (cuuint64_t)s.C * 2, 0, (cuuint64_t)s.C * 2 * s.W};
+        cuuint32_t box[5] = {(cuuint32_t)d->cb, 2, bw, 2, 8};
+        maps.emplace_back();
+        mi = (int)maps.size() - 1;
+        if (wh_encode(&maps[mi], s.ptr, 5, dims, str, box, p.xrb, "wgrad upsampled body")) { delete pl; return -1; }
+      }
+      {
+        cuuint64_t dims[5] = {(cuuint64_t)s.C, 2, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.N};
+        cuuint64_t str[4] = {0, (cuuint64_t)s.C * 2, (cuuint64_t)s.C * 2 * s.W, (cuuint64_t)s.C * 2 * s.W * s.H};
+        cuuint32_t box[5] = {(cuuint32_t)d->cb, 2, bw, 1, 1};
+        maps.emplace_back();
+        me = (int)maps.size() - 1;
+        if (wh_encode(&maps[me], s.ptr, 5, dims, str, box, p.xrb, "wgrad upsampled edge")) { delete pl; return -1; }
+      }
+    }
+    for (int c0 = 0; c0 < s.C; c0 += d->cb) {
+      MMR_REQUIRE(nchunks < kWhMaxChunks, "more than %d channel chunks", kWhMaxChunks);
+      p.chunk[nchunks++] = WhChunk{mi, me, c0, s.up == 2 ? 1 : 0, ci0 + c0};
+    }
+    ci0 += s.C;
+  }
+  p.nchunks = nchunks;
+  {
+    const MmrHaloSrc& z = d->dz;
+    cuuint64_t dims[4] = {(cuuint64_t)z.C, (cuuint64_t)z.W, (cuuint64_t)z.H, (cuuint64_t)z.N};
+    cuuint64_t str[3] = {(cuuint64_t)z.C * 2, (cuuint64_t)z.C * 2 * z.W, (cuuint64_t)z.C * 2 * z.W * z.H};
+    cuuint32_t box[4] = {(cuuint32_t)d->bn, (cuuint32_t)(8 * d->tx), 16, 1};
+    maps.emplace_back();
+    p.dzmap = (int)maps.size() - 1;
+    if (wh_encode(&maps[p.dzmap], z.ptr, 4, dims, str, box, p.zrb, "wgrad dz")) { delete pl; return -1; }
+  }
+  p.x_tx_bytes[0] = (uint32_t)(18 * p.pitch[0] * p.xrb);
+  p.x_tx_bytes[1] = (uint32_t)(18 * p.pitch[1] * p.xrb);
+  // + 1 KB: the unused atoms of the last M tile read a few pixels past the halo
+  p.x_stage_bytes = (p.x_tx_bytes[any_up ? 1 : 0] + 1024 + 1023) / 1024 * 1024;
+  p.z_tx_bytes = (uint32_t)(16 * 8 * d->tx * p.zrb);
+  p.stage_bytes = p.x_stage_bytes + (p.z_tx_bytes + 1023) / 1024 * 1024;
+  int stages = (int)((224 * 1024) / p.stage_bytes);
+  if (stages > kWhMaxStages) stages = kWhMaxStages;
+  MMR_REQUIRE(stages >= 2, "wgrad: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
+  p.stages = stages;
+  p.n_split = d->n_split < 1 ? 1 : d->n_split;
+  if (p.n_split > p.total_tiles) p.n_split = p.total_tiles;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.A * d->bn)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.partial = d->partial;
+  p.dst = d->dst;
+  p.dst_cout = d->dst_cout;
+  p.dst_cin = d->dst_cin;
+  size_t smem = (size_t)p.stages * p.stage_bytes + 256;
+  if (smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM (TMEM budget)
+  pl->smem_bytes = smem;
+
+  const size_t maps_bytes = maps.size() * sizeof(CUtensorMap);
+  cudaError_t e = cudaMalloc(&pl->dev_blob, maps_bytes);
+  if (e != cudaSuccess) {
+    delete pl;
+    return fail("cudaMalloc(%zu) failed: %s", maps_bytes, cudaGetErrorString(e));
+  }
+  e = cudaMemcpy(pl->dev_blob, maps.data(), maps_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(pl->dev_blob);
+    delete pl;
+    return fail("cudaMemcpy failed: %s", cudaGetErrorString(e));
+  }
+  p.maps = reinterpret_cast<const CUtensorMap*>(pl->dev_blob);
+  e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e != cudaSuccess) cudaGetLastError();
+  *out_plan = pl;
+  return 0;
+}
+
+extern "C" int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t stream) {
+  MMR_REQUIRE(plan, "null plan");
+  WhPlan* pl = reinterpret_cast<WhPlan*>(plan);
+  const WhParams& p = pl->prm;
+  dim3 grid(p.nchunks * p.n_ntiles, p.n_split);
+  conv_wgrad_halo_kernel<<<grid, kWhThreads, pl->smem_bytes, as_stream(stream)>>>(p);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  const size_t total = (size_t)p.A * 128 * p.bn * p.nchunks * p.n_ntiles;
+  int64_t blocks = (int64_t)((total + 255) / 256);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  wgrad_halo_reduce_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(p, accumulate);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_wgrad_halo_plan_destroy(void* plan) {
+  if (!plan) return 0;
+  WhPlan* pl = reinterpret_cast<WhPlan*>(plan);
+  if (pl->dev_blob) cudaFree(pl->dev_blob);
+  delete pl;
+  return 0;
+}

@@ -100,6 +100,12 @@ extern "C" int mmr_adam_step(float* p, const float* g, float* m, float* v, int64
   return 0;
 }
 
+extern "C" int mmr_zero_async(void* ptr, int64_t nbytes, mmr_stream_t stream) {
+  MMR_REQUIRE(ptr != nullptr && nbytes >= 0, "bad argument");
+  MMR_CUDA_CHECK(cudaMemsetAsync(ptr, 0, (size_t)nbytes, as_stream(stream)));
+  return 0;
+}
+
 extern "C" int mmr_sumsq(const float* g, int64_t n, double* out, mmr_stream_t stream) {
   int64_t blocks = (n + kOptThreads * 4 - 1) / (kOptThreads * 4);
   const int64_t cap = (int64_t)num_sms() * 4;

@@ -21,6 +21,7 @@ from ._lib import MMR_OUT_BF16_NHWC, MMR_OUT_F32_NCHW, MmrContrib
 
 STEM_KPAD = 160  # 7*7*3 = 147 im2col columns padded to a multiple of 32
 BN_BLOCKS = 592  # CTAs of the per-channel reductions (4 per SM)
+HALO_STAT_SLOTS = 8  # statistics slots the halo conv kernel accumulates into (csrc/conv_halo.cu)
 WG_PARTIAL_FLOATS = 48 * 1024 * 1024  # 192 MB of fp32 split-K partials
 
 
@@ -104,6 +105,10 @@ class Engine:
         self.n_launch_bwd = 0
         self.weights_dirty = True
         self.param_ready_hooks = []  # (index in bwd call list, [param names]) for DDP overlap
+        self.use_halo = not os.environ.get("MMR_NO_HALO")
+        # BatchNorm statistics taken in the conv epilogues: [unit][slot][2][C] doubles, bump-allocated
+        self.halo_stats = torch.zeros((HALO_STAT_SLOTS * 2 * 16384,), device=device, dtype=torch.float64)
+        self.halo_stats_used = 0
         self.x_in = torch.empty((N, 3, H, W), device=device, dtype=torch.float32)
         self.bn_partial = torch.empty((BN_BLOCKS * 2 * 512,), device=device, dtype=torch.float64)
         # split-K partials of the weight-gradient GEMMs: one buffer, used by one layer at a time
@@ -170,6 +175,10 @@ class Engine:
                 self.out_seeds[op["in"]] = self._bf16(*act.shape, zero=True)
             else:
                 raise ValueError("unknown op %r" % kind)
+        if self.halo_stats_used:
+            # one memset per forward re-arms every statistics slot the conv epilogues accumulate into
+            fc.insert(0, (self.lib.mmr_zero_async, (C.c_void_p(self.halo_stats.data_ptr()),
+                                                     C.c_int64(self.halo_stats_used * 8))))
         self.n_launch_fwd = len(fc) + len(self.repack_calls)
 
     def _bn_state(self, unit, bn_name, Cc):
@@ -177,14 +186,20 @@ class Engine:
         unit.update(bn=bn_name, mean=st[0], invstd=st[1], scale=st[2], shift=st[3], coef=st[4:7])
         self.keep.append(st)
 
-    def _fwd_bn_train(self, unit, z, out, residual, relu):
+    def _fwd_bn_train(self, unit, z, out, residual, relu, stats=None):
+        """stats: per-channel sums already left by the conv epilogue ([8][2][C] doubles), else a
+        separate reduction pass over z."""
         fc = self.fwd_calls
         bn = unit["bn"]
         Cc = z.shape[-1]
         Pn = z.numel() // Cc
         nblk = self._nblk(Pn, Cc)
-        self._rec(fc, "mmr_bn_stats", z, Pn, Cc, self.bn_partial, nblk)
-        self._rec(fc, "mmr_bn_finalize", self.bn_partial, nblk, Pn, Cc, self.P[bn + ".weight"],
+        partial = self.bn_partial
+        if stats is not None:
+            partial, nblk = stats, HALO_STAT_SLOTS
+        else:
+            self._rec(fc, "mmr_bn_stats", z, Pn, Cc, self.bn_partial, nblk)
+        self._rec(fc, "mmr_bn_finalize", partial, nblk, Pn, Cc, self.P[bn + ".weight"],
                   self.P[bn + ".bias"], C.c_float(1e-5), C.c_float(0.1), self.P[bn + ".running_mean"],
                   self.P[bn + ".running_var"], self.P[bn + ".num_batches_tracked"], unit["mean"],
                   unit["invstd"], unit["scale"], unit["shift"])
@@ -262,29 +277,65 @@ class Engine:
         taps = k * k
         unit = {"kind": "head" if head else "conv", "op": op, "cout": cout, "cpad": cpad, "k": k, "s": s,
                 "pad": pad, "srcs": srcs, "in_hw": (Hin, Win)}
-        unit["wf"] = self._bf16(cpad, taps * cin, zero=True)
-        unit["wd"] = self._bf16(cin, taps * cpad, zero=True) if self.training else None
-        self._rec(self.repack_calls, "mmr_repack_weights", w, cout, cin, taps, unit["wf"], taps * cin,
-                  unit["wd"], taps * cpad, cpad)
         sources = [(a.buf, up) for a, up in srcs]
+        halo = self.use_halo and convplan.halo_supported(sources, k, s, pad)
+        unit["halo"] = halo
         res = self.acts[op["res"]] if (not head and op.get("res")) else None
         unit["res"] = res
+        bn_train = bool(not head and op.get("bn") and self.training)
+        if halo:
+            hcfg = convplan.fprop_halo_cfg(sources, cout, bf16_out=not head)
+            unit["wf_h"] = self._bf16(convplan.halo_packed_weights_numel(hcfg))
+            self._rec(self.repack_calls, "mmr_pack_weights_halo", w, cout, cin, 0, hcfg["cb"], hcfg["bn"],
+                      hcfg["n_ntiles"], hcfg["nchunks"], unit["wf_h"])
+            if self.training:
+                dsizes = [a.shape[3] for a, _ in srcs]
+                dcfg = convplan.dgrad_halo_cfg((n, Hin, Win, cpad), dsizes)
+                unit["dcfg"] = dcfg
+                unit["wd_h"] = self._bf16(convplan.halo_packed_weights_numel(dcfg))
+                self._rec(self.repack_calls, "mmr_pack_weights_halo", w, cout, cin, 1, dcfg["cb"], dcfg["bn"],
+                          dcfg["n_ntiles"], dcfg["nchunks"], unit["wd_h"])
+        else:
+            unit["wf"] = self._bf16(cpad, taps * cin, zero=True)
+            unit["wd"] = self._bf16(cin, taps * cpad, zero=True) if self.training else None
+            self._rec(self.repack_calls, "mmr_repack_weights", w, cout, cin, taps, unit["wf"], taps * cin,
+                      unit["wd"], taps * cpad, cpad)
+
+        def fprop(dst, **kw):
+            if halo:
+                plan = convplan.build_fprop_halo(sources, w, dst if not head else None, cfg=hcfg,
+                                                 packed=unit["wf_h"], out_f32=dst if head else None, **kw)
+                fc.append((self.lib.mmr_halo_conv_plan_run, (plan.handle,)))
+            else:
+                kw.pop("stats", None)
+                kw.pop("stats_ld", None)
+                if head:
+                    plan = convplan.build_fprop(sources, unit["wf"], k, 1, pad, dst, out_mode=MMR_OUT_F32_NCHW,
+                                                cout=cout, bn=cpad, **kw)
+                else:
+                    plan = convplan.build_fprop(sources, unit["wf"], k, s, pad, dst, **kw)
+                fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+            return plan
+
         if head:
             out = _Act(op["out"], (n, Ho, Wo, cout))
             out.buf = self._f32(n, cout, Ho, Wo)  # NCHW fp32 logits
-            plan = convplan.build_fprop(sources, unit["wf"], k, 1, pad, out.buf, bias=self.P[op["conv"] + ".bias"],
-                                        out_mode=MMR_OUT_F32_NCHW, cout=cout, bn=cpad)
-            fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+            plan = fprop(out.buf, bias=self.P[op["conv"] + ".bias"])
         else:
             out = _Act(op["out"], (n, Ho, Wo, cout))
             out.buf = self._bf16(*out.shape)
             bias = self.P[op["conv"] + ".bias"] if op.get("bias") else None
-            if op.get("bn") and self.training:
+            if bn_train:
                 unit["z"] = self._bf16(*out.shape)
                 self._bn_state(unit, op["bn"], cout)
-                plan = convplan.build_fprop(sources, unit["wf"], k, s, pad, unit["z"], bias=bias)
-                fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
-                self._fwd_bn_train(unit, unit["z"], out.buf, res.buf if res else None, op["relu"])
+                stats = None
+                if halo:
+                    nst = HALO_STAT_SLOTS * 2 * cout
+                    assert self.halo_stats_used + nst <= self.halo_stats.numel()
+                    stats = self.halo_stats[self.halo_stats_used:self.halo_stats_used + nst]
+                    self.halo_stats_used += nst
+                plan = fprop(unit["z"], bias=bias, stats=stats, stats_ld=cout)
+                self._fwd_bn_train(unit, unit["z"], out.buf, res.buf if res else None, op["relu"], stats)
             else:
                 scale = shift = None
                 if op.get("bn"):
@@ -293,9 +344,8 @@ class Engine:
                     assert bias is None
                 else:
                     shift = bias
-                plan = convplan.build_fprop(sources, unit["wf"], k, s, pad, out.buf, scale=scale, bias=shift,
-                                            residual=res.buf if res else None, relu=op["relu"])
-                fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+                plan = fprop(out.buf, scale=scale, bias=shift, residual=res.buf if res else None,
+                             relu=op["relu"])
         plan.flops = 2 * n * Ho * Wo * cout * taps * cin
         self.conv_flops_fwd += plan.flops
         unit["fplan"] = plan
@@ -436,10 +486,17 @@ class Engine:
                 wplan.flops = 2 * Pn * u["cout"] * 147
             else:
                 sources = [(a.buf, up) for a, up in u["srcs"]]
-                wplan = convplan.build_wgrad(dz, sources, u["k"], u["s"], u["pad"], gw, cout_gemm=cpad,
-                                             n_sms=self.n_sms, partial=self.wg_partial)
+                if u.get("halo"):
+                    wplan = convplan.build_wgrad_halo(dz, sources, gw, cout_gemm=cpad, n_sms=self.n_sms,
+                                                      partial=self.wg_partial)
+                else:
+                    wplan = convplan.build_wgrad(dz, sources, u["k"], u["s"], u["pad"], gw, cout_gemm=cpad,
+                                                 n_sms=self.n_sms, partial=self.wg_partial)
             u["wplan"] = wplan
-        calls.append((self.lib.mmr_wgrad_plan_run, (wplan.handle, 0, acc)))
+        if isinstance(wplan, convplan.WgradHaloPlan):
+            calls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, acc)))
+        else:
+            calls.append((self.lib.mmr_wgrad_plan_run, (wplan.handle, 0, acc)))
         if record_hooks:
             self.conv_flops_bwd += wplan.flops
             names = [conv + ".weight"]
@@ -466,8 +523,16 @@ class Engine:
             raise NotImplementedError("mixed grad / no-grad sources in one conv")
         dplan = u.get("dplan")
         if dplan is None:
-            dplan = u["dplan"] = convplan.build_dgrad(dz, u["wd"], u["k"], u["s"], u["pad"], (Hin, Win), grads)
-        calls.append((self.lib.mmr_conv_plan_run, (dplan.handle, 0)))
+            if u.get("halo"):
+                dplan = convplan.build_dgrad_halo(dz, self.P[conv + ".weight"], grads, cfg=u["dcfg"],
+                                                  packed=u["wd_h"])
+            else:
+                dplan = convplan.build_dgrad(dz, u["wd"], u["k"], u["s"], u["pad"], (Hin, Win), grads)
+            u["dplan"] = dplan
+        if u.get("halo"):
+            calls.append((self.lib.mmr_halo_conv_plan_run, (dplan.handle,)))
+        else:
+            calls.append((self.lib.mmr_conv_plan_run, (dplan.handle, 0)))
         if record_hooks:
             self.conv_flops_bwd += dplan.flops
         for si, (a, up) in enumerate(u["srcs"]):

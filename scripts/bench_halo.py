@@ -51,7 +51,8 @@ def main():
     only = os.environ.get("ONLY")
     gen = torch.Generator(device="cuda").manual_seed(0)
     rows = []
-    tot = {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0]}
+    kinds = os.environ.get("KINDS", "fprop,dgrad,wgrad").split(",")
+    tot = {"fprop": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
     for name, hw, srcs, cout in LAYERS:
         if only and only not in name:
             continue
@@ -60,9 +61,14 @@ def main():
         cin = sum(c for c, _ in srcs)
         w = torch.randn((cout, cin, 3, 3), generator=gen, device="cuda") / (9 * cin) ** 0.5
         out = torch.empty((N, hw, hw, cout), device="cuda", dtype=torch.bfloat16)
-        for kind in ("fprop", "dgrad"):
+        for kind in kinds:
             try:
-                if kind == "fprop":
+                if kind == "wgrad":
+                    cz = -(-cout // 16) * 16
+                    dz = torch.randn((N, hw, hw, cz), generator=gen, device="cuda").to(torch.bfloat16)
+                    dst = torch.empty((cout, cin, 3, 3), device="cuda")
+                    plan = convplan.build_wgrad_halo(dz, sources, dst, force=force)
+                elif kind == "fprop":
                     plan = convplan.build_fprop_halo(sources, w, out, force=force)
                 else:
                     cz = -(-cout // 16) * 16
@@ -75,9 +81,13 @@ def main():
             ms = timeit(plan)
             tf = plan.flops / ms / 1e9
             c = plan.cfg
-            print("%-14s %-5s %7.3f ms %7.1f TFLOP/s  bn=%d tx=%d tps=%d acc=%d hs=%d ws=%d os=%d" % (
-                name, kind, ms, tf, c["bn"], c["tx"], c["tps"], c["acc_bufs"], c["halo_stages"], c["w_slots"],
-                c["out_stages"]), flush=True)
+            if kind == "wgrad":
+                print("%-14s %-5s %7.3f ms %7.1f TFLOP/s  bn=%d tx=%d split=%d stages=%d" % (
+                    name, kind, ms, tf, c["bn"], c["tx"], c["n_split"], c["stages"]), flush=True)
+            else:
+                print("%-14s %-5s %7.3f ms %7.1f TFLOP/s  bn=%d tx=%d tps=%d acc=%d hs=%d ws=%d os=%d" % (
+                    name, kind, ms, tf, c["bn"], c["tx"], c["tps"], c["acc_bufs"], c["halo_stages"],
+                    c["w_slots"], c["out_stages"]), flush=True)
             rows.append((name, kind, plan.flops / 1e9, ms, tf))
             tot[kind][0] += plan.flops / 1e9
             tot[kind][1] += ms

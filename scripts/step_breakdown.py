@@ -1,0 +1,60 @@
+"""CUDA-event time of one U-Net++ train step (batch 16 @ 512x512) per C-ABI entry point."""
+import ctypes as C
+import os
+import sys
+from collections import defaultdict
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from mmrseg_b200.losses import DiceCrossEntropyLoss
+from mmrseg_b200.models import UnetPlusPlus
+from mmrseg_b200.optim import FusedAdam
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else bench.BATCH_PER_GPU
+torch.manual_seed(6210)
+model = UnetPlusPlus("resnet18", classes=bench.CLASSES).cuda().train()
+crit = DiceCrossEntropyLoss(0.5)
+opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+x, y = bench.synthetic(n)
+x, y = x.cuda(), y.cuda()
+for i in range(3):
+    for p in model.parameters():
+        p.grad = None
+    loss = crit(model(x), y)
+    loss.backward()
+    opt.step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(5):
+    for p in model.parameters():
+        p.grad = None
+    loss = crit(model(x), y)
+    loss.backward()
+    opt.step()
+e1.record()
+torch.cuda.synchronize()
+print("step %.3f ms (%.1f img/s)" % (e0.elapsed_time(e1) / 5, n * 5 / e0.elapsed_time(e1) * 1e3))
+eng = list(model._engines.values())[0]
+stream = torch.cuda.current_stream()
+sp = C.c_void_p(stream.cuda_stream)
+agg = defaultdict(lambda: [0.0, 0])
+for it in range(3):
+    evs = []
+    for phase, calls in (("repack", eng.repack_calls), ("fwd", eng.fwd_calls), ("bwd", eng.bwd_calls[False])):
+        for fn, a in calls:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            fn(*a, sp)
+            a1.record(stream)
+            evs.append((phase + ":" + fn.__name__, a0, a1))
+    torch.cuda.synchronize()
+    if it > 0:
+        for name, a0, a1 in evs:
+            agg[name][0] += a0.elapsed_time(a1) / 2
+            agg[name][1] += 0.5
+tot = sum(v[0] for v in agg.values())
+for name, (ms, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    print("%-40s %8.3f ms  %5.1f %%  %4d launches" % (name, ms, 100 * ms / tot, cnt))
+print("sum of per-call times %.3f ms" % tot)

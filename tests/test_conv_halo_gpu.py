@@ -165,3 +165,51 @@ def test_dgrad_matches_autograd(case):
                                      dz[..., :Cout].float().permute(0, 3, 1, 2), stride=1, padding=1)
     got = torch.cat(grads, 3)
     _check(got, ref)
+
+
+WGRAD_CASES = [
+    # (N, H, W, [(C, up)], Cout, force)
+    (2, 32, 32, [(64, 1)], 64, None),
+    (2, 32, 32, [(64, 1)], 64, dict(tx=1, n_split=1)),
+    (2, 32, 32, [(64, 1)], 64, dict(tx=2, n_split=3)),
+    (2, 32, 64, [(16, 1)], 16, dict(tx=4)),
+    (2, 16, 16, [(128, 1)], 128, None),
+    (1, 32, 32, [(128, 2), (64, 1)], 64, None),
+    (2, 32, 32, [(64, 2), (64, 1), (64, 1)], 32, dict(tx=2)),
+    (1, 32, 32, [(32, 1)], 32, None),
+    (1, 64, 64, [(32, 2)], 16, None),
+    (2, 32, 32, [(16, 1)], 16, None),
+    (2, 32, 32, [(16, 1)], 2, None),          # the head: dz padded to 16 channels
+    (3, 24, 40, [(64, 1)], 64, None),         # ragged
+    (1, 8, 8, [(256, 1)], 256, None),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad_matches_autograd(case):
+    from mmrseg_b200 import convplan
+    N, H, W, srcs, Cout, force = case
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    sources = [(_mk((N, H // up, W // up, C), gen), up) for C, up in srcs]
+    cin = sum(c for c, _ in srcs)
+    cz = -(-Cout // 16) * 16
+    dz = torch.zeros((N, H, W, cz), device="cuda", dtype=torch.bfloat16)
+    dz[..., :Cout] = _mk((N, H, W, Cout), gen, 0.1)
+    dst = torch.full((Cout, cin, 3, 3), float("nan"), device="cuda")
+    plan = convplan.build_wgrad_halo(dz, sources, dst, force=force)
+    plan.run()
+    torch.cuda.synchronize()
+    xs = []
+    for t, up in sources:
+        x = t.float().permute(0, 3, 1, 2)
+        xs.append(F.interpolate(x, scale_factor=2, mode="nearest") if up == 2 else x)
+    ref = torch.nn.grad.conv2d_weight(torch.cat(xs, 1), (Cout, cin, 3, 3),
+                                      dz[..., :Cout].float().permute(0, 3, 1, 2), stride=1, padding=1)
+    assert torch.isfinite(dst).all()
+    err = (dst - ref).abs().max().item()
+    rms = ref.pow(2).mean().sqrt().item()
+    assert err <= 2e-3 * max(rms, 1e-6) * 8, (err, rms)
+    # accumulate flag
+    plan.run(accumulate=True)
+    torch.cuda.synchronize()
+    assert (dst - 2 * ref).abs().max().item() <= 4e-3 * max(rms, 1e-6) * 8

@@ -37,7 +37,7 @@ def test_eval_forward_matches_oracle(classes, shape):
 
 
 @pytest.mark.parametrize("encoder,classes,n,hw", [("resnet18", 2, 4, 64), ("resnet18", 10, 2, 128),
-                                                  ("resnet34", 10, 2, 64)])
+                                                  ("resnet34", 10, 2, 128)])
 def test_train_step_matches_oracle(encoder, classes, n, hw):
     from oracle.losses import mixed_loss
     from mmrseg_b200.losses import DiceCrossEntropyLoss
