@@ -4,7 +4,8 @@ from tests.helpers import install_engine_masks, model_pair, rel, synthetic_batch
 from oracle.losses import mixed_loss
 from mmrseg_b200.losses import DiceCrossEntropyLoss
 ref, net = model_pair(10, "resnet34")
-x, y = synthetic_batch(2, 10, 64, 64)
+n, hw = int(sys.argv[1]), int(sys.argv[2])
+x, y = synthetic_batch(n, 10, hw, hw)
 ref.train(); net.train()
 got = net(x.cuda())
 loss = DiceCrossEntropyLoss(0.5)(got, y.cuda()); loss.backward(); torch.cuda.synchronize()
@@ -19,5 +20,5 @@ for name, p in net.named_parameters():
     cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
     rows.append((rel(g, r), cos, name))
 rows.sort(reverse=True)
-for r in rows[:12]: print("%.4f %.4f %s" % r)
+for r in rows[:4]: print("%.4f %.4f %s" % r)
 print("halo units:", sum(1 for u in eng.units if u.get("halo")), "of", len(eng.units))
