@@ -441,7 +441,7 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
                                 continue
                             items = N * (-(-H // 16)) * (-(-W // (8 * tx))) * n_nt
                             # issue time of the MMAs, plus the waits of the issuer on a chunk / item boundary
-                            mma = tx * nchunks * 9 * (cb // 16) * _mma_clk(bn) + nchunks * (150 + (9 // tps) * 120) + 600
+                            mma = tx * nchunks * 9 * (cb // 16) * _mma_clk(bn) + nchunks * (150 + (9 // tps) * 300) + 600
                             # one elected lane issues every TMA of a ring: ~360 clk per operation
                             # (scripts/probe/probe4.cu), so few large weight slots beat many small ones
                             wprod = nchunks * (9 // tps) * 360

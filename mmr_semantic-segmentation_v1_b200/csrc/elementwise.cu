@@ -161,85 +161,245 @@ __global__ void repack_weights_kernel(const float* __restrict__ w, int O, int I,
 
 // ------------------------------------------------------------------ BatchNorm forward
 // Thread layout for [P][C] reductions: tpc = C/8 threads span one pixel row, the block's
-// 256/tpc thread-rows stride over pixels.  Per-thread fp32 partial sums are flushed to double
-// every 16 rows; block partials are written (not atomically added) so results are
-// deterministic.
-template <int MODE>  // 0: stats of z ; 1: bn backward reduce ; 2: plain gradient gather
-__global__ void __launch_bounds__(kEwThreads)
-reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, int C, double* __restrict__ partial,
+// 256/tpc thread-rows stride over pixels, two rows per thread and iteration so that every load of
+// both rows is in flight before the first use.  Per-thread fp32 partial sums are flushed to double
+// every 16 iterations; block partials are written (not atomically added) so results are
+// deterministic.  Row indices are 32-bit (P < 2^31); (n, y, x) is only decomposed when a
+// contribution is 2x2-pooled, with shifts when H and W are powers of two.
+struct RowGeom {
+  int H, W, wshift, hshift;  // shifts are -1 when the extent is not a power of two
+};
+__device__ __forceinline__ void row_to_nyx(const RowGeom& g, uint32_t r, int& n, int& y, int& x) {
+  if (g.wshift >= 0 && g.hshift >= 0) {
+    x = (int)(r & (uint32_t)(g.W - 1));
+    const uint32_t t = r >> g.wshift;
+    y = (int)(t & (uint32_t)(g.H - 1));
+    n = (int)(t >> g.hshift);
+  } else {
+    x = (int)(r % (uint32_t)g.W);
+    const uint32_t t = r / (uint32_t)g.W;
+    y = (int)(t % (uint32_t)g.H);
+    n = (int)(t / (uint32_t)g.H);
+  }
+}
+
+template <bool POOLED>
+__device__ __forceinline__ void gather_row(const ContribList& cl, const RowGeom& geo, uint32_t r, int c, int C,
+                                           float (&g)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  int n = 0, y = 0, x = 0;
+  if (POOLED) row_to_nyx(geo, r, n, y, x);
+  for (int i = 0; i < cl.n; ++i) {
+    float v[8];
+    if (!POOLED || !cl.pool2[i]) {
+      load8(cl.ptr[i] + (size_t)r * C + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += v[j];
+    } else {
+      const int W2 = 2 * geo.W;
+      const __nv_bfloat16* base = cl.ptr[i] + (((size_t)n * (2 * geo.H) + 2 * y) * W2 + 2 * x) * C + c;
+      float v1[8], v2[8], v3[8];
+      load8(base, v);
+      load8(base + C, v1);
+      load8(base + (size_t)W2 * C, v2);
+      load8(base + (size_t)W2 * C + C, v3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += (v[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+  }
+}
+
+// All loads of a row are issued before the first use: the contribution count NC is a template
+// parameter (1..4; 0 = any count, serial gather), so the gather unrolls into independent loads.
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void add8(const uint4& u, float (&g)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    g[2 * j] += f.x;
+    g[2 * j + 1] += f.y;
+  }
+}
+__device__ __forceinline__ void cvt8(const uint4& u, float (&g)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  add8(u, g);
+}
+
+template <int NC, bool POOLED>
+struct RowRaw {
+  uint4 v[NC > 0 ? NC : 1][POOLED ? 4 : 1];
+  uint4 a, z;
+};
+
+template <int MODE, int NC, bool POOLED>
+__device__ __forceinline__ void issue_row(const ContribList& cl, const RowGeom& geo, uint32_t r, int c, int C,
+                                          const __nv_bfloat16* act, const __nv_bfloat16* z,
+                                          RowRaw<NC, POOLED>& raw) {
+  int n = 0, y = 0, x = 0;
+  if (POOLED) row_to_nyx(geo, r, n, y, x);
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    if (POOLED && cl.pool2[i]) {
+      const int W2 = 2 * geo.W;
+      const __nv_bfloat16* base = cl.ptr[i] + (((size_t)n * (2 * geo.H) + 2 * y) * W2 + 2 * x) * C + c;
+      raw.v[i][0] = ldg16(base);
+      raw.v[i][POOLED ? 1 : 0] = ldg16(base + C);
+      raw.v[i][POOLED ? 2 : 0] = ldg16(base + (size_t)W2 * C);
+      raw.v[i][POOLED ? 3 : 0] = ldg16(base + (size_t)W2 * C + C);
+    } else {
+      raw.v[i][0] = ldg16(cl.ptr[i] + (size_t)r * C + c);
+      if (POOLED) raw.v[i][1] = raw.v[i][2] = raw.v[i][3] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  if (act) raw.a = ldg16(act + (size_t)r * C + c);
+  if (MODE == 1) raw.z = ldg16(z + (size_t)r * C + c);
+}
+
+template <int MODE, int NC, bool POOLED>
+__device__ __forceinline__ void finish_row(const ContribList& cl, const RowGeom& geo, uint32_t r, int c, int C,
+                                           const __nv_bfloat16* act, const RowRaw<NC, POOLED>& raw,
+                                           __nv_bfloat16* gout, float (&f1)[8], float (&f2)[8]) {
+  float g[8];
+  if (NC == 0) {
+    gather_row<POOLED>(cl, geo, r, c, C, g);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+#pragma unroll
+      for (int q = 0; q < (POOLED ? 4 : 1); ++q) add8(raw.v[i][q], g);
+    }
+  }
+  if (act) {
+    float a[8];
+    cvt8(raw.a, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+  }
+  store8(gout + (size_t)r * C + c, g);
+  if (MODE == 1) {
+    float zz[8];
+    cvt8(raw.z, zz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f1[j] += g[j], f2[j] += g[j] * zz[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f1[j] += g[j];
+  }
+}
+
+template <int MODE, int NC, bool POOLED>  // MODE 0: stats of z ; 1: bn backward reduce ; 2: plain gradient gather
+__global__ void __launch_bounds__(kEwThreads, 2)
+reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, double* __restrict__ partial,
                    ContribList cl, const __nv_bfloat16* __restrict__ act,
-                   const float* __restrict__ mean, const float* __restrict__ invstd, int H, int W,
+                   const float* __restrict__ mean, const float* __restrict__ invstd, RowGeom geo,
                    __nv_bfloat16* __restrict__ gout) {
+  // double accumulators live in shared memory ([j][thread], conflict-free) so that two CTAs of
+  // 256 threads fit the register file; the loop itself accumulates in fp32 and flushes every 16
+  // iterations.  MODE 1 accumulates sum(g) and sum(g*z); sum(g*xhat) = (sum(g*z) - mean*sum(g))*invstd
+  // is formed in double when the block partial is written.
+  __shared__ double sd1[8 * kEwThreads];
+  __shared__ double sd2[8 * kEwThreads];
   const int tpc = C / 8;
   const int rows_per_iter = kEwThreads / tpc;
   const int cg = threadIdx.x % tpc;
   const int rl = threadIdx.x / tpc;
   const int c = cg * 8;
-  double d1[8], d2[8];
   float f1[8], f2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) d1[j] = d2[j] = 0.0, f1[j] = f2[j] = 0.f;
-  float mu[8], is[8];
-  if (MODE == 1) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mu[j] = __ldg(mean + c + j), is[j] = __ldg(invstd + c + j);
+  for (int j = 0; j < 8; ++j) {
+    f1[j] = f2[j] = 0.f;
+    sd1[j * kEwThreads + threadIdx.x] = 0.0;
+    sd2[j * kEwThreads + threadIdx.x] = 0.0;
   }
   int since_flush = 0;
-  for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + rl; r < P;
-       r += (int64_t)gridDim.x * rows_per_iter) {
+  const uint32_t stride = (uint32_t)gridDim.x * rows_per_iter;
+  constexpr int R = MODE == 0 ? 4 : (POOLED ? 1 : 2);  // rows in flight per thread
+  for (uint32_t r0 = (uint32_t)blockIdx.x * rows_per_iter + rl; r0 < P; r0 += R * stride) {
     if (MODE == 0) {
-      float v[8];
-      load8(z + r * C + c, v);
+      uint4 raw[R];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f1[j] += v[j], f2[j] += v[j] * v[j];
+      for (int k = 0; k < R; ++k)
+        if (r0 + k * stride < P) raw[k] = ldg16(z + (size_t)(r0 + k * stride) * C + c);
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (r0 + k * stride < P) {
+          float v[8];
+          cvt8(raw[k], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f1[j] += v[j], f2[j] += v[j] * v[j];
+        }
     } else {
-      const int x = (int)(r % W);
-      const int y = (int)((r / W) % H);
-      const int n = (int)(r / ((int64_t)W * H));
-      float g[8];
-      gather8(cl, n, y, x, c, H, W, C, g);
-      if (act) {
-        float a[8];
-        load8(act + r * C + c, a);
+      RowRaw<NC, POOLED> raw[R];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
-      }
-      store8(gout + r * C + c, g);
-      if (MODE == 1) {
-        float zz[8];
-        load8(z + r * C + c, zz);
+      for (int k = 0; k < R; ++k)
+        if (r0 + k * stride < P) issue_row<MODE, NC, POOLED>(cl, geo, r0 + k * stride, c, C, act, z, raw[k]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f1[j] += g[j], f2[j] += g[j] * ((zz[j] - mu[j]) * is[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f1[j] += g[j];
-      }
+      for (int k = 0; k < R; ++k)
+        if (r0 + k * stride < P)
+          finish_row<MODE, NC, POOLED>(cl, geo, r0 + k * stride, c, C, act, raw[k], gout, f1, f2);
     }
     if (++since_flush == 16) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d1[j] += f1[j], d2[j] += f2[j], f1[j] = f2[j] = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        sd1[j * kEwThreads + threadIdx.x] += (double)f1[j];
+        sd2[j * kEwThreads + threadIdx.x] += (double)f2[j];
+        f1[j] = f2[j] = 0.f;
+      }
       since_flush = 0;
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) d1[j] += f1[j], d2[j] += f2[j];
-  if (partial == nullptr) return;
-  __shared__ double sh[kEwThreads * 2];  // reused per channel j
   for (int j = 0; j < 8; ++j) {
-    sh[threadIdx.x] = d1[j];
-    sh[kEwThreads + threadIdx.x] = d2[j];
-    __syncthreads();
-    if (rl == 0) {
+    sd1[j * kEwThreads + threadIdx.x] += (double)f1[j];
+    sd2[j * kEwThreads + threadIdx.x] += (double)f2[j];
+  }
+  if (partial == nullptr) return;
+  __syncthreads();
+  if (rl == 0) {
+    for (int j = 0; j < 8; ++j) {
       double s1 = 0.0, s2 = 0.0;
       for (int k = 0; k < rows_per_iter; ++k) {
-        s1 += sh[k * tpc + cg];
-        s2 += sh[kEwThreads + k * tpc + cg];
+        s1 += sd1[j * kEwThreads + k * tpc + cg];
+        s2 += sd2[j * kEwThreads + k * tpc + cg];
       }
+      if (MODE == 1) s2 = (s2 - (double)__ldg(mean + c + j) * s1) * (double)__ldg(invstd + c + j);
       partial[((size_t)blockIdx.x * 2 + 0) * C + c + j] = s1;
       partial[((size_t)blockIdx.x * 2 + 1) * C + c + j] = s2;
     }
-    __syncthreads();
   }
+}
+
+template <int MODE>
+static void launch_reduce(int nblk, cudaStream_t st, const __nv_bfloat16* z, uint32_t P, int C, double* partial,
+                          const ContribList& cl, const __nv_bfloat16* act, const float* mean, const float* invstd,
+                          RowGeom geo, __nv_bfloat16* g) {
+  bool pooled = false;
+  for (int i = 0; i < cl.n; ++i) pooled |= cl.pool2[i] != 0;
+#define MMR_RR(NC, PL) \
+  reduce_rows_kernel<MODE, NC, PL><<<nblk, kEwThreads, 0, st>>>(z, P, C, partial, cl, act, mean, invstd, geo, g)
+  if (pooled) {
+    switch (cl.n) {
+      case 1: MMR_RR(1, true); break;
+      case 2: MMR_RR(2, true); break;
+      case 3: MMR_RR(3, true); break;
+      case 4: MMR_RR(4, true); break;
+      default: MMR_RR(0, true); break;
+    }
+  } else {
+    switch (cl.n) {
+      case 1: MMR_RR(1, false); break;
+      case 2: MMR_RR(2, false); break;
+      case 3: MMR_RR(3, false); break;
+      case 4: MMR_RR(4, false); break;
+      default: MMR_RR(0, false); break;
+    }
+  }
+#undef MMR_RR
 }
 
 // Sum partial[b][which][c] over the nblk blocks for 8 consecutive channels per CTA: 256 threads =
@@ -295,36 +455,64 @@ bn_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P, int 
   }
 }
 
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, int C,
-                                const float* __restrict__ scale, const float* __restrict__ shift,
-                                const __nv_bfloat16* __restrict__ residual, int relu,
-                                __nv_bfloat16* __restrict__ out) {
-  const int groups = C / 8;
+// Streaming apply: when the grid stride is a multiple of C/8 every thread keeps the same channel
+// group for its whole loop (FIXED), so scale / shift are loaded once; two items per iteration.
+template <bool FIXED>
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, int C,
+                const float* __restrict__ scale, const float* __restrict__ shift,
+                const __nv_bfloat16* __restrict__ residual, int relu,
+                __nv_bfloat16* __restrict__ out) {
+  const uint32_t groups = (uint32_t)C / 8;
   const int64_t total = P * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % groups) * 8;
-    float v[8];
-    load8(z + i * 8, v);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float sc[8], sh[8];
+  auto load_affine = [&](int c) {
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c));
     const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
     const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c));
     const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
+    sc[0] = s0.x, sc[1] = s0.y, sc[2] = s0.z, sc[3] = s0.w, sc[4] = s1.x, sc[5] = s1.y, sc[6] = s1.z, sc[7] = s1.w;
+    sh[0] = h0.x, sh[1] = h0.y, sh[2] = h0.z, sh[3] = h0.w, sh[4] = h1.x, sh[5] = h1.y, sh[6] = h1.z, sh[7] = h1.w;
+  };
+  if (FIXED) load_affine((int)((uint64_t)i % groups) * 8);
+  for (; i < total; i += 2 * stride) {
+    const int64_t i1 = i + stride;
+    const bool two = i1 < total;
+    float v0[8], v1[8], r0[8], r1[8];
+    load8(z + i * 8, v0);
+    if (two) load8(z + i1 * 8, v1);
     if (residual) {
-      float r[8];
-      load8(residual + i * 8, r);
+      load8(residual + i * 8, r0);
+      if (two) load8(residual + i1 * 8, r1);
+    }
+    if (!FIXED) load_affine((int)((uint64_t)i % groups) * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    for (int j = 0; j < 8; ++j) v0[j] = v0[j] * sc[j] + sh[j];
+    if (residual) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v0[j] += r0[j];
     }
     if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      for (int j = 0; j < 8; ++j) v0[j] = fmaxf(v0[j], 0.f);
     }
-    store8(out + i * 8, v);
+    store8(out + i * 8, v0);
+    if (two) {
+      if (!FIXED) load_affine((int)((uint64_t)i1 % groups) * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v1[j] = v1[j] * sc[j] + sh[j];
+      if (residual) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v1[j] += r1[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v1[j] = fmaxf(v1[j], 0.f);
+      }
+      store8(out + i1 * 8, v1);
+    }
   }
 }
 
@@ -348,25 +536,48 @@ bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P, 
   coef[2 * C + c] = (float)(-gi * s1 / (double)P);
 }
 
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g,
-                                    const __nv_bfloat16* __restrict__ z,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ coef, int64_t P, int C,
-                                    __nv_bfloat16* __restrict__ dz) {
-  const int groups = C / 8;
+// dz = cA*g + cB*xhat + cC with xhat = (z-mean)*invstd, folded per channel into
+// dz = cA*g + p*z + q,  p = cB*invstd,  q = cC - cB*mean*invstd  (loaded once per thread when FIXED).
+template <bool FIXED>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ z,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ coef, int64_t P, int C, __nv_bfloat16* __restrict__ dz) {
+  const uint32_t groups = (uint32_t)C / 8;
   const int64_t total = P * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % groups) * 8;
-    float gv[8], zv[8], o[8];
-    load8(g + i * 8, gv);
-    load8(z + i * 8, zv);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float ca[8], pz[8], q[8];
+  auto load_coef = [&](int c) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (zv[j] - __ldg(mean + c + j)) * __ldg(invstd + c + j);
-      o[j] = __ldg(coef + c + j) * gv[j] + __ldg(coef + C + c + j) * xh + __ldg(coef + 2 * C + c + j);
+      const float is = __ldg(invstd + c + j), cb = __ldg(coef + C + c + j);
+      ca[j] = __ldg(coef + c + j);
+      pz[j] = cb * is;
+      q[j] = __ldg(coef + 2 * C + c + j) - cb * __ldg(mean + c + j) * is;
     }
+  };
+  if (FIXED) load_coef((int)((uint64_t)i % groups) * 8);
+  for (; i < total; i += 2 * stride) {
+    const int64_t i1 = i + stride;
+    const bool two = i1 < total;
+    float g0[8], z0[8], g1[8], z1[8], o[8];
+    load8(g + i * 8, g0);
+    load8(z + i * 8, z0);
+    if (two) {
+      load8(g + i1 * 8, g1);
+      load8(z + i1 * 8, z1);
+    }
+    if (!FIXED) load_coef((int)((uint64_t)i % groups) * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = ca[j] * g0[j] + pz[j] * z0[j] + q[j];
     store8(dz + i * 8, o);
+    if (two) {
+      if (!FIXED) load_coef((int)((uint64_t)i1 % groups) * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = ca[j] * g1[j] + pz[j] * z1[j] + q[j];
+      store8(dz + i1 * 8, o);
+    }
   }
 }
 
@@ -548,6 +759,14 @@ extern "C" int mmr_repack_weights(const float* w, int O, int I, int taps, void* 
   return 0;
 }
 
+static RowGeom make_geom(int H, int W) {
+  auto lg = [](int v) {
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return (1 << s) == v ? s : -1;
+  };
+  return RowGeom{H, W, lg(W), lg(H)};
+}
 static int check_rows_layout(int C) {
   MMR_REQUIRE(C % 8 == 0 && C >= 8 && C <= 2048 && (kEwThreads % (C / 8)) == 0,
               "channel count %d unsupported by the row-reduction layout (need C/8 | 256)", C);
@@ -559,9 +778,10 @@ extern "C" int mmr_bn_stats(const void* z, int64_t P, int C, double* partial, in
   if (check_rows_layout(C)) return -1;
   ContribList cl;
   fill_contribs(cl, nullptr, 0);
-  reduce_rows_kernel<0><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(z), P, C, partial, cl, nullptr, nullptr, nullptr, 1, 1,
-      nullptr);
+  MMR_REQUIRE(P < ((int64_t)1 << 31), "row count must be below 2^31");
+  reduce_rows_kernel<0, 0, false><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, partial, cl, nullptr, nullptr, nullptr,
+      make_geom(1, 1), nullptr);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -580,9 +800,15 @@ extern "C" int mmr_bn_finalize(const double* partial, int nblk, int64_t P, int C
 extern "C" int mmr_bn_apply(const void* z, int64_t P, int C, const float* scale, const float* shift,
                             const void* residual, int relu, void* out, mmr_stream_t stream) {
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
-  bn_apply_kernel<<<ew_blocks(P * (C / 8), 16), kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
-      reinterpret_cast<const __nv_bfloat16*>(residual), relu, reinterpret_cast<__nv_bfloat16*>(out));
+  const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
+  if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
+    bn_apply_kernel<true><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
+        reinterpret_cast<const __nv_bfloat16*>(residual), relu, reinterpret_cast<__nv_bfloat16*>(out));
+  else
+    bn_apply_kernel<false><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
+        reinterpret_cast<const __nv_bfloat16*>(residual), relu, reinterpret_cast<__nv_bfloat16*>(out));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -594,10 +820,11 @@ extern "C" int mmr_bn_bwd_reduce(const MmrContrib* contribs, int ncontrib, const
   if (check_rows_layout(C)) return -1;
   ContribList cl;
   if (fill_contribs(cl, contribs, ncontrib)) return -1;
-  reduce_rows_kernel<1><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(z), (int64_t)N * H * W, C, partial, cl,
-      reinterpret_cast<const __nv_bfloat16*>(act), mean, invstd, H, W,
-      reinterpret_cast<__nv_bfloat16*>(g));
+  const int64_t P = (int64_t)N * H * W;
+  MMR_REQUIRE(P < ((int64_t)1 << 31), "row count must be below 2^31");
+  launch_reduce<1>(nblk, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, partial, cl,
+                   reinterpret_cast<const __nv_bfloat16*>(act), mean, invstd, make_geom(H, W),
+                   reinterpret_cast<__nv_bfloat16*>(g));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -614,9 +841,15 @@ extern "C" int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, i
 extern "C" int mmr_bn_bwd_apply(const void* g, const void* z, const float* mean, const float* invstd,
                                 const float* coef, int64_t P, int C, void* dz, mmr_stream_t stream) {
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
-  bn_bwd_apply_kernel<<<ew_blocks(P * (C / 8), 16), kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean,
-      invstd, coef, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
+  const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
+  if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
+    bn_bwd_apply_kernel<true><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd,
+        coef, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
+  else
+    bn_bwd_apply_kernel<false><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd,
+        coef, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -627,9 +860,11 @@ extern "C" int mmr_grad_gather(const MmrContrib* contribs, int ncontrib, const v
   if (check_rows_layout(C)) return -1;
   ContribList cl;
   if (fill_contribs(cl, contribs, ncontrib)) return -1;
-  reduce_rows_kernel<2><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
-      nullptr, (int64_t)N * H * W, C, partial, cl, reinterpret_cast<const __nv_bfloat16*>(act),
-      nullptr, nullptr, H, W, reinterpret_cast<__nv_bfloat16*>(g));
+  const int64_t P = (int64_t)N * H * W;
+  MMR_REQUIRE(P < ((int64_t)1 << 31), "row count must be below 2^31");
+  launch_reduce<2>(nblk, as_stream(stream), nullptr, (uint32_t)P, C, partial, cl,
+                   reinterpret_cast<const __nv_bfloat16*>(act), nullptr, nullptr, make_geom(H, W),
+                   reinterpret_cast<__nv_bfloat16*>(g));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -20,7 +20,7 @@ from . import _lib, convplan
 from ._lib import MMR_OUT_BF16_NHWC, MMR_OUT_F32_NCHW, MmrContrib
 
 STEM_KPAD = 160  # 7*7*3 = 147 im2col columns padded to a multiple of 32
-BN_BLOCKS = 592  # CTAs of the per-channel reductions (4 per SM)
+BN_BLOCKS = 296  # CTAs of the per-channel reductions: 2 per SM, all co-resident (one wave)
 HALO_STAT_SLOTS = 8  # statistics slots the halo conv kernel accumulates into (csrc/conv_halo.cu)
 WG_PARTIAL_FLOATS = 48 * 1024 * 1024  # 192 MB of fp32 split-K partials
 

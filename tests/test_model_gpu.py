@@ -12,7 +12,8 @@ Stated tolerances (relative Frobenius error unless noted), measured values in DE
   BatchNorm running statistics                 <= 1e-2, num_batches_tracked exact
 The resnet34 encoder doubles the number of bf16 storage points in front of layer4 (33 encoder
 convs instead of 17); measured worst case there is 13-17 % / cosine 0.986-0.991 on layer4's BN
-weights (logits 6.8-8.2 %), so that case states 1e-1 (logits), 2e-1 and cosine >= 0.98.
+weights (logits 6.8-8.2 %), so that case states 1e-1 (logits), 2e-1 and cosine >= 0.98, and 5e-2
+on the running statistics (layer4 normalises over 16 samples per channel there).
 """
 import pytest
 import torch
@@ -56,7 +57,8 @@ def test_train_step_matches_oracle(encoder, classes, n, hw):
     want = ref(x)
     loss_ref = mixed_loss(want, y, 0.5)
     loss_ref.backward()
-    tol_logits, tol_grad, tol_cos = (8e-2, 1.2e-1, 0.99) if encoder == "resnet18" else (1e-1, 2e-1, 0.98)
+    tol_logits, tol_grad, tol_cos, tol_buf = (8e-2, 1.2e-1, 0.99, 1e-2) if encoder == "resnet18" else \
+        (1e-1, 2e-1, 0.98, 5e-2)
     assert rel(got.detach().cpu(), want.detach()) <= tol_logits, rel(got.detach().cpu(), want.detach())
     assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item())
     ref_params = dict(ref.named_parameters())
@@ -70,7 +72,7 @@ def test_train_step_matches_oracle(encoder, classes, n, hw):
         if name.endswith("num_batches_tracked"):
             assert int(b) == int(ref_bufs[name]), name
         else:
-            assert rel(b.cpu().float(), ref_bufs[name].float()) <= 1e-2, name
+            assert rel(b.cpu().float(), ref_bufs[name].float()) <= tol_buf, (name, rel(b.cpu().float(), ref_bufs[name].float()))
 
 
 def test_gradient_accumulation_and_zero_grad():
