@@ -125,6 +125,7 @@ typedef struct {
   int32_t tx;          /* M-tiles per macro tile: 1, 2 or 4 */
   int32_t tps;         /* filter taps per weight slot: 1, 3 or 9; tps*bn <= 256 */
   int32_t halo_stages, w_slots, acc_bufs, out_stages; /* shared-memory / TMEM pipeline depths */
+  int32_t direct_store; /* 1: store bf16 tiles from registers (narrow groups) instead of TMA */
   int32_t ngroups;     /* n_ntiles * bn/sg store groups (bf16 NHWC mode) */
   const MmrOutSeg* groups; /* host array: destination tensor, its channel count, first channel */
   int32_t cout_total;  /* valid output channels */
@@ -149,6 +150,14 @@ int mmr_halo_conv_plan_destroy(void* plan);
  * channels, taps mirrored.  Out-of-range rows / columns are zero. */
 int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode, int cb, int bn, int n_ntiles,
                           int nchunks, void* out, mmr_stream_t stream);
+/* The same for every layer of a network in one launch: jobs_dev is a DEVICE array of njobs jobs
+ * (the optimiser rewrites the fp32 masters every step, so the packing runs once per step). */
+typedef struct {
+  const float* w_oihw;
+  void* out;
+  int32_t O, I, mode, cb, bn, n_ntiles, nchunks, pad_;
+} MmrPackJob;
+int mmr_pack_weights_halo_batch(const MmrPackJob* jobs_dev, int njobs, mmr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Weight gradient on tcgen05.  Replaces the weight-gradient half of `loss.backward()`

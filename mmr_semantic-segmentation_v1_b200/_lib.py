@@ -64,7 +64,7 @@ class MmrHaloConvDesc(C.Structure):
         ("weights", C.c_void_p), ("cb", C.c_int32), ("bn", C.c_int32), ("sg", C.c_int32), ("n_ntiles", C.c_int32),
         ("tx", C.c_int32), ("tps", C.c_int32),
         ("halo_stages", C.c_int32), ("w_slots", C.c_int32), ("acc_bufs", C.c_int32),
-        ("out_stages", C.c_int32),
+        ("out_stages", C.c_int32), ("direct_store", C.c_int32),
         ("ngroups", C.c_int32), ("groups", C.POINTER(MmrOutSeg)),
         ("cout_total", C.c_int32),
         ("scale", C.c_void_p), ("bias", C.c_void_p),
@@ -72,6 +72,12 @@ class MmrHaloConvDesc(C.Structure):
         ("out_mode", C.c_int32), ("out_f32", C.c_void_p), ("out_ldc", C.c_int32),
         ("stats", C.c_void_p), ("stats_ld", C.c_int32),
     ]
+
+
+class MmrPackJob(C.Structure):
+    _fields_ = [("w_oihw", C.c_void_p), ("out", C.c_void_p), ("O", C.c_int32), ("I", C.c_int32),
+                ("mode", C.c_int32), ("cb", C.c_int32), ("bn", C.c_int32), ("n_ntiles", C.c_int32),
+                ("nchunks", C.c_int32), ("pad_", C.c_int32)]
 
 
 class MmrWgradHaloDesc(C.Structure):
@@ -131,6 +137,7 @@ SIGNATURES = {
     "mmr_halo_conv_plan_run": (_i, [_vp, _vp]),
     "mmr_halo_conv_plan_destroy": (_i, [_vp]),
     "mmr_pack_weights_halo": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_pack_weights_halo_batch": (_i, [_vp, _i, _vp]),
     "mmr_wgrad_halo_partial_floats": (_i64, [_i, _i, _i, _i, _i]),
     "mmr_wgrad_halo_plan_create": (_i, [C.POINTER(MmrWgradHaloDesc), C.POINTER(_vp)]),
     "mmr_wgrad_halo_plan_run": (_i, [_vp, _i, _vp]),

@@ -437,18 +437,18 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
                                 continue
                             cfg = dict(bn=bn, sg=sg, n_ntiles=n_nt, tx=tx, tps=tps, acc_bufs=acc_bufs,
                                        halo_stages=halo_stages, w_slots=w_slots, out_stages=out_stages)
-                            if force and any(cfg[k] != v for k, v in force.items()):
+                            if force and any(cfg[k] != v for k, v in force.items() if k in cfg):
                                 continue
                             items = N * (-(-H // 16)) * (-(-W // (8 * tx))) * n_nt
                             # issue time of the MMAs, plus the waits of the issuer on a chunk / item boundary
-                            mma = tx * nchunks * 9 * (cb // 16) * _mma_clk(bn) + nchunks * (150 + (9 // tps) * 300) + 600
-                            # one elected lane issues every TMA of a ring: ~360 clk per operation
+                            mma = tx * nchunks * 9 * (cb // 16) * _mma_clk(bn) + nchunks * 150 + 600
+                            # one elected lane issues every TMA of a ring: ~520 clk per operation
                             # (scripts/probe/probe4.cu), so few large weight slots beat many small ones
-                            wprod = nchunks * (9 // tps) * 360
-                            hprod = nchunks * (3 if any_up else 1) * 400
+                            wprod = nchunks * (9 // tps) * 520
+                            hprod = nchunks * (3 if any_up else 1) * 520
                             traffic = nchunks * (18 * pitch * cb * 2 + 9 * bn * cb * 2) / 70.0
                             epi = tx * gpn * (450.0 if sg == 64 else 700.0)
-                            per_item = max(mma, wprod, hprod, traffic) + (epi if acc_bufs == 1 else 0.0)
+                            per_item = max(mma, wprod, hprod, traffic) + (1.5 * epi if acc_bufs == 1 else 0.0)
                             per_item = max(per_item, epi)
                             if w_slots * tps < 3:
                                 per_item *= 1.15
@@ -462,6 +462,8 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
         raise ValueError("no halo-kernel configuration for cout=%d cb=%d" % (cout, cb))
     cfg = best[1]
     cfg.update(cb=cb, nchunks=nchunks, cpad=cpad)
+    if force and "direct" in force:
+        cfg["direct"] = force["direct"]
     return cfg
 
 
@@ -535,6 +537,7 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     d.tx, d.tps = cfg["tx"], cfg["tps"]
     d.halo_stages, d.w_slots, d.acc_bufs = cfg["halo_stages"], cfg["w_slots"], cfg["acc_bufs"]
     d.out_stages = max(1, cfg["out_stages"])
+    d.direct_store = int(cfg.get("direct", cfg["sg"] < 64))
     keep = [sources, packed, scale, bias, residual, stats]
     if out_f32 is None:
         segs = (MmrOutSeg * len(groups))(*[MmrOutSeg(t.data_ptr(), t.shape[3], coff) for t, coff in groups])
@@ -664,7 +667,7 @@ def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=
             continue
         tiles = N * (-(-H // 16)) * (-(-W // (8 * tx)))
         slices = nchunks * n_nt
-        n_split = max(1, min(tiles, round(2 * n_sms / slices))) if slices < 2 * n_sms else 1
+        n_split = max(1, min(tiles, n_sms // slices)) if slices < n_sms else 1
         cfg = dict(bn=bn, tx=tx, n_split=n_split, stages=stages)
         if force and any(cfg.get(k, v) != v for k, v in force.items() if k != "n_split"):
             continue

@@ -43,6 +43,8 @@ struct HaloParams {
   const CUtensorMap* maps;  // device: [source maps ...][weight map][store-group maps ...]
   HaloChunk chunk[kMaxChunks];
   int32_t group_coff[kMaxGroups];
+  int32_t group_ldc[kMaxGroups];
+  __nv_bfloat16* group_ptr[kMaxGroups];
   int nchunks, wmap, smap0;
   int H, W, N;
   int TX, tiles_x, tiles_y, n_ntiles, total_items;
@@ -50,6 +52,7 @@ struct HaloParams {
   int bn, sg, gpn;  // store group = sg channels, gpn groups per N tile
   int tps, nslots;  // taps per weight slot, slots per chunk
   int halo_stages, w_slots, acc_bufs, out_stages;
+  int direct;  // 1: bf16 tiles go to global memory straight from registers (narrow store groups)
   uint32_t halo_stage_bytes, w_slot_bytes, out_stage_bytes, w_tx_bytes;
   uint32_t halo_tx_bytes[2];
   int pitch[2];
@@ -320,6 +323,23 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     const int npairs = p.sg >> 1;
     const int pr = m % npairs, rg = m / npairs, nrg = 128 / npairs;
     const int slot = blockIdx.x & (kStatSlots - 1);
+    // one channel set per CTA: keep the statistics in registers for the whole launch
+    const bool persist = p.n_ntiles == 1 && p.gpn == 1;
+    const bool staged = p.out_mode == MMR_OUT_BF16_NHWC && (!p.direct || p.stats != nullptr);
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+    auto flush_stats = [&](int ch0) {
+      const int ch = ch0 + 2 * pr;
+      if (ch < p.cout_total) {
+        double* s = p.stats + (size_t)slot * 2 * p.stats_ld;
+        atomicAdd(s + ch, (double)s1a);
+        atomicAdd(s + p.stats_ld + ch, (double)s2a);
+        if (ch + 1 < p.cout_total) {
+          atomicAdd(s + ch + 1, (double)s1b);
+          atomicAdd(s + p.stats_ld + ch + 1, (double)s2b);
+        }
+      }
+      s1a = s1b = s2a = s2b = 0.f;
+    };
     int it = 0, gcount = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
       const ItemCoord ic = decode_item(p, item);
@@ -330,7 +350,6 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       const int y = ic.y0 + h;
       for (int g = 0; g < p.gpn; ++g) {
         const int ch0 = ic.nt * p.bn + g * p.sg;
-        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
         for (int i = 0; i < p.TX; ++i) {
           const int x = ic.x0 + 8 * i + w;
           const bool valid = y < p.H && x < p.W;
@@ -338,9 +357,9 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
                                  (uint32_t)(buf * p.TX * p.bn + i * p.bn + g * p.sg);
           uint8_t* stage = out_base;
-          if (p.out_mode == MMR_OUT_BF16_NHWC) stage += (size_t)(gcount % p.out_stages) * p.out_stage_bytes;
-          if (p.out_mode == MMR_OUT_BF16_NHWC && p.out_stages == 1 && gcount > 0) {
-            if (m == 0) bulk_wait_read0();
+          if (staged) stage += (size_t)(gcount % p.out_stages) * p.out_stage_bytes;
+          if (staged && p.out_stages == 1 && gcount > 0) {
+            if (m == 0 && !p.direct) bulk_wait_read0();
             epi_bar();
           }
           const bool last = (g == p.gpn - 1) && (i == p.TX - 1);
@@ -395,10 +414,18 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
                 o0 = make_uint4(0, 0, 0, 0);
                 o1 = o0;
               }
-              uint8_t* rowp = stage + (size_t)m * orb;
-              const uint32_t j0 = (uint32_t)c0 >> 3;
-              *reinterpret_cast<uint4*>(rowp + ((j0 ^ xr) << 4)) = o0;
-              *reinterpret_cast<uint4*>(rowp + (((j0 + 1) ^ xr) << 4)) = o1;
+              if (staged) {
+                uint8_t* rowp = stage + (size_t)m * orb;
+                const uint32_t j0 = (uint32_t)c0 >> 3;
+                *reinterpret_cast<uint4*>(rowp + ((j0 ^ xr) << 4)) = o0;
+                *reinterpret_cast<uint4*>(rowp + (((j0 + 1) ^ xr) << 4)) = o1;
+              }
+              if (p.direct && valid) {
+                const int gi = ic.nt * p.gpn + g;
+                uint4* dst = reinterpret_cast<uint4*>(p.group_ptr[gi] + pix * p.group_ldc[gi] + p.group_coff[gi] + c0);
+                dst[0] = o0;
+                dst[1] = o1;
+              }
             } else if (valid) {
               const size_t hw = (size_t)p.H * p.W;
 #pragma unroll
@@ -409,11 +436,13 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
               }
             }
           }
-          if (p.out_mode == MMR_OUT_BF16_NHWC) {
-            if (p.out_stages > 1 && m == 0) bulk_wait_read0();  // the other staging buffer is free again
-            fence_proxy_async_smem();
+          if (staged) {
+            if (!p.direct) {
+              if (p.out_stages > 1 && m == 0) bulk_wait_read0();  // the other staging buffer is free again
+              fence_proxy_async_smem();
+            }
             epi_bar();
-            if (m == 0) {
+            if (m == 0 && !p.direct) {
               const int gi = ic.nt * p.gpn + g;
               tma_store_4d(&p.maps[p.smap0 + gi], stage, p.group_coff[gi], ic.x0 + 8 * i, ic.y0, ic.n);
               bulk_commit();
@@ -432,21 +461,11 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
             ++gcount;
           }
         }
-        if (p.stats) {
-          const int ch = ch0 + 2 * pr;
-          if (ch < p.cout_total) {
-            double* s = p.stats + (size_t)slot * 2 * p.stats_ld;
-            atomicAdd(s + ch, (double)s1a);
-            atomicAdd(s + p.stats_ld + ch, (double)s2a);
-            if (ch + 1 < p.cout_total) {
-              atomicAdd(s + ch + 1, (double)s1b);
-              atomicAdd(s + p.stats_ld + ch + 1, (double)s2b);
-            }
-          }
-        }
+        if (p.stats && !persist) flush_stats(ch0);
       }
     }
-    if (p.out_mode == MMR_OUT_BF16_NHWC && m == 0) bulk_wait0();
+    if (p.stats && persist) flush_stats(0);
+    if (p.out_mode == MMR_OUT_BF16_NHWC && !p.direct && m == 0) bulk_wait0();
   }
 
   tc_fence_before();
@@ -479,6 +498,34 @@ __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int O, int
       if (nidx < O && kidx < I) v = w[((size_t)nidx * I + kidx) * 9 + tap];
     } else {
       if (kidx < O && nidx < I) v = w[((size_t)kidx * I + nidx) * 9 + (8 - tap)];
+    }
+    out[idx] = __float2bfloat16(v);
+  }
+}
+
+// Every layer's packing in one launch: blockIdx.y selects the job.
+__global__ void pack_weights_halo_batch_kernel(const MmrPackJob* __restrict__ jobs) {
+  const MmrPackJob j = jobs[blockIdx.y];
+  const float* __restrict__ w = j.w_oihw;
+  __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(j.out);
+  const int64_t total = (int64_t)j.n_ntiles * j.nchunks * 9 * j.bn * j.cb;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = idx;
+    const int k = (int)(t % j.cb);
+    t /= j.cb;
+    const int r = (int)(t % j.bn);
+    t /= j.bn;
+    const int tap = (int)(t % 9);
+    t /= 9;
+    const int c = (int)(t % j.nchunks);
+    const int nt = (int)(t / j.nchunks);
+    const int nidx = nt * j.bn + r, kidx = c * j.cb + k;
+    float v = 0.f;
+    if (j.mode == 0) {
+      if (nidx < j.O && kidx < j.I) v = w[((size_t)nidx * j.I + kidx) * 9 + tap];
+    } else {
+      if (kidx < j.O && nidx < j.I) v = w[((size_t)kidx * j.I + nidx) * 9 + (8 - tap)];
     }
     out[idx] = __float2bfloat16(v);
   }
@@ -618,6 +665,7 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   }
   p.smap0 = (int)maps.size();
   p.out_mode = d->out_mode;
+  p.direct = d->direct_store != 0;
   if (d->out_mode == MMR_OUT_BF16_NHWC) {
     const int ng = d->n_ntiles * p.gpn;
     MMR_REQUIRE(d->ngroups == ng && d->groups, "expected %d store groups, got %d", ng, d->ngroups);
@@ -634,6 +682,8 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
       maps.emplace_back();
       if (encode_generic(&maps.back(), og.ptr, 4, dims, str, box, p.sg * 2, "store group")) { delete pl; return -1; }
       p.group_coff[g] = og.coff;
+      p.group_ldc[g] = og.ldc;
+      p.group_ptr[g] = reinterpret_cast<__nv_bfloat16*>(og.ptr);
     }
   } else {
     MMR_REQUIRE(d->out_f32 != nullptr && d->n_ntiles == 1, "fp32 NCHW output needs out_f32 and one N tile");
@@ -715,6 +765,14 @@ extern "C" int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode
   if (blocks < 1) blocks = 1;
   pack_weights_halo_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(
       w_oihw, O, I, mode, cb, bn, n_ntiles, nchunks, reinterpret_cast<__nv_bfloat16*>(out));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_pack_weights_halo_batch(const MmrPackJob* jobs_dev, int njobs, mmr_stream_t stream) {
+  MMR_REQUIRE(jobs_dev && njobs > 0, "bad argument");
+  dim3 grid(64, njobs);
+  pack_weights_halo_batch_kernel<<<grid, 256, 0, as_stream(stream)>>>(jobs_dev);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

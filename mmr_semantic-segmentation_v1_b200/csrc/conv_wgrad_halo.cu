@@ -235,15 +235,18 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// Sum the split-K partials in split order and scatter into OIHW fp32 (dst[co][ci][tap]).
+// Sum the split-K partials in split order and scatter into OIHW fp32 (dst[co][ci][tap]).  One
+// thread owns four consecutive output channels of one accumulator row (float4 loads, four splits in
+// flight); rows that belong to no filter tap are skipped before any load.
 __global__ void __launch_bounds__(256)
 wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
+  const int bn4 = p.bn >> 2;
   const size_t per_slice = (size_t)p.A * 128 * p.bn;
-  const size_t total = per_slice * p.nchunks * p.n_ntiles;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+  const size_t total4 = (size_t)p.A * 128 * bn4 * p.nchunks * p.n_ntiles;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
        idx += (size_t)gridDim.x * blockDim.x) {
-    const int n = (int)(idx % p.bn);
-    size_t t = idx / p.bn;
+    const int n4 = (int)(idx % bn4);
+    size_t t = idx / bn4;
     const int r = (int)(t % 128);
     t /= 128;
     const int a = (int)(t % p.A);
@@ -258,13 +261,32 @@ wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
       tap = kx < 3 ? 3 * a + kx : 9;
       chn = r % p.cb;
     }
-    const int co = nt * p.bn + n, ci = p.chunk[c].ci0 + chn;
+    const int co = nt * p.bn + n4 * 4, ci = p.chunk[c].ci0 + chn;
     if (tap >= 9 || co >= p.dst_cout || ci >= p.dst_cin) continue;
-    const float* src = p.partial + (size_t)slice * p.n_split * per_slice + (idx - (size_t)slice * per_slice);
-    float s = 0.f;
-    for (int k = 0; k < p.n_split; ++k) s += __ldg(src + (size_t)k * per_slice);
-    float* d = p.dst + ((size_t)co * p.dst_cin + ci) * 9 + tap;
-    *d = accumulate ? *d + s : s;
+    const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)slice * p.n_split * per_slice +
+                                                        ((size_t)a * 128 + r) * p.bn) + n4;
+    const size_t step = per_slice >> 2;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = 0;
+    for (; k + 4 <= p.n_split; k += 4) {
+      const float4 v0 = __ldg(src + (size_t)k * step), v1 = __ldg(src + (size_t)(k + 1) * step);
+      const float4 v2 = __ldg(src + (size_t)(k + 2) * step), v3 = __ldg(src + (size_t)(k + 3) * step);
+      s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+      s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+      s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
+      s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+    }
+    for (; k < p.n_split; ++k) {
+      const float4 v = __ldg(src + (size_t)k * step);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (co + j >= p.dst_cout) break;
+      float* d = p.dst + ((size_t)(co + j) * p.dst_cin + ci) * 9 + tap;
+      *d = accumulate ? *d + sv[j] : sv[j];
+    }
   }
 }
 
@@ -437,7 +459,7 @@ extern "C" int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t 
   dim3 grid(p.nchunks * p.n_ntiles, p.n_split);
   conv_wgrad_halo_kernel<<<grid, kWhThreads, pl->smem_bytes, as_stream(stream)>>>(p);
   MMR_CUDA_CHECK(cudaGetLastError());
-  const size_t total = (size_t)p.A * 128 * p.bn * p.nchunks * p.n_ntiles;
+  const size_t total = (size_t)p.A * 128 * (p.bn / 4) * p.nchunks * p.n_ntiles;
   int64_t blocks = (int64_t)((total + 255) / 256);
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;

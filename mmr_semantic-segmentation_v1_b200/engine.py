@@ -109,6 +109,7 @@ class Engine:
         # BatchNorm statistics taken in the conv epilogues: [unit][slot][2][C] doubles, bump-allocated
         self.halo_stats = torch.zeros((HALO_STAT_SLOTS * 2 * 16384,), device=device, dtype=torch.float64)
         self.halo_stats_used = 0
+        self.pack_jobs = []
         self.x_in = torch.empty((N, 3, H, W), device=device, dtype=torch.float32)
         self.bn_partial = torch.empty((BN_BLOCKS * 2 * 512,), device=device, dtype=torch.float64)
         # split-K partials of the weight-gradient GEMMs: one buffer, used by one layer at a time
@@ -136,6 +137,12 @@ class Engine:
             else:
                 conv.append(a)
         calls.append((getattr(self.lib, fname), tuple(conv)))
+
+    def _pack_job(self, w, out, O, I, mode, cfg):
+        """Queue one layer's fp32 OIHW -> packed bf16 conversion; all jobs run as ONE launch."""
+        self.pack_jobs.append(_lib.MmrPackJob(w.data_ptr(), out.data_ptr(), O, I, mode, cfg["cb"], cfg["bn"],
+                                              cfg["n_ntiles"], cfg["nchunks"], 0))
+        self.keep += [w, out]
 
     def _nblk(self, P, Cc):
         rows_per_iter = 256 // (Cc // 8)
@@ -175,6 +182,12 @@ class Engine:
                 self.out_seeds[op["in"]] = self._bf16(*act.shape, zero=True)
             else:
                 raise ValueError("unknown op %r" % kind)
+        if self.pack_jobs:
+            arr = (_lib.MmrPackJob * len(self.pack_jobs))(*self.pack_jobs)
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+            self.pack_jobs_dev = raw.to(self.dev)
+            self.repack_calls.append((self.lib.mmr_pack_weights_halo_batch,
+                                      (C.c_void_p(self.pack_jobs_dev.data_ptr()), len(self.pack_jobs))))
         if self.halo_stats_used:
             # one memset per forward re-arms every statistics slot the conv epilogues accumulate into
             fc.insert(0, (self.lib.mmr_zero_async, (C.c_void_p(self.halo_stats.data_ptr()),
@@ -286,15 +299,13 @@ class Engine:
         if halo:
             hcfg = convplan.fprop_halo_cfg(sources, cout, bf16_out=not head)
             unit["wf_h"] = self._bf16(convplan.halo_packed_weights_numel(hcfg))
-            self._rec(self.repack_calls, "mmr_pack_weights_halo", w, cout, cin, 0, hcfg["cb"], hcfg["bn"],
-                      hcfg["n_ntiles"], hcfg["nchunks"], unit["wf_h"])
+            self._pack_job(w, unit["wf_h"], cout, cin, 0, hcfg)
             if self.training:
                 dsizes = [a.shape[3] for a, _ in srcs]
                 dcfg = convplan.dgrad_halo_cfg((n, Hin, Win, cpad), dsizes)
                 unit["dcfg"] = dcfg
                 unit["wd_h"] = self._bf16(convplan.halo_packed_weights_numel(dcfg))
-                self._rec(self.repack_calls, "mmr_pack_weights_halo", w, cout, cin, 1, dcfg["cb"], dcfg["bn"],
-                          dcfg["n_ntiles"], dcfg["nchunks"], unit["wd_h"])
+                self._pack_job(w, unit["wd_h"], cout, cin, 1, dcfg)
         else:
             unit["wf"] = self._bf16(cpad, taps * cin, zero=True)
             unit["wd"] = self._bf16(cin, taps * cpad, zero=True) if self.training else None
