@@ -308,6 +308,15 @@ int mmr_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, u
 int mmr_maxpool3x3s2_bwd(const MmrContrib* contribs, int ncontrib, const uint8_t* idx, int N,
                          int H, int W, int C, void* gin, mmr_stream_t stream);
 
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) on NHWC bf16 and its adjoint;
+ * replaces self.upsample of the reference's ResNetUNet (SU/UArchModel/resnet_unet.py:195,262-294).
+ * x: [N][H][W][C] -> out: [N][2H][2W][C].  The backward gathers the (summed) gradient
+ * contributions of the upsampled tensor (each optionally 2x2-pooled) into gin [N][H][W][C]. */
+int mmr_upsample_bilinear2x_fwd(const void* x, int N, int H, int W, int C, void* out,
+                                mmr_stream_t stream);
+int mmr_upsample_bilinear2x_bwd(const MmrContrib* contribs, int ncontrib, int N, int H, int W, int C,
+                                void* gin, mmr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Loss: softmax + soft-Dice + cross-entropy, forward and backward.
  * Replaces dice_loss / DiceLoss.forward (SU/dice_loss.py:37-161,241-259) +

@@ -583,7 +583,8 @@ def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=No
     H = sources[0][0].shape[1] * sources[0][1]
     W = sources[0][0].shape[2] * sources[0][1]
     cout, cin = w_oihw.shape[0], w_oihw.shape[1]
-    assert cin == sum(t.shape[3] for t, _ in sources)
+    # cin below the stored channel count: a zero-padded source (the 3-channel image stored as 16)
+    assert cin <= sum(t.shape[3] for t, _ in sources)
     if cfg is None:
         cfg = fprop_halo_cfg(sources, cout, out_f32 is None, force)
     if packed is None:
@@ -700,12 +701,13 @@ def build_wgrad_halo(dz, sources, dst, *, cout_gemm=None, force=None, partial=No
     assert dz.dtype == torch.bfloat16 and dz.is_contiguous()
     assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape[2:]) == (3, 3)
     cout, cin = dst.shape[0], dst.shape[1]
-    assert cin == sum(t.shape[3] for t, _ in sources)
+    cin_stored = sum(t.shape[3] for t, _ in sources)
+    assert cin <= cin_stored
     if cout_gemm is None:
         cout_gemm = Cz
     cb = pick_bk([t.shape[3] for t, _ in sources])
     any_up = any(up == 2 for _, up in sources)
-    cfg = wgrad_halo_config(H, W, N, cb, cin // cb, cout_gemm, any_up, n_sms=n_sms, force=force,
+    cfg = wgrad_halo_config(H, W, N, cb, cin_stored // cb, cout_gemm, any_up, n_sms=n_sms, force=force,
                             max_partial=partial.numel() if partial is not None else None)
     need = cfg["nchunks"] * cfg["n_ntiles"] * cfg["n_split"] * cfg["A"] * 128 * cfg["bn"]
     if partial is None:

@@ -662,6 +662,103 @@ __global__ void maxpool_bwd_kernel(ContribList cl, const uint8_t* __restrict__ i
   }
 }
 
+// ------------------------------------------------------------------ bilinear x2 (align_corners)
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of the reference's ResNetUNet
+// (SU/UArchModel/resnet_unet.py:195): src = dst * (in-1)/(out-1) in fp32 as ATen computes it,
+// i0 = floor(src), i1 = i0 + (i0 < in-1), lambda = src - i0.
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Lerp lerp_coord(int dst, int in, float scale) {
+  Lerp l;
+  const float src = scale * (float)dst;
+  l.i0 = (int)src;
+  if (l.i0 > in - 1) l.i0 = in - 1;
+  l.i1 = l.i0 + (l.i0 < in - 1 ? 1 : 0);
+  l.w1 = src - (float)l.i0;
+  l.w0 = 1.f - l.w1;
+  return l;
+}
+
+__global__ void upsample_bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                               __nv_bfloat16* __restrict__ out) {
+  const int H2 = 2 * H, W2 = 2 * W;
+  const float sy = H2 > 1 ? (float)(H - 1) / (float)(H2 - 1) : 0.f;
+  const float sx = W2 > 1 ? (float)(W - 1) / (float)(W2 - 1) : 0.f;
+  const uint32_t groups = (uint32_t)C / 8;
+  const int64_t total = (int64_t)N * H2 * W2 * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)((uint64_t)i % groups) * 8;
+    const int64_t pix = i / groups;
+    const int ox = (int)(pix % W2), oy = (int)((pix / W2) % H2), n = (int)(pix / ((int64_t)W2 * H2));
+    const Lerp ly = lerp_coord(oy, H, sy), lx = lerp_coord(ox, W, sx);
+    const __nv_bfloat16* base = x + (size_t)n * H * W * C + c;
+    float v00[8], v01[8], v10[8], v11[8], o[8];
+    load8(base + ((size_t)ly.i0 * W + lx.i0) * C, v00);
+    load8(base + ((size_t)ly.i0 * W + lx.i1) * C, v01);
+    load8(base + ((size_t)ly.i1 * W + lx.i0) * C, v10);
+    load8(base + ((size_t)ly.i1 * W + lx.i1) * C, v11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = ly.w0 * (lx.w0 * v00[j] + lx.w1 * v01[j]) + ly.w1 * (lx.w0 * v10[j] + lx.w1 * v11[j]);
+    store8(out + pix * C + c, o);
+  }
+}
+
+// Adjoint, as a gather (deterministic): input pixel (yi, xi) collects every output pixel whose
+// interpolation stencil contains it.  With a scale of about 1/2 those lie in [2*i-2, 2*i+3].
+__device__ __forceinline__ void lerp_adjoint_weights(int i, int in, float scale, int& first, float (&w)[6]) {
+  first = 2 * i - 2;
+  const int out = 2 * in;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int d = first + k;
+    float wk = 0.f;
+    if (d >= 0 && d < out) {
+      const Lerp l = lerp_coord(d, in, scale);
+      if (l.i0 == i) wk += l.w0;
+      if (l.i1 == i) wk += l.w1;  // i0 == i1 on the last row/column: both weights land here
+    }
+    w[k] = wk;
+  }
+}
+
+__global__ void upsample_bilinear2x_bwd_kernel(ContribList cl, int N, int H, int W, int C,
+                                               __nv_bfloat16* __restrict__ gin) {
+  const int H2 = 2 * H, W2 = 2 * W;
+  const float sy = H2 > 1 ? (float)(H - 1) / (float)(H2 - 1) : 0.f;
+  const float sx = W2 > 1 ? (float)(W - 1) / (float)(W2 - 1) : 0.f;
+  const uint32_t groups = (uint32_t)C / 8;
+  const int64_t total = (int64_t)N * H * W * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)((uint64_t)i % groups) * 8;
+    const int64_t pix = i / groups;
+    const int xi = (int)(pix % W), yi = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+    int fy, fx;
+    float wy[6], wx[6];
+    lerp_adjoint_weights(yi, H, sy, fy, wy);
+    lerp_adjoint_weights(xi, W, sx, fx, wx);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 6; ++ky) {
+      if (wy[ky] == 0.f) continue;
+      for (int kx = 0; kx < 6; ++kx) {
+        const float wgt = wy[ky] * wx[kx];
+        if (wgt == 0.f) continue;
+        float g[8];
+        gather8(cl, n, fy + ky, fx + kx, c, H2, W2, C, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += wgt * g[j];
+      }
+    }
+    store8(gin + pix * C + c, acc);
+  }
+}
+
 // ------------------------------------------------------------------ head gradient prep
 // dlogits fp32 NCHW -> bf16 NHWC (cpad channels, zero padded); per-class sums -> dbias.
 __global__ void head_grad_prep_kernel(const float* __restrict__ dl, int N, int C, int H, int W,
@@ -925,5 +1022,27 @@ extern "C" int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int
                                                                accumulate);
     MMR_CUDA_CHECK(cudaGetLastError());
   }
+  return 0;
+}
+
+extern "C" int mmr_upsample_bilinear2x_fwd(const void* x, int N, int H, int W, int C, void* out,
+                                           mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  const int64_t total = (int64_t)N * 4 * H * W * (C / 8);
+  upsample_bilinear2x_fwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_upsample_bilinear2x_bwd(const MmrContrib* contribs, int ncontrib, int N, int H, int W,
+                                           int C, void* gin, mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  ContribList cl;
+  if (fill_contribs(cl, contribs, ncontrib)) return -1;
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  upsample_bilinear2x_bwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
+      cl, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
+  MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

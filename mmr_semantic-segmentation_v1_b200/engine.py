@@ -169,6 +169,20 @@ class Engine:
                 self._rec(fc, "mmr_maxpool3x3s2_fwd", src.buf, n, h, w, c, out.buf, out.idx)
             elif kind in ("conv", "head"):
                 self._fwd_conv(op)
+            elif kind == "pack16":   # image -> NHWC bf16, 3 channels zero-padded to 16
+                act = _Act(op["out"], (N, H, W, 16), needs_grad=False)
+                act.buf = self._bf16(N, H, W, 16)
+                self.acts[op["out"]] = act
+                self._rec(fc, "mmr_pack_nchw_f32_to_nhwc_bf16", self.x_in, N, 3, H, W, act.buf, 16)
+            elif kind == "upsample":
+                src = self.acts[op["in"]]
+                n, h, w, c = src.shape
+                out = _Act(op["out"], (n, 2 * h, 2 * w, c))
+                out.buf = self._bf16(*out.shape)
+                out.producer = {"kind": "upsample", "src": src, "out": out}
+                self.acts[op["out"]] = out
+                self.units.append(out.producer)
+                self._rec(fc, "mmr_upsample_bilinear2x_fwd", src.buf, n, h, w, c, out.buf)
             elif kind == "input":    # test seam: an activation fed from outside (bf16 NHWC)
                 h, w, c = op["shape"]
                 act = _Act(op["out"], (N, h, w, c))
@@ -285,7 +299,10 @@ class Engine:
         Ho, Wo = (Hin + 2 * pad - k) // s + 1, (Win + 2 * pad - k) // s + 1
         w = self.P[op["conv"] + ".weight"]
         cout, cin = w.shape[0], w.shape[1]
-        assert cin == sum(a.shape[3] for a, _ in srcs), (op["conv"], cin)
+        if not head and op.get("cin_pad"):   # image padded to 16 channels: the extra ones meet zero weights
+            assert len(srcs) == 1 and cin <= srcs[0][0].shape[3], (op["conv"], cin)
+        else:
+            assert cin == sum(a.shape[3] for a, _ in srcs), (op["conv"], cin)
         cpad = -(-cout // 16) * 16
         taps = k * k
         unit = {"kind": "head" if head else "conv", "op": op, "cout": cout, "cpad": cpad, "k": k, "s": s,
@@ -383,7 +400,7 @@ class Engine:
             kind = u["kind"]
             if kind == "input":
                 continue
-            if kind == "maxpool":
+            if kind in ("maxpool", "upsample"):
                 src = u["src"]
                 if src.needs_grad:
                     arena.request(("gin", id(u)), nbytes(src.shape), t, t_of[id(src.producer)])
@@ -438,6 +455,16 @@ class Engine:
             n, h, w, c = out.shape
             arr, cnt = self._contrib_array(out)
             self._rec(calls, "mmr_grad_gather", arr, cnt, None, n, h, w, c, u["grad"], None, self._nblk(n * h * w, c))
+            return
+        if kind == "upsample":
+            src, out = u["src"], u["out"]
+            if not src.needs_grad:
+                return
+            n, h, w, c = src.shape
+            gin = view(("gin", id(u)), src.shape)
+            arr, cnt = self._contrib_array(out)
+            self._rec(calls, "mmr_upsample_bilinear2x_bwd", arr, cnt, n, h, w, c, gin)
+            src.contribs.append((gin, 0))
             return
         if kind == "maxpool":
             src, out = u["src"], u["out"]

@@ -6,6 +6,8 @@ models, so the engine can bind the reference's own parameter tensors.
 
   {'op': 'stem',    'out', 'conv', 'bn'}                         7x7 s2 p3 conv + BN + ReLU on the image
   {'op': 'stem3',   'out', 'conv', 'cout', 'relu'}               3x3 s1 p1 conv(+bias)+ReLU on the image
+  {'op': 'pack16',  'out'}                                        image -> NHWC bf16 padded to 16 channels
+  {'op': 'upsample','in', 'out'}                                  bilinear x2, align_corners=True
   {'op': 'maxpool', 'in', 'out'}                                  3x3 s2 p1
   {'op': 'conv',    'out', 'conv', 'src': [(tensor, up)], 'k', 's', 'cout',
                     'bn': name|None, 'bias': bool, 'relu': bool, 'res': tensor|None}
@@ -109,3 +111,51 @@ def unetpp_graph(encoder_name="resnet18", classes=2, deep_supervision=False):
             ops.append({"op": "head", "out": "logits." + node, "conv": "ds_heads." + node,
                         "src": [(node, 1)], "k": 3, "cout": classes})
     return ops
+
+
+def resnet_unet_graph(resnet_model=18, n_class=10):
+    """The reference's in-tree ResNet encoder/decoder (SU/UArchModel/resnet_unet.py:134-300):
+    torchvision BasicBlock encoder, 1x1 conv+ReLU laterals, bilinear x2 (align_corners=True)
+    -> cat([upsampled, lateral]) -> 3x3 conv + bias + ReLU decoder without BatchNorm, a full-resolution
+    side path of two 3x3 convs, and a 1x1 `conv_last`.  Parameter names are the reference's."""
+    ops = [{"op": "pack16", "out": "image16"}]
+
+    def conv(out, name, src, k, cout, cin_pad=False):
+        ops.append({"op": "conv", "out": out, "conv": name, "src": src, "k": k, "s": 1, "cout": cout,
+                    "bn": None, "bias": True, "relu": True, "res": None, "cin_pad": cin_pad})
+
+    conv("xo0", "conv_original_size0.0", [("image16", 1)], 3, 64, cin_pad=True)
+    conv("xo1", "conv_original_size1.0", [("xo0", 1)], 3, 64)
+    feats, chans = resnet_encoder_ops("base_model.", RESNET_LAYERS["resnet%d" % resnet_model], ops)
+    l0, l1, l2, l3, l4 = feats
+    conv("l4p", "layer4_1x1.0", [(l4, 1)], 1, 512)
+    ops.append({"op": "upsample", "in": "l4p", "out": "u4"})
+    conv("l3p", "layer3_1x1.0", [(l3, 1)], 1, 256)
+    conv("d3", "conv_up3.0", [("u4", 1), ("l3p", 1)], 3, 512)
+    ops.append({"op": "upsample", "in": "d3", "out": "u3"})
+    conv("l2p", "layer2_1x1.0", [(l2, 1)], 1, 128)
+    conv("d2", "conv_up2.0", [("u3", 1), ("l2p", 1)], 3, 256)
+    ops.append({"op": "upsample", "in": "d2", "out": "u2"})
+    conv("l1p", "layer1_1x1.0", [(l1, 1)], 1, 64)
+    conv("d1", "conv_up1.0", [("u2", 1), ("l1p", 1)], 3, 256)
+    ops.append({"op": "upsample", "in": "d1", "out": "u1"})
+    conv("l0p", "layer0_1x1.0", [(l0, 1)], 1, 64)
+    conv("d0", "conv_up0.0", [("u1", 1), ("l0p", 1)], 3, 128)
+    ops.append({"op": "upsample", "in": "d0", "out": "u0"})
+    conv("dfull", "conv_original_size2.0", [("u0", 1), ("xo1", 1)], 3, 64)
+    ops.append({"op": "head", "out": "logits", "conv": "conv_last", "src": [("dfull", 1)], "k": 1,
+                "cout": n_class})
+    return ops
+
+
+def graph_param_names(ops):
+    """state_dict names of the parameters a graph reads (their gradients are produced by the plan)."""
+    names = []
+    for op in ops:
+        if op["op"] in ("conv", "head", "stem"):
+            names.append(op["conv"] + ".weight")
+            if op["op"] == "head" or op.get("bias"):
+                names.append(op["conv"] + ".bias")
+            if op.get("bn"):
+                names += [op["bn"] + ".weight", op["bn"] + ".bias"]
+    return names

@@ -162,18 +162,24 @@ class _PlanModel(nn.Module):
 
     def _grads_live(self):
         """True when every .grad is still our view (gradient accumulation step)."""
-        live = [p.grad is not None for p in self.parameters()]
+        used = getattr(self, "_plan_params", None)
+        live = [p.grad is not None for n, p in self.named_parameters() if used is None or n in used]
         if not any(live):
             return False
         if all(live) and all(p.grad.data_ptr() == self._gviews[n].data_ptr()
-                             for n, p in self.named_parameters()):
+                             for n, p in self.named_parameters() if p.grad is not None):
             return True
         raise _lib.MmrError("parameter .grad tensors were replaced; call zero_grad(set_to_none=True) "
                             "(or leave them untouched) between backward passes")
 
     def _publish_grads(self):
+        """Parameters the plan never reads (e.g. the torchvision `fc` the reference's ResNetUNet
+        keeps) stay without a gradient, as under autograd."""
+        used = getattr(self, "_plan_params", None)
+        if used is None:
+            used = self._plan_params = set(graph.graph_param_names(self._graph()))
         for n, p in self.named_parameters():
-            if p.grad is None:
+            if p.grad is None and n in used:
                 p.grad = self._gviews[n]
 
     # ---- plan cache ------------------------------------------------------------------------
@@ -244,6 +250,53 @@ class UnetPlusPlus(_PlanModel):
 
     def _graph(self):
         return graph.unetpp_graph(self.encoder_name, self.classes, self.deep_supervision)
+
+
+def _convrelu(cin, cout, kernel, padding):  # SU/UArchModel/resnet_unet.py:36-44
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel, padding=padding), nn.ReLU(inplace=True))
+
+
+class ResNetUNet(_PlanModel):
+    """The reference's in-tree `ResNetUNet(n_class, resnet_model)` (SU/UArchModel/resnet_unet.py:134-300;
+    constructed at SU/ModelTraining.py:244-246): same module tree, so `state_dict()` keys (including the
+    `layerN.*` aliases of `base_model.*`), `.base_model` (differential learning rate) and `conv_last`
+    (skipped on resume) are the reference's.  The torchvision backbone is a parameter container only;
+    `forward` replays the static plan.  `pretrained=True` of the reference needs a download: the encoder
+    is random-init here (BASELINE config 3) and checkpoints load through `load_state_dict`."""
+
+    def __init__(self, n_class, resnet_model):
+        super().__init__()
+        import torchvision
+        self.n_class, self.resnet_model = n_class, resnet_model
+        if resnet_model == 18:
+            self.base_model = torchvision.models.resnet18(weights=None)
+        elif resnet_model == 34:
+            self.base_model = torchvision.models.resnet34(weights=None)
+        else:
+            raise ValueError("Only ResNet-18 and ResNet-34 are supported")
+        self.base_layers = list(self.base_model.children())
+        self.layer0 = nn.Sequential(*self.base_layers[:3])
+        self.layer0_1x1 = _convrelu(64, 64, 1, 0)
+        self.layer1 = nn.Sequential(*self.base_layers[3:5])
+        self.layer1_1x1 = _convrelu(64, 64, 1, 0)
+        self.layer2 = self.base_layers[5]
+        self.layer2_1x1 = _convrelu(128, 128, 1, 0)
+        self.layer3 = self.base_layers[6]
+        self.layer3_1x1 = _convrelu(256, 256, 1, 0)
+        self.layer4 = self.base_layers[7]
+        self.layer4_1x1 = _convrelu(512, 512, 1, 0)
+        self.upsample = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.conv_up3 = _convrelu(256 + 512, 512, 3, 1)
+        self.conv_up2 = _convrelu(128 + 512, 256, 3, 1)
+        self.conv_up1 = _convrelu(64 + 256, 256, 3, 1)
+        self.conv_up0 = _convrelu(64 + 256, 128, 3, 1)
+        self.conv_original_size0 = _convrelu(3, 64, 3, 1)
+        self.conv_original_size1 = _convrelu(64, 64, 3, 1)
+        self.conv_original_size2 = _convrelu(64 + 128, 64, 3, 1)
+        self.conv_last = nn.Conv2d(64, n_class, 1)
+
+    def _graph(self):
+        return graph.resnet_unet_graph(self.resnet_model, self.n_class)
 
 
 def create_model(arch="UnetPlusPlus", encoder_name="resnet18", encoder_weights=None, in_channels=3,

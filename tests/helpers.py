@@ -73,3 +73,34 @@ def install_engine_masks(ref, eng):
     for name, blk in ref.decoder.blocks.items():
         blk.conv1[2] = ReLUWithMasks([m(name + ".mid")])
         blk.conv2[2] = ReLUWithMasks([m(name)])
+
+
+def install_masks_by_call_order(ref, eng, act_names):
+    """Generic version of install_engine_masks: every nn.ReLU of `ref` (shared module objects hooked
+    once) back-propagates through the engine's ReLU sign pattern; `act_names` lists the engine
+    activations in the order the oracle's forward calls its ReLUs."""
+    masks = [(eng.acts[n].buf.float().permute(0, 3, 1, 2).cpu() > 0).float() for n in act_names]
+    queue = list(masks)
+
+    def hook(mod, inp, out):
+        return _MaskedReLU.apply(inp[0], queue.pop(0))
+
+    seen = set()
+    for m in ref.modules():
+        if isinstance(m, torch.nn.ReLU) and id(m) not in seen:
+            seen.add(id(m))
+            m.inplace = False
+            m.register_forward_hook(hook)
+    return queue
+
+
+def resnet_unet_relu_order(resnet_model):
+    """Engine activation names in the order oracle.resnet_unet.ResNetUNet.forward applies ReLU."""
+    layers = {18: (2, 2, 2, 2), 34: (3, 4, 6, 3)}[resnet_model]
+    names = ["xo0", "xo1", "f_stem"]
+    for li, n in enumerate(layers, start=1):
+        for bi in range(n):
+            base = "base_model.layer%d.%d." % (li, bi)
+            names += [base + "t1", base + "out"]
+    names += ["l4p", "l3p", "d3", "l2p", "d2", "l1p", "d1", "l0p", "d0", "dfull"]
+    return names
