@@ -317,6 +317,14 @@ int mmr_upsample_bilinear2x_fwd(const void* x, int N, int H, int W, int C, void*
 int mmr_upsample_bilinear2x_bwd(const MmrContrib* contribs, int ncontrib, int N, int H, int W, int C,
                                 void* gin, mmr_stream_t stream);
 
+/* Deep-supervision heads (BASELINE config 4; no reference semantics, definition in
+ * oracle/unetpp.py::DeepSupervisionUnetPlusPlus): fp32 NCHW logits [planes][h][w] of an auxiliary
+ * head -> nearest-upsampled [planes][h*f][w*f], and the adjoint f x f sum-pool for the gradient. */
+int mmr_upsample_nearest_f32_nchw(const float* in, int64_t planes, int h, int w, int f, float* out,
+                                  mmr_stream_t stream);
+int mmr_sumpool_f32_nchw(const float* in, int64_t planes, int h, int w, int f, float* out,
+                         mmr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Loss: softmax + soft-Dice + cross-entropy, forward and backward.
  * Replaces dice_loss / DiceLoss.forward (SU/dice_loss.py:37-161,241-259) +

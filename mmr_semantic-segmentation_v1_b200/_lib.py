@@ -163,6 +163,8 @@ SIGNATURES = {
     "mmr_maxpool3x3s2_bwd": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mmr_upsample_bilinear2x_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "mmr_upsample_bilinear2x_bwd": (_i, [C.POINTER(MmrContrib), _i, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_upsample_nearest_f32_nchw": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
+    "mmr_sumpool_f32_nchw": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),
     "mmr_dice_ce_workspace_doubles": (_i64, [_i, _i, _i]),
     "mmr_dice_ce_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(MmrLossParams), _vp, _i, _vp,
                              _vp]),

@@ -759,6 +759,37 @@ __global__ void upsample_bilinear2x_bwd_kernel(ContribList cl, int N, int H, int
   }
 }
 
+// ------------------------------------------------------------------ deep-supervision logits
+// fp32 NCHW logits of an auxiliary head at 1/f resolution -> full resolution (nearest), and the
+// adjoint (f x f sum-pool) for the gradient.  The reference has no deep supervision;
+// the definition is oracle/unetpp.py::DeepSupervisionUnetPlusPlus.
+__global__ void upsample_nearest_f32_kernel(const float* __restrict__ in, int64_t planes, int h, int w, int f,
+                                            float* __restrict__ out) {
+  const int H = h * f, W = w * f;
+  const int64_t total = planes * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int64_t pl = i / ((int64_t)W * H);
+    out[i] = __ldg(in + (pl * h + y / f) * w + x / f);
+  }
+}
+__global__ void sumpool_f32_kernel(const float* __restrict__ in, int64_t planes, int h, int w, int f,
+                                   float* __restrict__ out) {
+  const int H = h * f, W = w * f;
+  const int64_t total = planes * h * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w), y = (int)((i / w) % h);
+    const int64_t pl = i / ((int64_t)w * h);
+    const float* src = in + (pl * H + (int64_t)y * f) * W + (int64_t)x * f;
+    float s = 0.f;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) s += __ldg(src + (int64_t)dy * W + dx);
+    out[i] = s;
+  }
+}
+
 // ------------------------------------------------------------------ head gradient prep
 // dlogits fp32 NCHW -> bf16 NHWC (cpad channels, zero padded); per-class sums -> dbias.
 __global__ void head_grad_prep_kernel(const float* __restrict__ dl, int N, int C, int H, int W,
@@ -1043,6 +1074,24 @@ extern "C" int mmr_upsample_bilinear2x_bwd(const MmrContrib* contribs, int ncont
   const int64_t total = (int64_t)N * H * W * (C / 8);
   upsample_bilinear2x_bwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
       cl, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_upsample_nearest_f32_nchw(const float* in, int64_t planes, int h, int w, int f, float* out,
+                                             mmr_stream_t stream) {
+  MMR_REQUIRE(f >= 1 && f <= 32, "factor must be 1..32");
+  upsample_nearest_f32_kernel<<<ew_blocks(planes * h * w * f * f, 16), kEwThreads, 0, as_stream(stream)>>>(
+      in, planes, h, w, f, out);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_sumpool_f32_nchw(const float* in, int64_t planes, int h, int w, int f, float* out,
+                                    mmr_stream_t stream) {
+  MMR_REQUIRE(f >= 1 && f <= 32, "factor must be 1..32");
+  sumpool_f32_kernel<<<ew_blocks(planes * h * w, 16), kEwThreads, 0, as_stream(stream)>>>(in, planes, h, w, f,
+                                                                                         out);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -349,6 +349,13 @@ class Engine:
             out = _Act(op["out"], (n, Ho, Wo, cout))
             out.buf = self._f32(n, cout, Ho, Wo)  # NCHW fp32 logits
             plan = fprop(out.buf, bias=self.P[op["conv"] + ".bias"])
+            up = op.get("up", 1)
+            unit["up"] = up
+            unit["result"] = out.buf
+            if up > 1 and self.training:   # auxiliary (deep-supervision) head: logits at full resolution
+                unit["result"] = self._f32(n, cout, Ho * up, Wo * up)
+                self._rec(fc, "mmr_upsample_nearest_f32_nchw", out.buf, C.c_int64(n * cout), Ho, Wo, up,
+                          unit["result"])
         else:
             out = _Act(op["out"], (n, Ho, Wo, cout))
             out.buf = self._bf16(*out.shape)
@@ -486,7 +493,12 @@ class Engine:
         if kind == "head":
             # the loss leaves fp32 NCHW dlogits in u["dlogits"]; convert + bias gradient
             if "dlogits" not in u:
-                u["dlogits"] = self._f32(n, u["cout"], ho, wo)
+                u["dlogits"] = self._f32(n, u["cout"], ho, wo, zero=True)
+                if u.get("up", 1) > 1:
+                    u["dlogits_full"] = self._f32(n, u["cout"], ho * u["up"], wo * u["up"], zero=True)
+            if u.get("up", 1) > 1:
+                self._rec(calls, "mmr_sumpool_f32_nchw", u["dlogits_full"], C.c_int64(n * u["cout"]), ho, wo,
+                          u["up"], u["dlogits"])
             self._rec(calls, "mmr_head_grad_prep", u["dlogits"], n, u["cout"], ho, wo, g, cpad,
                       self.G[conv + ".bias"], acc)
             dz = g
@@ -599,6 +611,9 @@ class Engine:
                 self._run(self.repack_calls, st)
                 self._w_versions, self.weights_dirty = ver, False
         self._run(self.fwd_calls, st)
+        heads = self.head_units()
+        if self.training and len(heads) > 1:
+            return [u["result"] for u in heads]
         return self.acts["logits"].buf if "logits" in self.acts else None
 
     def head_units(self):
@@ -609,7 +624,15 @@ class Engine:
         already wrote into `dlogits_buffer()`.  on_ready(param_names) is called (host side, in
         launch order) after the launches that complete those parameters' gradients."""
         if dlogits is not None:
-            self.head_units()[0]["dlogits"].copy_(dlogits, non_blocking=True)
+            heads = self.head_units()
+            grads = list(dlogits) if isinstance(dlogits, (list, tuple)) else [dlogits]
+            assert len(grads) == len(heads), "one gradient per head output"
+            for u, g in zip(heads, grads):
+                dst = u["dlogits_full"] if u.get("up", 1) > 1 else u["dlogits"]
+                if g is None:
+                    dst.zero_()
+                else:
+                    dst.copy_(g, non_blocking=True)
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         calls = self.bwd_calls[bool(accumulate)]
         if on_ready is None:

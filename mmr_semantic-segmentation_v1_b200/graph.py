@@ -107,9 +107,9 @@ def unetpp_graph(encoder_name="resnet18", classes=2, deep_supervision=False):
     ops.append({"op": "head", "out": "logits", "conv": "segmentation_head.0", "src": [("x_0_4", 1)],
                 "k": 3, "cout": classes})
     if deep_supervision:
-        for node in ("x_0_3", "x_0_2", "x_0_1"):
+        for node, up in (("x_0_3", 2), ("x_0_2", 4), ("x_0_1", 8)):
             ops.append({"op": "head", "out": "logits." + node, "conv": "ds_heads." + node,
-                        "src": [(node, 1)], "k": 3, "cout": classes})
+                        "src": [(node, 1)], "k": 3, "cout": classes, "up": up})
     return ops
 
 

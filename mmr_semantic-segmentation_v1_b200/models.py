@@ -99,13 +99,20 @@ class _PlanFunction(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         eng = model._engine_for(x, training=True)
         ctx.model, ctx.eng = model, eng
-        return eng.forward(x).detach()  # a fresh tensor object over the plan's logits buffer
+        out = eng.forward(x)
+        if isinstance(out, list):    # deep supervision: [main, aux...] at full resolution
+            ctx.n_out = len(out)
+            return tuple(t.detach() for t in out)
+        ctx.n_out = 1
+        return out.detach()  # a fresh tensor object over the plan's logits buffer
 
     @staticmethod
-    def backward(ctx, dlogits):
+    def backward(ctx, *dlogits):
         model, eng = ctx.model, ctx.eng
         accumulate = model._grads_live()
-        eng.backward(dlogits.contiguous(), accumulate=accumulate, on_ready=model._on_grads_ready)
+        grads = [g.contiguous() if g is not None else None for g in dlogits]
+        eng.backward(grads if ctx.n_out > 1 else grads[0], accumulate=accumulate,
+                     on_ready=model._on_grads_ready)
         model._publish_grads()
         if model._after_backward is not None:
             model._after_backward()
@@ -208,7 +215,8 @@ class _PlanModel(nn.Module):
         x = x.float() if x.dtype != torch.float32 else x
         if self.training and torch.is_grad_enabled():
             self._ensure_flat(x.device)
-            return _PlanFunction.apply(self, x.contiguous(), *self.parameters())
+            out = _PlanFunction.apply(self, x.contiguous(), *self.parameters())
+            return list(out) if isinstance(out, tuple) else out
         eng = self._engine_for(x, training=self.training)
         return eng.forward(x.contiguous())
 

@@ -102,3 +102,46 @@ def test_no_cpu_fallback():
         net(torch.zeros(1, 3, 32, 32))
     with pytest.raises(RuntimeError):
         net.cuda()(torch.zeros(1, 3, 48, 48, device="cuda"))
+
+
+def test_deep_supervision_train_step_matches_oracle():
+    """BASELINE config 4's model: auxiliary 3x3 heads on x_0_3 / x_0_2 / x_0_1, nearest-upsampled
+    to full resolution, loss = mean over the four outputs (definition: oracle/unetpp.py
+    DeepSupervisionUnetPlusPlus; the reference has no such code)."""
+    from oracle.losses import mixed_loss
+    from oracle.unetpp import DeepSupervisionUnetPlusPlus
+    from mmrseg_b200.losses import DiceCrossEntropyLoss
+    from mmrseg_b200.models import UnetPlusPlus
+    torch.manual_seed(6210)
+    ref = DeepSupervisionUnetPlusPlus("resnet18", None, 3, 2)
+    net = UnetPlusPlus("resnet18", classes=2, deep_supervision=True)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net = net.cuda()
+    x, y = synthetic_batch(4, 2, 64, 64)
+    ref.train()
+    net.train()
+    outs = net(x.cuda())
+    assert isinstance(outs, list) and len(outs) == 4 and all(o.shape == outs[0].shape for o in outs)
+    crit = DiceCrossEntropyLoss(0.5)
+    loss = sum(crit(o, y.cuda()) for o in outs) / len(outs)
+    loss.backward()
+    torch.cuda.synchronize()
+    install_engine_masks(ref, list(net._engines.values())[0])
+    wants = ref(x)
+    loss_ref = sum(mixed_loss(o, y, 0.5) for o in wants) / len(wants)
+    loss_ref.backward()
+    for got, want in zip(outs, wants):
+        assert rel(got.detach().cpu(), want.detach()) <= 8e-2
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item())
+    ref_params = dict(ref.named_parameters())
+    for name, p in net.named_parameters():
+        g, r = p.grad.cpu(), ref_params[name].grad
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
+        # a 2-class head's bias gradient is the sum of softmax gradients that cancel to ~1e-4 of
+        # their magnitude: relative error there is dominated by that cancellation
+        tol = 2.5e-1 if name.endswith("head.0.bias") or name.startswith("ds_heads") and name.endswith("bias") else 1.2e-1
+        assert rel(g, r) <= tol and cos >= 0.99, (name, rel(g, r), cos)
+    # eval mode returns the main head only
+    net.eval()
+    with torch.no_grad():
+        assert net(x.cuda()).shape == (4, 2, 64, 64)
