@@ -406,7 +406,9 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
     cpad = -(-cout // 16) * 16
     seg_sizes = seg_sizes or [cpad]
     best = None
-    for bn in (256, 192, 160, 128, 96, 64, 32, 16):
+    # N tiles wider than 128 (or 96/160/192) are legal for the kernel but measured slower than 64/128 with
+    # a wider macro tile (their weight slots crowd the shared-memory port): scripts/sweep_halo.sh
+    for bn in ((force or {}).get("bn"),) if force and "bn" in force else (128, 64, 32, 16):
         if bn > cpad or cpad % bn:
             continue
         sg = 64 if bn % 64 == 0 else (32 if bn % 32 == 0 else 16)
@@ -440,15 +442,23 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
                             if force and any(cfg[k] != v for k, v in force.items() if k in cfg):
                                 continue
                             items = N * (-(-H // 16)) * (-(-W // (8 * tx))) * n_nt
-                            # issue time of the MMAs, plus the waits of the issuer on a chunk / item boundary
-                            mma = tx * nchunks * 9 * (cb // 16) * _mma_clk(bn) + nchunks * 150 + 600
+                            # One item (tx M tiles x bn channels).  Measured (scripts/probe/probe3.cu, ncu of
+                            # x_1_3.conv1): an SS-mode MMA costs max(bn/2 clk of tensor pipe, its operand bytes
+                            # at 128 B/clk), and the same 128 B/clk shared-memory port also takes the TMA fills
+                            # and the epilogue staging, which is what bounds the bn = 64 layers.
+                            n_mma = tx * nchunks * 9 * (cb // 16)
+                            tensor = n_mma * bn / 2.0
+                            fill = nchunks * (18 * pitch * cb * 2 + 9 * bn * cb * 2)
+                            epi_bytes = tx * 128 * bn * 2 * (2 if sg == 64 else 0)
+                            smem = (n_mma * (4096 + 32 * bn) + fill + epi_bytes) / 128.0
                             # one elected lane issues every TMA of a ring: ~520 clk per operation
-                            # (scripts/probe/probe4.cu), so few large weight slots beat many small ones
                             wprod = nchunks * (9 // tps) * 520
                             hprod = nchunks * (3 if any_up else 1) * 520
-                            traffic = nchunks * (18 * pitch * cb * 2 + 9 * bn * cb * 2) / 70.0
-                            epi = tx * gpn * (450.0 if sg == 64 else 700.0)
-                            per_item = max(mma, wprod, hprod, traffic) + (1.5 * epi if acc_bufs == 1 else 0.0)
+                            traffic = fill / 75.0
+                            epi = tx * gpn * (450.0 if sg == 64 else 300.0)
+                            per_item = max(tensor, smem, wprod, hprod, traffic) + 1200 + nchunks * 150
+                            if acc_bufs == 1:
+                                per_item += 1.5 * epi
                             per_item = max(per_item, epi)
                             if w_slots * tps < 3:
                                 per_item *= 1.15

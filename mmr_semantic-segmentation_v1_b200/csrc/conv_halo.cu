@@ -118,16 +118,77 @@ __device__ __forceinline__ void umma_lohi_acc(uint32_t tmem_d, uint32_t a_lo, ui
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
       : "memory");
 }
-// All MMAs of one filter tap: TX accumulators x KS 16-channel steps against one weight block.
-template <int KS>
-__device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t a_tap, uint32_t a_hi, uint32_t b_tap,
-                                          uint32_t b_hi, uint32_t idesc, int TX, uint32_t tile_step,
-                                          uint32_t bn, uint32_t first_acc) {
-  uint32_t d = d0, a = a_tap;
-  for (int i = 0; i < TX; ++i, d += bn, a += tile_step) {
-    umma_lohi(d, a, a_hi, b_tap, b_hi, idesc, first_acc);
+// The MMA issuer's whole loop, specialised on (16-channel steps per tap, taps per weight slot, M tiles
+// per macro tile): every descriptor offset inside a chunk is a compile-time multiple of a few
+// uniform registers, so the elected lane spends 2-3 uniform instructions per tcgen05.mma.  With the
+// generic loop the issue overhead (~190 clk per MMA) bounded the thin layers (N = 16, K = 16).
+template <int KS, int TPS, int TX>
+__device__ __forceinline__ void mma_warp_loop(const HaloParams& p, uint32_t tmem_base, uint32_t halo0, uint32_t w0,
+                                              uint64_t* halo_full, uint64_t* halo_empty, uint64_t* w_full,
+                                              uint64_t* w_empty, uint64_t* tmem_full, uint64_t* tmem_empty) {
+  const uint32_t idesc = make_idesc_bf16(128, p.bn, 0, 0);
+  const uint32_t rb = (uint32_t)p.rowbytes;
+  const uint32_t swz = swizzle_code(p.rowbytes);
+  const uint32_t hiB = desc_hi32(8 * rb, swz);
+  const uint32_t tile_step = (8 * rb) >> 4;  // next M-tile of the macro tile: 8 pixels to the right
+  const uint32_t px_step = rb >> 4;
+  const uint32_t tap_step = ((uint32_t)p.bn * rb) >> 4;
+  const uint32_t bn = (uint32_t)p.bn;
+  int hs = 0, ws = 0, it = 0;
+  uint32_t hph = 0, wph = 0;
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+    const int buf = it % p.acc_bufs;
+    const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
+    mbar_wait(&tmem_empty[buf], par ^ 1);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + (uint32_t)(buf * TX) * bn;
+    for (int c = 0; c < p.nchunks; ++c) {
+      const int up = p.chunk[c].up;
+      const uint32_t pitch = (uint32_t)p.pitch[up];
+      const uint32_t hiA = desc_hi32(pitch * rb, swz);
+      const uint32_t row_step = (pitch * rb) >> 4;
+      mbar_wait(&halo_full[hs], hph);
+      tc_fence_after();
+      const uint32_t a_stage = ((halo0 + (uint32_t)hs * p.halo_stage_bytes + (up ? rb : 0u)) >> 4) | 0x10000u;
 #pragma unroll
-    for (int k = 1; k < KS; ++k) umma_lohi_acc(d, a + 2 * k, a_hi, b_tap + 2 * k, b_hi, idesc);
+      for (int s = 0; s < 9 / TPS; ++s) {
+        mbar_wait(&w_full[ws], wph);
+        tc_fence_after();
+        const uint32_t b_slot = ((w0 + (uint32_t)ws * p.w_slot_bytes) >> 4) | 0x10000u;
+        if (elect_one()) {
+#pragma unroll
+          for (int tt = 0; tt < TPS; ++tt) {
+            const int tap = s * TPS + tt;  // compile-time after unrolling
+            const uint32_t a_tap = a_stage + (uint32_t)(tap / 3) * row_step + (uint32_t)(tap % 3) * px_step;
+            const uint32_t b_tap = b_slot + (uint32_t)tt * tap_step;
+#pragma unroll
+            for (int i = 0; i < TX; ++i) {
+              const uint32_t d = d0 + (uint32_t)i * bn;
+              const uint32_t a = a_tap + (uint32_t)i * tile_step;
+              if (tap == 0)
+                umma_lohi(d, a, hiA, b_tap, hiB, idesc, (uint32_t)(c != 0));
+              else
+                umma_lohi_acc(d, a, hiA, b_tap, hiB, idesc);
+#pragma unroll
+              for (int k = 1; k < KS; ++k) umma_lohi_acc(d, a + 2 * k, hiA, b_tap + 2 * k, hiB, idesc);
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&w_empty[ws]);
+        if (++ws == p.w_slots) {
+          ws = 0;
+          wph ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&halo_empty[hs]);
+      if (++hs == p.halo_stages) {
+        hs = 0;
+        hph ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit(&tmem_full[buf]);
+    __syncwarp();
   }
 }
 
@@ -256,63 +317,19 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, p.bn, 0, 0);
-    const uint32_t rb = (uint32_t)p.rowbytes;
-    const uint32_t swz = swizzle_code(p.rowbytes);
-    const uint32_t hiB = desc_hi32(8 * rb, swz);
     const uint32_t halo0 = smem_u32(halo_base), w0 = smem_u32(w_base);
-    const uint32_t tile_step = (8 * rb) >> 4;  // next M-tile of the macro tile: 8 pixels to the right
-    const uint32_t tap_bytes = (uint32_t)p.bn * rb;
-    int hs = 0, ws = 0, it = 0;
-    uint32_t hph = 0, wph = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-      const int buf = it % p.acc_bufs;
-      const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
-      mbar_wait(&tmem_empty[buf], par ^ 1);
-      tc_fence_after();
-      const uint32_t d0 = tmem_base + (uint32_t)(buf * p.TX * p.bn);
-      for (int c = 0; c < p.nchunks; ++c) {
-        const int up = p.chunk[c].up;
-        const uint32_t pitch = (uint32_t)p.pitch[up];
-        const uint32_t hiA = desc_hi32(pitch * rb, swz);
-        mbar_wait(&halo_full[hs], hph);
-        tc_fence_after();
-        const uint32_t a_stage = ((halo0 + (uint32_t)hs * p.halo_stage_bytes + (up ? rb : 0u)) >> 4) | 0x10000u;
-        int tap = 0;
-        for (int s = 0; s < p.nslots; ++s) {
-          mbar_wait(&w_full[ws], wph);
-          tc_fence_after();
-          const uint32_t b_slot = ((w0 + (uint32_t)ws * p.w_slot_bytes) >> 4) | 0x10000u;
-          for (int tt = 0; tt < p.tps; ++tt, ++tap) {
-            const uint32_t ky = (uint32_t)tap / 3u, kx = (uint32_t)tap - 3u * ky;
-            const uint32_t a_tap = a_stage + (((ky * pitch + kx) * rb) >> 4);
-            const uint32_t b_tap = b_slot + (((uint32_t)tt * tap_bytes) >> 4);
-            const uint32_t first_acc = (uint32_t)((c | tap) != 0);
-            if (elect_one()) {
-              if (p.KS == 4)
-                issue_tap<4>(d0, a_tap, hiA, b_tap, hiB, idesc, p.TX, tile_step, (uint32_t)p.bn, first_acc);
-              else if (p.KS == 2)
-                issue_tap<2>(d0, a_tap, hiA, b_tap, hiB, idesc, p.TX, tile_step, (uint32_t)p.bn, first_acc);
-              else
-                issue_tap<1>(d0, a_tap, hiA, b_tap, hiB, idesc, p.TX, tile_step, (uint32_t)p.bn, first_acc);
-            }
-          }
-          __syncwarp();
-          if (elect_one()) umma_commit(&w_empty[ws]);
-          if (++ws == p.w_slots) {
-            ws = 0;
-            wph ^= 1;
-          }
-        }
-        if (elect_one()) umma_commit(&halo_empty[hs]);
-        if (++hs == p.halo_stages) {
-          hs = 0;
-          hph ^= 1;
-        }
-      }
-      if (elect_one()) umma_commit(&tmem_full[buf]);
-      __syncwarp();
-    }
+#define MMR_MMA_CASE(KS_, TPS_, TX_)                                                                        \
+  if (p.KS == KS_ && p.tps == TPS_ && p.TX == TX_)                                                          \
+    mma_warp_loop<KS_, TPS_, TX_>(p, tmem_base, halo0, w0, halo_full, halo_empty, w_full, w_empty, tmem_full, \
+                                  tmem_empty);
+#define MMR_MMA_CASES_TX(KS_, TPS_) MMR_MMA_CASE(KS_, TPS_, 1) MMR_MMA_CASE(KS_, TPS_, 2) MMR_MMA_CASE(KS_, TPS_, 4)
+#define MMR_MMA_CASES_TPS(KS_) MMR_MMA_CASES_TX(KS_, 1) MMR_MMA_CASES_TX(KS_, 3) MMR_MMA_CASES_TX(KS_, 9)
+    MMR_MMA_CASES_TPS(1)
+    MMR_MMA_CASES_TPS(2)
+    MMR_MMA_CASES_TPS(4)
+#undef MMR_MMA_CASES_TPS
+#undef MMR_MMA_CASES_TX
+#undef MMR_MMA_CASE
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp - 4;
