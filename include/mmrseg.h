@@ -107,6 +107,25 @@ int mmr_conv_plan_destroy(void* plan);
  * data-gradient half of `loss.backward()`; stride-2, 1x1 and 7x7 convolutions stay on
  * mmr_conv_plan_*.
  * ------------------------------------------------------------------------------------ */
+/* BatchNorm2d training-mode finalisation fused into the kernel that produced the statistics: the
+ * last CTA to finish (ticket counter) turns the accumulated sums into mean / invstd / scale / shift,
+ * updates the running statistics (unbiased variance, momentum) and num_batches_tracked, and re-arms
+ * (zeroes) the statistics slots and the ticket.  Same arithmetic as mmr_bn_finalize. */
+typedef struct {
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float* mean;
+  float* invstd;
+  float* scale;
+  float* shift;
+  int64_t count;    /* values per channel: N*H*W */
+  uint32_t* ticket; /* device counter, zero before the first launch */
+} MmrBnFinalize;
+
 typedef struct {
   const void* ptr; /* bf16 NHWC, stored resolution (half of the conv's when up == 2) */
   int32_t C, W, H, N;
@@ -140,6 +159,7 @@ typedef struct {
    * stored bf16 outputs (BatchNorm batch statistics); consumed by mmr_bn_finalize(nblk = 8). */
   double* stats;
   int32_t stats_ld;
+  const MmrBnFinalize* bn_finalize; /* optional (needs stats): fused mmr_bn_finalize */
 } MmrHaloConvDesc;
 
 int mmr_halo_conv_plan_create(const MmrHaloConvDesc* desc, void** plan);
@@ -285,6 +305,13 @@ typedef struct {
 int mmr_bn_bwd_reduce(const MmrContrib* contribs, int ncontrib, const void* act, const void* z,
                       const float* mean, const float* invstd, int N, int H, int W, int C, void* g,
                       double* partial, int nblk, mmr_stream_t stream);
+/* mmr_bn_bwd_reduce + mmr_bn_bwd_finalize in one launch: block sums go to slots [8][2][C] (double
+ * atomics, zero before the first launch), the last CTA (ticket) writes dgamma / dbeta / coef and
+ * re-arms slots and ticket. */
+int mmr_bn_bwd_reduce_fused(const MmrContrib* contribs, int ncontrib, const void* act, const void* z,
+                            const float* mean, const float* invstd, int N, int H, int W, int C, void* g,
+                            double* slots, int nblk, const float* gamma, float* dgamma, float* dbeta,
+                            int accumulate, float* coef, uint32_t* ticket, mmr_stream_t stream);
 /* partial -> dgamma, dbeta (fp32, accumulate flag) and the coefficients used by apply. */
 int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, int C, const float* gamma,
                         const float* invstd, float* dgamma, float* dbeta, int accumulate,

@@ -52,6 +52,13 @@ class MmrConvDesc(C.Structure):
     ]
 
 
+class MmrBnFinalize(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+                ("mean", C.c_void_p), ("invstd", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("count", C.c_int64), ("ticket", C.c_void_p)]
+
+
 class MmrHaloSrc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
                 ("N", C.c_int32), ("up", C.c_int32)]
@@ -71,6 +78,7 @@ class MmrHaloConvDesc(C.Structure):
         ("residual", C.c_void_p), ("res_ldc", C.c_int32), ("relu", C.c_int32),
         ("out_mode", C.c_int32), ("out_f32", C.c_void_p), ("out_ldc", C.c_int32),
         ("stats", C.c_void_p), ("stats_ld", C.c_int32),
+        ("bn_finalize", C.POINTER(MmrBnFinalize)),
     ]
 
 
@@ -155,6 +163,8 @@ SIGNATURES = {
     "mmr_bn_apply": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "mmr_bn_bwd_reduce": (_i, [C.POINTER(MmrContrib), _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
                                _vp, _i, _vp]),
+    "mmr_bn_bwd_reduce_fused": (_i, [C.POINTER(MmrContrib), _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i,
+                                     _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "mmr_bn_bwd_finalize": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "mmr_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "mmr_grad_gather": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),

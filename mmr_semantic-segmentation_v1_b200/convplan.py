@@ -528,7 +528,7 @@ def pack_weights_halo(w_oihw, cfg, mode, out=None, stream=None):
 
 
 def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=None, residual=None,
-               relu=False, out_f32=None, stats=None, stats_ld=0):
+               relu=False, out_f32=None, stats=None, stats_ld=0, bn_finalize=None):
     """sources: [(tensor [N,Hs,Ws,Cs] bf16, up)], packed: bf16 weights from pack_weights_halo,
     groups: [(dst tensor [N,H,W,ldc] bf16, coff)] one per store group of cfg['sg'] channels (bf16 NHWC
     mode), or out_f32 = fp32 [N,C,H,W] (head logits)."""
@@ -571,6 +571,9 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     d.relu = int(bool(relu))
     d.stats = stats.data_ptr() if stats is not None else None
     d.stats_ld = stats_ld
+    if bn_finalize is not None:
+        d.bn_finalize = C.pointer(bn_finalize)
+        keep.append(bn_finalize)
     plan = HaloPlan(d, keep)
     plan.cfg = cfg
     return plan
@@ -587,7 +590,7 @@ def fprop_halo_cfg(sources, cout, bf16_out=True, force=None):
 
 
 def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=None, relu=False,
-                     out_f32=None, stats=None, stats_ld=0, force=None, packed=None, cfg=None):
+                     out_f32=None, stats=None, stats_ld=0, force=None, packed=None, cfg=None, bn_finalize=None):
     """Forward 3x3 s1 p1 conv over the concatenation of `sources` (see build_fprop)."""
     N = sources[0][0].shape[0]
     H = sources[0][0].shape[1] * sources[0][1]
@@ -604,7 +607,7 @@ def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=No
         assert out.shape[3] >= cfg["cpad"]
         groups = [(out, g * cfg["sg"]) for g in range(cfg["cpad"] // cfg["sg"])]
     plan = build_halo(cfg, sources, packed, groups, N, H, W, cout, scale=scale, bias=bias, residual=residual,
-                      relu=relu, out_f32=out_f32, stats=stats, stats_ld=stats_ld)
+                      relu=relu, out_f32=out_f32, stats=stats, stats_ld=stats_ld, bn_finalize=bn_finalize)
     plan.flops = 2 * N * H * W * cout * 9 * cin
     plan.packed = packed
     return plan

@@ -65,6 +65,7 @@ struct HaloParams {
   int out_ldc, cout_total;
   double* stats;
   int stats_ld;
+  MmrBnFinalize bnf;  // ticket == nullptr: not fused
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -482,6 +483,46 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       }
     }
     if (p.stats && persist) flush_stats(0);
+    if (p.stats && p.bnf.ticket) {
+      // fused BatchNorm finalisation: the last CTA to get here owns the complete sums
+      uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 30);
+      __threadfence();
+      epi_bar();
+      if (m == 0) *flag = atomicAdd(p.bnf.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+      epi_bar();
+      if (*flag) {
+        __threadfence();
+        const double P = (double)p.bnf.count;
+        for (int c = m; c < p.cout_total; c += 128) {
+          double s1 = 0.0, s2 = 0.0;
+          for (int sl = 0; sl < kStatSlots; ++sl) {
+            double* a = p.stats + (size_t)sl * 2 * p.stats_ld + c;
+            s1 += __ldcg(a);
+            s2 += __ldcg(a + p.stats_ld);
+            a[0] = 0.0;
+            a[p.stats_ld] = 0.0;
+          }
+          const double mu = s1 / P;
+          double var = s2 / P - mu * mu;
+          if (var < 0.0) var = 0.0;
+          const float is = (float)(1.0 / sqrt(var + (double)p.bnf.eps));
+          const float ga = p.bnf.gamma ? p.bnf.gamma[c] : 1.f, be = p.bnf.beta ? p.bnf.beta[c] : 0.f;
+          p.bnf.mean[c] = (float)mu;
+          p.bnf.invstd[c] = is;
+          p.bnf.scale[c] = ga * is;
+          p.bnf.shift[c] = be - (float)mu * ga * is;
+          if (p.bnf.running_mean) {
+            const double unbiased = P > 1.0 ? var * P / (P - 1.0) : var;
+            p.bnf.running_mean[c] = (1.f - p.bnf.momentum) * p.bnf.running_mean[c] + p.bnf.momentum * (float)mu;
+            p.bnf.running_var[c] = (1.f - p.bnf.momentum) * p.bnf.running_var[c] + p.bnf.momentum * (float)unbiased;
+          }
+        }
+        if (m == 0) {
+          *p.bnf.ticket = 0u;
+          if (p.bnf.num_batches_tracked) p.bnf.num_batches_tracked[0] += 1;
+        }
+      }
+    }
     if (p.out_mode == MMR_OUT_BF16_NHWC && !p.direct && m == 0) bulk_wait0();
   }
 
@@ -732,6 +773,10 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.cout_total = d->cout_total;
   p.stats = d->stats;
   p.stats_ld = d->stats_ld;
+  if (d->bn_finalize) {
+    MMR_REQUIRE(d->stats != nullptr && d->bn_finalize->ticket != nullptr, "bn_finalize needs stats and a ticket");
+    p.bnf = *d->bn_finalize;
+  }
 
   const size_t maps_bytes = maps.size() * sizeof(CUtensorMap);
   cudaError_t e = cudaMalloc(&pl->dev_blob, maps_bytes);

@@ -292,12 +292,23 @@ __device__ __forceinline__ void finish_row(const ContribList& cl, const RowGeom&
   }
 }
 
+// Fused mmr_bn_bwd_finalize (MODE 1): block sums are added to slots [8][2][C] and the last CTA
+// (ticket) writes dgamma / dbeta / coef, then re-arms slots and ticket.
+struct BwdFused {
+  const float* gamma;
+  float* dgamma;
+  float* dbeta;
+  float* coef;
+  uint32_t* ticket;  // nullptr: not fused, `partial` receives per-block sums
+  int accumulate;
+};
+
 template <int MODE, int NC, bool POOLED>  // MODE 0: stats of z ; 1: bn backward reduce ; 2: plain gradient gather
 __global__ void __launch_bounds__(kEwThreads, 2)
 reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, double* __restrict__ partial,
                    ContribList cl, const __nv_bfloat16* __restrict__ act,
                    const float* __restrict__ mean, const float* __restrict__ invstd, RowGeom geo,
-                   __nv_bfloat16* __restrict__ gout) {
+                   __nv_bfloat16* __restrict__ gout, BwdFused fz) {
   // double accumulators live in shared memory ([j][thread], conflict-free) so that two CTAs of
   // 256 threads fit the register file; the loop itself accumulates in fp32 and flushes every 16
   // iterations.  MODE 1 accumulates sum(g) and sum(g*z); sum(g*xhat) = (sum(g*z) - mean*sum(g))*invstd
@@ -368,20 +379,52 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
         s2 += sd2[j * kEwThreads + k * tpc + cg];
       }
       if (MODE == 1) s2 = (s2 - (double)__ldg(mean + c + j) * s1) * (double)__ldg(invstd + c + j);
-      partial[((size_t)blockIdx.x * 2 + 0) * C + c + j] = s1;
-      partial[((size_t)blockIdx.x * 2 + 1) * C + c + j] = s2;
+      if (MODE == 1 && fz.ticket) {
+        double* sl = partial + (size_t)(blockIdx.x & 7) * 2 * C;
+        atomicAdd(sl + c + j, s1);
+        atomicAdd(sl + C + c + j, s2);
+      } else {
+        partial[((size_t)blockIdx.x * 2 + 0) * C + c + j] = s1;
+        partial[((size_t)blockIdx.x * 2 + 1) * C + c + j] = s2;
+      }
     }
+  }
+  if (MODE == 1 && fz.ticket) {
+    __shared__ uint32_t last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(fz.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int ch = threadIdx.x; ch < C; ch += kEwThreads) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int sl = 0; sl < 8; ++sl) {
+        double* a = partial + (size_t)sl * 2 * C + ch;
+        s1 += __ldcg(a);
+        s2 += __ldcg(a + C);
+        a[0] = 0.0;
+        a[C] = 0.0;
+      }
+      if (fz.dgamma) fz.dgamma[ch] = (fz.accumulate ? fz.dgamma[ch] : 0.f) + (float)s2;
+      if (fz.dbeta) fz.dbeta[ch] = (fz.accumulate ? fz.dbeta[ch] : 0.f) + (float)s1;
+      const double gi = (double)(fz.gamma ? fz.gamma[ch] : 1.f) * (double)invstd[ch];
+      fz.coef[ch] = (float)gi;
+      fz.coef[C + ch] = (float)(-gi * s2 / (double)P);
+      fz.coef[2 * C + ch] = (float)(-gi * s1 / (double)P);
+    }
+    if (threadIdx.x == 0) *fz.ticket = 0u;
   }
 }
 
 template <int MODE>
 static void launch_reduce(int nblk, cudaStream_t st, const __nv_bfloat16* z, uint32_t P, int C, double* partial,
                           const ContribList& cl, const __nv_bfloat16* act, const float* mean, const float* invstd,
-                          RowGeom geo, __nv_bfloat16* g) {
+                          RowGeom geo, __nv_bfloat16* g, BwdFused fz = BwdFused{}) {
   bool pooled = false;
   for (int i = 0; i < cl.n; ++i) pooled |= cl.pool2[i] != 0;
 #define MMR_RR(NC, PL) \
-  reduce_rows_kernel<MODE, NC, PL><<<nblk, kEwThreads, 0, st>>>(z, P, C, partial, cl, act, mean, invstd, geo, g)
+  reduce_rows_kernel<MODE, NC, PL><<<nblk, kEwThreads, 0, st>>>(z, P, C, partial, cl, act, mean, invstd, geo, g, fz)
   if (pooled) {
     switch (cl.n) {
       case 1: MMR_RR(1, true); break;
@@ -909,7 +952,7 @@ extern "C" int mmr_bn_stats(const void* z, int64_t P, int C, double* partial, in
   MMR_REQUIRE(P < ((int64_t)1 << 31), "row count must be below 2^31");
   reduce_rows_kernel<0, 0, false><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, partial, cl, nullptr, nullptr, nullptr,
-      make_geom(1, 1), nullptr);
+      make_geom(1, 1), nullptr, BwdFused{});
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1092,6 +1135,25 @@ extern "C" int mmr_sumpool_f32_nchw(const float* in, int64_t planes, int h, int 
   MMR_REQUIRE(f >= 1 && f <= 32, "factor must be 1..32");
   sumpool_f32_kernel<<<ew_blocks(planes * h * w, 16), kEwThreads, 0, as_stream(stream)>>>(in, planes, h, w, f,
                                                                                          out);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_bn_bwd_reduce_fused(const MmrContrib* contribs, int ncontrib, const void* act, const void* z,
+                                       const float* mean, const float* invstd, int N, int H, int W, int C,
+                                       void* g, double* slots, int nblk, const float* gamma, float* dgamma,
+                                       float* dbeta, int accumulate, float* coef, uint32_t* ticket,
+                                       mmr_stream_t stream) {
+  if (check_rows_layout(C)) return -1;
+  MMR_REQUIRE(slots && coef && ticket, "fused backward reduce needs slots, coef and a ticket");
+  ContribList cl;
+  if (fill_contribs(cl, contribs, ncontrib)) return -1;
+  const int64_t P = (int64_t)N * H * W;
+  MMR_REQUIRE(P < ((int64_t)1 << 31), "row count must be below 2^31");
+  BwdFused fz{gamma, dgamma, dbeta, coef, ticket, accumulate};
+  launch_reduce<1>(nblk, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, slots, cl,
+                   reinterpret_cast<const __nv_bfloat16*>(act), mean, invstd, make_geom(H, W),
+                   reinterpret_cast<__nv_bfloat16*>(g), fz);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

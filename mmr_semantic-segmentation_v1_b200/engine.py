@@ -110,6 +110,12 @@ class Engine:
         self.halo_stats = torch.zeros((HALO_STAT_SLOTS * 2 * 16384,), device=device, dtype=torch.float64)
         self.halo_stats_used = 0
         self.pack_jobs = []
+        # tickets of the fused BatchNorm finalisations (one per launch site) and the shared slots of
+        # the backward reductions; both are re-armed by the kernels themselves
+        self.tickets = torch.zeros((4096,), device=device, dtype=torch.int32)
+        self.tickets_used = 0
+        self.bwd_slots = torch.zeros((8 * 2 * 2048,), device=device, dtype=torch.float64)
+        self.fuse_finalize = not os.environ.get("MMR_NO_FUSED_FINALIZE")
         self.x_in = torch.empty((N, 3, H, W), device=device, dtype=torch.float32)
         self.bn_partial = torch.empty((BN_BLOCKS * 2 * 512,), device=device, dtype=torch.float64)
         # split-K partials of the weight-gradient GEMMs: one buffer, used by one layer at a time
@@ -143,6 +149,12 @@ class Engine:
         self.pack_jobs.append(_lib.MmrPackJob(w.data_ptr(), out.data_ptr(), O, I, mode, cfg["cb"], cfg["bn"],
                                               cfg["n_ntiles"], cfg["nchunks"], 0))
         self.keep += [w, out]
+
+    def _ticket(self):
+        t = self.tickets[self.tickets_used:self.tickets_used + 1]
+        self.tickets_used += 1
+        assert self.tickets_used <= self.tickets.numel()
+        return t
 
     def _nblk(self, P, Cc):
         rows_per_iter = 256 // (Cc // 8)
@@ -213,7 +225,7 @@ class Engine:
         unit.update(bn=bn_name, mean=st[0], invstd=st[1], scale=st[2], shift=st[3], coef=st[4:7])
         self.keep.append(st)
 
-    def _fwd_bn_train(self, unit, z, out, residual, relu, stats=None):
+    def _fwd_bn_train(self, unit, z, out, residual, relu, stats=None, finalized=False):
         """stats: per-channel sums already left by the conv epilogue ([8][2][C] doubles), else a
         separate reduction pass over z."""
         fc = self.fwd_calls
@@ -226,10 +238,11 @@ class Engine:
             partial, nblk = stats, HALO_STAT_SLOTS
         else:
             self._rec(fc, "mmr_bn_stats", z, Pn, Cc, self.bn_partial, nblk)
-        self._rec(fc, "mmr_bn_finalize", partial, nblk, Pn, Cc, self.P[bn + ".weight"],
-                  self.P[bn + ".bias"], C.c_float(1e-5), C.c_float(0.1), self.P[bn + ".running_mean"],
-                  self.P[bn + ".running_var"], self.P[bn + ".num_batches_tracked"], unit["mean"],
-                  unit["invstd"], unit["scale"], unit["shift"])
+        if not finalized:   # else the conv kernel's last CTA already wrote mean / invstd / scale / shift
+            self._rec(fc, "mmr_bn_finalize", partial, nblk, Pn, Cc, self.P[bn + ".weight"],
+                      self.P[bn + ".bias"], C.c_float(1e-5), C.c_float(0.1), self.P[bn + ".running_mean"],
+                      self.P[bn + ".running_var"], self.P[bn + ".num_batches_tracked"], unit["mean"],
+                      unit["invstd"], unit["scale"], unit["shift"])
         self._rec(fc, "mmr_bn_apply", z, Pn, Cc, unit["scale"], unit["shift"], residual, int(relu), out)
 
     def _fwd_stem(self, op):
@@ -337,6 +350,7 @@ class Engine:
             else:
                 kw.pop("stats", None)
                 kw.pop("stats_ld", None)
+                kw.pop("bn_finalize", None)
                 if head:
                     plan = convplan.build_fprop(sources, unit["wf"], k, 1, pad, dst, out_mode=MMR_OUT_F32_NCHW,
                                                 cout=cout, bn=cpad, **kw)
@@ -369,8 +383,18 @@ class Engine:
                     assert self.halo_stats_used + nst <= self.halo_stats.numel()
                     stats = self.halo_stats[self.halo_stats_used:self.halo_stats_used + nst]
                     self.halo_stats_used += nst
-                plan = fprop(unit["z"], bias=bias, stats=stats, stats_ld=cout)
-                self._fwd_bn_train(unit, unit["z"], out.buf, res.buf if res else None, op["relu"], stats)
+                bnf = None
+                if stats is not None and self.fuse_finalize:
+                    bn = op["bn"]
+                    bnf = _lib.MmrBnFinalize(
+                        self.P[bn + ".weight"].data_ptr(), self.P[bn + ".bias"].data_ptr(), 1e-5, 0.1,
+                        self.P[bn + ".running_mean"].data_ptr(), self.P[bn + ".running_var"].data_ptr(),
+                        self.P[bn + ".num_batches_tracked"].data_ptr(), unit["mean"].data_ptr(),
+                        unit["invstd"].data_ptr(), unit["scale"].data_ptr(), unit["shift"].data_ptr(),
+                        n * Ho * Wo, self._ticket().data_ptr())
+                plan = fprop(unit["z"], bias=bias, stats=stats, stats_ld=cout, bn_finalize=bnf)
+                self._fwd_bn_train(unit, unit["z"], out.buf, res.buf if res else None, op["relu"], stats,
+                                   finalized=bnf is not None)
             else:
                 scale = shift = None
                 if op.get("bn"):
@@ -510,10 +534,18 @@ class Engine:
             if u.get("bn"):
                 bn = u["bn"]
                 dz = view(("dz", id(u)), oshape)
-                self._rec(calls, "mmr_bn_bwd_reduce", arr, cnt, relu_act, u["z"], u["mean"], u["invstd"], n,
-                          ho, wo, Cc, g, self.bn_partial, nblk)
-                self._rec(calls, "mmr_bn_bwd_finalize", self.bn_partial, nblk, Pn, Cc, self.P[bn + ".weight"],
-                          u["invstd"], self.G[bn + ".weight"], self.G[bn + ".bias"], acc, u["coef"])
+                if self.fuse_finalize and Cc <= 2048:
+                    if "bwd_ticket" not in u:
+                        u["bwd_ticket"] = self._ticket()
+                    self._rec(calls, "mmr_bn_bwd_reduce_fused", arr, cnt, relu_act, u["z"], u["mean"],
+                              u["invstd"], n, ho, wo, Cc, g, self.bwd_slots, nblk, self.P[bn + ".weight"],
+                              self.G[bn + ".weight"], self.G[bn + ".bias"], acc, u["coef"], u["bwd_ticket"])
+                else:
+                    self._rec(calls, "mmr_bn_bwd_reduce", arr, cnt, relu_act, u["z"], u["mean"], u["invstd"],
+                              n, ho, wo, Cc, g, self.bn_partial, nblk)
+                    self._rec(calls, "mmr_bn_bwd_finalize", self.bn_partial, nblk, Pn, Cc,
+                              self.P[bn + ".weight"], u["invstd"], self.G[bn + ".weight"],
+                              self.G[bn + ".bias"], acc, u["coef"])
                 self._rec(calls, "mmr_bn_bwd_apply", g, u["z"], u["mean"], u["invstd"], u["coef"], Pn, Cc, dz)
             else:
                 has_bias = u["op"].get("bias")
