@@ -58,3 +58,43 @@ tot = sum(v[0] for v in agg.values())
 for name, (ms, cnt) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print("%-40s %8.3f ms  %5.1f %%  %4d launches" % (name, ms, 100 * ms / tot, cnt))
 print("sum of per-call times %.3f ms" % tot)
+
+# the same launch list replayed from a CUDA graph: how much of the step is launch gaps
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    sp2 = C.c_void_p(side.cuda_stream)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for calls in (eng.repack_calls, eng.fwd_calls, eng.bwd_calls[False]):
+            for fn, a in calls:
+                fn(*a, sp2)
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+for label, fn in (("graph replay", graph.replay),):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print("%s of repack+fwd+bwd: %.3f ms" % (label, e0.elapsed_time(e1) / 10))
+
+
+def eager():
+    for calls in (eng.repack_calls, eng.fwd_calls, eng.bwd_calls[False]):
+        for fn, a in calls:
+            fn(*a, sp)
+
+
+for _ in range(3):
+    eager()
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10):
+    eager()
+e1.record()
+torch.cuda.synchronize()
+print("eager launch list of repack+fwd+bwd: %.3f ms" % (e0.elapsed_time(e1) / 10))
