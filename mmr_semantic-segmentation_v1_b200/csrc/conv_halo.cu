@@ -214,6 +214,146 @@ __device__ __forceinline__ ItemCoord decode_item(const HaloParams& p, int item) 
   return c;
 }
 
+// Epilogue of the layers whose whole output-channel set is one store group (Cout = bn = sg in
+// {16, 32, 64}: every full-resolution decoder layer).  Per M tile: SG accumulator columns in one or
+// two TMEM round trips -> scale / bias / residual / ReLU -> bf16 -> swizzled staging tile + TMA store
+// (sg = 64) or straight to global memory (narrow groups).  The BatchNorm batch statistics of the
+// stored (bf16-rounded) values stay in registers for the whole launch -- one fp32 sum and sum of
+// squares per channel and accumulator row -- and are reduced across rows once, by warp shuffles,
+// when the CTA has finished its last item.
+template <int SG, bool STATS>
+__device__ __forceinline__ void epi_narrow(const HaloParams& p, uint32_t tmem_base, uint8_t* out_base,
+                                           uint64_t* tmem_full, uint64_t* tmem_empty, int q, int lane) {
+  constexpr int CH = SG < 32 ? SG : 32;  // accumulator columns per TMEM round trip
+  constexpr int orb = SG * 2;            // staging row bytes
+  const int m = q * 32 + lane;           // accumulator row = pixel (h, w) of the M tile
+  const int h = m >> 3, w = m & 7;
+  const uint32_t xr = row_xor((uint32_t)m, orb);
+  const bool staged = !p.direct;
+  float s1[STATS ? SG : 1], s2[STATS ? SG : 1];
+#pragma unroll
+  for (int j = 0; j < (STATS ? SG : 1); ++j) s1[j] = s2[j] = 0.f;
+  __nv_bfloat16* const gptr = p.group_ptr[0];
+  const int gldc = p.group_ldc[0], gcoff = p.group_coff[0];
+  int it = 0, gcount = 0;
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+    const ItemCoord ic = decode_item(p, item);
+    const int buf = it % p.acc_bufs;
+    const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
+    mbar_wait(&tmem_full[buf], par);
+    tc_fence_after();
+    const int y = ic.y0 + h;
+    for (int i = 0; i < p.TX; ++i) {
+      const int x = ic.x0 + 8 * i + w;
+      const bool valid = y < p.H && x < p.W;
+      const size_t pix = ((size_t)ic.n * p.H + y) * p.W + x;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.TX + i) * SG);
+      uint8_t* stage = out_base;
+      if (staged) {
+        stage += (size_t)(gcount % p.out_stages) * p.out_stage_bytes;
+        if (p.out_stages == 1 && gcount > 0) {
+          if (m == 0) bulk_wait_read0();
+          epi_bar();
+        }
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < SG; c0 += CH) {
+        uint32_t r[CH];
+#pragma unroll
+        for (int k = 0; k < CH; k += 16) tmem_ld16(taddr + c0 + k, reinterpret_cast<uint32_t(&)[16]>(r[k]));
+        tmem_ld_wait();
+        if (i == p.TX - 1 && c0 + CH >= SG) {
+          // every TMEM read of this item is done: hand the accumulators back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.scale) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] *= __ldg(p.scale + min(c0 + j, p.cout_total - 1));
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + min(c0 + j, p.cout_total - 1));
+        }
+        if (p.residual && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_ldc + c0);
+#pragma unroll
+          for (int k = 0; k < CH / 8; ++k) {
+            const uint4 rv = __ldg(rp + k);
+            const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16x2(rr[j]);
+              v[8 * k + 2 * j] += f.x;
+              v[8 * k + 2 * j + 1] += f.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        uint32_t o[CH / 2];
+#pragma unroll
+        for (int j = 0; j < CH / 2; ++j) o[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
+        if (STATS) {
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) {
+            const float f0 = __uint_as_float(o[j] << 16), f1 = __uint_as_float(o[j] & 0xffff0000u);
+            s1[c0 + 2 * j] += f0;
+            s2[c0 + 2 * j] = fmaf(f0, f0, s2[c0 + 2 * j]);
+            s1[c0 + 2 * j + 1] += f1;
+            s2[c0 + 2 * j + 1] = fmaf(f1, f1, s2[c0 + 2 * j + 1]);
+          }
+        }
+        if (staged) {
+          uint8_t* rowp = stage + (size_t)m * orb;
+#pragma unroll
+          for (int k = 0; k < CH / 8; ++k)
+            *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(c0 >> 3) + k) ^ xr) << 4)) =
+                make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        } else if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(gptr + pix * gldc + gcoff + c0);
+#pragma unroll
+          for (int k = 0; k < CH / 8; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        }
+      }
+      if (staged) {
+        if (p.out_stages > 1 && m == 0) bulk_wait_read0();  // the other staging buffer is free again
+        fence_proxy_async_smem();
+        epi_bar();
+        if (m == 0) {
+          tma_store_4d(&p.maps[p.smap0], stage, gcoff, ic.x0 + 8 * i, ic.y0, ic.n);
+          bulk_commit();
+        }
+        ++gcount;
+      }
+    }
+  }
+  if (STATS) {
+    // column sums over the 32 accumulator rows of this warp, then one double atomic per channel
+    // and warp into the CTA's statistics slot (lane c % 32 owns channel c)
+    double* slot = p.stats + (size_t)(blockIdx.x & (kStatSlots - 1)) * 2 * p.stats_ld;
+#pragma unroll
+    for (int c = 0; c < SG; ++c) {
+      float a = s1[c], b = s2[c];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+      }
+      if ((c & 31) == lane && c < p.cout_total) {
+        atomicAdd(slot + c, (double)a);
+        atomicAdd(slot + p.stats_ld + c, (double)b);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -335,6 +475,20 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp - 4;
     const int m = q * 32 + lane;  // accumulator row = pixel (h, w) of the M tile
+    const bool narrow = p.n_ntiles == 1 && p.gpn == 1 && p.out_mode == MMR_OUT_BF16_NHWC;
+    if (narrow) {
+#define MMR_EPI_CASE(SG_)                                                                            \
+  if (p.sg == SG_) {                                                                                 \
+    if (p.stats)                                                                                     \
+      epi_narrow<SG_, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane);                 \
+    else                                                                                             \
+      epi_narrow<SG_, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane);                \
+  }
+      MMR_EPI_CASE(64)
+      MMR_EPI_CASE(32)
+      MMR_EPI_CASE(16)
+#undef MMR_EPI_CASE
+    } else {
     const int h = m >> 3, w = m & 7;
     const int orb = p.sg * 2;  // staging row bytes
     const uint32_t xr = row_xor((uint32_t)m, orb);
@@ -483,6 +637,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       }
     }
     if (p.stats && persist) flush_stats(0);
+    }  // generic epilogue
     if (p.stats && p.bnf.ticket) {
       // fused BatchNorm finalisation: the last CTA to get here owns the complete sums
       uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 30);

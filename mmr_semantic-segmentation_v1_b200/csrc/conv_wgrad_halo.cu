@@ -240,11 +240,16 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
 // flight); rows that belong to no filter tap are skipped before any load.
 __global__ void __launch_bounds__(256)
 wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
+  // 32 outputs (float4 each) per CTA x 8 split lanes (one warp each): a lane sums the splits
+  // k = lane, lane + 8, ... with four loads in flight, the eight lane sums are added in lane order
+  // through shared memory (deterministic), so the serial chain per thread is n_split / 8 long.
+  __shared__ float4 part[8][32];
   const int bn4 = p.bn >> 2;
   const size_t per_slice = (size_t)p.A * 128 * p.bn;
-  const size_t total4 = (size_t)p.A * 128 * bn4 * p.nchunks * p.n_ntiles;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total4;
-       idx += (size_t)gridDim.x * blockDim.x) {
+  const size_t total4 = (size_t)p.A * 128 * bn4 * p.nchunks * p.n_ntiles;  // a multiple of 32
+  const int sl = threadIdx.x >> 5, o = threadIdx.x & 31;
+  for (size_t base = (size_t)blockIdx.x * 32; base < total4; base += (size_t)gridDim.x * 32) {
+    const size_t idx = base + o;
     const int n4 = (int)(idx % bn4);
     size_t t = idx / bn4;
     const int r = (int)(t % 128);
@@ -262,31 +267,43 @@ wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
       chn = r % p.cb;
     }
     const int co = nt * p.bn + n4 * 4, ci = p.chunk[c].ci0 + chn;
-    if (tap >= 9 || co >= p.dst_cout || ci >= p.dst_cin) continue;
-    const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)slice * p.n_split * per_slice +
-                                                        ((size_t)a * 128 + r) * p.bn) + n4;
-    const size_t step = per_slice >> 2;
+    const bool live = tap < 9 && co < p.dst_cout && ci < p.dst_cin;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    int k = 0;
-    for (; k + 4 <= p.n_split; k += 4) {
-      const float4 v0 = __ldg(src + (size_t)k * step), v1 = __ldg(src + (size_t)(k + 1) * step);
-      const float4 v2 = __ldg(src + (size_t)(k + 2) * step), v3 = __ldg(src + (size_t)(k + 3) * step);
-      s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
-      s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
-      s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
-      s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+    if (live) {
+      const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)slice * p.n_split * per_slice +
+                                                          ((size_t)a * 128 + r) * p.bn) + n4;
+      const size_t step = per_slice >> 2;
+      int k = sl;
+      for (; k + 24 < p.n_split; k += 32) {
+        const float4 v0 = __ldg(src + (size_t)k * step), v1 = __ldg(src + (size_t)(k + 8) * step);
+        const float4 v2 = __ldg(src + (size_t)(k + 16) * step), v3 = __ldg(src + (size_t)(k + 24) * step);
+        s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+        s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+        s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
+        s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+      }
+      for (; k < p.n_split; k += 8) {
+        const float4 v = __ldg(src + (size_t)k * step);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
     }
-    for (; k < p.n_split; ++k) {
-      const float4 v = __ldg(src + (size_t)k * step);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-    const float sv[4] = {s.x, s.y, s.z, s.w};
+    part[sl][o] = s;
+    __syncthreads();
+    if (sl == 0 && live) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (co + j >= p.dst_cout) break;
-      float* d = p.dst + ((size_t)(co + j) * p.dst_cin + ci) * 9 + tap;
-      *d = accumulate ? *d + sv[j] : sv[j];
+      for (int j = 1; j < 8; ++j) {
+        const float4 v = part[j][o];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (co + j >= p.dst_cout) break;
+        float* d = p.dst + ((size_t)(co + j) * p.dst_cin + ci) * 9 + tap;
+        *d = accumulate ? *d + sv[j] : sv[j];
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -460,8 +477,8 @@ extern "C" int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t 
   conv_wgrad_halo_kernel<<<grid, kWhThreads, pl->smem_bytes, as_stream(stream)>>>(p);
   MMR_CUDA_CHECK(cudaGetLastError());
   const size_t total = (size_t)p.A * 128 * (p.bn / 4) * p.nchunks * p.n_ntiles;
-  int64_t blocks = (int64_t)((total + 255) / 256);
-  const int64_t cap = (int64_t)num_sms() * 8;
+  int64_t blocks = (int64_t)((total + 31) / 32);
+  const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   wgrad_halo_reduce_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(p, accumulate);
   MMR_CUDA_CHECK(cudaGetLastError());

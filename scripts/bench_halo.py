@@ -69,7 +69,10 @@ def main():
                     dst = torch.empty((cout, cin, 3, 3), device="cuda")
                     plan = convplan.build_wgrad_halo(dz, sources, dst, force=force)
                 elif kind == "fprop":
-                    plan = convplan.build_fprop_halo(sources, w, out, force=force)
+                    stats = None
+                    if os.environ.get("STATS"):   # BatchNorm batch statistics in the epilogue, as the training step runs it
+                        stats = torch.zeros((8 * 2 * cout,), device="cuda", dtype=torch.float64)
+                    plan = convplan.build_fprop_halo(sources, w, out, force=force, stats=stats, stats_ld=cout)
                 else:
                     cz = -(-cout // 16) * 16
                     dz = torch.randn((N, hw, hw, cz), generator=gen, device="cuda").to(torch.bfloat16)

@@ -28,13 +28,13 @@ sp = C.c_void_p(stream.cuda_stream)
 pk = bench.peaks()["tflops"]
 
 
-def time_call(fn, args):
+def time_call(plan):
     best = 1e9
     for _ in range(reps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        fn(*args, sp)
+        plan.run(stream.cuda_stream)
         e1.record(stream)
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
@@ -47,13 +47,10 @@ for u in eng.units:
     if "fplan" not in u:
         continue
     name = u["op"]["conv"]
-    for kind, plan, fn, args in (("fprop", u.get("fplan"), lib.mmr_conv_plan_run, None),
-                                 ("dgrad", u.get("dplan"), lib.mmr_conv_plan_run, None),
-                                 ("wgrad", u.get("wplan"), lib.mmr_wgrad_plan_run, None)):
+    for kind, plan in (("fprop", u.get("fplan")), ("dgrad", u.get("dplan")), ("wgrad", u.get("wplan"))):
         if plan is None:
             continue
-        a = (plan.handle, 0) if kind != "wgrad" else (plan.handle, 0, 0)
-        ms = time_call(fn, a)
+        ms = time_call(plan)
         tf = plan.flops / (ms * 1e-3) / 1e12
         rows.append((name, kind, plan.flops / 1e9, ms, tf, tf / pk))
 os.makedirs("profiles", exist_ok=True)
