@@ -23,6 +23,8 @@
 //              shared memory -> TMA store; per-channel sum / sum of squares of the stored values
 //              (BatchNorm batch statistics) are taken from the staging tile on the way.
 // Accumulators are double-buffered in TMEM when 2*TX*bn <= 512 columns.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.h"
@@ -66,6 +68,7 @@ struct HaloParams {
   double* stats;
   int stats_ld;
   MmrBnFinalize bnf;  // ticket == nullptr: not fused
+  int dbg;  // diagnostics (MMR_HALO_DBG): 1 no MMA issue, 2 no epilogue work, 4 no halo TMA, 8 no weight TMA
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -156,7 +159,7 @@ __device__ __forceinline__ void mma_warp_loop(const HaloParams& p, uint32_t tmem
         mbar_wait(&w_full[ws], wph);
         tc_fence_after();
         const uint32_t b_slot = ((w0 + (uint32_t)ws * p.w_slot_bytes) >> 4) | 0x10000u;
-        if (elect_one()) {
+        if (!(p.dbg & 1) && elect_one()) {
 #pragma unroll
           for (int tt = 0; tt < TPS; ++tt) {
             const int tap = s * TPS + tt;  // compile-time after unrolling
@@ -214,27 +217,33 @@ __device__ __forceinline__ ItemCoord decode_item(const HaloParams& p, int item) 
   return c;
 }
 
-// Epilogue of the layers whose whole output-channel set is one store group (Cout = bn = sg in
-// {16, 32, 64}: every full-resolution decoder layer).  Per M tile: SG accumulator columns in one or
-// two TMEM round trips -> scale / bias / residual / ReLU -> bf16 -> swizzled staging tile + TMA store
-// (sg = 64) or straight to global memory (narrow groups).  The BatchNorm batch statistics of the
+// Epilogue of every bf16 NHWC plan whose store groups use their default path (TMA store for 64-channel
+// groups, straight-to-global for narrower ones).  SG, the statistics mode and "no scale / bias /
+// residual / ReLU" (PLAIN: every training-time launch) are compile-time, so the per-group body is
+// straight-line code.  Each epilogue warp owns the 32 accumulator rows of its TMEM lanes = 4 image rows
+// x 8 pixels, stages them in its own 4 KB slice of the staging tile and issues its own TMA store:
+// no CTA-wide barrier on the way, the four warps drift freely.
+// STATS (needs one channel set per CTA: n_ntiles = gpn = 1): the BatchNorm batch statistics of the
 // stored (bf16-rounded) values stay in registers for the whole launch -- one fp32 sum and sum of
 // squares per channel and accumulator row -- and are reduced across rows once, by warp shuffles,
 // when the CTA has finished its last item.
-template <int SG, bool STATS>
-__device__ __forceinline__ void epi_narrow(const HaloParams& p, uint32_t tmem_base, uint8_t* out_base,
-                                           uint64_t* tmem_full, uint64_t* tmem_empty, int q, int lane) {
-  constexpr int CH = SG < 32 ? SG : 32;  // accumulator columns per TMEM round trip
-  constexpr int orb = SG * 2;            // staging row bytes
-  const int m = q * 32 + lane;           // accumulator row = pixel (h, w) of the M tile
+template <int N>
+__device__ __forceinline__ void bulk_wait_read_n() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <int SG, bool STATS, bool PLAIN>
+__device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base, uint8_t* out_base,
+                                         uint64_t* tmem_full, uint64_t* tmem_empty, int q, int lane) {
+  constexpr bool STAGED = SG == 64;
+  constexpr int CH = (STATS && SG > 32) ? 32 : SG;  // accumulator columns per TMEM round trip
+  constexpr int orb = SG * 2;                       // staging row bytes
+  const int m = q * 32 + lane;                      // accumulator row = pixel (h, w) of the M tile
   const int h = m >> 3, w = m & 7;
   const uint32_t xr = row_xor((uint32_t)m, orb);
-  const bool staged = !p.direct;
   float s1[STATS ? SG : 1], s2[STATS ? SG : 1];
 #pragma unroll
   for (int j = 0; j < (STATS ? SG : 1); ++j) s1[j] = s2[j] = 0.f;
-  __nv_bfloat16* const gptr = p.group_ptr[0];
-  const int gldc = p.group_ldc[0], gcoff = p.group_coff[0];
   int it = 0, gcount = 0;
   for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
     const ItemCoord ic = decode_item(p, item);
@@ -243,97 +252,114 @@ __device__ __forceinline__ void epi_narrow(const HaloParams& p, uint32_t tmem_ba
     mbar_wait(&tmem_full[buf], par);
     tc_fence_after();
     const int y = ic.y0 + h;
-    for (int i = 0; i < p.TX; ++i) {
-      const int x = ic.x0 + 8 * i + w;
-      const bool valid = y < p.H && x < p.W;
-      const size_t pix = ((size_t)ic.n * p.H + y) * p.W + x;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.TX + i) * SG);
-      uint8_t* stage = out_base;
-      if (staged) {
-        stage += (size_t)(gcount % p.out_stages) * p.out_stage_bytes;
-        if (p.out_stages == 1 && gcount > 0) {
-          if (m == 0) bulk_wait_read0();
-          epi_bar();
-        }
-      }
-#pragma unroll
-      for (int c0 = 0; c0 < SG; c0 += CH) {
-        uint32_t r[CH];
-#pragma unroll
-        for (int k = 0; k < CH; k += 16) tmem_ld16(taddr + c0 + k, reinterpret_cast<uint32_t(&)[16]>(r[k]));
-        tmem_ld_wait();
-        if (i == p.TX - 1 && c0 + CH >= SG) {
-          // every TMEM read of this item is done: hand the accumulators back to the MMA warp
-          tc_fence_before();
+    if (p.dbg & 2) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      continue;
+    }
+    for (int g = 0; g < p.gpn; ++g) {
+      const int ch0 = ic.nt * p.bn + g * SG;
+      const int gi = ic.nt * p.gpn + g;
+      __nv_bfloat16* const gptr = p.group_ptr[gi];
+      const int gldc = p.group_ldc[gi], gcoff = p.group_coff[gi];
+      for (int i = 0; i < p.TX; ++i, ++gcount) {
+        const int x = ic.x0 + 8 * i + w;
+        const bool valid = y < p.H && x < p.W;
+        const size_t pix = ((size_t)ic.n * p.H + y) * p.W + x;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                               (uint32_t)((buf * p.TX + i) * p.bn + g * SG);
+        uint8_t* stage = out_base + (size_t)(gcount % p.out_stages) * p.out_stage_bytes;
+        if (STAGED && gcount >= p.out_stages) {
+          // this warp's slice of the staging buffer is free once its store from out_stages groups
+          // ago has been read out of shared memory
+          if (lane == 0) {
+            if (p.out_stages == 1) bulk_wait_read_n<0>(); else bulk_wait_read_n<1>();
+          }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
-        float v[CH];
+        const bool last = (g == p.gpn - 1) && (i == p.TX - 1);
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.scale) {
+        for (int c0 = 0; c0 < SG; c0 += CH) {
+          uint32_t r[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] *= __ldg(p.scale + min(c0 + j, p.cout_total - 1));
-        }
-        if (p.bias) {
+          for (int k = 0; k < CH; k += 16) tmem_ld16(taddr + c0 + k, reinterpret_cast<uint32_t(&)[16]>(r[k]));
+          tmem_ld_wait();
+          if (last && c0 + CH >= SG) {
+            // every TMEM read of this item is done: hand the accumulators back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+          }
+          float v[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + min(c0 + j, p.cout_total - 1));
-        }
-        if (p.residual && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_ldc + c0);
+          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+          if (!PLAIN) {
+            if (p.scale) {
 #pragma unroll
-          for (int k = 0; k < CH / 8; ++k) {
-            const uint4 rv = __ldg(rp + k);
-            const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+              for (int j = 0; j < CH; ++j) v[j] *= __ldg(p.scale + min(ch0 + c0 + j, p.cout_total - 1));
+            }
+            if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16x2(rr[j]);
-              v[8 * k + 2 * j] += f.x;
-              v[8 * k + 2 * j + 1] += f.y;
+              for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + min(ch0 + c0 + j, p.cout_total - 1));
+            }
+            if (p.residual && valid) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_ldc + ch0 + c0);
+#pragma unroll
+              for (int k = 0; k < CH / 8; ++k) {
+                const uint4 rv = __ldg(rp + k);
+                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16x2(rr[j]);
+                  v[8 * k + 2 * j] += f.x;
+                  v[8 * k + 2 * j + 1] += f.y;
+                }
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
             }
           }
-        }
-        if (p.relu) {
+          uint32_t o[CH / 2];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        uint32_t o[CH / 2];
+          for (int j = 0; j < CH / 2; ++j) o[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
+          if (STATS) {
 #pragma unroll
-        for (int j = 0; j < CH / 2; ++j) o[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
-        if (STATS) {
+            for (int j = 0; j < CH / 2; ++j) {
+              const float f0 = __uint_as_float(o[j] << 16), f1 = __uint_as_float(o[j] & 0xffff0000u);
+              s1[c0 + 2 * j] += f0;
+              s2[c0 + 2 * j] = fmaf(f0, f0, s2[c0 + 2 * j]);
+              s1[c0 + 2 * j + 1] += f1;
+              s2[c0 + 2 * j + 1] = fmaf(f1, f1, s2[c0 + 2 * j + 1]);
+            }
+          }
+          if (STAGED) {
+            uint8_t* rowp = stage + (size_t)m * orb;
 #pragma unroll
-          for (int j = 0; j < CH / 2; ++j) {
-            const float f0 = __uint_as_float(o[j] << 16), f1 = __uint_as_float(o[j] & 0xffff0000u);
-            s1[c0 + 2 * j] += f0;
-            s2[c0 + 2 * j] = fmaf(f0, f0, s2[c0 + 2 * j]);
-            s1[c0 + 2 * j + 1] += f1;
-            s2[c0 + 2 * j + 1] = fmaf(f1, f1, s2[c0 + 2 * j + 1]);
+            for (int k = 0; k < CH / 8; ++k)
+              *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(c0 >> 3) + k) ^ xr) << 4)) =
+                  make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+          } else if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(gptr + pix * gldc + gcoff + c0);
+#pragma unroll
+            for (int k = 0; k < CH / 8; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
           }
         }
-        if (staged) {
-          uint8_t* rowp = stage + (size_t)m * orb;
-#pragma unroll
-          for (int k = 0; k < CH / 8; ++k)
-            *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(c0 >> 3) + k) ^ xr) << 4)) =
-                make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-        } else if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(gptr + pix * gldc + gcoff + c0);
-#pragma unroll
-          for (int k = 0; k < CH / 8; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        if (STAGED) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.maps[p.smap0 + gi], stage + (size_t)q * 32 * orb, gcoff, ic.x0 + 8 * i, ic.y0 + 4 * q,
+                         ic.n);
+            bulk_commit();
+          }
         }
-      }
-      if (staged) {
-        if (p.out_stages > 1 && m == 0) bulk_wait_read0();  // the other staging buffer is free again
-        fence_proxy_async_smem();
-        epi_bar();
-        if (m == 0) {
-          tma_store_4d(&p.maps[p.smap0], stage, gcoff, ic.x0 + 8 * i, ic.y0, ic.n);
-          bulk_commit();
-        }
-        ++gcount;
       }
     }
   }
+  if (STAGED && lane == 0) bulk_wait0();
   if (STATS) {
     // column sums over the 32 accumulator rows of this warp, then one double atomic per channel
     // and warp into the CTA's statistics slot (lane c % 32 owns channel c)
@@ -407,7 +433,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       const ItemCoord ic = decode_item(p, item);
       for (int c = 0; c < p.nchunks; ++c) {
         mbar_wait(&halo_empty[hs], hph ^ 1);
-        if (elect_one()) {
+        if ((p.dbg & 4) && elect_one()) mbar_arrive(&halo_full[hs]);
+        if (!(p.dbg & 4) && elect_one()) {
           const HaloChunk ch = p.chunk[c];
           uint8_t* dst = halo_base + (size_t)hs * p.halo_stage_bytes;
           if (!ch.up) {
@@ -443,7 +470,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       for (int c = 0; c < p.nchunks; ++c) {
         for (int s = 0; s < p.nslots; ++s) {
           mbar_wait(&w_empty[ws], wph ^ 1);
-          if (elect_one()) {
+          if ((p.dbg & 8) && elect_one()) mbar_arrive(&w_full[ws]);
+          if (!(p.dbg & 8) && elect_one()) {
             mbar_arrive_expect_tx(&w_full[ws], p.w_tx_bytes);
             tma_load_2d(w_base + (size_t)ws * p.w_slot_bytes, &p.maps[p.wmap], &w_full[ws], 0, row);
           }
@@ -475,19 +503,21 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp - 4;
     const int m = q * 32 + lane;  // accumulator row = pixel (h, w) of the M tile
-    const bool narrow = p.n_ntiles == 1 && p.gpn == 1 && p.out_mode == MMR_OUT_BF16_NHWC;
-    if (narrow) {
-#define MMR_EPI_CASE(SG_)                                                                            \
-  if (p.sg == SG_) {                                                                                 \
-    if (p.stats)                                                                                     \
-      epi_narrow<SG_, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane);                 \
-    else                                                                                             \
-      epi_narrow<SG_, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane);                \
-  }
+    // fast path: default store mode of the group width, statistics (if any) of one channel set per CTA
+    const bool plain = !p.scale && !p.bias && !p.residual && !p.relu;
+    const bool fast = p.out_mode == MMR_OUT_BF16_NHWC && (p.direct != 0) == (p.sg < 64) &&
+                      (p.stats == nullptr || (p.n_ntiles == 1 && p.gpn == 1 && plain));
+    if (fast) {
+#define MMR_EPI_CASE2(SG_, ST_, PL_)                                                                   \
+  if (p.sg == SG_ && (p.stats != nullptr) == ST_ && plain == PL_)                                      \
+    epi_fast<SG_, ST_, PL_>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane);
+#define MMR_EPI_CASE(SG_)                                                                              \
+  MMR_EPI_CASE2(SG_, true, true) MMR_EPI_CASE2(SG_, false, true) MMR_EPI_CASE2(SG_, false, false)
       MMR_EPI_CASE(64)
       MMR_EPI_CASE(32)
       MMR_EPI_CASE(16)
 #undef MMR_EPI_CASE
+#undef MMR_EPI_CASE2
     } else {
     const int h = m >> 3, w = m & 7;
     const int orb = p.sg * 2;  // staging row bytes
@@ -616,7 +646,9 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
             epi_bar();
             if (m == 0 && !p.direct) {
               const int gi = ic.nt * p.gpn + g;
-              tma_store_4d(&p.maps[p.smap0 + gi], stage, p.group_coff[gi], ic.x0 + 8 * i, ic.y0, ic.n);
+              for (int qq = 0; qq < 4; ++qq)  // the store box is one warp's slice: 4 image rows
+                tma_store_4d(&p.maps[p.smap0 + gi], stage + (size_t)qq * 32 * orb, p.group_coff[gi], ic.x0 + 8 * i,
+                             ic.y0 + 4 * qq, ic.n);
               bulk_commit();
             }
             if (p.stats) {
@@ -891,7 +923,7 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
       cuuint64_t dims[4] = {(cuuint64_t)og.ldc, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
       cuuint64_t str[3] = {(cuuint64_t)og.ldc * 2, (cuuint64_t)og.ldc * 2 * d->W,
                            (cuuint64_t)og.ldc * 2 * d->W * d->H};
-      cuuint32_t box[4] = {(cuuint32_t)p.sg, 8, 16, 1};
+      cuuint32_t box[4] = {(cuuint32_t)p.sg, 8, 4, 1};
       maps.emplace_back();
       if (encode_generic(&maps.back(), og.ptr, 4, dims, str, box, p.sg * 2, "store group")) { delete pl; return -1; }
       p.group_coff[g] = og.coff;
@@ -928,6 +960,7 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.cout_total = d->cout_total;
   p.stats = d->stats;
   p.stats_ld = d->stats_ld;
+  if (const char* dbg = getenv("MMR_HALO_DBG")) p.dbg = atoi(dbg);
   if (d->bn_finalize) {
     MMR_REQUIRE(d->stats != nullptr && d->bn_finalize->ticket != nullptr, "bn_finalize needs stats and a ticket");
     p.bnf = *d->bn_finalize;
