@@ -106,6 +106,9 @@ class Engine:
         self.weights_dirty = True
         self.param_ready_hooks = []  # (index in bwd call list, [param names]) for DDP overlap
         self.use_halo = not os.environ.get("MMR_NO_HALO")
+        self.use_graphs = not os.environ.get("MMR_NO_GRAPH")
+        self._graphs = {}
+        self._train_calls = None
         # BatchNorm statistics taken in the conv epilogues: [unit][slot][2][C] doubles, bump-allocated
         self.halo_stats = torch.zeros((HALO_STAT_SLOTS * 2 * 16384,), device=device, dtype=torch.float64)
         self.halo_stats_used = 0
@@ -622,9 +625,35 @@ class Engine:
 
     # ------------------------------------------------------------------ execution
     def _run(self, calls, stream, lo=0, hi=None):
+        """Replay calls[lo:hi].  On torch's current stream (stream None) a segment is launched eagerly
+        the first time (kernel attributes, lazily allocated workspaces), captured into a CUDA graph the
+        second time and replayed from then on: every argument of a plan is fixed at build time, so the
+        graph stays valid for the life of the engine and the ~300 launches of a step cost one."""
+        hi = len(calls) if hi is None else hi
+        if hi <= lo:
+            return
+        if stream is None and self.use_graphs:
+            key = (id(calls), lo, hi)
+            g = self._graphs.get(key)
+            if g is None:
+                self._graphs[key] = False          # seen once: capture on the next use
+            elif g is False:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._launch(calls, torch.cuda.current_stream().cuda_stream, lo, hi)
+                self._graphs[key] = g
+                g.replay()
+                return
+            else:
+                g.replay()
+                return
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self._launch(calls, st, lo, hi)
+
+    def _launch(self, calls, stream, lo, hi):
         s = C.c_void_p(stream)
         err = 0
-        for fn, args in (calls[lo:hi] if (lo or hi is not None) else calls):
+        for fn, args in calls[lo:hi]:
             err |= fn(*args, s)
         if err:
             raise _lib.MmrError(self.lib.mmr_last_error().decode(errors="replace"))
@@ -633,16 +662,17 @@ class Engine:
         """x: fp32 NCHW [N,3,H,W] on the device (copied into the plan's input buffer)."""
         if x is not None:
             self.x_in.copy_(x, non_blocking=True)
-        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         if self.training:
-            self._run(self.repack_calls, st)  # the optimiser rewrites the fp32 masters every step
+            if self._train_calls is None:   # the optimiser rewrites the fp32 masters every step
+                self._train_calls = self.repack_calls + self.fwd_calls
+            self._run(self._train_calls, stream)
         else:
             self.refresh_folded()
             ver = tuple(t._version for t in self.P.values())
             if ver != self._w_versions or self.weights_dirty:
-                self._run(self.repack_calls, st)
+                self._run(self.repack_calls, stream)
                 self._w_versions, self.weights_dirty = ver, False
-        self._run(self.fwd_calls, st)
+            self._run(self.fwd_calls, stream)
         heads = self.head_units()
         if self.training and len(heads) > 1:
             return [u["result"] for u in heads]
@@ -651,7 +681,7 @@ class Engine:
     def head_units(self):
         return [u for u in self.units if u["kind"] == "head"]
 
-    def backward(self, dlogits=None, accumulate=False, stream=None, on_ready=None):
+    def backward(self, dlogits=None, accumulate=False, stream=None, on_ready=None, cuts=None):
         """dlogits: fp32 NCHW gradient of the main head (copied in), or None when a loss kernel
         already wrote into `dlogits_buffer()`.  on_ready(param_names) is called (host side, in
         launch order) after the launches that complete those parameters' gradients."""
@@ -665,17 +695,23 @@ class Engine:
                     dst.zero_()
                 else:
                     dst.copy_(g, non_blocking=True)
-        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         calls = self.bwd_calls[bool(accumulate)]
         if on_ready is None:
-            self._run(calls, st)
+            self._run(calls, stream)
             return
-        lo = 0
-        for hi, names in self.param_ready_hooks:
-            self._run(calls, st, lo, hi)
+        # cuts: the hook positions after which the caller wants control (DDP: where a gradient bucket
+        # is complete); the hooks in between are coalesced so that a segment is one graph launch
+        lo, names = 0, []
+        for hi, ns in self.param_ready_hooks:
+            names += ns
+            if cuts is not None and hi not in cuts:
+                continue
+            self._run(calls, stream, lo, hi)
             on_ready(names)
-            lo = hi
-        self._run(calls, st, lo, len(calls))
+            lo, names = hi, []
+        self._run(calls, stream, lo, len(calls))
+        if names:
+            on_ready(names)
 
     def dlogits_buffer(self, which=0):
         return self.head_units()[which]["dlogits"]

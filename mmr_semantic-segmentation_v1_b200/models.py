@@ -111,8 +111,9 @@ class _PlanFunction(torch.autograd.Function):
         model, eng = ctx.model, ctx.eng
         accumulate = model._grads_live()
         grads = [g.contiguous() if g is not None else None for g in dlogits]
+        cuts = model._grad_cuts(eng.param_ready_hooks) if model._grad_cuts is not None else None
         eng.backward(grads if ctx.n_out > 1 else grads[0], accumulate=accumulate,
-                     on_ready=model._on_grads_ready)
+                     on_ready=model._on_grads_ready, cuts=cuts)
         model._publish_grads()
         if model._after_backward is not None:
             model._after_backward()
@@ -131,6 +132,7 @@ class _PlanModel(nn.Module):
         self._flat = None
         self._on_grads_ready = None  # DDP installs callbacks here
         self._after_backward = None
+        self._grad_cuts = None       # DDP: hook positions where a gradient bucket completes
 
     # ---- flat parameter storage ------------------------------------------------------------
     def _flatten(self, device):

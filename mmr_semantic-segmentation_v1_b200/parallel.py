@@ -18,8 +18,10 @@ class DistributedDataParallel(torch.nn.Module):
         self.world = dist.get_world_size(self.pg) if dist.is_initialized() else 1
         self._buckets = None
         self._side = None
+        self._cuts = {}
         module._on_grads_ready = self._ready
         module._after_backward = self._finish
+        module._grad_cuts = self.cuts
 
     def forward(self, *a, **k):
         return self.module(*a, **k)
@@ -51,6 +53,22 @@ class DistributedDataParallel(torch.nn.Module):
             dist.broadcast(m._flat, 0, group=self.pg)
             for b in m.buffers():
                 dist.broadcast(b, 0, group=self.pg)
+
+    def cuts(self, hooks):
+        """hooks: the engine's [(position in the backward launch list, [parameter names])].  Returns the
+        positions at which some bucket has all its gradients: the backward plan is replayed as one CUDA
+        graph per stretch between two of them, and the bucket's all-reduce starts at the cut."""
+        if self._buckets is None:
+            self._setup()
+        key = id(hooks)
+        if self._cuts.get(key) is None:
+            ready_at = {}
+            for pos, names in hooks:
+                for n in names:
+                    ready_at.setdefault(n, pos)
+            last = max(pos for pos, _ in hooks)
+            self._cuts[key] = {max(ready_at.get(n, last) for n in names) for _, _, names in self._buckets}
+        return self._cuts[key]
 
     def sync_parameters(self):
         """Call once after the model is on its device and flattened."""

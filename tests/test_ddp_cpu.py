@@ -17,6 +17,7 @@ class _FakePlanModel(torch.nn.Module):
         self.c = torch.nn.Parameter(torch.zeros(10))
         self._on_grads_ready = None
         self._after_backward = None
+        self._grad_cuts = None
         names = ["a", "b", "c"]
         offs, tot = {}, 0
         for n in names:
@@ -48,6 +49,21 @@ def _worker(rank, world, port):
         m._after_backward()
         want = torch.arange(m._gflat.numel(), dtype=torch.float32) * (sum(range(1, world + 1)) / world)
         assert torch.allclose(m._gflat, want), (rank, step)
+    # cut positions of the engine's backward launch list: every bucket closes at the hook of its last
+    # parameter; coalescing the hooks between two cuts (engine.Engine.backward) still reduces everything
+    hooks = [(3, ["c"]), (7, ["b"]), (9, ["a"])]
+    cuts = m._grad_cuts(hooks)
+    assert cuts and cuts <= {3, 7, 9} and 9 in cuts
+    m._gflat.copy_(torch.arange(m._gflat.numel(), dtype=torch.float32) * (rank + 1))
+    names = []
+    for pos, ns in hooks:
+        names += ns
+        if pos in cuts:
+            m._on_grads_ready(names)
+            names = []
+    assert not names
+    m._after_backward()
+    assert torch.allclose(m._gflat, want), rank
     dist.destroy_process_group()
 
 
