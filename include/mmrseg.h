@@ -260,10 +260,16 @@ int mmr_wgrad_halo_plan_destroy(void* plan);
  * Layout / packing kernels at the boundary of the path.
  * ------------------------------------------------------------------------------------ */
 /* NCHW fp32 image -> im2col rows for the 7x7 stride-2 pad-3 stem (encoder.conv1), bf16
- * [N*Ho*Wo][kpad], column = (ky*7+kx)*3 + c, zero padded to kpad.  Optionally applies
- * (x-mean[c])/std[c] first (utils.normalize, SU/utils.py:480-519) when mean != NULL. */
+ * [N*Ho*Wo][kpad], column = c*49 + ky*7 + kx (the OIHW order of conv1.weight[o]), zero padded to kpad
+ * (152 <= kpad <= 256).  Optionally applies (x-mean[c])/std[c] first (utils.normalize,
+ * SU/utils.py:480-519) when mean != NULL. */
 int mmr_stem_im2col(const float* x, int N, int H, int W, void* out, int kpad, const float* mean,
                     const float* std_, mmr_stream_t stream);
+/* The same from uint8 HWC frames [N][H][W][3] (what the data loaders hold before ToTensor,
+ * SU/SegNetDataLoaderV1_SAR.py:150-151): x/255, then the optional normalisation.  Replaces the CPU
+ * ToTensor + utils.normalize + fp32 host-to-device copy in front of the model. */
+int mmr_stem_im2col_u8(const uint8_t* x_nhwc, int N, int H, int W, void* out, int kpad, const float* mean,
+                       const float* std_, mmr_stream_t stream);
 /* NCHW fp32 -> NHWC bf16 with channel padding to cpad (zeros). */
 int mmr_pack_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, void* out,
                                    int cpad, mmr_stream_t stream);
@@ -307,11 +313,14 @@ int mmr_bn_bwd_reduce(const MmrContrib* contribs, int ncontrib, const void* act,
                       double* partial, int nblk, mmr_stream_t stream);
 /* mmr_bn_bwd_reduce + mmr_bn_bwd_finalize in one launch: block sums go to slots [8][2][C] (double
  * atomics, zero before the first launch), the last CTA (ticket) writes dgamma / dbeta / coef and
- * re-arms slots and ticket. */
+ * re-arms slots and ticket.  ReLU mask: (act > 0) when act != NULL, or -- for units without a
+ * residual -- (z * mask_scale + mask_shift > 0) with the forward pass's scale / shift, which is the
+ * same predicate without reading the activation back; neither: no mask. */
 int mmr_bn_bwd_reduce_fused(const MmrContrib* contribs, int ncontrib, const void* act, const void* z,
                             const float* mean, const float* invstd, int N, int H, int W, int C, void* g,
                             double* slots, int nblk, const float* gamma, float* dgamma, float* dbeta,
-                            int accumulate, float* coef, uint32_t* ticket, mmr_stream_t stream);
+                            int accumulate, float* coef, uint32_t* ticket, const float* mask_scale,
+                            const float* mask_shift, mmr_stream_t stream);
 /* partial -> dgamma, dbeta (fp32, accumulate flag) and the coefficients used by apply. */
 int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, int C, const float* gamma,
                         const float* invstd, float* dgamma, float* dbeta, int accumulate,

@@ -154,6 +154,7 @@ SIGNATURES = {
     "mmr_wgrad_plan_run": (_i, [_vp, _i, _i, _vp]),
     "mmr_wgrad_plan_destroy": (_i, [_vp]),
     "mmr_stem_im2col": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "mmr_stem_im2col_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "mmr_unpack_nhwc_bf16_to_nchw_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_repack_weights": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
@@ -164,7 +165,7 @@ SIGNATURES = {
     "mmr_bn_bwd_reduce": (_i, [C.POINTER(MmrContrib), _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
                                _vp, _i, _vp]),
     "mmr_bn_bwd_reduce_fused": (_i, [C.POINTER(MmrContrib), _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i,
-                                     _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+                                     _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mmr_bn_bwd_finalize": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "mmr_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "mmr_grad_gather": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),

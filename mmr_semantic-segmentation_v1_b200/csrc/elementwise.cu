@@ -79,34 +79,51 @@ static int ew_blocks(int64_t work_items, int cap_mult = 8) {
 }
 
 // ------------------------------------------------------------------ packing
-__global__ void stem_im2col_kernel(const float* __restrict__ x, int N, int H, int W, int Ho, int Wo,
-                                   __nv_bfloat16* __restrict__ out, int kpad,
-                                   const float* __restrict__ mean, const float* __restrict__ std_) {
+// One CTA = 64 consecutive output pixels of one output row: the 3 x 7 x 133 input patch they share
+// is staged in shared memory with coalesced row reads (optionally normalised, or taken from uint8 HWC
+// frames), then written out as im2col rows [pixel][kpad] in 16-byte pieces.  A per-thread gather
+// from global memory ran at 1/8 of the write bandwidth.
+constexpr int kStemSeg = 64;
+constexpr int kStemTw = 2 * kStemSeg + 5;   // input columns under one segment
+constexpr int kStemTwp = kStemTw + 3;       // padded row pitch
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const TIn* __restrict__ x, int N, int H, int W, int Ho, int Wo,
+                   __nv_bfloat16* __restrict__ out, int kpad, const float* __restrict__ mean,
+                   const float* __restrict__ std_) {
+  __shared__ float tile[3 * 7 * kStemTwp];
+  __shared__ int lut[256];
+  const int ox0 = blockIdx.x * kStemSeg, oy = blockIdx.y, n = blockIdx.z;
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+    const int c = k / 49, r = k % 49;
+    lut[k] = k < 147 ? (c * 7 + r / 7) * kStemTwp + r % 7 : -1;
+  }
+  for (int idx = threadIdx.x; idx < 3 * 7 * kStemTw; idx += blockDim.x) {
+    const int col = idx % kStemTw, rr = idx / kStemTw, ky = rr % 7, c = rr / 7;
+    const int iy = 2 * oy + ky - 3, ix = 2 * ox0 + col - 3;
+    float val = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      if (sizeof(TIn) == 1)   // uint8 frames, HWC: ToTensor's /255 happens here
+        val = (float)x[(((size_t)n * H + iy) * W + ix) * 3 + c] * (1.f / 255.f);
+      else
+        val = (float)x[(((size_t)n * 3 + c) * H + iy) * W + ix];
+      if (mean) val = (val - __ldg(mean + c)) / __ldg(std_ + c);
+    }
+    tile[(c * 7 + ky) * kStemTwp + col] = val;
+  }
+  __syncthreads();
   const int groups = kpad / 8;
-  const int64_t total = (int64_t)N * Ho * Wo * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % groups);
-    const int64_t pix = i / groups;
-    const int ox = (int)(pix % Wo);
-    const int oy = (int)((pix / Wo) % Ho);
-    const int n = (int)(pix / ((int64_t)Wo * Ho));
+  const int npx = min(kStemSeg, Wo - ox0);
+  const size_t pix0 = ((size_t)n * Ho + oy) * Wo + ox0;
+  for (int item = threadIdx.x; item < npx * groups; item += blockDim.x) {
+    const int p = item / groups, g = item % groups;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float val = 0.f;
-      if (k < 147) {
-        const int c = k / 49, r = k % 49, ky = r / 7, kx = r % 7;
-        const int iy = 2 * oy + ky - 3, ix = 2 * ox + kx - 3;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-          val = __ldg(x + (((size_t)n * 3 + c) * H + iy) * W + ix);
-          if (mean) val = (val - __ldg(mean + c)) / __ldg(std_ + c);
-        }
-      }
-      v[j] = val;
+      const int o = lut[g * 8 + j];
+      v[j] = o >= 0 ? tile[o + 2 * p] : 0.f;
     }
-    store8(out + pix * kpad + g * 8, v);
+    store8(out + (pix0 + p) * kpad + g * 8, v);
   }
 }
 
@@ -255,13 +272,14 @@ __device__ __forceinline__ void issue_row(const ContribList& cl, const RowGeom& 
     }
   }
   if (act) raw.a = ldg16(act + (size_t)r * C + c);
-  if (MODE == 1) raw.z = ldg16(z + (size_t)r * C + c);
+  if (MODE == 1 || MODE == 3) raw.z = ldg16(z + (size_t)r * C + c);
 }
 
 template <int MODE, int NC, bool POOLED>
 __device__ __forceinline__ void finish_row(const ContribList& cl, const RowGeom& geo, uint32_t r, int c, int C,
                                            const __nv_bfloat16* act, const RowRaw<NC, POOLED>& raw,
-                                           __nv_bfloat16* gout, float (&f1)[8], float (&f2)[8]) {
+                                           __nv_bfloat16* gout, float (&f1)[8], float (&f2)[8],
+                                           const float (&msc)[8], const float (&msh)[8]) {
   float g[8];
   if (NC == 0) {
     gather_row<POOLED>(cl, geo, r, c, C, g);
@@ -274,16 +292,20 @@ __device__ __forceinline__ void finish_row(const ContribList& cl, const RowGeom&
       for (int q = 0; q < (POOLED ? 4 : 1); ++q) add8(raw.v[i][q], g);
     }
   }
-  if (act) {
+  float zz[8];
+  if (MODE == 1 || MODE == 3) cvt8(raw.z, zz);
+  if (MODE == 3) {
+    // ReLU mask recomputed from z with the very FMA bn_apply used: the activation is not re-read
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = fmaf(zz[j], msc[j], msh[j]) > 0.f ? g[j] : 0.f;
+  } else if (act) {
     float a[8];
     cvt8(raw.a, a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
   }
   store8(gout + (size_t)r * C + c, g);
-  if (MODE == 1) {
-    float zz[8];
-    cvt8(raw.z, zz);
+  if (MODE == 1 || MODE == 3) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) f1[j] += g[j], f2[j] += g[j] * zz[j];
   } else {
@@ -301,9 +323,12 @@ struct BwdFused {
   float* coef;
   uint32_t* ticket;  // nullptr: not fused, `partial` receives per-block sums
   int accumulate;
+  const float* mask_scale;  // MODE 3: ReLU mask = (z * mask_scale + mask_shift > 0)
+  const float* mask_shift;
 };
 
-template <int MODE, int NC, bool POOLED>  // MODE 0: stats of z ; 1: bn backward reduce ; 2: plain gradient gather
+template <int MODE, int NC, bool POOLED>  // MODE 0: stats of z ; 1: bn backward reduce ; 2: plain gradient gather ;
+                                          // 3: as 1 with the ReLU mask recomputed from z
 __global__ void __launch_bounds__(kEwThreads, 2)
 reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, double* __restrict__ partial,
                    ContribList cl, const __nv_bfloat16* __restrict__ act,
@@ -320,7 +345,12 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
   const int cg = threadIdx.x % tpc;
   const int rl = threadIdx.x / tpc;
   const int c = cg * 8;
-  float f1[8], f2[8];
+  float f1[8], f2[8], msc[8], msh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    msc[j] = MODE == 3 ? __ldg(fz.mask_scale + c + j) : 0.f;
+    msh[j] = MODE == 3 ? __ldg(fz.mask_shift + c + j) : 0.f;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     f1[j] = f2[j] = 0.f;
@@ -352,7 +382,7 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
 #pragma unroll
       for (int k = 0; k < R; ++k)
         if (r0 + k * stride < P)
-          finish_row<MODE, NC, POOLED>(cl, geo, r0 + k * stride, c, C, act, raw[k], gout, f1, f2);
+          finish_row<MODE, NC, POOLED>(cl, geo, r0 + k * stride, c, C, act, raw[k], gout, f1, f2, msc, msh);
     }
     if (++since_flush == 16) {
 #pragma unroll
@@ -378,8 +408,8 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
         s1 += sd1[j * kEwThreads + k * tpc + cg];
         s2 += sd2[j * kEwThreads + k * tpc + cg];
       }
-      if (MODE == 1) s2 = (s2 - (double)__ldg(mean + c + j) * s1) * (double)__ldg(invstd + c + j);
-      if (MODE == 1 && fz.ticket) {
+      if (MODE == 1 || MODE == 3) s2 = (s2 - (double)__ldg(mean + c + j) * s1) * (double)__ldg(invstd + c + j);
+      if ((MODE == 1 || MODE == 3) && fz.ticket) {
         double* sl = partial + (size_t)(blockIdx.x & 7) * 2 * C;
         atomicAdd(sl + c + j, s1);
         atomicAdd(sl + C + c + j, s2);
@@ -389,7 +419,7 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
       }
     }
   }
-  if (MODE == 1 && fz.ticket) {
+  if ((MODE == 1 || MODE == 3) && fz.ticket) {
     __shared__ uint32_t last;
     __threadfence();
     __syncthreads();
@@ -665,43 +695,76 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, i
 }
 
 // gin[n,y,x,c] = sum over the (<=4) windows containing (y,x) whose recorded argmax is (y,x).
-__global__ void maxpool_bwd_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N, int H,
-                                   int W, int C, __nv_bfloat16* __restrict__ gin) {
+// An odd coordinate lies in two windows (taps 0 and 2), an even one in one (tap 1).  Every load of a
+// pixel (window argmax bytes + NC contributions per window) is issued before the first use.
+template <int NC>
+__global__ void __launch_bounds__(kEwThreads)
+maxpool_bwd_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N, int H, int W, int C,
+                   __nv_bfloat16* __restrict__ gin) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int groups = C / 8;
-  const int64_t total = (int64_t)N * H * W * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const uint32_t groups = (uint32_t)C / 8;
+  const uint32_t total = (uint32_t)N * H * W * groups;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = (int)(i % groups) * 8;
-    const int64_t pix = i / groups;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+    const uint32_t pix = i / groups;
+    const int x = (int)(pix % (uint32_t)W), y = (int)((pix / (uint32_t)W) % (uint32_t)H);
+    const int n = (int)(pix / ((uint32_t)W * H));
+    // window candidates per axis: (output coordinate, tap)
+    int oys[2], kys[2], oxs[2], kxs[2], ny = 0, nx = 0;
+    if (y & 1) {
+      if ((y + 1) / 2 < Ho) oys[ny] = (y + 1) / 2, kys[ny++] = 0;
+      oys[ny] = (y - 1) / 2, kys[ny++] = 2;
+    } else if (y / 2 < Ho) {
+      oys[ny] = y / 2, kys[ny++] = 1;
+    }
+    if (x & 1) {
+      if ((x + 1) / 2 < Wo) oxs[nx] = (x + 1) / 2, kxs[nx++] = 0;
+      oxs[nx] = (x - 1) / 2, kxs[nx++] = 2;
+    } else if (x / 2 < Wo) {
+      oxs[nx] = x / 2, kxs[nx++] = 1;
+    }
+    uint2 packed[4];
+    uint4 raw[4][NC > 0 ? NC : 1];
+    int want[4];
+    bool live[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int wi = a * 2 + b;
+        live[wi] = a < ny && b < nx;
+        if (live[wi]) {
+          const size_t opix = ((size_t)n * Ho + oys[a]) * Wo + oxs[b];
+          want[wi] = kys[a] * 3 + kxs[b];
+          packed[wi] = __ldg(reinterpret_cast<const uint2*>(idx + opix * C + c));
+#pragma unroll
+          for (int k = 0; k < NC; ++k) raw[wi][k] = __ldg(reinterpret_cast<const uint4*>(cl.ptr[k] + opix * C + c));
+        }
+      }
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int ky = 0; ky < 3; ++ky) {
-      const int ty = y + 1 - ky;
-      if (ty < 0 || (ty & 1)) continue;
-      const int oy = ty >> 1;
-      if (oy >= Ho) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int tx = x + 1 - kx;
-        if (tx < 0 || (tx & 1)) continue;
-        const int ox = tx >> 1;
-        if (ox >= Wo) continue;
-        const size_t opix = ((size_t)n * Ho + oy) * Wo + ox;
-        const uint2 packed = *reinterpret_cast<const uint2*>(idx + opix * C + c);
-        float g[8];
-        gather8(cl, n, oy, ox, c, Ho, Wo, C, g);
-        const int want = ky * 3 + kx;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t word = j < 4 ? packed.x : packed.y;
-          const int id = (int)((word >> (8 * (j & 3))) & 0xFF);
-          if (id == want) acc[j] += g[j];
-        }
+    for (int wi = 0; wi < 4; ++wi) {
+      if (!live[wi]) continue;
+      float g[8];
+      if (NC > 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) add8(raw[wi][k], g);
+      } else {
+        const int a = wi >> 1, b = wi & 1;
+        gather8(cl, n, oys[a], oxs[b], c, Ho, Wo, C, g);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t word = j < 4 ? packed[wi].x : packed[wi].y;
+        const int id = (int)((word >> (8 * (j & 3))) & 0xFF);
+        if (id == want[wi]) acc[j] += g[j];
       }
     }
-    store8(gin + pix * C + c, acc);
+    store8(gin + (size_t)pix * C + c, acc);
   }
 }
 
@@ -872,13 +935,20 @@ __global__ void head_grad_prep_kernel(const float* __restrict__ dl, int N, int C
   }
 }
 
-__global__ void head_bias_finalize_kernel(const double* __restrict__ partial, int nblk, int C,
-                                          float* dbias, int accumulate) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256)
+head_bias_finalize_kernel(const double* __restrict__ partial, int nblk, int C, float* dbias, int accumulate) {
+  // 16 channels x 16 block-lanes, combined in lane order through shared memory (deterministic)
+  __shared__ double sh[16][17];
+  const int c = threadIdx.x & 15, lane = threadIdx.x >> 4;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * 16 + c];
-  dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)s;
+  if (c < C)
+    for (int b = lane; b < nblk; b += 16) s += partial[(size_t)b * 16 + c];
+  sh[lane][c] = s;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    for (int l = 1; l < 16; ++l) s += sh[l][c];
+    dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)s;
+  }
 }
 
 static double* g_head_ws = nullptr;  // small persistent workspace for head_grad_prep partials
@@ -892,9 +962,22 @@ extern "C" int mmr_stem_im2col(const float* x, int N, int H, int W, void* out, i
                                const float* mean, const float* std_, mmr_stream_t stream) {
   MMR_REQUIRE(kpad % 8 == 0 && kpad >= 152, "kpad must be a multiple of 8 and >= 152, got %d", kpad);
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  const int64_t total = (int64_t)N * Ho * Wo * (kpad / 8);
-  stem_im2col_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
+  MMR_REQUIRE(kpad <= 256 && Ho <= 65535 && N <= 65535, "stem_im2col: kpad <= 256, Ho and N <= 65535");
+  dim3 grid((Wo + kStemSeg - 1) / kStemSeg, Ho, N);
+  stem_im2col_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
       x, N, H, W, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out), kpad, mean, std_);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_stem_im2col_u8(const uint8_t* x_nhwc, int N, int H, int W, void* out, int kpad,
+                                  const float* mean, const float* std_, mmr_stream_t stream) {
+  MMR_REQUIRE(kpad % 8 == 0 && kpad >= 152 && kpad <= 256, "kpad must be a multiple of 8 in [152, 256], got %d", kpad);
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  MMR_REQUIRE(Ho <= 65535 && N <= 65535, "stem_im2col: Ho and N <= 65535");
+  dim3 grid((Wo + kStemSeg - 1) / kStemSeg, Ho, N);
+  stem_im2col_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>(
+      x_nhwc, N, H, W, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out), kpad, mean, std_);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1076,8 +1159,19 @@ extern "C" int mmr_maxpool3x3s2_bwd(const MmrContrib* contribs, int ncontrib, co
   ContribList cl;
   if (fill_contribs(cl, contribs, ncontrib)) return -1;
   const int64_t total = (int64_t)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
-      cl, idx, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
+  MMR_REQUIRE(total < ((int64_t)1 << 31), "maxpool backward: tensor too large for 32-bit indexing");
+  bool pooled = false;
+  for (int i = 0; i < cl.n; ++i) pooled |= cl.pool2[i] != 0;
+  const int blocks = ew_blocks(total, 64);
+  __nv_bfloat16* go = reinterpret_cast<__nv_bfloat16*>(gin);
+  if (!pooled && cl.n == 1)
+    maxpool_bwd_kernel<1><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
+  else if (!pooled && cl.n == 2)
+    maxpool_bwd_kernel<2><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
+  else if (!pooled && cl.n == 3)
+    maxpool_bwd_kernel<3><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
+  else
+    maxpool_bwd_kernel<0><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1092,7 +1186,7 @@ extern "C" int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int
       dlogits, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), cpad, dbias ? g_head_ws : nullptr);
   MMR_CUDA_CHECK(cudaGetLastError());
   if (dbias) {
-    head_bias_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(g_head_ws, kHeadBlocks, C, dbias,
+    head_bias_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(g_head_ws, kHeadBlocks, C, dbias,
                                                                accumulate);
     MMR_CUDA_CHECK(cudaGetLastError());
   }
@@ -1143,17 +1237,23 @@ extern "C" int mmr_bn_bwd_reduce_fused(const MmrContrib* contribs, int ncontrib,
                                        const float* mean, const float* invstd, int N, int H, int W, int C,
                                        void* g, double* slots, int nblk, const float* gamma, float* dgamma,
                                        float* dbeta, int accumulate, float* coef, uint32_t* ticket,
-                                       mmr_stream_t stream) {
+                                       const float* mask_scale, const float* mask_shift, mmr_stream_t stream) {
   if (check_rows_layout(C)) return -1;
   MMR_REQUIRE(slots && coef && ticket, "fused backward reduce needs slots, coef and a ticket");
+  MMR_REQUIRE((mask_scale == nullptr) == (mask_shift == nullptr) && !(mask_scale && act),
+              "pass either the activation or (mask_scale, mask_shift)");
   ContribList cl;
   if (fill_contribs(cl, contribs, ncontrib)) return -1;
   const int64_t P = (int64_t)N * H * W;
   MMR_REQUIRE(P < ((int64_t)1 << 31), "row count must be below 2^31");
-  BwdFused fz{gamma, dgamma, dbeta, coef, ticket, accumulate};
-  launch_reduce<1>(nblk, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, slots, cl,
-                   reinterpret_cast<const __nv_bfloat16*>(act), mean, invstd, make_geom(H, W),
-                   reinterpret_cast<__nv_bfloat16*>(g), fz);
+  BwdFused fz{gamma, dgamma, dbeta, coef, ticket, accumulate, mask_scale, mask_shift};
+  if (mask_scale)
+    launch_reduce<3>(nblk, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, slots, cl,
+                     nullptr, mean, invstd, make_geom(H, W), reinterpret_cast<__nv_bfloat16*>(g), fz);
+  else
+    launch_reduce<1>(nblk, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, slots, cl,
+                     reinterpret_cast<const __nv_bfloat16*>(act), mean, invstd, make_geom(H, W),
+                     reinterpret_cast<__nv_bfloat16*>(g), fz);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -540,9 +540,12 @@ class Engine:
                 if self.fuse_finalize and Cc <= 2048:
                     if "bwd_ticket" not in u:
                         u["bwd_ticket"] = self._ticket()
-                    self._rec(calls, "mmr_bn_bwd_reduce_fused", arr, cnt, relu_act, u["z"], u["mean"],
-                              u["invstd"], n, ho, wo, Cc, g, self.bwd_slots, nblk, self.P[bn + ".weight"],
-                              self.G[bn + ".weight"], self.G[bn + ".bias"], acc, u["coef"], u["bwd_ticket"])
+                    # without a residual the ReLU mask is a function of z alone: do not re-read the activation
+                    zmask = relu_act is not None and u.get("res") is None
+                    self._rec(calls, "mmr_bn_bwd_reduce_fused", arr, cnt, None if zmask else relu_act, u["z"],
+                              u["mean"], u["invstd"], n, ho, wo, Cc, g, self.bwd_slots, nblk, self.P[bn + ".weight"],
+                              self.G[bn + ".weight"], self.G[bn + ".bias"], acc, u["coef"], u["bwd_ticket"],
+                              u["scale"] if zmask else None, u["shift"] if zmask else None)
                 else:
                     self._rec(calls, "mmr_bn_bwd_reduce", arr, cnt, relu_act, u["z"], u["mean"], u["invstd"],
                               n, ho, wo, Cc, g, self.bn_partial, nblk)

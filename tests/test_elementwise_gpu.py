@@ -94,6 +94,55 @@ def test_bn_forward_backward(shape, with_res):
         assert rel(_nchw(g), resf.grad) < 1e-2
 
 
+def test_bn_bwd_reduce_fused_mask_from_z():
+    """mmr_bn_bwd_reduce_fused: the ReLU mask recomputed from z (scale / shift of the forward pass) is the
+    mask read from the stored activation, bit for bit in g, and the fused finalisation matches
+    mmr_bn_bwd_reduce + mmr_bn_bwd_finalize."""
+    L = _lib()
+    lib = L.lib()
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    n, h, w, c = 3, 20, 12, 64
+    shape = (n, h, w, c)
+    P = n * h * w
+    z = (torch.randn(shape, generator=gen, device="cuda") * 2 + 0.3).to(torch.bfloat16)
+    gamma = torch.rand(c, generator=gen, device="cuda") + 0.5
+    beta = torch.randn(c, generator=gen, device="cuda") * 0.2
+    nblk = 23
+    partial = torch.empty((nblk * 2 * c,), device="cuda", dtype=torch.float64)
+    st = torch.empty((7, c), device="cuda")
+    act = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mmr_bn_stats(_p(z), P, c, _p(partial), nblk, _s()))
+    L.check(lib.mmr_bn_finalize(_p(partial), nblk, P, c, _p(gamma), _p(beta), 1e-5, 0.1, None, None, None,
+                                _p(st[0]), _p(st[1]), _p(st[2]), _p(st[3]), _s()))
+    L.check(lib.mmr_bn_apply(_p(z), P, c, _p(st[2]), _p(st[3]), None, 1, _p(act), _s()))
+    g1 = torch.randn(shape, generator=gen, device="cuda").to(torch.bfloat16)
+    arr = _contribs([(g1, 0)])
+    # unfused reference path
+    g_ref = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+    dgamma_ref, dbeta_ref = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    coef_ref = torch.empty((3, c), device="cuda")
+    L.check(lib.mmr_bn_bwd_reduce(arr, 1, _p(act), _p(z), _p(st[0]), _p(st[1]), n, h, w, c, _p(g_ref),
+                                  _p(partial), nblk, _s()))
+    L.check(lib.mmr_bn_bwd_finalize(_p(partial), nblk, P, c, _p(gamma), _p(st[1]), _p(dgamma_ref), _p(dbeta_ref),
+                                    0, _p(coef_ref), _s()))
+    slots = torch.zeros((8 * 2 * c,), device="cuda", dtype=torch.float64)
+    ticket = torch.zeros((1,), device="cuda", dtype=torch.int32)
+    for use_z in (False, True):
+        g = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+        dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+        coef = torch.empty((3, c), device="cuda")
+        L.check(lib.mmr_bn_bwd_reduce_fused(arr, 1, None if use_z else _p(act), _p(z), _p(st[0]), _p(st[1]), n, h,
+                                            w, c, _p(g), _p(slots), nblk, _p(gamma), _p(dgamma), _p(dbeta), 0,
+                                            _p(coef), _p(ticket), _p(st[2]) if use_z else None,
+                                            _p(st[3]) if use_z else None, _s()))
+        torch.cuda.synchronize()
+        assert torch.equal(g, g_ref), use_z
+        assert int(ticket) == 0 and float(slots.abs().max()) == 0.0      # re-armed by the last CTA
+        assert torch.allclose(dgamma, dgamma_ref, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(dbeta, dbeta_ref, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(coef, coef_ref, rtol=1e-5, atol=1e-7)
+
+
 def test_grad_gather_pool2_and_mask():
     L = _lib()
     lib = L.lib()
