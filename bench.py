@@ -229,6 +229,20 @@ def run_ours(args):
         opt.step()
         return loss.item()          # device -> host read of the step's result
 
+    # the same step fed with uint8 HWC frames (what the loaders hold): /255 and utils.normalize on the device
+    fh = (torch.rand((n, H, W, 3), generator=torch.Generator().manual_seed(6210 + rank)) * 255).to(torch.uint8).pin_memory()
+    model.set_input_normalization((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+
+    def step_e2e_u8():
+        x = fh.to(dev, non_blocking=True)
+        y = yh.to(dev, non_blocking=True)
+        for p in model.parameters():
+            p.grad = None
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -258,6 +272,9 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    for _ in range(3):
+        step_e2e_u8()
+    ms_e2e_u8 = timed(step_e2e_u8, args.steps)
 
     eng = model._engine_for(xd, training=True)
     line = None
@@ -289,6 +306,9 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": world * n * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4},
+            "e2e_uint8_frames": {"value": world * n * args.steps / (ms_e2e_u8 * 1e-3), "unit": "images/s",
+                                 "h2d_bytes_per_step": fh.numel() + yh.numel() * 8, "d2h_bytes_per_step": 4,
+                                 "note": "same step through model(frames_u8): ToTensor + utils.normalize fused into the stem loader"},
             "gpu_launches": per_step * args.steps,
             "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel + conv_gemm_tc_kernel (all fprop + dgrad launches of a step)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],

@@ -273,6 +273,10 @@ int mmr_stem_im2col_u8(const uint8_t* x_nhwc, int N, int H, int W, void* out, in
 /* NCHW fp32 -> NHWC bf16 with channel padding to cpad (zeros). */
 int mmr_pack_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, void* out,
                                    int cpad, mmr_stream_t stream);
+/* uint8 HWC frames [N][H][W][3] -> NHWC bf16 padded to cpad channels: x/255, then (x-mean)/std when
+ * mean != NULL (the image feed of the 3x3 full-resolution convs of ResNetUNet). */
+int mmr_pack_nhwc_u8_to_nhwc_bf16(const uint8_t* x, int N, int H, int W, void* out, int cpad,
+                                  const float* mean, const float* std_, mmr_stream_t stream);
 /* NHWC bf16 -> NCHW fp32 (first C of ldc channels). */
 int mmr_unpack_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int ldc, int H, int W,
                                      float* out, mmr_stream_t stream);

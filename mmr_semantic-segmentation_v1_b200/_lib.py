@@ -155,6 +155,7 @@ SIGNATURES = {
     "mmr_wgrad_plan_destroy": (_i, [_vp]),
     "mmr_stem_im2col": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_stem_im2col_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "mmr_pack_nhwc_u8_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "mmr_unpack_nhwc_bf16_to_nchw_f32": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_repack_weights": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),

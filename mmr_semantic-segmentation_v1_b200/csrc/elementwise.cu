@@ -148,6 +148,30 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C, int 
   }
 }
 
+// uint8 HWC frames -> NHWC bf16 padded to cpad channels: x/255, optional (x-mean)/std.
+__global__ void pack_u8_kernel(const uint8_t* __restrict__ x, int64_t npix, __nv_bfloat16* __restrict__ out,
+                               int cpad, const float* __restrict__ mean, const float* __restrict__ std_) {
+  const int groups = cpad / 8;
+  const int64_t total = npix * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const int64_t p = i / groups;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float val = 0.f;
+      if (c < 3) {
+        val = (float)x[p * 3 + c] * (1.f / 255.f);
+        if (mean) val = (val - __ldg(mean + c)) / __ldg(std_ + c);
+      }
+      v[j] = val;
+    }
+    store8(out + p * cpad + g * 8, v);
+  }
+}
+
 __global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int N, int C, int ldc, int H,
                                    int W, float* __restrict__ out) {
   const int64_t hw = (int64_t)H * W;
@@ -988,6 +1012,17 @@ extern "C" int mmr_pack_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int 
   const int64_t total = (int64_t)N * H * W * (cpad / 8);
   pack_nchw_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
       x, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), cpad);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_pack_nhwc_u8_to_nhwc_bf16(const uint8_t* x, int N, int H, int W, void* out, int cpad,
+                                             const float* mean, const float* std_, mmr_stream_t stream) {
+  MMR_REQUIRE(cpad % 8 == 0 && cpad >= 8, "cpad must be a multiple of 8");
+  MMR_REQUIRE((mean == nullptr) == (std_ == nullptr), "pass both mean and std or neither");
+  const int64_t npix = (int64_t)N * H * W;
+  pack_u8_kernel<<<ew_blocks(npix * (cpad / 8), 16), kEwThreads, 0, as_stream(stream)>>>(
+      x, npix, reinterpret_cast<__nv_bfloat16*>(out), cpad, mean, std_);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

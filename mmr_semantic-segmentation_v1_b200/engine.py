@@ -108,7 +108,8 @@ class Engine:
         self.use_halo = not os.environ.get("MMR_NO_HALO")
         self.use_graphs = not os.environ.get("MMR_NO_GRAPH")
         self._graphs = {}
-        self._train_calls = None
+        self._train_calls = {}
+        self._fwd_u8 = None
         # BatchNorm statistics taken in the conv epilogues: [unit][slot][2][C] doubles, bump-allocated
         self.halo_stats = torch.zeros((HALO_STAT_SLOTS * 2 * 16384,), device=device, dtype=torch.float64)
         self.halo_stats_used = 0
@@ -120,6 +121,11 @@ class Engine:
         self.bwd_slots = torch.zeros((8 * 2 * 2048,), device=device, dtype=torch.float64)
         self.fuse_finalize = not os.environ.get("MMR_NO_FUSED_FINALIZE")
         self.x_in = torch.empty((N, 3, H, W), device=device, dtype=torch.float32)
+        # uint8 HWC frames straight from the loader: /255 and the optional
+        # (x - mean) / std of utils.normalize happen in the kernels that read the image
+        self.x_u8 = torch.empty((N, H, W, 3), device=device, dtype=torch.uint8)
+        self.in_norm = torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0]], device=device, dtype=torch.float32)
+        self.u8_swaps = []           # (index in fwd_calls, replacement call) of the image readers
         self.bn_partial = torch.empty((BN_BLOCKS * 2 * 512,), device=device, dtype=torch.float64)
         # split-K partials of the weight-gradient GEMMs: one buffer, used by one layer at a time
         self.wg_partial = torch.empty((WG_PARTIAL_FLOATS,), device=device, dtype=torch.float32) \
@@ -189,6 +195,10 @@ class Engine:
                 act.buf = self._bf16(N, H, W, 16)
                 self.acts[op["out"]] = act
                 self._rec(fc, "mmr_pack_nchw_f32_to_nhwc_bf16", self.x_in, N, 3, H, W, act.buf, 16)
+                alt = []
+                self._rec(alt, "mmr_pack_nhwc_u8_to_nhwc_bf16", self.x_u8, N, H, W, act.buf, 16, self.in_norm[0],
+                          self.in_norm[1])
+                self.u8_swaps.append((len(fc) - 1, alt[0]))
             elif kind == "upsample":
                 src = self.acts[op["in"]]
                 n, h, w, c = src.shape
@@ -221,6 +231,7 @@ class Engine:
             # one memset per forward re-arms every statistics slot the conv epilogues accumulate into
             fc.insert(0, (self.lib.mmr_zero_async, (C.c_void_p(self.halo_stats.data_ptr()),
                                                      C.c_int64(self.halo_stats_used * 8))))
+            self.u8_swaps = [(i + 1, call) for i, call in self.u8_swaps]
         self.n_launch_fwd = len(fc) + len(self.repack_calls)
 
     def _bn_state(self, unit, bn_name, Cc):
@@ -263,6 +274,10 @@ class Engine:
         out.producer = unit
         unit["out"] = out
         self._rec(fc, "mmr_stem_im2col", self.x_in, N, H, W, unit["mat"], STEM_KPAD, None, None)
+        alt = []
+        self._rec(alt, "mmr_stem_im2col_u8", self.x_u8, N, H, W, unit["mat"], STEM_KPAD, self.in_norm[0],
+                  self.in_norm[1])
+        self.u8_swaps.append((len(fc) - 1, alt[0]))
         self._rec(self.repack_calls, "mmr_repack_weights", w, cout, 147, 1, unit["wf"], STEM_KPAD, None, 0, 0)
         if self.training:
             unit["z"] = self._bf16(N, Ho, Wo, cout)
@@ -662,24 +677,39 @@ class Engine:
             raise _lib.MmrError(self.lib.mmr_last_error().decode(errors="replace"))
 
     def forward(self, x=None, stream=None):
-        """x: fp32 NCHW [N,3,H,W] on the device (copied into the plan's input buffer)."""
-        if x is not None:
+        """x: fp32 NCHW [N,3,H,W] on the device (copied into the plan's input buffer), or uint8 NHWC
+        [N,H,W,3] frames (normalised by `set_input_norm` constants inside the first kernels)."""
+        u8 = x is not None and x.dtype == torch.uint8
+        if u8:
+            self.x_u8.copy_(x, non_blocking=True)
+            if self._fwd_u8 is None:
+                self._fwd_u8 = list(self.fwd_calls)
+                for i, call in self.u8_swaps:
+                    self._fwd_u8[i] = call
+        elif x is not None:
             self.x_in.copy_(x, non_blocking=True)
+        fwd = self._fwd_u8 if u8 else self.fwd_calls
         if self.training:
-            if self._train_calls is None:   # the optimiser rewrites the fp32 masters every step
-                self._train_calls = self.repack_calls + self.fwd_calls
-            self._run(self._train_calls, stream)
+            key = "u8" if u8 else "f32"
+            if key not in self._train_calls:   # the optimiser rewrites the fp32 masters every step
+                self._train_calls[key] = self.repack_calls + fwd
+            self._run(self._train_calls[key], stream)
         else:
             self.refresh_folded()
             ver = tuple(t._version for t in self.P.values())
             if ver != self._w_versions or self.weights_dirty:
                 self._run(self.repack_calls, stream)
                 self._w_versions, self.weights_dirty = ver, False
-            self._run(self.fwd_calls, stream)
+            self._run(fwd, stream)
         heads = self.head_units()
         if self.training and len(heads) > 1:
             return [u["result"] for u in heads]
         return self.acts["logits"].buf if "logits" in self.acts else None
+
+    def set_input_norm(self, mean, std):
+        """(x/255 - mean) / std for uint8 frames (utils.normalize, SU/utils.py:480-519)."""
+        self.in_norm[0].copy_(torch.as_tensor(mean, dtype=torch.float32))
+        self.in_norm[1].copy_(torch.as_tensor(std, dtype=torch.float32))
 
     def head_units(self):
         return [u for u in self.units if u["kind"] == "head"]

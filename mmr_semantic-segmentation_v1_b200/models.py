@@ -133,6 +133,7 @@ class _PlanModel(nn.Module):
         self._on_grads_ready = None  # DDP installs callbacks here
         self._after_backward = None
         self._grad_cuts = None       # DDP: hook positions where a gradient bucket completes
+        self._input_norm = None      # (mean, std) applied on the device to uint8 frames
 
     # ---- flat parameter storage ------------------------------------------------------------
     def _flatten(self, device):
@@ -196,9 +197,14 @@ class _PlanModel(nn.Module):
         if not x.is_cuda:
             raise _lib.MmrError("mmrseg_b200 models run on a B200 only: input is on %s and there is "
                                 "no CPU fallback" % x.device)
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError("expected input of shape [N, 3, H, W], got %s" % (tuple(x.shape),))
-        n, _, h, w = x.shape
+        if x.dtype == torch.uint8:       # frames as the loaders hold them: [N, H, W, 3]
+            if x.dim() != 4 or x.shape[3] != 3:
+                raise ValueError("expected uint8 frames of shape [N, H, W, 3], got %s" % (tuple(x.shape),))
+            n, h, w, _ = x.shape
+        else:
+            if x.dim() != 4 or x.shape[1] != 3:
+                raise ValueError("expected input of shape [N, 3, H, W], got %s" % (tuple(x.shape),))
+            n, _, h, w = x.shape
         if h % 32 or w % 32:
             raise RuntimeError("Wrong input shape height=%d, width=%d. Expected image height and width "
                                "divisible by 32." % (h, w))
@@ -210,11 +216,22 @@ class _PlanModel(nn.Module):
             tensors.update(dict(self.named_buffers()))
             params = {k: v.data for k, v in tensors.items()}
             eng = Engine(self._graph(), params, self._gviews, n, h, w, x.device, training=training)
+            if self._input_norm is not None:
+                eng.set_input_norm(*self._input_norm)
             self._engines[key] = eng
         return eng
 
+    def set_input_normalization(self, mean, std):
+        """Constants of `utils.normalize(batch, mean, std)` (SU/utils.py:480-519; SU/ModelTraining.py:300-301,
+        579) applied on the device to uint8 HWC frames: `model(frames_u8)` then equals
+        `model(normalize(ToTensor(frames)))` without the CPU loop and the fp32 host-to-device copy."""
+        self._input_norm = (tuple(float(v) for v in mean), tuple(float(v) for v in std))
+        for eng in self._engines.values():
+            eng.set_input_norm(*self._input_norm)
+
     def forward(self, x):
-        x = x.float() if x.dtype != torch.float32 else x
+        if x.dtype != torch.uint8 and x.dtype != torch.float32:
+            x = x.float()
         if self.training and torch.is_grad_enabled():
             self._ensure_flat(x.device)
             out = _PlanFunction.apply(self, x.contiguous(), *self.parameters())
