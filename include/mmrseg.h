@@ -160,6 +160,11 @@ typedef struct {
   double* stats;
   int32_t stats_ld;
   const MmrBnFinalize* bn_finalize; /* optional (needs stats): fused mmr_bn_finalize */
+  /* Row-phase stacking: 1 (off), 2 or 4.  An M tile takes every rph-th output row and one MMA of
+   * N = (phases) * bn serves up to three vertically adjacent output rows from ONE read of the activation
+   * operand (what bounds N <= 64 MMAs).  Needs tps = 3, bn <= 64, H % rph == 0 (H % (16 rph) == 0 with
+   * nearest-x2 sources), weights packed with layout 1, tx * rph * bn * acc_bufs <= 512. */
+  int32_t rph;
 } MmrHaloConvDesc;
 
 int mmr_halo_conv_plan_create(const MmrHaloConvDesc* desc, void** plan);
@@ -167,15 +172,16 @@ int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream);
 int mmr_halo_conv_plan_destroy(void* plan);
 /* OIHW fp32 3x3 master weights -> bf16 [n_ntiles][nchunks][9][bn][cb].  mode 0 (fprop): rows are
  * output channels, columns input channels; mode 1 (dgrad): rows are input channels, columns output
- * channels, taps mirrored.  Out-of-range rows / columns are zero. */
+ * channels, taps mirrored.  Out-of-range rows / columns are zero.  layout: see MmrPackJob. */
 int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode, int cb, int bn, int n_ntiles,
-                          int nchunks, void* out, mmr_stream_t stream);
+                          int nchunks, int layout, void* out, mmr_stream_t stream);
 /* The same for every layer of a network in one launch: jobs_dev is a DEVICE array of njobs jobs
  * (the optimiser rewrites the fp32 masters every step, so the packing runs once per step). */
 typedef struct {
   const float* w_oihw;
   void* out;
-  int32_t O, I, mode, cb, bn, n_ntiles, nchunks, pad_;
+  int32_t O, I, mode, cb, bn, n_ntiles, nchunks;
+  int32_t layout; /* order of the 9 taps inside a chunk: 0 = ky*3+kx; 1 = [kx][ky = 2,1,0] (rph > 1) */
 } MmrPackJob;
 int mmr_pack_weights_halo_batch(const MmrPackJob* jobs_dev, int njobs, mmr_stream_t stream);
 

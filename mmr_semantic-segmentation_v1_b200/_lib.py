@@ -79,13 +79,14 @@ class MmrHaloConvDesc(C.Structure):
         ("out_mode", C.c_int32), ("out_f32", C.c_void_p), ("out_ldc", C.c_int32),
         ("stats", C.c_void_p), ("stats_ld", C.c_int32),
         ("bn_finalize", C.POINTER(MmrBnFinalize)),
+        ("rph", C.c_int32),
     ]
 
 
 class MmrPackJob(C.Structure):
     _fields_ = [("w_oihw", C.c_void_p), ("out", C.c_void_p), ("O", C.c_int32), ("I", C.c_int32),
                 ("mode", C.c_int32), ("cb", C.c_int32), ("bn", C.c_int32), ("n_ntiles", C.c_int32),
-                ("nchunks", C.c_int32), ("pad_", C.c_int32)]
+                ("nchunks", C.c_int32), ("layout", C.c_int32)]
 
 
 class MmrWgradHaloDesc(C.Structure):
@@ -144,7 +145,7 @@ SIGNATURES = {
     "mmr_halo_conv_plan_create": (_i, [C.POINTER(MmrHaloConvDesc), C.POINTER(_vp)]),
     "mmr_halo_conv_plan_run": (_i, [_vp, _vp]),
     "mmr_halo_conv_plan_destroy": (_i, [_vp]),
-    "mmr_pack_weights_halo": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_pack_weights_halo": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_pack_weights_halo_batch": (_i, [_vp, _i, _vp]),
     "mmr_wgrad_halo_partial_floats": (_i64, [_i, _i, _i, _i, _i]),
     "mmr_wgrad_halo_plan_create": (_i, [C.POINTER(MmrWgradHaloDesc), C.POINTER(_vp)]),

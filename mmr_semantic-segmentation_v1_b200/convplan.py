@@ -397,15 +397,19 @@ def _mma_clk(bn):
     return max(bn / 2.0, (4096 + bn * 32) / 128.0)
 
 
-def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, seg_sizes=None, force=None):
-    """Pick (bn, tx, tps, pipeline depths) for a halo-kernel plan: minimise the modelled time of the
+def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, seg_sizes=None, force=None,
+                stats=False):
+    """Pick (bn, tx, rph, tps, pipeline depths) for a halo-kernel plan: minimise the modelled time of the
     whole layer (MMA issue under the shared-memory operand limit, L2 -> shared traffic, exposed
     epilogue, wave quantisation over the SMs) subject to 227 KB of shared memory and 512 TMEM columns.
     seg_sizes: channel counts of the destination tensors in concat order (dgrad); an N tile's store
-    groups must not straddle them."""
+    groups must not straddle them.  stats: the launch takes BatchNorm statistics in its epilogue.
+    rph > 1 (row-phase stacking, csrc/conv_halo.cu) reads the activation operand once for up to three
+    vertically adjacent output rows: the remedy for N tiles of 64 channels and fewer."""
     cpad = -(-cout // 16) * 16
     seg_sizes = seg_sizes or [cpad]
     best = None
+    no_r = bool(__import__("os").environ.get("MMR_NO_RPH"))
     # N tiles wider than 128 (or 96/160/192) are legal for the kernel but measured slower than 64/128 with
     # a wider macro tile (their weight slots crowd the shared-memory port): scripts/sweep_halo.sh
     for bn in ((force or {}).get("bn"),) if force and "bn" in force else (128, 64, 32, 16):
@@ -418,56 +422,78 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
         gpn = bn // sg
         if n_nt * gpn > 16:
             continue
-        for tx in (4, 2, 1):
-            if tx > 1 and 8 * tx > -(-W // 8) * 8:
-                continue
-            pitch = 8 * tx + (4 if any_up else 2)
-            halo_stage = -(-(18 * pitch * cb * 2) // 1024) * 1024
-            for acc_bufs in (2, 1):
-                if acc_bufs * tx * bn > 512:
+        for rph in (4, 2, 1):
+            if rph > 1:
+                # the fast epilogue only; statistics need one channel set per CTA; fp32 logits stay unstacked
+                if no_r or not bf16_out or 3 * bn > 256 or H % rph or (any_up and H % (16 * rph)):
                     continue
-                for tps in (9, 3, 1):
-                    if tps * bn > 256:
+                if stats and not (n_nt == 1 and gpn == 1):
+                    continue
+                if H < 16 * rph:
+                    continue
+            for tx in (4, 2, 1):
+                if tx > 1 and 8 * tx > -(-W // 8) * 8:
+                    continue
+                if rph == 4 and tx == 4:
+                    continue
+                pitch = 8 * tx + (4 if any_up else 2)
+                rows = 16 * rph + 2
+                halo_stage = -(-(rows * pitch * cb * 2) // 1024) * 1024
+                for acc_bufs in (2, 1):
+                    if acc_bufs * tx * rph * bn > 512:
                         continue
-                    w_slot = -(-(tps * bn * cb * 2) // 1024) * 1024
-                    for out_stages in ((2, 1) if bf16_out else (0,)):
-                        out_stage = 128 * sg * 2
-                        for halo_stages in (3, 2):
-                            rest = HALO_SMEM - halo_stages * halo_stage - out_stages * out_stage
-                            w_slots = min(8, rest // w_slot)
-                            if w_slots < 2:
-                                continue
-                            cfg = dict(bn=bn, sg=sg, n_ntiles=n_nt, tx=tx, tps=tps, acc_bufs=acc_bufs,
-                                       halo_stages=halo_stages, w_slots=w_slots, out_stages=out_stages)
-                            if force and any(cfg[k] != v for k, v in force.items() if k in cfg):
-                                continue
-                            items = N * (-(-H // 16)) * (-(-W // (8 * tx))) * n_nt
-                            # One item (tx M tiles x bn channels).  Measured (scripts/probe/probe3.cu, ncu of
-                            # x_1_3.conv1): an SS-mode MMA costs max(bn/2 clk of tensor pipe, its operand bytes
-                            # at 128 B/clk), and the same 128 B/clk shared-memory port also takes the TMA fills
-                            # and the epilogue staging, which is what bounds the bn = 64 layers.
-                            n_mma = tx * nchunks * 9 * (cb // 16)
-                            tensor = n_mma * bn / 2.0
-                            fill = nchunks * (18 * pitch * cb * 2 + 9 * bn * cb * 2)
-                            epi_bytes = tx * 128 * bn * 2 * (2 if sg == 64 else 0)
-                            smem = (n_mma * (4096 + 32 * bn) + fill + epi_bytes) / 128.0
-                            # one elected lane issues every TMA of a ring: ~520 clk per operation
-                            wprod = nchunks * (9 // tps) * 520
-                            hprod = nchunks * (3 if any_up else 1) * 520
-                            traffic = fill / 75.0
-                            epi = tx * gpn * (450.0 if sg == 64 else 300.0)
-                            per_item = max(tensor, smem, wprod, hprod, traffic) + 1200 + nchunks * 150
-                            if acc_bufs == 1:
-                                per_item += 1.5 * epi
-                            per_item = max(per_item, epi)
-                            if w_slots * tps < 3:
-                                per_item *= 1.15
-                            if out_stages == 1:
-                                per_item *= 1.01
-                            total = -(-items // n_sms) * per_item
-                            key = (total, -tx, -w_slots)
-                            if best is None or key < best[0]:
-                                best = (key, cfg)
+                    for tps in ((3,) if rph > 1 else (9, 3, 1)):
+                        if tps * bn > 256:
+                            continue
+                        w_slot = -(-(tps * bn * cb * 2) // 1024) * 1024
+                        for out_stages in ((2, 1) if bf16_out else (0,)):
+                            out_stage = 128 * sg * 2
+                            for halo_stages in (3, 2):
+                                rest = HALO_SMEM - halo_stages * halo_stage - out_stages * out_stage
+                                w_slots = min(8, rest // w_slot)
+                                if w_slots < 2:
+                                    continue
+                                cfg = dict(bn=bn, sg=sg, n_ntiles=n_nt, tx=tx, rph=rph, tps=tps, acc_bufs=acc_bufs,
+                                           halo_stages=halo_stages, w_slots=w_slots, out_stages=out_stages)
+                                if force and any(cfg[k] != v for k, v in force.items() if k in cfg):
+                                    continue
+                                items = N * (-(-H // (16 * rph))) * (-(-W // (8 * tx))) * n_nt
+                                # One item (tx * rph M tiles x bn channels).  Measured (scripts/probe/probe3.cu, ncu
+                                # of x_1_3.conv1): an SS-mode MMA costs max(N/2 clk of tensor pipe, its operand
+                                # bytes at 128 B/clk), and the same 128 B/clk shared-memory port also takes the
+                                # TMA fills and the epilogue staging, which is what bounds the bn = 64 layers.
+                                ksteps = cb // 16
+                                if rph == 1:
+                                    mma_list = [bn] * 9
+                                else:   # per filter column: row shifts ty = -1 .. rph, 1-3 phases each
+                                    mma_list = [bn * (min(rph - 1, ty + 1) - max(0, ty - 1) + 1)
+                                                for ty in range(-1, rph + 1)] * 3
+                                # Measured in the kernel (scripts/gpu_rph_sweep.sh, stage-skip diagnostics): an
+                                # SS-mode M = 128 x N x K = 16 MMA costs about 28 + 0.625 N clk -- the tensor
+                                # time N/2 plus most of its operand fetch, which overlaps the math poorly -- i.e.
+                                # 68 clk at N = 64, 108 at N = 128, 148 at N = 192.
+                                tensor = tx * nchunks * ksteps * sum(28.0 + 0.625 * n for n in mma_list)
+                                fill = nchunks * (rows * pitch * cb * 2 + 9 * bn * cb * 2)
+                                epi_bytes = tx * rph * 128 * bn * 2 * (2 if sg == 64 else 0)
+                                smem = (tx * nchunks * ksteps * sum(4096 + 32 * n for n in mma_list) + fill
+                                        + epi_bytes) / 128.0
+                                # one elected lane issues every TMA of a ring: ~520 clk per operation
+                                wprod = nchunks * (9 // tps) * 520
+                                hprod = nchunks * (3 if any_up else 1) * 520
+                                traffic = fill / 75.0
+                                epi = tx * rph * gpn * (300.0 if sg == 64 else 200.0)
+                                per_item = max(tensor, smem, wprod, hprod, traffic) + 1200 + nchunks * 150
+                                if acc_bufs == 1:
+                                    per_item += 1.5 * epi
+                                per_item = max(per_item, epi)
+                                if w_slots * tps < 3:
+                                    per_item *= 1.15
+                                if out_stages == 1:
+                                    per_item *= 1.01
+                                total = -(-items // n_sms) * per_item
+                                key = (total, -tx, -w_slots)
+                                if best is None or key < best[0]:
+                                    best = (key, cfg)
     if best is None:
         raise ValueError("no halo-kernel configuration for cout=%d cb=%d" % (cout, cb))
     cfg = best[1]
@@ -522,8 +548,8 @@ def pack_weights_halo(w_oihw, cfg, mode, out=None, stream=None):
         out = torch.empty((halo_packed_weights_numel(cfg),), device=w_oihw.device, dtype=torch.bfloat16)
     s = torch.cuda.current_stream().cuda_stream if stream is None else stream
     _lib.check(_lib.lib().mmr_pack_weights_halo(C.c_void_p(w_oihw.data_ptr()), O, I, mode, cfg["cb"], cfg["bn"],
-                                                cfg["n_ntiles"], cfg["nchunks"], C.c_void_p(out.data_ptr()),
-                                                C.c_void_p(s)))
+                                                cfg["n_ntiles"], cfg["nchunks"], int(cfg.get("rph", 1) > 1),
+                                                C.c_void_p(out.data_ptr()), C.c_void_p(s)))
     return out
 
 
@@ -545,6 +571,7 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     d.weights = packed.data_ptr()
     d.cb, d.bn, d.sg, d.n_ntiles = cfg["cb"], cfg["bn"], cfg["sg"], cfg["n_ntiles"]
     d.tx, d.tps = cfg["tx"], cfg["tps"]
+    d.rph = cfg.get("rph", 1)
     d.halo_stages, d.w_slots, d.acc_bufs = cfg["halo_stages"], cfg["w_slots"], cfg["acc_bufs"]
     d.out_stages = max(1, cfg["out_stages"])
     d.direct_store = int(cfg.get("direct", cfg["sg"] < 64))
@@ -579,14 +606,14 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     return plan
 
 
-def fprop_halo_cfg(sources, cout, bf16_out=True, force=None):
+def fprop_halo_cfg(sources, cout, bf16_out=True, force=None, stats=False):
     N = sources[0][0].shape[0]
     H = sources[0][0].shape[1] * sources[0][1]
     W = sources[0][0].shape[2] * sources[0][1]
     cin = sum(t.shape[3] for t, _ in sources)
     cb = pick_bk([t.shape[3] for t, _ in sources])
     any_up = any(up == 2 for _, up in sources)
-    return halo_config(H, W, N, cb, cin // cb, cout, any_up, bf16_out=bf16_out, force=force)
+    return halo_config(H, W, N, cb, cin // cb, cout, any_up, bf16_out=bf16_out, force=force, stats=stats)
 
 
 def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=None, relu=False,
@@ -599,7 +626,7 @@ def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=No
     # cin below the stored channel count: a zero-padded source (the 3-channel image stored as 16)
     assert cin <= sum(t.shape[3] for t, _ in sources)
     if cfg is None:
-        cfg = fprop_halo_cfg(sources, cout, out_f32 is None, force)
+        cfg = fprop_halo_cfg(sources, cout, out_f32 is None, force, stats=stats is not None)
     if packed is None:
         packed = pack_weights_halo(w_oihw, cfg, 0)
     groups = None

@@ -49,7 +49,7 @@ struct HaloParams {
   __nv_bfloat16* group_ptr[kMaxGroups];
   int nchunks, wmap, smap0;
   int H, W, N;
-  int TX, tiles_x, tiles_y, n_ntiles, total_items;
+  int TX, R, tiles_x, tiles_y, n_ntiles, total_items;  // R: output-row phases stacked along N (1, 2, 4)
   int rowbytes, KS;
   int bn, sg, gpn;  // store group = sg channels, gpn groups per N tile
   int tps, nslots;  // taps per weight slot, slots per chunk
@@ -92,6 +92,13 @@ __device__ __forceinline__ void tma_store_4d(const void* map, const void* src, i
   asm volatile(
       "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
       "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const void* map, const void* src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -196,6 +203,95 @@ __device__ __forceinline__ void mma_warp_loop(const HaloParams& p, uint32_t tmem
   }
 }
 
+// Row-phase stacking (R = 2 or 4).  An M tile takes every R-th output row (row-group stride of the A
+// descriptor = R halo rows), so the A view at halo row shift ty serves the output rows of phase
+// r = ty-1, ty, ty+1 (filter rows ky = ty - r + 1) at once: ONE tcgen05.mma of N = (#phases) * bn
+// against the weight rows [ky = 2, 1, 0] of filter column kx, which the slot holds in exactly that
+// order, accumulates into the adjacent column blocks of those phases.  The 4 KB A operand -- what bounds
+// an N = 64 MMA at the shared-memory port -- is read once for up to three phases: (R+2)*3 MMAs of average
+// N = 3R/(R+2) * bn replace 9R MMAs of N = bn.  A phase is first touched at ty = r-1: at chunk 0,
+// filter column 0, K step 0 the new phase gets its own non-accumulating MMA.
+template <int KS, int TX, int R>
+__device__ __forceinline__ void mma_warp_loop_r(const HaloParams& p, uint32_t tmem_base, uint32_t halo0, uint32_t w0,
+                                                uint64_t* halo_full, uint64_t* halo_empty, uint64_t* w_full,
+                                                uint64_t* w_empty, uint64_t* tmem_full, uint64_t* tmem_empty) {
+  const uint32_t bn = (uint32_t)p.bn;
+  const uint32_t idesc[4] = {0u, make_idesc_bf16(128, p.bn, 0, 0), make_idesc_bf16(128, 2 * p.bn, 0, 0),
+                             make_idesc_bf16(128, 3 * p.bn, 0, 0)};
+  const uint32_t rb = (uint32_t)p.rowbytes;
+  const uint32_t swz = swizzle_code(p.rowbytes);
+  const uint32_t hiB = desc_hi32(8 * rb, swz);
+  const uint32_t tile_step = (8 * rb) >> 4;
+  const uint32_t px_step = rb >> 4;
+  const uint32_t ky_step = (bn * rb) >> 4;  // next filter row of the slot ([ky = 2, 1, 0][bn rows])
+  int hs = 0, ws = 0, it = 0;
+  uint32_t hph = 0, wph = 0;
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+    const int buf = it % p.acc_bufs;
+    const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
+    mbar_wait(&tmem_empty[buf], par ^ 1);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + (uint32_t)(buf * TX * R) * bn;
+    for (int c = 0; c < p.nchunks; ++c) {
+      const int up = p.chunk[c].up;
+      const uint32_t pitch = (uint32_t)p.pitch[up];
+      const uint32_t hiA = desc_hi32((uint32_t)R * pitch * rb, swz);
+      const uint32_t row_step = (pitch * rb) >> 4;
+      mbar_wait(&halo_full[hs], hph);
+      tc_fence_after();
+      const uint32_t a_stage = ((halo0 + (uint32_t)hs * p.halo_stage_bytes + (up ? rb : 0u)) >> 4) | 0x10000u;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {  // filter column kx = s: one weight slot
+        mbar_wait(&w_full[ws], wph);
+        tc_fence_after();
+        const uint32_t b_slot = ((w0 + (uint32_t)ws * p.w_slot_bytes) >> 4) | 0x10000u;
+        if (!(p.dbg & 1) && elect_one()) {
+#pragma unroll
+          for (int ty = -1; ty <= R; ++ty) {
+            constexpr int kDummy = 0;
+            (void)kDummy;
+            const int r_lo = ty - 1 < 0 ? 0 : ty - 1;
+            const int r_hi = ty + 1 > R - 1 ? R - 1 : ty + 1;
+            const int nph = r_hi - r_lo + 1;
+            const int nold = (ty > R - 1 ? R - 1 : ty) - r_lo + 1;  // phases r <= ty: already touched
+            const bool has_new = ty + 1 <= R - 1;
+            const uint32_t a_ty = a_stage + (uint32_t)(ty + 1) * row_step + (uint32_t)s * px_step;
+            const uint32_t b_ty = b_slot + (uint32_t)(1 - ty + r_lo) * ky_step;
+#pragma unroll
+            for (int i = 0; i < TX; ++i) {
+              const uint32_t d = d0 + (uint32_t)(i * R + r_lo) * bn;
+              const uint32_t a = a_ty + (uint32_t)i * tile_step;
+              if (s == 0 && c == 0) {
+                if (nold > 0) umma_lohi_acc(d, a, hiA, b_ty, hiB, idesc[nold > 0 ? nold : 1]);
+                if (has_new)
+                  umma_lohi(d + (uint32_t)(nold > 0 ? nold : 0) * bn, a, hiA,
+                            b_ty + (uint32_t)(nold > 0 ? nold : 0) * ky_step, hiB, idesc[1], 0u);
+              } else {
+                umma_lohi_acc(d, a, hiA, b_ty, hiB, idesc[nph]);
+              }
+#pragma unroll
+              for (int k = 1; k < KS; ++k) umma_lohi_acc(d, a + 2 * k, hiA, b_ty + 2 * k, hiB, idesc[nph]);
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&w_empty[ws]);
+        if (++ws == p.w_slots) {
+          ws = 0;
+          wph ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(&halo_empty[hs]);
+      if (++hs == p.halo_stages) {
+        hs = 0;
+        hph ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit(&tmem_full[buf]);
+    __syncwarp();
+  }
+}
+
 // XOR applied to the 16-byte chunk index of staging row r (matches TMA SWIZZLE_{128,64,32}B).
 __device__ __forceinline__ uint32_t row_xor(uint32_t r, int rowbytes) {
   return rowbytes == 128 ? (r & 7u) : (rowbytes == 64 ? ((r >> 1) & 3u) : ((r >> 2) & 1u));
@@ -213,7 +309,7 @@ __device__ __forceinline__ ItemCoord decode_item(const HaloParams& p, int item) 
   const int ty = t % p.tiles_y;
   c.n = t / p.tiles_y;
   c.x0 = tx * 8 * p.TX;
-  c.y0 = ty * 16;
+  c.y0 = ty * 16 * p.R;
   return c;
 }
 
@@ -251,7 +347,6 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
     const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
     mbar_wait(&tmem_full[buf], par);
     tc_fence_after();
-    const int y = ic.y0 + h;
     if (p.dbg & 2) {
       tc_fence_before();
       __syncwarp();
@@ -263,12 +358,14 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
       const int gi = ic.nt * p.gpn + g;
       __nv_bfloat16* const gptr = p.group_ptr[gi];
       const int gldc = p.group_ldc[gi], gcoff = p.group_coff[gi];
-      for (int i = 0; i < p.TX; ++i, ++gcount) {
+      for (int ir = 0; ir < p.TX * p.R; ++ir, ++gcount) {
+        const int i = ir / p.R, r = ir % p.R;   // M tile, output-row phase
         const int x = ic.x0 + 8 * i + w;
+        const int y = ic.y0 + p.R * h + r;
         const bool valid = y < p.H && x < p.W;
         const size_t pix = ((size_t)ic.n * p.H + y) * p.W + x;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                               (uint32_t)((buf * p.TX + i) * p.bn + g * SG);
+                               (uint32_t)((buf * p.TX * p.R + ir) * p.bn + g * SG);
         uint8_t* stage = out_base + (size_t)(gcount % p.out_stages) * p.out_stage_bytes;
         if (STAGED && gcount >= p.out_stages) {
           // this warp's slice of the staging buffer is free once its store from out_stages groups
@@ -278,7 +375,7 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
           }
           __syncwarp();
         }
-        const bool last = (g == p.gpn - 1) && (i == p.TX - 1);
+        const bool last = (g == p.gpn - 1) && (ir == p.TX * p.R - 1);
 #pragma unroll
         for (int c0 = 0; c0 < SG; c0 += CH) {
           uint32_t r[CH];
@@ -351,8 +448,12 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&p.maps[p.smap0 + gi], stage + (size_t)q * 32 * orb, gcoff, ic.x0 + 8 * i, ic.y0 + 4 * q,
-                         ic.n);
+            if (p.R == 1)
+              tma_store_4d(&p.maps[p.smap0 + gi], stage + (size_t)q * 32 * orb, gcoff, ic.x0 + 8 * i, ic.y0 + 4 * q,
+                           ic.n);
+            else  // (C, W, R, H/R, N): the warp's four tile rows are R image rows apart
+              tma_store_5d(&p.maps[p.smap0 + gi], stage + (size_t)q * 32 * orb, gcoff, ic.x0 + 8 * i, r,
+                           ic.y0 / p.R + 4 * q, ic.n);
             bulk_commit();
           }
         }
@@ -441,7 +542,7 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
             mbar_arrive_expect_tx(&halo_full[hs], p.halo_tx_bytes[0]);
             tma_load_4d(dst, &p.maps[ch.map], &halo_full[hs], ch.c0, ic.x0 - 1, ic.y0 - 1, ic.n);
           } else {
-            // halo row 0 = upsampled row y0-1, rows 1..16 = y0..y0+15, row 17 = y0+16;
+            // halo row 0 = upsampled row y0-1, rows 1..16R = y0..y0+16R-1, row 16R+1 = y0+16R;
             // halo column 0 = upsampled column x0-2 (even, so the pair replication lines up).
             const int xl = (ic.x0 >> 1) - 1, yl = ic.y0 >> 1;
             const uint32_t rowb = (uint32_t)p.pitch[1] * p.rowbytes;
@@ -449,8 +550,8 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
             tma_load_5d(dst, &p.maps[ch.map_edge], &halo_full[hs], ch.c0, 0, xl, yl - 1, ic.n);
             tma_load_5d(dst + rowb, &p.maps[ch.map], &halo_full[hs], ch.c0, 0, xl, 0,
                         ic.n * (p.H >> 1) + yl);
-            tma_load_5d(dst + 17 * rowb, &p.maps[ch.map_edge], &halo_full[hs], ch.c0, 0, xl, yl + 8,
-                        ic.n);
+            tma_load_5d(dst + (size_t)(16 * p.R + 1) * rowb, &p.maps[ch.map_edge], &halo_full[hs], ch.c0, 0, xl,
+                        yl + 8 * p.R, ic.n);
           }
         }
         __syncwarp();
@@ -493,9 +594,22 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
                                   tmem_empty);
 #define MMR_MMA_CASES_TX(KS_, TPS_) MMR_MMA_CASE(KS_, TPS_, 1) MMR_MMA_CASE(KS_, TPS_, 2) MMR_MMA_CASE(KS_, TPS_, 4)
 #define MMR_MMA_CASES_TPS(KS_) MMR_MMA_CASES_TX(KS_, 1) MMR_MMA_CASES_TX(KS_, 3) MMR_MMA_CASES_TX(KS_, 9)
-    MMR_MMA_CASES_TPS(1)
-    MMR_MMA_CASES_TPS(2)
-    MMR_MMA_CASES_TPS(4)
+    if (p.R == 1) {
+      MMR_MMA_CASES_TPS(1)
+      MMR_MMA_CASES_TPS(2)
+      MMR_MMA_CASES_TPS(4)
+    }
+#define MMR_MMA_RCASE(KS_, TX_, R_)                                                                             \
+  if (p.KS == KS_ && p.TX == TX_ && p.R == R_)                                                                  \
+    mma_warp_loop_r<KS_, TX_, R_>(p, tmem_base, halo0, w0, halo_full, halo_empty, w_full, w_empty, tmem_full,   \
+                                  tmem_empty);
+#define MMR_MMA_RCASES(KS_) \
+  MMR_MMA_RCASE(KS_, 1, 2) MMR_MMA_RCASE(KS_, 2, 2) MMR_MMA_RCASE(KS_, 4, 2) MMR_MMA_RCASE(KS_, 1, 4) MMR_MMA_RCASE(KS_, 2, 4)
+    MMR_MMA_RCASES(1)
+    MMR_MMA_RCASES(2)
+    MMR_MMA_RCASES(4)
+#undef MMR_MMA_RCASES
+#undef MMR_MMA_RCASE
 #undef MMR_MMA_CASES_TPS
 #undef MMR_MMA_CASES_TX
 #undef MMR_MMA_CASE
@@ -723,8 +837,11 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
 // out[((nt*nchunks + c)*9 + tap)*bn + r][k], bf16.  mode 0 (fprop): N index = output channel,
 // K index = concatenated input channel, filter tap as is.  mode 1 (dgrad): N index = input channel,
 // K index = output channel, tap mirrored (the data gradient correlates dz with the flipped filter).
+// layout 1 (row-phase stacking): slot position t holds filter column kx = t / 3, filter row ky = 2 - t % 3.
+__device__ __forceinline__ int pack_tap(int t, int layout) { return layout ? (2 - t % 3) * 3 + t / 3 : t; }
+
 __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int O, int I, int mode, int cb, int bn,
-                                         int n_ntiles, int nchunks, __nv_bfloat16* __restrict__ out) {
+                                         int n_ntiles, int nchunks, int layout, __nv_bfloat16* __restrict__ out) {
   const int64_t total = (int64_t)n_ntiles * nchunks * 9 * bn * cb;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -733,7 +850,7 @@ __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int O, int
     t /= cb;
     const int r = (int)(t % bn);
     t /= bn;
-    const int tap = (int)(t % 9);
+    const int tap = pack_tap((int)(t % 9), layout);
     t /= 9;
     const int c = (int)(t % nchunks);
     const int nt = (int)(t / nchunks);
@@ -761,7 +878,7 @@ __global__ void pack_weights_halo_batch_kernel(const MmrPackJob* __restrict__ jo
     t /= j.cb;
     const int r = (int)(t % j.bn);
     t /= j.bn;
-    const int tap = (int)(t % 9);
+    const int tap = pack_tap((int)(t % 9), j.layout);
     t /= 9;
     const int c = (int)(t % j.nchunks);
     const int nt = (int)(t / j.nchunks);
@@ -820,7 +937,19 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   MMR_REQUIRE(d->tps == 1 || d->tps == 3 || d->tps == 9, "tps must be 1, 3 or 9, got %d", d->tps);
   MMR_REQUIRE(d->tps * d->bn <= 256, "tps*bn must be <= 256 (TMA box rows)");
   MMR_REQUIRE(d->acc_bufs == 1 || d->acc_bufs == 2, "acc_bufs must be 1 or 2");
-  MMR_REQUIRE(d->acc_bufs * d->tx * d->bn <= 512, "accumulators exceed 512 TMEM columns");
+  const int R = d->rph < 1 ? 1 : d->rph;
+  MMR_REQUIRE(R == 1 || R == 2 || R == 4, "rph must be 1, 2 or 4, got %d", d->rph);
+  MMR_REQUIRE(d->acc_bufs * d->tx * R * d->bn <= 512, "accumulators exceed 512 TMEM columns");
+  if (R > 1) {
+    MMR_REQUIRE(d->tps == 3 && 3 * d->bn <= 256, "row-phase stacking needs tps = 3 and bn <= 85");
+    MMR_REQUIRE(d->H % R == 0, "row-phase stacking needs H %% rph == 0");
+    MMR_REQUIRE(!(R == 4 && d->tx == 4), "rph = 4 with tx = 4 is not instantiated");
+    MMR_REQUIRE(d->out_mode == MMR_OUT_BF16_NHWC && (d->direct_store != 0) == (d->sg < 64),
+                "row-phase stacking needs the bf16 NHWC output with the default store mode of its group width");
+    const bool plain = !d->scale && !d->bias && !d->residual && !d->relu;
+    MMR_REQUIRE(d->stats == nullptr || (d->n_ntiles == 1 && d->bn == d->sg && plain),
+                "row-phase stacking with statistics needs one channel set per CTA and a plain epilogue");
+  }
   MMR_REQUIRE(d->halo_stages >= 1 && d->halo_stages <= 4, "halo_stages must be 1..4");
   MMR_REQUIRE(d->w_slots >= 1 && d->w_slots <= 8, "w_slots must be 1..8");
   MMR_REQUIRE(d->out_stages >= 1 && d->out_stages <= 2, "out_stages must be 1 or 2");
@@ -836,6 +965,7 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.W = d->W;
   p.N = d->N;
   p.TX = d->tx;
+  p.R = R;
   p.bn = d->bn;
   MMR_REQUIRE((d->sg == 16 || d->sg == 32 || d->sg == 64) && d->bn % d->sg == 0,
               "sg must be 16/32/64 and divide bn (sg %d, bn %d)", d->sg, d->bn);
@@ -845,7 +975,7 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.nslots = 9 / d->tps;
   p.n_ntiles = d->n_ntiles;
   p.tiles_x = (d->W + 8 * d->tx - 1) / (8 * d->tx);
-  p.tiles_y = (d->H + 15) / 16;
+  p.tiles_y = (d->H + 16 * R - 1) / (16 * R);
   p.total_items = p.tiles_x * p.tiles_y * d->N * d->n_ntiles;
   p.halo_stages = d->halo_stages;
   p.w_slots = d->w_slots;
@@ -866,20 +996,20 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
       MMR_REQUIRE(s.H == d->H && s.W == d->W, "source %d: resolution mismatch", si);
       cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.N};
       cuuint64_t str[3] = {(cuuint64_t)s.C * 2, (cuuint64_t)s.C * 2 * s.W, (cuuint64_t)s.C * 2 * s.W * s.H};
-      cuuint32_t box[4] = {(cuuint32_t)d->cb, (cuuint32_t)p.pitch[0], 18, 1};
+      cuuint32_t box[4] = {(cuuint32_t)d->cb, (cuuint32_t)p.pitch[0], (cuuint32_t)(16 * R + 2), 1};
       maps.emplace_back();
       mi = (int)maps.size() - 1;
       if (encode_generic(&maps[mi], s.ptr, 4, dims, str, box, rb, "halo source")) { delete pl; return -1; }
     } else {
       MMR_REQUIRE(s.up == 2, "source %d: up must be 1 or 2", si);
       MMR_REQUIRE(s.H * 2 == d->H && s.W * 2 == d->W, "source %d: upsampled resolution mismatch", si);
-      MMR_REQUIRE(d->H % 16 == 0, "nearest-x2 sources need H %% 16 == 0 (got %d)", d->H);
+      MMR_REQUIRE(d->H % (16 * R) == 0, "nearest-x2 sources need H %% (16 * rph) == 0 (got %d)", d->H);
       any_up = true;
       const cuuint32_t bw = (cuuint32_t)(4 * d->tx + 2);
       {  // 16 interior rows: (C, dupx, Wl, dupy, N*Hl), replication through zero strides
         cuuint64_t dims[5] = {(cuuint64_t)s.C, 2, (cuuint64_t)s.W, 2, (cuuint64_t)s.N * s.H};
         cuuint64_t str[4] = {0, (cuuint64_t)s.C * 2, 0, (cuuint64_t)s.C * 2 * s.W};
-        cuuint32_t box[5] = {(cuuint32_t)d->cb, 2, bw, 2, 8};
+        cuuint32_t box[5] = {(cuuint32_t)d->cb, 2, bw, 2, (cuuint32_t)(8 * R)};
         maps.emplace_back();
         mi = (int)maps.size() - 1;
         if (encode_generic(&maps[mi], s.ptr, 5, dims, str, box, rb, "upsampled halo body")) { delete pl; return -1; }
@@ -920,12 +1050,21 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
       MMR_REQUIRE(og.ldc % 8 == 0 && og.coff % 8 == 0 && og.coff + p.sg <= og.ldc,
                   "store group %d: channels [%d, %d) do not fit a tensor of %d channels", g, og.coff,
                   og.coff + p.sg, og.ldc);
-      cuuint64_t dims[4] = {(cuuint64_t)og.ldc, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-      cuuint64_t str[3] = {(cuuint64_t)og.ldc * 2, (cuuint64_t)og.ldc * 2 * d->W,
-                           (cuuint64_t)og.ldc * 2 * d->W * d->H};
-      cuuint32_t box[4] = {(cuuint32_t)p.sg, 8, 4, 1};
       maps.emplace_back();
-      if (encode_generic(&maps.back(), og.ptr, 4, dims, str, box, p.sg * 2, "store group")) { delete pl; return -1; }
+      if (R == 1) {
+        cuuint64_t dims[4] = {(cuuint64_t)og.ldc, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        cuuint64_t str[3] = {(cuuint64_t)og.ldc * 2, (cuuint64_t)og.ldc * 2 * d->W,
+                             (cuuint64_t)og.ldc * 2 * d->W * d->H};
+        cuuint32_t box[4] = {(cuuint32_t)p.sg, 8, 4, 1};
+        if (encode_generic(&maps.back(), og.ptr, 4, dims, str, box, p.sg * 2, "store group")) { delete pl; return -1; }
+      } else {  // (C, W, phase, H / R, N): a warp's four tile rows are R image rows apart
+        const cuuint64_t rowb = (cuuint64_t)og.ldc * 2 * d->W;
+        cuuint64_t dims[5] = {(cuuint64_t)og.ldc, (cuuint64_t)d->W, (cuuint64_t)R, (cuuint64_t)(d->H / R),
+                              (cuuint64_t)d->N};
+        cuuint64_t str[4] = {(cuuint64_t)og.ldc * 2, rowb, rowb * R, rowb * d->H};
+        cuuint32_t box[5] = {(cuuint32_t)p.sg, 8, 1, 4, 1};
+        if (encode_generic(&maps.back(), og.ptr, 5, dims, str, box, p.sg * 2, "store group")) { delete pl; return -1; }
+      }
       p.group_coff[g] = og.coff;
       p.group_ldc[g] = og.ldc;
       p.group_ptr[g] = reinterpret_cast<__nv_bfloat16*>(og.ptr);
@@ -934,8 +1073,8 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
     MMR_REQUIRE(d->out_f32 != nullptr && d->n_ntiles == 1, "fp32 NCHW output needs out_f32 and one N tile");
     MMR_REQUIRE(d->stats == nullptr, "statistics need the bf16 NHWC output mode");
   }
-  p.halo_tx_bytes[0] = (uint32_t)(18 * p.pitch[0] * rb);
-  p.halo_tx_bytes[1] = (uint32_t)(18 * p.pitch[1] * rb);
+  p.halo_tx_bytes[0] = (uint32_t)((16 * R + 2) * p.pitch[0] * rb);
+  p.halo_tx_bytes[1] = (uint32_t)((16 * R + 2) * p.pitch[1] * rb);
   const uint32_t halo_bytes = p.halo_tx_bytes[any_up ? 1 : 0];
   p.halo_stage_bytes = (halo_bytes + 1023) / 1024 * 1024;
   p.w_tx_bytes = (uint32_t)(d->tps * d->bn * rb);
@@ -943,7 +1082,7 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.out_stage_bytes = d->out_mode == MMR_OUT_BF16_NHWC ? (uint32_t)((128 * p.sg * 2 + 1023) / 1024 * 1024) : 0;
   if (d->out_mode != MMR_OUT_BF16_NHWC) p.out_stages = 0;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(d->acc_bufs * d->tx * d->bn)) cols <<= 1;
+  while (cols < (uint32_t)(d->acc_bufs * d->tx * R * d->bn)) cols <<= 1;
   p.tmem_cols = cols;
   size_t smem = (size_t)p.halo_stages * p.halo_stage_bytes + (size_t)p.w_slots * p.w_slot_bytes +
                 (size_t)p.out_stages * p.out_stage_bytes + 256;
@@ -1005,7 +1144,7 @@ extern "C" int mmr_halo_conv_plan_destroy(void* plan) {
 }
 
 extern "C" int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode, int cb, int bn, int n_ntiles,
-                                     int nchunks, void* out, mmr_stream_t stream) {
+                                     int nchunks, int layout, void* out, mmr_stream_t stream) {
   MMR_REQUIRE(w_oihw && out, "null argument");
   MMR_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (fprop) or 1 (dgrad)");
   const int64_t total = (int64_t)n_ntiles * nchunks * 9 * bn * cb;
@@ -1014,7 +1153,7 @@ extern "C" int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   pack_weights_halo_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(
-      w_oihw, O, I, mode, cb, bn, n_ntiles, nchunks, reinterpret_cast<__nv_bfloat16*>(out));
+      w_oihw, O, I, mode, cb, bn, n_ntiles, nchunks, layout, reinterpret_cast<__nv_bfloat16*>(out));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -156,7 +156,7 @@ class Engine:
     def _pack_job(self, w, out, O, I, mode, cfg):
         """Queue one layer's fp32 OIHW -> packed bf16 conversion; all jobs run as ONE launch."""
         self.pack_jobs.append(_lib.MmrPackJob(w.data_ptr(), out.data_ptr(), O, I, mode, cfg["cb"], cfg["bn"],
-                                              cfg["n_ntiles"], cfg["nchunks"], 0))
+                                              cfg["n_ntiles"], cfg["nchunks"], int(cfg.get("rph", 1) > 1)))
         self.keep += [w, out]
 
     def _ticket(self):
@@ -345,7 +345,9 @@ class Engine:
         unit["res"] = res
         bn_train = bool(not head and op.get("bn") and self.training)
         if halo:
-            hcfg = convplan.fprop_halo_cfg(sources, cout, bf16_out=not head)
+            # statistics of a biased conv go through the generic epilogue, which has no row-phase stacking
+            hcfg = convplan.fprop_halo_cfg(sources, cout, bf16_out=not head, stats=bn_train,
+                                           force={"rph": 1} if (bn_train and op.get("bias")) else None)
             unit["wf_h"] = self._bf16(convplan.halo_packed_weights_numel(hcfg))
             self._pack_job(w, unit["wf_h"], cout, cin, 0, hcfg)
             if self.training:

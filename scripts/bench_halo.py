@@ -88,8 +88,8 @@ def main():
                 print("%-14s %-5s %7.3f ms %7.1f TFLOP/s  bn=%d tx=%d split=%d stages=%d" % (
                     name, kind, ms, tf, c["bn"], c["tx"], c["n_split"], c["stages"]), flush=True)
             else:
-                print("%-14s %-5s %7.3f ms %7.1f TFLOP/s  bn=%d tx=%d tps=%d acc=%d hs=%d ws=%d os=%d" % (
-                    name, kind, ms, tf, c["bn"], c["tx"], c["tps"], c["acc_bufs"], c["halo_stages"],
+                print("%-14s %-5s %7.3f ms %7.1f TFLOP/s  bn=%d tx=%d rph=%d tps=%d acc=%d hs=%d ws=%d os=%d" % (
+                    name, kind, ms, tf, c["bn"], c["tx"], c.get("rph", 1), c["tps"], c["acc_bufs"], c["halo_stages"],
                     c["w_slots"], c["out_stages"]), flush=True)
             rows.append((name, kind, plan.flops / 1e9, ms, tf))
             tot[kind][0] += plan.flops / 1e9

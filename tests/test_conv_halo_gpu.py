@@ -57,6 +57,20 @@ FPROP_CASES = [
     (2, 8, 8, [(512, 1)], 512, None),        # image smaller than one tile
     (1, 64, 64, [(32, 2)], 16, None),
     (1, 32, 48, [(64, 2)], 64, dict(tx=4)),  # upsampled source, ragged in x
+    # row-phase stacking: one MMA of N = 2-3 x Cout serves vertically adjacent output rows
+    (2, 64, 32, [(64, 1)], 64, dict(rph=2, tx=2)),
+    (2, 64, 32, [(64, 1)], 64, dict(rph=2, tx=1, acc_bufs=1)),
+    (1, 64, 32, [(64, 1)], 64, dict(rph=4, tx=1)),
+    (1, 64, 32, [(32, 1)], 32, dict(rph=4, tx=2, acc_bufs=1)),
+    (1, 64, 64, [(128, 2), (64, 1)], 64, dict(rph=2, tx=2)),       # nearest-x2 source: 8*rph low-res body rows
+    (1, 64, 32, [(64, 2), (64, 1), (64, 1)], 64, dict(rph=4, tx=1)),
+    (1, 64, 64, [(32, 1)], 32, dict(rph=4, tx=2)),
+    (1, 64, 64, [(64, 1), (64, 1)], 32, dict(rph=2, tx=2)),
+    (1, 64, 64, [(16, 1)], 16, dict(rph=4, tx=2)),
+    (1, 128, 64, [(32, 2)], 16, dict(rph=2, tx=4)),
+    (3, 40, 24, [(64, 1)], 64, dict(rph=2, tx=2)),                 # ragged: 40 rows = one full + one partial item
+    (2, 72, 40, [(64, 1)], 64, dict(rph=4, tx=1)),
+    (2, 64, 64, [(64, 1)], 64, None),                              # whatever the config model picks
 ]
 
 
@@ -80,17 +94,18 @@ def test_fprop_matches_conv2d(case):
     _check(out, _ref_conv(sources, w))
 
 
-def test_fprop_epilogue_scale_bias_residual_relu():
+@pytest.mark.parametrize("Cout,force", [(128, None), (64, dict(rph=2)), (64, dict(rph=1)), (32, dict(rph=4))])
+def test_fprop_epilogue_scale_bias_residual_relu(Cout, force):
     from mmrseg_b200 import convplan
     gen = torch.Generator(device="cuda").manual_seed(1)
-    N, H, W, C, Cout = 2, 32, 32, 64, 128
+    N, H, W, C = 2, 64, 32, 64
     x = _mk((N, H, W, C), gen)
     w = torch.randn((Cout, C, 3, 3), generator=gen, device="cuda") / 24
     scale = torch.rand(Cout, generator=gen, device="cuda") + 0.5
     bias = torch.randn(Cout, generator=gen, device="cuda")
     res = _mk((N, H, W, Cout), gen)
     out = torch.empty((N, H, W, Cout), device="cuda", dtype=torch.bfloat16)
-    plan = convplan.build_fprop_halo([(x, 1)], w, out, scale=scale, bias=bias, residual=res, relu=True)
+    plan = convplan.build_fprop_halo([(x, 1)], w, out, scale=scale, bias=bias, residual=res, relu=True, force=force)
     plan.run()
     torch.cuda.synchronize()
     ref = _ref_conv([(x, 1)], w) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
@@ -115,18 +130,24 @@ def test_head_f32_nchw_output():
 
 
 @pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (3, 24, 40, 64, 128), (2, 32, 32, 16, 16),
-                                   (2, 32, 32, 32, 32)])
+                                   (2, 32, 32, 32, 32), (2, 64, 32, 64, 64, dict(rph=2)),
+                                   (2, 64, 32, 64, 64, dict(rph=2, tx=1)), (1, 72, 40, 32, 32, dict(rph=4)),
+                                   (2, 64, 64, 16, 16, dict(rph=2))])
 def test_batchnorm_statistics_from_epilogue(shape):
     from mmrseg_b200 import convplan
-    N, H, W, C, Cout = shape
+    force = shape[5] if len(shape) > 5 else None
+    N, H, W, C, Cout = shape[:5]
     gen = torch.Generator(device="cuda").manual_seed(3)
     x = _mk((N, H, W, C), gen)
     w = torch.randn((Cout, C, 3, 3), generator=gen, device="cuda") / (9 * C) ** 0.5
     out = torch.empty((N, H, W, Cout), device="cuda", dtype=torch.bfloat16)
     stats = torch.zeros((8, 2, Cout), device="cuda", dtype=torch.float64)
-    plan = convplan.build_fprop_halo([(x, 1)], w, out, stats=stats, stats_ld=Cout)
+    plan = convplan.build_fprop_halo([(x, 1)], w, out, stats=stats, stats_ld=Cout, force=force)
+    if force:
+        assert all(plan.cfg[k] == v for k, v in force.items())
     plan.run()
     torch.cuda.synchronize()
+    _check(out, _ref_conv([(x, 1)], w))
     z = out.double().reshape(-1, Cout)
     got = stats.sum(0)
     assert torch.allclose(got[0], z.sum(0), rtol=1e-5, atol=1e-5 * z.abs().sum(0).max().item())
@@ -144,6 +165,10 @@ DGRAD_CASES = [
     (3, 24, 40, [64, 64], 64, None),
     (2, 32, 32, [64, 64], 64, dict(bn=128)),
     (2, 32, 32, [64, 64], 64, dict(bn=64, tx=4)),
+    (2, 64, 32, [64, 64, 64], 64, dict(bn=64, rph=2, tx=2)),       # three N tiles, stacked row phases
+    (1, 64, 32, [64], 64, dict(rph=4, tx=1)),
+    (1, 64, 64, [32], 16, dict(rph=2)),
+    (2, 40, 24, [64, 64], 32, dict(bn=64, rph=2)),
 ]
 
 
