@@ -148,6 +148,8 @@ def run_reference(args):
 # ----------------------------------------------------------------------------- our arm
 def kernels_per_call(lib, fn):
     two = (lib.mmr_wgrad_plan_run, lib.mmr_wgrad_halo_plan_run, lib.mmr_head_grad_prep)
+    if not hasattr(fn, "restype"):      # scheduling marker of the engine's launch lists, not a kernel
+        return 0
     return 2 if any(fn is f for f in two) else 1
 
 
@@ -219,29 +221,27 @@ def run_ours(args):
         opt.step()
         return loss
 
-    def step_e2e():
-        x = xh.to(dev, non_blocking=True)
-        y = yh.to(dev, non_blocking=True)
-        for p in model.parameters():
-            p.grad = None
-        loss = crit(model(x), y)
-        loss.backward()
-        opt.step()
-        return loss.item()          # device -> host read of the step's result
-
     # the same step fed with uint8 HWC frames (what the loaders hold): /255 and utils.normalize on the device
     fh = (torch.rand((n, H, W, 3), generator=torch.Generator().manual_seed(6210 + rank)) * 255).to(torch.uint8).pin_memory()
     model.set_input_normalization((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
 
-    def step_e2e_u8():
-        x = fh.to(dev, non_blocking=True)
-        y = yh.to(dev, non_blocking=True)
-        for p in model.parameters():
-            p.grad = None
-        loss = crit(model(x), y)
-        loss.backward()
-        opt.step()
-        return loss.item()
+    # the loop a user writes: batches come through the package's DevicePrefetcher (one batch in flight on a
+    # copy stream); every timed step still moves its own inputs host -> device and reads its loss back
+    from mmrseg_b200.data import DevicePrefetcher
+
+    feed = DevicePrefetcher(None, dev)      # one prefetcher (copy stream + two device buffer sets) for the run
+
+    def run_e2e(host_x, steps):
+        last = None
+        feed.loader = [(host_x, yh)] * steps
+        for x, y in feed:
+            for p in model.parameters():
+                p.grad = None
+            loss = crit(model(x), y)
+            loss.backward()
+            opt.step()
+            last = loss.item()      # device -> host read of the step's result
+        return last
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,12 +269,21 @@ def run_ours(args):
     sampler.start()
     ms = timed(step_resident, args.steps)
     clocks = sampler.result()
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    for _ in range(3):
-        step_e2e_u8()
-    ms_e2e_u8 = timed(step_e2e_u8, args.steps)
+    def timed_loop(host_x):
+        run_e2e(host_x, 3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_e2e(host_x, args.steps)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    ms_e2e = timed_loop(xh)
+    ms_e2e_u8 = timed_loop(fh)
 
     eng = model._engine_for(xd, training=True)
     line = None

@@ -107,6 +107,8 @@ class Engine:
         self.param_ready_hooks = []  # (index in bwd call list, [param names]) for DDP overlap
         self.use_halo = not os.environ.get("MMR_NO_HALO")
         self.use_graphs = not os.environ.get("MMR_NO_GRAPH")
+        self.use_lanes = not os.environ.get("MMR_NO_LANES")
+        self._side = None
         self._graphs = {}
         self._train_calls = {}
         self._fwd_u8 = None
@@ -461,9 +463,11 @@ class Engine:
             t_g = t
             if u.get("res") is not None and u["res"].needs_grad and u["res"].producer is not None:
                 t_g = t_of[id(u["res"].producer)]
-            arena.request(("g", id(u)), nbytes(oshape), t, t_g)
+            # the weight gradient runs on the side stream and is joined two units later: its dz operand
+            # (g itself when there is no BatchNorm) must not be recycled before that
+            arena.request(("g", id(u)), nbytes(oshape), t, t_g if u.get("bn") else max(t_g, t + 1))
             if u.get("bn"):
-                arena.request(("dz", id(u)), nbytes(oshape), t, t)
+                arena.request(("dz", id(u)), nbytes(oshape), t, t + 1)
             if kind == "stem":
                 continue
             Hin, Win = u["in_hw"]
@@ -487,6 +491,8 @@ class Engine:
                 self.acts[name].contribs.append((seed, 0))
             calls = self.bwd_calls[acc]
             for t, u in enumerate(order):
+                calls.append((Engine._mark, ("join", t - 2)))
+                self._bwd_t = t
                 self._bwd_unit(u, calls, view, int(acc), record_hooks=not acc)
         self.n_launch_bwd = len(self.bwd_calls[False])
 
@@ -598,10 +604,12 @@ class Engine:
                     wplan = convplan.build_wgrad(dz, sources, u["k"], u["s"], u["pad"], gw, cout_gemm=cpad,
                                                  n_sms=self.n_sms, partial=self.wg_partial)
             u["wplan"] = wplan
+        calls.append((Engine._mark, ("side_begin", self._bwd_t)))
         if isinstance(wplan, convplan.WgradHaloPlan):
             calls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, acc)))
         else:
             calls.append((self.lib.mmr_wgrad_plan_run, (wplan.handle, 0, acc)))
+        calls.append((Engine._mark, ("side_end", self._bwd_t)))
         if record_hooks:
             self.conv_flops_bwd += wplan.flops
             names = [conv + ".weight"]
@@ -660,7 +668,7 @@ class Engine:
             elif g is False:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self._launch(calls, torch.cuda.current_stream().cuda_stream, lo, hi)
+                    self._launch(calls, torch.cuda.current_stream().cuda_stream, lo, hi, lanes=True)
                 self._graphs[key] = g
                 g.replay()
                 return
@@ -668,13 +676,49 @@ class Engine:
                 g.replay()
                 return
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
-        self._launch(calls, st, lo, hi)
+        self._launch(calls, st, lo, hi, lanes=stream is None)
 
-    def _launch(self, calls, stream, lo, hi):
-        s = C.c_void_p(stream)
+    @staticmethod
+    def _mark(kind, key, stream=None):
+        """Scheduling marker inside a launch list (a no-op when a list is replayed serially):
+        ("side_begin", k) .. ("side_end", k) bracket launches that may run on the side stream once the
+        main stream has reached the marker; ("join", k) makes the main stream wait for bracket k."""
+        return 0
+
+    def _launch(self, calls, stream, lo, hi, lanes=False):
+        """lanes: `stream` is torch's current stream; bracketed launches (the weight-gradient GEMMs, which
+        nothing on the backward critical path waits for) go to a second stream, forked and joined with
+        events -- inside a capture this becomes a parallel branch of the CUDA graph."""
         err = 0
-        for fn, args in calls[lo:hi]:
-            err |= fn(*args, s)
+        if not (lanes and self.use_lanes):
+            s = C.c_void_p(stream)
+            for fn, args in calls[lo:hi]:
+                err |= fn(*args, s)
+        else:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            side = self._side
+            cur, done, pending = main, {}, None
+            for fn, args in calls[lo:hi]:
+                if fn is Engine._mark:
+                    kind, key = args
+                    if kind == "side_begin":
+                        ev = torch.cuda.Event()
+                        ev.record(main)
+                        side.wait_event(ev)
+                        cur = side
+                    elif kind == "side_end":
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        done[key] = pending = ev
+                        cur = main
+                    elif kind == "join" and key in done:
+                        main.wait_event(done.pop(key))
+                    continue
+                err |= fn(*args, C.c_void_p(cur.cuda_stream))
+            if pending is not None:      # the segment ends with everything back on the main stream
+                main.wait_event(pending)
         if err:
             raise _lib.MmrError(self.lib.mmr_last_error().decode(errors="replace"))
 

@@ -94,3 +94,17 @@ def test_uint8_frames_train_step():
         grads.append({k: p.grad.clone() for k, p in net.named_parameters()})
     worst = max(rel(grads[1][k], grads[0][k]) for k in grads[0])
     assert worst <= 5e-2, worst
+
+
+def test_device_prefetcher_order_and_values():
+    from mmrseg_b200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(3)
+    host = [(torch.randint(0, 256, (2, 8, 8, 3), generator=g, dtype=torch.uint8).pin_memory(),
+             torch.randint(0, 5, (2, 8, 8), generator=g).pin_memory(), i) for i in range(5)]
+    seen = 0
+    for (x, y, i), (hx, hy, hi) in zip(DevicePrefetcher(host), host):
+        assert x.is_cuda and y.is_cuda and i == hi
+        assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
+        seen += 1
+    assert seen == 5 and len(DevicePrefetcher(host)) == 5
+    assert list(DevicePrefetcher([])) == []
