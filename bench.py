@@ -193,6 +193,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever libraries print (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a B200: the CUDA path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
@@ -335,7 +339,8 @@ def run_ours(args):
                                               "PyTorch oracle (restated smp U-Net++) + torch.optim.Adam" % (CPU_SAMPLE_BATCH, H, W)}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

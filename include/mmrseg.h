@@ -353,6 +353,12 @@ int mmr_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, u
                          mmr_stream_t stream);
 int mmr_maxpool3x3s2_bwd(const MmrContrib* contribs, int ncontrib, const uint8_t* idx, int N,
                          int H, int W, int C, void* gin, mmr_stream_t stream);
+/* nn.MaxPool2d(2) of the in-tree UNet's Down block (SU/UArchModel/unet_parts.py): disjoint 2x2 windows,
+ * floor mode; idx (uint8, 0..3) = position of the first maximum in scan order. */
+int mmr_maxpool2x2s2_fwd(const void* x, int N, int H, int W, int C, void* out, uint8_t* idx,
+                         mmr_stream_t stream);
+int mmr_maxpool2x2s2_bwd(const MmrContrib* contribs, int ncontrib, const uint8_t* idx, int N, int H, int W,
+                         int C, void* gin, mmr_stream_t stream);
 
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) on NHWC bf16 and its adjoint;
  * replaces self.upsample of the reference's ResNetUNet (SU/UArchModel/resnet_unet.py:195,262-294).

@@ -174,6 +174,8 @@ SIGNATURES = {
     "mmr_bias_grad_finalize": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "mmr_maxpool3x3s2_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mmr_maxpool3x3s2_bwd": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_maxpool2x2s2_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "mmr_maxpool2x2s2_bwd": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mmr_upsample_bilinear2x_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "mmr_upsample_bilinear2x_bwd": (_i, [C.POINTER(MmrContrib), _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_upsample_nearest_f32_nchw": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp]),

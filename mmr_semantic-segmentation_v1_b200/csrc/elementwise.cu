@@ -718,6 +718,72 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, i
   }
 }
 
+// ------------------------------------------------------------------ max-pool 2x2 s2 (nn.MaxPool2d(2))
+// The in-tree UNet's Down block (SU/UArchModel/unet_parts.py, `Down.maxpool_conv`): disjoint windows,
+// floor mode (an odd last row / column is dropped).  idx = position of the first maximum in scan order.
+__global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                    __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  const int Ho = H / 2, Wo = W / 2;
+  const uint32_t groups = (uint32_t)C / 8;
+  const uint32_t total = (uint32_t)N * Ho * Wo * groups;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    const uint32_t pix = i / groups;
+    const int ox = (int)(pix % (uint32_t)Wo), oy = (int)((pix / (uint32_t)Wo) % (uint32_t)Ho);
+    const int n = (int)(pix / ((uint32_t)Wo * Ho));
+    const __nv_bfloat16* base = x + (((size_t)n * H + 2 * oy) * W + 2 * ox) * C + c;
+    float v[4][8];
+    load8(base, v[0]);
+    load8(base + C, v[1]);
+    load8(base + (size_t)W * C, v[2]);
+    load8(base + (size_t)W * C + C, v[3]);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = v[0][j], bi[j] = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k][j] > best[j] || v[k][j] != v[k][j]) best[j] = v[k][j], bi[j] = k;
+    }
+    store8(out + (size_t)pix * C + c, best);
+    uint2 packed;
+    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + (size_t)pix * C + c) = packed;
+  }
+}
+
+__global__ void maxpool2_bwd_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N, int H, int W, int C,
+                                    __nv_bfloat16* __restrict__ gin) {
+  const int Ho = H / 2, Wo = W / 2;
+  const uint32_t groups = (uint32_t)C / 8;
+  const uint32_t total = (uint32_t)N * H * W * groups;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    const uint32_t pix = i / groups;
+    const int x = (int)(pix % (uint32_t)W), y = (int)((pix / (uint32_t)W) % (uint32_t)H);
+    const int n = (int)(pix / ((uint32_t)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int oy = y >> 1, ox = x >> 1;
+    if (oy < Ho && ox < Wo) {
+      const size_t opix = ((size_t)n * Ho + oy) * Wo + ox;
+      const uint2 packed = __ldg(reinterpret_cast<const uint2*>(idx + opix * C + c));
+      float g[8];
+      gather8(cl, n, oy, ox, c, Ho, Wo, C, g);
+      const int want = (y & 1) * 2 + (x & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t word = j < 4 ? packed.x : packed.y;
+        if ((int)((word >> (8 * (j & 3))) & 0xFF) == want) acc[j] = g[j];
+      }
+    }
+    store8(gin + (size_t)pix * C + c, acc);
+  }
+}
+
 // gin[n,y,x,c] = sum over the (<=4) windows containing (y,x) whose recorded argmax is (y,x).
 // An odd coordinate lies in two windows (taps 0 and 2), an even one in one (tap 1).  Every load of a
 // pixel (window argmax bytes + NC contributions per window) is issued before the first use.
@@ -1207,6 +1273,30 @@ extern "C" int mmr_maxpool3x3s2_bwd(const MmrContrib* contribs, int ncontrib, co
     maxpool_bwd_kernel<3><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
   else
     maxpool_bwd_kernel<0><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_maxpool2x2s2_fwd(const void* x, int N, int H, int W, int C, void* out, uint8_t* idx,
+                                    mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "C must be a multiple of 8 and the image at least 2x2");
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  MMR_REQUIRE((int64_t)N * H * W * (C / 8) < ((int64_t)1 << 31), "max-pool: tensor too large for 32-bit indexing");
+  maxpool2_fwd_kernel<<<ew_blocks(total, 64), kEwThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out), idx);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_maxpool2x2s2_bwd(const MmrContrib* contribs, int ncontrib, const uint8_t* idx, int N, int H,
+                                    int W, int C, void* gin, mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  ContribList cl;
+  if (fill_contribs(cl, contribs, ncontrib)) return -1;
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  MMR_REQUIRE(total < ((int64_t)1 << 31), "max-pool backward: tensor too large for 32-bit indexing");
+  maxpool2_bwd_kernel<<<ew_blocks(total, 64), kEwThreads, 0, as_stream(stream)>>>(
+      cl, idx, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -183,13 +183,16 @@ class Engine:
             elif kind == "maxpool":
                 src = self.acts[op["in"]]
                 n, h, w, c = src.shape
-                out = _Act(op["out"], (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c))
+                k = op.get("k", 3)   # 3: MaxPool2d(3, 2, 1) of the ResNet stem; 2: MaxPool2d(2) of the in-tree UNet
+                oshape = (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c) if k == 3 else (n, h // 2, w // 2, c)
+                out = _Act(op["out"], oshape)
                 out.buf = self._bf16(*out.shape)
                 out.idx = torch.empty(out.shape, device=self.dev, dtype=torch.uint8)
-                out.producer = {"kind": "maxpool", "src": src, "out": out}
+                out.producer = {"kind": "maxpool", "src": src, "out": out, "k": k}
                 self.acts[op["out"]] = out
                 self.units.append(out.producer)
-                self._rec(fc, "mmr_maxpool3x3s2_fwd", src.buf, n, h, w, c, out.buf, out.idx)
+                self._rec(fc, "mmr_maxpool3x3s2_fwd" if k == 3 else "mmr_maxpool2x2s2_fwd", src.buf, n, h, w, c,
+                          out.buf, out.idx)
             elif kind in ("conv", "head"):
                 self._fwd_conv(op)
             elif kind == "pack16":   # image -> NHWC bf16, 3 channels zero-padded to 16
@@ -298,10 +301,11 @@ class Engine:
         self.acts[op["out"]] = out
         self.units.append(unit)
 
-    def _fold(self, unit, bn_name, Cc):
-        """Eval mode: scale/shift from the running statistics, refreshed by `refresh_folded`."""
+    def _fold(self, unit, bn_name, Cc, conv_bias=None):
+        """Eval mode: scale/shift from the running statistics, refreshed by `refresh_folded`; a conv bias
+        in front of the BatchNorm (the in-tree UNet's DoubleConv) folds into the shift."""
         st = self._f32(2, Cc)
-        unit.update(bn=bn_name, scale=st[0], shift=st[1])
+        unit.update(bn=bn_name, scale=st[0], shift=st[1], fold_bias=conv_bias)
         self.keep.append(st)
         self.folded = getattr(self, "folded", [])
         self.folded.append(unit)
@@ -309,7 +313,8 @@ class Engine:
     def refresh_folded(self):
         units = getattr(self, "folded", [])
         ver = tuple(self.P[u["bn"] + sfx]._version for u in units
-                    for sfx in (".weight", ".bias", ".running_mean", ".running_var"))
+                    for sfx in (".weight", ".bias", ".running_mean", ".running_var")) + \
+            tuple(self.P[u["fold_bias"]]._version for u in units if u.get("fold_bias"))
         if ver == getattr(self, "_fold_versions", None):
             return
         self._fold_versions = ver
@@ -318,7 +323,10 @@ class Engine:
             inv = torch.rsqrt(self.P[bn + ".running_var"].float() + 1e-5)
             sc = self.P[bn + ".weight"].float() * inv
             u["scale"].copy_(sc)
-            u["shift"].copy_(self.P[bn + ".bias"].float() - self.P[bn + ".running_mean"].float() * sc)
+            mean = self.P[bn + ".running_mean"].float()
+            if u.get("fold_bias"):
+                mean = mean - self.P[u["fold_bias"]].float()
+            u["shift"].copy_(self.P[bn + ".bias"].float() - mean * sc)
 
     def _fwd_conv(self, op):
         fc = self.fwd_calls
@@ -420,9 +428,8 @@ class Engine:
             else:
                 scale = shift = None
                 if op.get("bn"):
-                    self._fold(unit, op["bn"], cout)
+                    self._fold(unit, op["bn"], cout, op["conv"] + ".bias" if bias is not None else None)
                     scale, shift = unit["scale"], unit["shift"]
-                    assert bias is None
                 else:
                     shift = bias
                 plan = fprop(out.buf, scale=scale, bias=shift, residual=res.buf if res else None,
@@ -530,7 +537,8 @@ class Engine:
             n, h, w, c = src.shape
             gin = view(("gin", id(u)), src.shape)
             arr, cnt = self._contrib_array(out)
-            self._rec(calls, "mmr_maxpool3x3s2_bwd", arr, cnt, out.idx, n, h, w, c, gin)
+            self._rec(calls, "mmr_maxpool3x3s2_bwd" if u.get("k", 3) == 3 else "mmr_maxpool2x2s2_bwd", arr, cnt,
+                      out.idx, n, h, w, c, gin)
             src.contribs.append((gin, 0))
             return
         out = u["out"]

@@ -8,7 +8,7 @@ models, so the engine can bind the reference's own parameter tensors.
   {'op': 'stem3',   'out', 'conv', 'cout', 'relu'}               3x3 s1 p1 conv(+bias)+ReLU on the image
   {'op': 'pack16',  'out'}                                        image -> NHWC bf16 padded to 16 channels
   {'op': 'upsample','in', 'out'}                                  bilinear x2, align_corners=True
-  {'op': 'maxpool', 'in', 'out'}                                  3x3 s2 p1
+  {'op': 'maxpool', 'in', 'out', 'k'}                             3x3 s2 p1 (k absent or 3) or 2x2 s2 (k = 2)
   {'op': 'conv',    'out', 'conv', 'src': [(tensor, up)], 'k', 's', 'cout',
                     'bn': name|None, 'bias': bool, 'relu': bool, 'res': tensor|None}
   {'op': 'head',    'out', 'conv', 'src': [(tensor, 1)], 'k', 'cout'}   conv + bias -> fp32 NCHW logits
@@ -145,6 +145,36 @@ def resnet_unet_graph(resnet_model=18, n_class=10):
     conv("dfull", "conv_original_size2.0", [("u0", 1), ("xo1", 1)], 3, 64)
     ops.append({"op": "head", "out": "logits", "conv": "conv_last", "src": [("dfull", 1)], "k": 1,
                 "cout": n_class})
+    return ops
+
+
+def unet_graph(n_classes=2):
+    """The reference's in-tree `UNet(n_channels=3, n_classes, bilinear=True)` (SU/UArchModel/unet.py:104-245,
+    unet_parts.py): DoubleConv = (3x3 conv WITH bias -> BatchNorm -> ReLU) x 2, Down = MaxPool2d(2) +
+    DoubleConv, Up = nearest x2 (the `bilinear=True` branch builds nn.Upsample(mode='nearest')) ->
+    cat([skip, upsampled]) -> DoubleConv(in, out, mid = in // 2), OutConv = 1x1 conv with bias.
+    `F.pad` to the skip's size is the identity when H and W are multiples of 16."""
+    ops = [{"op": "pack16", "out": "image16"}]
+
+    def double_conv(prefix, src, mid, cout, out, cin_pad=False):
+        ops.append({"op": "conv", "out": out + ".mid", "conv": prefix + "double_conv.0", "src": src, "k": 3, "s": 1,
+                    "cout": mid, "bn": prefix + "double_conv.1", "bias": True, "relu": True, "res": None,
+                    "cin_pad": cin_pad})
+        ops.append({"op": "conv", "out": out, "conv": prefix + "double_conv.3", "src": [(out + ".mid", 1)], "k": 3,
+                    "s": 1, "cout": cout, "bn": prefix + "double_conv.4", "bias": True, "relu": True, "res": None})
+
+    double_conv("inc.", [("image16", 1)], 64, 64, "x1", cin_pad=True)
+    prev = "x1"
+    for i, cout in enumerate((128, 256, 512, 512), start=1):
+        ops.append({"op": "maxpool", "in": prev, "out": "p%d" % i, "k": 2})
+        double_conv("down%d.maxpool_conv.1." % i, [("p%d" % i, 1)], cout, cout, "x%d" % (i + 1))
+        prev = "x%d" % (i + 1)
+    for i, (skip, cin, cout) in enumerate((("x4", 1024, 256), ("x3", 512, 128), ("x2", 256, 64), ("x1", 128, 64)),
+                                          start=1):
+        double_conv("up%d.conv." % i, [(skip, 1), (prev, 2)], cin // 2, cout, "u%d" % i)
+        prev = "u%d" % i
+    ops.append({"op": "head", "out": "logits", "conv": "outc.conv", "src": [(prev, 1)], "k": 1,
+                "cout": n_classes})
     return ops
 
 

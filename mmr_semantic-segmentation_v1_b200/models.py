@@ -123,6 +123,8 @@ class _PlanFunction(torch.autograd.Function):
 class _PlanModel(nn.Module):
     """Shared machinery: flat fp32 parameter / gradient buffers, plan cache, autograd bridge."""
 
+    _size_multiple = 32   # five stride-2 stages
+
     def _graph(self):
         raise NotImplementedError
 
@@ -205,9 +207,10 @@ class _PlanModel(nn.Module):
             if x.dim() != 4 or x.shape[1] != 3:
                 raise ValueError("expected input of shape [N, 3, H, W], got %s" % (tuple(x.shape),))
             n, _, h, w = x.shape
-        if h % 32 or w % 32:
+        m = self._size_multiple
+        if h % m or w % m:
             raise RuntimeError("Wrong input shape height=%d, width=%d. Expected image height and width "
-                               "divisible by 32." % (h, w))
+                               "divisible by %d." % (h, w, m))
         self._ensure_flat(x.device)
         key = (n, h, w, bool(training))
         eng = self._engines.get(key)
@@ -324,6 +327,66 @@ class ResNetUNet(_PlanModel):
 
     def _graph(self):
         return graph.resnet_unet_graph(self.resnet_model, self.n_class)
+
+
+class _DoubleConv(nn.Module):      # SU/UArchModel/unet_parts.py DoubleConv: indices 0,1,3,4 carry parameters
+    def __init__(self, cin, cout, mid=None):
+        super().__init__()
+        mid = mid or cout
+        self.double_conv = nn.Sequential(nn.Conv2d(cin, mid, 3, padding=1), nn.BatchNorm2d(mid), nn.ReLU(inplace=True),
+                                         nn.Conv2d(mid, cout, 3, padding=1), nn.BatchNorm2d(cout),
+                                         nn.ReLU(inplace=True))
+
+
+class _Down(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), _DoubleConv(cin, cout))
+
+
+class _Up(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.up = nn.Upsample(scale_factor=2, mode="nearest")
+        self.conv = _DoubleConv(cin, cout, cin // 2)
+
+
+class _OutConv(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 1)
+
+
+class UNet(_PlanModel):
+    """The reference's in-tree `UNet(n_channels, n_classes, bilinear)` (SU/UArchModel/unet.py:104-245;
+    constructed as `UNet(n_channels=3, n_classes=num_classes, bilinear=True)` at SU/ModelTraining.py:242 and
+    SU/ModelEval.py:328): same module tree and `state_dict()` keys, default PyTorch initialisation in the
+    same construction order.  Only the configuration the reference constructs is built (3 input channels,
+    `bilinear=True`, whose Up block is nearest x2); the transposed-convolution variant raises."""
+
+    _size_multiple = 16   # four MaxPool2d(2) stages; F.pad to the skip size is then the identity
+
+    def __init__(self, n_channels=3, n_classes=2, bilinear=False):
+        super().__init__()
+        if n_channels != 3:
+            raise NotImplementedError("only n_channels=3 is built (the reference's call sites)")
+        if not bilinear:
+            raise NotImplementedError("bilinear=False (ConvTranspose2d upsampling) is not built; the reference "
+                                      "constructs UNet(..., bilinear=True)")
+        self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear
+        self.inc = _DoubleConv(n_channels, 64)
+        self.down1 = _Down(64, 128)
+        self.down2 = _Down(128, 256)
+        self.down3 = _Down(256, 512)
+        self.down4 = _Down(512, 512)
+        self.up1 = _Up(1024, 256)
+        self.up2 = _Up(512, 128)
+        self.up3 = _Up(256, 64)
+        self.up4 = _Up(128, 64)
+        self.outc = _OutConv(64, n_classes)
+
+    def _graph(self):
+        return graph.unet_graph(self.n_classes)
 
 
 def create_model(arch="UnetPlusPlus", encoder_name="resnet18", encoder_weights=None, in_channels=3,

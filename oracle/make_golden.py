@@ -13,6 +13,9 @@ What is pinned:
                           torch.manual_seed(6210) with torchvision `pretrained` patched off
                           (no network); stores the input, the logits and a per-tensor checksum
                           of the state_dict so the weights can be regenerated and verified.
+  unet_reference.npz      SU/UArchModel/unet.py UNet(n_channels=3, n_classes=3, bilinear=True) (the call
+                          of SU/ModelTraining.py:242): eval-mode logits with randomised BatchNorm
+                          statistics and train-mode logits on a seeded 2x3x32x48 input, same checksums.
 """
 import argparse
 import os
@@ -48,8 +51,38 @@ def metric_cases():
     return cases
 
 
+def unet_golden():
+    """Run the reference's own UNet (package import: unet.py does `from .unet_parts import *`)."""
+    sys.path.insert(0, REF)
+    from UArchModel import unet as ref_unet  # the reference's SU/UArchModel/unet.py
+    torch.manual_seed(6210)
+    model = ref_unet.UNet(n_channels=3, n_classes=3, bilinear=True)
+    g = torch.Generator().manual_seed(6211)
+    for m in model.modules():   # non-trivial BatchNorm state, as tests/helpers.model_pair does
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5, generator=g)
+            m.bias.data.normal_(0, 0.2, generator=g)
+            m.running_mean.normal_(0, 0.2, generator=g)
+            m.running_var.uniform_(0.5, 1.5, generator=g)
+    x = torch.randn((2, 3, 32, 48), generator=torch.Generator().manual_seed(1))
+    model.eval()
+    with torch.no_grad():
+        y_eval = model(x)
+    sums = {k: float(v.double().sum()) for k, v in model.state_dict().items() if v.dtype.is_floating_point}
+    model.train()
+    with torch.no_grad():
+        y_train = model(x)
+    np.savez_compressed(os.path.join(OUT, "unet_reference.npz"), x=x.numpy(), logits_eval=y_eval.numpy(),
+                        logits_train=y_train.numpy(), keys=np.array(list(sums.keys())),
+                        sums=np.array(list(sums.values())))
+    print("wrote unet_reference.npz")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--unet-only" in sys.argv:
+        unet_golden()
+        return
     U = load_reference_utils()
     args = types.SimpleNamespace(dataset="sarrarp50")
     out = {}
@@ -102,6 +135,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "resnet_unet_reference.npz"), x=x.numpy(), logits=y.numpy(),
                         keys=np.array(list(sums.keys())), sums=np.array(list(sums.values())))
     torchvision.models.resnet18, torchvision.models.resnet34 = orig18, orig34
+    unet_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 

@@ -104,3 +104,39 @@ def resnet_unet_relu_order(resnet_model):
             names += [base + "t1", base + "out"]
     names += ["l4p", "l3p", "d3", "l2p", "d2", "l1p", "d1", "l0p", "d0", "dfull"]
     return names
+
+
+class _RoutedMaxPool2(torch.autograd.Function):
+    """MaxPool2d(2) whose backward routes through externally supplied window positions (0..3)."""
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        ctx.save_for_backward(pos)
+        ctx.shape = x.shape
+        return torch.nn.functional.max_pool2d(x, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        n, c, h, w = ctx.shape
+        gin = torch.zeros((n, c, h, w), dtype=g.dtype)
+        ho, wo = g.shape[2], g.shape[3]
+        for k in range(4):
+            dy, dx = k // 2, k % 2
+            gin[:, :, dy:2 * ho:2, dx:2 * wo:2] = g * (pos == k)
+        return gin, None
+
+
+def install_pool_routes(ref, eng, pool_names):
+    """Every nn.MaxPool2d of `ref`, in call order, back-propagates through the engine's recorded argmax
+    positions: with bf16 activations near-ties inside a window resolve differently than in fp32, which
+    moves gradients the same way a flipped ReLU mask does (see install_engine_masks)."""
+    queue = [eng.acts[n].idx.permute(0, 3, 1, 2).cpu().long() for n in pool_names]
+
+    def hook(mod, inp, out):
+        return _RoutedMaxPool2.apply(inp[0], queue.pop(0))
+
+    for m in ref.modules():
+        if isinstance(m, torch.nn.MaxPool2d):
+            m.register_forward_hook(hook)
+    return queue

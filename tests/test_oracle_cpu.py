@@ -75,6 +75,39 @@ def test_resnet_unet_matches_reference_golden():
     assert np.allclose(y.numpy(), g["logits"], rtol=0, atol=1e-5)
 
 
+def _oracle_unet_like_golden():
+    from oracle.unet import UNet
+    torch.manual_seed(6210)
+    model = UNet(3, 3, bilinear=True)
+    g = torch.Generator().manual_seed(6211)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5, generator=g)
+            m.bias.data.normal_(0, 0.2, generator=g)
+            m.running_mean.normal_(0, 0.2, generator=g)
+            m.running_var.uniform_(0.5, 1.5, generator=g)
+    return model
+
+
+def test_unet_matches_reference_golden():
+    """oracle/unet.py against the reference's own UNet(3, 3, bilinear=True) run by oracle/make_golden.py:
+    identical weights from the same seed, eval- and train-mode logits."""
+    g = np.load(os.path.join(GOLD, "unet_reference.npz"))
+    model = _oracle_unet_like_golden()
+    sd = model.state_dict()
+    assert [str(k) for k in g["keys"]] == [k for k, v in sd.items() if v.dtype.is_floating_point]
+    for k, s in zip(g["keys"], g["sums"]):
+        assert abs(float(sd[str(k)].double().sum()) - float(s)) <= 1e-9 * max(1.0, abs(float(s))), k
+    x = torch.from_numpy(g["x"])
+    model.eval()
+    with torch.no_grad():
+        assert np.allclose(model(x).numpy(), g["logits_eval"], rtol=0, atol=1e-5)
+    model.train()
+    with torch.no_grad():
+        assert np.allclose(model(x).numpy(), g["logits_train"], rtol=0, atol=1e-5)
+    assert sum(p.numel() for p in model.parameters()) == 17267523     # 17.27 M (SURVEY 8a-3)
+
+
 def test_unetpp_structure_pins():
     """README torchinfo dump of UnetPlusPlus + mobilenetv3 (MMR_EN:DE_CODER/README.md:149-188):
     the restated decoder formula reproduces all 11 block parameter counts and their sum; the
