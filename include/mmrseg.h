@@ -409,6 +409,22 @@ int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int W, void* o
                        float* dbias, int accumulate, mmr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Sliding-window inference (monai.inferers.sliding_window_inference with mode="constant", called at
+ * ED/Main_MMR_SegModel.py:1308-1317, followed by preds.argmax(1) at :1320).  Windows of one frame are
+ * ordered (iy, ix) over the start lists ys[ny] x xs[nx]; window w = frame * ny*nx + iy*nx + ix.
+ * ------------------------------------------------------------------------------------ */
+/* Copy windows [w_begin, w_begin + w_count) into the predictor's input batch: fp32 NCHW frames
+ * [N][3][H][W] -> [w_count][3][rh][rw], or (is_u8) uint8 NHWC frames [N][H][W][3] -> [w_count][rh][rw][3].
+ * Windows past the last one (padding of the final batch) are zero. */
+int mmr_window_gather(const void* frames, int is_u8, int N, int H, int W, const int* ys, int ny, const int* xs,
+                      int nx, int rh, int rw, int w_begin, int w_count, void* out, mmr_stream_t stream);
+/* out[n][c][y][x] = mean over the windows covering (y, x) of win_logits[w][c][y - y0(w)][x - x0(w)], summed in
+ * window order by one thread per pixel (deterministic); pred (int64 [N][H][W], optional) = argmax over c of the
+ * blended logits with torch's first-maximum / NaN rule.  Either output may be NULL. */
+int mmr_window_blend(const float* win_logits, int N, int C, int H, int W, const int* ys, int ny, const int* xs,
+                     int nx, int rh, int rw, float* out, int64_t* pred, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Metric: argmax -> per-image confusion matrix, integer and bit-exact.
  * Replaces torch.argmax + Evaluate.addBatch (SU/utils.py:82-138) and smp get_stats
  * (ED/Main_MMR_SegModel.py:634-639,1323-1325): cm[n][g][p] += #{label==g & pred==p}.

@@ -174,6 +174,10 @@ SIGNATURES = {
     "mmr_bias_grad_finalize": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "mmr_maxpool3x3s2_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mmr_maxpool3x3s2_bwd": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_window_gather": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int), _i, C.POINTER(C.c_int), _i, _i, _i, _i, _i,
+                               _vp, _vp]),
+    "mmr_window_blend": (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_int), _i, C.POINTER(C.c_int), _i, _i, _i, _vp, _vp,
+                              _vp]),
     "mmr_maxpool2x2s2_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mmr_maxpool2x2s2_bwd": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp]),
     "mmr_upsample_bilinear2x_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
