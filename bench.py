@@ -29,6 +29,8 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
 import torch  # noqa: E402
 
 METRIC = "train images/sec (512x512, U-Net++)"
+WORKLOAD = ("BASELINE configs[1]: U-Net++ (resnet18 encoder, random init) binary train step "
+            "fwd + 0.5*Dice+0.5*CE + bwd + Adam(lr 1e-3, wd 1e-5), batch %d per GPU @ %dx%d")
 H = W = 512
 CLASSES = 2
 BATCH_PER_GPU = 16
@@ -138,8 +140,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "U-Net++ (resnet18) binary train step fwd+bwd+Adam, %dx%d" % (H, W),
-                       "batch_per_step": CPU_SAMPLE_BATCH},
+            "config": {"workload": WORKLOAD % (BATCH_PER_GPU, H, W), "global_batch": BATCH_PER_GPU * args.gpus,
+                       "classes": CLASSES, "parallelism": "cpu, %d threads" % cores,
+                       "sample_batch_per_step": CPU_SAMPLE_BATCH},
             "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -310,8 +313,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: U-Net++ (resnet18 encoder, random init) binary train step "
-                                   "fwd + 0.5*Dice+0.5*CE + bwd + Adam(lr 1e-3, wd 1e-5), batch %d per GPU @ %dx%d" % (n, H, W),
+            "config": {"workload": WORKLOAD % (n, H, W),
                        "global_batch": world * n, "classes": CLASSES, "parallelism": "dp%d" % world,
                        "l2": "per-step working set %.1f GB >> 126 MB L2 (no flush needed)" % (
                            (eng.arena_bytes + sum(a.buf.numel() * a.buf.element_size() for a in eng.acts.values() if a.buf is not None)) / 1e9),
