@@ -338,6 +338,12 @@ int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, int C, const
 /* dz = coefA*g + coefB*xhat + coefC, bf16. */
 int mmr_bn_bwd_apply(const void* g, const void* z, const float* mean, const float* invstd,
                      const float* coef, int64_t P, int C, void* dz, mmr_stream_t stream);
+/* The same for a unit with ONE full-resolution gradient contribution dx and no residual: the masked
+ * gradient g = (z*mask_scale + mask_shift > 0) ? dx : 0 is recomputed here, so mmr_bn_bwd_reduce_fused
+ * may be called with g = NULL (it then writes nothing but the sums). */
+int mmr_bn_bwd_apply_masked(const void* dx, const void* z, const float* mean, const float* invstd,
+                            const float* coef, const float* mask_scale, const float* mask_shift, int64_t P,
+                            int C, void* dz, mmr_stream_t stream);
 /* g = mask * sum(contribs) only (layers without BN), plus optional per-channel sum (bias
  * gradient) as double partials. */
 int mmr_grad_gather(const MmrContrib* contribs, int ncontrib, const void* act, int N, int H, int W,

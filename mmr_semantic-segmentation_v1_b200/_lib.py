@@ -170,6 +170,7 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "mmr_bn_bwd_finalize": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "mmr_bn_bwd_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "mmr_bn_bwd_apply_masked": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "mmr_grad_gather": (_i, [C.POINTER(MmrContrib), _i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "mmr_bias_grad_finalize": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "mmr_maxpool3x3s2_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -328,7 +328,7 @@ __device__ __forceinline__ void finish_row(const ContribList& cl, const RowGeom&
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
   }
-  store8(gout + (size_t)r * C + c, g);
+  if (gout) store8(gout + (size_t)r * C + c, g);   // NULL: the apply pass recomputes g from the contribution
   if (MODE == 1 || MODE == 3) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) f1[j] += g[j], f2[j] += g[j] * zz[j];
@@ -673,6 +673,61 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
       if (!FIXED) load_coef((int)((uint64_t)i1 % groups) * 8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = ca[j] * g1[j] + pz[j] * z1[j] + q[j];
+      store8(dz + i1 * 8, o);
+    }
+  }
+}
+
+// The same for a unit whose only gradient contribution is one full-resolution tensor dx and whose ReLU
+// mask is a function of z (no residual): g = (z*msc + msh > 0) ? dx : 0 is recomputed here, so the
+// reduction pass never writes g and this pass reads dx instead (2 B/element less traffic per unit).
+template <bool FIXED>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_masked_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ z,
+                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                           const float* __restrict__ coef, const float* __restrict__ msc_,
+                           const float* __restrict__ msh_, int64_t P, int C, __nv_bfloat16* __restrict__ dz) {
+  const uint32_t groups = (uint32_t)C / 8;
+  const int64_t total = P * groups;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float ca[8], pz[8], q[8], msc[8], msh[8];
+  auto load_coef = [&](int c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float is = __ldg(invstd + c + j), cb = __ldg(coef + C + c + j);
+      ca[j] = __ldg(coef + c + j);
+      pz[j] = cb * is;
+      q[j] = __ldg(coef + 2 * C + c + j) - cb * __ldg(mean + c + j) * is;
+      msc[j] = __ldg(msc_ + c + j);
+      msh[j] = __ldg(msh_ + c + j);
+    }
+  };
+  if (FIXED) load_coef((int)((uint64_t)i % groups) * 8);
+  for (; i < total; i += 2 * stride) {
+    const int64_t i1 = i + stride;
+    const bool two = i1 < total;
+    float g0[8], z0[8], g1[8], z1[8], o[8];
+    load8(dx + i * 8, g0);
+    load8(z + i * 8, z0);
+    if (two) {
+      load8(dx + i1 * 8, g1);
+      load8(z + i1 * 8, z1);
+    }
+    if (!FIXED) load_coef((int)((uint64_t)i % groups) * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g = fmaf(z0[j], msc[j], msh[j]) > 0.f ? g0[j] : 0.f;
+      o[j] = ca[j] * g + pz[j] * z0[j] + q[j];
+    }
+    store8(dz + i * 8, o);
+    if (two) {
+      if (!FIXED) load_coef((int)((uint64_t)i1 % groups) * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = fmaf(z1[j], msc[j], msh[j]) > 0.f ? g1[j] : 0.f;
+        o[j] = ca[j] * g + pz[j] * z1[j] + q[j];
+      }
       store8(dz + i1 * 8, o);
     }
   }
@@ -1205,6 +1260,23 @@ extern "C" int mmr_bn_bwd_apply(const void* g, const void* z, const float* mean,
     bn_bwd_apply_kernel<false><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
         reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd,
         coef, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_bn_bwd_apply_masked(const void* dx, const void* z, const float* mean, const float* invstd,
+                                       const float* coef, const float* mask_scale, const float* mask_shift,
+                                       int64_t P, int C, void* dz, mmr_stream_t stream) {
+  MMR_REQUIRE(C % 8 == 0 && mask_scale && mask_shift, "C must be a multiple of 8; mask_scale / mask_shift required");
+  const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
+  if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
+    bn_bwd_apply_masked_kernel<true><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,
+        mask_scale, mask_shift, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
+  else
+    bn_bwd_apply_masked_kernel<false><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,
+        mask_scale, mask_shift, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -573,17 +573,26 @@ class Engine:
                         u["bwd_ticket"] = self._ticket()
                     # without a residual the ReLU mask is a function of z alone: do not re-read the activation
                     zmask = relu_act is not None and u.get("res") is None
+                    # one full-resolution contribution: the apply pass recomputes the masked gradient from it,
+                    # the reduction writes no g at all
+                    nog = zmask and cnt == 1 and not out.contribs[0][1] and not os.environ.get("MMR_NO_NOG")
                     self._rec(calls, "mmr_bn_bwd_reduce_fused", arr, cnt, None if zmask else relu_act, u["z"],
-                              u["mean"], u["invstd"], n, ho, wo, Cc, g, self.bwd_slots, nblk, self.P[bn + ".weight"],
+                              u["mean"], u["invstd"], n, ho, wo, Cc, None if nog else g, self.bwd_slots, nblk,
+                              self.P[bn + ".weight"],
                               self.G[bn + ".weight"], self.G[bn + ".bias"], acc, u["coef"], u["bwd_ticket"],
                               u["scale"] if zmask else None, u["shift"] if zmask else None)
                 else:
+                    nog = False
                     self._rec(calls, "mmr_bn_bwd_reduce", arr, cnt, relu_act, u["z"], u["mean"], u["invstd"],
                               n, ho, wo, Cc, g, self.bn_partial, nblk)
                     self._rec(calls, "mmr_bn_bwd_finalize", self.bn_partial, nblk, Pn, Cc,
                               self.P[bn + ".weight"], u["invstd"], self.G[bn + ".weight"],
                               self.G[bn + ".bias"], acc, u["coef"])
-                self._rec(calls, "mmr_bn_bwd_apply", g, u["z"], u["mean"], u["invstd"], u["coef"], Pn, Cc, dz)
+                if nog:
+                    self._rec(calls, "mmr_bn_bwd_apply_masked", out.contribs[0][0], u["z"], u["mean"], u["invstd"],
+                              u["coef"], u["scale"], u["shift"], Pn, Cc, dz)
+                else:
+                    self._rec(calls, "mmr_bn_bwd_apply", g, u["z"], u["mean"], u["invstd"], u["coef"], Pn, Cc, dz)
             else:
                 has_bias = u["op"].get("bias")
                 self._rec(calls, "mmr_grad_gather", arr, cnt, relu_act, n, ho, wo, Cc, g,

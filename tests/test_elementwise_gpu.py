@@ -141,6 +141,19 @@ def test_bn_bwd_reduce_fused_mask_from_z():
         assert torch.allclose(dgamma, dgamma_ref, rtol=1e-5, atol=1e-5)
         assert torch.allclose(dbeta, dbeta_ref, rtol=1e-5, atol=1e-5)
         assert torch.allclose(coef, coef_ref, rtol=1e-5, atol=1e-7)
+    # no-g variant: the reduction writes only the sums, the apply pass recomputes the masked gradient from dx
+    dz_ref = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+    dz = torch.empty(shape, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.mmr_bn_bwd_apply(_p(g_ref), _p(z), _p(st[0]), _p(st[1]), _p(coef_ref), P, c, _p(dz_ref), _s()))
+    coef = torch.empty((3, c), device="cuda")
+    L.check(lib.mmr_bn_bwd_reduce_fused(arr, 1, None, _p(z), _p(st[0]), _p(st[1]), n, h, w, c, None, _p(slots), nblk,
+                                        _p(gamma), _p(dgamma), _p(dbeta), 0, _p(coef), _p(ticket), _p(st[2]),
+                                        _p(st[3]), _s()))
+    L.check(lib.mmr_bn_bwd_apply_masked(_p(g1), _p(z), _p(st[0]), _p(st[1]), _p(coef), _p(st[2]), _p(st[3]), P, c,
+                                        _p(dz), _s()))
+    torch.cuda.synchronize()
+    assert torch.allclose(coef, coef_ref, rtol=1e-5, atol=1e-7)
+    assert (dz.float() - dz_ref.float()).abs().max().item() <= 2.0 ** -7 * dz_ref.float().abs().max().item()
 
 
 def test_grad_gather_pool2_and_mask():
