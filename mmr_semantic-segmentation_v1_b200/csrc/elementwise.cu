@@ -383,7 +383,9 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
   }
   int since_flush = 0;
   const uint32_t stride = (uint32_t)gridDim.x * rows_per_iter;
-  constexpr int R = MODE == 0 ? 4 : (POOLED ? 1 : 2);  // rows in flight per thread
+  // rows in flight per thread: with 2 x 256 threads per SM a row of (NC + 2) 16-byte loads must be
+  // multiplied up to ~100 B per thread to cover the HBM latency-bandwidth product (~44 KB per SM)
+  constexpr int R = MODE == 0 ? 4 : (POOLED ? 1 : (NC == 1 ? 4 : (NC == 2 ? 3 : 2)));
   for (uint32_t r0 = (uint32_t)blockIdx.x * rows_per_iter + rl; r0 < P; r0 += R * stride) {
     if (MODE == 0) {
       uint4 raw[R];
