@@ -1,4 +1,6 @@
 // Error handling, device probing and CUtensorMap encoding for libmmrseg.so.
+#include <stdlib.h>
+
 #include "common.h"
 
 #include <cudaTypedefs.h>
@@ -20,6 +22,11 @@ int fail(const char* fmt, ...) {
   va_end(ap);
   g_last_error = buf;
   return -1;
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("MMR_NO_PDL") == nullptr;
+  return on;
 }
 
 int num_sms() {

@@ -38,4 +38,41 @@ int encode_mat_map(CUtensorMap* out, const void* ptr, int rows, int cols, int bo
 inline cudaStream_t as_stream(mmr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 int num_sms();
 
+// Programmatic dependent launch: every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_prologue().  The next
+// kernel of the stream (or graph) is then scheduled while this one drains -- its launch latency, block
+// scheduling and whatever precedes its own griddepcontrol.wait overlap our tail -- and blocks in
+// griddepcontrol.wait until this grid has completed and its writes are visible.  wait comes before
+// launch_dependents, so a kernel never runs ahead of its grandparent either.  MMR_NO_PDL=1 turns the
+// attribute off (the prologue is then a no-op).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef MMR_PDL_EARLY_TRIGGER
+#define MMR_PDL_EARLY_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_wait();
+#if MMR_PDL_EARLY_TRIGGER
+  pdl_trigger();
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t mmr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 }  // namespace mmr

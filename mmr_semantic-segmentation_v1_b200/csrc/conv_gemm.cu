@@ -119,6 +119,7 @@ __device__ __forceinline__ void store_row16(const ConvParams& p, const MmrOutSeg
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms and the UMMA descriptors assume it.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -276,6 +277,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
 // Scalar reference: one CTA per tile, one thread per pixel row, same tables and epilogue.
 __global__ void __launch_bounds__(kTileM)
 conv_gemm_ref_kernel(const __grid_constant__ ConvParams p) {
+  pdl_prologue();
   const int t = blockIdx.x;
   if (t >= p.total_tiles) return;
   const TileCoord tc = decode_tile(p, t);
@@ -464,9 +466,9 @@ extern "C" int mmr_conv_plan_run(void* plan, int impl, mmr_stream_t stream) {
   ConvPlan* pl = reinterpret_cast<ConvPlan*>(plan);
   if (pl->prm.total_tiles == 0) return 0;
   if (impl == 0) {
-    conv_gemm_tc_kernel<<<pl->grid, kThreads, pl->smem_bytes, as_stream(stream)>>>(pl->prm);
+    mmr_launch((conv_gemm_tc_kernel), pl->grid, kThreads, pl->smem_bytes, as_stream(stream), pl->prm);
   } else {
-    conv_gemm_ref_kernel<<<pl->prm.total_tiles, kTileM, 0, as_stream(stream)>>>(pl->prm);
+    mmr_launch((conv_gemm_ref_kernel), pl->prm.total_tiles, kTileM, 0, as_stream(stream), pl->prm);
   }
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -483,6 +483,7 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
 
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* halo_base = smem;
   uint8_t* w_base = halo_base + (size_t)p.halo_stages * p.halo_stage_bytes;
@@ -842,6 +843,7 @@ __device__ __forceinline__ int pack_tap(int t, int layout) { return layout ? (2 
 
 __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int O, int I, int mode, int cb, int bn,
                                          int n_ntiles, int nchunks, int layout, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int64_t total = (int64_t)n_ntiles * nchunks * 9 * bn * cb;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -867,6 +869,7 @@ __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int O, int
 
 // Every layer's packing in one launch: blockIdx.y selects the job.
 __global__ void pack_weights_halo_batch_kernel(const MmrPackJob* __restrict__ jobs) {
+  pdl_prologue();
   const MmrPackJob j = jobs[blockIdx.y];
   const float* __restrict__ w = j.w_oihw;
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(j.out);
@@ -1130,7 +1133,7 @@ extern "C" int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream) {
   MMR_REQUIRE(plan, "null plan");
   HaloPlan* pl = reinterpret_cast<HaloPlan*>(plan);
   if (pl->prm.total_items == 0) return 0;
-  conv_halo_kernel<<<pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream)>>>(pl->prm);
+  mmr_launch((conv_halo_kernel), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1152,8 +1155,7 @@ extern "C" int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  pack_weights_halo_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(
-      w_oihw, O, I, mode, cb, bn, n_ntiles, nchunks, layout, reinterpret_cast<__nv_bfloat16*>(out));
+  mmr_launch((pack_weights_halo_kernel), (int)blocks, 256, 0, as_stream(stream), w_oihw, O, I, mode, cb, bn, n_ntiles, nchunks, layout, reinterpret_cast<__nv_bfloat16*>(out));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1161,7 +1163,7 @@ extern "C" int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode
 extern "C" int mmr_pack_weights_halo_batch(const MmrPackJob* jobs_dev, int njobs, mmr_stream_t stream) {
   MMR_REQUIRE(jobs_dev && njobs > 0, "bad argument");
   dim3 grid(64, njobs);
-  pack_weights_halo_batch_kernel<<<grid, 256, 0, as_stream(stream)>>>(jobs_dev);
+  mmr_launch((pack_weights_halo_batch_kernel), grid, 256, 0, as_stream(stream), jobs_dev);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

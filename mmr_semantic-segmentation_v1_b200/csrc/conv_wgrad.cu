@@ -65,6 +65,7 @@ __device__ __forceinline__ WgStep wg_decode(const WgParams& p, int it) {
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -198,6 +199,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
 // Scalar reference on the same tables: one thread per (row, co); writes split 0 only.
 __global__ void __launch_bounds__(256)
 conv_wgrad_ref_kernel(const __grid_constant__ WgParams p) {
+  pdl_prologue();
   const size_t rows_total = (size_t)p.n_mtiles * 128;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows_total * p.cout) return;
@@ -231,6 +233,7 @@ conv_wgrad_ref_kernel(const __grid_constant__ WgParams p) {
 // Sum the split-K partials in split order and scatter into OIHW fp32.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const __grid_constant__ WgParams p, int n_split, int accumulate) {
+  pdl_prologue();
   const size_t rows_total = (size_t)p.n_mtiles * 128;
   const size_t total = rows_total * p.cout;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -379,16 +382,16 @@ extern "C" int mmr_wgrad_plan_run(void* plan, int impl, int accumulate, mmr_stre
   int n_split = p.n_split;
   if (impl == 0) {
     dim3 grid(p.n_groups * p.n_ntiles, p.n_split);
-    conv_wgrad_tc_kernel<<<grid, kWgThreads, pl->smem_bytes, as_stream(stream)>>>(p);
+    mmr_launch((conv_wgrad_tc_kernel), grid, kWgThreads, pl->smem_bytes, as_stream(stream), p);
   } else {
-    conv_wgrad_ref_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(p);
+    mmr_launch((conv_wgrad_ref_kernel), (unsigned)((total + 255) / 256), 256, 0, as_stream(stream), p);
     n_split = 1;
   }
   MMR_CUDA_CHECK(cudaGetLastError());
   int64_t blocks = (int64_t)((total + 255) / 256);
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(p, n_split, accumulate);
+  mmr_launch((wgrad_reduce_kernel), (int)blocks, 256, 0, as_stream(stream), p, n_split, accumulate);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -84,6 +84,7 @@ __device__ __forceinline__ void wh_view(int cb, int a, int pitch, int& voff_px, 
 
 __global__ void __launch_bounds__(kWhThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
   uint64_t* full = bars;
@@ -240,6 +241,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
 // flight); rows that belong to no filter tap are skipped before any load.
 __global__ void __launch_bounds__(256)
 wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
+  pdl_prologue();
   // 32 outputs (float4 each) per CTA x 8 split lanes (one warp each): a lane sums the splits
   // k = lane, lane + 8, ... with four loads in flight, the eight lane sums are added in lane order
   // through shared memory (deterministic), so the serial chain per thread is n_split / 8 long.
@@ -474,13 +476,13 @@ extern "C" int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t 
   WhPlan* pl = reinterpret_cast<WhPlan*>(plan);
   const WhParams& p = pl->prm;
   dim3 grid(p.nchunks * p.n_ntiles, p.n_split);
-  conv_wgrad_halo_kernel<<<grid, kWhThreads, pl->smem_bytes, as_stream(stream)>>>(p);
+  mmr_launch((conv_wgrad_halo_kernel), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
   MMR_CUDA_CHECK(cudaGetLastError());
   const size_t total = (size_t)p.A * 128 * (p.bn / 4) * p.nchunks * p.n_ntiles;
   int64_t blocks = (int64_t)((total + 31) / 32);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  wgrad_halo_reduce_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(p, accumulate);
+  mmr_launch((wgrad_halo_reduce_kernel), (int)blocks, 256, 0, as_stream(stream), p, accumulate);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const TIn* __restrict__ x, int N, int H, int W, int Ho, int Wo,
                    __nv_bfloat16* __restrict__ out, int kpad, const float* __restrict__ mean,
                    const float* __restrict__ std_) {
+  pdl_prologue();
   __shared__ float tile[3 * 7 * kStemTwp];
   __shared__ int lut[256];
   const int ox0 = blockIdx.x * kStemSeg, oy = blockIdx.y, n = blockIdx.z;
@@ -129,6 +130,7 @@ stem_im2col_kernel(const TIn* __restrict__ x, int N, int H, int W, int Ho, int W
 
 __global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C, int H, int W,
                                  __nv_bfloat16* __restrict__ out, int cpad) {
+  pdl_prologue();
   const int groups = cpad / 8;
   const int64_t hw = (int64_t)H * W;
   const int64_t total = (int64_t)N * hw * groups;
@@ -151,6 +153,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C, int 
 // uint8 HWC frames -> NHWC bf16 padded to cpad channels: x/255, optional (x-mean)/std.
 __global__ void pack_u8_kernel(const uint8_t* __restrict__ x, int64_t npix, __nv_bfloat16* __restrict__ out,
                                int cpad, const float* __restrict__ mean, const float* __restrict__ std_) {
+  pdl_prologue();
   const int groups = cpad / 8;
   const int64_t total = npix * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -174,6 +177,7 @@ __global__ void pack_u8_kernel(const uint8_t* __restrict__ x, int64_t npix, __nv
 
 __global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int N, int C, int ldc, int H,
                                    int W, float* __restrict__ out) {
+  pdl_prologue();
   const int64_t hw = (int64_t)H * W;
   const int64_t total = (int64_t)N * C * hw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -188,6 +192,7 @@ __global__ void unpack_nhwc_kernel(const __nv_bfloat16* __restrict__ x, int N, i
 __global__ void repack_weights_kernel(const float* __restrict__ w, int O, int I, int taps,
                                       __nv_bfloat16* __restrict__ fwd, int ldf,
                                       __nv_bfloat16* __restrict__ dgrad, int ldd, int o_pad) {
+  pdl_prologue();
   const int64_t total = (int64_t)O * I * taps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -358,6 +363,7 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
                    ContribList cl, const __nv_bfloat16* __restrict__ act,
                    const float* __restrict__ mean, const float* __restrict__ invstd, RowGeom geo,
                    __nv_bfloat16* __restrict__ gout, BwdFused fz) {
+  pdl_prologue();
   // double accumulators live in shared memory ([j][thread], conflict-free) so that two CTAs of
   // 256 threads fit the register file; the loop itself accumulates in fp32 and flushes every 16
   // iterations.  MODE 1 accumulates sum(g) and sum(g*z); sum(g*xhat) = (sum(g*z) - mean*sum(g))*invstd
@@ -480,7 +486,7 @@ static void launch_reduce(int nblk, cudaStream_t st, const __nv_bfloat16* z, uin
   bool pooled = false;
   for (int i = 0; i < cl.n; ++i) pooled |= cl.pool2[i] != 0;
 #define MMR_RR(NC, PL) \
-  reduce_rows_kernel<MODE, NC, PL><<<nblk, kEwThreads, 0, st>>>(z, P, C, partial, cl, act, mean, invstd, geo, g, fz)
+  mmr_launch((reduce_rows_kernel<MODE, NC, PL>), nblk, kEwThreads, 0, st, z, P, C, partial, cl, act, mean, invstd, geo, g, fz)
   if (pooled) {
     switch (cl.n) {
       case 1: MMR_RR(1, true); break;
@@ -533,6 +539,7 @@ bn_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P, int 
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float momentum, float* running_mean, float* running_var, int64_t* nbt, float* mean,
                    float* invstd, float* scale, float* shift) {
+  pdl_prologue();
   double s1, s2;
   reduce_partials8(partial, nblk, C, blockIdx.x * 8, s1, s2);
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) nbt[0] += 1;
@@ -562,6 +569,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, int C,
                 const float* __restrict__ scale, const float* __restrict__ shift,
                 const __nv_bfloat16* __restrict__ residual, int relu,
                 __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const uint32_t groups = (uint32_t)C / 8;
   const int64_t total = P * groups;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -623,6 +631,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const double* __restrict__ partial, int nblk, int64_t P, int C,
                        const float* __restrict__ gamma, const float* __restrict__ invstd, float* dgamma,
                        float* dbeta, int accumulate, float* coef) {
+  pdl_prologue();
   double s1, s2;
   reduce_partials8(partial, nblk, C, blockIdx.x * 8, s1, s2);
   const int c = blockIdx.x * 8 + (threadIdx.x & 7);
@@ -642,6 +651,7 @@ __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ z,
                     const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ coef, int64_t P, int C, __nv_bfloat16* __restrict__ dz) {
+  pdl_prologue();
   const uint32_t groups = (uint32_t)C / 8;
   const int64_t total = P * groups;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -689,6 +699,7 @@ bn_bwd_apply_masked_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bflo
                            const float* __restrict__ mean, const float* __restrict__ invstd,
                            const float* __restrict__ coef, const float* __restrict__ msc_,
                            const float* __restrict__ msh_, int64_t P, int C, __nv_bfloat16* __restrict__ dz) {
+  pdl_prologue();
   const uint32_t groups = (uint32_t)C / 8;
   const int64_t total = P * groups;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -738,6 +749,7 @@ bn_bwd_apply_masked_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bflo
 // ------------------------------------------------------------------ max-pool 3x3 s2 p1
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
                                    __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  pdl_prologue();
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int groups = C / 8;
   const int64_t total = (int64_t)N * Ho * Wo * groups;
@@ -780,6 +792,7 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, i
 // floor mode (an odd last row / column is dropped).  idx = position of the first maximum in scan order.
 __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
                                     __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+  pdl_prologue();
   const int Ho = H / 2, Wo = W / 2;
   const uint32_t groups = (uint32_t)C / 8;
   const uint32_t total = (uint32_t)N * Ho * Wo * groups;
@@ -813,6 +826,7 @@ __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, 
 
 __global__ void maxpool2_bwd_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N, int H, int W, int C,
                                     __nv_bfloat16* __restrict__ gin) {
+  pdl_prologue();
   const int Ho = H / 2, Wo = W / 2;
   const uint32_t groups = (uint32_t)C / 8;
   const uint32_t total = (uint32_t)N * H * W * groups;
@@ -848,6 +862,7 @@ template <int NC>
 __global__ void __launch_bounds__(kEwThreads)
 maxpool_bwd_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N, int H, int W, int C,
                    __nv_bfloat16* __restrict__ gin) {
+  pdl_prologue();
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const uint32_t groups = (uint32_t)C / 8;
   const uint32_t total = (uint32_t)N * H * W * groups;
@@ -936,6 +951,7 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, float scale) {
 
 __global__ void upsample_bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
                                                __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int H2 = 2 * H, W2 = 2 * W;
   const float sy = H2 > 1 ? (float)(H - 1) / (float)(H2 - 1) : 0.f;
   const float sx = W2 > 1 ? (float)(W - 1) / (float)(W2 - 1) : 0.f;
@@ -980,6 +996,7 @@ __device__ __forceinline__ void lerp_adjoint_weights(int i, int in, float scale,
 
 __global__ void upsample_bilinear2x_bwd_kernel(ContribList cl, int N, int H, int W, int C,
                                                __nv_bfloat16* __restrict__ gin) {
+  pdl_prologue();
   const int H2 = 2 * H, W2 = 2 * W;
   const float sy = H2 > 1 ? (float)(H - 1) / (float)(H2 - 1) : 0.f;
   const float sx = W2 > 1 ? (float)(W - 1) / (float)(W2 - 1) : 0.f;
@@ -1018,6 +1035,7 @@ __global__ void upsample_bilinear2x_bwd_kernel(ContribList cl, int N, int H, int
 // the definition is oracle/unetpp.py::DeepSupervisionUnetPlusPlus.
 __global__ void upsample_nearest_f32_kernel(const float* __restrict__ in, int64_t planes, int h, int w, int f,
                                             float* __restrict__ out) {
+  pdl_prologue();
   const int H = h * f, W = w * f;
   const int64_t total = planes * H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -1029,6 +1047,7 @@ __global__ void upsample_nearest_f32_kernel(const float* __restrict__ in, int64_
 }
 __global__ void sumpool_f32_kernel(const float* __restrict__ in, int64_t planes, int h, int w, int f,
                                    float* __restrict__ out) {
+  pdl_prologue();
   const int H = h * f, W = w * f;
   const int64_t total = planes * h * w;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -1048,6 +1067,7 @@ __global__ void sumpool_f32_kernel(const float* __restrict__ in, int64_t planes,
 __global__ void head_grad_prep_kernel(const float* __restrict__ dl, int N, int C, int H, int W,
                                       __nv_bfloat16* __restrict__ out, int cpad,
                                       double* __restrict__ partial) {
+  pdl_prologue();
   const int64_t hw = (int64_t)H * W;
   const int64_t total = (int64_t)N * hw;
   double acc[16];
@@ -1084,6 +1104,7 @@ __global__ void head_grad_prep_kernel(const float* __restrict__ dl, int N, int C
 
 __global__ void __launch_bounds__(256)
 head_bias_finalize_kernel(const double* __restrict__ partial, int nblk, int C, float* dbias, int accumulate) {
+  pdl_prologue();
   // 16 channels x 16 block-lanes, combined in lane order through shared memory (deterministic)
   __shared__ double sh[16][17];
   const int c = threadIdx.x & 15, lane = threadIdx.x >> 4;
@@ -1111,8 +1132,7 @@ extern "C" int mmr_stem_im2col(const float* x, int N, int H, int W, void* out, i
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   MMR_REQUIRE(kpad <= 256 && Ho <= 65535 && N <= 65535, "stem_im2col: kpad <= 256, Ho and N <= 65535");
   dim3 grid((Wo + kStemSeg - 1) / kStemSeg, Ho, N);
-  stem_im2col_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(
-      x, N, H, W, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out), kpad, mean, std_);
+  mmr_launch((stem_im2col_kernel<float>), grid, 256, 0, as_stream(stream), x, N, H, W, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out), kpad, mean, std_);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1123,8 +1143,7 @@ extern "C" int mmr_stem_im2col_u8(const uint8_t* x_nhwc, int N, int H, int W, vo
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   MMR_REQUIRE(Ho <= 65535 && N <= 65535, "stem_im2col: Ho and N <= 65535");
   dim3 grid((Wo + kStemSeg - 1) / kStemSeg, Ho, N);
-  stem_im2col_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>(
-      x_nhwc, N, H, W, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out), kpad, mean, std_);
+  mmr_launch((stem_im2col_kernel<uint8_t>), grid, 256, 0, as_stream(stream), x_nhwc, N, H, W, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out), kpad, mean, std_);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1133,8 +1152,7 @@ extern "C" int mmr_pack_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int 
                                               int cpad, mmr_stream_t stream) {
   MMR_REQUIRE(cpad % 8 == 0 && cpad >= C, "cpad must be a multiple of 8 and >= C");
   const int64_t total = (int64_t)N * H * W * (cpad / 8);
-  pack_nchw_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
-      x, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), cpad);
+  mmr_launch((pack_nchw_kernel), ew_blocks(total, 16), kEwThreads, 0, as_stream(stream), x, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), cpad);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1144,8 +1162,7 @@ extern "C" int mmr_pack_nhwc_u8_to_nhwc_bf16(const uint8_t* x, int N, int H, int
   MMR_REQUIRE(cpad % 8 == 0 && cpad >= 8, "cpad must be a multiple of 8");
   MMR_REQUIRE((mean == nullptr) == (std_ == nullptr), "pass both mean and std or neither");
   const int64_t npix = (int64_t)N * H * W;
-  pack_u8_kernel<<<ew_blocks(npix * (cpad / 8), 16), kEwThreads, 0, as_stream(stream)>>>(
-      x, npix, reinterpret_cast<__nv_bfloat16*>(out), cpad, mean, std_);
+  mmr_launch((pack_u8_kernel), ew_blocks(npix * (cpad / 8), 16), kEwThreads, 0, as_stream(stream), x, npix, reinterpret_cast<__nv_bfloat16*>(out), cpad, mean, std_);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1153,8 +1170,7 @@ extern "C" int mmr_pack_nhwc_u8_to_nhwc_bf16(const uint8_t* x, int N, int H, int
 extern "C" int mmr_unpack_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int ldc, int H, int W,
                                                 float* out, mmr_stream_t stream) {
   const int64_t total = (int64_t)N * C * H * W;
-  unpack_nhwc_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), N, C, ldc, H, W, out);
+  mmr_launch((unpack_nhwc_kernel), ew_blocks(total, 16), kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), N, C, ldc, H, W, out);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1164,8 +1180,7 @@ extern "C" int mmr_repack_weights(const float* w, int O, int I, int taps, void* 
   MMR_REQUIRE(!fwd || ldf >= taps * I, "forward row stride too small");
   MMR_REQUIRE(!dgrad || (o_pad >= O && ldd >= taps * o_pad), "dgrad row stride too small");
   const int64_t total = (int64_t)O * I * taps;
-  repack_weights_kernel<<<ew_blocks(total, 4), kEwThreads, 0, as_stream(stream)>>>(
-      w, O, I, taps, reinterpret_cast<__nv_bfloat16*>(fwd), ldf,
+  mmr_launch((repack_weights_kernel), ew_blocks(total, 4), kEwThreads, 0, as_stream(stream), w, O, I, taps, reinterpret_cast<__nv_bfloat16*>(fwd), ldf,
       reinterpret_cast<__nv_bfloat16*>(dgrad), ldd, o_pad);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1191,8 +1206,7 @@ extern "C" int mmr_bn_stats(const void* z, int64_t P, int C, double* partial, in
   ContribList cl;
   fill_contribs(cl, nullptr, 0);
   MMR_REQUIRE(P < ((int64_t)1 << 31), "row count must be below 2^31");
-  reduce_rows_kernel<0, 0, false><<<nblk, kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, partial, cl, nullptr, nullptr, nullptr,
+  mmr_launch((reduce_rows_kernel<0, 0, false>), nblk, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), (uint32_t)P, C, partial, cl, nullptr, nullptr, nullptr,
       make_geom(1, 1), nullptr, BwdFused{});
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1202,8 +1216,7 @@ extern "C" int mmr_bn_finalize(const double* partial, int nblk, int64_t P, int C
                                const float* beta, float eps, float momentum, float* running_mean,
                                float* running_var, int64_t* nbt, float* mean, float* invstd,
                                float* scale, float* shift, mmr_stream_t stream) {
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(
-      partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd,
+  mmr_launch((bn_finalize_kernel), (C + 7) / 8, 256, 0, as_stream(stream), partial, nblk, P, C, gamma, beta, eps, momentum, running_mean, running_var, nbt, mean, invstd,
       scale, shift);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1214,12 +1227,10 @@ extern "C" int mmr_bn_apply(const void* z, int64_t P, int C, const float* scale,
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
   if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
-    bn_apply_kernel<true><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
+    mmr_launch((bn_apply_kernel<true>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
         reinterpret_cast<const __nv_bfloat16*>(residual), relu, reinterpret_cast<__nv_bfloat16*>(out));
   else
-    bn_apply_kernel<false><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
+    mmr_launch((bn_apply_kernel<false>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
         reinterpret_cast<const __nv_bfloat16*>(residual), relu, reinterpret_cast<__nv_bfloat16*>(out));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1244,8 +1255,7 @@ extern "C" int mmr_bn_bwd_reduce(const MmrContrib* contribs, int ncontrib, const
 extern "C" int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, int C,
                                    const float* gamma, const float* invstd, float* dgamma,
                                    float* dbeta, int accumulate, float* coef, mmr_stream_t stream) {
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(
-      partial, nblk, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
+  mmr_launch((bn_bwd_finalize_kernel), (C + 7) / 8, 256, 0, as_stream(stream), partial, nblk, P, C, gamma, invstd, dgamma, dbeta, accumulate, coef);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1255,12 +1265,10 @@ extern "C" int mmr_bn_bwd_apply(const void* g, const void* z, const float* mean,
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
   if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
-    bn_bwd_apply_kernel<true><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd,
+    mmr_launch((bn_bwd_apply_kernel<true>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd,
         coef, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
   else
-    bn_bwd_apply_kernel<false><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd,
+    mmr_launch((bn_bwd_apply_kernel<false>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd,
         coef, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1272,12 +1280,10 @@ extern "C" int mmr_bn_bwd_apply_masked(const void* dx, const void* z, const floa
   MMR_REQUIRE(C % 8 == 0 && mask_scale && mask_shift, "C must be a multiple of 8; mask_scale / mask_shift required");
   const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
   if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
-    bn_bwd_apply_masked_kernel<true><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,
+    mmr_launch((bn_bwd_apply_masked_kernel<true>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,
         mask_scale, mask_shift, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
   else
-    bn_bwd_apply_masked_kernel<false><<<blocks, kEwThreads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,
+    mmr_launch((bn_bwd_apply_masked_kernel<false>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,
         mask_scale, mask_shift, P, C, reinterpret_cast<__nv_bfloat16*>(dz));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1301,6 +1307,7 @@ extern "C" int mmr_grad_gather(const MmrContrib* contribs, int ncontrib, const v
 // Bias gradient of a conv without BatchNorm: column sums left by mmr_grad_gather.
 __global__ void bias_grad_finalize_kernel(const double* __restrict__ partial, int nblk, int C,
                                           float* dbias, int accumulate) {
+  pdl_prologue();
   double s1, s2;
   reduce_partials8(partial, nblk, C, blockIdx.x * 8, s1, s2);
   const int c = blockIdx.x * 8 + (threadIdx.x & 7);
@@ -1310,7 +1317,7 @@ __global__ void bias_grad_finalize_kernel(const double* __restrict__ partial, in
 
 extern "C" int mmr_bias_grad_finalize(const double* partial, int nblk, int C, float* dbias,
                                       int accumulate, mmr_stream_t stream) {
-  bias_grad_finalize_kernel<<<(C + 7) / 8, 256, 0, as_stream(stream)>>>(partial, nblk, C, dbias,
+  mmr_launch((bias_grad_finalize_kernel), (C + 7) / 8, 256, 0, as_stream(stream), partial, nblk, C, dbias,
                                                                          accumulate);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1321,8 +1328,7 @@ extern "C" int mmr_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, v
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  maxpool_fwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out),
+  mmr_launch((maxpool_fwd_kernel), ew_blocks(total, 16), kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out),
       idx);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1340,13 +1346,13 @@ extern "C" int mmr_maxpool3x3s2_bwd(const MmrContrib* contribs, int ncontrib, co
   const int blocks = ew_blocks(total, 64);
   __nv_bfloat16* go = reinterpret_cast<__nv_bfloat16*>(gin);
   if (!pooled && cl.n == 1)
-    maxpool_bwd_kernel<1><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
+    mmr_launch((maxpool_bwd_kernel<1>), blocks, kEwThreads, 0, as_stream(stream), cl, idx, N, H, W, C, go);
   else if (!pooled && cl.n == 2)
-    maxpool_bwd_kernel<2><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
+    mmr_launch((maxpool_bwd_kernel<2>), blocks, kEwThreads, 0, as_stream(stream), cl, idx, N, H, W, C, go);
   else if (!pooled && cl.n == 3)
-    maxpool_bwd_kernel<3><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
+    mmr_launch((maxpool_bwd_kernel<3>), blocks, kEwThreads, 0, as_stream(stream), cl, idx, N, H, W, C, go);
   else
-    maxpool_bwd_kernel<0><<<blocks, kEwThreads, 0, as_stream(stream)>>>(cl, idx, N, H, W, C, go);
+    mmr_launch((maxpool_bwd_kernel<0>), blocks, kEwThreads, 0, as_stream(stream), cl, idx, N, H, W, C, go);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1356,8 +1362,7 @@ extern "C" int mmr_maxpool2x2s2_fwd(const void* x, int N, int H, int W, int C, v
   MMR_REQUIRE(C % 8 == 0 && H >= 2 && W >= 2, "C must be a multiple of 8 and the image at least 2x2");
   const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   MMR_REQUIRE((int64_t)N * H * W * (C / 8) < ((int64_t)1 << 31), "max-pool: tensor too large for 32-bit indexing");
-  maxpool2_fwd_kernel<<<ew_blocks(total, 64), kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out), idx);
+  mmr_launch((maxpool2_fwd_kernel), ew_blocks(total, 64), kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out), idx);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1369,8 +1374,7 @@ extern "C" int mmr_maxpool2x2s2_bwd(const MmrContrib* contribs, int ncontrib, co
   if (fill_contribs(cl, contribs, ncontrib)) return -1;
   const int64_t total = (int64_t)N * H * W * (C / 8);
   MMR_REQUIRE(total < ((int64_t)1 << 31), "max-pool backward: tensor too large for 32-bit indexing");
-  maxpool2_bwd_kernel<<<ew_blocks(total, 64), kEwThreads, 0, as_stream(stream)>>>(
-      cl, idx, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
+  mmr_launch((maxpool2_bwd_kernel), ew_blocks(total, 64), kEwThreads, 0, as_stream(stream), cl, idx, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1381,11 +1385,10 @@ extern "C" int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int
   if (dbias && g_head_ws == nullptr) {
     MMR_CUDA_CHECK(cudaMalloc(&g_head_ws, sizeof(double) * 16 * kHeadBlocks));
   }
-  head_grad_prep_kernel<<<kHeadBlocks, kEwThreads, 0, as_stream(stream)>>>(
-      dlogits, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), cpad, dbias ? g_head_ws : nullptr);
+  mmr_launch((head_grad_prep_kernel), kHeadBlocks, kEwThreads, 0, as_stream(stream), dlogits, N, C, H, W, reinterpret_cast<__nv_bfloat16*>(out), cpad, dbias ? g_head_ws : nullptr);
   MMR_CUDA_CHECK(cudaGetLastError());
   if (dbias) {
-    head_bias_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(g_head_ws, kHeadBlocks, C, dbias,
+    mmr_launch((head_bias_finalize_kernel), 1, 256, 0, as_stream(stream), g_head_ws, kHeadBlocks, C, dbias,
                                                                accumulate);
     MMR_CUDA_CHECK(cudaGetLastError());
   }
@@ -1396,8 +1399,7 @@ extern "C" int mmr_upsample_bilinear2x_fwd(const void* x, int N, int H, int W, i
                                            mmr_stream_t stream) {
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   const int64_t total = (int64_t)N * 4 * H * W * (C / 8);
-  upsample_bilinear2x_fwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+  mmr_launch((upsample_bilinear2x_fwd_kernel), ew_blocks(total, 16), kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1408,8 +1410,7 @@ extern "C" int mmr_upsample_bilinear2x_bwd(const MmrContrib* contribs, int ncont
   ContribList cl;
   if (fill_contribs(cl, contribs, ncontrib)) return -1;
   const int64_t total = (int64_t)N * H * W * (C / 8);
-  upsample_bilinear2x_bwd_kernel<<<ew_blocks(total, 16), kEwThreads, 0, as_stream(stream)>>>(
-      cl, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
+  mmr_launch((upsample_bilinear2x_bwd_kernel), ew_blocks(total, 16), kEwThreads, 0, as_stream(stream), cl, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1417,8 +1418,7 @@ extern "C" int mmr_upsample_bilinear2x_bwd(const MmrContrib* contribs, int ncont
 extern "C" int mmr_upsample_nearest_f32_nchw(const float* in, int64_t planes, int h, int w, int f, float* out,
                                              mmr_stream_t stream) {
   MMR_REQUIRE(f >= 1 && f <= 32, "factor must be 1..32");
-  upsample_nearest_f32_kernel<<<ew_blocks(planes * h * w * f * f, 16), kEwThreads, 0, as_stream(stream)>>>(
-      in, planes, h, w, f, out);
+  mmr_launch((upsample_nearest_f32_kernel), ew_blocks(planes * h * w * f * f, 16), kEwThreads, 0, as_stream(stream), in, planes, h, w, f, out);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1426,7 +1426,7 @@ extern "C" int mmr_upsample_nearest_f32_nchw(const float* in, int64_t planes, in
 extern "C" int mmr_sumpool_f32_nchw(const float* in, int64_t planes, int h, int w, int f, float* out,
                                     mmr_stream_t stream) {
   MMR_REQUIRE(f >= 1 && f <= 32, "factor must be 1..32");
-  sumpool_f32_kernel<<<ew_blocks(planes * h * w, 16), kEwThreads, 0, as_stream(stream)>>>(in, planes, h, w, f,
+  mmr_launch((sumpool_f32_kernel), ew_blocks(planes * h * w, 16), kEwThreads, 0, as_stream(stream), in, planes, h, w, f,
                                                                                          out);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;

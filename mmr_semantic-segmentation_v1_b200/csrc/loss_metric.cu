@@ -35,6 +35,7 @@ template <int CP>
 __global__ void __launch_bounds__(kLossThreads)
 dice_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int C,
                    int64_t HW, MmrLossParams prm, double* __restrict__ ws, int nblk) {
+  pdl_prologue();
   const int n = blockIdx.y;
   const float* lg = logits + (size_t)n * C * HW;
   const int64_t* lb = labels + (size_t)n * HW;
@@ -101,6 +102,7 @@ dice_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__
 
 __global__ void dice_ce_finalize_kernel(double* __restrict__ ws, int N, int C, int nblk,
                                         MmrLossParams prm, float* __restrict__ out) {
+  pdl_prologue();
   // single block; thread per (n,c)
   double* red = ws;
   double* tail = red + (size_t)N * C * 3;
@@ -162,6 +164,7 @@ dice_ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__
                    int64_t HW, MmrLossParams prm, const double* __restrict__ ws,
                    float grad_scale, const float* __restrict__ grad_scale_dev,
                    float* __restrict__ dlogits) {
+  pdl_prologue();
   if (grad_scale_dev) grad_scale *= __ldg(grad_scale_dev);
   const int n = blockIdx.y;
   const double* red = ws;
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(kLossThreads)
 confusion_logits_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int C,
                         int64_t HW, unsigned long long* __restrict__ cm,
                         int64_t* __restrict__ pred_out) {
+  pdl_prologue();
   __shared__ unsigned int hist[kMaxClasses * kMaxClasses];
   for (int k = threadIdx.x; k < C * C; k += blockDim.x) hist[k] = 0u;
   __syncthreads();
@@ -265,6 +269,7 @@ confusion_logits_kernel(const float* __restrict__ logits, const int64_t* __restr
 template <typename T>
 __global__ void __launch_bounds__(kLossThreads)
 onehot_to_labels_kernel(const T* __restrict__ oh, int C, int64_t HW, int64_t* __restrict__ labels) {
+  pdl_prologue();
   const int n = blockIdx.y;
   const T* src = oh + (size_t)n * C * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(kLossThreads)
 confusion_preds_kernel(const int64_t* __restrict__ preds, const int64_t* __restrict__ labels, int C,
                        int64_t HW, int64_t ignore_index, int overflow,
                        unsigned long long* __restrict__ cm) {
+  pdl_prologue();
   __shared__ unsigned int hist[(kMaxClasses + 1) * (kMaxClasses + 1)];
   const int Cb = C + (overflow ? 1 : 0);
   for (int k = threadIdx.x; k < Cb * Cb; k += blockDim.x) hist[k] = 0u;
@@ -342,10 +348,9 @@ extern "C" int mmr_dice_ce_fwd(const float* logits, const int64_t* labels, int N
   MMR_REQUIRE(N * C <= 65536, "N*C too large for the finalize kernel");
   const int64_t HW = (int64_t)H * W;
   dim3 grid(nblk, N);
-  DISPATCH_CP(C, (dice_ce_fwd_kernel<CP><<<grid, kLossThreads, 0, as_stream(stream)>>>(
-                     logits, labels, C, HW, *p, workspace, nblk)));
+  DISPATCH_CP(C, (mmr_launch((dice_ce_fwd_kernel<CP>), grid, kLossThreads, 0, as_stream(stream), logits, labels, C, HW, *p, workspace, nblk)));
   MMR_CUDA_CHECK(cudaGetLastError());
-  dice_ce_finalize_kernel<<<1, kLossThreads, 0, as_stream(stream)>>>(workspace, N, C, nblk, *p, out);
+  mmr_launch((dice_ce_finalize_kernel), 1, kLossThreads, 0, as_stream(stream), workspace, N, C, nblk, *p, out);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -356,8 +361,7 @@ extern "C" int mmr_dice_ce_bwd(const float* logits, const int64_t* labels, int N
   MMR_REQUIRE(C >= 1 && C <= kMaxClasses, "classes must be in [1,%d], got %d", kMaxClasses, C);
   const int64_t HW = (int64_t)H * W;
   dim3 grid(blocks_per_image(HW, N), N);
-  DISPATCH_CP(C, (dice_ce_bwd_kernel<CP><<<grid, kLossThreads, 0, as_stream(stream)>>>(
-                     logits, labels, N, C, HW, *p, workspace, grad_scale, grad_scale_dev, dlogits)));
+  DISPATCH_CP(C, (mmr_launch((dice_ce_bwd_kernel<CP>), grid, kLossThreads, 0, as_stream(stream), logits, labels, N, C, HW, *p, workspace, grad_scale, grad_scale_dev, dlogits)));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -369,8 +373,7 @@ extern "C" int mmr_confusion_from_logits(const float* logits, const int64_t* lab
   MMR_REQUIRE(cm == nullptr || labels != nullptr, "confusion matrix requested without labels");
   const int64_t HW = (int64_t)H * W;
   dim3 grid(blocks_per_image(HW, N), N);
-  DISPATCH_CP(C, (confusion_logits_kernel<CP><<<grid, kLossThreads, 0, as_stream(stream)>>>(
-                     logits, labels, C, HW, reinterpret_cast<unsigned long long*>(cm), pred_out)));
+  DISPATCH_CP(C, (mmr_launch((confusion_logits_kernel<CP>), grid, kLossThreads, 0, as_stream(stream), logits, labels, C, HW, reinterpret_cast<unsigned long long*>(cm), pred_out)));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -380,11 +383,9 @@ extern "C" int mmr_onehot_to_labels(const void* onehot, int is_float, int N, int
   const int64_t HW = (int64_t)H * W;
   dim3 grid(blocks_per_image(HW, N), N);
   if (is_float)
-    onehot_to_labels_kernel<float><<<grid, kLossThreads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float*>(onehot), C, HW, labels);
+    mmr_launch((onehot_to_labels_kernel<float>), grid, kLossThreads, 0, as_stream(stream), reinterpret_cast<const float*>(onehot), C, HW, labels);
   else
-    onehot_to_labels_kernel<int64_t><<<grid, kLossThreads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const int64_t*>(onehot), C, HW, labels);
+    mmr_launch((onehot_to_labels_kernel<int64_t>), grid, kLossThreads, 0, as_stream(stream), reinterpret_cast<const int64_t*>(onehot), C, HW, labels);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -394,8 +395,7 @@ extern "C" int mmr_confusion_from_preds(const int64_t* preds, const int64_t* lab
                                         int64_t* cm, mmr_stream_t stream) {
   MMR_REQUIRE(C >= 1 && C <= kMaxClasses, "classes must be in [1,%d], got %d", kMaxClasses, C);
   dim3 grid(blocks_per_image(npix, N), N);
-  confusion_preds_kernel<<<grid, kLossThreads, 0, as_stream(stream)>>>(
-      preds, labels, C, npix, ignore_index, overflow_bin, reinterpret_cast<unsigned long long*>(cm));
+  mmr_launch((confusion_preds_kernel), grid, kLossThreads, 0, as_stream(stream), preds, labels, C, npix, ignore_index, overflow_bin, reinterpret_cast<unsigned long long*>(cm));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

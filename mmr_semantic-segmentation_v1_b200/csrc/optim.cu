@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(kOptThreads)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
             float bc1, float bc2, int mode, float grad_scale) {
+  pdl_prologue();
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const int64_t n4 = n / 4;
@@ -64,6 +65,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 __global__ void __launch_bounds__(kOptThreads)
 sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  pdl_prologue();
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -94,7 +96,7 @@ extern "C" int mmr_adam_step(float* p, const float* g, float* m, float* v, int64
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  adam_kernel<<<(int)blocks, kOptThreads, 0, as_stream(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, wd,
+  mmr_launch((adam_kernel), (int)blocks, kOptThreads, 0, as_stream(stream), p, g, m, v, n, lr, b1, b2, eps, wd,
                                                                   bc1, bc2, mode, grad_scale);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -111,7 +113,7 @@ extern "C" int mmr_sumsq(const float* g, int64_t n, double* out, mmr_stream_t st
   const int64_t cap = (int64_t)num_sms() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(int)blocks, kOptThreads, 0, as_stream(stream)>>>(g, n, out);
+  mmr_launch((sumsq_kernel), (int)blocks, kOptThreads, 0, as_stream(stream), g, n, out);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -24,6 +24,7 @@ struct WindowGrid {
 template <typename TIn>
 __global__ void window_gather_kernel(const TIn* __restrict__ frames, int N, int H, int W, WindowGrid g, int rh,
                                      int rw, int w_begin, int w_count, TIn* __restrict__ out) {
+  pdl_prologue();
   // fp32: NCHW in, NCHW out.  uint8: NHWC in, NHWC out.
   const int wpf = g.ny * g.nx;
   const int64_t per = (int64_t)3 * rh * rw;
@@ -51,6 +52,7 @@ __global__ void window_gather_kernel(const TIn* __restrict__ frames, int N, int 
 
 __global__ void window_blend_kernel(const float* __restrict__ win, int N, int C, int H, int W, WindowGrid g, int rh,
                                     int rw, float* __restrict__ out, int64_t* __restrict__ pred) {
+  pdl_prologue();
   const int wpf = g.ny * g.nx;
   const int64_t hw = (int64_t)H * W;
   const int64_t total = (int64_t)N * hw;
@@ -129,11 +131,9 @@ extern "C" int mmr_window_gather(const void* frames, int is_u8, int N, int H, in
   if (fill_grid(g, ys, ny, xs, nx, H, W, rh, rw)) return -1;
   const int64_t total = (int64_t)3 * rh * rw * w_count;
   if (is_u8)
-    window_gather_kernel<uint8_t><<<sw_blocks(total), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const uint8_t*>(frames), N, H, W, g, rh, rw, w_begin, w_count, reinterpret_cast<uint8_t*>(out));
+    mmr_launch((window_gather_kernel<uint8_t>), sw_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const uint8_t*>(frames), N, H, W, g, rh, rw, w_begin, w_count, reinterpret_cast<uint8_t*>(out));
   else
-    window_gather_kernel<float><<<sw_blocks(total), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float*>(frames), N, H, W, g, rh, rw, w_begin, w_count, reinterpret_cast<float*>(out));
+    mmr_launch((window_gather_kernel<float>), sw_blocks(total), 256, 0, as_stream(stream), reinterpret_cast<const float*>(frames), N, H, W, g, rh, rw, w_begin, w_count, reinterpret_cast<float*>(out));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -144,7 +144,7 @@ extern "C" int mmr_window_blend(const float* win_logits, int N, int C, int H, in
   MMR_REQUIRE(win_logits && (out || pred) && ys && xs && C >= 1, "bad argument");
   WindowGrid g;
   if (fill_grid(g, ys, ny, xs, nx, H, W, rh, rw)) return -1;
-  window_blend_kernel<<<sw_blocks((int64_t)N * H * W), 256, 0, as_stream(stream)>>>(win_logits, N, C, H, W, g, rh, rw,
+  mmr_launch((window_blend_kernel), sw_blocks((int64_t)N * H * W), 256, 0, as_stream(stream), win_logits, N, C, H, W, g, rh, rw,
                                                                                     out, pred);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
