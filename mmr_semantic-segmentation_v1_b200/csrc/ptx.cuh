@@ -36,7 +36,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
+#ifdef MMR_MBAR_SPIN
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
