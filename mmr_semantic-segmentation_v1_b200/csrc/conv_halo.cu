@@ -481,6 +481,45 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
   }
 }
 
+// Epilogue of the segmentation head: up to 16 classes, bias only, fp32 NCHW logits (what `model(img)`
+// returns).  One TMEM round trip per M tile, the bias in registers, one predicated store per class: a
+// warp's 32 pixels are 4 image rows x 8 consecutive pixels, i.e. four full 32-byte sectors per class plane.
+__device__ __forceinline__ void epi_head_f32(const HaloParams& p, uint32_t tmem_base, uint64_t* tmem_full,
+                                             uint64_t* tmem_empty, int q, int lane) {
+  const int m = q * 32 + lane;
+  const int h = m >> 3, w = m & 7;
+  const size_t hw = (size_t)p.H * p.W;
+  float bias[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) bias[j] = (p.bias && j < p.cout_total) ? __ldg(p.bias + j) : 0.f;
+  int it = 0;
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+    const ItemCoord ic = decode_item(p, item);
+    const int buf = it % p.acc_bufs;
+    const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
+    mbar_wait(&tmem_full[buf], par);
+    tc_fence_after();
+    const int y = ic.y0 + h;
+    for (int i = 0; i < p.TX; ++i) {
+      const int x = ic.x0 + 8 * i + w;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.TX + i) * p.bn), r);
+      tmem_ld_wait();
+      if (i == p.TX - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      }
+      if (y < p.H && x < p.W && !(p.dbg & 2)) {
+        float* dst = p.out_f32 + (size_t)ic.n * p.out_ldc * hw + (size_t)y * p.W + x;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < p.cout_total) dst[(size_t)j * hw] = __uint_as_float(r[j]) + bias[j];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloParams p) {
   pdl_prologue();
@@ -622,7 +661,11 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
     const bool plain = !p.scale && !p.bias && !p.residual && !p.relu;
     const bool fast = p.out_mode == MMR_OUT_BF16_NHWC && (p.direct != 0) == (p.sg < 64) &&
                       (p.stats == nullptr || (p.n_ntiles == 1 && p.gpn == 1 && plain));
-    if (fast) {
+    const bool head = p.out_mode == MMR_OUT_F32_NCHW && p.bn == 16 && p.n_ntiles == 1 && p.R == 1 && !p.scale &&
+                      !p.residual && !p.relu;
+    if (head) {
+      epi_head_f32(p, tmem_base, tmem_full, tmem_empty, q, lane);
+    } else if (fast) {
 #define MMR_EPI_CASE2(SG_, ST_, PL_)                                                                   \
   if (p.sg == SG_ && (p.stats != nullptr) == ST_ && plain == PL_)                                      \
     epi_fast<SG_, ST_, PL_>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane);

@@ -29,6 +29,7 @@ LAYERS = [
     ("x_0_3.conv2", 256, [(32, 1)], 32),
     ("x_0_4.conv1", 512, [(32, 2)], 16),
     ("x_0_4.conv2", 512, [(16, 1)], 16),
+    ("head10", 512, [(16, 1)], 10),      # segmentation head: fp32 NCHW logits (fprop only)
 ]
 
 
@@ -62,12 +63,18 @@ def main():
         w = torch.randn((cout, cin, 3, 3), generator=gen, device="cuda") / (9 * cin) ** 0.5
         out = torch.empty((N, hw, hw, cout), device="cuda", dtype=torch.bfloat16)
         for kind in kinds:
+            if name.startswith("head") and kind != "fprop":
+                continue
             try:
                 if kind == "wgrad":
                     cz = -(-cout // 16) * 16
                     dz = torch.randn((N, hw, hw, cz), generator=gen, device="cuda").to(torch.bfloat16)
                     dst = torch.empty((cout, cin, 3, 3), device="cuda")
                     plan = convplan.build_wgrad_halo(dz, sources, dst, force=force)
+                elif kind == "fprop" and name.startswith("head"):
+                    logits = torch.empty((N, cout, hw, hw), device="cuda")
+                    plan = convplan.build_fprop_halo(sources, w, None, bias=torch.zeros(cout, device="cuda"),
+                                                     out_f32=logits, force=force)
                 elif kind == "fprop":
                     stats = None
                     if os.environ.get("STATS"):   # BatchNorm batch statistics in the epilogue, as the training step runs it
