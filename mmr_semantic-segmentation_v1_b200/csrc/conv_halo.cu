@@ -248,8 +248,6 @@ __device__ __forceinline__ void mma_warp_loop_r(const HaloParams& p, uint32_t tm
         if (!(p.dbg & 1) && elect_one()) {
 #pragma unroll
           for (int ty = -1; ty <= R; ++ty) {
-            constexpr int kDummy = 0;
-            (void)kDummy;
             const int r_lo = ty - 1 < 0 ? 0 : ty - 1;
             const int r_hi = ty + 1 > R - 1 ? R - 1 : ty + 1;
             const int nph = r_hi - r_lo + 1;
