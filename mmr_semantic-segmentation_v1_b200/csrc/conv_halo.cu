@@ -908,32 +908,55 @@ __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int O, int
   }
 }
 
-// Every layer's packing in one launch: blockIdx.y selects the job.
-__global__ void pack_weights_halo_batch_kernel(const MmrPackJob* __restrict__ jobs) {
+// Every layer's packing in one launch.  A block owns kPackPerBlock consecutive (N tile, chunk, row, k) items
+// of one job and finds its job by walking the job sizes (staged in shared memory); a thread reads the nine
+// contiguous taps of its (output channel, input channel) pair once and writes them to the nine tap planes,
+// so consecutive lanes (consecutive k) read one contiguous stretch of the fp32 master in the fprop layout.
+constexpr int kPackPerBlock = 256 * 4;
+constexpr int kMaxPackJobs = 512;
+__device__ __forceinline__ int64_t pack_items(const MmrPackJob& j) {
+  return (int64_t)j.n_ntiles * j.nchunks * j.bn * j.cb;
+}
+__global__ void __launch_bounds__(256)
+pack_weights_halo_batch_kernel(const MmrPackJob* __restrict__ jobs, int njobs) {
   pdl_prologue();
-  const MmrPackJob j = jobs[blockIdx.y];
+  __shared__ int64_t totals[kMaxPackJobs];
+  for (int i = threadIdx.x; i < njobs; i += blockDim.x) totals[i] = pack_items(jobs[i]);
+  __syncthreads();
+  int64_t b = blockIdx.x, total = 0;
+  int ji = 0;
+  for (; ji < njobs; ++ji) {
+    total = totals[ji];
+    const int64_t nb = (total + kPackPerBlock - 1) / kPackPerBlock;
+    if (b < nb) break;
+    b -= nb;
+  }
+  if (ji == njobs) return;
+  const MmrPackJob j = jobs[ji];
   const float* __restrict__ w = j.w_oihw;
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(j.out);
-  const int64_t total = (int64_t)j.n_ntiles * j.nchunks * 9 * j.bn * j.cb;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t t = idx;
-    const int k = (int)(t % j.cb);
-    t /= j.cb;
-    const int r = (int)(t % j.bn);
-    t /= j.bn;
-    const int tap = pack_tap((int)(t % 9), j.layout);
-    t /= 9;
-    const int c = (int)(t % j.nchunks);
-    const int nt = (int)(t / j.nchunks);
-    const int nidx = nt * j.bn + r, kidx = c * j.cb + k;
-    float v = 0.f;
-    if (j.mode == 0) {
-      if (nidx < j.O && kidx < j.I) v = w[((size_t)nidx * j.I + kidx) * 9 + tap];
-    } else {
-      if (kidx < j.O && nidx < j.I) v = w[((size_t)kidx * j.I + nidx) * 9 + (8 - tap)];
+  const uint32_t cb = (uint32_t)j.cb, bn = (uint32_t)j.bn, nch = (uint32_t)j.nchunks;
+  const int64_t end = min(total, (b + 1) * kPackPerBlock);
+  for (int64_t idx = b * kPackPerBlock + threadIdx.x; idx < end; idx += 256) {
+    uint32_t t = (uint32_t)idx;
+    const uint32_t k = t % cb;
+    t /= cb;
+    const uint32_t r = t % bn;
+    t /= bn;
+    const uint32_t c = t % nch, nt = t / nch;
+    const int nidx = (int)(nt * bn + r), kidx = (int)(c * cb + k);
+    float v[9];
+    const bool live = j.mode == 0 ? (nidx < j.O && kidx < j.I) : (kidx < j.O && nidx < j.I);
+    const float* src = j.mode == 0 ? w + ((size_t)nidx * j.I + kidx) * 9 : w + ((size_t)kidx * j.I + nidx) * 9;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) v[q] = live ? __ldg(src + q) : 0.f;
+    // out[((nt*nchunks + c)*9 + slot)*bn + r][k], slot -> filter tap by layout, mirrored for dgrad
+    __nv_bfloat16* dst = out + ((size_t)(nt * nch + c) * 9 * bn + r) * cb + k;
+#pragma unroll
+    for (int slot = 0; slot < 9; ++slot) {
+      const int tap = pack_tap(slot, j.layout);
+      dst[(size_t)slot * bn * cb] = __float2bfloat16(v[j.mode == 0 ? tap : 8 - tap]);
     }
-    out[idx] = __float2bfloat16(v);
   }
 }
 
@@ -1201,10 +1224,11 @@ extern "C" int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode
   return 0;
 }
 
-extern "C" int mmr_pack_weights_halo_batch(const MmrPackJob* jobs_dev, int njobs, mmr_stream_t stream) {
-  MMR_REQUIRE(jobs_dev && njobs > 0, "bad argument");
-  dim3 grid(64, njobs);
-  mmr_launch((pack_weights_halo_batch_kernel), grid, 256, 0, as_stream(stream), jobs_dev);
+extern "C" int mmr_pack_weights_halo_batch(const MmrPackJob* jobs_dev, int njobs, int64_t total_blocks,
+                                           mmr_stream_t stream) {
+  MMR_REQUIRE(jobs_dev && njobs > 0 && njobs <= kMaxPackJobs && total_blocks > 0 && total_blocks < ((int64_t)1 << 31),
+              "bad argument (at most %d jobs)", kMaxPackJobs);
+  mmr_launch((pack_weights_halo_batch_kernel), (unsigned)total_blocks, 256, 0, as_stream(stream), jobs_dev, njobs);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -229,35 +229,6 @@ __device__ __forceinline__ void row_to_nyx(const RowGeom& g, uint32_t r, int& n,
   }
 }
 
-template <bool POOLED>
-__device__ __forceinline__ void gather_row(const ContribList& cl, const RowGeom& geo, uint32_t r, int c, int C,
-                                           float (&g)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) g[j] = 0.f;
-  int n = 0, y = 0, x = 0;
-  if (POOLED) row_to_nyx(geo, r, n, y, x);
-  for (int i = 0; i < cl.n; ++i) {
-    float v[8];
-    if (!POOLED || !cl.pool2[i]) {
-      load8(cl.ptr[i] + (size_t)r * C + c, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] += v[j];
-    } else {
-      const int W2 = 2 * geo.W;
-      const __nv_bfloat16* base = cl.ptr[i] + (((size_t)n * (2 * geo.H) + 2 * y) * W2 + 2 * x) * C + c;
-      float v1[8], v2[8], v3[8];
-      load8(base, v);
-      load8(base + C, v1);
-      load8(base + (size_t)W2 * C, v2);
-      load8(base + (size_t)W2 * C + C, v3);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] += (v[j] + v1[j]) + (v2[j] + v3[j]);
-    }
-  }
-}
-
-// All loads of a row are issued before the first use: the contribution count NC is a template
-// parameter (1..4; 0 = any count, serial gather), so the gather unrolls into independent loads.
 __device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void add8(const uint4& u, float (&g)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -274,6 +245,44 @@ __device__ __forceinline__ void cvt8(const uint4& u, float (&g)[8]) {
   add8(u, g);
 }
 
+// Any number of contributions (the NC = 0 instantiations: more than four consumers, e.g. the encoder
+// features every decoder column reads).  All same-resolution loads of the row are issued first (up to
+// eight 16-byte loads in flight), then each 2x2-pooled contribution issues its four loads together.
+template <bool POOLED>
+__device__ __forceinline__ void gather_row(const ContribList& cl, const RowGeom& geo, uint32_t r, int c, int C,
+                                           float (&g)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  uint4 raw[kMaxContrib];
+#pragma unroll
+  for (int i = 0; i < kMaxContrib; ++i)
+    if (i < cl.n && !(POOLED && cl.pool2[i])) raw[i] = ldg16(cl.ptr[i] + (size_t)r * C + c);
+  if (POOLED) {
+    int n = 0, y = 0, x = 0;
+    row_to_nyx(geo, r, n, y, x);
+    const int W2 = 2 * geo.W;
+    for (int i = 0; i < cl.n; ++i) {
+      if (!cl.pool2[i]) continue;
+      const __nv_bfloat16* base = cl.ptr[i] + (((size_t)n * (2 * geo.H) + 2 * y) * W2 + 2 * x) * C + c;
+      const uint4 v0 = ldg16(base), v1 = ldg16(base + C), v2 = ldg16(base + (size_t)W2 * C),
+                  v3 = ldg16(base + (size_t)W2 * C + C);
+      float t[8];
+      cvt8(v0, t);
+      add8(v1, t);
+      float u[8];
+      cvt8(v2, u);
+      add8(v3, u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += t[j] + u[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxContrib; ++i)
+    if (i < cl.n && !(POOLED && cl.pool2[i])) add8(raw[i], g);
+}
+
+// All loads of a row are issued before the first use: the contribution count NC is a template
+// parameter (1..4; 0 = any count, serial gather), so the gather unrolls into independent loads.
 template <int NC, bool POOLED>
 struct RowRaw {
   uint4 v[NC > 0 ? NC : 1][POOLED ? 4 : 1];

@@ -230,8 +230,10 @@ class Engine:
             arr = (_lib.MmrPackJob * len(self.pack_jobs))(*self.pack_jobs)
             raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
             self.pack_jobs_dev = raw.to(self.dev)
+            blocks = sum(-(-(j.n_ntiles * j.nchunks * j.bn * j.cb) // 1024) for j in self.pack_jobs)
             self.repack_calls.append((self.lib.mmr_pack_weights_halo_batch,
-                                      (C.c_void_p(self.pack_jobs_dev.data_ptr()), len(self.pack_jobs))))
+                                      (C.c_void_p(self.pack_jobs_dev.data_ptr()), len(self.pack_jobs),
+                                       C.c_int64(blocks))))
         if self.halo_stats_used:
             # one memset per forward re-arms every statistics slot the conv epilogues accumulate into
             fc.insert(0, (self.lib.mmr_zero_async, (C.c_void_p(self.halo_stats.data_ptr()),
