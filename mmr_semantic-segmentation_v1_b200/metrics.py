@@ -125,6 +125,19 @@ def dice(im1, im2, empty_score=1.0):
     return 2.0 * int(cm[1, 1]) / im_sum
 
 
+def dice_per_image(preds, labels, num_classes, empty_score=1.0):
+    """The reference's per-image Dice of the validation loop (SU/ModelTraining.py:625-634, 765-774):
+    `dice(one_hot(seg_im), one_hot(label_im))` for every image of the batch, i.e. 2 |A and B| / (|A| + |B|) over
+    the C x H x W one-hot volumes, without the per-image `.cpu()` round trips: one confusion-matrix launch
+    for the whole batch, |A and B| = trace(cm[n]), |A| + |B| = row sums + column sums of cm[n].
+    preds / labels: int64 [N, H, W] on the device; returns float64 [N] on the device."""
+    cm = confusion_matrix_from_preds(preds, labels, num_classes).double()
+    inter = torch.diagonal(cm, dim1=1, dim2=2).sum(1)
+    total = cm.sum((1, 2)) * 2.0            # every counted pixel is one element of A and one of B
+    out = 2.0 * inter / total.clamp_min(1.0)
+    return torch.where(total > 0, out, torch.full_like(out, float(empty_score)))
+
+
 def get_stats(output, target, mode="multiclass", ignore_index=None, threshold=None, num_classes=None):
     """smp.metrics.get_stats for mode='multiclass': (tp, fp, fn, tn), each int64 [N, C]."""
     if mode != "multiclass":

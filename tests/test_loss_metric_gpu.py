@@ -191,3 +191,22 @@ def test_adam_matches_torch():
         got = torch.cat([p.data for p in p2])
         want = torch.cat([p.data for p in p1])
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-7)
+
+
+def test_dice_per_image_matches_reference_dice_on_one_hots():
+    """metrics.dice_per_image against oracle.metrics.dice (pinned to the reference's utils.dice by
+    tests/golden/metrics_reference.npz) applied to the one-hot volumes, as SU/ModelTraining.py:629-634 does."""
+    import numpy as np
+    from oracle import metrics as OM
+    from mmrseg_b200.metrics import dice_per_image
+    g = torch.Generator().manual_seed(12)
+    n, c, h, w = 3, 5, 20, 28
+    pred = torch.randint(0, c, (n, h, w), generator=g)
+    gt = torch.randint(0, c, (n, h, w), generator=g)
+    gt[2] = pred[2]                                   # a perfect image
+    got = dice_per_image(pred.cuda(), gt.cuda(), c).cpu().numpy()
+    for i in range(n):
+        a = torch.nn.functional.one_hot(pred[i], c).permute(2, 0, 1).numpy()
+        b = torch.nn.functional.one_hot(gt[i], c).permute(2, 0, 1).numpy()
+        assert abs(got[i] - OM.dice(a, b)) <= 1e-12, i
+    assert got[2] == 1.0
