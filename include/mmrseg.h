@@ -465,6 +465,11 @@ int mmr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
 /* cudaMemsetAsync(ptr, 0, nbytes) on the stream: re-arms accumulated buffers (statistics slots of
  * mmr_halo_conv_plan_*, split-K partials) inside a replayed launch list. */
 int mmr_zero_async(void* ptr, int64_t nbytes, mmr_stream_t stream);
+/* torch.optim.SGD(lr, momentum, weight_decay) with dampening 0, no Nesterov (SU/ModelTraining.py:372,381):
+ * g' = g*grad_scale + wd*p; buf = first_step ? g' : momentum*buf + g'; p -= lr*buf.  momentum_buf may be NULL
+ * when momentum == 0. */
+int mmr_sgd_step(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum, float wd,
+                 int first_step, float grad_scale, mmr_stream_t stream);
 /* sum of squares of g (double out[0] accumulated) for clip_grad_norm_. */
 int mmr_sumsq(const float* g, int64_t n, double* out, mmr_stream_t stream);
 

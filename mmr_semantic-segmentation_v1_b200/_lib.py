@@ -196,6 +196,7 @@ SIGNATURES = {
     "mmr_onehot_to_labels": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "mmr_zero_async": (_i, [_vp, _i64, _vp]),
+    "mmr_sgd_step": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _f, _vp]),
     "mmr_sumsq": (_i, [_vp, _i64, _vp, _vp]),
 }
 

@@ -63,6 +63,24 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+// torch.optim.SGD(momentum, weight_decay) (SU/ModelTraining.py:372, 381), dampening 0, no Nesterov:
+//   g = g*grad_scale + wd*p;  buf = first ? g : momentum*buf + g;  p -= lr*buf   (20 B/param)
+__global__ void __launch_bounds__(kOptThreads)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n, float lr,
+           float momentum, float wd, int first, float grad_scale) {
+  pdl_prologue();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gr = g[i] * grad_scale + wd * pv;
+    float b = gr;
+    if (momentum != 0.f) {
+      b = first ? gr : momentum * buf[i] + gr;
+      buf[i] = b;
+    }
+    p[i] = pv - lr * b;
+  }
+}
+
 __global__ void __launch_bounds__(kOptThreads)
 sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
   pdl_prologue();
@@ -105,6 +123,19 @@ extern "C" int mmr_adam_step(float* p, const float* g, float* m, float* v, int64
 extern "C" int mmr_zero_async(void* ptr, int64_t nbytes, mmr_stream_t stream) {
   MMR_REQUIRE(ptr != nullptr && nbytes >= 0, "bad argument");
   MMR_CUDA_CHECK(cudaMemsetAsync(ptr, 0, (size_t)nbytes, as_stream(stream)));
+  return 0;
+}
+
+extern "C" int mmr_sgd_step(float* p, const float* g, float* momentum_buf, int64_t n, float lr, float momentum,
+                            float wd, int first_step, float grad_scale, mmr_stream_t stream) {
+  MMR_REQUIRE(p && g && n >= 0 && (momentum == 0.f || momentum_buf), "bad argument");
+  if (n == 0) return 0;
+  int64_t blocks = (n + kOptThreads - 1) / kOptThreads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  mmr_launch((sgd_kernel), (int)blocks, kOptThreads, 0, as_stream(stream), p, g, momentum_buf, n, lr, momentum, wd,
+             first_step, grad_scale);
+  MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 

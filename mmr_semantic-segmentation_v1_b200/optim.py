@@ -1,5 +1,6 @@
 """Optimiser seam: torch.optim.Adam(lr, weight_decay) (SU/ModelTraining.py:366), AdamW
-(:369, ED/Main_MMR_SegModel.py:878-880), clip_grad_norm_ (ED/...:718-727) on the flat fp32
+(:369, ED/Main_MMR_SegModel.py:878-880), SGD(momentum=0.9) (SU/ModelTraining.py:372,381),
+clip_grad_norm_ (ED/...:718-727) on the flat fp32
 parameter / gradient buffers of a plan model: one HBM-bound launch (28 B per parameter)."""
 import ctypes as C
 import math
@@ -53,6 +54,50 @@ class FusedAdam(torch.optim.Optimizer):
                                              pt.numel(), group["lr"], b1, b2, group["eps"],
                                              group["weight_decay"], bc1, bc2,
                                              1 if group["decoupled"] else 0, self.grad_scale, _stream()))
+        return loss
+
+
+def _flat_view(tensors):
+    """One fp32 tensor spanning the common storage of `tensors` (views of one buffer), else None."""
+    st = tensors[0].untyped_storage()
+    if any(t.untyped_storage().data_ptr() != st.data_ptr() for t in tensors):
+        return None
+    return torch.empty(0, dtype=torch.float32, device=tensors[0].device).set_(st)
+
+
+class FusedSGD(torch.optim.Optimizer):
+    """torch.optim.SGD(lr, momentum, weight_decay) (dampening 0, no Nesterov), the reference's
+    `optim.SGD(model.parameters(), lr=args.lr, momentum=0.9)`; per-group learning rates (the differential
+    encoder / decoder rates of SU/ModelTraining.py:375-383) run one launch per parameter tensor."""
+
+    def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        self.grad_scale = 1.0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        lib = _lib.lib()
+        for group in self.param_groups:
+            params = [p for p in group["params"] if p.grad is not None]
+            if not params:
+                continue
+            st = self.state.setdefault("group%d" % id(group), {})
+            flat = _flat_view([p.data for p in params]) if len(self.param_groups) == 1 else None
+            gflat = _flat_view([p.grad for p in params]) if flat is not None else None
+            if flat is not None and gflat is not None and flat.numel() == gflat.numel() and \
+                    len(params) == len(group["params"]):
+                jobs = [("flat", flat, gflat)]
+            else:
+                jobs = [(id(p), p.data, p.grad) for p in params]
+            for key, pt, gt in jobs:
+                first = key not in st
+                if first:
+                    st[key] = torch.zeros_like(pt) if group["momentum"] != 0 else None
+                buf = st[key]
+                _lib.check(lib.mmr_sgd_step(pt.data_ptr(), gt.data_ptr(), buf.data_ptr() if buf is not None else None,
+                                            pt.numel(), group["lr"], group["momentum"], group["weight_decay"],
+                                            int(first), self.grad_scale, _stream()))
         return loss
 
 

@@ -193,6 +193,36 @@ def test_adam_matches_torch():
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-7)
 
 
+def test_sgd_matches_torch():
+    """FusedSGD against torch.optim.SGD (the reference's optim.SGD(..., momentum=0.9), SU/ModelTraining.py:372,381):
+    one flat launch, per-group learning rates, with and without momentum / weight decay."""
+    from mmrseg_b200.optim import FusedSGD
+    g = torch.Generator().manual_seed(13)
+    for momentum, wd, groups in ((0.9, 0.0, False), (0.9, 1e-2, True), (0.0, 1e-3, False)):
+        flat = torch.randn(10007, generator=g).cuda()
+        p1 = [torch.nn.Parameter(flat[:5000].clone()), torch.nn.Parameter(flat[5000:].clone())]
+        holder = flat.clone()
+        p2 = [torch.nn.Parameter(holder[:5000]), torch.nn.Parameter(holder[5000:])]
+        if groups:   # differential learning rates (SU/ModelTraining.py:375-383)
+            ref = torch.optim.SGD([{"params": [p1[0]], "lr": 1e-2}, {"params": [p1[1]]}], lr=1e-3, momentum=momentum,
+                                  weight_decay=wd)
+            opt = FusedSGD([{"params": [p2[0]], "lr": 1e-2}, {"params": [p2[1]]}], lr=1e-3, momentum=momentum,
+                           weight_decay=wd)
+        else:
+            ref = torch.optim.SGD(p1, lr=1e-2, momentum=momentum, weight_decay=wd)
+            opt = FusedSGD(p2, lr=1e-2, momentum=momentum, weight_decay=wd)
+        for step in range(4):
+            gr = torch.randn(10007, generator=g).cuda()
+            gh = gr.clone()
+            p1[0].grad, p1[1].grad = gr[:5000].clone(), gr[5000:].clone()
+            p2[0].grad, p2[1].grad = gh[:5000], gh[5000:]
+            ref.step()
+            opt.step()
+        got = torch.cat([p.data for p in p2])
+        want = torch.cat([p.data for p in p1])
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-7), (momentum, wd, groups)
+
+
 def test_dice_per_image_matches_reference_dice_on_one_hots():
     """metrics.dice_per_image against oracle.metrics.dice (pinned to the reference's utils.dice by
     tests/golden/metrics_reference.npz) applied to the one-hot volumes, as SU/ModelTraining.py:629-634 does."""
