@@ -355,13 +355,13 @@ int mmr_bias_grad_finalize(const double* partial, int nblk, int C, float* dbias,
                            mmr_stream_t stream);
 
 /* MaxPool2d(3, stride 2, pad 1) on NHWC bf16; idx = window position 0..8 of the first
- * maximum (torch tie rule).  Replaces encoder.maxpool. */
+ * maximum (torch tie rule), may be NULL (eval mode: only the backward pass reads it).  Replaces encoder.maxpool. */
 int mmr_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, uint8_t* idx,
                          mmr_stream_t stream);
 int mmr_maxpool3x3s2_bwd(const MmrContrib* contribs, int ncontrib, const uint8_t* idx, int N,
                          int H, int W, int C, void* gin, mmr_stream_t stream);
 /* nn.MaxPool2d(2) of the in-tree UNet's Down block (SU/UArchModel/unet_parts.py): disjoint 2x2 windows,
- * floor mode; idx (uint8, 0..3) = position of the first maximum in scan order. */
+ * floor mode; idx (uint8, 0..3) = position of the first maximum in scan order (may be NULL). */
 int mmr_maxpool2x2s2_fwd(const void* x, int N, int H, int W, int C, void* out, uint8_t* idx,
                          mmr_stream_t stream);
 int mmr_maxpool2x2s2_bwd(const MmrContrib* contribs, int ncontrib, const uint8_t* idx, int N, int H, int W,

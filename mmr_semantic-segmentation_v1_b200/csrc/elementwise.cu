@@ -756,43 +756,51 @@ bn_bwd_apply_masked_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bflo
 }
 
 // ------------------------------------------------------------------ max-pool 3x3 s2 p1
-__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
-                                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
+__global__ void __launch_bounds__(kEwThreads)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ idx) {
   pdl_prologue();
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const int groups = C / 8;
-  const int64_t total = (int64_t)N * Ho * Wo * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const uint32_t groups = (uint32_t)C / 8;
+  const uint32_t total = (uint32_t)N * Ho * Wo * groups;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int c = (int)(i % groups) * 8;
-    const int64_t pix = i / groups;
-    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), n = (int)(pix / ((int64_t)Wo * Ho));
+    const uint32_t pix = i / groups;
+    const int ox = (int)(pix % (uint32_t)Wo), oy = (int)((pix / (uint32_t)Wo) % (uint32_t)Ho);
+    const int n = (int)(pix / ((uint32_t)Wo * Ho));
+    // all (up to nine) window loads first, then the scan
+    uint4 raw[9];
+    bool live[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int iy = 2 * oy + k / 3 - 1, ix = 2 * ox + k % 3 - 1;
+      live[k] = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      if (live[k]) raw[k] = ldg16(x + (((size_t)n * H + iy) * W + ix) * C + c);
+    }
     float best[8];
     int bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) best[j] = -INFINITY, bi[j] = 0;
     bool first = true;
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = 2 * oy + ky - 1;
-      if (iy < 0 || iy >= H) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox + kx - 1;
-        if (ix < 0 || ix >= W) continue;
-        float v[8];
-        load8(x + (((size_t)n * H + iy) * W + ix) * C + c, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // torch: first maximum in window scan order wins; NaN propagates
-          if (first || v[j] > best[j] || v[j] != v[j]) best[j] = v[j], bi[j] = ky * 3 + kx;
-        }
-        first = false;
+    for (int k = 0; k < 9; ++k) {
+      if (!live[k]) continue;
+      float v[8];
+      cvt8(raw[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // torch: first maximum in window scan order wins; NaN propagates
+        if (first || v[j] > best[j] || v[j] != v[j]) best[j] = v[j], bi[j] = k;
       }
+      first = false;
     }
-    store8(out + pix * C + c, best);
-    uint2 packed;
-    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-    *reinterpret_cast<uint2*>(idx + pix * C + c) = packed;
+    store8(out + (size_t)pix * C + c, best);
+    if (idx) {   // NULL in eval mode: the argmax is only needed by the backward pass
+      uint2 packed;
+      packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + (size_t)pix * C + c) = packed;
+    }
   }
 }
 
@@ -826,10 +834,12 @@ __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, 
         if (v[k][j] > best[j] || v[k][j] != v[k][j]) best[j] = v[k][j], bi[j] = k;
     }
     store8(out + (size_t)pix * C + c, best);
-    uint2 packed;
-    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-    *reinterpret_cast<uint2*>(idx + (size_t)pix * C + c) = packed;
+    if (idx) {
+      uint2 packed;
+      packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + (size_t)pix * C + c) = packed;
+    }
   }
 }
 
@@ -1337,7 +1347,8 @@ extern "C" int mmr_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, v
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  mmr_launch((maxpool_fwd_kernel), ew_blocks(total, 16), kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out),
+  MMR_REQUIRE(total < ((int64_t)1 << 31), "max-pool: tensor too large for 32-bit indexing");
+  mmr_launch((maxpool_fwd_kernel), ew_blocks(total, 64), kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out),
       idx);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;

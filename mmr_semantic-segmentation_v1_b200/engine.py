@@ -187,7 +187,8 @@ class Engine:
                 oshape = (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c) if k == 3 else (n, h // 2, w // 2, c)
                 out = _Act(op["out"], oshape)
                 out.buf = self._bf16(*out.shape)
-                out.idx = torch.empty(out.shape, device=self.dev, dtype=torch.uint8)
+                # the argmax positions are only read by the backward pass
+                out.idx = torch.empty(out.shape, device=self.dev, dtype=torch.uint8) if self.training else None
                 out.producer = {"kind": "maxpool", "src": src, "out": out, "k": k}
                 self.acts[op["out"]] = out
                 self.units.append(out.producer)
