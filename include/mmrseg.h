@@ -62,6 +62,10 @@ typedef struct {
   void* ptr;    /* destination tensor base (bf16 NHWC, or fp32 NCHW in out_mode 1) */
   int32_t ldc;  /* channels of the destination tensor */
   int32_t coff; /* first destination channel written by this N-tile */
+  /* halo conv store groups only (0 / 1 = dense): the conv's pixel (y, x) is pixel (step*y + oy, step*x + ox) of
+   * a destination tensor [N][step*H][step*W][ldc] -- depth-to-space through the TMA store's strides (the
+   * space-to-depth stem, mmr_stem_s2d_*). */
+  int32_t step, oy, ox;
 } MmrOutSeg;
 
 enum { MMR_OUT_BF16_NHWC = 0, MMR_OUT_F32_NCHW = 1 };
@@ -277,6 +281,18 @@ int mmr_stem_im2col(const float* x, int N, int H, int W, void* out, int kpad, co
  * ToTensor + utils.normalize + fp32 host-to-device copy in front of the model. */
 int mmr_stem_im2col_u8(const uint8_t* x_nhwc, int N, int H, int W, void* out, int kpad, const float* mean,
                        const float* std_, mmr_stream_t stream);
+/* Space-to-depth form of the 7x7 stride-2 pad-3 stem (encoder.conv1) for the halo kernel: with 4x4 pixel blocks
+ * as channels the stem is a 3x3 pad-1 convolution from 48 (+16 zero) block channels to 4 output phases x Cout
+ * channels on the H/4 x W/4 grid (phase (qy, qx) of block (Y, X) is output pixel (2Y + qy, 2X + qx)):
+ *   input row 2*oy + ky - 3 = 4*(Y + A - 1) + ry   <=>   ky = 4*(A - 1) + ry - 2*qy + 3,  A in {0,1,2}.
+ * No im2col matrix (320 B per output pixel, written and read back) exists; the blocked image is 6 B per input
+ * pixel.  mmr_stem_s2d_pack: image -> bf16 [N][H/4][W/4][64], channel (ry*4 + rx)*3 + c; fp32 NCHW input, or
+ * (is_u8) uint8 NHWC frames scaled by 1/255; optional (x - mean[c]) / std[c].
+ * mmr_stem_s2d_weights: conv1.weight fp32 [Cout][3][7][7] -> fp32 OIHW [4*Cout][64][3][3] (row = phase*Cout + co),
+ * which mmr_pack_weights_halo then packs like any 3x3 layer. */
+int mmr_stem_s2d_pack(const void* x, int is_u8, int N, int H, int W, void* out, const float* mean,
+                      const float* std_, mmr_stream_t stream);
+int mmr_stem_s2d_weights(const float* w7, int Cout, float* w3_oihw, mmr_stream_t stream);
 /* NCHW fp32 -> NHWC bf16 with channel padding to cpad (zeros). */
 int mmr_pack_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, void* out,
                                    int cpad, mmr_stream_t stream);

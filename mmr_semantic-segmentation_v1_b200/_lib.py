@@ -30,7 +30,8 @@ class MmrConvClass(C.Structure):
 
 
 class MmrOutSeg(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("ldc", C.c_int32), ("coff", C.c_int32)]
+    _fields_ = [("ptr", C.c_void_p), ("ldc", C.c_int32), ("coff", C.c_int32),
+                ("step", C.c_int32), ("oy", C.c_int32), ("ox", C.c_int32)]
 
 
 class MmrConvDesc(C.Structure):
@@ -155,6 +156,8 @@ SIGNATURES = {
     "mmr_wgrad_plan_run": (_i, [_vp, _i, _i, _vp]),
     "mmr_wgrad_plan_destroy": (_i, [_vp]),
     "mmr_stem_im2col": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "mmr_stem_s2d_pack": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "mmr_stem_s2d_weights": (_i, [_vp, _i, _vp, _vp]),
     "mmr_stem_im2col_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_pack_nhwc_u8_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),

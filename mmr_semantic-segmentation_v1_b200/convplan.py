@@ -97,7 +97,7 @@ def _make_desc(srcs, ksteps_per_cls, cls_meta, weights, bk, bn, out_segs, grid, 
     arr = (MmrKStep * max(1, len(flat)))(*flat)
     d.nksteps = len(flat)
     d.ksteps = C.cast(arr, C.POINTER(MmrKStep))
-    segs = (MmrOutSeg * len(out_segs))(*[MmrOutSeg(t.data_ptr(), ldc, coff)
+    segs = (MmrOutSeg * len(out_segs))(*[MmrOutSeg(t.data_ptr(), ldc, coff, 1, 0, 0)
                                          for (t, ldc, coff) in out_segs])
     d.n_tiles_n = len(out_segs)
     d.outsegs = C.cast(segs, C.POINTER(MmrOutSeg))
@@ -577,9 +577,13 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     d.direct_store = int(cfg.get("direct", cfg["sg"] < 64))
     keep = [sources, packed, scale, bias, residual, stats]
     if out_f32 is None:
-        segs = (MmrOutSeg * len(groups))(*[MmrOutSeg(t.data_ptr(), t.shape[3], coff) for t, coff in groups])
-        for t, _ in groups:
-            assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape[:3]) == (N, H, W)
+        # (tensor, coff) or (tensor, coff, step, oy, ox): pixel (y, x) -> (step*y + oy, step*x + ox) of the tensor
+        groups = [g if len(g) == 5 else (g[0], g[1], 1, 0, 0) for g in groups]
+        segs = (MmrOutSeg * len(groups))(*[MmrOutSeg(t.data_ptr(), t.shape[3], coff, step, oy, ox)
+                                           for t, coff, step, oy, ox in groups])
+        for t, _, step, _, _ in groups:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape[:3]) == (N, step * H, step * W)
+        groups = [(t, coff) for t, coff, _, _, _ in groups]
         d.ngroups = len(groups)
         d.groups = C.cast(segs, C.POINTER(MmrOutSeg))
         d.out_mode = MMR_OUT_BF16_NHWC

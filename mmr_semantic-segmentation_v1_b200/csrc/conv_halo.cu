@@ -1118,12 +1118,18 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
                   "store group %d: channels [%d, %d) do not fit a tensor of %d channels", g, og.coff,
                   og.coff + p.sg, og.ldc);
       maps.emplace_back();
+      const int step = og.step > 1 ? og.step : 1;
+      MMR_REQUIRE(step == 1 || (R == 1 && !d->direct_store && og.oy >= 0 && og.oy < step && og.ox >= 0 && og.ox < step &&
+                                !d->residual && !d->stats),
+                  "strided store groups need rph = 1, TMA stores, no residual / statistics and 0 <= oy, ox < step");
       if (R == 1) {
+        // dense (step 1), or pixel (y, x) -> (step*y + oy, step*x + ox) of [N][step*H][step*W][ldc]
+        const cuuint64_t pxb = (cuuint64_t)og.ldc * 2, rowb = pxb * d->W * step;
         cuuint64_t dims[4] = {(cuuint64_t)og.ldc, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-        cuuint64_t str[3] = {(cuuint64_t)og.ldc * 2, (cuuint64_t)og.ldc * 2 * d->W,
-                             (cuuint64_t)og.ldc * 2 * d->W * d->H};
+        cuuint64_t str[3] = {pxb * step, rowb * step, rowb * step * d->H};
         cuuint32_t box[4] = {(cuuint32_t)p.sg, 8, 4, 1};
-        if (encode_generic(&maps.back(), og.ptr, 4, dims, str, box, p.sg * 2, "store group")) { delete pl; return -1; }
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(og.ptr) + (size_t)og.oy * rowb + (size_t)og.ox * pxb;
+        if (encode_generic(&maps.back(), base, 4, dims, str, box, p.sg * 2, "store group")) { delete pl; return -1; }
       } else {  // (C, W, phase, H / R, N): a warp's four tile rows are R image rows apart
         const cuuint64_t rowb = (cuuint64_t)og.ldc * 2 * d->W;
         cuuint64_t dims[5] = {(cuuint64_t)og.ldc, (cuuint64_t)d->W, (cuuint64_t)R, (cuuint64_t)(d->H / R),

@@ -128,6 +128,55 @@ stem_im2col_kernel(const TIn* __restrict__ x, int N, int H, int W, int Ho, int W
   }
 }
 
+// Space-to-depth stem (see mmrseg.h): thread = (block pixel, 8-channel group) of the [N][H/4][W/4][64] tensor.
+template <typename TIn>
+__global__ void __launch_bounds__(kEwThreads)
+stem_s2d_pack_kernel(const TIn* __restrict__ x, int N, int H, int W, __nv_bfloat16* __restrict__ out,
+                     const float* __restrict__ mean, const float* __restrict__ std_) {
+  pdl_prologue();
+  const int Hb = H / 4, Wb = W / 4;
+  const uint32_t total = (uint32_t)N * Hb * Wb * 8;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    const uint32_t pix = i >> 3;
+    const int X = (int)(pix % (uint32_t)Wb), Y = (int)((pix / (uint32_t)Wb) % (uint32_t)Hb);
+    const int n = (int)(pix / ((uint32_t)Wb * Hb));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;   // (ry*4 + rx)*3 + c
+      float val = 0.f;
+      if (ch < 48) {
+        const int c = ch % 3, rx = (ch / 3) & 3, ry = ch / 12;
+        const int iy = 4 * Y + ry, ix = 4 * X + rx;
+        if (sizeof(TIn) == 1)
+          val = (float)x[(((size_t)n * H + iy) * W + ix) * 3 + c] * (1.f / 255.f);
+        else
+          val = (float)x[(((size_t)n * 3 + c) * H + iy) * W + ix];
+        if (mean) val = (val - __ldg(mean + c)) / __ldg(std_ + c);
+      }
+      v[j] = val;
+    }
+    store8(out + (size_t)pix * 64 + g * 8, v);
+  }
+}
+
+__global__ void stem_s2d_weights_kernel(const float* __restrict__ w7, int Cout, float* __restrict__ w3) {
+  pdl_prologue();
+  const int total = 4 * Cout * 64 * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int B = i % 3, A = (i / 3) % 3, ch = (i / 9) % 64, row = i / (9 * 64);
+    const int co = row % Cout, q = row / Cout, qy = q >> 1, qx = q & 1;
+    float v = 0.f;
+    if (ch < 48) {
+      const int c = ch % 3, rx = (ch / 3) & 3, ry = ch / 12;
+      const int ky = 4 * (A - 1) + ry - 2 * qy + 3, kx = 4 * (B - 1) + rx - 2 * qx + 3;
+      if (ky >= 0 && ky < 7 && kx >= 0 && kx < 7) v = w7[((co * 3 + c) * 7 + ky) * 7 + kx];
+    }
+    w3[i] = v;
+  }
+}
+
 __global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C, int H, int W,
                                  __nv_bfloat16* __restrict__ out, int cpad) {
   pdl_prologue();
@@ -1163,6 +1212,30 @@ extern "C" int mmr_stem_im2col_u8(const uint8_t* x_nhwc, int N, int H, int W, vo
   MMR_REQUIRE(Ho <= 65535 && N <= 65535, "stem_im2col: Ho and N <= 65535");
   dim3 grid((Wo + kStemSeg - 1) / kStemSeg, Ho, N);
   mmr_launch((stem_im2col_kernel<uint8_t>), grid, 256, 0, as_stream(stream), x_nhwc, N, H, W, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out), kpad, mean, std_);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_stem_s2d_pack(const void* x, int is_u8, int N, int H, int W, void* out, const float* mean,
+                                 const float* std_, mmr_stream_t stream) {
+  MMR_REQUIRE(x && out && H % 4 == 0 && W % 4 == 0, "stem_s2d_pack: H and W must be multiples of 4");
+  MMR_REQUIRE((mean == nullptr) == (std_ == nullptr), "pass both mean and std or neither");
+  const int64_t total = (int64_t)N * (H / 4) * (W / 4) * 8;
+  MMR_REQUIRE(total < ((int64_t)1 << 31), "stem_s2d_pack: tensor too large for 32-bit indexing");
+  if (is_u8)
+    mmr_launch((stem_s2d_pack_kernel<uint8_t>), ew_blocks(total, 32), kEwThreads, 0, as_stream(stream),
+               reinterpret_cast<const uint8_t*>(x), N, H, W, reinterpret_cast<__nv_bfloat16*>(out), mean, std_);
+  else
+    mmr_launch((stem_s2d_pack_kernel<float>), ew_blocks(total, 32), kEwThreads, 0, as_stream(stream),
+               reinterpret_cast<const float*>(x), N, H, W, reinterpret_cast<__nv_bfloat16*>(out), mean, std_);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_stem_s2d_weights(const float* w7, int Cout, float* w3_oihw, mmr_stream_t stream) {
+  MMR_REQUIRE(w7 && w3_oihw && Cout >= 1, "bad argument");
+  const int total = 4 * Cout * 64 * 9;
+  mmr_launch((stem_s2d_weights_kernel), (total + 255) / 256, 256, 0, as_stream(stream), w7, Cout, w3_oihw);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

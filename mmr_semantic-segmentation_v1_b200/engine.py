@@ -275,40 +275,70 @@ class Engine:
         w = self.P[op["conv"] + ".weight"]
         cout = w.shape[0]
         unit = {"kind": "stem", "op": op, "cout": cout}
-        unit["mat"] = self._bf16(1, 1, Pn, STEM_KPAD)
-        unit["wf"] = self._bf16(cout, STEM_KPAD, zero=True)
         out = _Act(op["out"], (N, Ho, Wo, cout))
         out.buf = self._bf16(*out.shape)
         out.producer = unit
         unit["out"] = out
-        self._rec(fc, "mmr_stem_im2col", self.x_in, N, H, W, unit["mat"], STEM_KPAD, None, None)
-        alt = []
-        self._rec(alt, "mmr_stem_im2col_u8", self.x_u8, N, H, W, unit["mat"], STEM_KPAD, self.in_norm[0],
-                  self.in_norm[1])
-        self.u8_swaps.append((len(fc) - 1, alt[0]))
-        self._rec(self.repack_calls, "mmr_repack_weights", w, cout, 147, 1, unit["wf"], STEM_KPAD, None, 0, 0)
-        if self.training:
-            unit["z"] = self._bf16(N, Ho, Wo, cout)
-            self._bn_state(unit, op["bn"], cout)
-            plan = convplan.build_fprop([(unit["mat"], 1)], unit["wf"], 1, 1, 0, unit["z"].view(1, 1, Pn, cout))
-            fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
-            self._fwd_bn_train(unit, unit["z"], out.buf, None, True)
+        if not self.training and cout == 64 and H % 4 == 0 and W % 4 == 0 and not os.environ.get("MMR_NO_S2D"):
+            self._fwd_stem_s2d(op, unit, out, w)
         else:
-            self._fold(unit, op["bn"], cout)
-            plan = convplan.build_fprop([(unit["mat"], 1)], unit["wf"], 1, 1, 0, out.buf.view(1, 1, Pn, cout),
-                                        scale=unit["scale"], bias=unit["shift"], relu=True)
-            fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
-        plan.flops = 2 * Pn * cout * 147
-        self.conv_flops_fwd += plan.flops
-        unit["fplan"] = plan
+            unit["mat"] = self._bf16(1, 1, Pn, STEM_KPAD)
+            unit["wf"] = self._bf16(cout, STEM_KPAD, zero=True)
+            self._rec(fc, "mmr_stem_im2col", self.x_in, N, H, W, unit["mat"], STEM_KPAD, None, None)
+            alt = []
+            self._rec(alt, "mmr_stem_im2col_u8", self.x_u8, N, H, W, unit["mat"], STEM_KPAD, self.in_norm[0],
+                      self.in_norm[1])
+            self.u8_swaps.append((len(fc) - 1, alt[0]))
+            self._rec(self.repack_calls, "mmr_repack_weights", w, cout, 147, 1, unit["wf"], STEM_KPAD, None, 0, 0)
+            if self.training:
+                unit["z"] = self._bf16(N, Ho, Wo, cout)
+                self._bn_state(unit, op["bn"], cout)
+                plan = convplan.build_fprop([(unit["mat"], 1)], unit["wf"], 1, 1, 0, unit["z"].view(1, 1, Pn, cout))
+                fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+                self._fwd_bn_train(unit, unit["z"], out.buf, None, True)
+            else:
+                self._fold(unit, op["bn"], cout)
+                plan = convplan.build_fprop([(unit["mat"], 1)], unit["wf"], 1, 1, 0, out.buf.view(1, 1, Pn, cout),
+                                            scale=unit["scale"], bias=unit["shift"], relu=True)
+                fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+            unit["fplan"] = plan
+        unit["fplan"].flops = 2 * Pn * cout * 147
+        self.conv_flops_fwd += unit["fplan"].flops
         self.acts[op["out"]] = out
         self.units.append(unit)
 
-    def _fold(self, unit, bn_name, Cc, conv_bias=None):
+    def _fwd_stem_s2d(self, op, unit, out, w):
+        """Eval mode: the 7x7 stride-2 stem as a 3x3 convolution over 4x4 pixel blocks (include/mmrseg.h,
+        mmr_stem_s2d_*) on the halo kernel: 48 block channels -> 4 output phases x 64 channels, each phase
+        stored by its own strided TMA map (depth-to-space for free); no im2col matrix."""
+        N, H, W = self.N, self.H, self.W
+        fc = self.fwd_calls
+        cout = unit["cout"]
+        s2d = self._bf16(N, H // 4, W // 4, 64)
+        self._rec(fc, "mmr_stem_s2d_pack", self.x_in, 0, N, H, W, s2d, None, None)
+        alt = []
+        self._rec(alt, "mmr_stem_s2d_pack", self.x_u8, 1, N, H, W, s2d, self.in_norm[0], self.in_norm[1])
+        self.u8_swaps.append((len(fc) - 1, alt[0]))
+        w3 = self._f32(4 * cout, 64, 3, 3)
+        self._rec(self.repack_calls, "mmr_stem_s2d_weights", w, cout, w3)
+        sources = [(s2d, 1)]
+        hcfg = convplan.fprop_halo_cfg(sources, 4 * cout, bf16_out=True, force={"rph": 1, "sg": 64})
+        assert hcfg["sg"] == cout == 64
+        unit["wf_h"] = self._bf16(convplan.halo_packed_weights_numel(hcfg))
+        self._pack_job(w3, unit["wf_h"], 4 * cout, 64, 0, hcfg)
+        self._fold(unit, op["bn"], cout, rep=4)
+        groups = [(out.buf, 0, 2, q >> 1, q & 1) for q in range(4)]
+        plan = convplan.build_halo(hcfg, sources, unit["wf_h"], groups, N, H // 4, W // 4, 4 * cout,
+                                   scale=unit["scale"], bias=unit["shift"], relu=True)
+        fc.append((self.lib.mmr_halo_conv_plan_run, (plan.handle,)))
+        unit["fplan"] = plan
+
+    def _fold(self, unit, bn_name, Cc, conv_bias=None, rep=1):
         """Eval mode: scale/shift from the running statistics, refreshed by `refresh_folded`; a conv bias
-        in front of the BatchNorm (the in-tree UNet's DoubleConv) folds into the shift."""
-        st = self._f32(2, Cc)
-        unit.update(bn=bn_name, scale=st[0], shift=st[1], fold_bias=conv_bias)
+        in front of the BatchNorm (the in-tree UNet's DoubleConv) folds into the shift.  rep: the GEMM's
+        output channels are `rep` copies of the layer's (the space-to-depth stem's four output phases)."""
+        st = self._f32(2, Cc * rep)
+        unit.update(bn=bn_name, scale=st[0], shift=st[1], fold_bias=conv_bias, fold_rep=rep)
         self.keep.append(st)
         self.folded = getattr(self, "folded", [])
         self.folded.append(unit)
@@ -325,11 +355,12 @@ class Engine:
             bn = u["bn"]
             inv = torch.rsqrt(self.P[bn + ".running_var"].float() + 1e-5)
             sc = self.P[bn + ".weight"].float() * inv
-            u["scale"].copy_(sc)
+            rep = u.get("fold_rep", 1)
+            u["scale"].copy_(sc.repeat(rep))
             mean = self.P[bn + ".running_mean"].float()
             if u.get("fold_bias"):
                 mean = mean - self.P[u["fold_bias"]].float()
-            u["shift"].copy_(self.P[bn + ".bias"].float() - mean * sc)
+            u["shift"].copy_((self.P[bn + ".bias"].float() - mean * sc).repeat(rep))
 
     def _fwd_conv(self, op):
         fc = self.fwd_calls

@@ -108,3 +108,44 @@ def test_device_prefetcher_order_and_values():
         seen += 1
     assert seen == 5 and len(DevicePrefetcher(host)) == 5
     assert list(DevicePrefetcher([])) == []
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_stem_space_to_depth_matches_conv2d(u8):
+    """The 7x7 stride-2 pad-3 stem as a 3x3 conv over 4x4 pixel blocks (mmr_stem_s2d_pack / _weights + the halo
+    kernel with strided store groups) against F.conv2d on the same bf16-rounded operands: 4e-3 x 8 of the output
+    RMS, as for every conv kernel; fp32 NCHW and uint8 HWC inputs."""
+    import torch.nn.functional as F
+    from mmrseg_b200 import _lib as L
+    from mmrseg_b200 import convplan
+    lib = L.lib()
+    n, h, w, cout = 2, 64, 96, 64
+    g = torch.Generator().manual_seed(5)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    s2d = torch.empty((n, h // 4, w // 4, 64), device="cuda", dtype=torch.bfloat16)
+    if u8:
+        frames = torch.randint(0, 256, (n, h, w, 3), generator=g, dtype=torch.uint8)
+        x = _reference_preprocess(frames)
+        mean, std = torch.tensor(MEAN, device="cuda"), torch.tensor(STD, device="cuda")
+        L.check(lib.mmr_stem_s2d_pack(p(frames.cuda()), 1, n, h, w, p(s2d), p(mean), p(std), s))
+    else:
+        x = torch.randn((n, 3, h, w), generator=g)
+        L.check(lib.mmr_stem_s2d_pack(p(x.cuda()), 0, n, h, w, p(s2d), None, None, s))
+    w7 = (torch.randn((cout, 3, 7, 7), generator=g) / 12).cuda()
+    w3 = torch.empty((4 * cout, 64, 3, 3), device="cuda")
+    L.check(lib.mmr_stem_s2d_weights(p(w7), cout, p(w3), s))
+    # every original tap appears exactly once per output phase
+    assert torch.allclose(w3.view(4, cout, -1).sum(2), w7.view(cout, -1).sum(1).expand(4, cout), atol=1e-4)
+    out = torch.full((n, h // 2, w // 2, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    cfg = convplan.fprop_halo_cfg([(s2d, 1)], 4 * cout, force={"rph": 1, "sg": 64})
+    packed = convplan.pack_weights_halo(w3, cfg, 0)
+    groups = [(out, 0, 2, q >> 1, q & 1) for q in range(4)]
+    plan = convplan.build_halo(cfg, [(s2d, 1)], packed, groups, n, h // 4, w // 4, 4 * cout)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w7.cpu().to(torch.bfloat16).float(), None, 2, 3)
+    got = out.float().permute(0, 3, 1, 2).cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 4e-3 * 8 * ref.pow(2).mean().sqrt().item() + (0.02 if u8 else 0.0), err
