@@ -293,6 +293,11 @@ int mmr_stem_im2col_u8(const uint8_t* x_nhwc, int N, int H, int W, void* out, in
 int mmr_stem_s2d_pack(const void* x, int is_u8, int N, int H, int W, void* out, const float* mean,
                       const float* std_, mmr_stream_t stream);
 int mmr_stem_s2d_weights(const float* w7, int Cout, float* w3_oihw, mmr_stream_t stream);
+/* Backward of mmr_stem_s2d_weights: dw7[co][c][ky][kx] (+)= sum over the four phases of the matching element of
+ * dw3 [4*Cout][64][3][3] (the weight gradient of the 3x3 form, from mmr_wgrad_halo_plan_* with a phased dz:
+ * MmrWgradHaloDesc.dz.up = 2 means dz is [N][2H][2W][C] and GEMM output channel (q, c) is channel c of pixel
+ * (2y + qy, 2x + qx); needs bn = C, cout_gemm = 4 C). */
+int mmr_stem_s2d_wgrad_fold(const float* dw3_oihw, int Cout, float* dw7, int accumulate, mmr_stream_t stream);
 /* NCHW fp32 -> NHWC bf16 with channel padding to cpad (zeros). */
 int mmr_pack_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, void* out,
                                    int cpad, mmr_stream_t stream);

@@ -158,6 +158,7 @@ SIGNATURES = {
     "mmr_stem_im2col": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_stem_s2d_pack": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mmr_stem_s2d_weights": (_i, [_vp, _i, _vp, _vp]),
+    "mmr_stem_s2d_wgrad_fold": (_i, [_vp, _i, _vp, _i, _vp]),
     "mmr_stem_im2col_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_pack_nhwc_u8_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "mmr_pack_nchw_f32_to_nhwc_bf16": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp]),

@@ -737,11 +737,15 @@ def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=
     return cfg
 
 
-def build_wgrad_halo(dz, sources, dst, *, cout_gemm=None, force=None, partial=None, n_sms=148):
+def build_wgrad_halo(dz, sources, dst, *, cout_gemm=None, force=None, partial=None, n_sms=148, dz_phased=False):
     """Weight gradient of a 3x3 s1 p1 conv.  dz: [N,H,W,Cz] bf16; sources as in build_fprop_halo;
-    dst: fp32 OIHW [Cout][Cin_total][3][3]."""
+    dst: fp32 OIHW [Cout][Cin_total][3][3].  dz_phased: dz is [N,2H,2W,C] and the GEMM's output channel (q, c)
+    is channel c of pixel (2y + qy, 2x + qx) (the space-to-depth stem): Cout = 4 C."""
     from ._lib import MmrHaloSrc, MmrWgradHaloDesc
     N, H, W, Cz = dz.shape
+    if dz_phased:
+        H, W, Cz = H // 2, W // 2, 4 * Cz
+        force = dict(force or {}, bn=dz.shape[3])
     assert dz.dtype == torch.bfloat16 and dz.is_contiguous()
     assert dst.dtype == torch.float32 and dst.is_contiguous() and tuple(dst.shape[2:]) == (3, 3)
     cout, cin = dst.shape[0], dst.shape[1]
@@ -758,7 +762,7 @@ def build_wgrad_halo(dz, sources, dst, *, cout_gemm=None, force=None, partial=No
         partial = torch.empty((need,), device=dz.device, dtype=torch.float32)
     assert partial.dtype == torch.float32 and partial.numel() >= need
     d = MmrWgradHaloDesc()
-    d.dz = MmrHaloSrc(dz.data_ptr(), Cz, W, H, N, 1)
+    d.dz = MmrHaloSrc(dz.data_ptr(), dz.shape[3], W, H, N, 2 if dz_phased else 1)
     d.nsrc = len(sources)
     for i, (t, up) in enumerate(sources):
         assert t.dtype == torch.bfloat16 and t.is_contiguous()

@@ -31,7 +31,7 @@ struct WhChunk {
 struct WhParams {
   const CUtensorMap* maps;  // device: [activation maps ...][dz map]
   WhChunk chunk[kWhMaxChunks];
-  int nchunks, dzmap;
+  int nchunks, dzmap, dz_phased;  // dz_phased: N tile nt reads output phase nt through its own strided map
   int H, W, N, TX, tiles_x, tiles_y, total_tiles;
   int cb, xrb, bn, zrb, n_ntiles, A;
   int n_split, stages;
@@ -132,7 +132,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
         uint8_t* sz = sx + p.x_stage_bytes;
         const int x0 = tx * 8 * p.TX, y0 = ty * 16;
         mbar_arrive_expect_tx(&full[stage], p.x_tx_bytes[ch.up] + p.z_tx_bytes);
-        tma_load_4d(sz, &p.maps[p.dzmap], &full[stage], nt * p.bn, x0, y0, n);
+        tma_load_4d(sz, &p.maps[p.dzmap + (p.dz_phased ? nt : 0)], &full[stage], p.dz_phased ? 0 : nt * p.bn, x0, y0, n);
         if (!ch.up) {
           tma_load_4d(sx, &p.maps[ch.map], &full[stage], ch.c0, x0 - 1, y0 - 1, n);
         } else {
@@ -351,10 +351,12 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   MMR_REQUIRE(d->nsrc >= 1 && d->nsrc <= 6, "nsrc must be 1..6, got %d", d->nsrc);
   MMR_REQUIRE(d->cb == 64 || d->cb == 32 || d->cb == 16, "cb must be 16/32/64, got %d", d->cb);
   MMR_REQUIRE(d->bn == 64 || d->bn == 32 || d->bn == 16, "bn must be 16/32/64, got %d", d->bn);
-  MMR_REQUIRE(d->cout_gemm % d->bn == 0 && d->dz.C >= d->cout_gemm, "cout_gemm %d must be a multiple of bn %d and fit dz (%d)",
-              d->cout_gemm, d->bn, d->dz.C);
+  const int dz_channels = d->dz.up == 2 ? 4 * d->dz.C : d->dz.C;   // up == 2: four output phases (see below)
+  MMR_REQUIRE(d->cout_gemm % d->bn == 0 && dz_channels >= d->cout_gemm,
+              "cout_gemm %d must be a multiple of bn %d and fit dz (%d)", d->cout_gemm, d->bn, dz_channels);
   MMR_REQUIRE(d->tx == 1 || d->tx == 2 || d->tx == 4, "tx must be 1, 2 or 4");
-  MMR_REQUIRE(d->dz.up == 1 && d->dz.H == d->H && d->dz.W == d->W && d->dz.N == d->N, "dz resolution mismatch");
+  MMR_REQUIRE((d->dz.up == 1 || d->dz.up == 2) && d->dz.H == d->H && d->dz.W == d->W && d->dz.N == d->N,
+              "dz resolution mismatch");
   MMR_REQUIRE(d->partial && d->dst, "null output");
   WhPlan* pl = new WhPlan();
   WhParams& p = pl->prm;
@@ -422,12 +424,27 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.nchunks = nchunks;
   {
     const MmrHaloSrc& z = d->dz;
-    cuuint64_t dims[4] = {(cuuint64_t)z.C, (cuuint64_t)z.W, (cuuint64_t)z.H, (cuuint64_t)z.N};
-    cuuint64_t str[3] = {(cuuint64_t)z.C * 2, (cuuint64_t)z.C * 2 * z.W, (cuuint64_t)z.C * 2 * z.W * z.H};
     cuuint32_t box[4] = {(cuuint32_t)d->bn, (cuuint32_t)(8 * d->tx), 16, 1};
-    maps.emplace_back();
-    p.dzmap = (int)maps.size() - 1;
-    if (wh_encode(&maps[p.dzmap], z.ptr, 4, dims, str, box, p.zrb, "wgrad dz")) { delete pl; return -1; }
+    p.dzmap = (int)maps.size();
+    p.dz_phased = z.up == 2;
+    if (!p.dz_phased) {
+      cuuint64_t dims[4] = {(cuuint64_t)z.C, (cuuint64_t)z.W, (cuuint64_t)z.H, (cuuint64_t)z.N};
+      cuuint64_t str[3] = {(cuuint64_t)z.C * 2, (cuuint64_t)z.C * 2 * z.W, (cuuint64_t)z.C * 2 * z.W * z.H};
+      maps.emplace_back();
+      if (wh_encode(&maps[p.dzmap], z.ptr, 4, dims, str, box, p.zrb, "wgrad dz")) { delete pl; return -1; }
+    } else {
+      // dz is [N][2H][2W][C] and the GEMM's output channel (q, c) is channel c of pixel (2y + qy, 2x + qx): the
+      // space-to-depth stem (mmr_stem_s2d_*).  One strided map per phase = per N tile.
+      MMR_REQUIRE(d->bn == z.C && d->cout_gemm == 4 * z.C, "phased dz needs bn = C and cout_gemm = 4 C");
+      const cuuint64_t pxb = (cuuint64_t)z.C * 2, rowb = pxb * z.W * 2;
+      for (int q = 0; q < 4; ++q) {
+        cuuint64_t dims[4] = {(cuuint64_t)z.C, (cuuint64_t)z.W, (cuuint64_t)z.H, (cuuint64_t)z.N};
+        cuuint64_t str[3] = {pxb * 2, rowb * 2, rowb * 2 * z.H};
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(z.ptr) + (size_t)(q >> 1) * rowb + (size_t)(q & 1) * pxb;
+        maps.emplace_back();
+        if (wh_encode(&maps[p.dzmap + q], base, 4, dims, str, box, p.zrb, "wgrad dz phase")) { delete pl; return -1; }
+      }
+    }
   }
   p.x_tx_bytes[0] = (uint32_t)(18 * p.pitch[0] * p.xrb);
   p.x_tx_bytes[1] = (uint32_t)(18 * p.pitch[1] * p.xrb);

@@ -177,6 +177,25 @@ __global__ void stem_s2d_weights_kernel(const float* __restrict__ w7, int Cout, 
   }
 }
 
+// dW of the 7x7 stem from the gradient of its phase-expanded 3x3 form: every original tap occurs once per
+// output phase.  dw7[co][c][ky][kx] (+)= sum over (qy, qx) of dw3[q*Cout + co][(ry*4 + rx)*3 + c][A][B].
+__global__ void stem_s2d_wgrad_fold_kernel(const float* __restrict__ dw3, int Cout, float* __restrict__ dw7,
+                                           int accumulate) {
+  pdl_prologue();
+  const int total = Cout * 3 * 49;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kx = i % 7, ky = (i / 7) % 7, c = (i / 49) % 3, co = i / 147;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ty = ky + 2 * (q >> 1) - 3 + 4, tx = kx + 2 * (q & 1) - 3 + 4;   // + 4: floor division of negatives
+      const int A = ty / 4, ry = ty % 4, B = tx / 4, rx = tx % 4;
+      s += dw3[(((size_t)(q * Cout + co)) * 64 + (ry * 4 + rx) * 3 + c) * 9 + A * 3 + B];
+    }
+    dw7[i] = accumulate ? dw7[i] + s : s;
+  }
+}
+
 __global__ void pack_nchw_kernel(const float* __restrict__ x, int N, int C, int H, int W,
                                  __nv_bfloat16* __restrict__ out, int cpad) {
   pdl_prologue();
@@ -1236,6 +1255,16 @@ extern "C" int mmr_stem_s2d_weights(const float* w7, int Cout, float* w3_oihw, m
   MMR_REQUIRE(w7 && w3_oihw && Cout >= 1, "bad argument");
   const int total = 4 * Cout * 64 * 9;
   mmr_launch((stem_s2d_weights_kernel), (total + 255) / 256, 256, 0, as_stream(stream), w7, Cout, w3_oihw);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_stem_s2d_wgrad_fold(const float* dw3_oihw, int Cout, float* dw7, int accumulate,
+                                       mmr_stream_t stream) {
+  MMR_REQUIRE(dw3_oihw && dw7 && Cout >= 1, "bad argument");
+  const int total = Cout * 147;
+  mmr_launch((stem_s2d_wgrad_fold_kernel), (total + 255) / 256, 256, 0, as_stream(stream), dw3_oihw, Cout, dw7,
+             accumulate);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -279,7 +279,7 @@ class Engine:
         out.buf = self._bf16(*out.shape)
         out.producer = unit
         unit["out"] = out
-        if not self.training and cout == 64 and H % 4 == 0 and W % 4 == 0 and not os.environ.get("MMR_NO_S2D"):
+        if cout == 64 and H % 4 == 0 and W % 4 == 0 and not os.environ.get("MMR_NO_S2D"):
             self._fwd_stem_s2d(op, unit, out, w)
         else:
             unit["mat"] = self._bf16(1, 1, Pn, STEM_KPAD)
@@ -308,7 +308,7 @@ class Engine:
         self.units.append(unit)
 
     def _fwd_stem_s2d(self, op, unit, out, w):
-        """Eval mode: the 7x7 stride-2 stem as a 3x3 convolution over 4x4 pixel blocks (include/mmrseg.h,
+        """The 7x7 stride-2 stem as a 3x3 convolution over 4x4 pixel blocks (include/mmrseg.h,
         mmr_stem_s2d_*) on the halo kernel: 48 block channels -> 4 output phases x 64 channels, each phase
         stored by its own strided TMA map (depth-to-space for free); no im2col matrix."""
         N, H, W = self.N, self.H, self.W
@@ -326,12 +326,21 @@ class Engine:
         assert hcfg["sg"] == cout == 64
         unit["wf_h"] = self._bf16(convplan.halo_packed_weights_numel(hcfg))
         self._pack_job(w3, unit["wf_h"], 4 * cout, 64, 0, hcfg)
-        self._fold(unit, op["bn"], cout, rep=4)
-        groups = [(out.buf, 0, 2, q >> 1, q & 1) for q in range(4)]
-        plan = convplan.build_halo(hcfg, sources, unit["wf_h"], groups, N, H // 4, W // 4, 4 * cout,
-                                   scale=unit["scale"], bias=unit["shift"], relu=True)
+        unit["s2d"] = s2d
+        if self.training:    # raw z through the strided groups, then the usual statistics / apply passes
+            unit["z"] = self._bf16(*out.shape)
+            self._bn_state(unit, op["bn"], cout)
+            groups = [(unit["z"], 0, 2, q >> 1, q & 1) for q in range(4)]
+            plan = convplan.build_halo(hcfg, sources, unit["wf_h"], groups, N, H // 4, W // 4, 4 * cout)
+        else:
+            self._fold(unit, op["bn"], cout, rep=4)
+            groups = [(out.buf, 0, 2, q >> 1, q & 1) for q in range(4)]
+            plan = convplan.build_halo(hcfg, sources, unit["wf_h"], groups, N, H // 4, W // 4, 4 * cout,
+                                       scale=unit["scale"], bias=unit["shift"], relu=True)
         fc.append((self.lib.mmr_halo_conv_plan_run, (plan.handle,)))
         unit["fplan"] = plan
+        if self.training:
+            self._fwd_bn_train(unit, unit["z"], out.buf, None, True)
 
     def _fold(self, unit, bn_name, Cc, conv_bias=None, rep=1):
         """Eval mode: scale/shift from the running statistics, refreshed by `refresh_folded`; a conv bias
@@ -641,7 +650,14 @@ class Engine:
         gw = self.G[conv + ".weight"]
         wplan = u.get("wplan")
         if wplan is None:
-            if kind == "stem":
+            if kind == "stem" and "s2d" in u:
+                # weight gradient of the 3x3 space-to-depth form (dz read phase by phase through strided maps),
+                # folded back onto the 7x7 filter afterwards
+                u["dw3"] = self._f32(4 * u["cout"], 64, 3, 3)
+                wplan = convplan.build_wgrad_halo(dz, [(u["s2d"], 1)], u["dw3"], n_sms=self.n_sms,
+                                                  partial=self.wg_partial, dz_phased=True)
+                wplan.flops = 2 * Pn * u["cout"] * 147
+            elif kind == "stem":
                 wplan = convplan.build_wgrad(dz.view(1, 1, Pn, cpad), [(u["mat"], 1)], 1, 1, 0,
                                              gw.view(gw.shape[0], 147, 1, 1), n_sms=self.n_sms,
                                              partial=self.wg_partial)
@@ -656,7 +672,10 @@ class Engine:
                                                  n_sms=self.n_sms, partial=self.wg_partial)
             u["wplan"] = wplan
         calls.append((Engine._mark, ("side_begin", self._bwd_t)))
-        if isinstance(wplan, convplan.WgradHaloPlan):
+        if kind == "stem" and "s2d" in u:
+            calls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, 0)))
+            self._rec(calls, "mmr_stem_s2d_wgrad_fold", u["dw3"], u["cout"], gw, acc)
+        elif isinstance(wplan, convplan.WgradHaloPlan):
             calls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, acc)))
         else:
             calls.append((self.lib.mmr_wgrad_plan_run, (wplan.handle, 0, acc)))
