@@ -10,11 +10,12 @@ import torch.distributed as dist
 
 
 class DistributedDataParallel(torch.nn.Module):
-    def __init__(self, module, bucket_mb=8.0, process_group=None):
+    def __init__(self, module, bucket_mb=8.0, process_group=None, tail_mb=1.0):
         super().__init__()
         self.module = module
         self.pg = process_group
         self.bucket_elems = int(bucket_mb * 1024 * 1024 / 4)
+        self.tail_elems = int(tail_mb * 1024 * 1024 / 4)
         self.world = dist.get_world_size(self.pg) if dist.is_initialized() else 1
         self._buckets = None
         self._side = None
@@ -28,7 +29,10 @@ class DistributedDataParallel(torch.nn.Module):
 
     # ---- bucket plan: contiguous slices of the flat gradient buffer, closed in backward order
     def plan_buckets(self, names, offsets, sizes, total):
-        """names in flat order; returns [(lo, hi, set(names))] covering [0,total)."""
+        """names in flat order; returns [(lo, hi, set(names))] covering [0,total).  Buckets are closed in
+        backward order (from the end of the flat buffer); the one that completes LAST -- the front of the
+        buffer, the first layers of the encoder -- is cut down to `tail_elems`, because its all-reduce is the
+        only one nothing is left to overlap with."""
         buckets, hi, cur = [], total, set()
         for name in reversed(names):
             cur.add(name)
@@ -38,6 +42,13 @@ class DistributedDataParallel(torch.nn.Module):
                 hi, cur = lo, set()
         if cur:
             buckets.append((0, hi, cur))
+        lo, hi, cur = buckets[-1]
+        if hi - lo > 2 * self.tail_elems:
+            front = [n for n in names if n in cur and offsets[n] < lo + self.tail_elems]
+            rest = cur - set(front)
+            if front and rest:
+                cut = min(offsets[n] for n in rest)
+                buckets[-1:] = [(cut, hi, rest), (lo, cut, set(front))]
         return buckets
 
     def _setup(self):
@@ -46,7 +57,9 @@ class DistributedDataParallel(torch.nn.Module):
         sizes = {n: p.numel() for n, p in m.named_parameters()}
         self._buckets = self.plan_buckets(names, m._flat_offsets, sizes, m._gflat.numel())
         self._pending = None
-        self._side = torch.cuda.Stream(device=m._gflat.device) if m._gflat.is_cuda else None
+        # high priority: a bucket's all-reduce gets its few CTAs at the next kernel boundary of the backward
+        # instead of waiting for idle SMs behind the persistent conv kernels
+        self._side = torch.cuda.Stream(device=m._gflat.device, priority=-1) if m._gflat.is_cuda else None
         self._works = []
         # broadcast_parameters: rank 0's weights and BN buffers
         if self.world > 1:

@@ -42,6 +42,13 @@ def _worker(rank, world, port):
     covered = sorted((lo, hi) for lo, hi, _ in ddp._buckets)
     assert covered[0][0] == 0 and covered[-1][1] == m._gflat.numel()
     assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+    # the bucket that completes last (front of the buffer) is cut down to the tail size
+    tail = DistributedDataParallel(_FakePlanModel(), bucket_mb=0.016, tail_mb=0.002)
+    tb = tail.plan_buckets(m._flat_names, m._flat_offsets, None, m._gflat.numel())
+    cov = sorted((lo, hi) for lo, hi, _ in tb)
+    assert cov[0][0] == 0 and cov[-1][1] == m._gflat.numel()
+    assert all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1))
+    assert tb[-1][0] == 0 and tb[-1][2] == {"a"} and tb[-1][1] == 1000      # only the first tensor is left in it
     for step in range(2):
         m._gflat.copy_(torch.arange(m._gflat.numel(), dtype=torch.float32) * (rank + 1))
         for names in (["c"], ["b"], ["a"]):                 # backward order: last parameter first
