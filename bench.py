@@ -325,7 +325,7 @@ def run_ours(args):
                                  "h2d_bytes_per_step": fh.numel() + yh.numel() * 8, "d2h_bytes_per_step": 4,
                                  "note": "same step through model(frames_u8): ToTensor + utils.normalize fused into the stem loader"},
             "gpu_launches": per_step * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel + conv_gemm_tc_kernel (all fprop + dgrad launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel + conv_gemm_tc_kernel (all fprop + dgrad launches of a step; their epilogues also take the BatchNorm batch statistics (fprop) and the BatchNorm-backward sums of single-reader units (dgrad), which is not counted as work)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                          "traffic": traffic, "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
                          "algorithmic_tflop_per_step": conv_flops / 1e12, "peak_source": pk["src"]},

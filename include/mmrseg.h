@@ -130,6 +130,27 @@ typedef struct {
   uint32_t* ticket; /* device counter, zero before the first launch */
 } MmrBnFinalize;
 
+/* BatchNorm backward reduction fused into the data-gradient launch that produces the ONLY gradient contribution dx
+ * of a conv -> BatchNorm -> ReLU unit (no residual): the epilogue reads the unit's z tile, recomputes the ReLU
+ * mask (z*mask_scale + mask_shift > 0), accumulates sum(g) and sum(g*z) of g = mask ? dx : 0 per channel, and the
+ * last CTA (ticket) writes dgamma / dbeta / coef exactly as mmr_bn_bwd_reduce_fused does.  dx itself is stored
+ * unmasked; mmr_bn_bwd_apply_masked recomputes the mask.  Needs one N tile = one store group = the whole tensor. */
+typedef struct {
+  const void* z;            /* bf16 NHWC, same shape as dx */
+  const float* mask_scale;  /* the forward pass's scale / shift of the unit */
+  const float* mask_shift;
+  const float* mean;
+  const float* invstd;
+  const float* gamma;       /* may be NULL (= 1) */
+  float* dgamma;            /* may be NULL */
+  float* dbeta;             /* may be NULL */
+  float* coef;              /* [3][C] */
+  double* slots;            /* [8][2][C], zero before the first launch, re-armed by the last CTA */
+  uint32_t* ticket;
+  int64_t count;            /* N*H*W */
+  int32_t accumulate;
+} MmrBnBwdFused;
+
 typedef struct {
   const void* ptr; /* bf16 NHWC, stored resolution (half of the conv's when up == 2) */
   int32_t C, W, H, N;
@@ -169,6 +190,7 @@ typedef struct {
    * operand (what bounds N <= 64 MMAs).  Needs tps = 3, bn <= 64, H % rph == 0 (H % (16 rph) == 0 with
    * nearest-x2 sources), weights packed with layout 1, tx * rph * bn * acc_bufs <= 512. */
   int32_t rph;
+  const MmrBnBwdFused* bn_bwd; /* optional (data-gradient launches): see MmrBnBwdFused */
 } MmrHaloConvDesc;
 
 int mmr_halo_conv_plan_create(const MmrHaloConvDesc* desc, void** plan);

@@ -60,6 +60,13 @@ class MmrBnFinalize(C.Structure):
                 ("count", C.c_int64), ("ticket", C.c_void_p)]
 
 
+class MmrBnBwdFused(C.Structure):
+    _fields_ = [("z", C.c_void_p), ("mask_scale", C.c_void_p), ("mask_shift", C.c_void_p), ("mean", C.c_void_p),
+                ("invstd", C.c_void_p), ("gamma", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("coef", C.c_void_p), ("slots", C.c_void_p), ("ticket", C.c_void_p), ("count", C.c_int64),
+                ("accumulate", C.c_int32)]
+
+
 class MmrHaloSrc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
                 ("N", C.c_int32), ("up", C.c_int32)]
@@ -81,6 +88,7 @@ class MmrHaloConvDesc(C.Structure):
         ("stats", C.c_void_p), ("stats_ld", C.c_int32),
         ("bn_finalize", C.POINTER(MmrBnFinalize)),
         ("rph", C.c_int32),
+        ("bn_bwd", C.POINTER(MmrBnBwdFused)),
     ]
 
 

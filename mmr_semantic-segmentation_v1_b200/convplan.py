@@ -388,7 +388,7 @@ def build_wgrad(dz, sources, ksize, stride, pad, dst, *, cout_gemm=None, dst_cin
 # ------------------------------------------------------------------------------------------
 # Second kernel generation (csrc/conv_halo.cu): 3x3 / stride 1 / pad 1 convolutions.
 # ------------------------------------------------------------------------------------------
-HALO_SMEM = 227 * 1024 - 256
+HALO_SMEM = 227 * 1024 - 1024
 
 
 def _mma_clk(bn):
@@ -554,7 +554,7 @@ def pack_weights_halo(w_oihw, cfg, mode, out=None, stream=None):
 
 
 def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=None, residual=None,
-               relu=False, out_f32=None, stats=None, stats_ld=0, bn_finalize=None):
+               relu=False, out_f32=None, stats=None, stats_ld=0, bn_finalize=None, bn_bwd=None):
     """sources: [(tensor [N,Hs,Ws,Cs] bf16, up)], packed: bf16 weights from pack_weights_halo,
     groups: [(dst tensor [N,H,W,ldc] bf16, coff)] one per store group of cfg['sg'] channels (bf16 NHWC
     mode), or out_f32 = fp32 [N,C,H,W] (head logits)."""
@@ -605,6 +605,9 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     if bn_finalize is not None:
         d.bn_finalize = C.pointer(bn_finalize)
         keep.append(bn_finalize)
+    if bn_bwd is not None:
+        d.bn_bwd = C.pointer(bn_bwd)
+        keep.append(bn_bwd)
     plan = HaloPlan(d, keep)
     plan.cfg = cfg
     return plan
@@ -650,7 +653,7 @@ def dgrad_halo_cfg(dz_shape, sizes, force=None):
     return halo_config(H, W, N, cb, Cz // cb, sum(sizes), False, seg_sizes=list(sizes), force=force)
 
 
-def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None, cfg=None):
+def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None, cfg=None, bn_bwd=None):
     """Data gradient of a 3x3 s1 p1 conv: dz [N,H,W,Cz] bf16 (Cz = Cout padded to 16), grads = one bf16
     tensor [N,H,W,Cs] per source in concat order."""
     N, H, W, Cz = dz.shape
@@ -666,7 +669,7 @@ def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None, cfg=None):
     for g in grads:
         for c in range(0, g.shape[3], cfg["sg"]):
             groups.append((g, c))
-    plan = build_halo(cfg, [(dz, 1)], packed, groups, N, H, W, cin)
+    plan = build_halo(cfg, [(dz, 1)], packed, groups, N, H, W, cin, bn_bwd=bn_bwd)
     plan.flops = 2 * N * H * W * cout * 9 * cin
     plan.packed = packed
     return plan

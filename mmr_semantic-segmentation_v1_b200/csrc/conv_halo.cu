@@ -68,6 +68,7 @@ struct HaloParams {
   double* stats;
   int stats_ld;
   MmrBnFinalize bnf;  // ticket == nullptr: not fused
+  MmrBnBwdFused bb;   // z == nullptr: no fused BatchNorm backward sums
   int dbg;  // diagnostics (MMR_HALO_DBG): 1 no MMA issue, 2 no epilogue work, 4 no halo TMA, 8 no weight TMA
 };
 
@@ -326,9 +327,13 @@ __device__ __forceinline__ void bulk_wait_read_n() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 
-template <int SG, bool STATS, bool PLAIN>
+// STATS: 0 none; 1 forward statistics (sum, sum of squares of the stored values); 2 BatchNorm-backward sums of a
+// data-gradient launch (MmrBnBwdFused): sum g and sum g*z with g = (z*msc + msh > 0) ? dx : 0, msc / msh read from
+// the `bb_affine` staging in shared memory.
+template <int SG, int STATS, bool PLAIN>
 __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base, uint8_t* out_base,
-                                         uint64_t* tmem_full, uint64_t* tmem_empty, int q, int lane) {
+                                         uint64_t* tmem_full, uint64_t* tmem_empty, int q, int lane,
+                                         const float* bb_affine) {
   constexpr bool STAGED = SG == 64;
   constexpr int CH = (STATS && SG > 32) ? 32 : SG;  // accumulator columns per TMEM round trip
   constexpr int orb = SG * 2;                       // staging row bytes
@@ -343,6 +348,18 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
     const ItemCoord ic = decode_item(p, item);
     const int buf = it % p.acc_bufs;
     const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
+    if (STATS == 2) {
+      // the z rows this thread will need for the item go to L2 while the MMAs of the item are still running
+      for (int ir = 0; ir < p.TX * p.R; ++ir) {
+        const int x = ic.x0 + 8 * (ir / p.R) + w, y = ic.y0 + p.R * h + ir % p.R;
+        if (y < p.H && x < p.W) {
+          const __nv_bfloat16* zr = reinterpret_cast<const __nv_bfloat16*>(p.bb.z) +
+                                    (((size_t)ic.n * p.H + y) * p.W + x) * SG;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(zr));
+          if (SG == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(zr + 32));
+        }
+      }
+    }
     mbar_wait(&tmem_full[buf], par);
     tc_fence_after();
     if (p.dbg & 2) {
@@ -377,6 +394,13 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
 #pragma unroll
         for (int c0 = 0; c0 < SG; c0 += CH) {
           uint32_t r[CH];
+          uint4 rz[STATS == 2 ? CH / 8 : 1];
+          if (STATS == 2) {   // the unit's z at the same pixel: in flight while the accumulators are read
+            const uint4* zp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bb.z) +
+                                                             pix * SG + c0);
+#pragma unroll
+            for (int k = 0; k < CH / 8; ++k) rz[k] = valid ? __ldg(zp + k) : make_uint4(0, 0, 0, 0);
+          }
 #pragma unroll
           for (int k = 0; k < CH; k += 16) tmem_ld16(taddr + c0 + k, reinterpret_cast<uint32_t(&)[16]>(r[k]));
           tmem_ld_wait();
@@ -420,7 +444,7 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
           uint32_t o[CH / 2];
 #pragma unroll
           for (int j = 0; j < CH / 2; ++j) o[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
-          if (STATS) {
+          if (STATS == 1) {
 #pragma unroll
             for (int j = 0; j < CH / 2; ++j) {
               const float f0 = __uint_as_float(o[j] << 16), f1 = __uint_as_float(o[j] & 0xffff0000u);
@@ -428,6 +452,25 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
               s2[c0 + 2 * j] = fmaf(f0, f0, s2[c0 + 2 * j]);
               s1[c0 + 2 * j + 1] += f1;
               s2[c0 + 2 * j + 1] = fmaf(f1, f1, s2[c0 + 2 * j + 1]);
+            }
+          }
+          if (STATS == 2) {
+#pragma unroll
+            for (int k = 0; k < CH / 8; ++k) {
+              const uint32_t zw[4] = {rz[k].x, rz[k].y, rz[k].z, rz[k].w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = 4 * k + jj, c = c0 + 2 * j;
+                const float2 a = *reinterpret_cast<const float2*>(bb_affine + c);        // mask scale
+                const float2 b = *reinterpret_cast<const float2*>(bb_affine + SG + c);   // mask shift
+                const float z0 = __uint_as_float(zw[jj] << 16), z1 = __uint_as_float(zw[jj] & 0xffff0000u);
+                const float d0 = __uint_as_float(o[j] << 16), d1 = __uint_as_float(o[j] & 0xffff0000u);
+                const float g0 = fmaf(z0, a.x, b.x) > 0.f ? d0 : 0.f, g1 = fmaf(z1, a.y, b.y) > 0.f ? d1 : 0.f;
+                s1[c] += g0;
+                s2[c] = fmaf(g0, z0, s2[c]);
+                s1[c + 1] += g1;
+                s2[c + 1] = fmaf(g1, z1, s2[c + 1]);
+              }
             }
           }
           if (STAGED) {
@@ -462,7 +505,7 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
   if (STATS) {
     // column sums over the 32 accumulator rows of this warp, then one double atomic per channel
     // and warp into the CTA's statistics slot (lane c % 32 owns channel c)
-    double* slot = p.stats + (size_t)(blockIdx.x & (kStatSlots - 1)) * 2 * p.stats_ld;
+    double* slot = (STATS == 2 ? p.bb.slots : p.stats) + (size_t)(blockIdx.x & (kStatSlots - 1)) * 2 * p.stats_ld;
 #pragma unroll
     for (int c = 0; c < SG; ++c) {
       float a = s1[c], b = s2[c];
@@ -663,12 +706,23 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
                       !p.residual && !p.relu;
     if (head) {
       epi_head_f32(p, tmem_base, tmem_full, tmem_empty, q, lane);
+    } else if (fast && p.bb.z) {
+      // data gradient with the consumer unit's BatchNorm-backward sums: mask scale / shift staged in shared memory
+      float* bb_affine = reinterpret_cast<float*>(bars + 32);
+      for (int c = m; c < p.sg; c += 128) {
+        bb_affine[c] = __ldg(p.bb.mask_scale + c);
+        bb_affine[p.sg + c] = __ldg(p.bb.mask_shift + c);
+      }
+      epi_bar();
+      if (p.sg == 64) epi_fast<64, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
+      if (p.sg == 32) epi_fast<32, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
+      if (p.sg == 16) epi_fast<16, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
     } else if (fast) {
 #define MMR_EPI_CASE2(SG_, ST_, PL_)                                                                   \
-  if (p.sg == SG_ && (p.stats != nullptr) == ST_ && plain == PL_)                                      \
-    epi_fast<SG_, ST_, PL_>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane);
+  if (p.sg == SG_ && (p.stats != nullptr) == (ST_ != 0) && plain == PL_)                               \
+    epi_fast<SG_, ST_, PL_>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
 #define MMR_EPI_CASE(SG_)                                                                              \
-  MMR_EPI_CASE2(SG_, true, true) MMR_EPI_CASE2(SG_, false, true) MMR_EPI_CASE2(SG_, false, false)
+  MMR_EPI_CASE2(SG_, 1, true) MMR_EPI_CASE2(SG_, 0, true) MMR_EPI_CASE2(SG_, 0, false)
       MMR_EPI_CASE(64)
       MMR_EPI_CASE(32)
       MMR_EPI_CASE(16)
@@ -864,6 +918,36 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
           *p.bnf.ticket = 0u;
           if (p.bnf.num_batches_tracked) p.bnf.num_batches_tracked[0] += 1;
         }
+      }
+    }
+    if (p.bb.z) {
+      // fused BatchNorm-backward finalisation (the arithmetic of reduce_rows_kernel's last CTA)
+      uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 30);
+      __threadfence();
+      epi_bar();
+      if (m == 0) *flag = atomicAdd(p.bb.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+      epi_bar();
+      if (*flag) {
+        __threadfence();
+        const int Cn = p.cout_total;
+        for (int c = m; c < Cn; c += 128) {
+          double s1 = 0.0, s2 = 0.0;
+          for (int sl = 0; sl < kStatSlots; ++sl) {
+            double* a = p.bb.slots + (size_t)sl * 2 * p.stats_ld + c;
+            s1 += __ldcg(a);
+            s2 += __ldcg(a + p.stats_ld);
+            a[0] = 0.0;
+            a[p.stats_ld] = 0.0;
+          }
+          s2 = (s2 - (double)p.bb.mean[c] * s1) * (double)p.bb.invstd[c];   // sum g*xhat
+          if (p.bb.dgamma) p.bb.dgamma[c] = (p.bb.accumulate ? p.bb.dgamma[c] : 0.f) + (float)s2;
+          if (p.bb.dbeta) p.bb.dbeta[c] = (p.bb.accumulate ? p.bb.dbeta[c] : 0.f) + (float)s1;
+          const double gi = (double)(p.bb.gamma ? p.bb.gamma[c] : 1.f) * (double)p.bb.invstd[c];
+          p.bb.coef[c] = (float)gi;
+          p.bb.coef[Cn + c] = (float)(-gi * s2 / (double)p.bb.count);
+          p.bb.coef[2 * Cn + c] = (float)(-gi * s1 / (double)p.bb.count);
+        }
+        if (m == 0) *p.bb.ticket = 0u;
       }
     }
     if (p.out_mode == MMR_OUT_BF16_NHWC && !p.direct && m == 0) bulk_wait0();
@@ -1158,7 +1242,7 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   while (cols < (uint32_t)(d->acc_bufs * d->tx * R * d->bn)) cols <<= 1;
   p.tmem_cols = cols;
   size_t smem = (size_t)p.halo_stages * p.halo_stage_bytes + (size_t)p.w_slots * p.w_slot_bytes +
-                (size_t)p.out_stages * p.out_stage_bytes + 256;
+                (size_t)p.out_stages * p.out_stage_bytes + 1024;  // barriers (256 B) + BN-backward mask affine (512 B)
   MMR_REQUIRE(smem <= 227 * 1024, "shared memory plan needs %zu bytes (> 227 KB)", smem);
   if (smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM: the TMEM allocation assumes it
   pl->smem_bytes = smem;
@@ -1173,6 +1257,18 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.stats = d->stats;
   p.stats_ld = d->stats_ld;
   if (const char* dbg = getenv("MMR_HALO_DBG")) p.dbg = atoi(dbg);
+  if (d->bn_bwd) {
+    const MmrBnBwdFused& b = *d->bn_bwd;
+    const bool plain = !d->scale && !d->bias && !d->residual && !d->relu;
+    MMR_REQUIRE(b.z && b.mask_scale && b.mask_shift && b.mean && b.invstd && b.coef && b.slots && b.ticket,
+                "bn_bwd: z, mask_scale, mask_shift, mean, invstd, coef, slots and ticket are required");
+    MMR_REQUIRE(d->out_mode == MMR_OUT_BF16_NHWC && d->n_ntiles == 1 && d->bn == d->sg && plain && !d->stats &&
+                    (d->direct_store != 0) == (d->sg < 64) && d->ngroups == 1 && d->groups[0].ldc == d->sg &&
+                    d->groups[0].coff == 0 && d->groups[0].step <= 1 && d->cout_total == d->sg,
+                "bn_bwd needs one plain bf16 store group that is the whole destination tensor");
+    p.bb = b;
+    p.stats_ld = d->cout_total;
+  }
   if (d->bn_finalize) {
     MMR_REQUIRE(d->stats != nullptr && d->bn_finalize->ticket != nullptr, "bn_finalize needs stats and a ticket");
     p.bnf = *d->bn_finalize;

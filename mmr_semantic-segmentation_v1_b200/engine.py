@@ -487,6 +487,16 @@ class Engine:
 
     # ------------------------------------------------------------------ backward plan
     def _build_backward(self):
+        # how many ops read each activation (sources, residuals, pools, test seeds): a unit whose output has
+        # exactly one reader can have its BatchNorm-backward sums taken by that reader's data-gradient launch
+        self.n_readers = {}
+        for op in self.ops:
+            for name in [n for n, _ in op.get("src", [])] + [op.get("res"), op.get("in")]:
+                if name is not None:
+                    self.n_readers[name] = self.n_readers.get(name, 0) + 1
+        for name in getattr(self, "out_seeds", {}):
+            self.n_readers[name] = self.n_readers.get(name, 0) + 1
+        self.fuse_bwd_reduce = self.fuse_finalize and not os.environ.get("MMR_NO_FUSED_BWD_REDUCE")
         order = list(reversed(self.units))
         t_of = {id(u): t for t, u in enumerate(order)}
         arena = _Arena()
@@ -619,11 +629,14 @@ class Engine:
                     # one full-resolution contribution: the apply pass recomputes the masked gradient from it,
                     # the reduction writes no g at all
                     nog = zmask and cnt == 1 and not out.contribs[0][1] and not os.environ.get("MMR_NO_NOG")
-                    self._rec(calls, "mmr_bn_bwd_reduce_fused", arr, cnt, None if zmask else relu_act, u["z"],
-                              u["mean"], u["invstd"], n, ho, wo, Cc, None if nog else g, self.bwd_slots, nblk,
-                              self.P[bn + ".weight"],
-                              self.G[bn + ".weight"], self.G[bn + ".bias"], acc, u["coef"], u["bwd_ticket"],
-                              u["scale"] if zmask else None, u["shift"] if zmask else None)
+                    if u.get("reduce_done_by_dgrad"):
+                        assert nog    # the reader's data-gradient launch already left dgamma / dbeta / coef
+                    else:
+                        self._rec(calls, "mmr_bn_bwd_reduce_fused", arr, cnt, None if zmask else relu_act, u["z"],
+                                  u["mean"], u["invstd"], n, ho, wo, Cc, None if nog else g, self.bwd_slots, nblk,
+                                  self.P[bn + ".weight"],
+                                  self.G[bn + ".weight"], self.G[bn + ".bias"], acc, u["coef"], u["bwd_ticket"],
+                                  u["scale"] if zmask else None, u["shift"] if zmask else None)
                 else:
                     nog = False
                     self._rec(calls, "mmr_bn_bwd_reduce", arr, cnt, relu_act, u["z"], u["mean"], u["invstd"],
@@ -704,13 +717,34 @@ class Engine:
                 grads.append(None)
         if not all(need):
             raise NotImplementedError("mixed grad / no-grad sources in one conv")
-        dplan = u.get("dplan")
+        # the only reader of a conv -> BN -> ReLU unit's output takes that unit's BatchNorm-backward sums in its
+        # own epilogue (MmrBnBwdFused): one store group that is the whole tensor, same resolution, no residual
+        bb = None
+        src_a, src_up = u["srcs"][0]
+        L = src_a.producer
+        if (self.fuse_bwd_reduce and u.get("halo") and len(u["srcs"]) == 1 and src_up == 1 and L is not None
+                and L.get("kind") == "conv" and L.get("bn") and L["op"]["relu"] and L.get("res") is None
+                and self.n_readers.get(src_a.name, 0) == 1 and L["cout"] == src_a.shape[3]
+                and L["cout"] in (16, 32, 64) and u["dcfg"]["n_ntiles"] == 1 and u["dcfg"]["bn"] == u["dcfg"]["sg"]
+                and int(u["dcfg"].get("direct", u["dcfg"]["sg"] < 64)) == int(u["dcfg"]["sg"] < 64)):
+            bnL = L["bn"]
+            if "bwd_ticket" not in L:
+                L["bwd_ticket"] = self._ticket()
+            bb = _lib.MmrBnBwdFused(
+                L["z"].data_ptr(), L["scale"].data_ptr(), L["shift"].data_ptr(), L["mean"].data_ptr(),
+                L["invstd"].data_ptr(), self.P[bnL + ".weight"].data_ptr(), self.G[bnL + ".weight"].data_ptr(),
+                self.G[bnL + ".bias"].data_ptr(), L["coef"].data_ptr(), self.bwd_slots.data_ptr(),
+                L["bwd_ticket"].data_ptr(), src_a.shape[0] * Hin * Win, acc)
+            L["reduce_done_by_dgrad"] = True
+        key = ("dplan", acc if bb is not None else None)
+        dplan = u.get(key)
         if dplan is None:
             if u.get("halo"):
                 dplan = convplan.build_dgrad_halo(dz, self.P[conv + ".weight"], grads, cfg=u["dcfg"],
-                                                  packed=u["wd_h"])
+                                                  packed=u["wd_h"], bn_bwd=bb)
             else:
                 dplan = convplan.build_dgrad(dz, u["wd"], u["k"], u["s"], u["pad"], (Hin, Win), grads)
+            u[key] = dplan
             u["dplan"] = dplan
         if u.get("halo"):
             calls.append((self.lib.mmr_halo_conv_plan_run, (dplan.handle,)))
