@@ -561,8 +561,13 @@ __device__ __forceinline__ void epi_head_f32(const HaloParams& p, uint32_t tmem_
   }
 }
 
-__global__ void __launch_bounds__(kHaloThreads, 1)
-conv_halo_kernel(const __grid_constant__ HaloParams p) {
+// Epilogue family of a launch.  One __global__ instantiation per family: the register allocation and the code
+// of the statistics / BatchNorm-backward / plain epilogues do not disturb each other (with all of them in one
+// kernel the forward-statistics epilogue of a 64 -> 64 layer ran 20 % slower).
+enum { kEpiOther = 0, kEpiStats = 1, kEpiPlain = 2, kEpiBnBwd = 3 };
+
+template <int EK>
+__device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* halo_base = smem;
@@ -704,9 +709,9 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
                       (p.stats == nullptr || (p.n_ntiles == 1 && p.gpn == 1 && plain));
     const bool head = p.out_mode == MMR_OUT_F32_NCHW && p.bn == 16 && p.n_ntiles == 1 && p.R == 1 && !p.scale &&
                       !p.residual && !p.relu;
-    if (head) {
-      epi_head_f32(p, tmem_base, tmem_full, tmem_empty, q, lane);
-    } else if (fast && p.bb.z) {
+    (void)fast;
+    (void)head;
+    if constexpr (EK == kEpiBnBwd) {
       // data gradient with the consumer unit's BatchNorm-backward sums: mask scale / shift staged in shared memory
       float* bb_affine = reinterpret_cast<float*>(bars + 32);
       for (int c = m; c < p.sg; c += 128) {
@@ -717,17 +722,20 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
       if (p.sg == 64) epi_fast<64, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
       if (p.sg == 32) epi_fast<32, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
       if (p.sg == 16) epi_fast<16, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
-    } else if (fast) {
-#define MMR_EPI_CASE2(SG_, ST_, PL_)                                                                   \
-  if (p.sg == SG_ && (p.stats != nullptr) == (ST_ != 0) && plain == PL_)                               \
-    epi_fast<SG_, ST_, PL_>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
-#define MMR_EPI_CASE(SG_)                                                                              \
-  MMR_EPI_CASE2(SG_, 1, true) MMR_EPI_CASE2(SG_, 0, true) MMR_EPI_CASE2(SG_, 0, false)
-      MMR_EPI_CASE(64)
-      MMR_EPI_CASE(32)
-      MMR_EPI_CASE(16)
-#undef MMR_EPI_CASE
-#undef MMR_EPI_CASE2
+    } else if constexpr (EK == kEpiStats) {
+      if (p.sg == 64) epi_fast<64, 1, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+      if (p.sg == 32) epi_fast<32, 1, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+      if (p.sg == 16) epi_fast<16, 1, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+    } else if constexpr (EK == kEpiPlain) {
+      if (p.sg == 64) epi_fast<64, 0, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+      if (p.sg == 32) epi_fast<32, 0, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+      if (p.sg == 16) epi_fast<16, 0, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+    } else if (head) {
+      epi_head_f32(p, tmem_base, tmem_full, tmem_empty, q, lane);
+    } else if (fast) {   // scale / bias / residual / ReLU epilogues (eval mode, biased convs)
+      if (p.sg == 64) epi_fast<64, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+      if (p.sg == 32) epi_fast<32, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+      if (p.sg == 16) epi_fast<16, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
     } else {
     const int h = m >> 3, w = m & 7;
     const int orb = p.sg * 2;  // staging row bytes
@@ -959,6 +967,11 @@ conv_halo_kernel(const __grid_constant__ HaloParams p) {
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+template <int EK>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<EK>(p);
+}
+
 // ------------------------------------------------------------------ weight packing
 // out[((nt*nchunks + c)*9 + tap)*bn + r][k], bf16.  mode 0 (fprop): N index = output channel,
 // K index = concatenated input channel, filter tap as is.  mode 1 (dgrad): N index = input channel,
@@ -1068,6 +1081,7 @@ static int encode_generic(CUtensorMap* out, const void* ptr, int rank, const cuu
 }
 
 struct HaloPlan {
+  int epi_kind = kEpiOther;
   HaloParams prm;
   void* dev_blob = nullptr;
   size_t smem_bytes = 0;
@@ -1289,8 +1303,27 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.maps = reinterpret_cast<const CUtensorMap*>(pl->dev_blob);
   const int sms = num_sms();
   pl->grid = p.total_items < sms ? p.total_items : sms;
-  e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-  if (e != cudaSuccess) cudaGetLastError();  // tolerated on non-sm_100 devices; the launch will report
+  {
+    // the same predicates the device code used to evaluate: which epilogue family this launch runs
+    const bool plain = !p.scale && !p.bias && !p.residual && !p.relu;
+    const bool fast = p.out_mode == MMR_OUT_BF16_NHWC && (p.direct != 0) == (p.sg < 64) &&
+                      (p.stats == nullptr || (p.n_ntiles == 1 && p.gpn == 1 && plain));
+    if (fast && p.bb.z)
+      pl->epi_kind = kEpiBnBwd;
+    else if (fast && p.stats)
+      pl->epi_kind = kEpiStats;
+    else if (fast && plain)
+      pl->epi_kind = kEpiPlain;
+    else
+      pl->epi_kind = kEpiOther;
+  }
+  for (int k = 0; k < 4; ++k) {
+    e = k == kEpiStats   ? cudaFuncSetAttribute(conv_halo_kernel<kEpiStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
+        : k == kEpiPlain ? cudaFuncSetAttribute(conv_halo_kernel<kEpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
+        : k == kEpiBnBwd ? cudaFuncSetAttribute(conv_halo_kernel<kEpiBnBwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
+                         : cudaFuncSetAttribute(conv_halo_kernel<kEpiOther>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) cudaGetLastError();  // tolerated on non-sm_100 devices; the launch will report
+  }
   *out_plan = pl;
   return 0;
 }
@@ -1299,7 +1332,12 @@ extern "C" int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream) {
   MMR_REQUIRE(plan, "null plan");
   HaloPlan* pl = reinterpret_cast<HaloPlan*>(plan);
   if (pl->prm.total_items == 0) return 0;
-  mmr_launch((conv_halo_kernel), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm);
+  switch (pl->epi_kind) {
+    case kEpiStats: mmr_launch((conv_halo_kernel<kEpiStats>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+    case kEpiPlain: mmr_launch((conv_halo_kernel<kEpiPlain>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+    case kEpiBnBwd: mmr_launch((conv_halo_kernel<kEpiBnBwd>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+    default: mmr_launch((conv_halo_kernel<kEpiOther>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+  }
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
