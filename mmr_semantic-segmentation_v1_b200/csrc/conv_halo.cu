@@ -564,7 +564,7 @@ __device__ __forceinline__ void epi_head_f32(const HaloParams& p, uint32_t tmem_
 // Epilogue family of a launch.  One __global__ instantiation per family: the register allocation and the code
 // of the statistics / BatchNorm-backward / plain epilogues do not disturb each other (with all of them in one
 // kernel the forward-statistics epilogue of a 64 -> 64 layer ran 20 % slower).
-enum { kEpiOther = 0, kEpiStats = 1, kEpiPlain = 2, kEpiBnBwd = 3 };
+enum { kEpiOther = 0, kEpiStats = 1, kEpiPlain = 2, kEpiBnBwd = 3, kEpiAffine = 4, kEpiHead = 5, kEpiKinds = 6 };
 
 template <int EK>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
@@ -730,9 +730,9 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       if (p.sg == 64) epi_fast<64, 0, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
       if (p.sg == 32) epi_fast<32, 0, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
       if (p.sg == 16) epi_fast<16, 0, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
-    } else if (head) {
+    } else if constexpr (EK == kEpiHead) {
       epi_head_f32(p, tmem_base, tmem_full, tmem_empty, q, lane);
-    } else if (fast) {   // scale / bias / residual / ReLU epilogues (eval mode, biased convs)
+    } else if constexpr (EK == kEpiAffine) {   // scale / bias / residual / ReLU epilogues (eval mode, biased convs)
       if (p.sg == 64) epi_fast<64, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
       if (p.sg == 32) epi_fast<32, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
       if (p.sg == 16) epi_fast<16, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
@@ -1308,21 +1308,29 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
     const bool plain = !p.scale && !p.bias && !p.residual && !p.relu;
     const bool fast = p.out_mode == MMR_OUT_BF16_NHWC && (p.direct != 0) == (p.sg < 64) &&
                       (p.stats == nullptr || (p.n_ntiles == 1 && p.gpn == 1 && plain));
+    const bool head = p.out_mode == MMR_OUT_F32_NCHW && p.bn == 16 && p.n_ntiles == 1 && p.R == 1 && !p.scale &&
+                      !p.residual && !p.relu;
     if (fast && p.bb.z)
       pl->epi_kind = kEpiBnBwd;
     else if (fast && p.stats)
       pl->epi_kind = kEpiStats;
     else if (fast && plain)
       pl->epi_kind = kEpiPlain;
+    else if (fast)
+      pl->epi_kind = kEpiAffine;
+    else if (head)
+      pl->epi_kind = kEpiHead;
     else
       pl->epi_kind = kEpiOther;
   }
-  for (int k = 0; k < 4; ++k) {
-    e = k == kEpiStats   ? cudaFuncSetAttribute(conv_halo_kernel<kEpiStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
-        : k == kEpiPlain ? cudaFuncSetAttribute(conv_halo_kernel<kEpiPlain>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
-        : k == kEpiBnBwd ? cudaFuncSetAttribute(conv_halo_kernel<kEpiBnBwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
-                         : cudaFuncSetAttribute(conv_halo_kernel<kEpiOther>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
-    if (e != cudaSuccess) cudaGetLastError();  // tolerated on non-sm_100 devices; the launch will report
+  {
+    const void* fns[kEpiKinds] = {(const void*)conv_halo_kernel<kEpiOther>, (const void*)conv_halo_kernel<kEpiStats>,
+                                  (const void*)conv_halo_kernel<kEpiPlain>, (const void*)conv_halo_kernel<kEpiBnBwd>,
+                                  (const void*)conv_halo_kernel<kEpiAffine>, (const void*)conv_halo_kernel<kEpiHead>};
+    for (int k = 0; k < kEpiKinds; ++k) {
+      e = cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+      if (e != cudaSuccess) cudaGetLastError();  // tolerated on non-sm_100 devices; the launch will report
+    }
   }
   *out_plan = pl;
   return 0;
@@ -1336,6 +1344,8 @@ extern "C" int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream) {
     case kEpiStats: mmr_launch((conv_halo_kernel<kEpiStats>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
     case kEpiPlain: mmr_launch((conv_halo_kernel<kEpiPlain>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
     case kEpiBnBwd: mmr_launch((conv_halo_kernel<kEpiBnBwd>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+    case kEpiAffine: mmr_launch((conv_halo_kernel<kEpiAffine>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+    case kEpiHead: mmr_launch((conv_halo_kernel<kEpiHead>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
     default: mmr_launch((conv_halo_kernel<kEpiOther>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
   }
   MMR_CUDA_CHECK(cudaGetLastError());
