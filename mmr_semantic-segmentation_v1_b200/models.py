@@ -138,10 +138,33 @@ class _PlanModel(nn.Module):
         self._input_norm = None      # (mean, std) applied on the device to uint8 frames
 
     # ---- flat parameter storage ------------------------------------------------------------
+    def _named_params(self):
+        """(name, Parameter) pairs, cached: walking the module tree five times per step cost more host time than
+        launching the step's two CUDA graphs.  Parameter objects survive .to() / .cuda() / load_state_dict (only
+        their .data moves); assigning a new submodule or Parameter invalidates the cache through __setattr__."""
+        cached = self.__dict__.get("_named_params_cache")
+        if cached is None:
+            cached = list(super().named_parameters())
+            self.__dict__["_named_params_cache"] = cached
+        return cached
+
+    def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
+        """The reference's loops (`for param in model.parameters(): param.grad = None`, SU/ModelTraining.py:610)
+        hit the cached list as well."""
+        if prefix == "" and recurse and remove_duplicate:
+            return iter(self._named_params())
+        return super().named_parameters(prefix, recurse, remove_duplicate)
+
+    def __setattr__(self, name, value):
+        if isinstance(value, (nn.Module, nn.Parameter)):
+            self.__dict__["_named_params_cache"] = None
+        super().__setattr__(name, value)
+
     def _flatten(self, device):
         """Re-home every parameter into one fp32 buffer (so Adam and the gradient all-reduce are
         single launches) and create the matching flat gradient buffer."""
-        named = list(self.named_parameters())
+        self.__dict__["_named_params_cache"] = None
+        named = self._named_params()
         offs, total = [], 0
         for _, p in named:
             offs.append(total)
@@ -161,9 +184,9 @@ class _PlanModel(nn.Module):
         self._engines = {}
 
     def _ensure_flat(self, device):
-        ptrs = [p.data_ptr() for p in self.parameters()]
+        ptrs = [p.data_ptr() for _, p in self._named_params()]
         if self._flat is None or ptrs != self._flat_ptrs or self._flat.device != device:
-            for p in self.parameters():
+            for _, p in self._named_params():
                 if p.dtype != torch.float32:
                     raise _lib.MmrError("parameters must stay fp32 masters (the kernels compute in "
                                         "bf16 with fp32 accumulate on their own); got %s" % p.dtype)
@@ -175,11 +198,11 @@ class _PlanModel(nn.Module):
     def _grads_live(self):
         """True when every .grad is still our view (gradient accumulation step)."""
         used = getattr(self, "_plan_params", None)
-        live = [p.grad is not None for n, p in self.named_parameters() if used is None or n in used]
+        live = [p.grad is not None for n, p in self._named_params() if used is None or n in used]
         if not any(live):
             return False
         if all(live) and all(p.grad.data_ptr() == self._gviews[n].data_ptr()
-                             for n, p in self.named_parameters() if p.grad is not None):
+                             for n, p in self._named_params() if p.grad is not None):
             return True
         raise _lib.MmrError("parameter .grad tensors were replaced; call zero_grad(set_to_none=True) "
                             "(or leave them untouched) between backward passes")
@@ -190,7 +213,7 @@ class _PlanModel(nn.Module):
         used = getattr(self, "_plan_params", None)
         if used is None:
             used = self._plan_params = set(graph.graph_param_names(self._graph()))
-        for n, p in self.named_parameters():
+        for n, p in self._named_params():
             if p.grad is None and n in used:
                 p.grad = self._gviews[n]
 
@@ -237,7 +260,7 @@ class _PlanModel(nn.Module):
             x = x.float()
         if self.training and torch.is_grad_enabled():
             self._ensure_flat(x.device)
-            out = _PlanFunction.apply(self, x.contiguous(), *self.parameters())
+            out = _PlanFunction.apply(self, x.contiguous(), *[p for _, p in self._named_params()])
             return list(out) if isinstance(out, tuple) else out
         eng = self._engine_for(x, training=self.training)
         return eng.forward(x.contiguous())

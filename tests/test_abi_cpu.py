@@ -108,3 +108,17 @@ def test_arena_never_overlaps_live_buffers():
             if i < j and not (a1 < b0 or b1 < a0):            # lifetimes intersect
                 assert off[i] + s <= off[j] or off[j] + s2 <= off[i], (i, j)
     assert peak < sum(s for _, s, _, _ in reqs)
+
+
+def test_cached_parameter_list_matches_module_tree():
+    """Plan models answer named_parameters() / parameters() from a cached list (the reference's per-step loops walk
+    it): same names and order as nn.Module's traversal, shared modules de-duplicated, invalidated by assignment."""
+    import torch
+    from mmrseg_b200.models import ResNetUNet, UNet, UnetPlusPlus
+    for m in (UnetPlusPlus("resnet18", classes=2), ResNetUNet(3, 18), UNet(3, 2, bilinear=True)):
+        want = [n for n, _ in torch.nn.Module.named_parameters(m)]
+        assert [n for n, _ in m.named_parameters()] == want
+        assert [id(p) for p in m.parameters()] == [id(p) for _, p in torch.nn.Module.named_parameters(m)]
+        assert [n for n, _ in m.named_parameters(prefix="net")] == ["net." + n for n in want]
+        m.extra = torch.nn.Linear(2, 2)
+        assert len(list(m.parameters())) == len(want) + 2
