@@ -414,13 +414,25 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
 #pragma unroll
           for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
           if (!PLAIN) {
-            if (p.scale) {
+            if (bb_affine) {   // one channel set per CTA: scale / shift staged in shared memory (broadcast reads)
 #pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] *= __ldg(p.scale + min(ch0 + c0 + j, p.cout_total - 1));
-            }
-            if (p.bias) {
+              for (int k = 0; k < CH / 4; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(bb_affine + c0 + 4 * k);
+                const float4 b = *reinterpret_cast<const float4*>(bb_affine + SG + c0 + 4 * k);
+                v[4 * k] = fmaf(v[4 * k], a.x, b.x);
+                v[4 * k + 1] = fmaf(v[4 * k + 1], a.y, b.y);
+                v[4 * k + 2] = fmaf(v[4 * k + 2], a.z, b.z);
+                v[4 * k + 3] = fmaf(v[4 * k + 3], a.w, b.w);
+              }
+            } else {
+              if (p.scale) {
 #pragma unroll
-              for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + min(ch0 + c0 + j, p.cout_total - 1));
+                for (int j = 0; j < CH; ++j) v[j] *= __ldg(p.scale + min(ch0 + c0 + j, p.cout_total - 1));
+              }
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + min(ch0 + c0 + j, p.cout_total - 1));
+              }
             }
             if (p.residual && valid) {
               const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_ldc + ch0 + c0);
@@ -733,9 +745,19 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     } else if constexpr (EK == kEpiHead) {
       epi_head_f32(p, tmem_base, tmem_full, tmem_empty, q, lane);
     } else if constexpr (EK == kEpiAffine) {   // scale / bias / residual / ReLU epilogues (eval mode, biased convs)
-      if (p.sg == 64) epi_fast<64, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
-      if (p.sg == 32) epi_fast<32, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
-      if (p.sg == 16) epi_fast<16, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+      float* aff = nullptr;
+      if (p.n_ntiles == 1 && p.gpn == 1) {     // the whole channel set is one store group: stage scale / shift once
+        aff = reinterpret_cast<float*>(bars + 32);
+        for (int c = m; c < p.sg; c += 128) {
+          const int cc = min(c, p.cout_total - 1);
+          aff[c] = p.scale ? __ldg(p.scale + cc) : 1.f;
+          aff[p.sg + c] = p.bias ? __ldg(p.bias + cc) : 0.f;
+        }
+        epi_bar();
+      }
+      if (p.sg == 64) epi_fast<64, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, aff);
+      if (p.sg == 32) epi_fast<32, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, aff);
+      if (p.sg == 16) epi_fast<16, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, aff);
     } else {
     const int h = m >> 3, w = m & 7;
     const int orb = p.sg * 2;  // staging row bytes
