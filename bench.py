@@ -158,14 +158,16 @@ def kernels_per_call(lib, fn):
 
 def conv_kernel_time(eng, n_iter=3):
     """CUDA-event time of every implicit-GEMM conv launch (fprop + dgrad: conv_halo_kernel for the 3x3
-    stride-1 layers, conv_gemm_tc_kernel for the strided / 1x1 / stem ones) of one step, on the
-    launching stream; returns (ms per step spent in those kernels, launches per step)."""
+    stride-1 layers and the stem, conv_gemm_tc_kernel for the strided / 1x1 ones) of one step, on the
+    launching stream; returns (ms per step spent in those kernels, launches per step, ms and launches of the
+    dgrad launches whose epilogue also takes a BatchNorm-backward reduction)."""
     lib = eng.lib
     stream = torch.cuda.current_stream()
     s = stream.cuda_stream
     import ctypes as C
     sp = C.c_void_p(s)
-    total_ms, launches = 0.0, 0
+    fused = getattr(eng, "fused_dgrad_handles", set())
+    total_ms, launches, fused_ms, fused_n = 0.0, 0, 0.0, 0
     for it in range(n_iter):
         evs = []
         for calls in (eng.repack_calls, eng.fwd_calls, eng.bwd_calls[False]):
@@ -175,14 +177,15 @@ def conv_kernel_time(eng, n_iter=3):
                     e0.record(stream)
                     fn(*a, sp)
                     e1.record(stream)
-                    evs.append((e0, e1))
+                    evs.append((e0, e1, getattr(a[0], "value", None) in fused))
                 else:
                     fn(*a, sp)
         torch.cuda.synchronize()
         if it > 0:
-            total_ms += sum(a.elapsed_time(b) for a, b in evs)
-            launches = len(evs)
-    return total_ms / (n_iter - 1), launches
+            total_ms += sum(a.elapsed_time(b) for a, b, _ in evs)
+            fused_ms += sum(a.elapsed_time(b) for a, b, f in evs if f)
+            launches, fused_n = len(evs), sum(1 for _, _, f in evs if f)
+    return total_ms / (n_iter - 1), launches, fused_ms / (n_iter - 1), fused_n
 
 
 def run_ours(args):
@@ -296,10 +299,15 @@ def run_ours(args):
     line = None
     if rank == 0:
         pk = peaks()
-        conv_ms, conv_launches = conv_kernel_time(eng)
+        conv_ms, conv_launches, fused_ms, fused_n = conv_kernel_time(eng)
         conv_flops = sum(u["fplan"].flops for u in eng.units if "fplan" in u) + \
             sum(u["dplan"].flops for u in eng.units if "dplan" in u)
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+        # the same without the dgrad launches that also carry a BatchNorm-backward reduction (separate kernel
+        # instantiation conv_halo_kernel<3>, extra HBM reads and ALU work that are not conv FLOPs)
+        fused_flops = sum(u["dplan"].flops for u in eng.units
+                          if "dplan" in u and getattr(u["dplan"].handle, "value", None) in eng.fused_dgrad_handles)
+        conv_only = (conv_flops - fused_flops) / ((conv_ms - fused_ms) * 1e-3) / 1e12 if conv_ms > fused_ms else None
         lib = eng.lib
         per_step = sum(kernels_per_call(lib, fn) for calls in (eng.repack_calls, eng.fwd_calls, eng.bwd_calls[False])
                        for fn, _ in calls) + 3 + 1   # + loss fwd (2 kernels) + loss bwd + Adam
@@ -328,7 +336,11 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "conv_halo_kernel + conv_gemm_tc_kernel (all fprop + dgrad launches of a step; their epilogues also take the BatchNorm batch statistics (fprop) and the BatchNorm-backward sums of single-reader units (dgrad), which is not counted as work)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                          "traffic": traffic, "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
-                         "algorithmic_tflop_per_step": conv_flops / 1e12, "peak_source": pk["src"]},
+                         "algorithmic_tflop_per_step": conv_flops / 1e12, "peak_source": pk["src"],
+                         "conv_only_launches": {"launches": conv_launches - fused_n, "achieved": conv_only,
+                                                "frac": conv_only / pk["tflops"] if conv_only else None,
+                                                "note": "excluding the %d dgrad launches (conv_halo_kernel<3>) whose epilogue "
+                                                        "also reduces a BatchNorm backward" % fused_n}},
             "step_tensor_frac": step_flops / (ms / args.steps * 1e-3) / 1e12 / pk["tflops"],
         }
     if world > 1:

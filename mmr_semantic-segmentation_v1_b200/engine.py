@@ -497,6 +497,7 @@ class Engine:
         for name in getattr(self, "out_seeds", {}):
             self.n_readers[name] = self.n_readers.get(name, 0) + 1
         self.fuse_bwd_reduce = self.fuse_finalize and not os.environ.get("MMR_NO_FUSED_BWD_REDUCE")
+        self.fused_dgrad_handles = set()   # data-gradient plans that also take a BatchNorm-backward reduction
         order = list(reversed(self.units))
         t_of = {id(u): t for t, u in enumerate(order)}
         arena = _Arena()
@@ -746,6 +747,8 @@ class Engine:
                 dplan = convplan.build_dgrad(dz, u["wd"], u["k"], u["s"], u["pad"], (Hin, Win), grads)
             u[key] = dplan
             u["dplan"] = dplan
+            if bb is not None:
+                self.fused_dgrad_handles.add(dplan.handle.value)
         if u.get("halo"):
             calls.append((self.lib.mmr_halo_conv_plan_run, (dplan.handle,)))
         else:
