@@ -35,6 +35,30 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// 32-byte global accesses (LDG.256 / STG.256, sm_100+): the streaming BatchNorm passes measured 6.3-6.5 TB/s
+// with these against 5.5-5.6 TB/s with 16-byte ones (scripts/probe/ew_stream_probe.cu; cudaMemcpy D2D 5.9).
+struct alignas(32) Words8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ Words8 ld256(const __nv_bfloat16* p) {
+  Words8 r;
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st256(__nv_bfloat16* p, const Words8& r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
+               "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
+}
+// Per-channel constants of the 16-channel passes live in shared memory as [C/16][NA][16] floats with every
+// 16-channel block skewed by 4 floats, so the float4 reads of the (up to eight) channel groups a warp touches
+// fall into different banks.
+template <int NA>
+__host__ __device__ constexpr int coef16_stride() { return NA * 16 + 4; }
+
 // Sum of all contributions at pixel (n,y,x), channels [c, c+8).
 __device__ __forceinline__ void gather8(const ContribList& cl, int n, int y, int x, int c, int H,
                                         int W, int C, float (&g)[8]) {
@@ -76,6 +100,13 @@ static int ew_blocks(int64_t work_items, int cap_mult = 8) {
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
+}
+
+// The 16-channel (32-byte) passes need C % 16 == 0, 32-byte aligned tensors and constants that fit the default
+// 48 KB of dynamic shared memory; everything else takes the 8-channel kernels.
+static bool ew16_ok(int C, int n_arrays, const void* a, const void* b, const void* c) {
+  if (C % 16 != 0 || (size_t)(C / 16) * (n_arrays * 16 + 4) * sizeof(float) > 48 * 1024) return false;
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 31) == 0;
 }
 
 // ------------------------------------------------------------------ packing
@@ -700,6 +731,51 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int64_t P, int C,
   }
 }
 
+// 16 channels (32 bytes) per thread and step; constants in shared memory (any grid size works).
+template <bool RES>
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply16_kernel(const __nv_bfloat16* __restrict__ z, int64_t total, int C, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
+                  __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float sc[];
+  constexpr int S = coef16_stride<2>();
+  pdl_prologue();
+  for (int t = threadIdx.x; t < C; t += blockDim.x) {
+    float* d = sc + (t >> 4) * S + (t & 15);
+    d[0] = scale[t];
+    d[16] = shift[t];
+  }
+  __syncthreads();
+  const uint32_t groups = (uint32_t)C / 16;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t gi = (uint32_t)(i % groups);
+  const uint32_t gstep = (uint32_t)(stride % groups);
+  for (; i < total; i += stride) {
+    const Words8 zv = ld256(z + i * 16);
+    Words8 rv;
+    if (RES) rv = ld256(residual + i * 16);
+    const float* k = sc + gi * S;
+    Words8 o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(k + 4 * q), b = *reinterpret_cast<const float4*>(k + 16 + 4 * q);
+      const float2 z0 = unpack_bf16x2(zv.v[2 * q]), z1 = unpack_bf16x2(zv.v[2 * q + 1]);
+      float v0 = fmaf(z0.x, a.x, b.x), v1 = fmaf(z0.y, a.y, b.y), v2 = fmaf(z1.x, a.z, b.z), v3 = fmaf(z1.y, a.w, b.w);
+      if (RES) {
+        const float2 r0 = unpack_bf16x2(rv.v[2 * q]), r1 = unpack_bf16x2(rv.v[2 * q + 1]);
+        v0 += r0.x, v1 += r0.y, v2 += r1.x, v3 += r1.y;
+      }
+      if (relu) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
+      o.v[2 * q] = pack_bf16x2(v0, v1);
+      o.v[2 * q + 1] = pack_bf16x2(v2, v3);
+    }
+    st256(out + i * 16, o);
+    gi += gstep;
+    if (gi >= groups) gi -= groups;
+  }
+}
+
 // ------------------------------------------------------------------ BatchNorm backward
 // With g = dL/d(bn output) already masked by ReLU, xhat = (z-mean)*invstd, M = N*H*W:
 //   dgamma = sum g*xhat,  dbeta = sum g,
@@ -820,6 +896,59 @@ bn_bwd_apply_masked_kernel(const __nv_bfloat16* __restrict__ dx, const __nv_bflo
       }
       store8(dz + i1 * 8, o);
     }
+  }
+}
+
+// Both backward apply passes with 16 channels (32 bytes) per thread and step, constants in shared memory.
+template <bool MASKED>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply16_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ z,
+                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                      const float* __restrict__ coef, const float* __restrict__ msc, const float* __restrict__ msh,
+                      int64_t total, int C, __nv_bfloat16* __restrict__ dz) {
+  extern __shared__ float sc[];
+  constexpr int S = coef16_stride<MASKED ? 5 : 3>();
+  pdl_prologue();
+  for (int t = threadIdx.x; t < C; t += blockDim.x) {
+    float* d = sc + (t >> 4) * S + (t & 15);
+    const float is = invstd[t], cb = coef[C + t];
+    d[0] = coef[t];
+    d[16] = cb * is;
+    d[32] = coef[2 * C + t] - cb * mean[t] * is;
+    if (MASKED) {
+      d[48] = msc[t];
+      d[64] = msh[t];
+    }
+  }
+  __syncthreads();
+  const uint32_t groups = (uint32_t)C / 16;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t gi = (uint32_t)(i % groups);
+  const uint32_t gstep = (uint32_t)(stride % groups);
+  for (; i < total; i += stride) {
+    const Words8 gv = ld256(g + i * 16), zv = ld256(z + i * 16);
+    const float* k = sc + gi * S;
+    Words8 o;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 ca = *reinterpret_cast<const float4*>(k + 4 * q), pz = *reinterpret_cast<const float4*>(k + 16 + 4 * q),
+                   qq = *reinterpret_cast<const float4*>(k + 32 + 4 * q);
+      const float2 z0 = unpack_bf16x2(zv.v[2 * q]), z1 = unpack_bf16x2(zv.v[2 * q + 1]);
+      float2 g0 = unpack_bf16x2(gv.v[2 * q]), g1 = unpack_bf16x2(gv.v[2 * q + 1]);
+      if (MASKED) {
+        const float4 ms = *reinterpret_cast<const float4*>(k + 48 + 4 * q), mh = *reinterpret_cast<const float4*>(k + 64 + 4 * q);
+        g0.x = fmaf(z0.x, ms.x, mh.x) > 0.f ? g0.x : 0.f;
+        g0.y = fmaf(z0.y, ms.y, mh.y) > 0.f ? g0.y : 0.f;
+        g1.x = fmaf(z1.x, ms.z, mh.z) > 0.f ? g1.x : 0.f;
+        g1.y = fmaf(z1.y, ms.w, mh.w) > 0.f ? g1.y : 0.f;
+      }
+      o.v[2 * q] = pack_bf16x2(ca.x * g0.x + pz.x * z0.x + qq.x, ca.y * g0.y + pz.y * z0.y + qq.y);
+      o.v[2 * q + 1] = pack_bf16x2(ca.z * g1.x + pz.z * z1.x + qq.z, ca.w * g1.y + pz.w * z1.y + qq.w);
+    }
+    st256(dz + i * 16, o);
+    gi += gstep;
+    if (gi >= groups) gi -= groups;
   }
 }
 
@@ -1346,6 +1475,19 @@ extern "C" int mmr_bn_finalize(const double* partial, int nblk, int64_t P, int C
 extern "C" int mmr_bn_apply(const void* z, int64_t P, int C, const float* scale, const float* shift,
                             const void* residual, int relu, void* out, mmr_stream_t stream) {
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  if (ew16_ok(C, 2, z, residual, out)) {
+    const int64_t total = P * (C / 16);
+    const size_t smem = (size_t)(C / 16) * coef16_stride<2>() * sizeof(float);
+    const __nv_bfloat16 *zp = reinterpret_cast<const __nv_bfloat16*>(z), *rp = reinterpret_cast<const __nv_bfloat16*>(residual);
+    if (residual)
+      mmr_launch((bn_apply16_kernel<true>), ew_blocks(total, 32), kEwThreads, smem, as_stream(stream), zp, total, C,
+                 scale, shift, rp, relu, reinterpret_cast<__nv_bfloat16*>(out));
+    else
+      mmr_launch((bn_apply16_kernel<false>), ew_blocks(total, 32), kEwThreads, smem, as_stream(stream), zp, total, C,
+                 scale, shift, rp, relu, reinterpret_cast<__nv_bfloat16*>(out));
+    MMR_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
   if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
     mmr_launch((bn_apply_kernel<true>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(z), P, C, scale, shift,
@@ -1384,6 +1526,15 @@ extern "C" int mmr_bn_bwd_finalize(const double* partial, int nblk, int64_t P, i
 extern "C" int mmr_bn_bwd_apply(const void* g, const void* z, const float* mean, const float* invstd,
                                 const float* coef, int64_t P, int C, void* dz, mmr_stream_t stream) {
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  if (ew16_ok(C, 3, g, z, dz)) {
+    const int64_t total = P * (C / 16);
+    mmr_launch((bn_bwd_apply16_kernel<false>), ew_blocks(total, 32), kEwThreads,
+               (size_t)(C / 16) * coef16_stride<3>() * sizeof(float), as_stream(stream),
+               reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,
+               (const float*)nullptr, (const float*)nullptr, total, C, reinterpret_cast<__nv_bfloat16*>(dz));
+    MMR_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
   if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
     mmr_launch((bn_bwd_apply_kernel<true>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(g), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd,
@@ -1399,6 +1550,15 @@ extern "C" int mmr_bn_bwd_apply_masked(const void* dx, const void* z, const floa
                                        const float* coef, const float* mask_scale, const float* mask_shift,
                                        int64_t P, int C, void* dz, mmr_stream_t stream) {
   MMR_REQUIRE(C % 8 == 0 && mask_scale && mask_shift, "C must be a multiple of 8; mask_scale / mask_shift required");
+  if (ew16_ok(C, 5, dx, z, dz)) {
+    const int64_t total = P * (C / 16);
+    mmr_launch((bn_bwd_apply16_kernel<true>), ew_blocks(total, 32), kEwThreads,
+               (size_t)(C / 16) * coef16_stride<5>() * sizeof(float), as_stream(stream),
+               reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,
+               mask_scale, mask_shift, total, C, reinterpret_cast<__nv_bfloat16*>(dz));
+    MMR_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   const int blocks = ew_blocks((P * (C / 8) + 1) / 2, 16);
   if (((int64_t)blocks * kEwThreads) % (C / 8) == 0)
     mmr_launch((bn_bwd_apply_masked_kernel<true>), blocks, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(dx), reinterpret_cast<const __nv_bfloat16*>(z), mean, invstd, coef,

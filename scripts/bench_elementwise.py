@@ -54,9 +54,12 @@ for H, Cc, pools in SHAPES:
     t_red = timeit(lambda: lib.mmr_bn_bwd_reduce(arr, len(pools), vp(a), vp(z), vp(st[0]), vp(st[1]), N, H, H, Cc,
                                                  vp(g), vp(partial), nblk, s))
     t_bap = timeit(lambda: lib.mmr_bn_bwd_apply(vp(g), vp(z), vp(st[0]), vp(st[1]), vp(st[4]), P, Cc, vp(dz), s))
+    t_bam = timeit(lambda: lib.mmr_bn_bwd_apply_masked(vp(contribs[0] if not pools[0] else g), vp(z), vp(st[0]), vp(st[1]),
+                                                       vp(st[4]), vp(st[2]), vp(st[3]), P, Cc, vp(dz), s))
     t_app = timeit(lambda: lib.mmr_bn_apply(vp(z), P, Cc, vp(st[2]), vp(st[3]), None, 1, vp(a), s))
     t_sta = timeit(lambda: lib.mmr_bn_stats(vp(z), P, Cc, vp(partial), nblk, s))
     print("H %4d C %4d pools %-14s reduce %7.1f us %5.2f TB/s | bwd_apply %6.1f us %5.2f TB/s | apply %6.1f us %5.2f TB/s"
-          " | stats %6.1f us %5.2f TB/s" % (H, Cc, pools, t_red * 1e3, (cb + 3 * el) / t_red / 1e9, t_bap * 1e3,
-                                            3 * el / t_bap / 1e9, t_app * 1e3, 2 * el / t_app / 1e9, t_sta * 1e3,
-                                            el / t_sta / 1e9), flush=True)
+          " | stats %6.1f us %5.2f TB/s | bwd_apply_masked %6.1f us %5.2f TB/s" % (
+              H, Cc, pools, t_red * 1e3, (cb + 3 * el) / t_red / 1e9, t_bap * 1e3,
+              3 * el / t_bap / 1e9, t_app * 1e3, 2 * el / t_app / 1e9, t_sta * 1e3,
+              el / t_sta / 1e9, t_bam * 1e3, 3 * el / t_bam / 1e9), flush=True)

@@ -36,7 +36,8 @@ def _contribs(items):
     return arr
 
 
-@pytest.mark.parametrize("shape", [(4, 16, 16, 64), (2, 32, 32, 16), (3, 8, 8, 512), (2, 24, 40, 128)])
+# C % 16 == 0 takes the 32-byte apply kernels, C = 8 the 8-channel ones
+@pytest.mark.parametrize("shape", [(4, 16, 16, 64), (2, 32, 32, 16), (3, 8, 8, 512), (2, 24, 40, 128), (2, 10, 6, 8)])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_bn_forward_backward(shape, with_res):
     L = _lib()
@@ -92,6 +93,36 @@ def test_bn_forward_backward(shape, with_res):
     assert rel(_nchw(dz), zf.grad) < 1e-2, rel(_nchw(dz), zf.grad)
     if with_res:
         assert rel(_nchw(g), resf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("c", [16, 48, 80, 24, 256])
+def test_bn_apply_passes_any_channel_count(c):
+    """The three streaming apply passes against their formulas (fp32 on the same bf16 inputs, bf16 output rounding)
+    for channel counts whose 16-channel groups are not a power of two (48, 80), for the 8-channel kernels (24)
+    and with a grid that wraps the channel groups (256), with and without residual / ReLU."""
+    L = _lib()
+    lib = L.lib()
+    gen = torch.Generator(device="cuda").manual_seed(c)
+    P = 3 * 37 * 29
+    z = (torch.randn((P, c), generator=gen, device="cuda") * 1.5).to(torch.bfloat16)
+    g = torch.randn((P, c), generator=gen, device="cuda").to(torch.bfloat16)
+    res = torch.randn((P, c), generator=gen, device="cuda").to(torch.bfloat16)
+    st = torch.randn((7, c), generator=gen, device="cuda")    # mean, invstd, scale, shift, cA, cB, cC
+    st[1] = st[1].abs() + 0.5
+    out = torch.empty((P, c), device="cuda", dtype=torch.bfloat16)
+    zf, gf = z.float(), g.float()
+    close = lambda a, b: torch.allclose(a.float(), b, rtol=1e-2, atol=1e-2)
+    for r, relu in ((None, 1), (res, 1), (res, 0), (None, 0)):
+        L.check(lib.mmr_bn_apply(_p(z), P, c, _p(st[2]), _p(st[3]), _p(r), relu, _p(out), _s()))
+        want = zf * st[2] + st[3] + (r.float() if r is not None else 0)
+        assert close(out, torch.relu(want) if relu else want)
+    xhat = (zf - st[0]) * st[1]
+    L.check(lib.mmr_bn_bwd_apply(_p(g), _p(z), _p(st[0]), _p(st[1]), _p(st[4]), P, c, _p(out), _s()))
+    assert close(out, st[4] * gf + st[5] * xhat + st[6])
+    L.check(lib.mmr_bn_bwd_apply_masked(_p(g), _p(z), _p(st[0]), _p(st[1]), _p(st[4]), _p(st[2]), _p(st[3]), P, c,
+                                        _p(out), _s()))
+    gm = torch.where(torch.addcmul(st[3], zf, st[2]) > 0, gf, torch.zeros_like(gf))
+    assert close(out, st[4] * gm + st[5] * xhat + st[6])
 
 
 def test_bn_bwd_reduce_fused_mask_from_z():
