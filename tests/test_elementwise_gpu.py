@@ -208,7 +208,8 @@ def test_grad_gather_pool2_and_mask():
     assert torch.allclose(sums.float(), want.sum((0, 2, 3)), rtol=1e-3, atol=1e-2)
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 14, 10, 64)])
+# even H and W: the 2x2-block backward kernel; odd sizes and three contributions: the per-pixel one
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 14, 10, 64), (2, 13, 9, 16), (1, 12, 15, 8), (3, 2, 2, 8)])
 def test_maxpool(shape):
     L = _lib()
     lib = L.lib()
@@ -230,6 +231,15 @@ def test_maxpool(shape):
     L.check(lib.mmr_maxpool3x3s2_bwd(arr, 1, _p(idx), n, h, w, c, _p(gin), _s()))
     torch.cuda.synchronize()
     assert (_nchw(gin) - xf.grad).abs().max().item() <= 0.03
+    # several contributions are summed in front of the routing
+    extra = [torch.randn((n, ho, wo, c), generator=gen, device="cuda").to(torch.bfloat16) for _ in range(2)]
+    for k in (2, 3):
+        gs = [g] + extra[:k - 1]
+        xf.grad = None
+        F.max_pool2d(xf, 3, 2, 1).backward(sum(_nchw(t) for t in gs))
+        L.check(lib.mmr_maxpool3x3s2_bwd(_contribs([(t, 0) for t in gs]), k, _p(idx), n, h, w, c, _p(gin), _s()))
+        torch.cuda.synchronize()
+        assert (_nchw(gin) - xf.grad).abs().max().item() <= 0.06
 
 
 def test_pack_unpack_im2col_headprep():
@@ -263,3 +273,25 @@ def test_pack_unpack_im2col_headprep():
     assert torch.equal(g[..., :2].float().permute(0, 3, 1, 2), dl.to(torch.bfloat16).float())
     assert g[..., 2:].abs().max().item() == 0
     assert torch.allclose(db, dl.sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,classes,h,w", [(2, 2, 24, 20), (1, 3, 16, 16), (3, 10, 12, 8), (2, 16, 8, 8), (2, 3, 7, 9)])
+def test_head_grad_prep_layouts(n, classes, h, w):
+    """fp32 NCHW dlogits -> bf16 NHWC padded to 16 channels + per-class sums: bit-exact conversion for the
+    four-pixel kernel (<= 4 classes, <= 16 classes) and the scalar one (H*W not a multiple of 4), bias gradient
+    with and without accumulation."""
+    L = _lib()
+    lib = L.lib()
+    gen = torch.Generator(device="cuda").manual_seed(n * 100 + classes)
+    dl = torch.randn((n, classes, h, w), generator=gen, device="cuda")
+    g = torch.full((n, h, w, 16), 7.0, device="cuda", dtype=torch.bfloat16)
+    db = torch.full((classes,), 3.0, device="cuda")
+    L.check(lib.mmr_head_grad_prep(_p(dl), n, classes, h, w, _p(g), 16, _p(db), 0, _s()))
+    torch.cuda.synchronize()
+    assert torch.equal(g[..., :classes].permute(0, 3, 1, 2), dl.to(torch.bfloat16))
+    assert classes == 16 or g[..., classes:].abs().max().item() == 0
+    want = dl.double().sum((0, 2, 3))
+    assert torch.allclose(db.double(), want, rtol=1e-5, atol=1e-5)
+    L.check(lib.mmr_head_grad_prep(_p(dl), n, classes, h, w, _p(g), 16, _p(db), 1, _s()))
+    torch.cuda.synchronize()
+    assert torch.allclose(db.double(), 2 * want, rtol=1e-5, atol=1e-5)
