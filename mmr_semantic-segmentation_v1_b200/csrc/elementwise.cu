@@ -965,31 +965,38 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
     const uint32_t pix = i / groups;
     const int ox = (int)(pix % (uint32_t)Wo), oy = (int)((pix / (uint32_t)Wo) % (uint32_t)Ho);
     const int n = (int)(pix / ((uint32_t)Wo * Ho));
-    // all (up to nine) window loads first, then the scan
+    // all (up to nine) window loads first, then a branch-free scan: a tap outside the image reads as -inf,
+    // which can never win, and the argmax starts at the first tap inside the image
+    const uint32_t ninf2 = 0xFF80FF80u;   // two bf16 -inf
     uint4 raw[9];
-    bool live[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const int iy = 2 * oy + k / 3 - 1, ix = 2 * ox + k % 3 - 1;
-      live[k] = iy >= 0 && iy < H && ix >= 0 && ix < W;
-      if (live[k]) raw[k] = ldg16(x + (((size_t)n * H + iy) * W + ix) * C + c);
+      const bool live = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      raw[k] = make_uint4(ninf2, ninf2, ninf2, ninf2);
+      if (live) raw[k] = ldg16(x + (((size_t)n * H + iy) * W + ix) * C + c);
     }
     float best[8];
     int bi[8];
+    const int k0 = (oy == 0 ? 3 : 0) + (ox == 0 ? 1 : 0);
+    {
+      const uint4 f = oy == 0 ? (ox == 0 ? raw[4] : raw[3]) : (ox == 0 ? raw[1] : raw[0]);
+      cvt8(f, best);
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) best[j] = -INFINITY, bi[j] = 0;
-    bool first = true;
+    for (int j = 0; j < 8; ++j) bi[j] = k0;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      if (!live[k]) continue;
+    for (int k = 1; k < 9; ++k) {
       float v[8];
       cvt8(raw[k], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        // torch: first maximum in window scan order wins; NaN propagates
-        if (first || v[j] > best[j] || v[j] != v[j]) best[j] = v[j], bi[j] = k;
+        // torch: first maximum in window scan order wins; NaN propagates.  Taps before k0 are outside the
+        // image (-inf: never taken) and tap k0 itself compares equal or is the NaN already held.
+        const bool take = v[j] > best[j] || v[j] != v[j];
+        best[j] = take ? v[j] : best[j];
+        bi[j] = take ? k : bi[j];
       }
-      first = false;
     }
     store8(out + (size_t)pix * C + c, best);
     if (idx) {   // NULL in eval mode: the argmax is only needed by the backward pass
@@ -1018,14 +1025,16 @@ maxpool_bwd_block_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N,
     const uint32_t blk = i / groups;
     const int b = (int)(blk % (uint32_t)Wo), a = (int)((blk / (uint32_t)Wo) % (uint32_t)Ho);
     const int n = (int)(blk / ((uint32_t)Wo * Ho));
+    // a window outside the image reads as argmax byte 255 (no tap) and zero gradient: no branches below
     uint2 packed[4];
     uint4 raw[4][NC];
-    bool live[4];
 #pragma unroll
     for (int wi = 0; wi < 4; ++wi) {
       const int oy = a + (wi >> 1), ox = b + (wi & 1);
-      live[wi] = oy < Ho && ox < Wo;
-      if (live[wi]) {
+      packed[wi] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+      for (int k = 0; k < NC; ++k) raw[wi][k] = make_uint4(0u, 0u, 0u, 0u);
+      if (oy < Ho && ox < Wo) {
         const size_t opix = ((size_t)n * Ho + oy) * Wo + ox;
         packed[wi] = __ldg(reinterpret_cast<const uint2*>(idx + opix * C + c));
 #pragma unroll
@@ -1039,12 +1048,10 @@ maxpool_bwd_block_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N,
       for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
 #pragma unroll
     for (int wi = 0; wi < 4; ++wi) {
-      if (!live[wi]) continue;
       float g[8];
+      cvt8(raw[wi][0], g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = 0.f;
-#pragma unroll
-      for (int k = 0; k < NC; ++k) add8(raw[wi][k], g);
+      for (int k = 1; k < NC; ++k) add8(raw[wi][k], g);
       const int wy = wi >> 1, wx = wi & 1;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -1056,7 +1063,7 @@ maxpool_bwd_block_kernel(ContribList cl, const uint8_t* __restrict__ idx, int N,
           for (int dx = 0; dx < 2; ++dx) {
             if ((wy && !dy) || (wx && !dx)) continue;   // the next window only reaches the odd row / column
             const int tap = (wy ? 0 : 1 + dy) * 3 + (wx ? 0 : 1 + dx);
-            if (id == tap) acc[dy * 2 + dx][j] += g[j];
+            acc[dy * 2 + dx][j] += id == tap ? g[j] : 0.f;
           }
       }
     }

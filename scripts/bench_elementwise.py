@@ -56,6 +56,19 @@ for H, Cc, pools in SHAPES:
     t_bap = timeit(lambda: lib.mmr_bn_bwd_apply(vp(g), vp(z), vp(st[0]), vp(st[1]), vp(st[4]), P, Cc, vp(dz), s))
     t_bam = timeit(lambda: lib.mmr_bn_bwd_apply_masked(vp(contribs[0] if not pools[0] else g), vp(z), vp(st[0]), vp(st[1]),
                                                        vp(st[4]), vp(st[2]), vp(st[3]), P, Cc, vp(dz), s))
+    slots = torch.zeros((8 * 2 * Cc,), device="cuda", dtype=torch.float64)
+    ticket = torch.zeros((1,), device="cuda", dtype=torch.int32)
+    dgb = torch.zeros((2, Cc), device="cuda")
+    fused = lambda gout, masked: lib.mmr_bn_bwd_reduce_fused(
+        arr, len(pools), None if masked else vp(a), vp(z), vp(st[0]), vp(st[1]), N, H, H, Cc, gout, vp(slots), nblk,
+        vp(st[2]), vp(dgb[0]), vp(dgb[1]), 0, vp(st[4]), vp(ticket), vp(st[2]) if masked else None,
+        vp(st[3]) if masked else None, s)
+    t_f1 = timeit(lambda: fused(vp(g), False))
+    t_f3 = timeit(lambda: fused(vp(g), True))
+    t_f3n = timeit(lambda: fused(None, True))
+    print("   fused reduce: act mask + g %6.1f us %5.2f TB/s | z mask + g %6.1f us %5.2f TB/s | z mask, no g %6.1f us %5.2f TB/s"
+          % (t_f1 * 1e3, (cb + 3 * el) / t_f1 / 1e9, t_f3 * 1e3, (cb + 2 * el) / t_f3 / 1e9, t_f3n * 1e3,
+             (cb + el) / t_f3n / 1e9), flush=True)
     t_app = timeit(lambda: lib.mmr_bn_apply(vp(z), P, Cc, vp(st[2]), vp(st[3]), None, 1, vp(a), s))
     t_sta = timeit(lambda: lib.mmr_bn_stats(vp(z), P, Cc, vp(partial), nblk, s))
     print("H %4d C %4d pools %-14s reduce %7.1f us %5.2f TB/s | bwd_apply %6.1f us %5.2f TB/s | apply %6.1f us %5.2f TB/s"
