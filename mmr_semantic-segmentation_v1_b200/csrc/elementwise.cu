@@ -499,7 +499,7 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
   const uint32_t stride = (uint32_t)gridDim.x * rows_per_iter;
   // rows in flight per thread: with 2 x 256 threads per SM a row of (NC + 2) 16-byte loads must be
   // multiplied up to ~100 B per thread to cover the HBM latency-bandwidth product (~44 KB per SM)
-  constexpr int R = MODE == 0 ? 4 : (POOLED ? 1 : (NC == 1 ? 4 : (NC == 2 ? 3 : 2)));
+  constexpr int R = MODE == 0 ? 4 : (POOLED || NC > 4 ? 1 : (NC == 1 ? 4 : (NC == 2 ? 3 : 2)));
   for (uint32_t r0 = (uint32_t)blockIdx.x * rows_per_iter + rl; r0 < P; r0 += R * stride) {
     if (MODE == 0) {
       uint4 raw[R];
@@ -541,22 +541,22 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
   }
   if (partial == nullptr) return;
   __syncthreads();
-  if (rl == 0) {
-    for (int j = 0; j < 8; ++j) {
-      double s1 = 0.0, s2 = 0.0;
-      for (int k = 0; k < rows_per_iter; ++k) {
-        s1 += sd1[j * kEwThreads + k * tpc + cg];
-        s2 += sd2[j * kEwThreads + k * tpc + cg];
-      }
-      if (MODE == 1 || MODE == 3) s2 = (s2 - (double)__ldg(mean + c + j) * s1) * (double)__ldg(invstd + c + j);
-      if ((MODE == 1 || MODE == 3) && fz.ticket) {
-        double* sl = partial + (size_t)(blockIdx.x & 7) * 2 * C;
-        atomicAdd(sl + c + j, s1);
-        atomicAdd(sl + C + c + j, s2);
-      } else {
-        partial[((size_t)blockIdx.x * 2 + 0) * C + c + j] = s1;
-        partial[((size_t)blockIdx.x * 2 + 1) * C + c + j] = s2;
-      }
+  // block sums: one thread per channel (not one per channel group) adds the rows_per_iter row lanes in lane order
+  for (int t = threadIdx.x; t < C; t += kEwThreads) {
+    const int j = t / tpc, g8 = t % tpc, ch = g8 * 8 + j;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < rows_per_iter; ++k) {
+      s1 += sd1[j * kEwThreads + k * tpc + g8];
+      s2 += sd2[j * kEwThreads + k * tpc + g8];
+    }
+    if (MODE == 1 || MODE == 3) s2 = (s2 - (double)__ldg(mean + ch) * s1) * (double)__ldg(invstd + ch);
+    if ((MODE == 1 || MODE == 3) && fz.ticket) {
+      double* sl = partial + (size_t)(blockIdx.x & 7) * 2 * C;
+      atomicAdd(sl + ch, s1);
+      atomicAdd(sl + C + ch, s2);
+    } else {
+      partial[((size_t)blockIdx.x * 2 + 0) * C + ch] = s1;
+      partial[((size_t)blockIdx.x * 2 + 1) * C + ch] = s2;
     }
   }
   if ((MODE == 1 || MODE == 3) && fz.ticket) {
@@ -609,6 +609,8 @@ static void launch_reduce(int nblk, cudaStream_t st, const __nv_bfloat16* z, uin
       case 2: MMR_RR(2, false); break;
       case 3: MMR_RR(3, false); break;
       case 4: MMR_RR(4, false); break;
+      case 5: MMR_RR(5, false); break;   // x_0_0 .. x_0_3 read by five decoder nodes
+      case 6: MMR_RR(6, false); break;
       default: MMR_RR(0, false); break;
     }
   }
