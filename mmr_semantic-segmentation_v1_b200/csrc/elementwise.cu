@@ -339,9 +339,13 @@ __device__ __forceinline__ void add8(const uint4& u, float (&g)[8]) {
   }
 }
 __device__ __forceinline__ void cvt8(const uint4& u, float (&g)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-  for (int j = 0; j < 8; ++j) g[j] = 0.f;
-  add8(u, g);
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    g[2 * j] = f.x;
+    g[2 * j + 1] = f.y;
+  }
 }
 
 // Any number of contributions (the NC = 0 instantiations: more than four consumers, e.g. the encoder
@@ -421,12 +425,13 @@ __device__ __forceinline__ void finish_row(const ContribList& cl, const RowGeom&
   if (NC == 0) {
     gather_row<POOLED>(cl, geo, r, c, C, g);
   } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    // the first piece converts (0 + v is not folded by the compiler: -0.0), the others add
+    cvt8(raw.v[0][0], g);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
 #pragma unroll
-      for (int q = 0; q < (POOLED ? 4 : 1); ++q) add8(raw.v[i][q], g);
+      for (int q = 0; q < (POOLED ? 4 : 1); ++q)
+        if (i + q > 0) add8(raw.v[i][q], g);
     }
   }
   float zz[8];
