@@ -103,27 +103,38 @@ dice_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__
 __global__ void dice_ce_finalize_kernel(double* __restrict__ ws, int N, int C, int nblk,
                                         MmrLossParams prm, float* __restrict__ out) {
   pdl_prologue();
-  // single block; thread per (n,c)
+  // single block
   double* red = ws;
   double* tail = red + (size_t)N * C * 3;
   const double* part = ws + ws_head_doubles(N, C);
   __shared__ double sh_dice[kLossThreads];
   __shared__ double sh_ce[kLossThreads], sh_cnt[kLossThreads];
   double dice_acc = 0.0, ce_acc = 0.0, cnt_acc = 0.0;
-  for (int k = threadIdx.x; k < N * C; k += blockDim.x) {
+  // one warp per (image, class): the lanes stride over the block partials (loads in flight instead of a serial
+  // chain of L2 round trips), then a fixed-order shuffle tree
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int k = warp; k < N * C; k += nwarp) {
     const int n = k / C, c = k % C;
     double I = 0.0, P = 0.0, Y = 0.0;
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = lane; b < nblk; b += 32) {
       const double* src = part + ((size_t)n * nblk + b) * (3 * C + 2);
       I += src[c];
       P += src[C + c];
       Y += src[2 * C + c];
     }
-    red[(size_t)k * 3 + 0] = I;
-    red[(size_t)k * 3 + 1] = P;
-    red[(size_t)k * 3 + 2] = Y;
-    if (c < prm.dice_channels)
-      dice_acc += 1.0 - (2.0 * I + (double)prm.dice_eps_nr) / (P + Y + (double)prm.dice_eps_dr);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      I += __shfl_xor_sync(0xffffffffu, I, o);
+      P += __shfl_xor_sync(0xffffffffu, P, o);
+      Y += __shfl_xor_sync(0xffffffffu, Y, o);
+    }
+    if (lane == 0) {
+      red[(size_t)k * 3 + 0] = I;
+      red[(size_t)k * 3 + 1] = P;
+      red[(size_t)k * 3 + 2] = Y;
+      if (c < prm.dice_channels)
+        dice_acc += 1.0 - (2.0 * I + (double)prm.dice_eps_nr) / (P + Y + (double)prm.dice_eps_dr);
+    }
   }
   for (int k = threadIdx.x; k < N * nblk; k += blockDim.x) {
     const double* src = part + (size_t)k * (3 * C + 2);
