@@ -95,21 +95,26 @@ def test_bn_forward_backward(shape, with_res):
         assert rel(_nchw(g), resf.grad) < 1e-2
 
 
-@pytest.mark.parametrize("c", [16, 48, 80, 24, 256])
-def test_bn_apply_passes_any_channel_count(c):
+@pytest.mark.parametrize("c,shift", [(16, 0), (48, 0), (80, 0), (24, 0), (256, 0), (64, 8)])
+def test_bn_apply_passes_any_channel_count(c, shift):
     """The three streaming apply passes against their formulas (fp32 on the same bf16 inputs, bf16 output rounding)
     for channel counts whose 16-channel groups are not a power of two (48, 80), for the 8-channel kernels (24)
-    and with a grid that wraps the channel groups (256), with and without residual / ReLU."""
+    and with a grid that wraps the channel groups (256), with and without residual / ReLU; shift = 8: tensors that
+    are 16- but not 32-byte aligned must take the 8-channel kernels and give the same results."""
     L = _lib()
     lib = L.lib()
     gen = torch.Generator(device="cuda").manual_seed(c)
     P = 3 * 37 * 29
-    z = (torch.randn((P, c), generator=gen, device="cuda") * 1.5).to(torch.bfloat16)
-    g = torch.randn((P, c), generator=gen, device="cuda").to(torch.bfloat16)
-    res = torch.randn((P, c), generator=gen, device="cuda").to(torch.bfloat16)
+    def buf(fill):
+        t = torch.empty((P * c + shift,), device="cuda", dtype=torch.bfloat16)[shift:].view(P, c)
+        if fill is not None:
+            t.copy_((torch.randn((P, c), generator=gen, device="cuda") * fill).to(torch.bfloat16))
+        return t
+
+    z, g, res, out = buf(1.5), buf(1.0), buf(1.0), buf(None)
+    assert z.data_ptr() % 32 == (16 if shift else 0)
     st = torch.randn((7, c), generator=gen, device="cuda")    # mean, invstd, scale, shift, cA, cB, cC
     st[1] = st[1].abs() + 0.5
-    out = torch.empty((P, c), device="cuda", dtype=torch.bfloat16)
     zf, gf = z.float(), g.float()
     close = lambda a, b: torch.allclose(a.float(), b, rtol=1e-2, atol=1e-2)
     for r, relu in ((None, 1), (res, 1), (res, 0), (None, 0)):
