@@ -515,6 +515,31 @@ int mmr_sgd_step(float* p, const float* g, float* momentum_buf, int64_t n, float
                  int first_step, float grad_scale, mmr_stream_t stream);
 /* sum of squares of g (double out[0] accumulated) for clip_grad_norm_. */
 int mmr_sumsq(const float* g, int64_t n, double* out, mmr_stream_t stream);
+/* Second half of torch.nn.utils.clip_grad_norm_(parameters, max_norm) (ED/Main_MMR_SegModel.py:722):
+ * total = sqrt(sumsq[0]); coef = min(1, max_norm / (total + 1e-6)); g *= coef when coef < 1, in place.  The
+ * sum of squares stays on the device (no host read); norm_out (may be NULL) receives total as fp32. */
+int mmr_clip_scale(float* g, int64_t n, const double* sumsq, float max_norm, float* norm_out, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Eval-mode BatchNorm folding for every conv of a network in ONE launch (model.eval() forward,
+ * SU/ModelTraining.py:703,736; SU/ModelEval.py:363-458): for each job
+ *   scale[r*C + c] = gamma[c] * rsqrt(running_var[c] + eps)
+ *   shift[r*C + c] = beta[c] - (running_mean[c] - conv_bias[c]) * scale[c]        r = 0 .. rep-1
+ * conv_bias may be NULL (bias-free conv in front of the BatchNorm); rep > 1 repeats the layer's channels
+ * (the space-to-depth stem's four output phases).  jobs_dev is a DEVICE array.  Runs inside the replayed
+ * eval launch list, so the folded constants always follow the current parameters and running statistics.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* gamma;
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  const float* conv_bias;
+  float* scale;
+  float* shift;
+  int32_t C, rep;
+} MmrBnFoldJob;
+int mmr_bn_fold_batch(const MmrBnFoldJob* jobs_dev, int njobs, float eps, mmr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,12 @@ class MmrPackJob(C.Structure):
                 ("nchunks", C.c_int32), ("layout", C.c_int32)]
 
 
+class MmrBnFoldJob(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("conv_bias", C.c_void_p), ("scale", C.c_void_p),
+                ("shift", C.c_void_p), ("C", C.c_int32), ("rep", C.c_int32)]
+
+
 class MmrWgradHaloDesc(C.Structure):
     _fields_ = [
         ("dz", MmrHaloSrc), ("nsrc", C.c_int32), ("src", MmrHaloSrc * 6),
@@ -210,6 +216,8 @@ SIGNATURES = {
     "mmr_zero_async": (_i, [_vp, _i64, _vp]),
     "mmr_sgd_step": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _f, _vp]),
     "mmr_sumsq": (_i, [_vp, _i64, _vp, _vp]),
+    "mmr_clip_scale": (_i, [_vp, _i64, _vp, _f, _vp, _vp]),
+    "mmr_bn_fold_batch": (_i, [_vp, _i, _f, _vp]),
 }
 
 _lib = None

@@ -100,9 +100,66 @@ sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
   if (threadIdx.x == 0) atomicAdd(out, sh[0]);
 }
 
+// clip_grad_norm_'s scaling half: every thread reads the device-side sum of squares.
+__global__ void __launch_bounds__(kOptThreads)
+clip_scale_kernel(float* __restrict__ g, int64_t n, const double* __restrict__ sumsq, float max_norm,
+                  float* __restrict__ norm_out) {
+  pdl_prologue();
+  const float total = (float)sqrt(*sumsq);
+  if (norm_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = total;
+  const float coef = max_norm / (total + 1e-6f);
+  if (!(coef < 1.f)) return;
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(g)[i];
+    v.x *= coef; v.y *= coef; v.z *= coef; v.w *= coef;
+    reinterpret_cast<float4*>(g)[i] = v;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    g[i] *= coef;
+}
+
+// Eval-mode BatchNorm folding, one CTA per job (a job is one BatchNorm layer: at most 2048 channels).
+__global__ void __launch_bounds__(kOptThreads)
+bn_fold_kernel(const MmrBnFoldJob* __restrict__ jobs, float eps) {
+  pdl_prologue();
+  const MmrBnFoldJob j = jobs[blockIdx.x];
+  for (int c = threadIdx.x; c < j.C; c += blockDim.x) {
+    const float sc = j.gamma[c] * rsqrtf(j.running_var[c] + eps);
+    float mean = j.running_mean[c];
+    if (j.conv_bias != nullptr) mean -= j.conv_bias[c];
+    const float sh = j.beta[c] - mean * sc;
+    for (int r = 0; r < j.rep; ++r) {
+      j.scale[r * j.C + c] = sc;
+      j.shift[r * j.C + c] = sh;
+    }
+  }
+}
+
 }  // namespace mmr
 
 using namespace mmr;
+
+extern "C" int mmr_clip_scale(float* g, int64_t n, const double* sumsq, float max_norm, float* norm_out,
+                              mmr_stream_t stream) {
+  MMR_REQUIRE(g && sumsq && n >= 0, "bad argument");
+  MMR_REQUIRE(reinterpret_cast<uintptr_t>(g) % 16 == 0, "gradient buffer must be 16-byte aligned");
+  int64_t blocks = (n / 4 + kOptThreads - 1) / kOptThreads;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  mmr_launch((clip_scale_kernel), (int)blocks, kOptThreads, 0, as_stream(stream), g, n, sumsq, max_norm, norm_out);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_bn_fold_batch(const MmrBnFoldJob* jobs_dev, int njobs, float eps, mmr_stream_t stream) {
+  MMR_REQUIRE(jobs_dev && njobs >= 0, "bad argument");
+  if (njobs == 0) return 0;
+  mmr_launch((bn_fold_kernel), njobs, kOptThreads, 0, as_stream(stream), jobs_dev, eps);
+  MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int mmr_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                              float b1, float b2, float eps, float wd, float bc1, float bc2, int mode,

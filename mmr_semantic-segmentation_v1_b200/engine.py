@@ -97,14 +97,13 @@ class Engine:
         self.units = []
         self.fwd_calls = []
         self.repack_calls = []
-        self._w_versions = None
         self.bwd_calls = {False: [], True: []}
         self.conv_flops_fwd = 0
         self.conv_flops_bwd = 0
         self.n_launch_fwd = 0
         self.n_launch_bwd = 0
-        self.weights_dirty = True
         self.param_ready_hooks = []  # (index in bwd call list, [param names]) for DDP overlap
+        self.generation = 0          # forwards run so far: the saved activations belong to the latest one
         self.use_halo = not os.environ.get("MMR_NO_HALO")
         self.use_graphs = not os.environ.get("MMR_NO_GRAPH")
         self.use_lanes = not os.environ.get("MMR_NO_LANES")
@@ -235,6 +234,20 @@ class Engine:
             self.repack_calls.append((self.lib.mmr_pack_weights_halo_batch,
                                       (C.c_void_p(self.pack_jobs_dev.data_ptr()), len(self.pack_jobs),
                                        C.c_int64(blocks))))
+        if getattr(self, "folded", None):
+            jobs = []
+            for u in self.folded:
+                bn = u["bn"]
+                cb = self.P[u["fold_bias"]].data_ptr() if u.get("fold_bias") else None
+                jobs.append(_lib.MmrBnFoldJob(
+                    self.P[bn + ".weight"].data_ptr(), self.P[bn + ".bias"].data_ptr(),
+                    self.P[bn + ".running_mean"].data_ptr(), self.P[bn + ".running_var"].data_ptr(), cb,
+                    u["scale"].data_ptr(), u["shift"].data_ptr(), self.P[bn + ".weight"].numel(),
+                    u.get("fold_rep", 1)))
+            arr = (_lib.MmrBnFoldJob * len(jobs))(*jobs)
+            self.fold_jobs_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(self.dev)
+            self.repack_calls.append((self.lib.mmr_bn_fold_batch,
+                                      (C.c_void_p(self.fold_jobs_dev.data_ptr()), len(jobs), C.c_float(1e-5))))
         if self.halo_stats_used:
             # one memset per forward re-arms every statistics slot the conv epilogues accumulate into
             fc.insert(0, (self.lib.mmr_zero_async, (C.c_void_p(self.halo_stats.data_ptr()),
@@ -343,7 +356,9 @@ class Engine:
             self._fwd_bn_train(unit, unit["z"], out.buf, None, True)
 
     def _fold(self, unit, bn_name, Cc, conv_bias=None, rep=1):
-        """Eval mode: scale/shift from the running statistics, refreshed by `refresh_folded`; a conv bias
+        """Eval mode: scale/shift from the running statistics, recomputed by ONE `mmr_bn_fold_batch` launch at the
+        head of every eval forward (so they always follow the current parameters / running statistics: an
+        optimiser step, a training forward or load_state_dict in between needs no notification); a conv bias
         in front of the BatchNorm (the in-tree UNet's DoubleConv) folds into the shift.  rep: the GEMM's
         output channels are `rep` copies of the layer's (the space-to-depth stem's four output phases)."""
         st = self._f32(2, Cc * rep)
@@ -351,25 +366,6 @@ class Engine:
         self.keep.append(st)
         self.folded = getattr(self, "folded", [])
         self.folded.append(unit)
-
-    def refresh_folded(self):
-        units = getattr(self, "folded", [])
-        ver = tuple(self.P[u["bn"] + sfx]._version for u in units
-                    for sfx in (".weight", ".bias", ".running_mean", ".running_var")) + \
-            tuple(self.P[u["fold_bias"]]._version for u in units if u.get("fold_bias"))
-        if ver == getattr(self, "_fold_versions", None):
-            return
-        self._fold_versions = ver
-        for u in units:
-            bn = u["bn"]
-            inv = torch.rsqrt(self.P[bn + ".running_var"].float() + 1e-5)
-            sc = self.P[bn + ".weight"].float() * inv
-            rep = u.get("fold_rep", 1)
-            u["scale"].copy_(sc.repeat(rep))
-            mean = self.P[bn + ".running_mean"].float()
-            if u.get("fold_bias"):
-                mean = mean - self.P[u["fold_bias"]].float()
-            u["shift"].copy_((self.P[bn + ".bias"].float() - mean * sc).repeat(rep))
 
     def _fwd_conv(self, op):
         fc = self.fwd_calls
@@ -543,6 +539,9 @@ class Engine:
         def view(key, shape):
             off = offsets[key]
             return self.arena[off:off + nbytes(shape)].view(torch.bfloat16).view(shape)
+
+        self.arena_view = view      # tests read the backward temporaries through it (MMR_NO_ARENA_REUSE=1)
+        self.arena_keys = set(offsets)
 
         # 2. emit launches in backward order; contributions are registered as we go
         for acc in (False, True):
@@ -842,18 +841,15 @@ class Engine:
         elif x is not None:
             self.x_in.copy_(x, non_blocking=True)
         fwd = self._fwd_u8 if u8 else self.fwd_calls
-        if self.training:
-            key = "u8" if u8 else "f32"
-            if key not in self._train_calls:   # the optimiser rewrites the fp32 masters every step
-                self._train_calls[key] = self.repack_calls + fwd
-            self._run(self._train_calls[key], stream)
-        else:
-            self.refresh_folded()
-            ver = tuple(t._version for t in self.P.values())
-            if ver != self._w_versions or self.weights_dirty:
-                self._run(self.repack_calls, stream)
-                self._w_versions, self.weights_dirty = ver, False
-            self._run(fwd, stream)
+        # Both modes re-derive the bf16 GEMM weights (and, in eval mode, the folded BatchNorm constants) from
+        # the fp32 masters at the head of every forward: the optimiser kernels, the training engine's running
+        # statistics and load_state_dict all write those buffers without telling this engine (two launches,
+        # ~40 us, inside the same CUDA graph as the forward).
+        key = "u8" if u8 else "f32"
+        if key not in self._train_calls:
+            self._train_calls[key] = self.repack_calls + fwd
+        self._run(self._train_calls[key], stream)
+        self.generation += 1
         heads = self.head_units()
         if self.training and len(heads) > 1:
             return [u["result"] for u in heads]

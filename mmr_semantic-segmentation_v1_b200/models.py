@@ -11,7 +11,10 @@ layer: it replays the static plan of `engine.Engine` (hand-written sm_100a kerne
 C-ABI of include/mmrseg.h).  There is no CPU or eager-PyTorch fallback: calling the model with a
 CPU tensor raises.
 """
+import glob
 import math
+import os
+import warnings
 
 import torch
 import torch.nn as nn
@@ -90,6 +93,28 @@ class _Decoder(nn.Module):
                 nn.init.constant_(m.bias, 0)
 
 
+def _load_pretrained_resnet(module, name, source):
+    """`encoder_weights="imagenet"` (SU/ModelTraining.py:248-253) / `models.resnet18(pretrained=True)`
+    (SU/UArchModel/resnet_unet.py:139-145) without a network: take the torchvision checkpoint from the local
+    torch-hub cache (or $MMRSEG_PRETRAINED_DIR) when it is there, otherwise keep the random initialisation and
+    say so -- the stock constructor call must not raise on a box without egress."""
+    dirs = [os.environ.get("MMRSEG_PRETRAINED_DIR"), os.path.join(torch.hub.get_dir(), "checkpoints")]
+    for d in [d for d in dirs if d]:
+        files = sorted(glob.glob(os.path.join(d, name + "-*.pth")) + glob.glob(os.path.join(d, name + ".pth")))
+        for f in files:
+            sd = torch.load(f, map_location="cpu", weights_only=True)
+            own = module.state_dict()
+            sd = {k: v for k, v in sd.items() if k in own}      # smp deletes fc; torchvision keeps it
+            missing = [k for k in own if k not in sd and not k.endswith("num_batches_tracked")]
+            if missing:
+                continue
+            module.load_state_dict(sd, strict=False)
+            return f
+    warnings.warn("%s: no %s checkpoint in the local torch-hub cache (%s) and no network: the encoder keeps its "
+                  "random initialisation; load a checkpoint with load_state_dict" % (source, name, dirs[-1]))
+    return None
+
+
 # ------------------------------------------------------------------ autograd bridge
 class _PlanFunction(torch.autograd.Function):
     """logits = plan(x); backward replays the plan's backward and leaves parameter gradients in
@@ -100,15 +125,25 @@ class _PlanFunction(torch.autograd.Function):
         eng = model._engine_for(x, training=True)
         ctx.model, ctx.eng = model, eng
         out = eng.forward(x)
+        ctx.generation = eng.generation
+        # fresh tensors ("outputs are fresh tensors"): the plan's logits buffers are rewritten by
+        # the next forward, so `outs = [model(b) for b in batches]` must not alias them
         if isinstance(out, list):    # deep supervision: [main, aux...] at full resolution
             ctx.n_out = len(out)
-            return tuple(t.detach() for t in out)
+            return tuple(t.clone() for t in out)
         ctx.n_out = 1
-        return out.detach()  # a fresh tensor object over the plan's logits buffer
+        return out.clone()
 
     @staticmethod
     def backward(ctx, *dlogits):
         model, eng = ctx.model, ctx.eng
+        if eng.generation != ctx.generation:
+            raise _lib.MmrError(
+                "backward() of a forward pass that is no longer the latest one at this input shape: the plan "
+                "keeps ONE set of saved activations per (batch, H, W), and another model(x) call in training "
+                "mode has overwritten them.  Call backward() before the next training-mode forward (gradient "
+                "accumulation: forward, backward, forward, backward), or run the extra forward under "
+                "model.eval()")
         accumulate = model._grads_live()
         grads = [g.contiguous() if g is not None else None for g in dlogits]
         cuts = model._grad_cuts(eng.param_ready_hooks) if model._grad_cuts is not None else None
@@ -136,6 +171,38 @@ class _PlanModel(nn.Module):
         self._after_backward = None
         self._grad_cuts = None       # DDP: hook positions where a gradient bucket completes
         self._input_norm = None      # (mean, std) applied on the device to uint8 frames
+        self._io_dtype = None        # .half() / .bfloat16(): dtype of the returned logits (masters stay fp32)
+        self._io_channels_last = False
+
+    # ---- dtype / memory-format requests of the reference's inference path -------------------
+    # `self.model.to(memory_format=torch.channels_last); self.model.half()` (ED/Main_MMR_SegModel.py:1243-1244)
+    # ask PyTorch for what this engine does on its own: NHWC activations and 16-bit tensor-core math.  The
+    # fp32 master parameters are therefore left alone (converting them would only lose the checkpoint's
+    # precision); the request is honoured at the boundary: inputs of any float dtype / memory format are
+    # accepted and the logits come back in the requested dtype (and memory format).
+    def half(self):
+        self._io_dtype = torch.float16
+        return self
+
+    def bfloat16(self):
+        self._io_dtype = torch.bfloat16
+        return self
+
+    def float(self):
+        self._io_dtype = None
+        return super().float()
+
+    def to(self, *args, **kwargs):
+        device, dtype, non_blocking, memory_format = torch._C._nn._parse_to(*args, **kwargs)
+        if dtype is not None:
+            if not dtype.is_floating_point:
+                raise TypeError("nn.Module.to only accepts floating point dtypes, but got desired dtype=%s" % dtype)
+            self._io_dtype = None if dtype == torch.float32 else dtype
+        if memory_format is not None:
+            self._io_channels_last = memory_format == torch.channels_last
+        if device is not None:
+            return super().to(device=device, non_blocking=non_blocking)
+        return self
 
     # ---- flat parameter storage ------------------------------------------------------------
     def _named_params(self):
@@ -255,20 +322,29 @@ class _PlanModel(nn.Module):
         for eng in self._engines.values():
             eng.set_input_norm(*self._input_norm)
 
+    def _finish(self, t):
+        if self._io_dtype is not None:
+            t = t.to(self._io_dtype)
+        if self._io_channels_last:
+            t = t.contiguous(memory_format=torch.channels_last)
+        return t
+
     def forward(self, x):
         if x.dtype != torch.uint8 and x.dtype != torch.float32:
             x = x.float()
         if self.training and torch.is_grad_enabled():
             self._ensure_flat(x.device)
             out = _PlanFunction.apply(self, x.contiguous(), *[p for _, p in self._named_params()])
-            return list(out) if isinstance(out, tuple) else out
+            return [self._finish(t) for t in out] if isinstance(out, tuple) else self._finish(out)
         eng = self._engine_for(x, training=self.training)
-        return eng.forward(x.contiguous())
+        out = eng.forward(x.contiguous())
+        return [self._finish(t.clone()) for t in out] if isinstance(out, list) else self._finish(out.clone())
 
 
 class UnetPlusPlus(_PlanModel):
-    """`smp.UnetPlusPlus` with the reference's arguments.  `encoder_weights` other than None
-    would need a download; BASELINE configs are random-init, checkpoints load through
+    """`smp.UnetPlusPlus` with the reference's arguments.  `encoder_weights="imagenet"` loads the torchvision
+    checkpoint from the local torch-hub cache when present and otherwise warns and keeps the random
+    initialisation (no network here; BASELINE configs are random-init); checkpoints load through
     `load_state_dict`."""
 
     def __init__(self, encoder_name="resnet18", encoder_depth=5, encoder_weights=None,
@@ -283,11 +359,13 @@ class UnetPlusPlus(_PlanModel):
                 or activation is not None or aux_params is not None):
             raise NotImplementedError("only the configuration the reference uses is built: depth 5, "
                                       "decoder (256,128,64,32,16) with batch-norm, 3 input channels")
-        if encoder_weights is not None:
-            raise ValueError("pretrained encoder weights need a download; pass encoder_weights=None and "
-                             "load a checkpoint with load_state_dict")
+        if encoder_weights not in (None, "imagenet"):
+            raise KeyError("Wrong pretrained weights `%s` for encoder `%s`. Available options are: ['imagenet']"
+                           % (encoder_weights, encoder_name))
         self.encoder_name, self.classes, self.deep_supervision = encoder_name, classes, deep_supervision
         self.encoder = _ResNetEncoder(encoder_name)
+        if encoder_weights == "imagenet":
+            _load_pretrained_resnet(self.encoder, encoder_name, "UnetPlusPlus(encoder_weights='imagenet')")
         self.decoder = _Decoder((3, 64, 64, 128, 256, 512))
         head = _conv(16, classes, 3, bias=True)
         nn.init.xavier_uniform_(head.weight)
@@ -314,10 +392,11 @@ class ResNetUNet(_PlanModel):
     constructed at SU/ModelTraining.py:244-246): same module tree, so `state_dict()` keys (including the
     `layerN.*` aliases of `base_model.*`), `.base_model` (differential learning rate) and `conv_last`
     (skipped on resume) are the reference's.  The torchvision backbone is a parameter container only;
-    `forward` replays the static plan.  `pretrained=True` of the reference needs a download: the encoder
-    is random-init here (BASELINE config 3) and checkpoints load through `load_state_dict`."""
+    `forward` replays the static plan.  `pretrained=True` of the reference: the checkpoint is taken from the
+    local torch-hub cache when present, else the encoder stays random-init with a warning (BASELINE config 3
+    is random-init); checkpoints load through `load_state_dict`."""
 
-    def __init__(self, n_class, resnet_model):
+    def __init__(self, n_class, resnet_model, pretrained=True):
         super().__init__()
         import torchvision
         self.n_class, self.resnet_model = n_class, resnet_model
@@ -327,6 +406,8 @@ class ResNetUNet(_PlanModel):
             self.base_model = torchvision.models.resnet34(weights=None)
         else:
             raise ValueError("Only ResNet-18 and ResNet-34 are supported")
+        if pretrained:   # the reference's `models.resnet18(pretrained=True)`: local cache or random init + warning
+            _load_pretrained_resnet(self.base_model, "resnet%d" % resnet_model, "ResNetUNet(pretrained=True)")
         self.base_layers = list(self.base_model.children())
         self.layer0 = nn.Sequential(*self.base_layers[:3])
         self.layer0_1x1 = _convrelu(64, 64, 1, 0)

@@ -1,113 +1,238 @@
 """Optimiser seam: torch.optim.Adam(lr, weight_decay) (SU/ModelTraining.py:366), AdamW
 (:369, ED/Main_MMR_SegModel.py:878-880), SGD(momentum=0.9) (SU/ModelTraining.py:372,381),
-clip_grad_norm_ (ED/...:718-727) on the flat fp32
-parameter / gradient buffers of a plan model: one HBM-bound launch (28 B per parameter)."""
-import ctypes as C
-import math
+clip_grad_norm_ (ED/...:718-727) on the flat fp32 parameter / gradient buffers of a plan model:
+HBM-bound launches over contiguous memory (Adam: 28 B per parameter).
 
+State layout is torch's: `state[p] = {"step", "exp_avg", "exp_avg_sq"}` (Adam) / `{"momentum_buffer"}` (SGD),
+keyed per parameter, so `optimizer.state_dict()` / `load_state_dict()` round-trip and a checkpoint written
+by the reference's torch.optim.Adam resumes here (ED/Main_MMR_SegModel.py:991).  The moment tensors are views
+of one flat buffer laid out like the model's flat parameter buffer, which is what lets a param group be
+stepped with ONE launch per contiguous run of its parameters (the whole model: one launch).
+"""
 import torch
 
 from . import _lib
 from .losses import _stream
 
 
-class FusedAdam(torch.optim.Optimizer):
+def _runs(params, slots):
+    """Split `params` (each with a gradient) into maximal runs that are contiguous, in the same order and at the
+    same relative offsets, in ALL of: parameter storage, gradient storage and every state slot in `slots`
+    (name -> {param: tensor}).  Returns [(indices into params, [start pointers], numel including alignment
+    padding between members, all-members-launchable-as-one)].
+    Only the parameters handed in are ever covered by a run: a group holding a subset of a model's flat
+    buffer steps that subset and nothing else."""
+    order = sorted(range(len(params)), key=lambda i: params[i].data_ptr())
+    runs, cur = [], None
+    for i in order:
+        p = params[i]
+        ptrs = [p.data_ptr(), p.grad.data_ptr()] + [slots[k][p].data_ptr() for k in sorted(slots)]
+        ok = p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32 and \
+            p.grad.dtype == torch.float32 and all(q % 16 == 0 for q in ptrs)
+        if cur is not None and ok and cur["ok"]:
+            gap = ptrs[0] - cur["end"][0]
+            # the flat layout pads every tensor to a multiple of 4 floats; pad elements are zero in p, g, m, v
+            if 0 <= gap < 16 and all(q - e == gap for q, e in zip(ptrs, cur["end"])):
+                cur["idx"].append(i)
+                cur["end"] = [q + p.numel() * 4 for q in ptrs]
+                continue
+        cur = {"idx": [i], "start": ptrs, "end": [q + p.numel() * 4 for q in ptrs], "ok": ok}
+        runs.append(cur)
+    return [(r["idx"], r["start"], (r["end"][0] - r["start"][0]) // 4, r["ok"]) for r in runs]
+
+
+class _FlatStateOptimizer(torch.optim.Optimizer):
+    """Shared machinery: per-parameter torch-layout state whose tensors are views of flat buffers that mirror
+    the parameters' own storage layout."""
+
+    _slots = ()
+
+    def __init__(self, params, defaults):
+        super().__init__(params, defaults)
+        self.grad_scale = 1.0
+        self._flat_state = {}     # (storage ptr, slot) -> flat fp32 tensor spanning that storage
+        self._plans = {}
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._plans = {}          # loaded tensors are fresh allocations: re-home them on the next step
+        for g in self.param_groups:
+            for k, v in self.defaults.items():
+                g.setdefault(k, v)
+
+    def _slot_view(self, p, slot):
+        """View for parameter p inside the flat `slot` buffer that mirrors p's storage."""
+        st = p.untyped_storage()
+        key = (st.data_ptr(), slot)
+        flat = self._flat_state.get(key)
+        if flat is None or flat.numel() * 4 != st.nbytes() or flat.device != p.device:
+            flat = torch.zeros(st.nbytes() // 4, dtype=torch.float32, device=p.device)
+            self._flat_state[key] = flat
+        off = p.storage_offset()
+        return flat[off:off + p.numel()].view(p.shape)
+
+    def _home(self, p, slot, init=None):
+        """state[p][slot] as a view of the flat buffer; a tensor that came from load_state_dict (or an
+        existing one after the parameters moved) is copied in."""
+        st = self.state[p]
+        cur = st.get(slot)
+        if p.dtype != torch.float32 or not p.is_contiguous():
+            if cur is None:
+                st[slot] = cur = torch.zeros_like(p, memory_format=torch.preserve_format)
+            return cur
+        view = self._slot_view(p, slot)
+        if cur is None:
+            if init is not None:
+                view.copy_(init)
+            else:
+                view.zero_()
+        elif cur.data_ptr() != view.data_ptr():
+            view.copy_(cur.to(view.dtype))
+        st[slot] = view
+        return view
+
+    def _plan(self, gi, params):
+        """Cached run decomposition of group gi, keyed by what it depends on (parameter, gradient and state
+        addresses), so the per-step host cost is one tuple comparison."""
+        sig = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
+        plan = self._plans.get(gi)
+        if plan is not None and plan[0] == sig:
+            return plan[1]
+        slots = {s: {p: self._home(p, s) for p in params} for s in self._slots}
+        runs = _runs(params, slots)
+        self._plans[gi] = (sig, runs)
+        return runs
+
+
+class FusedAdam(_FlatStateOptimizer):
     """Adam (L2 folded into the gradient, like torch.optim.Adam) or AdamW (decoupled=True)."""
+
+    _slots = ("exp_avg", "exp_avg_sq")
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                       decoupled=decoupled))
-        self.grad_scale = 1.0
-
-    def _flat_of(self, tensors):
-        """Flat fp32 views spanning the storages of `tensors` (they are views of one buffer)."""
-        st = tensors[0].untyped_storage()
-        if any(t.untyped_storage().data_ptr() != st.data_ptr() for t in tensors):
-            return None
-        flat = torch.empty(0, dtype=torch.float32, device=tensors[0].device).set_(st)
-        return flat
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         lib = _lib.lib()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:
                 continue
             b1, b2 = group["betas"]
-            st = self.state.setdefault("group%d" % id(group), {})
-            st["step"] = st.get("step", 0) + 1
-            bc1, bc2 = 1.0 - b1 ** st["step"], 1.0 - b2 ** st["step"]
-            flat = self._flat_of([p.data for p in params])
-            gflat = self._flat_of([p.grad for p in params])
-            if flat is not None and gflat is not None and flat.numel() == gflat.numel() and \
-                    len(params) == len(group["params"]):
-                jobs = [("flat", flat, gflat)]
-            else:
-                jobs = [(id(p), p.data, p.grad) for p in params]
-            for key, pt, gt in jobs:
-                if key not in st:
-                    st[key] = (torch.zeros_like(pt), torch.zeros_like(pt))
-                m, v = st[key]
-                _lib.check(lib.mmr_adam_step(pt.data_ptr(), gt.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                             pt.numel(), group["lr"], b1, b2, group["eps"],
-                                             group["weight_decay"], bc1, bc2,
-                                             1 if group["decoupled"] else 0, self.grad_scale, _stream()))
+            runs = self._plan(gi, params)
+            mode = 1 if group.get("decoupled", self.defaults["decoupled"]) else 0
+            for idx, ptrs, numel, ok in runs:
+                # torch keeps one step counter per parameter; the parameters of a run advance together
+                steps = set()
+                for i in idx:
+                    st = self.state[params[i]]
+                    if "step" in st:
+                        st["step"] += 1
+                    else:
+                        st["step"] = torch.tensor(1.0, dtype=torch.float32)
+                    steps.add(float(st["step"]))
+                if len(steps) == 1 and ok:
+                    jobs = [(ptrs, numel, steps.pop())]
+                else:
+                    jobs = []
+                    for i in idx:
+                        p = params[i]
+                        st = self.state[p]
+                        g = p.grad if p.grad.is_contiguous() and p.grad.dtype == torch.float32 else None
+                        if g is None or not p.is_contiguous() or p.dtype != torch.float32:
+                            raise _lib.MmrError("FusedAdam needs contiguous fp32 parameters and gradients")
+                        jobs.append(([p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
+                                      st["exp_avg_sq"].data_ptr()], p.numel(), float(st["step"])))
+                for (pp, gp, mp, vp), n, t in jobs:
+                    if any(q % 16 for q in (pp, gp, mp, vp)):
+                        raise _lib.MmrError("FusedAdam: a parameter, gradient or moment buffer is not 16-byte "
+                                            "aligned (parameters of mmrseg_b200 models always are)")
+                    _lib.check(lib.mmr_adam_step(pp, gp, mp, vp, n, group["lr"], b1, b2, group["eps"],
+                                                 group["weight_decay"], 1.0 - b1 ** t, 1.0 - b2 ** t, mode,
+                                                 self.grad_scale, _stream()))
         return loss
 
 
-def _flat_view(tensors):
-    """One fp32 tensor spanning the common storage of `tensors` (views of one buffer), else None."""
-    st = tensors[0].untyped_storage()
-    if any(t.untyped_storage().data_ptr() != st.data_ptr() for t in tensors):
-        return None
-    return torch.empty(0, dtype=torch.float32, device=tensors[0].device).set_(st)
-
-
-class FusedSGD(torch.optim.Optimizer):
+class FusedSGD(_FlatStateOptimizer):
     """torch.optim.SGD(lr, momentum, weight_decay) (dampening 0, no Nesterov), the reference's
     `optim.SGD(model.parameters(), lr=args.lr, momentum=0.9)`; per-group learning rates (the differential
-    encoder / decoder rates of SU/ModelTraining.py:375-383) run one launch per parameter tensor."""
+    encoder / decoder rates of SU/ModelTraining.py:375-383) run one launch per contiguous run of a group."""
+
+    _slots = ("momentum_buffer",)
 
     def __init__(self, params, lr=1e-3, momentum=0.0, weight_decay=0.0):
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
-        self.grad_scale = 1.0
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         lib = _lib.lib()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:
                 continue
-            st = self.state.setdefault("group%d" % id(group), {})
-            flat = _flat_view([p.data for p in params]) if len(self.param_groups) == 1 else None
-            gflat = _flat_view([p.grad for p in params]) if flat is not None else None
-            if flat is not None and gflat is not None and flat.numel() == gflat.numel() and \
-                    len(params) == len(group["params"]):
-                jobs = [("flat", flat, gflat)]
-            else:
-                jobs = [(id(p), p.data, p.grad) for p in params]
-            for key, pt, gt in jobs:
-                first = key not in st
-                if first:
-                    st[key] = torch.zeros_like(pt) if group["momentum"] != 0 else None
-                buf = st[key]
-                _lib.check(lib.mmr_sgd_step(pt.data_ptr(), gt.data_ptr(), buf.data_ptr() if buf is not None else None,
-                                            pt.numel(), group["lr"], group["momentum"], group["weight_decay"],
-                                            int(first), self.grad_scale, _stream()))
+            # torch initialises the momentum buffer with the first gradient; a zero-initialised buffer gives
+            # the same first step (momentum * 0 + g), so the kernel's first_step flag stays 0
+            for idx, ptrs, numel, ok in self._plan(gi, params):
+                if ok:
+                    jobs = [(ptrs, numel)]
+                else:
+                    jobs = [([params[i].data_ptr(), params[i].grad.data_ptr(),
+                              self.state[params[i]]["momentum_buffer"].data_ptr()], params[i].numel()) for i in idx]
+                for (pp, gp, bp), n in jobs:
+                    _lib.check(lib.mmr_sgd_step(pp, gp, bp if group["momentum"] != 0 else None, n, group["lr"],
+                                                group["momentum"], group["weight_decay"], 0, self.grad_scale,
+                                                _stream()))
         return loss
 
 
-def clip_grad_norm_(model_or_gflat, max_norm):
-    """torch.nn.utils.clip_grad_norm_ on the flat gradient buffer; returns the total norm as a
-    device tensor (no host sync) and scales the gradients in place when it exceeds max_norm."""
-    g = model_or_gflat.flat_parameters()[1] if hasattr(model_or_gflat, "flat_parameters") else model_or_gflat
-    acc = torch.zeros((1,), device=g.device, dtype=torch.float64)
-    _lib.check(_lib.lib().mmr_sumsq(g.data_ptr(), g.numel(), acc.data_ptr(), _stream()))
-    norm = acc.sqrt().float()
-    coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
-    g.mul_(coef)
+def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=False, foreach=None):
+    """`torch.nn.utils.clip_grad_norm_(parameters, max_norm)` (ED/Main_MMR_SegModel.py:722:
+    `clip_grad_norm_(self.model.parameters(), 12)`), same signature and return value (the total norm, a
+    0-dim tensor on the gradients' device).  Two launches when the gradients are the views of a plan
+    model's flat gradient buffer (sum of squares, then an in-place scale that reads the norm on the device:
+    no host synchronisation), one pair per tensor otherwise.  `parameters` may also be a plan model or its
+    flat gradient tensor."""
+    if float(norm_type) != 2.0:
+        raise NotImplementedError("only the 2-norm (the reference's call) is built")
+    if hasattr(parameters, "flat_parameters"):
+        grads = [parameters.flat_parameters()[1]]
+    elif isinstance(parameters, torch.Tensor):   # a single parameter (torch's API), or a gradient buffer itself
+        grads = [parameters.grad if (parameters.requires_grad or parameters.grad is not None) else parameters]
+    else:
+        grads = [p.grad for p in parameters if p.grad is not None]
+    grads = [g for g in grads if g is not None]
+    if not grads:
+        return torch.tensor(0.0)
+    dev = grads[0].device
+    if not grads[0].is_cuda:
+        raise _lib.MmrError("clip_grad_norm_ runs on a B200 only (gradients on %s); there is no CPU fallback" % dev)
+    # gradients that tile one flat buffer (views of the model's gflat, in order, alignment padding only)
+    jobs = []
+    order = sorted(grads, key=lambda g: g.data_ptr())
+    start, end = order[0].data_ptr(), order[0].data_ptr() + order[0].numel() * 4
+    if any(g.dtype != torch.float32 or not g.is_contiguous() for g in order):
+        raise _lib.MmrError("clip_grad_norm_ needs contiguous fp32 gradients")
+    for g in order[1:]:
+        if 0 <= g.data_ptr() - end < 16 and g.untyped_storage().data_ptr() == order[0].untyped_storage().data_ptr():
+            end = g.data_ptr() + g.numel() * 4
+        else:
+            jobs.append((start, (end - start) // 4))
+            start, end = g.data_ptr(), g.data_ptr() + g.numel() * 4
+    jobs.append((start, (end - start) // 4))
+    lib = _lib.lib()
+    acc = torch.zeros((1,), device=dev, dtype=torch.float64)
+    norm = torch.empty((1,), device=dev, dtype=torch.float32)
+    for ptr, n in jobs:
+        _lib.check(lib.mmr_sumsq(ptr, n, acc.data_ptr(), _stream()))
+    for ptr, n in jobs:
+        if ptr % 16:
+            raise _lib.MmrError("clip_grad_norm_: gradient buffer is not 16-byte aligned")
+        _lib.check(lib.mmr_clip_scale(ptr, n, acc.data_ptr(), float(max_norm), norm.data_ptr(), _stream()))
+    if error_if_nonfinite and not torch.isfinite(norm).all():
+        raise RuntimeError("The total norm of order 2.0 for gradients from `parameters` is non-finite, so it "
+                           "cannot be clipped.")
     return norm[0]

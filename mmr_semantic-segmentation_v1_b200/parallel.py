@@ -3,7 +3,8 @@ over NVLink in buckets that start while the backward plan is still running.
 
 The reference is single-process; semantics follow torch DDP defaults: per-replica
 BatchNorm statistics, loss mean per replica, gradients averaged over ranks, parameters
-broadcast from rank 0 at construction.
+broadcast from rank 0 at construction (or, when the module is moved to its device after wrapping, before
+the first forward).
 """
 import torch
 import torch.distributed as dist
@@ -23,8 +24,22 @@ class DistributedDataParallel(torch.nn.Module):
         module._on_grads_ready = self._ready
         module._after_backward = self._finish
         module._grad_cuts = self.cuts
+        # torch DDP broadcasts rank 0's parameters and buffers in its constructor: do the same as soon as the
+        # module sits on its device (otherwise step 1's forward would run on per-rank weights and the
+        # broadcast would land in the middle of the first backward)
+        first = next(iter(module.parameters()), None)
+        if first is not None and (first.is_cuda or not torch.cuda.is_available()):
+            module._ensure_flat(first.device)
+            self._setup()
 
     def forward(self, *a, **k):
+        if self._buckets is None:       # the module was moved to its device after wrapping
+            first = next(iter(self.module.parameters()))
+            self.module._ensure_flat(first.device)
+            self._setup()
+        elif self.module._gflat is not self._gflat_seen:   # re-flattened (moved again): rebuild the buckets
+            self._cuts = {}
+            self._setup()
         return self.module(*a, **k)
 
     # ---- bucket plan: contiguous slices of the flat gradient buffer, closed in backward order
@@ -57,6 +72,7 @@ class DistributedDataParallel(torch.nn.Module):
         sizes = {n: p.numel() for n, p in m.named_parameters()}
         self._buckets = self.plan_buckets(names, m._flat_offsets, sizes, m._gflat.numel())
         self._pending = None
+        self._gflat_seen = m._gflat
         # high priority: a bucket's all-reduce gets its few CTAs at the next kernel boundary of the backward
         # instead of waiting for idle SMs behind the persistent conv kernels
         self._side = torch.cuda.Stream(device=m._gflat.device, priority=-1) if m._gflat.is_cuda else None

@@ -69,34 +69,39 @@ def _bn(bn, z):
                         bn.momentum, bn.eps)
 
 
-def _conv_bn_relu(conv, bn, x, res=None, relu=True):
-    y = _bn(bn, _conv(conv, x))
+def _conv_bn_relu(conv, bn, x, res=None, relu=True, trace=None, name=None):
+    z = _conv(conv, x)
+    y = _bn(bn, z)
     if res is not None:
         y = y + res
     if relu:
         y = torch.relu(y)
-    return rb(y)
+    y = rb(y)
+    if trace is not None:
+        trace[name] = (z.detach(), y.detach())
+    return y
 
 
-def _basic_block(blk, x):
-    t = _conv_bn_relu(blk.conv1, blk.bn1, x)
+def _basic_block(blk, x, trace=None, base=None):
+    t = _conv_bn_relu(blk.conv1, blk.bn1, x, trace=trace, name=base and base + "t1")
     idn = x
     if blk.downsample is not None:
-        idn = _conv_bn_relu(blk.downsample[0], blk.downsample[1], x, relu=False)
-    return _conv_bn_relu(blk.conv2, blk.bn2, t, res=idn)
+        idn = _conv_bn_relu(blk.downsample[0], blk.downsample[1], x, relu=False, trace=trace, name=base and base + "idn")
+    return _conv_bn_relu(blk.conv2, blk.bn2, t, res=idn, trace=trace, name=base and base + "out")
 
 
-def unetpp_forward(model, x):
-    """model: oracle.unetpp.UnetPlusPlus.  Returns fp32 logits with bf16 rounding points."""
+def unetpp_forward(model, x, trace=None):
+    """model: oracle.unetpp.UnetPlusPlus.  Returns fp32 logits with bf16 rounding points.  trace (a dict)
+    receives {engine activation name: (conv output z, activation)} for layer-by-layer comparisons."""
     enc, dec = model.encoder, model.decoder
     x = rf(x)
-    f_stem = _conv_bn_relu(enc.conv1, enc.bn1, x)
+    f_stem = _conv_bn_relu(enc.conv1, enc.bn1, x, trace=trace, name="f_stem")
     # the pooled tensor is stored in bf16 (exact: max of bf16 values); its input gradient is rounded
     t = F.max_pool2d(rbw(f_stem), 3, 2, 1)
     feats = [f_stem]
-    for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
-        for blk in layer:
-            t = _basic_block(blk, t)
+    for li, layer in enumerate((enc.layer1, enc.layer2, enc.layer3, enc.layer4), start=1):
+        for bi, blk in enumerate(layer):
+            t = _basic_block(blk, t, trace, "encoder.layer%d.%d." % (li, bi))
         feats.append(t)
     feats = feats[::-1]
     dense = {}
@@ -105,8 +110,8 @@ def unetpp_forward(model, x):
         blk = dec.blocks[name]
         up = F.interpolate(get(xsrc), scale_factor=2, mode="nearest")
         cat = torch.cat([up] + [get(s) for s in skips], 1) if skips else up
-        mid = _conv_bn_relu(blk.conv1[0], blk.conv1[1], cat)
-        dense[name] = _conv_bn_relu(blk.conv2[0], blk.conv2[1], mid)
+        mid = _conv_bn_relu(blk.conv1[0], blk.conv1[1], cat, trace=trace, name=name + ".mid")
+        dense[name] = _conv_bn_relu(blk.conv2[0], blk.conv2[1], mid, trace=trace, name=name)
     head = model.segmentation_head[0]
     xin = rbw(dense["x_0_%d" % dec.depth])
     logits = F.conv2d(xin, rf(head.weight), head.bias, 1, head.padding)

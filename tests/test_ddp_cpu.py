@@ -27,6 +27,9 @@ class _FakePlanModel(torch.nn.Module):
         self._gflat = torch.zeros(tot)
         self._flat_names, self._flat_offsets = names, offs
 
+    def _ensure_flat(self, device):
+        pass
+
 
 def _worker(rank, world, port):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -36,8 +39,9 @@ def _worker(rank, world, port):
     m = _FakePlanModel()
     m._flat.fill_(float(rank + 1))
     ddp = DistributedDataParallel(m, bucket_mb=0.008)      # ~2k floats per bucket -> several buckets
-    ddp.sync_parameters()
-    assert torch.all(m._flat == 1.0)                        # rank 0's parameters everywhere
+    assert torch.all(m._flat == 1.0)                        # rank 0's parameters everywhere, from the constructor on
+    ddp.sync_parameters()                                   # (idempotent)
+    assert torch.all(m._flat == 1.0)
     assert len(ddp._buckets) >= 2
     covered = sorted((lo, hi) for lo, hi, _ in ddp._buckets)
     assert covered[0][0] == 0 and covered[-1][1] == m._gflat.numel()

@@ -124,7 +124,8 @@ def test_train_steps_at_bench_configuration():
     model = UnetPlusPlus("resnet18", classes=2).cuda().train()
     crit = DiceCrossEntropyLoss(0.5)
     opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
-    x, y = bench.synthetic(bench.BATCH_PER_GPU)
+    cfg = bench.resolve("c2", 1)
+    x, y = bench.synthetic(cfg, cfg["batch"])
     x, y = x.cuda(), y.cuda()
     losses = []
     for _ in range(4):          # eager, capture, two graph replays
