@@ -196,6 +196,10 @@ typedef struct {
 int mmr_halo_conv_plan_create(const MmrHaloConvDesc* desc, void** plan);
 int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream);
 int mmr_halo_conv_plan_destroy(void* plan);
+/* Diagnostic (MMR_HALO_DBG bit 16): per-CTA %globaltimer stamps of the LAST mmr_halo_conv_plan_run launch, eight
+ * per CTA (entry, after the grid dependency wait, after setup, first operands landed, last MMA committed, last
+ * item stored, finalisation done, exit), copied to host memory.  Synchronises the device; never on the hot path. */
+int mmr_debug_halo_trace(unsigned long long* out_host, int n_ctas);
 /* OIHW fp32 3x3 master weights -> bf16 [n_ntiles][nchunks][9][bn][cb].  mode 0 (fprop): rows are
  * output channels, columns input channels; mode 1 (dgrad): rows are input channels, columns output
  * channels, taps mirrored.  Out-of-range rows / columns are zero.  layout: see MmrPackJob. */

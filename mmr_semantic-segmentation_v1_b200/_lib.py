@@ -160,6 +160,7 @@ SIGNATURES = {
     "mmr_halo_conv_plan_create": (_i, [C.POINTER(MmrHaloConvDesc), C.POINTER(_vp)]),
     "mmr_halo_conv_plan_run": (_i, [_vp, _vp]),
     "mmr_halo_conv_plan_destroy": (_i, [_vp]),
+    "mmr_debug_halo_trace": (_i, [_vp, _i]),
     "mmr_pack_weights_halo": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_pack_weights_halo_batch": (_i, [_vp, _i, _i64, _vp]),
     "mmr_wgrad_halo_partial_floats": (_i64, [_i, _i, _i, _i, _i]),

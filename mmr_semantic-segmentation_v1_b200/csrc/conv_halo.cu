@@ -41,6 +41,16 @@ struct HaloChunk {
   int32_t map, map_edge, c0, up;
 };
 
+// MMR_HALO_DBG bit 16: per-CTA timestamps of the last conv_halo launch (diagnostic; scripts/halo_trace.py):
+// [0] entry, [1] after griddepcontrol.wait, [2] after setup, [3] MMA warp: first operands landed,
+// [4] MMA warp: last commit issued, [5] epilogue warp 0: last item stored, [6] epilogue: finalisation done, [7] exit
+constexpr int kTraceSlots = 8;
+__device__ unsigned long long g_halo_trace[256 * kTraceSlots];
+#define MMR_TRACE(slot)                                                                              \
+  do {                                                                                               \
+    if ((p.dbg & 16) && blockIdx.x < 256) g_halo_trace[blockIdx.x * kTraceSlots + (slot)] = globaltimer_ns(); \
+  } while (0)
+
 struct HaloParams {
   const CUtensorMap* maps;  // device: [source maps ...][weight map][store-group maps ...]
   HaloChunk chunk[kMaxChunks];
@@ -161,6 +171,7 @@ __device__ __forceinline__ void mma_warp_loop(const HaloParams& p, uint32_t tmem
       const uint32_t row_step = (pitch * rb) >> 4;
       mbar_wait(&halo_full[hs], hph);
       tc_fence_after();
+      if (it == 0 && c == 0 && (threadIdx.x & 31) == 0) MMR_TRACE(3);
       const uint32_t a_stage = ((halo0 + (uint32_t)hs * p.halo_stage_bytes + (up ? rb : 0u)) >> 4) | 0x10000u;
 #pragma unroll
       for (int s = 0; s < 9 / TPS; ++s) {
@@ -240,6 +251,7 @@ __device__ __forceinline__ void mma_warp_loop_r(const HaloParams& p, uint32_t tm
       const uint32_t row_step = (pitch * rb) >> 4;
       mbar_wait(&halo_full[hs], hph);
       tc_fence_after();
+      if (it == 0 && c == 0 && (threadIdx.x & 31) == 0) MMR_TRACE(3);
       const uint32_t a_stage = ((halo0 + (uint32_t)hs * p.halo_stage_bytes + (up ? rb : 0u)) >> 4) | 0x10000u;
 #pragma unroll
       for (int s = 0; s < 3; ++s) {  // filter column kx = s: one weight slot
@@ -325,6 +337,28 @@ __device__ __forceinline__ ItemCoord decode_item(const HaloParams& p, int item) 
 template <int N>
 __device__ __forceinline__ void bulk_wait_read_n() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// One round (lane mask MK) of the halving butterfly that ends a statistics launch; CUR = channels a lane still
+// holds.  Template recursion keeps every array index a compile-time constant (the arrays stay in registers).
+template <int SG, int CUR, int MK>
+__device__ __forceinline__ void colsum_butterfly(float (&s1)[SG], float (&s2)[SG], int lane) {
+  const bool upper = (lane & MK) != 0;
+  if constexpr (CUR > 1) {
+    constexpr int half = CUR / 2;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send1 = upper ? s1[j] : s1[j + half], keep1 = upper ? s1[j + half] : s1[j];
+      const float send2 = upper ? s2[j] : s2[j + half], keep2 = upper ? s2[j + half] : s2[j];
+      s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, MK);
+      s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, MK);
+    }
+    if constexpr (MK > 1) colsum_butterfly<SG, half, MK / 2>(s1, s2, lane);
+  } else {
+    s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], MK);
+    s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], MK);
+    if constexpr (MK > 1) colsum_butterfly<SG, 1, MK / 2>(s1, s2, lane);
+  }
 }
 
 // STATS: 0 none; 1 forward statistics (sum, sum of squares of the stored values); 2 BatchNorm-backward sums of a
@@ -514,21 +548,23 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
     }
   }
   if (STAGED && lane == 0) bulk_wait0();
-  if (STATS) {
-    // column sums over the 32 accumulator rows of this warp, then one double atomic per channel
-    // and warp into the CTA's statistics slot (lane c % 32 owns channel c)
+  if constexpr (STATS != 0) {
+    // column sums over the 32 accumulator rows of this warp by a halving butterfly: in the round with lane
+    // mask mk a lane keeps one half of its channels and hands the other half to its partner, so the SG sums
+    // cost SG - SG/32 shuffles per array (62 at SG = 64) instead of 5 * SG (the plain per-channel reduction
+    // ran as 640 latency-bound shuffles: 8 us at the end of every launch).  Afterwards lane l owns the
+    // channels [l * SG / 32, (l + 1) * SG / 32) (SG = 16: lanes 2c and 2c + 1 both hold channel c).
     double* slot = (STATS == 2 ? p.bb.slots : p.stats) + (size_t)(blockIdx.x & (kStatSlots - 1)) * 2 * p.stats_ld;
+    colsum_butterfly<SG, SG, 16>(s1, s2, lane);
+    constexpr int PER = SG >= 32 ? SG / 32 : 1;
+    const int cbase = SG >= 32 ? lane * PER : (lane >> 1);
+    if (SG >= 32 || !(lane & 1)) {
 #pragma unroll
-    for (int c = 0; c < SG; ++c) {
-      float a = s1[c], b = s2[c];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, off);
-        b += __shfl_xor_sync(0xffffffffu, b, off);
-      }
-      if ((c & 31) == lane && c < p.cout_total) {
-        atomicAdd(slot + c, (double)a);
-        atomicAdd(slot + p.stats_ld + c, (double)b);
+      for (int j = 0; j < PER; ++j) {
+        if (cbase + j < p.cout_total) {
+          atomicAdd(slot + cbase + j, (double)s1[j]);
+          atomicAdd(slot + p.stats_ld + cbase + j, (double)s2[j]);
+        }
       }
     }
   }
@@ -580,7 +616,9 @@ enum { kEpiOther = 0, kEpiStats = 1, kEpiPlain = 2, kEpiBnBwd = 3, kEpiAffine = 
 
 template <int EK>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
+  if (threadIdx.x == 0) MMR_TRACE(0);
   pdl_prologue();
+  if (threadIdx.x == 0) MMR_TRACE(1);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* halo_base = smem;
   uint8_t* w_base = halo_base + (size_t)p.halo_stages * p.halo_stage_bytes;
@@ -623,6 +661,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  if (threadIdx.x == 0) MMR_TRACE(2);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- halo producer
@@ -711,6 +750,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
 #undef MMR_MMA_CASES_TPS
 #undef MMR_MMA_CASES_TX
 #undef MMR_MMA_CASE
+    if (lane == 0) MMR_TRACE(4);
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp - 4;
@@ -910,6 +950,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     }
     if (p.stats && persist) flush_stats(0);
     }  // generic epilogue
+    if (m == 0) MMR_TRACE(5);
     if (p.stats && p.bnf.ticket) {
       // fused BatchNorm finalisation: the last CTA to get here owns the complete sums
       uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 30);
@@ -981,12 +1022,14 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       }
     }
     if (p.out_mode == MMR_OUT_BF16_NHWC && !p.direct && m == 0) bulk_wait0();
+    if (m == 0) MMR_TRACE(6);
   }
 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (threadIdx.x == 0) MMR_TRACE(7);
 }
 
 template <int EK>
@@ -1371,6 +1414,13 @@ extern "C" int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream) {
     default: mmr_launch((conv_halo_kernel<kEpiOther>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
   }
   MMR_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mmr_debug_halo_trace(unsigned long long* out_host, int n_ctas) {
+  MMR_REQUIRE(out_host && n_ctas > 0 && n_ctas <= 256, "bad argument");
+  MMR_CUDA_CHECK(cudaDeviceSynchronize());
+  MMR_CUDA_CHECK(cudaMemcpyFromSymbol(out_host, mmr::g_halo_trace, sizeof(unsigned long long) * n_ctas * mmr::kTraceSlots));
   return 0;
 }
 
