@@ -324,6 +324,7 @@ def measure(cfg, args, world, rank, local, dev, full=True):
 
     n, H, W, classes = cfg["batch"], cfg["H"], cfg["W"], cfg["classes"]
     train = cfg["kind"] == "train"
+    torch.cuda.reset_peak_memory_stats(dev)
     model = build_model(cfg, dev)
     model.train() if train else model.eval()
     crit = DiceCrossEntropyLoss(0.5)
@@ -347,8 +348,9 @@ def measure(cfg, args, world, rank, local, dev, full=True):
             loss.backward()
             opt.step()
             return loss
-        with torch.no_grad():
-            confusion_matrix(model(x), y, cm=cm)
+        # eval step: argmax + confusion matrix in the head's epilogue (model.segment), no logits in HBM
+        pred, c = model.segment(x, y)
+        cm.add_(c)
         return cm
 
     def barrier():
@@ -441,7 +443,7 @@ def measure(cfg, args, world, rank, local, dev, full=True):
         lib = eng.lib
         lists = (eng.repack_calls, eng.fwd_calls) + ((eng.bwd_calls[False],) if train else ())
         per_step = sum(kernels_per_call(lib, fn) for calls in lists for fn, _ in calls)
-        per_step += (3 * (4 if cfg["ds"] else 1) + 1) if train else 1   # loss fwd (2) + bwd per output, Adam | metric
+        per_step += (3 * (4 if cfg["ds"] else 1) + 1) if train else 1   # loss fwd (2) + bwd per output, Adam | zeroing of the confusion counters (the metric itself is the head's epilogue)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
         if os.path.exists(tpath) and cfg["name"] == "c2":

@@ -191,7 +191,23 @@ typedef struct {
    * nearest-x2 sources), weights packed with layout 1, tx * rph * bn * acc_bufs <= 512. */
   int32_t rph;
   const MmrBnBwdFused* bn_bwd; /* optional (data-gradient launches): see MmrBnBwdFused */
+  const struct MmrHeadMetric* head_metric; /* optional (fp32 NCHW head launches): see MmrHeadMetric */
 } MmrHaloConvDesc;
+
+/* Eval-time metric fused into the segmentation head's epilogue: the reference's
+ *   seg = model(img); evaluator.addBatch(seg, oneHotGT, args); seg = torch.argmax(seg, 1)
+ * (SU/ModelTraining.py:736-760, SU/ModelEval.py:363-458, SU/utils.py:109-133) without the logits ever reaching
+ * HBM.  Per pixel, on the fp32 logits the epilogue holds in registers (accumulator + bias, the very values the
+ * plain head launch would store): pred = first maximal class (torch.argmax's rule, NaN counts as maximal);
+ * pred_out[n][y][x] = pred (uint8, optional); confusion[n][label][pred] += 1 (unsigned 64-bit, counted with
+ * shared-memory 32-bit integer atomics per CTA and image, optional; labels outside [0, classes) are skipped as
+ * in mmr_confusion_from_logits).  With a head_metric the descriptor's out_f32 may be NULL (no logits written). */
+typedef struct MmrHeadMetric {
+  const void* labels;          /* [N][H][W], int64 (labels_u8 = 0) or uint8 (labels_u8 = 1); NULL: no confusion */
+  int32_t labels_u8;
+  uint8_t* pred_out;           /* [N][H][W] or NULL */
+  unsigned long long* confusion; /* [N][classes][classes], accumulated, or NULL */
+} MmrHeadMetric;
 
 int mmr_halo_conv_plan_create(const MmrHaloConvDesc* desc, void** plan);
 int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream);

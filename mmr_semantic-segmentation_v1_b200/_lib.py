@@ -67,6 +67,11 @@ class MmrBnBwdFused(C.Structure):
                 ("accumulate", C.c_int32)]
 
 
+class MmrHeadMetric(C.Structure):
+    _fields_ = [("labels", C.c_void_p), ("labels_u8", C.c_int32), ("pred_out", C.c_void_p),
+                ("confusion", C.c_void_p)]
+
+
 class MmrHaloSrc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("W", C.c_int32), ("H", C.c_int32),
                 ("N", C.c_int32), ("up", C.c_int32)]
@@ -89,6 +94,7 @@ class MmrHaloConvDesc(C.Structure):
         ("bn_finalize", C.POINTER(MmrBnFinalize)),
         ("rph", C.c_int32),
         ("bn_bwd", C.POINTER(MmrBnBwdFused)),
+        ("head_metric", C.POINTER(MmrHeadMetric)),
     ]
 
 

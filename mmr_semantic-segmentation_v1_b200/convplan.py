@@ -554,7 +554,7 @@ def pack_weights_halo(w_oihw, cfg, mode, out=None, stream=None):
 
 
 def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=None, residual=None,
-               relu=False, out_f32=None, stats=None, stats_ld=0, bn_finalize=None, bn_bwd=None):
+               relu=False, out_f32=None, stats=None, stats_ld=0, bn_finalize=None, bn_bwd=None, head_metric=None):
     """sources: [(tensor [N,Hs,Ws,Cs] bf16, up)], packed: bf16 weights from pack_weights_halo,
     groups: [(dst tensor [N,H,W,ldc] bf16, coff)] one per store group of cfg['sg'] channels (bf16 NHWC
     mode), or out_f32 = fp32 [N,C,H,W] (head logits)."""
@@ -576,7 +576,7 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     d.out_stages = max(1, cfg["out_stages"])
     d.direct_store = int(cfg.get("direct", cfg["sg"] < 64))
     keep = [sources, packed, scale, bias, residual, stats]
-    if out_f32 is None:
+    if out_f32 is None and head_metric is None:
         # (tensor, coff) or (tensor, coff, step, oy, ox): pixel (y, x) -> (step*y + oy, step*x + ox) of the tensor
         groups = [g if len(g) == 5 else (g[0], g[1], 1, 0, 0) for g in groups]
         segs = (MmrOutSeg * len(groups))(*[MmrOutSeg(t.data_ptr(), t.shape[3], coff, step, oy, ox)
@@ -589,11 +589,27 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
         d.out_mode = MMR_OUT_BF16_NHWC
         keep += [segs, [t for t, _ in groups]]
     else:
-        assert out_f32.dtype == torch.float32 and tuple(out_f32.shape) == (N, out_f32.shape[1], H, W)
         d.out_mode = MMR_OUT_F32_NCHW
-        d.out_f32 = out_f32.data_ptr()
-        d.out_ldc = out_f32.shape[1]
-        keep.append(out_f32)
+        if out_f32 is not None:
+            assert out_f32.dtype == torch.float32 and tuple(out_f32.shape) == (N, out_f32.shape[1], H, W)
+            d.out_f32 = out_f32.data_ptr()
+            d.out_ldc = out_f32.shape[1]
+            keep.append(out_f32)
+        if head_metric is not None:     # (labels int64 / uint8 [N,H,W] or None, pred uint8 [N,H,W] or None, cm int64 [N,C,C] or None)
+            from ._lib import MmrHeadMetric
+            labels, pred, cm = head_metric
+            hm = MmrHeadMetric()
+            if labels is not None:
+                assert labels.dtype in (torch.int64, torch.uint8) and tuple(labels.shape) == (N, H, W) and labels.is_contiguous()
+                hm.labels, hm.labels_u8 = labels.data_ptr(), int(labels.dtype == torch.uint8)
+            if pred is not None:
+                assert pred.dtype == torch.uint8 and tuple(pred.shape) == (N, H, W) and pred.is_contiguous()
+                hm.pred_out = pred.data_ptr()
+            if cm is not None:
+                assert cm.dtype == torch.int64 and tuple(cm.shape) == (N, cout, cout) and cm.is_contiguous()
+                hm.confusion = cm.data_ptr()
+            d.head_metric = C.pointer(hm)
+            keep += [hm, labels, pred, cm]
     d.cout_total = cout
     d.scale = scale.data_ptr() if scale is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
@@ -624,7 +640,8 @@ def fprop_halo_cfg(sources, cout, bf16_out=True, force=None, stats=False):
 
 
 def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=None, relu=False,
-                     out_f32=None, stats=None, stats_ld=0, force=None, packed=None, cfg=None, bn_finalize=None):
+                     out_f32=None, stats=None, stats_ld=0, force=None, packed=None, cfg=None, bn_finalize=None,
+                     head_metric=None):
     """Forward 3x3 s1 p1 conv over the concatenation of `sources` (see build_fprop)."""
     N = sources[0][0].shape[0]
     H = sources[0][0].shape[1] * sources[0][1]
@@ -632,16 +649,18 @@ def build_fprop_halo(sources, w_oihw, out, *, scale=None, bias=None, residual=No
     cout, cin = w_oihw.shape[0], w_oihw.shape[1]
     # cin below the stored channel count: a zero-padded source (the 3-channel image stored as 16)
     assert cin <= sum(t.shape[3] for t, _ in sources)
+    head = out_f32 is not None or head_metric is not None
     if cfg is None:
-        cfg = fprop_halo_cfg(sources, cout, out_f32 is None, force, stats=stats is not None)
+        cfg = fprop_halo_cfg(sources, cout, not head, force, stats=stats is not None)
     if packed is None:
         packed = pack_weights_halo(w_oihw, cfg, 0)
     groups = None
-    if out_f32 is None:
+    if not head:
         assert out.shape[3] >= cfg["cpad"]
         groups = [(out, g * cfg["sg"]) for g in range(cfg["cpad"] // cfg["sg"])]
     plan = build_halo(cfg, sources, packed, groups, N, H, W, cout, scale=scale, bias=bias, residual=residual,
-                      relu=relu, out_f32=out_f32, stats=stats, stats_ld=stats_ld, bn_finalize=bn_finalize)
+                      relu=relu, out_f32=out_f32, stats=stats, stats_ld=stats_ld, bn_finalize=bn_finalize,
+                      head_metric=head_metric)
     plan.flops = 2 * N * H * W * cout * 9 * cin
     plan.packed = packed
     return plan

@@ -79,6 +79,7 @@ struct HaloParams {
   int stats_ld;
   MmrBnFinalize bnf;  // ticket == nullptr: not fused
   MmrBnBwdFused bb;   // z == nullptr: no fused BatchNorm backward sums
+  MmrHeadMetric hm;   // head launches: argmax / confusion matrix in the epilogue (all NULL: plain logits)
   int dbg;  // diagnostics (MMR_HALO_DBG): 1 no MMA issue, 2 no epilogue work, 4 no halo TMA, 8 no weight TMA
 };
 
@@ -573,19 +574,42 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
 // Epilogue of the segmentation head: up to 16 classes, bias only, fp32 NCHW logits (what `model(img)`
 // returns).  One TMEM round trip per M tile, the bias in registers, one predicated store per class: a
 // warp's 32 pixels are 4 image rows x 8 consecutive pixels, i.e. four full 32-byte sectors per class plane.
+// With a head metric (MmrHeadMetric) the same registers feed torch.argmax's rule and the confusion matrix:
+// `hist` is a per-CTA [classes][classes] table of 32-bit counters in shared memory, flushed to the 64-bit
+// global matrix of image n whenever the CTA moves on to another image (items are ordered image-major, so
+// that is every few items) -- the logits of an eval step then never exist in HBM.
 __device__ __forceinline__ void epi_head_f32(const HaloParams& p, uint32_t tmem_base, uint64_t* tmem_full,
-                                             uint64_t* tmem_empty, int q, int lane) {
+                                             uint64_t* tmem_empty, int q, int lane, unsigned int* hist) {
   const int m = q * 32 + lane;
   const int h = m >> 3, w = m & 7;
   const size_t hw = (size_t)p.H * p.W;
+  const int C = p.cout_total;
+  const bool count = p.hm.confusion != nullptr && p.hm.labels != nullptr;
   float bias[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) bias[j] = (p.bias && j < p.cout_total) ? __ldg(p.bias + j) : 0.f;
-  int it = 0;
+  for (int j = 0; j < 16; ++j) bias[j] = (p.bias && j < C) ? __ldg(p.bias + j) : 0.f;
+  if (count) {
+    for (int k = m; k < C * C; k += 128) hist[k] = 0u;
+    epi_bar();
+  }
+  int it = 0, cur_n = -1;
+  auto flush = [&](int n) {   // all four epilogue warps: counters of image n -> global, then cleared
+    epi_bar();
+    for (int k = m; k < C * C; k += 128) {
+      const unsigned int v = hist[k];
+      if (v) atomicAdd(p.hm.confusion + (size_t)n * C * C + k, (unsigned long long)v);
+      hist[k] = 0u;
+    }
+    epi_bar();
+  };
   for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
     const ItemCoord ic = decode_item(p, item);
     const int buf = it % p.acc_bufs;
     const uint32_t par = (uint32_t)(it / p.acc_bufs) & 1u;
+    if (count && ic.n != cur_n) {
+      if (cur_n >= 0) flush(cur_n);
+      cur_n = ic.n;
+    }
     mbar_wait(&tmem_full[buf], par);
     tc_fence_after();
     const int y = ic.y0 + h;
@@ -600,13 +624,36 @@ __device__ __forceinline__ void epi_head_f32(const HaloParams& p, uint32_t tmem_
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
       if (y < p.H && x < p.W && !(p.dbg & 2)) {
-        float* dst = p.out_f32 + (size_t)ic.n * p.out_ldc * hw + (size_t)y * p.W + x;
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < p.cout_total) dst[(size_t)j * hw] = __uint_as_float(r[j]) + bias[j];
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bias[j];
+        const size_t px = (size_t)y * p.W + x;
+        if (p.out_f32) {
+          float* dst = p.out_f32 + (size_t)ic.n * p.out_ldc * hw + px;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < C) dst[(size_t)j * hw] = v[j];
+        }
+        if (p.hm.pred_out || count) {
+          float best = v[0];
+          int arg = 0;
+#pragma unroll
+          for (int j = 1; j < 16; ++j) {
+            // torch.argmax: first maximal index; NaN counts as maximal (mmr_confusion_from_logits' rule)
+            if (j < C && (v[j] > best || (v[j] != v[j] && best == best))) best = v[j], arg = j;
+          }
+          if (p.hm.pred_out) p.hm.pred_out[(size_t)ic.n * hw + px] = (uint8_t)arg;
+          if (count) {
+            const long long t = p.hm.labels_u8
+                                    ? (long long)__ldg(reinterpret_cast<const uint8_t*>(p.hm.labels) + (size_t)ic.n * hw + px)
+                                    : __ldg(reinterpret_cast<const long long*>(p.hm.labels) + (size_t)ic.n * hw + px);
+            if (t >= 0 && t < C) atomicAdd(&hist[(int)t * C + arg], 1u);
+          }
+        }
       }
     }
   }
+  if (count && cur_n >= 0) flush(cur_n);
 }
 
 // Epilogue family of a launch.  One __global__ instantiation per family: the register allocation and the code
@@ -783,7 +830,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       if (p.sg == 32) epi_fast<32, 0, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
       if (p.sg == 16) epi_fast<16, 0, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
     } else if constexpr (EK == kEpiHead) {
-      epi_head_f32(p, tmem_base, tmem_full, tmem_empty, q, lane);
+      epi_head_f32(p, tmem_base, tmem_full, tmem_empty, q, lane, reinterpret_cast<unsigned int*>(bars + 32));
     } else if constexpr (EK == kEpiAffine) {   // scale / bias / residual / ReLU epilogues (eval mode, biased convs)
       float* aff = nullptr;
       if (p.n_ntiles == 1 && p.gpn == 1) {     // the whole channel set is one store group: stage scale / shift once
@@ -1306,8 +1353,15 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
       p.group_ptr[g] = reinterpret_cast<__nv_bfloat16*>(og.ptr);
     }
   } else {
-    MMR_REQUIRE(d->out_f32 != nullptr && d->n_ntiles == 1, "fp32 NCHW output needs out_f32 and one N tile");
+    const bool metric = d->head_metric && (d->head_metric->pred_out || d->head_metric->confusion);
+    MMR_REQUIRE((d->out_f32 != nullptr || metric) && d->n_ntiles == 1,
+                "fp32 NCHW output needs out_f32 (or a head metric) and one N tile");
     MMR_REQUIRE(d->stats == nullptr, "statistics need the bf16 NHWC output mode");
+    if (d->head_metric) {
+      MMR_REQUIRE(d->bn == 16 && R == 1 && !d->scale && !d->residual && !d->relu && d->cout_total <= 16,
+                  "head metric: needs the head epilogue (bn 16, rph 1, bias only, <= 16 classes)");
+      MMR_REQUIRE(!d->head_metric->confusion || d->head_metric->labels, "head metric: confusion needs labels");
+    }
   }
   p.halo_tx_bytes[0] = (uint32_t)((16 * R + 2) * p.pitch[0] * rb);
   p.halo_tx_bytes[1] = (uint32_t)((16 * R + 2) * p.pitch[1] * rb);
@@ -1322,6 +1376,8 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.tmem_cols = cols;
   size_t smem = (size_t)p.halo_stages * p.halo_stage_bytes + (size_t)p.w_slots * p.w_slot_bytes +
                 (size_t)p.out_stages * p.out_stage_bytes + 1024;  // barriers (256 B) + BN-backward mask affine (512 B)
+  // head confusion counters (classes^2 x 4 B) sit after the barriers: 768 B are free there (up to 13 classes)
+  if (d->out_mode == MMR_OUT_F32_NCHW && d->head_metric && d->cout_total * d->cout_total * 4 > 768) smem += 1024;
   MMR_REQUIRE(smem <= 227 * 1024, "shared memory plan needs %zu bytes (> 227 KB)", smem);
   if (smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM: the TMEM allocation assumes it
   pl->smem_bytes = smem;
@@ -1335,6 +1391,7 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
   p.cout_total = d->cout_total;
   p.stats = d->stats;
   p.stats_ld = d->stats_ld;
+  if (d->head_metric && d->out_mode == MMR_OUT_F32_NCHW) p.hm = *d->head_metric;
   if (const char* dbg = getenv("MMR_HALO_DBG")) p.dbg = atoi(dbg);
   if (d->bn_bwd) {
     const MmrBnBwdFused& b = *d->bn_bwd;

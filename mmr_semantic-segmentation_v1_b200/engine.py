@@ -253,6 +253,8 @@ class Engine:
             fc.insert(0, (self.lib.mmr_zero_async, (C.c_void_p(self.halo_stats.data_ptr()),
                                                      C.c_int64(self.halo_stats_used * 8))))
             self.u8_swaps = [(i + 1, call) for i, call in self.u8_swaps]
+            if getattr(self, "metric_swap", None):
+                self.metric_swap = (self.metric_swap[0] + 1, self.metric_swap[1])
         self.n_launch_fwd = len(fc) + len(self.repack_calls)
 
     def _bn_state(self, unit, bn_name, Cc):
@@ -432,6 +434,20 @@ class Engine:
             out = _Act(op["out"], (n, Ho, Wo, cout))
             out.buf = self._f32(n, cout, Ho, Wo)  # NCHW fp32 logits
             plan = fprop(out.buf, bias=self.P[op["conv"] + ".bias"])
+            if halo and not self.training and op["out"] == "logits" and cout <= 16 and hcfg["bn"] == 16:
+                # eval: the same head with argmax + confusion matrix in its epilogue and NO logits store
+                # (`forward(..., metric=True)` swaps this launch in)
+                self.metric_labels = torch.zeros((n, Ho, Wo), device=self.dev, dtype=torch.int64)
+                self.metric_pred = torch.empty((n, Ho, Wo), device=self.dev, dtype=torch.uint8)
+                self.metric_cm = torch.zeros((n, cout, cout), device=self.dev, dtype=torch.int64)
+                try:
+                    mplan = convplan.build_fprop_halo(sources, w, None, cfg=hcfg, packed=unit["wf_h"],
+                                                      bias=self.P[op["conv"] + ".bias"],
+                                                      head_metric=(self.metric_labels, self.metric_pred, self.metric_cm))
+                    unit["mplan"] = mplan
+                    self.metric_swap = (len(fc) - 1, (self.lib.mmr_halo_conv_plan_run, (mplan.handle,)))
+                except _lib.MmrError:      # 14-16 classes need 1 KB more shared memory than this plan has left:
+                    self.metric_swap = None  # model.segment() then takes forward() + the metric kernel
             up = op.get("up", 1)
             unit["up"] = up
             unit["result"] = out.buf
@@ -828,9 +844,12 @@ class Engine:
         if err:
             raise _lib.MmrError(self.lib.mmr_last_error().decode(errors="replace"))
 
-    def forward(self, x=None, stream=None):
+    def forward(self, x=None, stream=None, metric=False):
         """x: fp32 NCHW [N,3,H,W] on the device (copied into the plan's input buffer), or uint8 NHWC
-        [N,H,W,3] frames (normalised by `set_input_norm` constants inside the first kernels)."""
+        [N,H,W,3] frames (normalised by `set_input_norm` constants inside the first kernels).
+        metric (eval engines with a fused head metric): run the head with argmax + confusion matrix in its
+        epilogue instead of storing logits; the caller fills `metric_labels` first and reads `metric_pred` /
+        `metric_cm` (re-zeroed by this call) afterwards; returns None."""
         u8 = x is not None and x.dtype == torch.uint8
         if u8:
             self.x_u8.copy_(x, non_blocking=True)
@@ -841,6 +860,18 @@ class Engine:
         elif x is not None:
             self.x_in.copy_(x, non_blocking=True)
         fwd = self._fwd_u8 if u8 else self.fwd_calls
+        if metric:
+            key = ("u8" if u8 else "f32") + "+metric"
+            if key not in self._train_calls:
+                calls = list(fwd)
+                i, call = self.metric_swap
+                calls[i] = call
+                zero = (self.lib.mmr_zero_async, (C.c_void_p(self.metric_cm.data_ptr()),
+                                                  C.c_int64(self.metric_cm.numel() * 8)))
+                self._train_calls[key] = self.repack_calls + [zero] + calls
+            self._run(self._train_calls[key], stream)
+            self.generation += 1
+            return None
         # Both modes re-derive the bf16 GEMM weights (and, in eval mode, the folded BatchNorm constants) from
         # the fp32 masters at the head of every forward: the optimiser kernels, the training engine's running
         # statistics and load_state_dict all write those buffers without telling this engine (two launches,

@@ -74,6 +74,16 @@ class Evaluate:
         cm = cm.sum(0)
         self._cm = cm if self._cm is None else self._cm + cm
 
+    def addBatchFromModel(self, model, img, labels):
+        """`seg = model(img); evaluator.addBatch(seg, oneHotGT, args); seg = torch.argmax(seg, 1)`
+        (SU/ModelTraining.py:736-760) as ONE replay of the eval plan: argmax and confusion counts are taken in
+        the segmentation head's epilogue (`model.segment`), the logits never reach HBM.  labels: int64 [N,H,W]
+        class indices (what the one-hot ground truth encodes).  Returns the argmax'ed prediction (uint8 [N,H,W])."""
+        pred, cm = model.segment(img, labels)
+        cm = cm.sum(0)
+        self._cm = cm if self._cm is None else self._cm + cm
+        return pred
+
     def confusion(self):
         """int64 [C,C] on the device: rows ground truth, columns prediction."""
         return self._cm

@@ -341,6 +341,40 @@ class _PlanModel(nn.Module):
         return [self._finish(t.clone()) for t in out] if isinstance(out, list) else self._finish(out.clone())
 
 
+    @torch.no_grad()
+    def segment(self, x, labels=None):
+        """The eval step of the reference in one replay -- `seg = model(img); evaluator.addBatch(seg, oneHotGT,
+        args); seg = torch.argmax(seg, 1)` (SU/ModelTraining.py:736-760, SU/ModelEval.py:363-458) -- with the
+        argmax and the confusion matrix taken in the segmentation head's epilogue: the logits never reach HBM
+        (at BASELINE config 5 that is 3.4 GB per batch written and read back).
+        x as for forward(); labels: int64 [N,H,W] class indices (or None).  Returns (pred uint8 [N,H,W] --
+        torch.argmax's first-maximum rule, bit-identical to argmax of forward()'s logits --, confusion int64
+        [N,C,C] with rows = label, columns = prediction, or None without labels); both are fresh tensors.
+        Architectures whose head is not on the halo kernel (1x1 heads) take forward() + the metric kernel."""
+        if self.training:
+            raise _lib.MmrError("segment() is the eval-mode step: call model.eval() first")
+        if x.dtype != torch.uint8 and x.dtype != torch.float32:
+            x = x.float()
+        eng = self._engine_for(x, training=False)
+        if getattr(eng, "metric_swap", None) is None:
+            from .metrics import confusion_matrix
+            logits = eng.forward(x.contiguous())
+            if labels is None:
+                cm, pred = confusion_matrix(logits, torch.zeros(logits.shape[:1] + logits.shape[2:], dtype=torch.int64,
+                                                                device=logits.device), return_pred=True)
+                return pred.to(torch.uint8), None
+            cm, pred = confusion_matrix(logits, labels, return_pred=True)
+            return pred.to(torch.uint8), cm
+        if labels is not None:
+            if labels.shape != eng.metric_labels.shape:
+                raise ValueError("labels must be [N, H, W] = %s, got %s" % (tuple(eng.metric_labels.shape), tuple(labels.shape)))
+            eng.metric_labels.copy_(labels, non_blocking=True)
+        else:
+            eng.metric_labels.fill_(-1)      # out of range: nothing is counted
+        eng.forward(x.contiguous(), metric=True)
+        return eng.metric_pred.clone(), (eng.metric_cm.clone() if labels is not None else None)
+
+
 class UnetPlusPlus(_PlanModel):
     """`smp.UnetPlusPlus` with the reference's arguments.  `encoder_weights="imagenet"` loads the torchvision
     checkpoint from the local torch-hub cache when present and otherwise warns and keeps the random

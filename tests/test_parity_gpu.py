@@ -168,3 +168,37 @@ def test_config5_shape_eval_and_bit_exact_confusion():
     assert np.array_equal(ev.tp.numpy(), tp)
     want_iou = tp / (full.sum(0) + full.sum(1) - tp + 1e-15)
     assert np.abs(ev.getIoU().numpy() - want_iou).max() <= 1e-12
+
+
+@pytest.mark.parametrize("classes,shape,u8_labels", [(10, (2, 96, 160), False), (2, (3, 64, 64), False), (16, (1, 64, 96), False)])
+def test_fused_head_metric_is_bit_exact(classes, shape, u8_labels):
+    """argmax + confusion matrix in the head's epilogue (model.segment) against the two-kernel path
+    (forward -> logits in HBM -> mmr_confusion_from_logits) and the int64 numpy oracle on the same logits:
+    predictions and counts identical, including labels outside [0, C) (skipped) and an accumulating Evaluate."""
+    from oracle import metrics as OM
+    from mmrseg_b200.metrics import Evaluate, confusion_matrix
+    _, net = model_pair(classes)
+    n, h, w = shape
+    x, y = synthetic_batch(n, classes, h, w)
+    y[0, :3, :5] = classes + 3          # out of range: not counted
+    y[0, 3, :5] = -1
+    net.eval()
+    with torch.no_grad():
+        logits = net(x.cuda())
+    cm2, pred2 = confusion_matrix(logits, y.cuda(), return_pred=True)
+    pred, cm = net.segment(x.cuda(), y.cuda())
+    assert pred.dtype == torch.uint8 and cm.dtype == torch.int64
+    assert torch.equal(pred.long(), pred2) and torch.equal(cm, cm2)
+    want_pred = OM.argmax_first(logits.cpu().numpy())
+    assert np.array_equal(pred.cpu().numpy(), want_pred)
+    assert np.array_equal(cm.cpu().numpy(), OM.confusion_matrix(want_pred, y.numpy(), classes))
+    assert int(cm.sum()) == n * h * w - 20
+    # a second call starts from zero again; without labels nothing is counted
+    pred_b, cm_b = net.segment(x.cuda(), y.cuda())
+    assert torch.equal(cm_b, cm) and torch.equal(pred_b, pred)
+    pred_c, none = net.segment(x.cuda())
+    assert none is None and torch.equal(pred_c, pred)
+    ev = Evaluate({i: i for i in range(classes)}, use_gpu=True)
+    for _ in range(2):
+        ev.addBatchFromModel(net, x.cuda(), y.cuda())
+    assert torch.equal(ev.confusion(), 2 * cm.sum(0))
