@@ -192,7 +192,7 @@ def build_fprop(sources, weights, ksize, stride, pad, out, *, scale=None, bias=N
     return plan
 
 
-def build_dgrad(dz, weights_d, ksize, stride, pad, in_hw, grads, *, bn=None, box=None):
+def build_dgrad(dz, weights_d, ksize, stride, pad, in_hw, grads, *, bn=None, box=None, bias=None):
     """Data gradient.  dz: [N,Ho,Wo,Cout] bf16.  weights_d: bf16 [Cin_total][taps*Cout],
     column = (ky*k+kx)*Cout + co.  in_hw: (Hin, Win) of the (virtually concatenated) conv
     input.  grads: list of (tensor [N,Hin,Win,Cs] bf16) in concat order — one per source;
@@ -235,8 +235,10 @@ def build_dgrad(dz, weights_d, ksize, stride, pad, in_hw, grads, *, bn=None, box
         classes = [(py, px) for py in (0, 1) for px in (0, 1)]
         ksteps = [ksteps_for(py, px) for py, px in classes]
         grid, o_mul = (Win // 2, Hin // 2), (2, 2)
+    # bias: a per-output-channel constant added in the epilogue -- what makes this "data gradient" the FORWARD
+    # pass of a ConvTranspose2d(k, stride) (whose arithmetic is exactly the data gradient of Conv2d(k, stride))
     d, keep = _make_desc([(dz, 1)], ksteps, classes, weights_d, bk, bn, out_segs, grid, N, o_mul,
-                         Hin, Win, cin_total, None, None, None, False, MMR_OUT_BF16_NHWC, box)
+                         Hin, Win, cin_total, None, bias, None, False, MMR_OUT_BF16_NHWC, box)
     plan = ConvPlan(d, keep)
     plan.flops = 2 * N * Ho * Wo * Cout * ksize * ksize * cin_total
     return plan
@@ -280,9 +282,11 @@ class WgradPlan:
 
 
 def build_wgrad(dz, sources, ksize, stride, pad, dst, *, cout_gemm=None, dst_cin=None, n_sms=148,
-                n_split=None, partial=None):
+                n_split=None, partial=None, dz_c0=0):
     """Weight gradient.  dz: [N,Ho,Wo,Cz] bf16 (Cz >= cout_gemm).  sources: as in build_fprop.
-    dst: fp32 OIHW gradient [Cout][Cin_total][k][k] (written or accumulated at run time)."""
+    dst: fp32 OIHW gradient [Cout][Cin_total][k][k] (written or accumulated at run time).
+    dz_c0: first channel of dz this plan reads (a plan covers at most 512 output channels; wider layers run one
+    plan per slice: dz channels [dz_c0, dz_c0 + cout_gemm) -> dst rows of the same range, passed as dst)."""
     from ._lib import MmrWgChunk, MmrWgradDesc
     N, Ho, Wo, Cz = dz.shape
     assert dz.dtype == torch.bfloat16 and dz.is_contiguous()
@@ -294,7 +298,9 @@ def build_wgrad(dz, sources, ksize, stride, pad, dst, *, cout_gemm=None, dst_cin
         dst_cin = dst.shape[1]
     assert dst.numel() == cout * dst_cin * taps
     if cout_gemm is None:
-        cout_gemm = Cz
+        cout_gemm = Cz - dz_c0
+    assert 0 <= dz_c0 and dz_c0 + cout_gemm <= Cz and dz_c0 % 8 == 0
+    dz_ptr = dz.data_ptr() + 2 * dz_c0
     chunk_ch = pick_bk([t.shape[3] for t, _ in sources])
     cpm = 128 // chunk_ch
     any_up = any(up == 2 for _, up in sources)
@@ -337,14 +343,14 @@ def build_wgrad(dz, sources, ksize, stride, pad, dst, *, cout_gemm=None, dst_cin
     d = MmrWgradDesc()
     if any_up:
         gx, gy = Wo // 2, Ho // 2
-        d.dz = MmrSrc(dz.data_ptr(), Cz, Wo, Ho, N, 2)
+        d.dz = MmrSrc(dz_ptr, Cz, Wo, Ho, N, 2)
         d.dz_a = 2
         for ci, (py, px) in enumerate(classes):
             d.dz_bx[ci], d.dz_by[ci] = px, py
         srcs = [(t, 1 if up == 2 else 2) for t, up in sources]
     else:
         gx, gy = Wo, Ho
-        d.dz = MmrSrc(dz.data_ptr(), Cz, Wo, Ho, N, 1)
+        d.dz = MmrSrc(dz_ptr, Cz, Wo, Ho, N, 1)
         d.dz_a = 1
         srcs = [(t, stride) for t, _ in sources]
     d.nsrc = len(srcs)

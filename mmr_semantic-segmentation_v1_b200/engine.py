@@ -195,6 +195,8 @@ class Engine:
                           out.buf, out.idx)
             elif kind in ("conv", "head"):
                 self._fwd_conv(op)
+            elif kind == "convt":
+                self._fwd_convt(op)
             elif kind == "pack16":   # image -> NHWC bf16, 3 channels zero-padded to 16
                 act = _Act(op["out"], (N, H, W, 16), needs_grad=False)
                 act.buf = self._bf16(N, H, W, 16)
@@ -356,6 +358,39 @@ class Engine:
         unit["fplan"] = plan
         if self.training:
             self._fwd_bn_train(unit, unit["z"], out.buf, None, True)
+
+    def _fwd_convt(self, op):
+        """nn.ConvTranspose2d(cin, cout, kernel_size=2, stride=2) with bias (SU/UArchModel/unet_parts.py:269):
+        out[n, 2y+ky, 2x+kx, co] = b[co] + sum_ci x[n, y, x, ci] * W[ci, co, ky, kx], i.e. exactly the data
+        gradient of V = Conv2d(cout -> cin, k 2, stride 2) whose OIHW weight IS the ConvTranspose2d weight
+        ([cin][cout][2][2]).  So the forward runs as V's dgrad plan (four output parities, one 1x1 GEMM each,
+        bias in the epilogue), the data gradient as V's fprop plan, the weight gradient as V's wgrad plan with
+        the roles of activation and gradient swapped -- all on the first-generation tcgen05 kernels."""
+        fc = self.fwd_calls
+        src = self.acts[op["in"]]
+        n, h, w_, cin = src.shape
+        wt = self.P[op["conv"] + ".weight"]        # [cin][cout][2][2]
+        assert tuple(wt.shape) == (cin, op["cout"], 2, 2), (op["conv"], tuple(wt.shape), cin)
+        cout = op["cout"]
+        assert cin % 16 == 0 and cout % 16 == 0
+        out = _Act(op["out"], (n, 2 * h, 2 * w_, cout))
+        out.buf = self._bf16(*out.shape)
+        unit = {"kind": "convt", "op": dict(op, relu=False, bias=True), "cout": cout, "cpad": cout, "k": 2, "s": 2,
+                "pad": 0, "srcs": [(src, 1)], "in_hw": (h, w_), "out": out, "res": None, "halo": False}
+        # V's GEMM layouts: fprop rows = V's outputs (cin of the ConvT), dgrad rows = V's inputs (cout of the ConvT)
+        unit["wf"] = self._bf16(cin, 4 * cout, zero=True)
+        unit["wd"] = self._bf16(cout, 4 * cin, zero=True)
+        self._rec(self.repack_calls, "mmr_repack_weights", wt, cin, cout, 4, unit["wf"], 4 * cout, unit["wd"],
+                  4 * cin, cin)
+        plan = convplan.build_dgrad(src.buf, unit["wd"], 2, 2, 0, (2 * h, 2 * w_), [out.buf],
+                                    bias=self.P[op["conv"] + ".bias"])
+        plan.flops = 2 * n * h * w_ * cin * cout * 4
+        fc.append((self.lib.mmr_conv_plan_run, (plan.handle, 0)))
+        self.conv_flops_fwd += plan.flops
+        unit["fplan"] = plan
+        out.producer = unit
+        self.acts[op["out"]] = out
+        self.units.append(unit)
 
     def _fold(self, unit, bn_name, Cc, conv_bias=None, rep=1):
         """Eval mode: scale/shift from the running statistics, recomputed by ONE `mmr_bn_fold_batch` launch at the
@@ -691,6 +726,17 @@ class Engine:
                                              gw.view(gw.shape[0], 147, 1, 1), n_sms=self.n_sms,
                                              partial=self.wg_partial)
                 wplan.flops = 2 * Pn * u["cout"] * 147
+            elif kind == "convt":
+                # dW[ci][co][ky][kx] = sum x[ci] * g[co, 2y+ky, 2x+kx]: V's weight gradient with V's "dz" = the
+                # ConvT input and V's source = the ConvT output gradient
+                src_a = u["srcs"][0][0]
+                cin_t = src_a.shape[3]
+                u["wplans"] = [convplan.build_wgrad(src_a.buf, [(dz, 1)], 2, 2, 0, gw[c0:c0 + 512], dz_c0=c0,
+                                                    cout_gemm=min(512, cin_t - c0), n_sms=self.n_sms,
+                                                    partial=self.wg_partial)
+                               for c0 in range(0, cin_t, 512)]      # a plan covers <= 512 GEMM columns
+                wplan = u["wplans"][0]
+                wplan.flops = u["fplan"].flops
             else:
                 sources = [(a.buf, up) for a, up in u["srcs"]]
                 if u.get("halo"):
@@ -707,7 +753,8 @@ class Engine:
         elif isinstance(wplan, convplan.WgradHaloPlan):
             calls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, acc)))
         else:
-            calls.append((self.lib.mmr_wgrad_plan_run, (wplan.handle, 0, acc)))
+            for wp in u.get("wplans", [wplan]):
+                calls.append((self.lib.mmr_wgrad_plan_run, (wp.handle, 0, acc)))
         calls.append((Engine._mark, ("side_end", self._bwd_t)))
         if record_hooks:
             self.conv_flops_bwd += wplan.flops
@@ -758,6 +805,9 @@ class Engine:
             if u.get("halo"):
                 dplan = convplan.build_dgrad_halo(dz, self.P[conv + ".weight"], grads, cfg=u["dcfg"],
                                                   packed=u["wd_h"], bn_bwd=bb)
+            elif kind == "convt":   # dx = V(g): a plain 2x2 stride-2 conv of the output gradient
+                dplan = convplan.build_fprop([(dz, 1)], u["wf"], 2, 2, 0, grads[0])
+                dplan.flops = u["fplan"].flops
             else:
                 dplan = convplan.build_dgrad(dz, u["wd"], u["k"], u["s"], u["pad"], (Hin, Win), grads)
             u[key] = dplan

@@ -148,12 +148,15 @@ def resnet_unet_graph(resnet_model=18, n_class=10):
     return ops
 
 
-def unet_graph(n_classes=2):
+def unet_graph(n_classes=2, bilinear=True):
     """The reference's in-tree `UNet(n_channels=3, n_classes, bilinear=True)` (SU/UArchModel/unet.py:104-245,
     unet_parts.py): DoubleConv = (3x3 conv WITH bias -> BatchNorm -> ReLU) x 2, Down = MaxPool2d(2) +
     DoubleConv, Up = nearest x2 (the `bilinear=True` branch builds nn.Upsample(mode='nearest')) ->
     cat([skip, upsampled]) -> DoubleConv(in, out, mid = in // 2), OutConv = 1x1 conv with bias.
-    `F.pad` to the skip's size is the identity when H and W are multiples of 16."""
+    `F.pad` to the skip's size is the identity when H and W are multiples of 16.
+    bilinear=False (unet_parts.py:269; unet.py:153-163): Up = ConvTranspose2d(in, in // 2, kernel_size=2, stride=2)
+    -> cat([skip, upsampled]) -> DoubleConv(in, out), and down4 widens to 1024 channels
+      {'op': 'convt', 'in', 'out', 'conv', 'cout'}          2x2 stride-2 transposed conv with bias"""
     ops = [{"op": "pack16", "out": "image16"}]
 
     def double_conv(prefix, src, mid, cout, out, cin_pad=False):
@@ -165,13 +168,18 @@ def unet_graph(n_classes=2):
 
     double_conv("inc.", [("image16", 1)], 64, 64, "x1", cin_pad=True)
     prev = "x1"
-    for i, cout in enumerate((128, 256, 512, 512), start=1):
+    factor = 2 if bilinear else 1
+    for i, cout in enumerate((128, 256, 512, 1024 // factor), start=1):
         ops.append({"op": "maxpool", "in": prev, "out": "p%d" % i, "k": 2})
         double_conv("down%d.maxpool_conv.1." % i, [("p%d" % i, 1)], cout, cout, "x%d" % (i + 1))
         prev = "x%d" % (i + 1)
-    for i, (skip, cin, cout) in enumerate((("x4", 1024, 256), ("x3", 512, 128), ("x2", 256, 64), ("x1", 128, 64)),
-                                          start=1):
-        double_conv("up%d.conv." % i, [(skip, 1), (prev, 2)], cin // 2, cout, "u%d" % i)
+    for i, (skip, cin, cout) in enumerate((("x4", 1024, 512 // factor), ("x3", 512, 256 // factor),
+                                           ("x2", 256, 128 // factor), ("x1", 128, 64)), start=1):
+        if bilinear:
+            double_conv("up%d.conv." % i, [(skip, 1), (prev, 2)], cin // 2, cout, "u%d" % i)
+        else:
+            ops.append({"op": "convt", "in": prev, "out": "t%d" % i, "conv": "up%d.up" % i, "cout": cin // 2})
+            double_conv("up%d.conv." % i, [(skip, 1), ("t%d" % i, 1)], cout, cout, "u%d" % i)
         prev = "u%d" % i
     ops.append({"op": "head", "out": "logits", "conv": "outc.conv", "src": [(prev, 1)], "k": 1,
                 "cout": n_classes})
@@ -182,9 +190,9 @@ def graph_param_names(ops):
     """state_dict names of the parameters a graph reads (their gradients are produced by the plan)."""
     names = []
     for op in ops:
-        if op["op"] in ("conv", "head", "stem"):
+        if op["op"] in ("conv", "head", "stem", "convt"):
             names.append(op["conv"] + ".weight")
-            if op["op"] == "head" or op.get("bias"):
+            if op["op"] in ("head", "convt") or op.get("bias"):
                 names.append(op["conv"] + ".bias")
             if op.get("bn"):
                 names += [op["bn"] + ".weight", op["bn"] + ".bias"]

@@ -482,11 +482,15 @@ class _Down(nn.Module):
         self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), _DoubleConv(cin, cout))
 
 
-class _Up(nn.Module):
-    def __init__(self, cin, cout):
+class _Up(nn.Module):      # SU/UArchModel/unet_parts.py:248-271
+    def __init__(self, cin, cout, bilinear=True):
         super().__init__()
-        self.up = nn.Upsample(scale_factor=2, mode="nearest")
-        self.conv = _DoubleConv(cin, cout, cin // 2)
+        if bilinear:
+            self.up = nn.Upsample(scale_factor=2, mode="nearest")
+            self.conv = _DoubleConv(cin, cout, cin // 2)
+        else:
+            self.up = nn.ConvTranspose2d(cin, cin // 2, kernel_size=2, stride=2)
+            self.conv = _DoubleConv(cin, cout)
 
 
 class _OutConv(nn.Module):
@@ -499,8 +503,10 @@ class UNet(_PlanModel):
     """The reference's in-tree `UNet(n_channels, n_classes, bilinear)` (SU/UArchModel/unet.py:104-245;
     constructed as `UNet(n_channels=3, n_classes=num_classes, bilinear=True)` at SU/ModelTraining.py:242 and
     SU/ModelEval.py:328): same module tree and `state_dict()` keys, default PyTorch initialisation in the
-    same construction order.  Only the configuration the reference constructs is built (3 input channels,
-    `bilinear=True`, whose Up block is nearest x2); the transposed-convolution variant raises."""
+    same construction order.  `bilinear=True` (what the scripts construct) has a nearest-x2 Up block that is
+    folded into the consumer conv's loader; `bilinear=False` upsamples with ConvTranspose2d(in, in // 2, 2, 2)
+    (unet_parts.py:269), whose forward is the data gradient of a 2x2 stride-2 conv on the tcgen05 kernels
+    (engine._fwd_convt).  Only n_channels=3 (the reference's call sites) is built."""
 
     _size_multiple = 16   # four MaxPool2d(2) stages; F.pad to the skip size is then the identity
 
@@ -508,23 +514,21 @@ class UNet(_PlanModel):
         super().__init__()
         if n_channels != 3:
             raise NotImplementedError("only n_channels=3 is built (the reference's call sites)")
-        if not bilinear:
-            raise NotImplementedError("bilinear=False (ConvTranspose2d upsampling) is not built; the reference "
-                                      "constructs UNet(..., bilinear=True)")
         self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear
         self.inc = _DoubleConv(n_channels, 64)
         self.down1 = _Down(64, 128)
         self.down2 = _Down(128, 256)
         self.down3 = _Down(256, 512)
-        self.down4 = _Down(512, 512)
-        self.up1 = _Up(1024, 256)
-        self.up2 = _Up(512, 128)
-        self.up3 = _Up(256, 64)
-        self.up4 = _Up(128, 64)
+        factor = 2 if bilinear else 1                      # unet.py:153-163
+        self.down4 = _Down(512, 1024 // factor)
+        self.up1 = _Up(1024, 512 // factor, bilinear)
+        self.up2 = _Up(512, 256 // factor, bilinear)
+        self.up3 = _Up(256, 128 // factor, bilinear)
+        self.up4 = _Up(128, 64, bilinear)
         self.outc = _OutConv(64, n_classes)
 
     def _graph(self):
-        return graph.unet_graph(self.n_classes)
+        return graph.unet_graph(self.n_classes, self.bilinear)
 
 
 def create_model(arch="UnetPlusPlus", encoder_name="resnet18", encoder_weights=None, in_channels=3,

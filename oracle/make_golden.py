@@ -13,6 +13,7 @@ What is pinned:
                           torch.manual_seed(6210) with torchvision `pretrained` patched off
                           (no network); stores the input, the logits and a per-tensor checksum
                           of the state_dict so the weights can be regenerated and verified.
+  unet_convt_reference.npz  the same file's UNet(3, 3, bilinear=False): ConvTranspose2d 2x2 stride-2 upsampling
   unet_reference.npz      SU/UArchModel/unet.py UNet(n_channels=3, n_classes=3, bilinear=True) (the call
                           of SU/ModelTraining.py:242): eval-mode logits with randomised BatchNorm
                           statistics and train-mode logits on a seeded 2x3x32x48 input, same checksums.
@@ -51,12 +52,14 @@ def metric_cases():
     return cases
 
 
-def unet_golden():
-    """Run the reference's own UNet (package import: unet.py does `from .unet_parts import *`)."""
-    sys.path.insert(0, REF)
+def unet_golden(bilinear=True):
+    """Run the reference's own UNet (package import: unet.py does `from .unet_parts import *`); bilinear=False is
+    the ConvTranspose2d variant of unet_parts.py:269 (-> unet_convt_reference.npz)."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
     from UArchModel import unet as ref_unet  # the reference's SU/UArchModel/unet.py
     torch.manual_seed(6210)
-    model = ref_unet.UNet(n_channels=3, n_classes=3, bilinear=True)
+    model = ref_unet.UNet(n_channels=3, n_classes=3, bilinear=bilinear)
     g = torch.Generator().manual_seed(6211)
     for m in model.modules():   # non-trivial BatchNorm state, as tests/helpers.model_pair does
         if isinstance(m, torch.nn.BatchNorm2d):
@@ -72,16 +75,18 @@ def unet_golden():
     model.train()
     with torch.no_grad():
         y_train = model(x)
-    np.savez_compressed(os.path.join(OUT, "unet_reference.npz"), x=x.numpy(), logits_eval=y_eval.numpy(),
+    name = "unet_reference.npz" if bilinear else "unet_convt_reference.npz"
+    np.savez_compressed(os.path.join(OUT, name), x=x.numpy(), logits_eval=y_eval.numpy(),
                         logits_train=y_train.numpy(), keys=np.array(list(sums.keys())),
                         sums=np.array(list(sums.values())))
-    print("wrote unet_reference.npz")
+    print("wrote", name)
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--unet-only" in sys.argv:
         unet_golden()
+        unet_golden(bilinear=False)
         return
     U = load_reference_utils()
     args = types.SimpleNamespace(dataset="sarrarp50")

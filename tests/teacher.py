@@ -76,6 +76,12 @@ def check_forward(eng, P, x_in, training=True):
             want = F.interpolate(_nchw(u["src"].buf), scale_factor=2, mode="bilinear", align_corners=True)
             rows.append((u["out"].name, "bilinear x2", "bf16", _rel(_nchw(u["out"].buf), _r(want))))
             continue
+        if kind == "convt":     # nn.ConvTranspose2d(cin, cout, 2, stride=2) with bias
+            op = u["op"]
+            want = F.conv_transpose2d(_nchw(u["srcs"][0][0].buf), _r(P[op["conv"] + ".weight"]), P[op["conv"] + ".bias"],
+                                      stride=2)
+            rows.append((op["out"], "transposed conv", "bf16", _rel(_nchw(u["out"].buf), _r(want))))
+            continue
         if kind not in ("stem", "conv", "head"):
             continue
         op = u["op"]
@@ -135,6 +141,18 @@ def check_backward(eng, P, G, x_in):
                 y = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
             y.backward(_gathered(out))
             rows.append((out.name, kind + " input grad", "bf16", _rel(_nchw(eng.arena_view(("gin", id(u)), src.shape)), _r(x.grad))))
+            continue
+        if kind == "convt":
+            op, out, src = u["op"], u["out"], u["srcs"][0][0]
+            g_eng = _nchw(eng.arena_view(("g", id(u)), out.shape))
+            rows.append((op["out"], "g", "bf16", _rel(g_eng, _r(_gathered(out)))))
+            rows.append((op["out"], "bias grad", "f32", _rel(G[op["conv"] + ".bias"], _gathered(out).sum((0, 2, 3)))))
+            x = _nchw(src.buf).requires_grad_(True)
+            W = _r(P[op["conv"] + ".weight"]).requires_grad_(True)
+            F.conv_transpose2d(x, W, None, stride=2).backward(g_eng.contiguous())
+            rows.append((op["out"], "weight grad", "f32", _rel(G[op["conv"] + ".weight"], W.grad)))
+            rows.append((op["out"], "data grad -> %s" % src.name, "bf16",
+                         _rel(_nchw(eng.arena_view(("dx", id(u), 0), src.shape)), _r(x.grad))))
             continue
         if kind not in ("stem", "conv", "head"):
             continue

@@ -75,10 +75,10 @@ def test_resnet_unet_matches_reference_golden():
     assert np.allclose(y.numpy(), g["logits"], rtol=0, atol=1e-5)
 
 
-def _oracle_unet_like_golden():
+def _oracle_unet_like_golden(bilinear=True):
     from oracle.unet import UNet
     torch.manual_seed(6210)
-    model = UNet(3, 3, bilinear=True)
+    model = UNet(3, 3, bilinear=bilinear)
     g = torch.Generator().manual_seed(6211)
     for m in model.modules():
         if isinstance(m, torch.nn.BatchNorm2d):
@@ -106,6 +106,26 @@ def test_unet_matches_reference_golden():
     with torch.no_grad():
         assert np.allclose(model(x).numpy(), g["logits_train"], rtol=0, atol=1e-5)
     assert sum(p.numel() for p in model.parameters()) == 17267523     # 17.27 M
+
+
+def test_unet_convtranspose_matches_reference_golden():
+    """The bilinear=False variant (ConvTranspose2d(in, in // 2, 2, 2) upsampling, unet_parts.py:269; down4 widens
+    to 1024 channels, unet.py:153-163) against the reference's own UNet(3, 3, bilinear=False)."""
+    g = np.load(os.path.join(GOLD, "unet_convt_reference.npz"))
+    model = _oracle_unet_like_golden(bilinear=False)
+    sd = model.state_dict()
+    assert [str(k) for k in g["keys"]] == [k for k, v in sd.items() if v.dtype.is_floating_point]
+    for k, s in zip(g["keys"], g["sums"]):
+        assert abs(float(sd[str(k)].double().sum()) - float(s)) <= 1e-9 * max(1.0, abs(float(s))), k
+    x = torch.from_numpy(g["x"])
+    model.eval()
+    with torch.no_grad():
+        assert np.allclose(model(x).numpy(), g["logits_eval"], rtol=0, atol=1e-5)
+    model.train()
+    with torch.no_grad():
+        assert np.allclose(model(x).numpy(), g["logits_train"], rtol=0, atol=1e-5)
+    assert sum(p.numel() for p in model.parameters()) == 31043651     # 31.04 M
+    assert tuple(sd["up1.up.weight"].shape) == (1024, 512, 2, 2)
 
 
 def test_unetpp_structure_pins():

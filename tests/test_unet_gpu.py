@@ -20,11 +20,11 @@ import torch.nn.functional as F
 from tests.helpers import install_masks_by_call_order, install_pool_routes, rel, synthetic_batch
 
 
-def _pair(n_classes, seed=6210):
+def _pair(n_classes, seed=6210, bilinear=True):
     from oracle.unet import UNet as OracleNet
     from mmrseg_b200.models import UNet
     torch.manual_seed(seed)
-    ref = OracleNet(3, n_classes, bilinear=True)
+    ref = OracleNet(3, n_classes, bilinear=bilinear)
     g = torch.Generator().manual_seed(seed + 1)
     for m in ref.modules():
         if isinstance(m, torch.nn.BatchNorm2d):
@@ -32,7 +32,7 @@ def _pair(n_classes, seed=6210):
             m.bias.data.normal_(0, 0.2, generator=g)
             m.running_mean.normal_(0, 0.2, generator=g)
             m.running_var.uniform_(0.5, 1.5, generator=g)
-    net = UNet(3, n_classes, bilinear=True)
+    net = UNet(3, n_classes, bilinear=bilinear)
     net.load_state_dict(ref.state_dict(), strict=True)
     return ref, net
 
@@ -47,9 +47,10 @@ def test_state_dict_keys_and_errors():
     assert list(net.state_dict().keys()) == list(ref.state_dict().keys())
     assert net.outc.conv.weight.shape == (3, 64, 1, 1)
     with pytest.raises(NotImplementedError):
-        UNet(3, 2, bilinear=False)
-    with pytest.raises(NotImplementedError):
         UNet(1, 2, bilinear=True)
+    ref_t, net_t = _pair(3, bilinear=False)      # ConvTranspose2d variant (unet_parts.py:269)
+    assert list(net_t.state_dict().keys()) == list(ref_t.state_dict().keys())
+    assert net_t.up1.up.weight.shape == (1024, 512, 2, 2) and net_t.down4.maxpool_conv[1].double_conv[0].out_channels == 1024
 
 
 @pytest.mark.gpu
@@ -145,3 +146,38 @@ def test_train_step_matches_oracle(n_classes, n, h, w):
     for name, b in net.named_buffers():
         if name.endswith("running_mean"):
             assert rel(b.cpu(), rb[name]) <= 2e-2, name
+
+
+@pytest.mark.gpu
+def test_convtranspose_variant_matches_oracle_and_reference_golden():
+    """UNet(3, C, bilinear=False): ConvTranspose2d(in, in // 2, 2, stride=2) upsampling (unet_parts.py:269) as the
+    data gradient of a 2x2 stride-2 conv on the tcgen05 kernels.  Eval logits against the oracle and against the
+    golden logits produced by RUNNING the reference's own UNet(3, 3, bilinear=False) (oracle/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_convt_reference.npz"))
+    from tests.test_oracle_cpu import _oracle_unet_like_golden
+    from mmrseg_b200.models import UNet
+    ref = _oracle_unet_like_golden(bilinear=False)
+    net = UNet(3, 3, bilinear=False)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net = net.cuda().eval()
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        got = net(x.cuda()).cpu()
+    assert rel(got, torch.from_numpy(g["logits_eval"])) <= 2e-2
+    net.train()
+    with torch.no_grad():
+        got_t = net(x.cuda()).cpu()
+    assert rel(got_t, torch.from_numpy(g["logits_train"])) <= 8e-2
+
+
+@pytest.mark.gpu
+def test_convtranspose_variant_teacher_forced(monkeypatch):
+    """Every unit of the ConvTranspose2d U-Net, forward and backward, recomputed in fp32 from the engine's own
+    operands (tests/teacher.py): transposed-conv output / data gradient to one bf16 ulp flip, weight and bias
+    gradients to 1e-4."""
+    from tests.test_parity_gpu import _teacher_forced
+    _, net = _pair(10, bilinear=False)
+    x, y = synthetic_batch(2, 10, 96, 64)
+    worst = _teacher_forced(net.cuda(), x, y, monkeypatch)
+    print("teacher-forced UNet(bilinear=False): worst", worst)
