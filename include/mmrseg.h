@@ -517,6 +517,20 @@ int mmr_onehot_to_labels(const void* onehot, int is_float, int N, int C, int H, 
                          int64_t* labels, mmr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Per-image, per-class Hausdorff distance of the predicted vs the labelled mask.  Replaces the
+ * reference's every-25-epochs loop: one_hot -> .cpu() -> skimage.metrics.hausdorff_distance(seg_slice,
+ * label_slice) per image and class (SU/ModelTraining.py:625-649, 765-789).
+ *   hd2[n][c] = max( max_{b: label == c} min_{a: pred == c} |a - b|^2 , the same with the roles swapped )
+ * as an exact integer (separable Euclidean distance transform); 0 when both masks are empty, ~0ull (all ones)
+ * when exactly one is (skimage: inf).  The host takes sqrt in float64.  pred: [N][H][W] uint8 (pred_u8 = 1) or
+ * int64; labels int64; workspace: >= mmr_hausdorff_workspace_bytes(C, H, W) (one image; more lets several images
+ * share a launch).  classes <= 16.
+ * ------------------------------------------------------------------------------------ */
+int64_t mmr_hausdorff_workspace_bytes(int C, int H, int W);
+int mmr_hausdorff_sq(const void* pred, int pred_u8, const int64_t* labels, int N, int C, int H, int W,
+                     void* workspace, int64_t workspace_bytes, unsigned long long* hd2, mmr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Optimiser: Adam / AdamW over one flat fp32 buffer.  Replaces optim.Adam(...).step()
  * (SU/ModelTraining.py:366,617) and AdamW (ED/Main_MMR_SegModel.py:878-880).
  * mode 0: L2 (g += wd*p), mode 1: decoupled (AdamW).  bc1 = 1-b1^t, bc2 = 1-b2^t.

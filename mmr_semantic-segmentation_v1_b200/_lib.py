@@ -219,6 +219,8 @@ SIGNATURES = {
     "mmr_confusion_from_logits": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mmr_confusion_from_preds": (_i, [_vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp]),
     "mmr_onehot_to_labels": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_hausdorff_workspace_bytes": (_i64, [_i, _i, _i]),
+    "mmr_hausdorff_sq": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp, _vp]),
     "mmr_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "mmr_zero_async": (_i, [_vp, _i64, _vp]),
     "mmr_sgd_step": (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _i, _f, _vp]),

@@ -148,6 +148,44 @@ def dice_per_image(preds, labels, num_classes, empty_score=1.0):
     return torch.where(total > 0, out, torch.full_like(out, float(empty_score)))
 
 
+def hausdorff_distance(preds, labels, num_classes, workspace=None):
+    """skimage.metrics.hausdorff_distance(seg_slice, label_slice) for every image and class of a batch, on the
+    device (the reference's every-25-epochs loop, SU/ModelTraining.py:625-649, 765-789, moves every image to the
+    CPU and runs two cKDTree queries per class).  preds: uint8 or int64 [N,H,W] class indices (torch.argmax's
+    output or model.segment()'s), labels: int64 [N,H,W].  Returns float64 [N, num_classes] on the device: the
+    exact Euclidean Hausdorff distance, 0 where both masks are empty, inf where exactly one is."""
+    if not preds.is_cuda:
+        raise _lib.MmrError("metric kernels run on a B200 only (input on %s); there is no CPU fallback" % preds.device)
+    if preds.shape != labels.shape or preds.dim() != 3:
+        raise ValueError("preds and labels must both be [N, H, W], got %s and %s" % (tuple(preds.shape), tuple(labels.shape)))
+    if preds.dtype not in (torch.uint8, torch.int64):
+        preds = preds.long()
+    preds, labels = preds.contiguous(), labels.contiguous().long()
+    n, h, w = preds.shape
+    lib = _lib.lib()
+    per_image = lib.mmr_hausdorff_workspace_bytes(num_classes, h, w)
+    if workspace is None or workspace.numel() < per_image:
+        workspace = torch.empty((min(n, max(1, (256 << 20) // per_image)) * per_image,), device=preds.device,
+                                dtype=torch.uint8)
+    hd2 = torch.empty((n, num_classes), device=preds.device, dtype=torch.int64)
+    _lib.check(lib.mmr_hausdorff_sq(preds.data_ptr(), int(preds.dtype == torch.uint8), labels.data_ptr(), n,
+                                    num_classes, h, w, workspace.data_ptr(), workspace.numel(), hd2.data_ptr(),
+                                    _stream()))
+    out = hd2.double().sqrt()           # exact integers below 2^53: sqrt is the correctly rounded distance
+    return torch.where(hd2 < 0, torch.full_like(out, float("inf")), out)     # all-ones (-1 as int64) marks "one mask empty"
+
+
+def detailed_metrics(preds, labels, num_classes, inf_value=1000.0, empty_score=1.0):
+    """The reference's detailed per-image metrics block in two launches per batch instead of N * (1 + C) host round
+    trips (SU/ModelTraining.py:625-649): for each image the boolean Dice of the one-hot volumes (`utils.dice`) and,
+    per class, the Hausdorff distance with infinite distances capped at `inf_value` (the reference's 1000).
+    Returns (dice float64 [N], hausdorff float64 [N, C]) on the device; `dice.sum()` and `hausdorff.sum()` are what
+    the reference adds to total_dice_coeff / total_haus_dist."""
+    d = dice_per_image(preds.long() if preds.dtype != torch.int64 else preds, labels, num_classes, empty_score)
+    hd = hausdorff_distance(preds, labels, num_classes)
+    return d, torch.where(torch.isinf(hd), torch.full_like(hd, float(inf_value)), hd)
+
+
 def get_stats(output, target, mode="multiclass", ignore_index=None, threshold=None, num_classes=None):
     """smp.metrics.get_stats for mode='multiclass': (tp, fp, fn, tn), each int64 [N, C]."""
     if mode != "multiclass":

@@ -397,6 +397,7 @@ class UnetPlusPlus(_PlanModel):
             raise KeyError("Wrong pretrained weights `%s` for encoder `%s`. Available options are: ['imagenet']"
                            % (encoder_weights, encoder_name))
         self.encoder_name, self.classes, self.deep_supervision = encoder_name, classes, deep_supervision
+        self._init_kwargs = {"encoder_name": encoder_name, "classes": classes, "deep_supervision": bool(deep_supervision)}
         self.encoder = _ResNetEncoder(encoder_name)
         if encoder_weights == "imagenet":
             _load_pretrained_resnet(self.encoder, encoder_name, "UnetPlusPlus(encoder_weights='imagenet')")
@@ -434,6 +435,7 @@ class ResNetUNet(_PlanModel):
         super().__init__()
         import torchvision
         self.n_class, self.resnet_model = n_class, resnet_model
+        self._init_kwargs = {"n_class": n_class, "resnet_model": resnet_model, "pretrained": False}
         if resnet_model == 18:
             self.base_model = torchvision.models.resnet18(weights=None)
         elif resnet_model == 34:
@@ -515,6 +517,7 @@ class UNet(_PlanModel):
         if n_channels != 3:
             raise NotImplementedError("only n_channels=3 is built (the reference's call sites)")
         self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear
+        self._init_kwargs = {"n_channels": n_channels, "n_classes": n_classes, "bilinear": bool(bilinear)}
         self.inc = _DoubleConv(n_channels, 64)
         self.down1 = _Down(64, 128)
         self.down2 = _Down(128, 256)

@@ -108,3 +108,21 @@ def iou_score(tp, fp, fn, tn, reduction=None, zero_division=1.0):
     if reduction == "micro":
         return score(tp.sum(), fp.sum(), fn.sum())
     raise NotImplementedError(reduction)
+
+
+def hausdorff_distance(image0, image1):
+    """skimage.metrics.hausdorff_distance(image0, image1) (method='standard'), as called per class slice at
+    SU/ModelTraining.py:644, 784.  scikit-image is an un-vendored dependency that is not installed here: restated
+    from its published source (nonzero pixel coordinates of both images, two scipy.spatial.cKDTree nearest-neighbour
+    queries, max of the maxima; 0 for two empty images, inf when exactly one is empty) -- parity unpinned at that
+    boundary, although the quantity is a closed-form definition."""
+    from scipy.spatial import cKDTree
+    a = np.transpose(np.nonzero(np.asarray(image0)))
+    b = np.transpose(np.nonzero(np.asarray(image1)))
+    if len(a) == 0:
+        return 0.0 if len(b) == 0 else np.inf
+    if len(b) == 0:
+        return np.inf
+    fwd = cKDTree(a).query(b, k=1)[0]
+    bwd = cKDTree(b).query(a, k=1)[0]
+    return max(max(fwd), max(bwd))

@@ -240,3 +240,51 @@ def test_dice_per_image_matches_reference_dice_on_one_hots():
         b = torch.nn.functional.one_hot(gt[i], c).permute(2, 0, 1).numpy()
         assert abs(got[i] - OM.dice(a, b)) <= 1e-12, i
     assert got[2] == 1.0
+
+
+def _blobs(n, classes, h, w, seed):
+    """Labels with spatial structure (background + random ellipses, SURVEY 8d variant B) and a perturbed copy."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    maps = []
+    for _ in range(2):
+        m = torch.zeros((n, h, w), dtype=torch.int64)
+        for i in range(n):
+            for _ in range(6):
+                c = int(torch.randint(1, classes, (1,), generator=g))
+                cy, cx = float(torch.rand(1, generator=g)) * h, float(torch.rand(1, generator=g)) * w
+                ry, rx = 2 + float(torch.rand(1, generator=g)) * h / 5, 2 + float(torch.rand(1, generator=g)) * w / 5
+                m[i][((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1] = c
+        maps.append(m)
+    return maps
+
+
+@pytest.mark.parametrize("n,classes,h,w", [(3, 4, 40, 56), (2, 10, 96, 64), (1, 2, 33, 130)])
+def test_hausdorff_matches_skimage_restatement(n, classes, h, w):
+    """Every image and class against the restated skimage.metrics.hausdorff_distance (two cKDTree queries): the
+    device computes the exact squared distance in integers, so the float64 results are identical; covers classes
+    absent from one map (inf), from both (0) and the reference's cap of inf at 1000 (SU/ModelTraining.py:646)."""
+    from oracle import metrics as OM
+    from mmrseg_b200.metrics import detailed_metrics, hausdorff_distance
+    label, pred = _blobs(n, classes, h, w, seed=n * 100 + classes)
+    pred[0][pred[0] == 1] = 0                 # class 1 missing from the prediction of image 0 -> inf (if labelled)
+    if classes > 3:
+        label[:, :, :][label == 3] = 0        # class 3 labelled nowhere ...
+        pred[:, :, :][pred == 3] = 0          # ... and predicted nowhere -> 0
+    for p_dev in (pred.cuda(), pred.to(torch.uint8).cuda()):
+        got = hausdorff_distance(p_dev, label.cuda(), classes).cpu().numpy()
+        for i in range(n):
+            for c in range(classes):
+                want = OM.hausdorff_distance(pred[i].numpy() == c, label[i].numpy() == c)
+                assert got[i, c] == want, (i, c, got[i, c], want)
+    dice, hd = detailed_metrics(pred.cuda(), label.cuda(), classes)
+    # the reference's accumulation: dice of the C x H x W one-hot volumes, Hausdorff with inf -> 1000
+    oh = lambda m: torch.nn.functional.one_hot(m, classes).permute(2, 0, 1).numpy()
+    total_dice = sum(OM.dice(oh(pred[i]), oh(label[i])) for i in range(n))
+    total_haus = 0.0
+    for i in range(n):
+        for c in range(classes):
+            v = OM.hausdorff_distance(oh(pred[i])[c], oh(label[i])[c])
+            total_haus += 1000 if v == np.inf else v
+    assert abs(float(dice.sum()) - total_dice) <= 1e-12 * max(1.0, total_dice)
+    assert abs(float(hd.sum()) - total_haus) <= 1e-9 * max(1.0, total_haus)

@@ -180,3 +180,19 @@ def test_dice_loss_restatement_properties():
     v = losses.monai_dice_ce(z, oh).item()
     assert abs(v - (np.log(10) + 0.9)) < 0.02
     assert abs(losses.mixed_loss(z, t, -1).item() - np.log(10)) < 0.01
+
+
+def test_hausdorff_restatement_known_answers():
+    """oracle.metrics.hausdorff_distance (skimage.metrics.hausdorff_distance restated with scipy's cKDTree):
+    closed-form cases -- a 3-4-5 triangle, nested sets, and skimage's empty-set conventions (0 / inf)."""
+    from oracle.metrics import hausdorff_distance
+    a, b = np.zeros((8, 9), bool), np.zeros((8, 9), bool)
+    assert hausdorff_distance(a, b) == 0.0
+    a[1, 2] = True
+    assert hausdorff_distance(a, b) == np.inf and hausdorff_distance(b, a) == np.inf
+    b[4, 6] = True
+    assert hausdorff_distance(a, b) == 5.0
+    b[1, 2] = True                      # B now contains A: the far point of B decides
+    assert hausdorff_distance(a, b) == 5.0
+    a[4, 5] = True
+    assert hausdorff_distance(a, b) == 1.0

@@ -303,3 +303,37 @@ def test_amp_training_lines():
     loss2 = loss_fn(net2(images), masks_onehot.float())
     loss2.backward()
     assert abs(loss.item() - loss2.item()) <= 1e-6 * abs(loss2.item())
+
+
+def test_native_checkpoint_on_device(tmp_path):
+    """mmrseg_b200.checkpoint on a cuda model: the flat parameter buffer goes device -> file -> device, eval logits of
+    the reloaded model are bit-identical, training resumes (FusedAdam state included) on the same trajectory, and
+    the half-size bf16 OHWI inference checkpoint reproduces the ORIGINAL model's logits bit for bit (the kernels
+    round the fp32 masters to exactly those bf16 values anyway)."""
+    from mmrseg_b200 import checkpoint
+    from mmrseg_b200.optim import FusedAdam
+    _, net = model_pair(2)
+    x, y = synthetic_batch(2, 2, 64, 64)
+    xc, yc = x.cuda(), y.cuda()
+    opt = FusedAdam(net.parameters(), lr=1e-3, weight_decay=1e-5)
+    _train(net, opt, xc, yc, 2)
+    p32, p16 = str(tmp_path / "t.mmrseg"), str(tmp_path / "i.mmrseg")
+    checkpoint.save(p32, net, optimizer=opt, extra={"epoch": 2})
+    checkpoint.save(p16, net, weights="bf16")
+    net.eval()
+    with torch.no_grad():
+        want = net(xc)
+    for path in (p32, p16):
+        other, extra = checkpoint.load(path, device="cuda")
+        other.eval()
+        with torch.no_grad():
+            assert torch.equal(other(xc), want), path
+    # resume: two more steps from the checkpoint == two more steps of the original run
+    _train(net, opt, xc, yc, 2)
+    resumed, extra = checkpoint.load(p32, device="cuda")
+    assert extra == {"epoch": 2}
+    opt2 = FusedAdam(resumed.parameters(), lr=1.0)
+    checkpoint.load(p32, resumed, optimizer=opt2)
+    _train(resumed, opt2, xc, yc, 2)
+    for (k, a), (_, b) in zip(net.named_parameters(), resumed.named_parameters()):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), k
