@@ -5,8 +5,8 @@
     w*dice + (1-w)*CrossEntropy    SU/ModelTraining.py:342-360, 600-603 (train), 747-750 (val)
     DiceCELoss(softmax=True)       monai, ED/Main_MMR_SegModel.py:578, 709, 822
 
-All of them are one call of mmr_dice_ce_fwd (per-(image, class) sums, warp-shuffle reduction)
-and, under autograd, one call of mmr_dice_ce_bwd.  Inputs: fp32 NCHW logits (what the models
+All of them are one call of the custom op mmrseg::dice_ce_fwd (mmr_dice_ce_fwd: per-(image, class) sums,
+warp-shuffle reduction) and, under autograd, one call of mmrseg::dice_ce_bwd (mmrseg_b200/ops.py).  Inputs: fp32 NCHW logits (what the models
 return) and int64 labels; no one-hot tensor and no softmax tensor is materialised.
 """
 import ctypes as C
@@ -16,69 +16,22 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import MmrLossParams
-
-_LOSS_BLOCKS_CAP = 592
-
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _blocks(hw, n):
-    return int(max(1, min(-(-hw // 2048), -(-_LOSS_BLOCKS_CAP // n))))
-
-
-def _params(dice_eps_nr, dice_eps_dr, onehot_eps, w_dice, w_ce, dice_channels, ce_ignore_index):
-    return MmrLossParams(dice_eps_nr, dice_eps_dr, onehot_eps, w_dice, w_ce, dice_channels,
-                         ce_ignore_index)
-
-
-def dice_ce_forward(logits, labels, prm, out=None, ws=None):
-    """Raw launch: returns (out[3] = total, dice, ce), workspace."""
+def _loss(logits, labels, prm):
+    """One mmrseg::dice_ce_fwd (autograd: mmrseg::dice_ce_bwd); prm = (dice_eps_nr, dice_eps_dr, onehot_eps, w_dice,
+    w_ce, dice_channels, ce_ignore_index).  Returns (total, dice, ce) as a 3-element fp32 tensor."""
+    from . import ops
     if not logits.is_cuda:
         raise _lib.MmrError("loss kernels run on a B200 only (input on %s); there is no CPU fallback"
                             % logits.device)
-    n, c, h, w = logits.shape
-    nblk = _blocks(h * w, n)
-    need = _lib.lib().mmr_dice_ce_workspace_doubles(n, c, nblk)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty((need,), device=logits.device, dtype=torch.float64)
-    if out is None:
-        out = torch.empty((3,), device=logits.device, dtype=torch.float32)
-    _lib.check(_lib.lib().mmr_dice_ce_fwd(logits.data_ptr(), labels.data_ptr(), n, c, h, w, C.byref(prm),
-                                          ws.data_ptr(), nblk, out.data_ptr(), _stream()))
-    return out, ws
-
-
-def dice_ce_backward(logits, labels, prm, ws, dlogits, grad_scale=1.0, grad_scale_dev=None):
-    n, c, h, w = logits.shape
-    _lib.check(_lib.lib().mmr_dice_ce_bwd(
-        logits.data_ptr(), labels.data_ptr(), n, c, h, w, C.byref(prm), ws.data_ptr(),
-        C.c_float(grad_scale), grad_scale_dev.data_ptr() if grad_scale_dev is not None else None,
-        dlogits.data_ptr(), _stream()))
-    return dlogits
-
-
-class _DiceCE(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, logits, labels, prm, which):
-        logits = logits.contiguous()
-        if logits.dtype != torch.float32:
-            logits = logits.float()
-        labels = labels.contiguous()
-        out, ws = dice_ce_forward(logits, labels, prm)
-        ctx.prm, ctx.ws = prm, ws
-        ctx.save_for_backward(logits, labels)
-        return out[which]
-
-    @staticmethod
-    def backward(ctx, grad_out):
-        logits, labels = ctx.saved_tensors
-        dlogits = torch.empty_like(logits)
-        g = grad_out.to(torch.float32).contiguous()
-        dice_ce_backward(logits, labels, ctx.prm, ctx.ws, dlogits, 1.0, g)
-        return dlogits, None, None, None
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    out, _ = torch.ops.mmrseg.dice_ce_fwd(logits, labels, *prm)
+    return out
 
 
 def _validate(input, target):
@@ -103,8 +56,7 @@ def dice_loss(input: torch.Tensor, target: torch.Tensor, eps: float = 1.0,
         dc += c
     if not 1 <= dc <= c:
         raise ValueError("ignore_index=%r leaves no channel in the Dice term" % (ignore_index,))
-    prm = _params(eps, eps, 1e-6, 1.0, 0.0, dc, -100)
-    return _DiceCE.apply(input, target, prm, 1)
+    return _loss(input, target, (float(eps), float(eps), 1e-6, 1.0, 0.0, dc, -100))[0]
 
 
 class DiceLoss(nn.Module):
@@ -133,11 +85,11 @@ class DiceCrossEntropyLoss(nn.Module):
         w = self.dice_weight
         wd, wc = (0.0, 1.0) if w == -1 else (float(w), 1.0 - float(w))
         dc = c if self.dice_ignore_index is None else int(self.dice_ignore_index)
-        return _params(self.eps, self.eps, 1e-6, wd, wc, dc, self.ce_ignore_index)
+        return (float(self.eps), float(self.eps), 1e-6, wd, wc, dc, int(self.ce_ignore_index))
 
     def forward(self, input, target):
         _validate(input, target)
-        return _DiceCE.apply(input, target, self.params(input.shape[1]), 0)
+        return _loss(input, target, self.params(input.shape[1]))[0]
 
 
 def onehot_to_labels(onehot):
@@ -172,6 +124,6 @@ class DiceCELoss(nn.Module):
             labels = target
         else:
             raise ValueError("target must be one-hot [N,C,H,W] or labels [N,H,W], got %s" % (tuple(target.shape),))
-        prm = _params(self.smooth_nr, self.smooth_dr, 0.0, self.lambda_dice, self.lambda_ce,
-                      input.shape[1], -100)
-        return _DiceCE.apply(input, labels, prm, 0)
+        prm = (float(self.smooth_nr), float(self.smooth_dr), 0.0, float(self.lambda_dice), float(self.lambda_ce),
+               input.shape[1], -100)
+        return _loss(input, labels, prm)[0]

@@ -13,7 +13,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, ops  # noqa: F401  (ops registers the mmrseg:: custom ops)
 from .losses import onehot_to_labels, _stream
 
 
@@ -28,10 +28,7 @@ def confusion_matrix(logits, labels, cm=None, return_pred=False):
     n, c, h, w = logits.shape
     if cm is None:
         cm = torch.zeros((n, c, c), device=logits.device, dtype=torch.int64)
-    pred = torch.empty((n, h, w), device=logits.device, dtype=torch.int64) if return_pred else None
-    _lib.check(_lib.lib().mmr_confusion_from_logits(
-        logits.data_ptr(), labels.contiguous().data_ptr(), n, c, h, w, cm.data_ptr(),
-        pred.data_ptr() if pred is not None else None, _stream()))
+    pred = torch.ops.mmrseg.confusion_from_logits(logits, labels.contiguous(), cm, bool(return_pred))
     return (cm, pred) if return_pred else cm
 
 
@@ -47,8 +44,7 @@ def confusion_matrix_from_preds(preds, labels, num_classes, ignore_index=None, c
     if cm is None:
         cm = torch.zeros((n, cb, cb), device=preds.device, dtype=torch.int64)
     ign = -(2 ** 62) if ignore_index is None else int(ignore_index)
-    _lib.check(_lib.lib().mmr_confusion_from_preds(preds.data_ptr(), labels.data_ptr(), n, num_classes,
-                                                   npix, ign, int(overflow_bin), cm.data_ptr(), _stream()))
+    torch.ops.mmrseg.confusion_from_preds(preds, labels, cm, num_classes, ign, bool(overflow_bin))
     return cm
 
 

@@ -19,7 +19,7 @@ import warnings
 import torch
 import torch.nn as nn
 
-from . import _lib, graph
+from . import _lib, graph, ops
 from .engine import Engine
 
 
@@ -116,43 +116,10 @@ def _load_pretrained_resnet(module, name, source):
 
 
 # ------------------------------------------------------------------ autograd bridge
-class _PlanFunction(torch.autograd.Function):
-    """logits = plan(x); backward replays the plan's backward and leaves parameter gradients in
-    the model's flat gradient buffer (exposed as each parameter's .grad)."""
-
-    @staticmethod
-    def forward(ctx, model, x, *params):
-        eng = model._engine_for(x, training=True)
-        ctx.model, ctx.eng = model, eng
-        out = eng.forward(x)
-        ctx.generation = eng.generation
-        # fresh tensors (SURVEY 8b: "outputs are fresh tensors"): the plan's logits buffers are rewritten by
-        # the next forward, so `outs = [model(b) for b in batches]` must not alias them
-        if isinstance(out, list):    # deep supervision: [main, aux...] at full resolution
-            ctx.n_out = len(out)
-            return tuple(t.clone() for t in out)
-        ctx.n_out = 1
-        return out.clone()
-
-    @staticmethod
-    def backward(ctx, *dlogits):
-        model, eng = ctx.model, ctx.eng
-        if eng.generation != ctx.generation:
-            raise _lib.MmrError(
-                "backward() of a forward pass that is no longer the latest one at this input shape: the plan "
-                "keeps ONE set of saved activations per (batch, H, W), and another model(x) call in training "
-                "mode has overwritten them.  Call backward() before the next training-mode forward (gradient "
-                "accumulation: forward, backward, forward, backward), or run the extra forward under "
-                "model.eval()")
-        accumulate = model._grads_live()
-        grads = [g.contiguous() if g is not None else None for g in dlogits]
-        cuts = model._grad_cuts(eng.param_ready_hooks) if model._grad_cuts is not None else None
-        eng.backward(grads if ctx.n_out > 1 else grads[0], accumulate=accumulate,
-                     on_ready=model._on_grads_ready, cuts=cuts)
-        model._publish_grads()
-        if model._after_backward is not None:
-            model._after_backward()
-        return (None, None) + (None,) * len(model._flat_names)
+# `seg = model(img)` / `loss.backward()` go through the custom ops mmrseg::plan_forward / mmrseg::plan_backward
+# (mmrseg_b200/ops.py): plan_forward replays the static plan and returns the stacked logits in fresh memory, its
+# registered autograd formula replays the backward plan, which leaves the parameter gradients in the model's flat
+# gradient buffer (exposed as each parameter's .grad).
 
 
 class _PlanModel(nn.Module):
@@ -173,6 +140,13 @@ class _PlanModel(nn.Module):
         self._input_norm = None      # (mean, std) applied on the device to uint8 frames
         self._io_dtype = None        # .half() / .bfloat16(): dtype of the returned logits (masters stay fp32)
         self._io_channels_last = False
+        self._handle = ops.register_model(self)     # what the custom ops know this model by
+
+    def _n_classes(self):
+        return getattr(self, "classes", None) or getattr(self, "n_class", None) or getattr(self, "n_classes")
+
+    def _n_heads(self, training):
+        return 4 if (training and getattr(self, "deep_supervision", False)) else 1
 
     # ---- dtype / memory-format requests of the reference's inference path -------------------
     # `self.model.to(memory_format=torch.channels_last); self.model.half()` (ED/Main_MMR_SegModel.py:1243-1244)
@@ -332,13 +306,15 @@ class _PlanModel(nn.Module):
     def forward(self, x):
         if x.dtype != torch.uint8 and x.dtype != torch.float32:
             x = x.float()
-        if self.training and torch.is_grad_enabled():
-            self._ensure_flat(x.device)
-            out = _PlanFunction.apply(self, x.contiguous(), *[p for _, p in self._named_params()])
-            return [self._finish(t) for t in out] if isinstance(out, tuple) else self._finish(out)
-        eng = self._engine_for(x, training=self.training)
-        out = eng.forward(x.contiguous())
-        return [self._finish(t.clone()) for t in out] if isinstance(out, list) else self._finish(out.clone())
+        if not x.is_cuda:
+            raise _lib.MmrError("mmrseg_b200 models run on a B200 only: input is on %s and there is "
+                                "no CPU fallback" % x.device)
+        self._ensure_flat(x.device)
+        params = [p for _, p in self._named_params()] if (self.training and torch.is_grad_enabled()) else []
+        out = torch.ops.mmrseg.plan_forward(x.contiguous(), self._handle, self.training, params)
+        if out.shape[0] > 1:        # deep supervision (training): [main, aux...] at full resolution
+            return [self._finish(t) for t in out.unbind(0)]
+        return self._finish(out[0])
 
 
     @torch.no_grad()

@@ -11,7 +11,7 @@ stepped with ONE launch per contiguous run of its parameters (the whole model: o
 """
 import torch
 
-from . import _lib
+from . import _lib, ops  # noqa: F401  (ops registers the mmrseg:: custom ops)
 from .losses import _stream
 
 
@@ -39,6 +39,12 @@ def _runs(params, slots):
         cur = {"idx": [i], "start": ptrs, "end": [q + p.numel() * 4 for q in ptrs], "ok": ok}
         runs.append(cur)
     return [(r["idx"], r["start"], (r["end"][0] - r["start"][0]) // 4, r["ok"]) for r in runs]
+
+
+def _span(t, numel):
+    """fp32 tensor over `numel` consecutive elements of t's storage starting at t's first element (a run of
+    parameters that are views of one flat buffer, including the alignment padding between them)."""
+    return torch.empty(0, dtype=t.dtype, device=t.device).set_(t.untyped_storage(), t.storage_offset(), (numel,))
 
 
 class _FlatStateOptimizer(torch.optim.Optimizer):
@@ -99,7 +105,13 @@ class _FlatStateOptimizer(torch.optim.Optimizer):
         if plan is not None and plan[0] == sig:
             return plan[1]
         slots = {s: {p: self._home(p, s) for p in params} for s in self._slots}
-        runs = _runs(params, slots)
+        runs = []
+        for idx, ptrs, numel, ok in _runs(params, slots):
+            first = min((params[i] for i in idx), key=lambda p: p.data_ptr())
+            # the tensors the custom op is launched on: one span per run for (p, g, state slots...)
+            spans = [_span(first.data, numel), _span(first.grad, numel)] + \
+                    [_span(slots[s][first], numel) for s in sorted(slots)] if ok else None
+            runs.append((idx, ptrs, numel, ok, spans))
         self._plans[gi] = (sig, runs)
         return runs
 
@@ -124,7 +136,7 @@ class FusedAdam(_FlatStateOptimizer):
             b1, b2 = group["betas"]
             runs = self._plan(gi, params)
             mode = 1 if group.get("decoupled", self.defaults["decoupled"]) else 0
-            for idx, ptrs, numel, ok in runs:
+            for idx, ptrs, numel, ok, spans in runs:
                 # torch keeps one step counter per parameter; the parameters of a run advance together
                 steps = set()
                 for i in idx:
@@ -135,24 +147,22 @@ class FusedAdam(_FlatStateOptimizer):
                         st["step"] = torch.tensor(1.0, dtype=torch.float32)
                     steps.add(float(st["step"]))
                 if len(steps) == 1 and ok:
-                    jobs = [(ptrs, numel, steps.pop())]
+                    jobs = [(spans, steps.pop())]
                 else:
                     jobs = []
                     for i in idx:
                         p = params[i]
                         st = self.state[p]
-                        g = p.grad if p.grad.is_contiguous() and p.grad.dtype == torch.float32 else None
-                        if g is None or not p.is_contiguous() or p.dtype != torch.float32:
+                        if not (p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.is_contiguous()
+                                and p.dtype == torch.float32):
                             raise _lib.MmrError("FusedAdam needs contiguous fp32 parameters and gradients")
-                        jobs.append(([p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
-                                      st["exp_avg_sq"].data_ptr()], p.numel(), float(st["step"])))
-                for (pp, gp, mp, vp), n, t in jobs:
-                    if any(q % 16 for q in (pp, gp, mp, vp)):
+                        jobs.append(([p.data, p.grad, st["exp_avg"], st["exp_avg_sq"]], float(st["step"])))
+                for (pt, gt, mt, vt), t in jobs:
+                    if any(q.data_ptr() % 16 for q in (pt, gt, mt, vt)):
                         raise _lib.MmrError("FusedAdam: a parameter, gradient or moment buffer is not 16-byte "
                                             "aligned (parameters of mmrseg_b200 models always are)")
-                    _lib.check(lib.mmr_adam_step(pp, gp, mp, vp, n, group["lr"], b1, b2, group["eps"],
-                                                 group["weight_decay"], 1.0 - b1 ** t, 1.0 - b2 ** t, mode,
-                                                 self.grad_scale, _stream()))
+                    torch.ops.mmrseg.adam_step(pt, gt, mt, vt, group["lr"], b1, b2, group["eps"],
+                                               group["weight_decay"], t, bool(mode), self.grad_scale)
         return loss
 
 
@@ -176,16 +186,14 @@ class FusedSGD(_FlatStateOptimizer):
                 continue
             # torch initialises the momentum buffer with the first gradient; a zero-initialised buffer gives
             # the same first step (momentum * 0 + g), so the kernel's first_step flag stays 0
-            for idx, ptrs, numel, ok in self._plan(gi, params):
+            for idx, ptrs, numel, ok, spans in self._plan(gi, params):
                 if ok:
-                    jobs = [(ptrs, numel)]
+                    jobs = [spans]
                 else:
-                    jobs = [([params[i].data_ptr(), params[i].grad.data_ptr(),
-                              self.state[params[i]]["momentum_buffer"].data_ptr()], params[i].numel()) for i in idx]
-                for (pp, gp, bp), n in jobs:
-                    _lib.check(lib.mmr_sgd_step(pp, gp, bp if group["momentum"] != 0 else None, n, group["lr"],
-                                                group["momentum"], group["weight_decay"], 0, self.grad_scale,
-                                                _stream()))
+                    jobs = [[params[i].data, params[i].grad, self.state[params[i]]["momentum_buffer"]] for i in idx]
+                for pt, gt, bt in jobs:
+                    torch.ops.mmrseg.sgd_step(pt, gt, bt, group["lr"], group["momentum"], group["weight_decay"],
+                                              self.grad_scale)
         return loss
 
 

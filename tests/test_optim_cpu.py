@@ -27,7 +27,8 @@ def test_runs_cover_exactly_the_group():
     opt = FusedAdam(params)
     runs = opt._plan(0, params)
     assert len(runs) == 1                                   # the whole model: one launch
-    idx, ptrs, numel, ok = runs[0]
+    idx, ptrs, numel, ok, spans = runs[0]
+    assert spans[0].data_ptr() == flat.data_ptr() and spans[0].numel() == numel and len(spans) == 4
     assert sorted(idx) == [0, 1, 2, 3] and ok
     assert ptrs[0] == flat.data_ptr() and ptrs[1] == gflat.data_ptr()
     assert numel == offs[-1] + params[-1].numel()           # padding between members, none after the last
@@ -42,7 +43,7 @@ def test_subset_group_does_not_touch_other_parameters():
     opt = FusedAdam([params[1], params[2]])                 # e.g. FusedAdam(model.encoder.parameters())
     runs = opt._plan(0, [params[1], params[2]])
     assert len(runs) == 1
-    _, ptrs, numel, _ = runs[0]
+    _, ptrs, numel, _, _ = runs[0]
     lo = (ptrs[0] - flat.data_ptr()) // 4
     assert lo == offs[1] and lo + numel == offs[2] + params[2].numel()      # nothing of params[0] / params[3]
     # non-adjacent members: separate launches
@@ -52,7 +53,7 @@ def test_subset_group_does_not_touch_other_parameters():
     opt3 = FusedSGD([{"params": params[:2], "lr": 0.1}, {"params": params[2:], "lr": 0.01}], momentum=0.9)
     covered = []
     for gi, g in enumerate(opt3.param_groups):
-        for idx, ptrs, numel, ok in opt3._plan(gi, g["params"]):
+        for idx, ptrs, numel, ok, spans in opt3._plan(gi, g["params"]):
             lo = (ptrs[0] - flat.data_ptr()) // 4
             covered.append((lo, lo + numel))
     assert sorted(covered) == [(0, offs[1] + 7), (offs[2], offs[3] + 5)]

@@ -337,3 +337,21 @@ def test_native_checkpoint_on_device(tmp_path):
     _train(resumed, opt2, xc, yc, 2)
     for (k, a), (_, b) in zip(net.named_parameters(), resumed.named_parameters()):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), k
+
+
+def test_custom_ops_pass_opcheck():
+    """torch.library.opcheck on the differentiable and the mutating ops: schema vs actual aliasing / mutation, fake
+    implementation vs real outputs, autograd registration."""
+    from torch.library import opcheck
+    g = torch.Generator(device="cuda").manual_seed(0)
+    logits = torch.randn((2, 3, 32, 40), device="cuda", generator=g, requires_grad=True)
+    labels = torch.randint(0, 3, (2, 32, 40), device="cuda", generator=g)
+    prm = (1.0, 1.0, 1e-6, 0.5, 0.5, 3, -100)
+    opcheck(torch.ops.mmrseg.dice_ce_fwd, (logits, labels) + prm,
+            test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    cm = torch.zeros((2, 3, 3), device="cuda", dtype=torch.int64)
+    opcheck(torch.ops.mmrseg.confusion_from_logits, (logits.detach(), labels, cm, True),
+            test_utils=("test_schema", "test_faketensor"))
+    p, gr, m, v = (torch.randn(1024, device="cuda", generator=g) for _ in range(4))
+    opcheck(torch.ops.mmrseg.adam_step, (p, gr, m, v.abs(), 1e-3, 0.9, 0.999, 1e-8, 1e-5, 3.0, False, 1.0),
+            test_utils=("test_schema", "test_faketensor"))
