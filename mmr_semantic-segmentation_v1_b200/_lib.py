@@ -116,7 +116,7 @@ class MmrWgradHaloDesc(C.Structure):
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("cb", C.c_int32), ("bn", C.c_int32), ("cout_gemm", C.c_int32), ("tx", C.c_int32),
         ("n_split", C.c_int32), ("partial", C.c_void_p), ("dst", C.c_void_p),
-        ("dst_cout", C.c_int32), ("dst_cin", C.c_int32),
+        ("dst_cout", C.c_int32), ("dst_cin", C.c_int32), ("mode", C.c_int32),
     ]
 
 
@@ -170,6 +170,7 @@ SIGNATURES = {
     "mmr_pack_weights_halo": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "mmr_pack_weights_halo_batch": (_i, [_vp, _i, _i64, _vp]),
     "mmr_wgrad_halo_partial_floats": (_i64, [_i, _i, _i, _i, _i]),
+    "mmr_wgrad_kx_partial_floats": (_i64, [_i, _i, _i, _i]),
     "mmr_wgrad_halo_plan_create": (_i, [C.POINTER(MmrWgradHaloDesc), C.POINTER(_vp)]),
     "mmr_wgrad_halo_plan_run": (_i, [_vp, _i, _vp]),
     "mmr_wgrad_halo_plan_destroy": (_i, [_vp]),

@@ -8,6 +8,7 @@ upsampled source is read at (y>>1, x>>1) by splitting the output pixels into the
 parities, for which the gather is a plain shifted box.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -722,45 +723,59 @@ class WgradHaloPlan:
             pass
 
 
-def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=None, max_partial=None):
-    """(bn, tx, n_split) of a halo weight-gradient plan: slices = nchunks * cout_gemm/bn CTAs wide,
-    split-K so that about two waves of CTAs cover the SMs, tx as large as shared memory allows while
-    keeping at least 3 pipeline stages."""
+def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=None, max_partial=None,
+                      dz_phased=False):
+    """(mode, bn, tx, n_split) of a halo weight-gradient plan: slices = nchunks * cout_gemm/bn CTAs wide,
+    split-K so that one wave of CTAs covers the SMs, tx as large as shared memory allows while
+    keeping at least 3 pipeline stages.  mode 1 (64-channel chunks, bn 64 / 32): the filter column is a
+    one-pixel shift of the dz tile, 2 MMAs of N = 3 bn per 16 pixels instead of 5 of N = bn."""
     bn = 64 if cout_gemm % 64 == 0 else (32 if cout_gemm % 32 == 0 else 16)
     n_nt = cout_gemm // bn
     A = 5 if cb == 64 else 3
+    modes = (1, 0) if (cb == 64 and bn in (64, 32) and not dz_phased) else (0,)
+    if os.environ.get("MMR_WGRAD_MODE", "") != "":   # A/B switch for measurements
+        modes = tuple(m for m in modes if m == int(os.environ["MMR_WGRAD_MODE"])) or (0,)
+    if force and "mode" in force:
+        modes = tuple(m for m in modes if m == force["mode"])
     best = None
-    for tx in (4, 2, 1):
-        if tx > 1 and 8 * tx > -(-W // 8) * 8:
-            continue
-        pitch = 8 * tx + (4 if any_up else 2)
-        stage = -(-(18 * pitch * cb * 2 + 1024) // 1024) * 1024 + -(-(16 * 8 * tx * bn * 2) // 1024) * 1024
-        stages = min(6, (224 * 1024) // stage)
-        if stages < 2:
-            continue
-        tiles = N * (-(-H // 16)) * (-(-W // (8 * tx)))
-        slices = nchunks * n_nt
-        n_split = max(1, min(tiles, n_sms // slices)) if slices < n_sms else 1
-        cfg = dict(bn=bn, tx=tx, n_split=n_split, stages=stages)
-        if force and any(cfg.get(k, v) != v for k, v in force.items() if k != "n_split"):
-            continue
-        if force and "n_split" in force:
-            cfg["n_split"] = n_split = max(1, min(tiles, force["n_split"]))
-        # per-stage issue time vs. the ~2-4 TMA operations one lane issues per stage
-        mma = tx * 8 * A * _mma_clk(bn)
-        prod = (4 if any_up else 2) * 380
-        per_tile = max(mma, prod) / tx
-        waves = -(-(slices * n_split) // n_sms)
-        total = waves * (-(-tiles // n_split)) * tx * per_tile * (1.0 if stages >= 3 else 1.1)
-        key = (total, -tx)
-        if best is None or key < best[0]:
-            best = (key, cfg)
+    for mode in modes:
+        for tx in (4, 2, 1):
+            if tx > 1 and 8 * tx > -(-W // 8) * 8:
+                continue
+            if mode == 1:
+                if tx > 2:
+                    continue
+                stage = -(-(19 * 8 * tx * 128) // 1024) * 1024 + -(-(16 * (8 * tx + 2) * bn * 2) // 1024) * 1024
+            else:
+                pitch = 8 * tx + (4 if any_up else 2)
+                stage = -(-(18 * pitch * cb * 2 + 1024) // 1024) * 1024 + -(-(16 * 8 * tx * bn * 2) // 1024) * 1024
+            stages = min(6, (224 * 1024) // stage)
+            if stages < 2:
+                continue
+            tiles = N * (-(-H // 16)) * (-(-W // (8 * tx)))
+            slices = nchunks * n_nt
+            n_split = max(1, min(tiles, n_sms // slices)) if slices < n_sms else 1
+            cfg = dict(mode=mode, bn=bn, tx=tx, n_split=n_split, stages=stages)
+            if force and any(cfg.get(k, v) != v for k, v in force.items() if k != "n_split"):
+                continue
+            if force and "n_split" in force:
+                cfg["n_split"] = n_split = max(1, min(tiles, force["n_split"]))
+            # per-stage issue time vs. the ~2-4 TMA operations one lane issues per stage
+            mma = tx * 8 * (2 * _mma_clk(3 * bn) if mode == 1 else A * _mma_clk(bn))
+            prod = (4 if any_up else 2) * 380
+            per_tile = max(mma, prod) / tx
+            waves = -(-(slices * n_split) // n_sms)
+            total = waves * (-(-tiles // n_split)) * tx * per_tile * (1.0 if stages >= 3 else 1.1)
+            key = (total, -tx)
+            if best is None or key < best[0]:
+                best = (key, cfg)
     if best is None:
         raise ValueError("no halo wgrad configuration")
     cfg = best[1]
     cfg.update(cb=cb, nchunks=nchunks, n_ntiles=n_nt, A=A)
+    cfg["per_cta"] = 192 * 3 * bn if cfg["mode"] == 1 else A * 128 * bn   # fp32 partials of one CTA
     if max_partial is not None:
-        per_split = nchunks * n_nt * A * 128 * bn
+        per_split = nchunks * n_nt * cfg["per_cta"]
         cfg["n_split"] = max(1, min(cfg["n_split"], max_partial // per_split))
     return cfg
 
@@ -784,8 +799,8 @@ def build_wgrad_halo(dz, sources, dst, *, cout_gemm=None, force=None, partial=No
     cb = pick_bk([t.shape[3] for t, _ in sources])
     any_up = any(up == 2 for _, up in sources)
     cfg = wgrad_halo_config(H, W, N, cb, cin_stored // cb, cout_gemm, any_up, n_sms=n_sms, force=force,
-                            max_partial=partial.numel() if partial is not None else None)
-    need = cfg["nchunks"] * cfg["n_ntiles"] * cfg["n_split"] * cfg["A"] * 128 * cfg["bn"]
+                            max_partial=partial.numel() if partial is not None else None, dz_phased=dz_phased)
+    need = cfg["nchunks"] * cfg["n_ntiles"] * cfg["n_split"] * cfg["per_cta"]
     if partial is None:
         partial = torch.empty((need,), device=dz.device, dtype=torch.float32)
     assert partial.dtype == torch.float32 and partial.numel() >= need
@@ -802,6 +817,7 @@ def build_wgrad_halo(dz, sources, dst, *, cout_gemm=None, force=None, partial=No
     d.partial = partial.data_ptr()
     d.dst = dst.data_ptr()
     d.dst_cout, d.dst_cin = cout, cin
+    d.mode = cfg["mode"]
     plan = WgradHaloPlan(d, [dz, sources, dst, partial])
     plan.cfg = cfg
     plan.flops = 2 * N * H * W * cout * 9 * cin

@@ -37,9 +37,10 @@ struct WhParams {
   int n_split, stages;
   int pitch[2];
   uint32_t x_tx_bytes[2], x_stage_bytes, z_tx_bytes, stage_bytes, tmem_cols;
-  float* partial;  // [slice][split][A*128][bn]
+  float* partial;  // [slice][split][prow][pcol]: mode 0 [A*128][bn], mode 1 [192][3*bn]
   float* dst;
   int dst_cout, dst_cin;
+  int mode, prow, pcol;
 };
 
 __device__ __forceinline__ bool wh_elect() {
@@ -236,6 +237,179 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Third generation (mode 1, cb = 64): the filter COLUMN moves to the dz side.
+//
+//   dW[co][ci][ky][kx] = sum_q  x[q + (ky-1) rows][ci] * dz[q - (kx-1) pixels][co]
+//
+// so the B operand of one tcgen05.mma is three views of the dz tile one pixel apart (an MN-major operand
+// with three atoms, LBO = one pixel: N = 3 * bn = 192) and the A operand stacks two filter ROWS of the
+// 64-channel chunk (two atoms one tile row apart).  A K step of 16 pixels is 2 MMAs of N = 192 (tile 0 =
+// rows ky 0 / 1, tile 1 = row ky 2 + 64 discarded lanes) instead of 5 MMAs of N = 64.  Why: an N = 64 MMA
+// reads 4 KB of A + 2 KB of B from shared memory for 32 clk of tensor work and is bound by the 128 B / clk
+// shared-memory port at 48 clk (scripts/probe/umma_rate_probe.cu: 48.0 clk at N = 64, 96.0 = the tensor
+// floor at N = 192); per K step that is 30 KB / 240 clk before, 20 KB / 192 clk (tensor-bound) now.
+// The activation tile needs no halo in x any more (18 rows x 8 TX pixels), the dz tile gets one
+// (16 rows x (8 TX + 2) pixels); out-of-image pixels of either are zero-filled by TMA, which is exactly the
+// convolution's zero padding.
+template <int TX, int BN>
+__global__ void __launch_bounds__(kWhThreads, 1)
+conv_wgrad_kx_kernel(const __grid_constant__ WhParams p) {
+  constexpr uint32_t PX = 8 * TX, PZ = 8 * TX + 2, XRB = 128, ZRB = BN * 2, NN = 3 * BN;
+  pdl_prologue();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWhMaxStages;
+  uint64_t* tmem_full = bars + 2 * kWhMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kWhMaxStages + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int slice = blockIdx.x;
+  const int c = slice / p.n_ntiles, nt = slice % p.n_ntiles;
+  const int split = blockIdx.y;
+  const int k_begin = (int)(((long long)p.total_tiles * split) / p.n_split);
+  const int k_end = (int)(((long long)p.total_tiles * (split + 1)) / p.n_split);
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  const WhChunk ch = p.chunk[c];
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    int tx = k_begin % p.tiles_x, t = k_begin / p.tiles_x;
+    int ty = t % p.tiles_y, n = t / p.tiles_y;
+    for (int it = k_begin; it < k_end; ++it) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (wh_elect()) {
+        uint8_t* sx = smem + (size_t)stage * p.stage_bytes;
+        uint8_t* sz = sx + p.x_stage_bytes;
+        const int x0 = tx * (int)PX, y0 = ty * 16;
+        mbar_arrive_expect_tx(&full[stage], p.x_tx_bytes[0] + p.z_tx_bytes);
+        tma_load_4d(sz, &p.maps[p.dzmap], &full[stage], nt * BN, x0 - 1, y0, n);
+        if (!ch.up) {
+          tma_load_4d(sx, &p.maps[ch.map], &full[stage], ch.c0, x0, y0 - 1, n);
+        } else {
+          const int xl = x0 >> 1, yl = y0 >> 1;
+          constexpr uint32_t rowb = PX * XRB;
+          wh_tma_load_5d(sx, &p.maps[ch.map_edge], &full[stage], ch.c0, 0, xl, yl - 1, n);
+          wh_tma_load_5d(sx + rowb, &p.maps[ch.map], &full[stage], ch.c0, 0, xl, 0, n * (p.H >> 1) + yl);
+          wh_tma_load_5d(sx + 17 * rowb, &p.maps[ch.map_edge], &full[stage], ch.c0, 0, xl, yl + 8, n);
+        }
+      }
+      __syncwarp();
+      if (++tx == p.tiles_x) {
+        tx = 0;
+        if (++ty == p.tiles_y) {
+          ty = 0;
+          ++n;
+        }
+      }
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, NN, 1, 1);  // both operands MN-major
+    const uint32_t hiA = wh_desc_hi(PX * XRB, 2u);
+    const uint32_t hiB = wh_desc_hi(PZ * ZRB, ZRB == 128 ? 2u : 4u);
+    constexpr uint32_t a_lbo = (PX * XRB) >> 4;  // next atom along M: the same pixels one tile row down (ky + 1)
+    constexpr uint32_t b_lbo = ZRB >> 4;         // next atom along N: one pixel to the right (kx - 1)
+    const uint32_t smem0 = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = k_begin; it < k_end; ++it) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t x_lo = ((smem0 + (uint32_t)stage * p.stage_bytes) >> 4) | (a_lbo << 16);
+      const uint32_t z_lo = ((smem0 + (uint32_t)stage * p.stage_bytes + p.x_stage_bytes) >> 4) | (b_lbo << 16);
+      if (wh_elect()) {
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t a_k = x_lo + (((uint32_t)(2 * kk) * PX + 8u * i) * XRB >> 4);
+            const uint32_t b_k = z_lo + (((uint32_t)(2 * kk) * PZ + 8u * i) * ZRB >> 4);
+            if (i == 0 && kk == 0) {
+              const uint32_t acc = (uint32_t)(it != k_begin);
+              wh_umma(tmem_base, a_k, hiA, b_k, hiB, idesc, acc);
+              wh_umma(tmem_base + NN, a_k + (2u * PX * XRB >> 4), hiA, b_k, hiB, idesc, acc);
+            } else {
+              wh_umma(tmem_base, a_k, hiA, b_k, hiB, idesc, 1u);
+              wh_umma(tmem_base + NN, a_k + (2u * PX * XRB >> 4), hiA, b_k, hiB, idesc, 1u);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (wh_elect()) umma_commit(&empty[stage]);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (wh_elect()) {
+      if (k_end > k_begin)
+        umma_commit(tmem_full);
+      else
+        mbar_arrive(tmem_full);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: fp32 partials [192][NN]
+    const int q = warp - 4;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float* base = p.partial + ((size_t)slice * p.n_split + split) * (size_t)(192 * NN);
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      if (t == 1 && q >= 2) break;  // tile 1: lanes 64..127 belong to no filter row
+      float* dst = base + ((size_t)t * 128 + q * 32 + lane) * NN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * NN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < (int)NN; c0 += 16) {
+        uint32_t r[16];
+        if (k_end > k_begin) {
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 // Sum the split-K partials in split order and scatter into OIHW fp32 (dst[co][ci][tap]).  One
 // thread owns four consecutive output channels of one accumulator row (float4 loads, four splits in
 // flight); rows that belong to no filter tap are skipped before any load.
@@ -246,34 +420,41 @@ wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
   // k = lane, lane + 8, ... with four loads in flight, the eight lane sums are added in lane order
   // through shared memory (deterministic), so the serial chain per thread is n_split / 8 long.
   __shared__ float4 part[8][32];
-  const int bn4 = p.bn >> 2;
-  const size_t per_slice = (size_t)p.A * 128 * p.bn;
-  const size_t total4 = (size_t)p.A * 128 * bn4 * p.nchunks * p.n_ntiles;  // a multiple of 32
+  const int pc4 = p.pcol >> 2;
+  const size_t per_slice = (size_t)p.prow * p.pcol;
+  const size_t total4 = (size_t)p.prow * pc4 * p.nchunks * p.n_ntiles;  // a multiple of 32
   const int sl = threadIdx.x >> 5, o = threadIdx.x & 31;
   for (size_t base = (size_t)blockIdx.x * 32; base < total4; base += (size_t)gridDim.x * 32) {
     const size_t idx = base + o;
-    const int n4 = (int)(idx % bn4);
-    size_t t = idx / bn4;
-    const int r = (int)(t % 128);
-    t /= 128;
-    const int a = (int)(t % p.A);
-    const int slice = (int)(t / p.A);
+    const int n4 = (int)(idx % pc4);
+    size_t t = idx / pc4;
+    const int row = (int)(t % p.prow);
+    const int slice = (int)(t / p.prow);
     const int c = slice / p.n_ntiles, nt = slice % p.n_ntiles;
-    int tap, chn;
-    if (p.cb == 64) {
-      tap = 2 * a + (r >> 6);
-      chn = r & 63;
+    int tap, chn, co;
+    if (p.mode == 1) {  // rows (ky, ci), columns (2 - kx, co)
+      const int col = n4 * 4;
+      tap = (row >> 6) * 3 + 2 - col / p.bn;
+      chn = row & 63;
+      co = nt * p.bn + col % p.bn;
     } else {
-      const int kx = r / p.cb;
-      tap = kx < 3 ? 3 * a + kx : 9;
-      chn = r % p.cb;
+      const int a = row >> 7, r = row & 127;
+      if (p.cb == 64) {
+        tap = 2 * a + (r >> 6);
+        chn = r & 63;
+      } else {
+        const int kx = r / p.cb;
+        tap = kx < 3 ? 3 * a + kx : 9;
+        chn = r % p.cb;
+      }
+      co = nt * p.bn + n4 * 4;
     }
-    const int co = nt * p.bn + n4 * 4, ci = p.chunk[c].ci0 + chn;
+    const int ci = p.chunk[c].ci0 + chn;
     const bool live = tap < 9 && co < p.dst_cout && ci < p.dst_cin;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
       const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)slice * p.n_split * per_slice +
-                                                          ((size_t)a * 128 + r) * p.bn) + n4;
+                                                          (size_t)row * p.pcol) + n4;
       const size_t step = per_slice >> 2;
       int k = sl;
       for (; k + 24 < p.n_split; k += 32) {
@@ -346,6 +527,15 @@ extern "C" int64_t mmr_wgrad_halo_partial_floats(int nchunks, int cb, int bn, in
   return (int64_t)nchunks * n_ntiles * n_split * A * 128 * bn;
 }
 
+extern "C" int64_t mmr_wgrad_kx_partial_floats(int nchunks, int bn, int n_ntiles, int n_split) {
+  return (int64_t)nchunks * n_ntiles * n_split * 192 * 3 * bn;
+}
+
+template <int TX, int BN>
+static cudaError_t wh_kx_attr() {
+  return cudaFuncSetAttribute(conv_wgrad_kx_kernel<TX, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+}
+
 extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_plan) {
   MMR_REQUIRE(d && out_plan, "null argument");
   MMR_REQUIRE(d->nsrc >= 1 && d->nsrc <= 6, "nsrc must be 1..6, got %d", d->nsrc);
@@ -358,6 +548,11 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   MMR_REQUIRE((d->dz.up == 1 || d->dz.up == 2) && d->dz.H == d->H && d->dz.W == d->W && d->dz.N == d->N,
               "dz resolution mismatch");
   MMR_REQUIRE(d->partial && d->dst, "null output");
+  MMR_REQUIRE(d->mode == 0 || d->mode == 1, "mode must be 0 (taps on the activation side) or 1 (filter columns on dz)");
+  const bool kx = d->mode == 1;
+  if (kx)
+    MMR_REQUIRE(d->cb == 64 && (d->bn == 64 || d->bn == 32) && (d->tx == 1 || d->tx == 2) && d->dz.up == 1,
+                "mode 1 needs cb = 64, bn = 64 / 32, tx = 1 / 2 and a plain dz (got cb %d bn %d tx %d)", d->cb, d->bn, d->tx);
   WhPlan* pl = new WhPlan();
   WhParams& p = pl->prm;
   memset(&p, 0, sizeof(p));
@@ -374,8 +569,11 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.tiles_x = (d->W + 8 * d->tx - 1) / (8 * d->tx);
   p.tiles_y = (d->H + 15) / 16;
   p.total_tiles = p.tiles_x * p.tiles_y * d->N;
-  p.pitch[0] = 8 * d->tx + 2;
-  p.pitch[1] = 8 * d->tx + 4;
+  p.pitch[0] = kx ? 8 * d->tx : 8 * d->tx + 2;
+  p.pitch[1] = kx ? 8 * d->tx : 8 * d->tx + 4;
+  p.mode = d->mode;
+  p.prow = kx ? 192 : p.A * 128;
+  p.pcol = kx ? 3 * d->bn : d->bn;
 
   std::vector<CUtensorMap> maps;
   int nchunks = 0, ci0 = 0;
@@ -397,7 +595,7 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
       MMR_REQUIRE(s.up == 2 && s.H * 2 == d->H && s.W * 2 == d->W, "source %d: upsampled resolution mismatch", si);
       MMR_REQUIRE(d->H % 16 == 0, "nearest-x2 sources need H %% 16 == 0 (got %d)", d->H);
       any_up = true;
-      const cuuint32_t bw = (cuuint32_t)(4 * d->tx + 2);
+      const cuuint32_t bw = (cuuint32_t)(kx ? 4 * d->tx : 4 * d->tx + 2);
       {
         cuuint64_t dims[5] = {(cuuint64_t)s.C, 2, (cuuint64_t)s.W, 2, (cuuint64_t)s.N * s.H};
         cuuint64_t str[4] = {0, (cuuint64_t)s.C * 2, 0, (cuuint64_t)s.C * 2 * s.W};
@@ -424,7 +622,7 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.nchunks = nchunks;
   {
     const MmrHaloSrc& z = d->dz;
-    cuuint32_t box[4] = {(cuuint32_t)d->bn, (cuuint32_t)(8 * d->tx), 16, 1};
+    cuuint32_t box[4] = {(cuuint32_t)d->bn, (cuuint32_t)(kx ? 8 * d->tx + 2 : 8 * d->tx), 16, 1};
     p.dzmap = (int)maps.size();
     p.dz_phased = z.up == 2;
     if (!p.dz_phased) {
@@ -450,7 +648,9 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.x_tx_bytes[1] = (uint32_t)(18 * p.pitch[1] * p.xrb);
   // + 1 KB: the unused atoms of the last M tile read a few pixels past the halo
   p.x_stage_bytes = (p.x_tx_bytes[any_up ? 1 : 0] + 1024 + 1023) / 1024 * 1024;
-  p.z_tx_bytes = (uint32_t)(16 * 8 * d->tx * p.zrb);
+  p.z_tx_bytes = (uint32_t)(16 * (kx ? 8 * d->tx + 2 : 8 * d->tx) * p.zrb);
+  if (kx)  // + one tile row: the discarded atom of tile 1 (filter row 3) reads one row past the 18
+    p.x_stage_bytes = (p.x_tx_bytes[0] + (uint32_t)(p.pitch[0] * p.xrb) + 1023) / 1024 * 1024;
   p.stage_bytes = p.x_stage_bytes + (p.z_tx_bytes + 1023) / 1024 * 1024;
   int stages = (int)((224 * 1024) / p.stage_bytes);
   if (stages > kWhMaxStages) stages = kWhMaxStages;
@@ -459,7 +659,7 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.n_split = d->n_split < 1 ? 1 : d->n_split;
   if (p.n_split > p.total_tiles) p.n_split = p.total_tiles;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(p.A * d->bn)) cols <<= 1;
+  while (cols < (uint32_t)(kx ? 2 * 3 * d->bn : p.A * d->bn)) cols <<= 1;
   p.tmem_cols = cols;
   p.partial = d->partial;
   p.dst = d->dst;
@@ -484,6 +684,11 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.maps = reinterpret_cast<const CUtensorMap*>(pl->dev_blob);
   e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   if (e != cudaSuccess) cudaGetLastError();
+  if (kx) {
+    e = d->tx == 1 ? (d->bn == 64 ? wh_kx_attr<1, 64>() : wh_kx_attr<1, 32>())
+                   : (d->bn == 64 ? wh_kx_attr<2, 64>() : wh_kx_attr<2, 32>());
+    if (e != cudaSuccess) cudaGetLastError();
+  }
   *out_plan = pl;
   return 0;
 }
@@ -493,9 +698,16 @@ extern "C" int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t 
   WhPlan* pl = reinterpret_cast<WhPlan*>(plan);
   const WhParams& p = pl->prm;
   dim3 grid(p.nchunks * p.n_ntiles, p.n_split);
-  mmr_launch((conv_wgrad_halo_kernel), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
+  if (p.mode == 1) {
+    if (p.TX == 1 && p.bn == 64) mmr_launch((conv_wgrad_kx_kernel<1, 64>), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
+    else if (p.TX == 1) mmr_launch((conv_wgrad_kx_kernel<1, 32>), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
+    else if (p.bn == 64) mmr_launch((conv_wgrad_kx_kernel<2, 64>), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
+    else mmr_launch((conv_wgrad_kx_kernel<2, 32>), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
+  } else {
+    mmr_launch((conv_wgrad_halo_kernel), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
+  }
   MMR_CUDA_CHECK(cudaGetLastError());
-  const size_t total = (size_t)p.A * 128 * (p.bn / 4) * p.nchunks * p.n_ntiles;
+  const size_t total = (size_t)p.prow * (p.pcol / 4) * p.nchunks * p.n_ntiles;
   int64_t blocks = (int64_t)((total + 31) / 32);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;

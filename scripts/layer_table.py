@@ -12,11 +12,12 @@ import bench
 from mmrseg_b200.models import UnetPlusPlus
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-n = int(sys.argv[2]) if len(sys.argv) > 2 else bench.BATCH_PER_GPU
+cfg = bench.resolve("c2", 1)
+n = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["batch"]
 reps = 3
 torch.manual_seed(6210)
-model = UnetPlusPlus("resnet18", classes=bench.CLASSES).cuda().train()
-x, y = bench.synthetic(n)
+model = UnetPlusPlus("resnet18", classes=cfg["classes"]).cuda().train()
+x, y = bench.synthetic(cfg, n)
 x = x.cuda()
 eng = model._engine_for(x, training=True)
 eng.forward(x)

@@ -207,6 +207,17 @@ WGRAD_CASES = [
     (2, 32, 32, [(16, 1)], 2, None),          # the head: dz padded to 16 channels
     (3, 24, 40, [(64, 1)], 64, None),         # ragged
     (1, 8, 8, [(256, 1)], 256, None),
+    # third generation (filter column on the dz side) against the second, both forced
+    (2, 32, 32, [(64, 1)], 64, dict(mode=0)),
+    (2, 32, 32, [(64, 1)], 64, dict(mode=1, tx=1, n_split=1)),
+    (2, 32, 32, [(64, 1)], 64, dict(mode=1, tx=2, n_split=3)),
+    (3, 24, 40, [(64, 1)], 64, dict(mode=1, tx=2)),              # ragged in x and y
+    (3, 24, 40, [(64, 1)], 64, dict(mode=1, tx=1)),
+    (1, 32, 32, [(128, 2), (64, 1)], 64, dict(mode=1, tx=1)),    # nearest-x2 source
+    (1, 32, 48, [(128, 2), (64, 1)], 128, dict(mode=1, tx=2)),
+    (2, 32, 32, [(64, 2), (64, 1), (64, 1)], 32, dict(mode=1)),  # bn = 32: N = 96
+    (1, 16, 16, [(64, 1)], 96, dict(mode=1)),                    # Cout = 96: bn = 32, three N tiles
+    (1, 40, 24, [(64, 1)], 40, None),                            # Cout padded to 48: bn = 16, second generation
 ]
 
 
