@@ -316,7 +316,7 @@ def measure(cfg, args, world, rank, local, dev, full=True):
     """Runs one config; returns the JSON-able line (rank 0) or None.  full=False: the short form used for
     `other_configs` (device-resident value + conv aggregate only)."""
     import torch.distributed as dist
-    from mmrseg_b200.data import DevicePrefetcher
+    from mmrseg_b200.data import DevicePrefetcher, ResultReader
     from mmrseg_b200.losses import DiceCrossEntropyLoss
     from mmrseg_b200.metrics import confusion_matrix
     from mmrseg_b200.optim import FusedAdam
@@ -406,13 +406,20 @@ def measure(cfg, args, world, rank, local, dev, full=True):
     # ---- end to end through the public API: pinned host batches -> DevicePrefetcher -> step -> result read back
     feed = DevicePrefetcher(None, dev)
 
+    reader = ResultReader(lag=1)
+
     def run_e2e(host_x, k):
-        last = None
+        # every step's result (the loss / the confusion matrix) is read back to the host: an asynchronous copy into
+        # pinned memory behind the step's kernels, collected one step later (ResultReader), so the read does not
+        # drain the GPU queue the way `loss.item()` after every step does
+        got = []
         feed.loader = [(host_x, yh)] * k
         for x, y in feed:
             r = step_on(x, y)
-            last = r.item() if train else r.sum().item()     # device -> host read of the step's result
-        return last
+            got += reader.push(r if train else r.sum())
+        got += reader.flush()
+        assert len(got) == k
+        return float(got[-1])
 
     def timed_loop(host_x):
         run_e2e(host_x, 3)

@@ -732,6 +732,8 @@ def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=
     bn = 64 if cout_gemm % 64 == 0 else (32 if cout_gemm % 32 == 0 else 16)
     n_nt = cout_gemm // bn
     A = 5 if cb == 64 else 3
+    if os.environ.get("MMR_WGRAD_SMS"):   # A/B: CTAs of one launch (the side stream shares the SMs with the main one)
+        n_sms = int(os.environ["MMR_WGRAD_SMS"])
     modes = (1, 0) if (cb == 64 and bn in (64, 32) and not dz_phased) else (0,)
     if os.environ.get("MMR_WGRAD_MODE", "") != "":   # A/B switch for measurements
         modes = tuple(m for m in modes if m == int(os.environ["MMR_WGRAD_MODE"])) or (0,)

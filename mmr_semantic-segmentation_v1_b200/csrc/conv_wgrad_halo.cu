@@ -416,15 +416,18 @@ conv_wgrad_kx_kernel(const __grid_constant__ WhParams p) {
 __global__ void __launch_bounds__(256)
 wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
   pdl_prologue();
-  // 32 outputs (float4 each) per CTA x 8 split lanes (one warp each): a lane sums the splits
-  // k = lane, lane + 8, ... with four loads in flight, the eight lane sums are added in lane order
-  // through shared memory (deterministic), so the serial chain per thread is n_split / 8 long.
-  __shared__ float4 part[8][32];
+  // NL split lanes x (256 / NL) outputs (float4 each) per CTA, NL = 8 / 4 / 2 / 1 by the split count (with
+  // two splits, eight lanes left six of eight warps idle: 45 us on the 512-channel layers): a lane sums the
+  // splits k = lane, lane + NL, ... with four loads in flight, the lane sums are added in lane order
+  // through shared memory (deterministic), so the serial chain per thread is n_split / NL long.
+  __shared__ float4 part[256];
+  const int nl = p.n_split >= 8 ? 8 : (p.n_split >= 4 ? 4 : (p.n_split >= 2 ? 2 : 1));
+  const int per = 256 / nl;
   const int pc4 = p.pcol >> 2;
   const size_t per_slice = (size_t)p.prow * p.pcol;
-  const size_t total4 = (size_t)p.prow * pc4 * p.nchunks * p.n_ntiles;  // a multiple of 32
-  const int sl = threadIdx.x >> 5, o = threadIdx.x & 31;
-  for (size_t base = (size_t)blockIdx.x * 32; base < total4; base += (size_t)gridDim.x * 32) {
+  const size_t total4 = (size_t)p.prow * pc4 * p.nchunks * p.n_ntiles;  // a multiple of 256
+  const int sl = threadIdx.x / per, o = threadIdx.x % per;
+  for (size_t base = (size_t)blockIdx.x * per; base < total4; base += (size_t)gridDim.x * per) {
     const size_t idx = base + o;
     const int n4 = (int)(idx % pc4);
     size_t t = idx / pc4;
@@ -457,25 +460,26 @@ wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
                                                           (size_t)row * p.pcol) + n4;
       const size_t step = per_slice >> 2;
       int k = sl;
-      for (; k + 24 < p.n_split; k += 32) {
-        const float4 v0 = __ldg(src + (size_t)k * step), v1 = __ldg(src + (size_t)(k + 8) * step);
-        const float4 v2 = __ldg(src + (size_t)(k + 16) * step), v3 = __ldg(src + (size_t)(k + 24) * step);
+      for (; k + 3 * nl < p.n_split; k += 4 * nl) {
+        const float4 v0 = __ldg(src + (size_t)k * step), v1 = __ldg(src + (size_t)(k + nl) * step);
+        const float4 v2 = __ldg(src + (size_t)(k + 2 * nl) * step), v3 = __ldg(src + (size_t)(k + 3 * nl) * step);
         s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
         s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
         s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
         s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
       }
-      for (; k < p.n_split; k += 8) {
+      for (; k < p.n_split; k += nl) {
         const float4 v = __ldg(src + (size_t)k * step);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
     }
-    part[sl][o] = s;
-    __syncthreads();
+    if (nl > 1) {
+      part[threadIdx.x] = s;
+      __syncthreads();
+    }
     if (sl == 0 && live) {
-#pragma unroll
-      for (int j = 1; j < 8; ++j) {
-        const float4 v = part[j][o];
+      for (int j = 1; j < nl; ++j) {
+        const float4 v = part[j * per + o];
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
       const float sv[4] = {s.x, s.y, s.z, s.w};
@@ -486,7 +490,7 @@ wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
         *d = accumulate ? *d + sv[j] : sv[j];
       }
     }
-    __syncthreads();
+    if (nl > 1) __syncthreads();
   }
 }
 
@@ -708,7 +712,9 @@ extern "C" int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t 
   }
   MMR_CUDA_CHECK(cudaGetLastError());
   const size_t total = (size_t)p.prow * (p.pcol / 4) * p.nchunks * p.n_ntiles;
-  int64_t blocks = (int64_t)((total + 31) / 32);
+  const int nl = p.n_split >= 8 ? 8 : (p.n_split >= 4 ? 4 : (p.n_split >= 2 ? 2 : 1));
+  const int per = 256 / nl;
+  int64_t blocks = (int64_t)((total + per - 1) / per);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   mmr_launch((wgrad_halo_reduce_kernel), (int)blocks, 256, 0, as_stream(stream), p, accumulate);

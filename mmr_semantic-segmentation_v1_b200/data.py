@@ -60,3 +60,48 @@ class DevicePrefetcher:
 
     def __len__(self):
         return len(self.loader)
+
+
+class ResultReader:
+    """Per-step device -> host read of a small result (the loss, a confusion matrix) that does not drain the
+    GPU queue.  `loss.item()` after every step (SU/ModelTraining.py:619-622) stalls the host until the step has
+    finished and the GPU then idles while the host enqueues the next step (~0.4 ms of an 11 ms step).  `push(t)`
+    enqueues an asynchronous copy of `t` into pinned memory behind the step's kernels and returns the values of
+    the steps that have completed `lag` pushes ago (waiting on their copy events only); `flush()` returns the
+    rest.  Every step's value still reaches the host, in order, one step late."""
+
+    def __init__(self, lag=1):
+        self.lag = lag
+        self._slots = []      # (pinned tensor, event), oldest first
+        self._pool = []
+
+    def push(self, t):
+        t = t.detach()
+        host = None
+        for i, h in enumerate(self._pool):
+            if h.shape == t.shape and h.dtype == t.dtype:
+                host = self._pool.pop(i)
+                break
+        if host is None:
+            host = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        host.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        self._slots.append((host, ev))
+        out = []
+        while len(self._slots) > self.lag:
+            out.append(self._take())
+        return out
+
+    def _take(self):
+        host, ev = self._slots.pop(0)
+        ev.synchronize()
+        val = host.clone()
+        self._pool.append(host)
+        return val
+
+    def flush(self):
+        out = []
+        while self._slots:
+            out.append(self._take())
+        return out

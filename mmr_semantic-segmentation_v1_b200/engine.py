@@ -544,6 +544,9 @@ class Engine:
         for name in getattr(self, "out_seeds", {}):
             self.n_readers[name] = self.n_readers.get(name, 0) + 1
         self.fuse_bwd_reduce = self.fuse_finalize and not os.environ.get("MMR_NO_FUSED_BWD_REDUCE")
+        # channel counts of the units whose reduction rides on the consumer's data gradient (MMR_FUSED_BWD_CH: A/B)
+        self.fuse_bwd_channels = tuple(int(v) for v in os.environ.get("MMR_FUSED_BWD_CH", "64").split(",") if v)
+        self.wgrad_late = os.environ.get("MMR_WGRAD_LATE", "0") == "1"
         self.fused_dgrad_handles = set()   # data-gradient plans that also take a BatchNorm-backward reduction
         order = list(reversed(self.units))
         t_of = {id(u): t for t, u in enumerate(order)}
@@ -746,28 +749,36 @@ class Engine:
                     wplan = convplan.build_wgrad(dz, sources, u["k"], u["s"], u["pad"], gw, cout_gemm=cpad,
                                                  n_sms=self.n_sms, partial=self.wg_partial)
             u["wplan"] = wplan
-        calls.append((Engine._mark, ("side_begin", self._bwd_t)))
+        wcalls = [(Engine._mark, ("side_begin", self._bwd_t))]
         if kind == "stem" and "s2d" in u:
-            calls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, 0)))
-            self._rec(calls, "mmr_stem_s2d_wgrad_fold", u["dw3"], u["cout"], gw, acc)
+            wcalls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, 0)))
+            self._rec(wcalls, "mmr_stem_s2d_wgrad_fold", u["dw3"], u["cout"], gw, acc)
         elif isinstance(wplan, convplan.WgradHaloPlan):
-            calls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, acc)))
+            wcalls.append((self.lib.mmr_wgrad_halo_plan_run, (wplan.handle, acc)))
         else:
             for wp in u.get("wplans", [wplan]):
-                calls.append((self.lib.mmr_wgrad_plan_run, (wp.handle, 0, acc)))
-        calls.append((Engine._mark, ("side_end", self._bwd_t)))
-        if record_hooks:
-            self.conv_flops_bwd += wplan.flops
-            names = [conv + ".weight"]
-            if u.get("bn"):
-                names += [u["bn"] + ".weight", u["bn"] + ".bias"]
-            if kind == "head" or u["op"].get("bias"):
-                names.append(conv + ".bias")
-            self.param_ready_hooks.append((len(calls), names))
-        if kind == "stem":
-            return
+                wcalls.append((self.lib.mmr_wgrad_plan_run, (wp.handle, 0, acc)))
+        wcalls.append((Engine._mark, ("side_end", self._bwd_t)))
+
+        def emit_wgrad():
+            calls.extend(wcalls)
+            if record_hooks:
+                self.conv_flops_bwd += wplan.flops
+                names = [conv + ".weight"]
+                if u.get("bn"):
+                    names += [u["bn"] + ".weight", u["bn"] + ".bias"]
+                if kind == "head" or u["op"].get("bias"):
+                    names.append(conv + ".bias")
+                self.param_ready_hooks.append((len(calls), names))
+
         # data gradient, one tensor per source that needs it
-        need = [a.needs_grad and a.producer is not None for a, _ in u["srcs"]]
+        need = [] if kind == "stem" else [a.needs_grad and a.producer is not None for a, _ in u["srcs"]]
+        # MMR_WGRAD_LATE: fork the weight gradient AFTER the unit's data gradient is enqueued, so that it runs
+        # beside the next unit's BatchNorm-backward passes (HBM-bound) instead of beside its own data gradient
+        # (both tensor-bound, one CTA per SM each)
+        late = self.wgrad_late and any(need)
+        if not late:
+            emit_wgrad()
         if not any(need):
             return
         Hin, Win = u["in_hw"]
@@ -788,7 +799,7 @@ class Engine:
         if (self.fuse_bwd_reduce and u.get("halo") and len(u["srcs"]) == 1 and src_up == 1 and L is not None
                 and L.get("kind") == "conv" and L.get("bn") and L["op"]["relu"] and L.get("res") is None
                 and self.n_readers.get(src_a.name, 0) == 1 and L["cout"] == src_a.shape[3]
-                and L["cout"] in (16, 32, 64) and u["dcfg"]["n_ntiles"] == 1 and u["dcfg"]["bn"] == u["dcfg"]["sg"]
+                and L["cout"] in self.fuse_bwd_channels and u["dcfg"]["n_ntiles"] == 1 and u["dcfg"]["bn"] == u["dcfg"]["sg"]
                 and int(u["dcfg"].get("direct", u["dcfg"]["sg"] < 64)) == int(u["dcfg"]["sg"] < 64)):
             bnL = L["bn"]
             if "bwd_ticket" not in L:
@@ -822,6 +833,8 @@ class Engine:
             self.conv_flops_bwd += dplan.flops
         for si, (a, up) in enumerate(u["srcs"]):
             a.contribs.append((grads[si], 1 if up == 2 else 0))
+        if late:
+            emit_wgrad()
 
     # ------------------------------------------------------------------ execution
     def _run(self, calls, stream, lo=0, hi=None):

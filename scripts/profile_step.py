@@ -6,17 +6,18 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
+CFG = bench.resolve("c2", 1)
 from mmrseg_b200.losses import DiceCrossEntropyLoss
 from mmrseg_b200.models import UnetPlusPlus
 from mmrseg_b200.optim import FusedAdam
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else bench.BATCH_PER_GPU
+n = int(sys.argv[1]) if len(sys.argv) > 1 else CFG["batch"]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 torch.manual_seed(6210)
-model = UnetPlusPlus("resnet18", classes=bench.CLASSES).cuda().train()
+model = UnetPlusPlus("resnet18", classes=CFG["classes"]).cuda().train()
 crit = DiceCrossEntropyLoss(0.5)
 opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
-x, y = bench.synthetic(n)
+x, y = bench.synthetic(CFG, n)
 x, y = x.cuda(), y.cuda()
 for i in range(steps):
     for p in model.parameters():
