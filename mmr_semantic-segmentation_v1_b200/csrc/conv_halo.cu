@@ -81,6 +81,7 @@ struct HaloParams {
   MmrBnBwdFused bb;   // z == nullptr: no fused BatchNorm backward sums
   MmrHeadMetric hm;   // head launches: argmax / confusion matrix in the epilogue (all NULL: plain logits)
   int dbg;  // diagnostics (MMR_HALO_DBG): 1 no MMA issue, 2 no epilogue work, 4 no halo TMA, 8 no weight TMA
+  int epi_warps;  // 4, or 8: two warps per TMEM lane quarter, each taking 32 of the 64 channels of a store group
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -118,7 +119,11 @@ __device__ __forceinline__ void bulk_wait_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int nthreads = 128) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+// the two warps (column halves) of one TMEM lane quarter
+__device__ __forceinline__ void quarter_bar(int q) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory"); }
 
 // Shared-memory matrix descriptor split in two words so that the issue loop only adds to the low
 // one: hi = stride-dim offset | version 1 | swizzle; lo = (address >> 4) | LBO field 1.
@@ -365,19 +370,27 @@ __device__ __forceinline__ void colsum_butterfly(float (&s1)[SG], float (&s2)[SG
 // STATS: 0 none; 1 forward statistics (sum, sum of squares of the stored values); 2 BatchNorm-backward sums of a
 // data-gradient launch (MmrBnBwdFused): sum g and sum g*z with g = (z*msc + msh > 0) ? dx : 0, msc / msh read from
 // the `bb_affine` staging in shared memory.
-template <int SG, int STATS, bool PLAIN>
+// HV = 2 (SG = 64 only): eight epilogue warps, warp (q, hf) takes the channels [32 hf, 32 hf + 32) of the rows of TMEM
+// lane quarter q.  The statistics epilogues were as slow as the MMAs of an item (4 warps, one per scheduler, 128
+// accumulator registers each: a 9-10 us tail after the last MMA of every launch); with two warps per scheduler and
+// half the columns each they run ahead of the MMA warp again.  The two warps of a quarter fill one staging slice and
+// meet at a named barrier before warp hf = 0 issues its TMA store.
+template <int SG, int STATS, bool PLAIN, int HV = 1>
 __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base, uint8_t* out_base,
                                          uint64_t* tmem_full, uint64_t* tmem_empty, int q, int lane,
-                                         const float* bb_affine) {
+                                         const float* bb_affine, int hf = 0) {
+  static_assert(HV == 1 || SG == 64, "column halves only for 64-channel store groups");
   constexpr bool STAGED = SG == 64;
-  constexpr int CH = (STATS && SG > 32) ? 32 : SG;  // accumulator columns per TMEM round trip
+  constexpr int WC = SG / HV;                       // channels of this warp
+  constexpr int CH = (STATS && WC > 32) ? 32 : WC;  // accumulator columns per TMEM round trip
   constexpr int orb = SG * 2;                       // staging row bytes
   const int m = q * 32 + lane;                      // accumulator row = pixel (h, w) of the M tile
   const int h = m >> 3, w = m & 7;
+  const int cw = hf * WC;                           // first channel of this warp inside the store group
   const uint32_t xr = row_xor((uint32_t)m, orb);
-  float s1[STATS ? SG : 1], s2[STATS ? SG : 1];
+  float s1[STATS ? WC : 1], s2[STATS ? WC : 1];
 #pragma unroll
-  for (int j = 0; j < (STATS ? SG : 1); ++j) s1[j] = s2[j] = 0.f;
+  for (int j = 0; j < (STATS ? WC : 1); ++j) s1[j] = s2[j] = 0.f;
   int it = 0, gcount = 0;
   for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
     const ItemCoord ic = decode_item(p, item);
@@ -390,8 +403,8 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
         if (y < p.H && x < p.W) {
           const __nv_bfloat16* zr = reinterpret_cast<const __nv_bfloat16*>(p.bb.z) +
                                     (((size_t)ic.n * p.H + y) * p.W + x) * SG;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(zr));
-          if (SG == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(zr + 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(zr + cw));
+          if (WC == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(zr + 32));
         }
       }
     }
@@ -415,31 +428,32 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
         const bool valid = y < p.H && x < p.W;
         const size_t pix = ((size_t)ic.n * p.H + y) * p.W + x;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                               (uint32_t)((buf * p.TX * p.R + ir) * p.bn + g * SG);
+                               (uint32_t)((buf * p.TX * p.R + ir) * p.bn + g * SG + cw);
         uint8_t* stage = out_base + (size_t)(gcount % p.out_stages) * p.out_stage_bytes;
         if (STAGED && gcount >= p.out_stages) {
           // this warp's slice of the staging buffer is free once its store from out_stages groups
           // ago has been read out of shared memory
-          if (lane == 0) {
+          if (lane == 0 && hf == 0) {
             if (p.out_stages == 1) bulk_wait_read_n<0>(); else bulk_wait_read_n<1>();
           }
           __syncwarp();
         }
+        if (HV == 2) quarter_bar(q);   // the slice is free for both column halves
         const bool last = (g == p.gpn - 1) && (ir == p.TX * p.R - 1);
 #pragma unroll
-        for (int c0 = 0; c0 < SG; c0 += CH) {
+        for (int c0 = 0; c0 < WC; c0 += CH) {
           uint32_t r[CH];
           uint4 rz[STATS == 2 ? CH / 8 : 1];
           if (STATS == 2) {   // the unit's z at the same pixel: in flight while the accumulators are read
             const uint4* zp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.bb.z) +
-                                                             pix * SG + c0);
+                                                             pix * SG + cw + c0);
 #pragma unroll
             for (int k = 0; k < CH / 8; ++k) rz[k] = valid ? __ldg(zp + k) : make_uint4(0, 0, 0, 0);
           }
 #pragma unroll
           for (int k = 0; k < CH; k += 16) tmem_ld16(taddr + c0 + k, reinterpret_cast<uint32_t(&)[16]>(r[k]));
           tmem_ld_wait();
-          if (last && c0 + CH >= SG) {
+          if (last && c0 + CH >= WC) {
             // every TMEM read of this item is done: hand the accumulators back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -452,8 +466,8 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
             if (bb_affine) {   // one channel set per CTA: scale / shift staged in shared memory (broadcast reads)
 #pragma unroll
               for (int k = 0; k < CH / 4; ++k) {
-                const float4 a = *reinterpret_cast<const float4*>(bb_affine + c0 + 4 * k);
-                const float4 b = *reinterpret_cast<const float4*>(bb_affine + SG + c0 + 4 * k);
+                const float4 a = *reinterpret_cast<const float4*>(bb_affine + cw + c0 + 4 * k);
+                const float4 b = *reinterpret_cast<const float4*>(bb_affine + SG + cw + c0 + 4 * k);
                 v[4 * k] = fmaf(v[4 * k], a.x, b.x);
                 v[4 * k + 1] = fmaf(v[4 * k + 1], a.y, b.y);
                 v[4 * k + 2] = fmaf(v[4 * k + 2], a.z, b.z);
@@ -462,15 +476,15 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
             } else {
               if (p.scale) {
 #pragma unroll
-                for (int j = 0; j < CH; ++j) v[j] *= __ldg(p.scale + min(ch0 + c0 + j, p.cout_total - 1));
+                for (int j = 0; j < CH; ++j) v[j] *= __ldg(p.scale + min(ch0 + cw + c0 + j, p.cout_total - 1));
               }
               if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + min(ch0 + c0 + j, p.cout_total - 1));
+                for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + min(ch0 + cw + c0 + j, p.cout_total - 1));
               }
             }
             if (p.residual && valid) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_ldc + ch0 + c0);
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.res_ldc + ch0 + cw + c0);
 #pragma unroll
               for (int k = 0; k < CH / 8; ++k) {
                 const uint4 rv = __ldg(rp + k);
@@ -508,8 +522,8 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 const int j = 4 * k + jj, c = c0 + 2 * j;
-                const float2 a = *reinterpret_cast<const float2*>(bb_affine + c);        // mask scale
-                const float2 b = *reinterpret_cast<const float2*>(bb_affine + SG + c);   // mask shift
+                const float2 a = *reinterpret_cast<const float2*>(bb_affine + cw + c);        // mask scale
+                const float2 b = *reinterpret_cast<const float2*>(bb_affine + SG + cw + c);   // mask shift
                 const float z0 = __uint_as_float(zw[jj] << 16), z1 = __uint_as_float(zw[jj] & 0xffff0000u);
                 const float d0 = __uint_as_float(o[j] << 16), d1 = __uint_as_float(o[j] & 0xffff0000u);
                 const float g0 = fmaf(z0, a.x, b.x) > 0.f ? d0 : 0.f, g1 = fmaf(z1, a.y, b.y) > 0.f ? d1 : 0.f;
@@ -524,18 +538,18 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
             uint8_t* rowp = stage + (size_t)m * orb;
 #pragma unroll
             for (int k = 0; k < CH / 8; ++k)
-              *reinterpret_cast<uint4*>(rowp + ((((uint32_t)(c0 >> 3) + k) ^ xr) << 4)) =
+              *reinterpret_cast<uint4*>(rowp + ((((uint32_t)((cw + c0) >> 3) + k) ^ xr) << 4)) =
                   make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
           } else if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(gptr + pix * gldc + gcoff + c0);
+            uint4* dst = reinterpret_cast<uint4*>(gptr + pix * gldc + gcoff + cw + c0);
 #pragma unroll
             for (int k = 0; k < CH / 8; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
           }
         }
         if (STAGED) {
           fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
+          if (HV == 2) quarter_bar(q); else __syncwarp();   // both column halves of the slice are written
+          if (lane == 0 && hf == 0) {
             if (p.R == 1)
               tma_store_4d(&p.maps[p.smap0 + gi], stage + (size_t)q * 32 * orb, gcoff, ic.x0 + 8 * i, ic.y0 + 4 * q,
                            ic.n);
@@ -548,7 +562,7 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
       }
     }
   }
-  if (STAGED && lane == 0) bulk_wait0();
+  if (STAGED && lane == 0 && hf == 0) bulk_wait0();
   if constexpr (STATS != 0) {
     // column sums over the 32 accumulator rows of this warp by a halving butterfly: in the round with lane
     // mask mk a lane keeps one half of its channels and hands the other half to its partner, so the SG sums
@@ -556,10 +570,10 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
     // ran as 640 latency-bound shuffles: 8 us at the end of every launch).  Afterwards lane l owns the
     // channels [l * SG / 32, (l + 1) * SG / 32) (SG = 16: lanes 2c and 2c + 1 both hold channel c).
     double* slot = (STATS == 2 ? p.bb.slots : p.stats) + (size_t)(blockIdx.x & (kStatSlots - 1)) * 2 * p.stats_ld;
-    colsum_butterfly<SG, SG, 16>(s1, s2, lane);
-    constexpr int PER = SG >= 32 ? SG / 32 : 1;
-    const int cbase = SG >= 32 ? lane * PER : (lane >> 1);
-    if (SG >= 32 || !(lane & 1)) {
+    colsum_butterfly<WC, WC, 16>(s1, s2, lane);
+    constexpr int PER = WC >= 32 ? WC / 32 : 1;
+    const int cbase = cw + (WC >= 32 ? lane * PER : (lane >> 1));
+    if (WC >= 32 || !(lane & 1)) {
 #pragma unroll
       for (int j = 0; j < PER; ++j) {
         if (cbase + j < p.cout_total) {
@@ -696,7 +710,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], p.epi_warps);
     }
     fence_barrier_init();
   }
@@ -798,10 +812,12 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
 #undef MMR_MMA_CASES_TX
 #undef MMR_MMA_CASE
     if (lane == 0) MMR_TRACE(4);
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + p.epi_warps) {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp - 4;
-    const int m = q * 32 + lane;  // accumulator row = pixel (h, w) of the M tile
+    const int q = (warp - 4) & 3;   // TMEM lane quarter (a warp may only read the lanes 32 (warp % 4) ...)
+    const int hf = (warp - 4) >> 2; // column half (eight epilogue warps: statistics / BatchNorm-backward launches)
+    const int m = q * 32 + lane;    // accumulator row = pixel (h, w) of the M tile
+    const int et = (warp - 4) * 32 + lane, en = 32 * p.epi_warps;  // thread index / count of the epilogue group
     // fast path: default store mode of the group width, statistics (if any) of one channel set per CTA
     const bool plain = !p.scale && !p.bias && !p.residual && !p.relu;
     const bool fast = p.out_mode == MMR_OUT_BF16_NHWC && (p.direct != 0) == (p.sg < 64) &&
@@ -813,16 +829,16 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     if constexpr (EK == kEpiBnBwd) {
       // data gradient with the consumer unit's BatchNorm-backward sums: mask scale / shift staged in shared memory
       float* bb_affine = reinterpret_cast<float*>(bars + 32);
-      for (int c = m; c < p.sg; c += 128) {
+      for (int c = et; c < p.sg; c += en) {
         bb_affine[c] = __ldg(p.bb.mask_scale + c);
         bb_affine[p.sg + c] = __ldg(p.bb.mask_shift + c);
       }
-      epi_bar();
-      if (p.sg == 64) epi_fast<64, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
+      epi_bar(en);
+      if (p.sg == 64) epi_fast<64, 2, true, 2>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine, hf);
       if (p.sg == 32) epi_fast<32, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
       if (p.sg == 16) epi_fast<16, 2, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, bb_affine);
     } else if constexpr (EK == kEpiStats) {
-      if (p.sg == 64) epi_fast<64, 1, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
+      if (p.sg == 64) epi_fast<64, 1, true, 2>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr, hf);
       if (p.sg == 32) epi_fast<32, 1, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
       if (p.sg == 16) epi_fast<16, 1, true>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, nullptr);
     } else if constexpr (EK == kEpiPlain) {
@@ -997,18 +1013,18 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     }
     if (p.stats && persist) flush_stats(0);
     }  // generic epilogue
-    if (m == 0) MMR_TRACE(5);
+    if (et == 0) MMR_TRACE(5);
     if (p.stats && p.bnf.ticket) {
       // fused BatchNorm finalisation: the last CTA to get here owns the complete sums
       uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 30);
       __threadfence();
-      epi_bar();
-      if (m == 0) *flag = atomicAdd(p.bnf.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-      epi_bar();
+      epi_bar(en);
+      if (et == 0) *flag = atomicAdd(p.bnf.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+      epi_bar(en);
       if (*flag) {
         __threadfence();
         const double P = (double)p.bnf.count;
-        for (int c = m; c < p.cout_total; c += 128) {
+        for (int c = et; c < p.cout_total; c += en) {
           double s1 = 0.0, s2 = 0.0;
           for (int sl = 0; sl < kStatSlots; ++sl) {
             double* a = p.stats + (size_t)sl * 2 * p.stats_ld + c;
@@ -1032,7 +1048,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
             p.bnf.running_var[c] = (1.f - p.bnf.momentum) * p.bnf.running_var[c] + p.bnf.momentum * (float)unbiased;
           }
         }
-        if (m == 0) {
+        if (et == 0) {
           *p.bnf.ticket = 0u;
           if (p.bnf.num_batches_tracked) p.bnf.num_batches_tracked[0] += 1;
         }
@@ -1042,13 +1058,13 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       // fused BatchNorm-backward finalisation (the arithmetic of reduce_rows_kernel's last CTA)
       uint32_t* flag = reinterpret_cast<uint32_t*>(bars + 30);
       __threadfence();
-      epi_bar();
-      if (m == 0) *flag = atomicAdd(p.bb.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
-      epi_bar();
+      epi_bar(en);
+      if (et == 0) *flag = atomicAdd(p.bb.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+      epi_bar(en);
       if (*flag) {
         __threadfence();
         const int Cn = p.cout_total;
-        for (int c = m; c < Cn; c += 128) {
+        for (int c = et; c < Cn; c += en) {
           double s1 = 0.0, s2 = 0.0;
           for (int sl = 0; sl < kStatSlots; ++sl) {
             double* a = p.bb.slots + (size_t)sl * 2 * p.stats_ld + c;
@@ -1065,11 +1081,11 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
           p.bb.coef[Cn + c] = (float)(-gi * s2 / (double)p.bb.count);
           p.bb.coef[2 * Cn + c] = (float)(-gi * s1 / (double)p.bb.count);
         }
-        if (m == 0) *p.bb.ticket = 0u;
+        if (et == 0) *p.bb.ticket = 0u;
       }
     }
-    if (p.out_mode == MMR_OUT_BF16_NHWC && !p.direct && m == 0) bulk_wait0();
-    if (m == 0) MMR_TRACE(6);
+    if (p.out_mode == MMR_OUT_BF16_NHWC && !p.direct && et == 0) bulk_wait0();
+    if (et == 0) MMR_TRACE(6);
   }
 
   tc_fence_before();
@@ -1079,8 +1095,11 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   if (threadIdx.x == 0) MMR_TRACE(7);
 }
 
+// The statistics / BatchNorm-backward families run with eight epilogue warps (384 threads, 168 registers each).
+constexpr int halo_threads(int ek) { return (ek == kEpiStats || ek == kEpiBnBwd) ? kHaloThreads + 128 : kHaloThreads; }
+
 template <int EK>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(halo_threads(EK), 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
   conv_halo_body<EK>(p);
 }
 
@@ -1444,6 +1463,8 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
       pl->epi_kind = kEpiHead;
     else
       pl->epi_kind = kEpiOther;
+    // eight epilogue warps where the epilogue carries per-channel sums of a 64-channel store group
+    p.epi_warps = ((pl->epi_kind == kEpiStats || pl->epi_kind == kEpiBnBwd) && p.sg == 64) ? 8 : 4;
   }
   {
     const void* fns[kEpiKinds] = {(const void*)conv_halo_kernel<kEpiOther>, (const void*)conv_halo_kernel<kEpiStats>,
@@ -1463,9 +1484,9 @@ extern "C" int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream) {
   HaloPlan* pl = reinterpret_cast<HaloPlan*>(plan);
   if (pl->prm.total_items == 0) return 0;
   switch (pl->epi_kind) {
-    case kEpiStats: mmr_launch((conv_halo_kernel<kEpiStats>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+    case kEpiStats: mmr_launch((conv_halo_kernel<kEpiStats>), pl->grid, halo_threads(kEpiStats), pl->smem_bytes, as_stream(stream), pl->prm); break;
     case kEpiPlain: mmr_launch((conv_halo_kernel<kEpiPlain>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
-    case kEpiBnBwd: mmr_launch((conv_halo_kernel<kEpiBnBwd>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+    case kEpiBnBwd: mmr_launch((conv_halo_kernel<kEpiBnBwd>), pl->grid, halo_threads(kEpiBnBwd), pl->smem_bytes, as_stream(stream), pl->prm); break;
     case kEpiAffine: mmr_launch((conv_halo_kernel<kEpiAffine>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
     case kEpiHead: mmr_launch((conv_halo_kernel<kEpiHead>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
     default: mmr_launch((conv_halo_kernel<kEpiOther>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
