@@ -6,15 +6,21 @@ BatchNorm statistics, loss mean per replica, gradients averaged over ranks, para
 broadcast from rank 0 at construction (or, when the module is moved to its device after wrapping, before
 the first forward).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 
 class DistributedDataParallel(torch.nn.Module):
-    def __init__(self, module, bucket_mb=8.0, process_group=None, tail_mb=1.0):
+    def __init__(self, module, bucket_mb=None, process_group=None, tail_mb=None):
         super().__init__()
         self.module = module
         self.pg = process_group
+        # MMR_DDP_BUCKET_MB / MMR_DDP_TAIL_MB: measurement knobs (defaults: 24 MB buckets, 2 MB tail bucket: measured
+        # on 2 and 8 GPUs, 8 -> 24 MB buckets: 11.34 -> 11.20 ms and 11.59 -> 11.48 ms per step; fewer cuts of the backward graph)
+        bucket_mb = float(os.environ.get("MMR_DDP_BUCKET_MB", "24")) if bucket_mb is None else bucket_mb
+        tail_mb = float(os.environ.get("MMR_DDP_TAIL_MB", "2")) if tail_mb is None else tail_mb
         self.bucket_elems = int(bucket_mb * 1024 * 1024 / 4)
         self.tail_elems = int(tail_mb * 1024 * 1024 / 4)
         self.world = dist.get_world_size(self.pg) if dist.is_initialized() else 1
@@ -119,7 +125,7 @@ class DistributedDataParallel(torch.nn.Module):
     def _launch(self, i):
         lo, hi, _ = self._buckets[i]
         g = self.module._gflat[lo:hi]
-        if self.world == 1:
+        if self.world == 1 or os.environ.get("MMR_DDP_NO_COMM"):   # NO_COMM: attribution runs (N ranks, no exchange)
             return
         if self._side is not None:
             ev = torch.cuda.Event()
