@@ -168,7 +168,8 @@ class Engine:
 
     def _nblk(self, P, Cc):
         rows_per_iter = 256 // (Cc // 8)
-        return int(max(1, min(BN_BLOCKS, -(-P // (rows_per_iter * 4)))))
+        k = int(os.environ.get("MMR_BN_ITERS_PER_CTA", "4"))   # measurement knob: row iterations per CTA at least
+        return int(max(1, min(BN_BLOCKS, -(-P // (rows_per_iter * k)))))
 
     # ------------------------------------------------------------------ forward plan
     def _build_forward(self):

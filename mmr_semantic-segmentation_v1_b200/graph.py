@@ -113,6 +113,29 @@ def unetpp_graph(encoder_name="resnet18", classes=2, deep_supervision=False):
     return ops
 
 
+def smp_unet_graph(encoder_name="resnet18", classes=2):
+    """`smp.Unet` (the reference's `--model smp_unet18`, SU/ModelTraining.py:255-262): the plain U-Net decoder on the
+    same ResNet encoder -- five DecoderBlocks in a chain, block i = nearest x2 of the previous output ->
+    cat([x, skip_i]) -> Conv2dReLU -> Conv2dReLU with (in, skip, out) = (512, 256, 256), (256, 128, 128),
+    (128, 64, 64), (64, 64, 32), (32, 0, 16); `center` is the identity for ResNet encoders; 3x3 head with bias.
+    Parameter names are smp's (`decoder.blocks.<i>.conv1.0.weight`, ...)."""
+    ops = []
+    feats, chans = resnet_encoder_ops("encoder.", RESNET_LAYERS[encoder_name], ops)
+    rev = feats[::-1]                 # layer4, layer3, layer2, layer1, stem
+    x = rev[0]
+    for i, cout in enumerate(DECODER_CHANNELS):
+        src = [(x, 2)] + ([(rev[i + 1], 1)] if i + 1 < len(rev) else [])
+        base = "decoder.blocks.%d." % i
+        ops.append({"op": "conv", "out": "d%d.mid" % i, "conv": base + "conv1.0", "src": src, "k": 3, "s": 1,
+                    "cout": cout, "bn": base + "conv1.1", "bias": False, "relu": True, "res": None})
+        ops.append({"op": "conv", "out": "d%d" % i, "conv": base + "conv2.0", "src": [("d%d.mid" % i, 1)], "k": 3,
+                    "s": 1, "cout": cout, "bn": base + "conv2.1", "bias": False, "relu": True, "res": None})
+        x = "d%d" % i
+    ops.append({"op": "head", "out": "logits", "conv": "segmentation_head.0", "src": [(x, 1)], "k": 3,
+                "cout": classes})
+    return ops
+
+
 def resnet_unet_graph(resnet_model=18, n_class=10):
     """The reference's in-tree ResNet encoder/decoder (SU/UArchModel/resnet_unet.py:134-300):
     torchvision BasicBlock encoder, 1x1 conv+ReLU laterals, bilinear x2 (align_corners=True)

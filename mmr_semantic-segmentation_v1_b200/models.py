@@ -394,6 +394,57 @@ class UnetPlusPlus(_PlanModel):
         return graph.unetpp_graph(self.encoder_name, self.classes, self.deep_supervision)
 
 
+class _UnetDecoder(nn.Module):
+    """smp decoders/unet/decoder.py UnetDecoder for a ResNet encoder: `center` identity, five blocks in a list."""
+
+    def __init__(self):
+        super().__init__()
+        self.center = nn.Identity()
+        specs = [(512, 256, 256), (256, 128, 128), (128, 64, 64), (64, 64, 32), (32, 0, 16)]
+        self.blocks = nn.ModuleList([_DecoderBlock(i, s, o) for i, s, o in specs])
+        for m in self.modules():  # smp initialize_decoder
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+
+class Unet(_PlanModel):
+    """`smp.Unet(encoder_name="resnet18", encoder_weights="imagenet", in_channels=3, classes=C)` -- the reference's
+    `--model smp_unet18` (SU/ModelTraining.py:255-262): same constructor arguments and `state_dict` keys as smp's;
+    the decoder is a chain of the DecoderBlocks U-Net++ uses, on the same kernels (nearest x2 + concat in the
+    consumer's loader)."""
+
+    def __init__(self, encoder_name="resnet18", encoder_depth=5, encoder_weights=None,
+                 decoder_use_batchnorm=True, decoder_channels=(256, 128, 64, 32, 16),
+                 decoder_attention_type=None, in_channels=3, classes=1, activation=None, aux_params=None):
+        super().__init__()
+        if encoder_name not in graph.RESNET_LAYERS:
+            raise KeyError("encoder %r is not built; available: %s" % (encoder_name, list(graph.RESNET_LAYERS)))
+        if (encoder_depth != 5 or tuple(decoder_channels) != graph.DECODER_CHANNELS or in_channels != 3
+                or decoder_attention_type is not None or not decoder_use_batchnorm
+                or activation is not None or aux_params is not None):
+            raise NotImplementedError("only the configuration the reference uses is built: depth 5, "
+                                      "decoder (256,128,64,32,16) with batch-norm, 3 input channels")
+        if encoder_weights not in (None, "imagenet"):
+            raise KeyError("Wrong pretrained weights `%s` for encoder `%s`. Available options are: ['imagenet']"
+                           % (encoder_weights, encoder_name))
+        self.encoder_name, self.classes = encoder_name, classes
+        self._init_kwargs = {"encoder_name": encoder_name, "classes": classes}
+        self.encoder = _ResNetEncoder(encoder_name)
+        if encoder_weights == "imagenet":
+            _load_pretrained_resnet(self.encoder, encoder_name, "Unet(encoder_weights='imagenet')")
+        self.decoder = _UnetDecoder()
+        head = _conv(16, classes, 3, bias=True)
+        nn.init.xavier_uniform_(head.weight)
+        nn.init.constant_(head.bias, 0)
+        self.segmentation_head = nn.Sequential(head, nn.Identity(), nn.Identity())
+
+    def _graph(self):
+        return graph.smp_unet_graph(self.encoder_name, self.classes)
+
+
 def _convrelu(cin, cout, kernel, padding):  # SU/UArchModel/resnet_unet.py:36-44
     return nn.Sequential(nn.Conv2d(cin, cout, kernel, padding=padding), nn.ReLU(inplace=True))
 
@@ -513,7 +564,8 @@ class UNet(_PlanModel):
 def create_model(arch="UnetPlusPlus", encoder_name="resnet18", encoder_weights=None, in_channels=3,
                  classes=1, **kwargs):
     """`smp.create_model(**config['model'])` (ED/Main_MMR_SegModel.py:589)."""
-    if arch.lower() != "unetplusplus":
-        raise KeyError("architecture %r is not built; available: ['UnetPlusPlus']" % arch)
-    return UnetPlusPlus(encoder_name=encoder_name, encoder_weights=encoder_weights,
-                        in_channels=in_channels, classes=classes, **kwargs)
+    archs = {"unetplusplus": UnetPlusPlus, "unet": Unet}
+    if arch.lower() not in archs:
+        raise KeyError("architecture %r is not built; available: ['UnetPlusPlus', 'Unet']" % arch)
+    return archs[arch.lower()](encoder_name=encoder_name, encoder_weights=encoder_weights,
+                               in_channels=in_channels, classes=classes, **kwargs)

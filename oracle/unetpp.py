@@ -175,6 +175,39 @@ class UnetPlusPlus(nn.Module):
         return self.segmentation_head(self.decoder(*self.encoder(x)))
 
 
+class UnetDecoder(nn.Module):
+    """smp decoders/unet/decoder.py UnetDecoder (ResNet encoder: `center` = Identity, no attention):
+    features[1:] reversed; x = head; for every block x = block(x, skip_i or None)."""
+
+    def __init__(self, encoder_channels, decoder_channels=DECODER_CHANNELS, use_batchnorm=True):
+        super().__init__()
+        enc = list(encoder_channels[1:])[::-1]
+        in_ch = [enc[0]] + list(decoder_channels[:-1])
+        skip_ch = list(enc[1:]) + [0]
+        self.center = nn.Identity()
+        self.blocks = nn.ModuleList([DecoderBlock(i, s, o, use_batchnorm)
+                                     for i, s, o in zip(in_ch, skip_ch, decoder_channels)])
+
+    def forward(self, *features):
+        feats = list(features[1:])[::-1]
+        x = self.center(feats[0])
+        skips = feats[1:]
+        for i, block in enumerate(self.blocks):
+            x = block(x, skips[i] if i < len(skips) else None)
+        return x
+
+
+class Unet(UnetPlusPlus):
+    """`smp.Unet(encoder_name, encoder_weights, in_channels, classes)` (SU/ModelTraining.py:255-262, the
+    `--model smp_unet18` branch) with smp's defaults; same initialisation scheme as UnetPlusPlus.  smp is not on
+    disk: restated from the published architecture, numerically unpinned."""
+
+    def __init__(self, encoder_name="resnet18", encoder_weights=None, in_channels=3, classes=1):
+        super().__init__(encoder_name, encoder_weights, in_channels, classes)
+        self.decoder = UnetDecoder(self.encoder.out_channels)
+        self._init()
+
+
 def create_model(arch="UnetPlusPlus", encoder_name="resnet18", encoder_weights=None, in_channels=3,
                  classes=1, **kwargs):
     """smp.create_model as called at ED/Main_MMR_SegModel.py:589."""

@@ -196,3 +196,23 @@ def test_hausdorff_restatement_known_answers():
     assert hausdorff_distance(a, b) == 5.0
     a[4, 5] = True
     assert hausdorff_distance(a, b) == 1.0
+
+
+def test_smp_unet_restatement_structure():
+    """oracle.unetpp.Unet (the reference's `--model smp_unet18`, SU/ModelTraining.py:255-262): smp's published size
+    for Unet-resnet18 (14.3 M parameters: 14 328 209 at one class), smp's state_dict key scheme, and the product
+    model carries the same keys and shapes."""
+    import torch
+    from oracle.unetpp import Unet
+    from mmrseg_b200.models import Unet as Product
+    ref = Unet("resnet18", None, 3, 1)
+    assert sum(p.numel() for p in ref.parameters()) == 14_328_209
+    sd = ref.state_dict()
+    assert sd["decoder.blocks.0.conv1.0.weight"].shape == (256, 768, 3, 3)
+    assert sd["decoder.blocks.3.conv1.0.weight"].shape == (32, 128, 3, 3)
+    assert sd["decoder.blocks.4.conv1.0.weight"].shape == (16, 32, 3, 3)
+    prod = Product("resnet18", classes=1).state_dict()
+    assert list(prod.keys()) == list(sd.keys()) and all(prod[k].shape == sd[k].shape for k in sd)
+    ref.eval()
+    with torch.no_grad():
+        assert ref(torch.zeros(1, 3, 64, 96)).shape == (1, 1, 64, 96)
