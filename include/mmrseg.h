@@ -192,6 +192,9 @@ typedef struct {
   int32_t rph;
   const MmrBnBwdFused* bn_bwd; /* optional (data-gradient launches): see MmrBnBwdFused */
   const struct MmrHeadMetric* head_metric; /* optional (fp32 NCHW head launches): see MmrHeadMetric */
+  /* halo tile loader: 0 = one TMA box per chunk; 1 = cp.async gather by two warps (cb <= 32 only, halo_stages >= 2):
+   * TMA moves 32- / 64-byte pixel rows one at a time (~4 clk per row) and bounds the 16- / 32-channel 512^2 layers */
+  int32_t loader;
 } MmrHaloConvDesc;
 
 /* Eval-time metric fused into the segmentation head's epilogue: the reference's

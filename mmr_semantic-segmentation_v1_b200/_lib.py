@@ -95,6 +95,7 @@ class MmrHaloConvDesc(C.Structure):
         ("rph", C.c_int32),
         ("bn_bwd", C.POINTER(MmrBnBwdFused)),
         ("head_metric", C.POINTER(MmrHeadMetric)),
+        ("loader", C.c_int32),
     ]
 
 

@@ -417,6 +417,12 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
     seg_sizes = seg_sizes or [cpad]
     best = None
     no_r = bool(__import__("os").environ.get("MMR_NO_RPH"))
+    # halo loader of the narrow-row layers: 0 = TMA, 1 = cp.async gather by two warps.  Default: the gather for
+    # 16-channel sources at their own resolution (measured on x_0_4.conv2 / the head: 0.075 -> 0.064 ms; two warps
+    # sustain ~19 B/clk/SM of LDGSTS, TMA 10 B/clk/SM on 32-byte rows), TMA for 64-byte rows and nearest-x2 sources
+    # (x_0_4.conv1 fprop 0.079 vs 0.097 ms with the gather).  force['loader'] / MMR_HALO_LOADER override.
+    want = (force or {}).get("loader", os.environ.get("MMR_HALO_LOADER"))
+    cpl = cb <= 32 and (int(want) == 1 if want is not None else (cb == 16 and not any_up))
     # N tiles wider than 128 (or 96/160/192) are legal for the kernel but measured slower than 64/128 with
     # a wider macro tile (their weight slots crowd the shared-memory port): scripts/sweep_halo.sh
     for bn in ((force or {}).get("bn"),) if force and "bn" in force else (128, 64, 32, 16):
@@ -504,7 +510,7 @@ def halo_config(H, W, N, cb, nchunks, cout, any_up, bf16_out=True, n_sms=148, se
     if best is None:
         raise ValueError("no halo-kernel configuration for cout=%d cb=%d" % (cout, cb))
     cfg = best[1]
-    cfg.update(cb=cb, nchunks=nchunks, cpad=cpad)
+    cfg.update(cb=cb, nchunks=nchunks, cpad=cpad, loader=1 if cpl else 0)
     if force and "direct" in force:
         cfg["direct"] = force["direct"]
     return cfg
@@ -579,6 +585,7 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
     d.cb, d.bn, d.sg, d.n_ntiles = cfg["cb"], cfg["bn"], cfg["sg"], cfg["n_ntiles"]
     d.tx, d.tps = cfg["tx"], cfg["tps"]
     d.rph = cfg.get("rph", 1)
+    d.loader = cfg.get("loader", 0)
     d.halo_stages, d.w_slots, d.acc_bufs = cfg["halo_stages"], cfg["w_slots"], cfg["acc_bufs"]
     d.out_stages = max(1, cfg["out_stages"])
     d.direct_store = int(cfg.get("direct", cfg["sg"] < 64))

@@ -39,6 +39,8 @@ constexpr int kStatSlots = 8;
 
 struct HaloChunk {
   int32_t map, map_edge, c0, up;
+  const uint8_t* base;  // cp.async loader: channel c0 of pixel (0, 0, 0) of the source
+  int32_t pxb, sw, sh;  //   bytes per source pixel, stored width / height (half the conv's when up)
 };
 
 // MMR_HALO_DBG bit 16: per-CTA timestamps of the last conv_halo launch (diagnostic; scripts/halo_trace.py):
@@ -82,6 +84,7 @@ struct HaloParams {
   MmrHeadMetric hm;   // head launches: argmax / confusion matrix in the epilogue (all NULL: plain logits)
   int dbg;  // diagnostics (MMR_HALO_DBG): 1 no MMA issue, 2 no epilogue work, 4 no halo TMA, 8 no weight TMA
   int epi_warps;  // 4, or 8: two warps per TMEM lane quarter, each taking 32 of the 64 channels of a store group
+  int cpl;  // 1: halo tiles of 32- / 64-byte rows are gathered by warps 0 and 2 with cp.async
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -176,6 +179,7 @@ __device__ __forceinline__ void mma_warp_loop(const HaloParams& p, uint32_t tmem
       const uint32_t hiA = desc_hi32(pitch * rb, swz);
       const uint32_t row_step = (pitch * rb) >> 4;
       mbar_wait(&halo_full[hs], hph);
+      if (p.cpl) fence_proxy_async_smem();  // cp.async wrote the tile through the generic proxy
       tc_fence_after();
       if (it == 0 && c == 0 && (threadIdx.x & 31) == 0) MMR_TRACE(3);
       const uint32_t a_stage = ((halo0 + (uint32_t)hs * p.halo_stage_bytes + (up ? rb : 0u)) >> 4) | 0x10000u;
@@ -256,6 +260,7 @@ __device__ __forceinline__ void mma_warp_loop_r(const HaloParams& p, uint32_t tm
       const uint32_t hiA = desc_hi32((uint32_t)R * pitch * rb, swz);
       const uint32_t row_step = (pitch * rb) >> 4;
       mbar_wait(&halo_full[hs], hph);
+      if (p.cpl) fence_proxy_async_smem();  // cp.async wrote the tile through the generic proxy
       tc_fence_after();
       if (it == 0 && c == 0 && (threadIdx.x & 31) == 0) MMR_TRACE(3);
       const uint32_t a_stage = ((halo0 + (uint32_t)hs * p.halo_stage_bytes + (up ? rb : 0u)) >> 4) | 0x10000u;
@@ -682,6 +687,111 @@ __device__ __forceinline__ void epi_head_f32(const HaloParams& p, uint32_t tmem_
   if (count && cur_n >= 0) flush(cur_n);
 }
 
+
+// Halo producer for narrow rows (16 / 32 channels per chunk = 32- / 64-byte pixels).  TMA moves such a tile
+// one pixel row at a time (~4 clk per row: 75 us of an 84 us launch on the 16-channel 512^2 layers), so here
+// the 32 lanes of warp 0 gather it with 16-byte cp.async instead: each lane computes the source pixel (nearest
+// x2: low-resolution pixel (y >> 1, x >> 1)), zero-fills what lies outside the image (src-size 0) and writes
+// the 16-byte chunk where SWIZZLE_32B / 64B puts it (chunk index ^ address bits [7, 7 + log2(chunks))).
+// A stage is handed to the MMA warp by cp.async.mbarrier.arrive (one arrival per lane, when that lane's copies
+// have landed); the MMA warp issues the generic -> async proxy fence (tcgen05.mma reads shared memory through
+// the async proxy) after its wait.
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr int kCpWarps = 2;   // warps 0 and 2 (the TMEM allocator has nothing else to do) gather alternate rows
+constexpr int kCpMaxK = 5;    // 16-byte chunks of one tile row per lane: ceil(36 pixels * 4 chunks / 32)
+// The loop has to stay near 5 instructions per LDGSTS: scripts/probe/ldgsts_rate_probe.cu (profiles/r02r_ldgsts_rate.txt)
+// measures 47-54 clk per warp-wide LDGSTS.128 with 16-32 of them in flight per warp (11 / 19 / 24 B per clk and SM with
+// 1 / 2 / 4 warps: the HBM roofline needs 4), but 135 clk with only 4-8 in flight -- a first version with ~20 ALU
+// instructions per copy and a producer-side wait_group + proxy fence per stage ran at 120-300 clk.  So everything
+// that does not depend on the row is hoisted per item (source offset of the lane's chunks) or per launch (the
+// swizzled destination offsets of the lane's chunks for the 8 possible phases of a row start: row * pitch * rowbytes
+// modulo 1024), and a stage's copies are tracked by cp.async.mbarrier.arrive instead of a blocking wait.
+template <int K>
+__device__ __forceinline__ void halo_producer_cp_k(const HaloParams& p, uint8_t* halo_base, uint64_t* halo_full,
+                                                   uint64_t* halo_empty, int lane, int wsel) {
+  const int rows = 16 * p.R + 2;
+  const uint32_t rb = (uint32_t)p.rowbytes;
+  const int cpp_log = rb == 32 ? 1 : 2;       // 16-byte chunks per pixel: 2 or 4
+  const uint32_t cmask = (1u << cpp_log) - 1u;
+  const uint32_t jj = (uint32_t)lane & cmask;  // chunk index of every copy of this lane (32 % chunks per pixel == 0)
+  int hs = 0;
+  uint32_t hph = 0;
+  for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    const ItemCoord ic = decode_item(p, item);
+    for (int c = 0; c < p.nchunks; ++c) {
+      mbar_wait(&halo_empty[hs], hph ^ 1);
+      if (!(p.dbg & 4)) {
+        const HaloChunk ch = p.chunk[c];
+        const int pitch = p.pitch[ch.up];
+        const int per_row = pitch << cpp_log;
+        const uint32_t dst0 = smem_u32(halo_base + (size_t)hs * p.halo_stage_bytes);
+        const uint8_t* img = ch.base + (size_t)ic.n * ch.sh * ch.sw * ch.pxb;
+        const int xs = ch.up ? ic.x0 - 2 : ic.x0 - 1;
+        // per item: source byte offset of the lane's k-th chunk inside a row (-1: outside the image, -2: no chunk)
+        uint32_t soff[K], ssz[K], px_off[K];   // source offset (clamped), 16 / 0 bytes to read, pixel offset in the tile
+        bool have[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int e = lane + 32 * k;
+          const int px = e >> cpp_log;
+          int x = xs + px;
+          const bool ok = x >= 0 && x < p.W;
+          if (ch.up) x >>= 1;
+          have[k] = e < per_row;
+          soff[k] = ok ? (uint32_t)(x * ch.pxb) + jj * 16u : 0u;
+          ssz[k] = ok ? 16u : 0u;
+          px_off[k] = (uint32_t)px * rb + dst0;
+        }
+        const size_t row_stride = (size_t)ch.sw * ch.pxb;
+        const uint32_t row_bytes = (uint32_t)pitch * rb;
+#pragma unroll 2
+        for (int r = wsel; r < rows; r += kCpWarps) {
+          int y = ic.y0 - 1 + r;
+          const bool row_ok = y >= 0 && y < p.H;
+          if (ch.up) y >>= 1;
+          const uint8_t* rowp = img + (row_ok ? (size_t)y * row_stride : 0);   // a valid address either way
+          const uint32_t drow = (uint32_t)r * row_bytes;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if (have[k]) {
+              const uint32_t off = drow + px_off[k];     // dst0 is 1024-aligned: bits [7, 10) are the tile's own
+              cp_async16_zfill(off + ((jj ^ ((off >> 7) & cmask)) << 4), rowp + soff[k], row_ok ? ssz[k] : 0u);
+            }
+          }
+        }
+      }
+      // the lane's arrival fires when its copies of this stage have landed; the MMA warp then crosses to the
+      // async proxy itself
+      cp_async_mbar_arrive_noinc(&halo_full[hs]);
+      if (++hs == p.halo_stages) {
+        hs = 0;
+        hph ^= 1;
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+__device__ __forceinline__ void halo_producer_cp(const HaloParams& p, uint8_t* halo_base, uint64_t* halo_full,
+                                                 uint64_t* halo_empty, int lane, int wsel) {
+  // chunks per tile row and lane, over every source of the launch
+  const int cpp = p.rowbytes / 16;
+  const int pitch = p.pitch[1] > p.pitch[0] ? p.pitch[1] : p.pitch[0];
+  const int k = (pitch * cpp + 31) / 32;
+  if (k <= 2) halo_producer_cp_k<2>(p, halo_base, halo_full, halo_empty, lane, wsel);
+  else if (k == 3) halo_producer_cp_k<3>(p, halo_base, halo_full, halo_empty, lane, wsel);
+  else halo_producer_cp_k<kCpMaxK>(p, halo_base, halo_full, halo_empty, lane, wsel);
+}
+
 // Epilogue family of a launch.  One __global__ instantiation per family: the register allocation and the code
 // of the statistics / BatchNorm-backward / plain epilogues do not disturb each other (with all of them in one
 // kernel the forward-statistics epilogue of a 64 -> 64 layer ran 20 % slower).
@@ -713,7 +823,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();  // swizzled operands need the 1024-byte alignment
     for (int s = 0; s < p.halo_stages; ++s) {
-      mbar_init(&halo_full[s], 1);
+      mbar_init(&halo_full[s], p.cpl ? 32 * kCpWarps : 1);
       mbar_init(&halo_empty[s], 1);
     }
     for (int s = 0; s < p.w_slots; ++s) {
@@ -736,7 +846,9 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
   if (threadIdx.x == 0) MMR_TRACE(2);
 
-  if (warp == 0) {
+  if ((warp == 0 || warp == 2) && p.cpl) {
+    halo_producer_cp(p, halo_base, halo_full, halo_empty, lane, warp >> 1);
+  } else if (warp == 0) {
     // ---------------------------------------------------------------- halo producer
     int hs = 0;
     uint32_t hph = 0;
@@ -1333,7 +1445,8 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
     }
     for (int c0 = 0; c0 < s.C; c0 += d->cb) {
       MMR_REQUIRE(nchunks < kMaxChunks, "more than %d channel chunks", kMaxChunks);
-      p.chunk[nchunks++] = HaloChunk{mi, me, c0, s.up == 2 ? 1 : 0};
+      p.chunk[nchunks++] = HaloChunk{mi, me, c0, s.up == 2 ? 1 : 0,
+                                     reinterpret_cast<const uint8_t*>(s.ptr) + (size_t)c0 * 2, s.C * 2, s.W, s.H};
     }
   }
   p.nchunks = nchunks;
@@ -1394,6 +1507,9 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
       MMR_REQUIRE(!d->head_metric->confusion || d->head_metric->labels, "head metric: confusion needs labels");
     }
   }
+  p.cpl = d->loader == 1;
+  MMR_REQUIRE(d->loader == 0 || d->loader == 1, "loader must be 0 (TMA) or 1 (cp.async)");
+  MMR_REQUIRE(!p.cpl || (rb <= 64 && d->halo_stages >= 2), "the cp.async halo loader needs cb <= 32 and >= 2 halo stages");
   p.halo_tx_bytes[0] = (uint32_t)((16 * R + 2) * p.pitch[0] * rb);
   p.halo_tx_bytes[1] = (uint32_t)((16 * R + 2) * p.pitch[1] * rb);
   const uint32_t halo_bytes = p.halo_tx_bytes[any_up ? 1 : 0];

@@ -71,7 +71,15 @@ FPROP_CASES = [
     (3, 40, 24, [(64, 1)], 64, dict(rph=2, tx=2)),                 # ragged: 40 rows = one full + one partial item
     (2, 72, 40, [(64, 1)], 64, dict(rph=4, tx=1)),
     (2, 64, 64, [(64, 1)], 64, None),                              # whatever the config model picks
-    # narrow rows (32- / 64-byte pixels), ragged tiles, nearest-x2 sources
+    # narrow rows (32- / 64-byte pixels), ragged tiles, nearest-x2 sources; loader 1 = cp.async gather instead of TMA
+    (1, 32, 32, [(16, 1)], 16, dict(loader=1)),
+    (1, 64, 64, [(32, 2)], 16, dict(loader=1)),
+    (3, 24, 40, [(16, 1)], 16, dict(tx=4, loader=1)),              # ragged, zero fill on every side
+    (3, 24, 40, [(16, 1)], 16, dict(tx=1, halo_stages=2, loader=1)),
+    (2, 40, 24, [(32, 1)], 32, dict(tx=2, loader=1)),
+    (2, 32, 24, [(32, 2)], 16, dict(tx=2, loader=1)),
+    (2, 64, 48, [(32, 2), (16, 1)], 16, dict(rph=2, tx=4, loader=1)),
+    (1, 128, 64, [(16, 1)], 16, dict(rph=4, tx=2, loader=1)),
     (3, 24, 40, [(16, 1)], 16, dict(tx=4)),                        # ragged, zero fill on every side
     (3, 24, 40, [(16, 1)], 16, dict(tx=1, halo_stages=2)),
     (2, 40, 24, [(32, 1)], 32, dict(tx=2)),
