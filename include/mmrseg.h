@@ -306,11 +306,14 @@ typedef struct {
   int32_t dst_cout, dst_cin;
   int32_t mode;      /* 0: the nine taps are views of the activation halo tile (any cb);
                         1: third generation, cb = 64, bn = 64 / 32, tx <= 2: the filter column is a one-pixel shift of
-                           the dz tile (N = 3 bn per tcgen05.mma); partials [slices][n_split][192][3 bn] */
+                           the dz tile (N = 3 bn per tcgen05.mma); partials [slices][n_split][192][3 bn];
+                        2: the same formulation for narrow layers, cb = 16 / 32, bn = 16 / 32, tx = 2 / 4, tiles gathered
+                           with cp.async by six warps; partials [slices][n_split][3 cb][3 bn] */
 } MmrWgradHaloDesc;
 
 int64_t mmr_wgrad_halo_partial_floats(int nchunks, int cb, int bn, int n_ntiles, int n_split);
 int64_t mmr_wgrad_kx_partial_floats(int nchunks, int bn, int n_ntiles, int n_split); /* mode 1 */
+int64_t mmr_wgrad_thin_partial_floats(int nchunks, int cb, int bn, int n_ntiles, int n_split); /* mode 2 */
 int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* desc, void** plan);
 /* accumulate != 0 adds into dst (gradient accumulation). */
 int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t stream);

@@ -172,6 +172,7 @@ SIGNATURES = {
     "mmr_pack_weights_halo_batch": (_i, [_vp, _i, _i64, _vp]),
     "mmr_wgrad_halo_partial_floats": (_i64, [_i, _i, _i, _i, _i]),
     "mmr_wgrad_kx_partial_floats": (_i64, [_i, _i, _i, _i]),
+    "mmr_wgrad_thin_partial_floats": (_i64, [_i, _i, _i, _i, _i]),
     "mmr_wgrad_halo_plan_create": (_i, [C.POINTER(MmrWgradHaloDesc), C.POINTER(_vp)]),
     "mmr_wgrad_halo_plan_run": (_i, [_vp, _i, _vp]),
     "mmr_wgrad_halo_plan_destroy": (_i, [_vp]),

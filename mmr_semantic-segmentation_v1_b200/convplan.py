@@ -741,7 +741,12 @@ def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=
     A = 5 if cb == 64 else 3
     if os.environ.get("MMR_WGRAD_SMS"):   # A/B: CTAs of one launch (the side stream shares the SMs with the main one)
         n_sms = int(os.environ["MMR_WGRAD_SMS"])
-    modes = (1, 0) if (cb == 64 and bn in (64, 32) and not dz_phased) else (0,)
+    if cb == 64 and bn in (64, 32) and not dz_phased:
+        modes = (1, 0)
+    elif cb in (16, 32) and bn in (16, 32) and not dz_phased and W >= 16:
+        modes = (2, 0)    # narrow layers: one MMA of N = 3 bn per 16 pixels, tiles gathered with cp.async
+    else:
+        modes = (0,)
     if os.environ.get("MMR_WGRAD_MODE", "") != "":   # A/B switch for measurements
         modes = tuple(m for m in modes if m == int(os.environ["MMR_WGRAD_MODE"])) or (0,)
     if force and "mode" in force:
@@ -751,7 +756,12 @@ def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=
         for tx in (4, 2, 1):
             if tx > 1 and 8 * tx > -(-W // 8) * 8:
                 continue
-            if mode == 1:
+            if mode == 2:
+                if tx < 2:
+                    continue
+                stage = (-(-((16 + 128 // cb) * 8 * tx * cb * 2) // 1024) * 1024
+                         + -(-(16 * (8 * tx + 2) * bn * 2) // 1024) * 1024)
+            elif mode == 1:
                 if tx > 2:
                     continue
                 stage = -(-(19 * 8 * tx * 128) // 1024) * 1024 + -(-(16 * (8 * tx + 2) * bn * 2) // 1024) * 1024
@@ -770,8 +780,11 @@ def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=
             if force and "n_split" in force:
                 cfg["n_split"] = n_split = max(1, min(tiles, force["n_split"]))
             # per-stage issue time vs. the ~2-4 TMA operations one lane issues per stage
-            mma = tx * 8 * (2 * _mma_clk(3 * bn) if mode == 1 else A * _mma_clk(bn))
+            mma = tx * 8 * (_mma_clk(3 * bn) if mode == 2 else (2 * _mma_clk(3 * bn) if mode == 1 else A * _mma_clk(bn)))
             prod = (4 if any_up else 2) * 380
+            if cb <= 32:   # narrow rows: TMA ~4 clk per pixel row (modes 0 / 1); the gather streams at the HBM share
+                rows_px = (18 * (8 * tx + (0 if mode else 2)) + 16 * (8 * tx + (2 if mode else 0)))
+                prod = rows_px * (cb + bn) / 24.0 if mode == 2 else rows_px * 4
             per_tile = max(mma, prod) / tx
             waves = -(-(slices * n_split) // n_sms)
             total = waves * (-(-tiles // n_split)) * tx * per_tile * (1.0 if stages >= 3 else 1.1)
@@ -782,7 +795,8 @@ def wgrad_halo_config(H, W, N, cb, nchunks, cout_gemm, any_up, n_sms=148, force=
         raise ValueError("no halo wgrad configuration")
     cfg = best[1]
     cfg.update(cb=cb, nchunks=nchunks, n_ntiles=n_nt, A=A)
-    cfg["per_cta"] = 192 * 3 * bn if cfg["mode"] == 1 else A * 128 * bn   # fp32 partials of one CTA
+    # fp32 partials of one CTA
+    cfg["per_cta"] = {2: 3 * cb * 3 * bn, 1: 192 * 3 * bn, 0: A * 128 * bn}[cfg["mode"]]
     if max_partial is not None:
         per_split = nchunks * n_nt * cfg["per_cta"]
         cfg["n_split"] = max(1, min(cfg["n_split"], max_partial // per_split))

@@ -26,6 +26,8 @@ constexpr int kWhMaxAcc = 5;
 
 struct WhChunk {
   int32_t map, map_edge, c0, up, ci0;
+  const uint8_t* base;  // mode 2 (cp.async gather): channel c0 of pixel (0, 0, 0) of the source
+  int32_t pxb, sw, sh;  //   bytes per source pixel, stored width / height (half the conv's when up)
 };
 
 struct WhParams {
@@ -41,6 +43,8 @@ struct WhParams {
   float* dst;
   int dst_cout, dst_cin;
   int mode, prow, pcol;
+  const uint8_t* dz_base;  // mode 2: dz pixel (0, 0, 0), channel 0
+  int dz_pxb;
 };
 
 __device__ __forceinline__ bool wh_elect() {
@@ -410,6 +414,193 @@ conv_wgrad_kx_kernel(const __grid_constant__ WhParams p) {
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Mode 2: the same kx-on-dz formulation for the narrow layers (16- / 32-channel chunks, 16 / 32 output channels:
+// x_0_4.conv1 / conv2, the head, x_0_3.conv2).  One M tile stacks 128 / CB filter rows of the chunk (atoms one
+// tile row apart; rows ky >= 3 are discarded), N = 3 * BN: ONE tcgen05.mma per 16 pixels instead of three of
+// N = BN.  TMA moves 32- / 64-byte pixel rows one at a time (~4 clk per row: 137 of the 165 us of these launches),
+// so the tiles are gathered with 16-byte cp.async by the six warps that have nothing else to do during the main
+// loop (TMEM allocator, the idle warp, the four epilogue warps): scripts/probe/ldgsts_rate_probe.cu measures
+// 24 B/clk/SM = the HBM roofline with four or more warps.  Zero fill through src-size 0 is the convolution's
+// padding; the destination chunk index is XORed with address bits [7, 7 + log2(chunks per pixel)) -- SWIZZLE_32B /
+// 64B as tcgen05.mma expects it; completion through cp.async.mbarrier.arrive, the MMA warp crosses to the async
+// proxy after its wait.
+__device__ __forceinline__ void wh_cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+constexpr int kWhThinProducers = 6;   // warps 2 .. 7
+
+template <int TX, int CB, int BN>
+__global__ void __launch_bounds__(kWhThreads, 1)
+conv_wgrad_thin_kernel(const __grid_constant__ WhParams p) {
+  constexpr uint32_t PX = 8 * TX, PZ = 8 * TX + 2, XRB = CB * 2, ZRB = BN * 2, NN = 3 * BN;
+  constexpr uint32_t CX = XRB / 16, CZ = ZRB / 16;            // 16-byte chunks per pixel
+  constexpr uint32_t XPR = PX * CX, ZPR = PZ * CZ;            // chunks per tile row
+  constexpr uint32_t XTOT = 18 * XPR, ZTOT = 16 * ZPR;        // chunks per tile
+  constexpr uint32_t LIVE = 3 * CB;                           // accumulator rows that belong to a filter row
+  pdl_prologue();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWhMaxStages;
+  uint64_t* tmem_full = bars + 2 * kWhMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kWhMaxStages + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int slice = blockIdx.x;
+  const int c = slice / p.n_ntiles, nt = slice % p.n_ntiles;
+  const int split = blockIdx.y;
+  const int k_begin = (int)(((long long)p.total_tiles * split) / p.n_split);
+  const int k_end = (int)(((long long)p.total_tiles * (split + 1)) / p.n_split);
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 32 * kWhThinProducers);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  const WhChunk ch = p.chunk[c];
+
+  if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, NN, 1, 1);  // both operands MN-major
+    const uint32_t hiA = wh_desc_hi(PX * XRB, XRB == 64 ? 4u : 6u);
+    const uint32_t hiB = wh_desc_hi(PZ * ZRB, ZRB == 64 ? 4u : 6u);
+    constexpr uint32_t a_lbo = (PX * XRB) >> 4;  // next atom along M: the same pixels one tile row down (ky + 1)
+    constexpr uint32_t b_lbo = ZRB >> 4;         // next atom along N: one pixel to the right (kx - 1)
+    const uint32_t smem0 = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = k_begin; it < k_end; ++it) {
+      mbar_wait(&full[stage], phase);
+      fence_proxy_async_smem();   // cp.async wrote the tiles through the generic proxy
+      tc_fence_after();
+      const uint32_t x_lo = ((smem0 + (uint32_t)stage * p.stage_bytes) >> 4) | (a_lbo << 16);
+      const uint32_t z_lo = ((smem0 + (uint32_t)stage * p.stage_bytes + p.x_stage_bytes) >> 4) | (b_lbo << 16);
+      if (wh_elect()) {
+#pragma unroll
+        for (int i = 0; i < TX; ++i) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t a_k = x_lo + (((uint32_t)(2 * kk) * PX + 8u * i) * XRB >> 4);
+            const uint32_t b_k = z_lo + (((uint32_t)(2 * kk) * PZ + 8u * i) * ZRB >> 4);
+            if (i == 0 && kk == 0)
+              wh_umma(tmem_base, a_k, hiA, b_k, hiB, idesc, (uint32_t)(it != k_begin));
+            else
+              wh_umma(tmem_base, a_k, hiA, b_k, hiB, idesc, 1u);
+          }
+        }
+      }
+      __syncwarp();
+      if (wh_elect()) umma_commit(&empty[stage]);
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (wh_elect()) {
+      if (k_end > k_begin)
+        umma_commit(tmem_full);
+      else
+        mbar_arrive(tmem_full);
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    // ---------------------------------------------------------------- gather: warps 2 .. 7
+    const int pw = warp - 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int tx = k_begin % p.tiles_x, t = k_begin / p.tiles_x;
+    int ty = t % p.tiles_y, n = t / p.tiles_y;
+    const uint8_t* zimg0 = p.dz_base + (size_t)nt * BN * 2;
+    for (int it = k_begin; it < k_end; ++it) {
+      mbar_wait(&empty[stage], phase ^ 1);
+      const uint32_t sx = smem_u32(smem + (size_t)stage * p.stage_bytes);
+      const uint32_t sz = sx + p.x_stage_bytes;
+      const int x0 = tx * (int)PX, y0 = ty * 16;
+      const uint8_t* ximg = ch.base + (size_t)n * ch.sh * ch.sw * ch.pxb;
+      const uint8_t* zimg = zimg0 + (size_t)n * p.H * p.W * p.dz_pxb;
+      // activation tile: 18 rows (y0 - 1 ...) x PX pixels, no halo in x
+      for (uint32_t e = (uint32_t)pw * 32 + lane; e < XTOT; e += 32 * kWhThinProducers) {
+        const uint32_t r = e / XPR, q = e % XPR, px = q / CX, j = q % CX;
+        int y = y0 - 1 + (int)r, x = x0 + (int)px;
+        const bool ok = y >= 0 && y < p.H && x < p.W;
+        if (ch.up) y >>= 1, x >>= 1;
+        const uint32_t off = (r * PX + px) * XRB;
+        wh_cp_async16(sx + off + ((j ^ ((off >> 7) & (CX - 1))) << 4),
+                      ok ? ximg + ((size_t)y * ch.sw + x) * ch.pxb + j * 16 : ximg, ok ? 16u : 0u);
+      }
+      // dz tile: 16 rows x PZ pixels (x0 - 1 ...)
+      for (uint32_t e = (uint32_t)pw * 32 + lane; e < ZTOT; e += 32 * kWhThinProducers) {
+        const uint32_t r = e / ZPR, q = e % ZPR, px = q / CZ, j = q % CZ;
+        const int y = y0 + (int)r, x = x0 - 1 + (int)px;
+        const bool ok = y < p.H && x >= 0 && x < p.W;
+        const uint32_t off = (r * PZ + px) * ZRB;
+        wh_cp_async16(sz + off + ((j ^ ((off >> 7) & (CZ - 1))) << 4),
+                      ok ? zimg + ((size_t)y * p.W + x) * p.dz_pxb + j * 16 : zimg, ok ? 16u : 0u);
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+      if (++tx == p.tiles_x) {
+        tx = 0;
+        if (++ty == p.tiles_y) {
+          ty = 0;
+          ++n;
+        }
+      }
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (warp >= 4) {
+      // ---------------------------------------------------------------- epilogue: fp32 partials [3 CB][NN]
+      const int q = warp - 4;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int row = q * 32 + lane;
+      if (q * 32 < (int)LIVE) {   // warp-uniform: tcgen05.ld is a warp-wide instruction
+        float* dst = p.partial + ((size_t)slice * p.n_split + split) * (size_t)(LIVE * NN) + (size_t)row * NN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < (int)NN; c0 += 16) {
+          uint32_t r[16];
+          if (k_end > k_begin) {
+            tmem_ld16(taddr + c0, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+          }
+          if (row < (int)LIVE) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 // Sum the split-K partials in split order and scatter into OIHW fp32 (dst[co][ci][tap]).  One
 // thread owns four consecutive output channels of one accumulator row (float4 loads, four splits in
 // flight); rows that belong to no filter tap are skipped before any load.
@@ -425,20 +616,21 @@ wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
   const int per = 256 / nl;
   const int pc4 = p.pcol >> 2;
   const size_t per_slice = (size_t)p.prow * p.pcol;
-  const size_t total4 = (size_t)p.prow * pc4 * p.nchunks * p.n_ntiles;  // a multiple of 256
+  const size_t total4 = (size_t)p.prow * pc4 * p.nchunks * p.n_ntiles;  // modes 0 / 1: a multiple of 256
   const int sl = threadIdx.x / per, o = threadIdx.x % per;
   for (size_t base = (size_t)blockIdx.x * per; base < total4; base += (size_t)gridDim.x * per) {
-    const size_t idx = base + o;
+    const size_t idx = base + o < total4 ? base + o : total4 - 1;   // mode 2: total4 need not be a multiple of `per`
+    const bool in_range = base + o < total4;
     const int n4 = (int)(idx % pc4);
     size_t t = idx / pc4;
     const int row = (int)(t % p.prow);
     const int slice = (int)(t / p.prow);
     const int c = slice / p.n_ntiles, nt = slice % p.n_ntiles;
     int tap, chn, co;
-    if (p.mode == 1) {  // rows (ky, ci), columns (2 - kx, co)
+    if (p.mode >= 1) {  // rows (ky, ci), columns (2 - kx, co)
       const int col = n4 * 4;
-      tap = (row >> 6) * 3 + 2 - col / p.bn;
-      chn = row & 63;
+      tap = (row / p.cb) * 3 + 2 - col / p.bn;
+      chn = row % p.cb;
       co = nt * p.bn + col % p.bn;
     } else {
       const int a = row >> 7, r = row & 127;
@@ -453,7 +645,7 @@ wgrad_halo_reduce_kernel(const __grid_constant__ WhParams p, int accumulate) {
       co = nt * p.bn + n4 * 4;
     }
     const int ci = p.chunk[c].ci0 + chn;
-    const bool live = tap < 9 && co < p.dst_cout && ci < p.dst_cin;
+    const bool live = in_range && tap < 9 && co < p.dst_cout && ci < p.dst_cin;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
       const float4* src = reinterpret_cast<const float4*>(p.partial + (size_t)slice * p.n_split * per_slice +
@@ -540,6 +732,27 @@ static cudaError_t wh_kx_attr() {
   return cudaFuncSetAttribute(conv_wgrad_kx_kernel<TX, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
 }
 
+extern "C" int64_t mmr_wgrad_thin_partial_floats(int nchunks, int cb, int bn, int n_ntiles, int n_split) {
+  return (int64_t)nchunks * n_ntiles * n_split * 3 * cb * 3 * bn;
+}
+
+// mode 2 instantiations: (tx, cb, bn) in {2, 4} x {16, 32} x {16, 32}
+template <int TX, int CB, int BN>
+static cudaError_t wh_thin_do(const WhParams* p, dim3 grid, size_t smem, cudaStream_t st) {
+  if (!p)
+    return cudaFuncSetAttribute(conv_wgrad_thin_kernel<TX, CB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(227 * 1024));
+  return mmr_launch((conv_wgrad_thin_kernel<TX, CB, BN>), grid, kWhThreads, smem, st, *p);
+}
+static cudaError_t wh_thin_dispatch(int tx, int cb, int bn, const WhParams* p, dim3 grid, size_t smem, cudaStream_t st) {
+#define MMR_THIN(TX_, CB_, BN_) \
+  if (tx == TX_ && cb == CB_ && bn == BN_) return wh_thin_do<TX_, CB_, BN_>(p, grid, smem, st);
+  MMR_THIN(2, 16, 16) MMR_THIN(2, 16, 32) MMR_THIN(2, 32, 16) MMR_THIN(2, 32, 32)
+  MMR_THIN(4, 16, 16) MMR_THIN(4, 16, 32) MMR_THIN(4, 32, 16) MMR_THIN(4, 32, 32)
+#undef MMR_THIN
+  return cudaErrorInvalidValue;
+}
+
 extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_plan) {
   MMR_REQUIRE(d && out_plan, "null argument");
   MMR_REQUIRE(d->nsrc >= 1 && d->nsrc <= 6, "nsrc must be 1..6, got %d", d->nsrc);
@@ -552,8 +765,13 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   MMR_REQUIRE((d->dz.up == 1 || d->dz.up == 2) && d->dz.H == d->H && d->dz.W == d->W && d->dz.N == d->N,
               "dz resolution mismatch");
   MMR_REQUIRE(d->partial && d->dst, "null output");
-  MMR_REQUIRE(d->mode == 0 || d->mode == 1, "mode must be 0 (taps on the activation side) or 1 (filter columns on dz)");
+  MMR_REQUIRE(d->mode >= 0 && d->mode <= 2, "mode must be 0 (taps on the activation side), 1 (filter columns on dz) "
+              "or 2 (the same for narrow layers, cp.async gather)");
   const bool kx = d->mode == 1;
+  const bool thin = d->mode == 2;
+  if (thin)
+    MMR_REQUIRE((d->cb == 16 || d->cb == 32) && (d->bn == 16 || d->bn == 32) && (d->tx == 2 || d->tx == 4) && d->dz.up == 1,
+                "mode 2 needs cb = 16 / 32, bn = 16 / 32, tx = 2 / 4 and a plain dz (got cb %d bn %d tx %d)", d->cb, d->bn, d->tx);
   if (kx)
     MMR_REQUIRE(d->cb == 64 && (d->bn == 64 || d->bn == 32) && (d->tx == 1 || d->tx == 2) && d->dz.up == 1,
                 "mode 1 needs cb = 64, bn = 64 / 32, tx = 1 / 2 and a plain dz (got cb %d bn %d tx %d)", d->cb, d->bn, d->tx);
@@ -573,11 +791,13 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.tiles_x = (d->W + 8 * d->tx - 1) / (8 * d->tx);
   p.tiles_y = (d->H + 15) / 16;
   p.total_tiles = p.tiles_x * p.tiles_y * d->N;
-  p.pitch[0] = kx ? 8 * d->tx : 8 * d->tx + 2;
-  p.pitch[1] = kx ? 8 * d->tx : 8 * d->tx + 4;
+  p.pitch[0] = (kx || thin) ? 8 * d->tx : 8 * d->tx + 2;
+  p.pitch[1] = (kx || thin) ? 8 * d->tx : 8 * d->tx + 4;
   p.mode = d->mode;
-  p.prow = kx ? 192 : p.A * 128;
-  p.pcol = kx ? 3 * d->bn : d->bn;
+  p.prow = thin ? 3 * d->cb : (kx ? 192 : p.A * 128);
+  p.pcol = (kx || thin) ? 3 * d->bn : d->bn;
+  p.dz_base = reinterpret_cast<const uint8_t*>(d->dz.ptr);
+  p.dz_pxb = d->dz.C * 2;
 
   std::vector<CUtensorMap> maps;
   int nchunks = 0, ci0 = 0;
@@ -586,8 +806,12 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
     const MmrHaloSrc& s = d->src[si];
     MMR_REQUIRE(s.C % d->cb == 0, "source %d: %d channels are not a multiple of the chunk %d", si, s.C, d->cb);
     MMR_REQUIRE(s.N == d->N, "source %d: batch mismatch", si);
-    int mi, me = -1;
-    if (s.up == 1) {
+    int mi = -1, me = -1;
+    if (thin) {
+      MMR_REQUIRE(s.up == 1 ? (s.H == d->H && s.W == d->W) : (s.up == 2 && s.H * 2 == d->H && s.W * 2 == d->W),
+                  "source %d: resolution mismatch", si);
+      any_up |= s.up == 2;
+    } else if (s.up == 1) {
       MMR_REQUIRE(s.H == d->H && s.W == d->W, "source %d: resolution mismatch", si);
       cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.N};
       cuuint64_t str[3] = {(cuuint64_t)s.C * 2, (cuuint64_t)s.C * 2 * s.W, (cuuint64_t)s.C * 2 * s.W * s.H};
@@ -619,7 +843,8 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
     }
     for (int c0 = 0; c0 < s.C; c0 += d->cb) {
       MMR_REQUIRE(nchunks < kWhMaxChunks, "more than %d channel chunks", kWhMaxChunks);
-      p.chunk[nchunks++] = WhChunk{mi, me, c0, s.up == 2 ? 1 : 0, ci0 + c0};
+      p.chunk[nchunks++] = WhChunk{mi, me, c0, s.up == 2 ? 1 : 0, ci0 + c0,
+                                   reinterpret_cast<const uint8_t*>(s.ptr) + (size_t)c0 * 2, s.C * 2, s.W, s.H};
     }
     ci0 += s.C;
   }
@@ -629,7 +854,9 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
     cuuint32_t box[4] = {(cuuint32_t)d->bn, (cuuint32_t)(kx ? 8 * d->tx + 2 : 8 * d->tx), 16, 1};
     p.dzmap = (int)maps.size();
     p.dz_phased = z.up == 2;
-    if (!p.dz_phased) {
+    if (thin) {
+      // gathered with cp.async: no tensor map
+    } else if (!p.dz_phased) {
       cuuint64_t dims[4] = {(cuuint64_t)z.C, (cuuint64_t)z.W, (cuuint64_t)z.H, (cuuint64_t)z.N};
       cuuint64_t str[3] = {(cuuint64_t)z.C * 2, (cuuint64_t)z.C * 2 * z.W, (cuuint64_t)z.C * 2 * z.W * z.H};
       maps.emplace_back();
@@ -652,9 +879,11 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.x_tx_bytes[1] = (uint32_t)(18 * p.pitch[1] * p.xrb);
   // + 1 KB: the unused atoms of the last M tile read a few pixels past the halo
   p.x_stage_bytes = (p.x_tx_bytes[any_up ? 1 : 0] + 1024 + 1023) / 1024 * 1024;
-  p.z_tx_bytes = (uint32_t)(16 * (kx ? 8 * d->tx + 2 : 8 * d->tx) * p.zrb);
+  p.z_tx_bytes = (uint32_t)(16 * ((kx || thin) ? 8 * d->tx + 2 : 8 * d->tx) * p.zrb);
   if (kx)  // + one tile row: the discarded atom of tile 1 (filter row 3) reads one row past the 18
     p.x_stage_bytes = (p.x_tx_bytes[0] + (uint32_t)(p.pitch[0] * p.xrb) + 1023) / 1024 * 1024;
+  if (thin)  // the M tile stacks 128 / cb filter rows: the discarded ones read up to tile row 15 + 128 / cb - 1
+    p.x_stage_bytes = ((uint32_t)((16 + 128 / d->cb) * p.pitch[0] * p.xrb) + 1023) / 1024 * 1024;
   p.stage_bytes = p.x_stage_bytes + (p.z_tx_bytes + 1023) / 1024 * 1024;
   int stages = (int)((224 * 1024) / p.stage_bytes);
   if (stages > kWhMaxStages) stages = kWhMaxStages;
@@ -663,7 +892,7 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   p.n_split = d->n_split < 1 ? 1 : d->n_split;
   if (p.n_split > p.total_tiles) p.n_split = p.total_tiles;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(kx ? 2 * 3 * d->bn : p.A * d->bn)) cols <<= 1;
+  while (cols < (uint32_t)(thin ? 3 * d->bn : (kx ? 2 * 3 * d->bn : p.A * d->bn))) cols <<= 1;
   p.tmem_cols = cols;
   p.partial = d->partial;
   p.dst = d->dst;
@@ -673,13 +902,13 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   if (smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM (TMEM budget)
   pl->smem_bytes = smem;
 
-  const size_t maps_bytes = maps.size() * sizeof(CUtensorMap);
+  const size_t maps_bytes = (maps.empty() ? 1 : maps.size()) * sizeof(CUtensorMap);
   cudaError_t e = cudaMalloc(&pl->dev_blob, maps_bytes);
   if (e != cudaSuccess) {
     delete pl;
     return fail("cudaMalloc(%zu) failed: %s", maps_bytes, cudaGetErrorString(e));
   }
-  e = cudaMemcpy(pl->dev_blob, maps.data(), maps_bytes, cudaMemcpyHostToDevice);
+  e = maps.empty() ? cudaSuccess : cudaMemcpy(pl->dev_blob, maps.data(), maps_bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cudaFree(pl->dev_blob);
     delete pl;
@@ -693,6 +922,10 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
                    : (d->bn == 64 ? wh_kx_attr<2, 64>() : wh_kx_attr<2, 32>());
     if (e != cudaSuccess) cudaGetLastError();
   }
+  if (thin) {
+    e = wh_thin_dispatch(d->tx, d->cb, d->bn, nullptr, dim3(), 0, nullptr);
+    if (e != cudaSuccess) cudaGetLastError();
+  }
   *out_plan = pl;
   return 0;
 }
@@ -702,7 +935,9 @@ extern "C" int mmr_wgrad_halo_plan_run(void* plan, int accumulate, mmr_stream_t 
   WhPlan* pl = reinterpret_cast<WhPlan*>(plan);
   const WhParams& p = pl->prm;
   dim3 grid(p.nchunks * p.n_ntiles, p.n_split);
-  if (p.mode == 1) {
+  if (p.mode == 2) {
+    wh_thin_dispatch(p.TX, p.cb, p.bn, &p, grid, pl->smem_bytes, as_stream(stream));
+  } else if (p.mode == 1) {
     if (p.TX == 1 && p.bn == 64) mmr_launch((conv_wgrad_kx_kernel<1, 64>), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
     else if (p.TX == 1) mmr_launch((conv_wgrad_kx_kernel<1, 32>), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);
     else if (p.bn == 64) mmr_launch((conv_wgrad_kx_kernel<2, 64>), grid, kWhThreads, pl->smem_bytes, as_stream(stream), p);

@@ -233,6 +233,17 @@ WGRAD_CASES = [
     (2, 32, 32, [(64, 2), (64, 1), (64, 1)], 32, dict(mode=1)),  # bn = 32: N = 96
     (1, 16, 16, [(64, 1)], 96, dict(mode=1)),                    # Cout = 96: bn = 32, three N tiles
     (1, 40, 24, [(64, 1)], 40, None),                            # Cout padded to 48: bn = 16, second generation
+    # narrow layers (mode 2: one MMA of N = 3 bn per 16 pixels, cp.async gather) against the second generation
+    (2, 32, 64, [(16, 1)], 16, dict(mode=2, tx=4)),
+    (2, 32, 64, [(16, 1)], 16, dict(mode=2, tx=2, n_split=5)),
+    (2, 32, 64, [(16, 1)], 16, dict(mode=0)),
+    (3, 24, 40, [(16, 1)], 16, dict(mode=2, tx=4)),              # ragged in x and y
+    (3, 24, 40, [(32, 1)], 32, dict(mode=2, tx=2)),
+    (1, 64, 64, [(32, 2)], 16, dict(mode=2)),                    # x_0_4.conv1: nearest-x2 32-channel source
+    (2, 32, 48, [(32, 2), (16, 1)], 16, dict(mode=2, tx=4)),     # 16-channel chunks of a 32-channel source
+    (2, 32, 32, [(16, 1)], 2, dict(mode=2)),                     # the head: dz padded to 16 channels
+    (1, 32, 32, [(32, 1)], 32, dict(mode=2)),                    # x_0_3.conv2
+    (1, 32, 32, [(16, 1)], 48, dict(mode=2)),                    # three N tiles of 16
 ]
 
 
