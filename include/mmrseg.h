@@ -66,6 +66,8 @@ typedef struct {
    * a destination tensor [N][step*H][step*W][ldc] -- depth-to-space through the TMA store's strides (the
    * space-to-depth stem, mmr_stem_s2d_*). */
   int32_t step, oy, ox;
+  /* step == -2 (data-gradient launches, plain epilogue): the group is stored 2x2 SUM-POOLED into a tensor
+   * [N][H/2][W/2][ldc] -- the gradient with respect to a nearest-x2 upsampled source (smp DecoderBlock). */
 } MmrOutSeg;
 
 enum { MMR_OUT_BF16_NHWC = 0, MMR_OUT_F32_NCHW = 1 };

@@ -595,8 +595,9 @@ def build_halo(cfg, sources, packed, groups, N, H, W, cout, *, scale=None, bias=
         groups = [g if len(g) == 5 else (g[0], g[1], 1, 0, 0) for g in groups]
         segs = (MmrOutSeg * len(groups))(*[MmrOutSeg(t.data_ptr(), t.shape[3], coff, step, oy, ox)
                                            for t, coff, step, oy, ox in groups])
-        for t, _, step, _, _ in groups:
-            assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape[:3]) == (N, step * H, step * W)
+        for t, _, step, _, _ in groups:    # step -2: 2x2 sum-pooled store into a half-resolution tensor
+            want = (N, H // 2, W // 2) if step == -2 else (N, step * H, step * W)
+            assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape[:3]) == want
         groups = [(t, coff) for t, coff, _, _, _ in groups]
         d.ngroups = len(groups)
         d.groups = C.cast(segs, C.POINTER(MmrOutSeg))
@@ -686,22 +687,25 @@ def dgrad_halo_cfg(dz_shape, sizes, force=None):
     return halo_config(H, W, N, cb, Cz // cb, sum(sizes), False, seg_sizes=list(sizes), force=force)
 
 
-def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None, cfg=None, bn_bwd=None):
+def build_dgrad_halo(dz, w_oihw, grads, *, force=None, packed=None, cfg=None, bn_bwd=None, pooled=None):
     """Data gradient of a 3x3 s1 p1 conv: dz [N,H,W,Cz] bf16 (Cz = Cout padded to 16), grads = one bf16
-    tensor [N,H,W,Cs] per source in concat order."""
+    tensor [N,H,W,Cs] per source in concat order.  pooled[i]: source i was read through nearest x2, its
+    gradient tensor is [N,H/2,W/2,Cs] and receives the 2x2 sum of the conv-resolution gradient."""
     N, H, W, Cz = dz.shape
     cout, cin = w_oihw.shape[0], w_oihw.shape[1]
     assert Cz >= cout and Cz % 16 == 0
     sizes = [g.shape[3] for g in grads]
     assert sum(sizes) == cin
+    pooled = pooled or [False] * len(grads)
     if cfg is None:
         cfg = dgrad_halo_cfg(dz.shape, sizes, force)
     if packed is None:
         packed = pack_weights_halo(w_oihw, cfg, 1)
     groups = []
-    for g in grads:
+    for g, pl in zip(grads, pooled):
+        assert tuple(g.shape[1:3]) == ((H // 2, W // 2) if pl else (H, W))
         for c in range(0, g.shape[3], cfg["sg"]):
-            groups.append((g, c))
+            groups.append((g, c, -2, 0, 0) if pl else (g, c))
     plan = build_halo(cfg, [(dz, 1)], packed, groups, N, H, W, cin, bn_bwd=bn_bwd)
     plan.flops = 2 * N * H * W * cout * 9 * cin
     plan.packed = packed

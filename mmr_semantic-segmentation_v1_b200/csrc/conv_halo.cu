@@ -59,6 +59,7 @@ struct HaloParams {
   int32_t group_coff[kMaxGroups];
   int32_t group_ldc[kMaxGroups];
   __nv_bfloat16* group_ptr[kMaxGroups];
+  int32_t group_pool[kMaxGroups];  // 1: 2x2 sum-pooled store into [N][H/2][W/2][ldc] (data gradient of a nearest-x2 source)
   int nchunks, wmap, smap0;
   int H, W, N;
   int TX, R, tiles_x, tiles_y, n_ntiles, total_items;  // R: output-row phases stacked along N (1, 2, 4)
@@ -375,6 +376,69 @@ __device__ __forceinline__ void colsum_butterfly(float (&s1)[SG], float (&s2)[SG
 // STATS: 0 none; 1 forward statistics (sum, sum of squares of the stored values); 2 BatchNorm-backward sums of a
 // data-gradient launch (MmrBnBwdFused): sum g and sum g*z with g = (z*msc + msh > 0) ? dx : 0, msc / msh read from
 // the `bb_affine` staging in shared memory.
+
+// Data gradient of a nearest-x2 source (smp DecoderBlock's F.interpolate): its gradient is the 2x2 sum of the
+// conv-resolution gradient.  Instead of storing that 4x larger tensor for the BatchNorm-backward reduction to
+// pool (write + read of 1.1 GB per step over the ten upsampled sources of U-Net++), the epilogue pools in registers:
+// the two image rows of a window are two row phases of the same accumulator lane (rph >= 2) or lanes 8 apart
+// (rph = 1), the two pixels are neighbouring lanes; fp32 sum, one bf16 rounding, 16-byte stores into the
+// low-resolution tensor [N][H/2][W/2][ldc].
+template <int SG>
+__device__ __forceinline__ void epi_pool_group(const HaloParams& p, uint32_t tmem_base, uint64_t* tmem_empty, int q,
+                                               int lane, const ItemCoord& ic, int buf, int g, int gi, bool last_group) {
+  constexpr int CH = SG > 32 ? 32 : SG;
+  const int m = q * 32 + lane, h = m >> 3, w = m & 7;
+  __nv_bfloat16* const gptr = p.group_ptr[gi];
+  const int gldc = p.group_ldc[gi], gcoff = p.group_coff[gi];
+  const int Hl = p.H >> 1, Wl = p.W >> 1;
+  const int R = p.R;
+  const int npair = R >= 2 ? R / 2 : 1;
+  for (int i = 0; i < p.TX; ++i) {
+    for (int rp = 0; rp < npair; ++rp) {
+      const int ir0 = i * R + (R >= 2 ? 2 * rp : 0);
+      const bool last = last_group && i == p.TX - 1 && rp == npair - 1;
+      const int y = ic.y0 + R * h + (R >= 2 ? 2 * rp : 0), x = ic.x0 + 8 * i + w;
+      const bool keep = !(w & 1) && (R >= 2 || !((lane >> 3) & 1)) && y < p.H && x < p.W;
+      __nv_bfloat16* dst = gptr + (((size_t)ic.n * Hl + (y >> 1)) * Wl + (x >> 1)) * gldc + gcoff;
+#pragma unroll
+      for (int c0 = 0; c0 < SG; c0 += CH) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
+                               (uint32_t)((buf * p.TX * R + ir0) * p.bn + g * SG + c0);
+        uint32_t a[CH], b[CH];
+#pragma unroll
+        for (int k = 0; k < CH; k += 16) tmem_ld16(taddr + k, reinterpret_cast<uint32_t(&)[16]>(a[k]));
+        if (R >= 2) {
+#pragma unroll
+          for (int k = 0; k < CH; k += 16) tmem_ld16(taddr + p.bn + k, reinterpret_cast<uint32_t(&)[16]>(b[k]));
+        }
+        tmem_ld_wait();
+        if (last && c0 + CH >= SG) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+        float v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          v[j] = __uint_as_float(a[j]);
+          if (R >= 2)
+            v[j] += __uint_as_float(b[j]);
+          else
+            v[j] += __shfl_xor_sync(0xffffffffu, v[j], 8);
+          v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);
+        }
+        if (keep && !(p.dbg & 2)) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+          for (int k = 0; k < CH / 8; ++k)
+            d4[k] = make_uint4(pack_bf16x2(v[8 * k], v[8 * k + 1]), pack_bf16x2(v[8 * k + 2], v[8 * k + 3]),
+                               pack_bf16x2(v[8 * k + 4], v[8 * k + 5]), pack_bf16x2(v[8 * k + 6], v[8 * k + 7]));
+        }
+      }
+    }
+  }
+}
+
 // HV = 2 (SG = 64 only): eight epilogue warps, warp (q, hf) takes the channels [32 hf, 32 hf + 32) of the rows of TMEM
 // lane quarter q.  The statistics epilogues were as slow as the MMAs of an item (4 warps, one per scheduler, 128
 // accumulator registers each: a 9-10 us tail after the last MMA of every launch); with two warps per scheduler and
@@ -426,6 +490,10 @@ __device__ __forceinline__ void epi_fast(const HaloParams& p, uint32_t tmem_base
       const int gi = ic.nt * p.gpn + g;
       __nv_bfloat16* const gptr = p.group_ptr[gi];
       const int gldc = p.group_ldc[gi], gcoff = p.group_coff[gi];
+      if (STATS == 0 && PLAIN && HV == 1 && p.group_pool[gi]) {
+        epi_pool_group<SG>(p, tmem_base, tmem_empty, q, lane, ic, buf, g, gi, g == p.gpn - 1);
+        continue;
+      }
       for (int ir = 0; ir < p.TX * p.R; ++ir, ++gcount) {
         const int i = ir / p.R, r = ir % p.R;   // M tile, output-row phase
         const int x = ic.x0 + 8 * i + w;
@@ -1472,6 +1540,17 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
                   "store group %d: channels [%d, %d) do not fit a tensor of %d channels", g, og.coff,
                   og.coff + p.sg, og.ldc);
       maps.emplace_back();
+      p.group_pool[g] = og.step == -2;
+      if (og.step == -2) {
+        // 2x2 sum-pooled group: stored from registers, no tensor map (the entry above stays unused)
+        MMR_REQUIRE(d->H % 2 == 0 && d->W % 2 == 0 && !d->stats && !d->residual && !d->bn_bwd && !d->scale && !d->bias &&
+                        !d->relu,
+                    "pooled store groups need even H and W and a plain epilogue");
+        p.group_coff[g] = og.coff;
+        p.group_ldc[g] = og.ldc;
+        p.group_ptr[g] = reinterpret_cast<__nv_bfloat16*>(og.ptr);
+        continue;
+      }
       const int step = og.step > 1 ? og.step : 1;
       MMR_REQUIRE(step == 1 || (R == 1 && !d->direct_store && og.oy >= 0 && og.oy < step && og.ox >= 0 && og.ox < step &&
                                 !d->residual && !d->stats),
@@ -1591,6 +1670,11 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
       pl->epi_kind = kEpiHead;
     else
       pl->epi_kind = kEpiOther;
+    for (int g = 0; g < kMaxGroups; ++g)
+      if (p.group_pool[g] && pl->epi_kind != kEpiPlain) {
+        delete pl;
+        return fail("pooled store groups need the plain bf16 epilogue (default store mode of the group width)");
+      }
     // eight epilogue warps where the epilogue carries per-channel sums of a 64-channel store group
     p.epi_warps = ((pl->epi_kind == kEpiStats || pl->epi_kind == kEpiBnBwd) && p.sg == 64) ? 8 : 4;
   }

@@ -548,6 +548,7 @@ class Engine:
         # channel counts of the units whose reduction rides on the consumer's data gradient (MMR_FUSED_BWD_CH: A/B)
         self.fuse_bwd_channels = tuple(int(v) for v in os.environ.get("MMR_FUSED_BWD_CH", "64").split(",") if v)
         self.wgrad_late = os.environ.get("MMR_WGRAD_LATE", "0") == "1"
+        self.pool_dgrad = os.environ.get("MMR_POOL_DGRAD", "1") == "1"   # A/B switch
         self.fused_dgrad_handles = set()   # data-gradient plans that also take a BatchNorm-backward reduction
         order = list(reversed(self.units))
         t_of = {id(u): t for t, u in enumerate(order)}
@@ -784,8 +785,13 @@ class Engine:
             return
         Hin, Win = u["in_hw"]
         grads = []
+        # a nearest-x2 source gets its gradient already 2x2 sum-pooled by the data-gradient epilogue (halo kernel,
+        # plain epilogue): a quarter of the bytes written here and read by the source's BatchNorm-backward passes
+        plain_epi = u.get("halo") and int(u["dcfg"].get("direct", u["dcfg"]["sg"] < 64)) == int(u["dcfg"]["sg"] < 64)
+        pool_dx = [bool(up == 2 and plain_epi and self.pool_dgrad and Hin % 2 == 0 and Win % 2 == 0)
+                   for _, up in u["srcs"]]
         for si, (a, up) in enumerate(u["srcs"]):
-            shape = (a.shape[0], Hin, Win, a.shape[3])
+            shape = (a.shape[0], Hin // 2, Win // 2, a.shape[3]) if pool_dx[si] else (a.shape[0], Hin, Win, a.shape[3])
             if need[si]:
                 grads.append(view(("dx", id(u), si), shape))
             else:
@@ -816,7 +822,7 @@ class Engine:
         if dplan is None:
             if u.get("halo"):
                 dplan = convplan.build_dgrad_halo(dz, self.P[conv + ".weight"], grads, cfg=u["dcfg"],
-                                                  packed=u["wd_h"], bn_bwd=bb)
+                                                  packed=u["wd_h"], bn_bwd=bb, pooled=pool_dx)
             elif kind == "convt":   # dx = V(g): a plain 2x2 stride-2 conv of the output gradient
                 dplan = convplan.build_fprop([(dz, 1)], u["wf"], 2, 2, 0, grads[0])
                 dplan.flops = u["fplan"].flops
@@ -833,7 +839,7 @@ class Engine:
         if record_hooks:
             self.conv_flops_bwd += dplan.flops
         for si, (a, up) in enumerate(u["srcs"]):
-            a.contribs.append((grads[si], 1 if up == 2 else 0))
+            a.contribs.append((grads[si], 1 if (up == 2 and not pool_dx[si]) else 0))
         if late:
             emit_wgrad()
 

@@ -221,8 +221,15 @@ def check_backward(eng, P, G, x_in):
             hin, win = u["in_hw"]
             for si, (a, up) in enumerate(u["srcs"]):
                 c = min(a.shape[3], W.shape[1] - c0)
-                got = _nchw(eng.arena_view(("dx", id(u), si), (a.shape[0], hin, win, a.shape[3])))[:, :c]
-                rows.append((name, "data grad -> %s" % a.name, "bf16", _rel(got, _r(x.grad[:, c0:c0 + c]))))
+                want = x.grad[:, c0:c0 + c]
+                pooled = (up == 2 and u.get("halo") and getattr(eng, "pool_dgrad", False) and hin % 2 == 0 and win % 2 == 0
+                          and int(u["dcfg"].get("direct", u["dcfg"]["sg"] < 64)) == int(u["dcfg"]["sg"] < 64))
+                if pooled:   # the epilogue stores the 2x2 sum (fp32) of the conv-resolution gradient, rounded once
+                    want = F.avg_pool2d(want, 2) * 4.0
+                    got = _nchw(eng.arena_view(("dx", id(u), si), (a.shape[0], hin // 2, win // 2, a.shape[3])))[:, :c]
+                else:
+                    got = _nchw(eng.arena_view(("dx", id(u), si), (a.shape[0], hin, win, a.shape[3])))[:, :c]
+                rows.append((name, "data grad -> %s" % a.name, "bf16", _rel(got, _r(want))))
                 c0 += a.shape[3]
     return rows
 

@@ -207,6 +207,43 @@ def test_dgrad_matches_autograd(case):
     _check(got, ref)
 
 
+@pytest.mark.parametrize("case", [
+    # (N, H, W, channel counts per source, pooled flags, Cout, force)
+    (2, 32, 32, [128, 64], [True, False], 64, None),
+    (2, 32, 32, [128, 64], [True, False], 64, dict(bn=64, rph=1, tx=2)),      # rph 1: window rows are lanes 8 apart
+    (2, 64, 32, [64, 64, 64], [True, False, False], 64, dict(bn=64, rph=2, tx=2)),
+    (1, 64, 32, [64], [True], 64, dict(rph=4, tx=1)),
+    (1, 64, 64, [32], [True], 16, None),                                      # x_0_4.conv1: direct-store group
+    (3, 24, 40, [64, 64], [True, False], 64, None),                           # ragged tiles, even image
+    (2, 32, 32, [64, 64], [False, True], 128, dict(bn=128)),                  # the pooled group is the LAST of its item
+])
+def test_dgrad_pooled_groups(case):
+    """Data gradient with respect to a nearest-x2 source: the epilogue stores the 2x2 sum of the conv-resolution
+    gradient (fp32 sum, one bf16 rounding) into a half-resolution tensor."""
+    from mmrseg_b200 import convplan
+    N, H, W, sizes, pooled, Cout, force = case
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    cin = sum(sizes)
+    cz = -(-Cout // 16) * 16
+    dz = torch.zeros((N, H, W, cz), device="cuda", dtype=torch.bfloat16)
+    dz[..., :Cout] = _mk((N, H, W, Cout), gen)
+    w = torch.randn((Cout, cin, 3, 3), generator=gen, device="cuda") * (1.0 / (Cout * 9) ** 0.5)
+    grads = [torch.full((N, H // 2, W // 2, c) if pl else (N, H, W, c), float("nan"), device="cuda", dtype=torch.bfloat16)
+             for c, pl in zip(sizes, pooled)]
+    plan = convplan.build_dgrad_halo(dz, w, grads, force=force, pooled=pooled)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((N, cin, H, W), w.to(torch.bfloat16).float(),
+                                     dz[..., :Cout].float().permute(0, 3, 1, 2), stride=1, padding=1)
+    c0 = 0
+    for g, c, pl in zip(grads, sizes, pooled):
+        want = ref[:, c0:c0 + c]
+        if pl:
+            want = F.avg_pool2d(want, 2) * 4.0
+        _check(g, want)
+        c0 += c
+
+
 WGRAD_CASES = [
     # (N, H, W, [(C, up)], Cout, force)
     (2, 32, 32, [(64, 1)], 64, None),
