@@ -11,6 +11,8 @@
 //   SU/ModelTraining.py:600-603  loss = w*dice + (1-w)*CrossEntropy(x, t)
 //   monai DiceCELoss(softmax=True) (ED/Main_MMR_SegModel.py:578,709): same with y exact one-hot
 //                             and smoothing 1e-5 in numerator and denominator, weights 1 and 1.
+#include <atomic>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -31,10 +33,81 @@ __device__ __forceinline__ float warp_sum(float v) {
 //   then N*nblk*(3C+2)            per-block partials: for each (n, blk): I[C], P[C], Y[C], ce, cnt
 __host__ __device__ inline int64_t ws_head_doubles(int N, int C) { return (int64_t)N * C * 3 + 4; }
 
+constexpr int kLossTickets = 64;
+__device__ unsigned int g_loss_tickets[kLossTickets];   // self-resetting arrival counters, one per launch in flight
+
+// The combine step of the forward, run by the LAST block of dice_ce_fwd_kernel (ticket): one launch for the whole
+// forward.  Partials written by the other blocks are read with ld.global.cg.
+__device__ __forceinline__ void dice_ce_finalize_body(double* __restrict__ ws, int N, int C, int nblk,
+                                                      const MmrLossParams& prm, float* __restrict__ out) {
+  double* red = ws;
+  double* tail = red + (size_t)N * C * 3;
+  const double* part = ws + ws_head_doubles(N, C);
+  __shared__ double sh_dice[kLossThreads];
+  __shared__ double sh_ce[kLossThreads], sh_cnt[kLossThreads];
+  double dice_acc = 0.0, ce_acc = 0.0, cnt_acc = 0.0;
+  // one warp per (image, class): the lanes stride over the block partials (loads in flight instead of a serial
+  // chain of L2 round trips), then a fixed-order shuffle tree
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int k = warp; k < N * C; k += nwarp) {
+    const int n = k / C, c = k % C;
+    double I = 0.0, P = 0.0, Y = 0.0;
+    for (int b = lane; b < nblk; b += 32) {
+      const double* src = part + ((size_t)n * nblk + b) * (3 * C + 2);
+      I += __ldcg(src + c);
+      P += __ldcg(src + C + c);
+      Y += __ldcg(src + 2 * C + c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      I += __shfl_xor_sync(0xffffffffu, I, o);
+      P += __shfl_xor_sync(0xffffffffu, P, o);
+      Y += __shfl_xor_sync(0xffffffffu, Y, o);
+    }
+    if (lane == 0) {
+      red[(size_t)k * 3 + 0] = I;
+      red[(size_t)k * 3 + 1] = P;
+      red[(size_t)k * 3 + 2] = Y;
+      if (c < prm.dice_channels)
+        dice_acc += 1.0 - (2.0 * I + (double)prm.dice_eps_nr) / (P + Y + (double)prm.dice_eps_dr);
+    }
+  }
+  for (int k = threadIdx.x; k < N * nblk; k += blockDim.x) {
+    const double* src = part + (size_t)k * (3 * C + 2);
+    ce_acc += __ldcg(src + 3 * C);
+    cnt_acc += __ldcg(src + 3 * C + 1);
+  }
+  sh_dice[threadIdx.x] = dice_acc;
+  sh_ce[threadIdx.x] = ce_acc;
+  sh_cnt[threadIdx.x] = cnt_acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sh_dice[threadIdx.x] += sh_dice[threadIdx.x + s];
+      sh_ce[threadIdx.x] += sh_ce[threadIdx.x + s];
+      sh_cnt[threadIdx.x] += sh_cnt[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double dice = sh_dice[0] / ((double)N * (double)prm.dice_channels);
+    const double cnt = sh_cnt[0];
+    const double cem = cnt > 0.0 ? sh_ce[0] / cnt : 0.0;
+    tail[0] = sh_ce[0];
+    tail[1] = cnt;
+    tail[2] = dice;
+    tail[3] = (double)prm.w_dice * dice + (double)prm.w_ce * cem;
+    out[0] = (float)tail[3];
+    out[1] = (float)dice;
+    out[2] = (float)cem;
+  }
+}
+
 template <int CP>
 __global__ void __launch_bounds__(kLossThreads)
 dice_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int C,
-                   int64_t HW, MmrLossParams prm, double* __restrict__ ws, int nblk) {
+                   int64_t HW, MmrLossParams prm, double* __restrict__ ws, int nblk, float* __restrict__ result,
+                   int ticket_slot) {
   pdl_prologue();
   const int n = blockIdx.y;
   const float* lg = logits + (size_t)n * C * HW;
@@ -98,73 +171,17 @@ dice_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__
     for (int w = 0; w < kLossThreads / 32; ++w) s += (double)sh[w][sidx];
     out[k] = s;
   }
-}
-
-__global__ void dice_ce_finalize_kernel(double* __restrict__ ws, int N, int C, int nblk,
-                                        MmrLossParams prm, float* __restrict__ out) {
-  pdl_prologue();
-  // single block
-  double* red = ws;
-  double* tail = red + (size_t)N * C * 3;
-  const double* part = ws + ws_head_doubles(N, C);
-  __shared__ double sh_dice[kLossThreads];
-  __shared__ double sh_ce[kLossThreads], sh_cnt[kLossThreads];
-  double dice_acc = 0.0, ce_acc = 0.0, cnt_acc = 0.0;
-  // one warp per (image, class): the lanes stride over the block partials (loads in flight instead of a serial
-  // chain of L2 round trips), then a fixed-order shuffle tree
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  for (int k = warp; k < N * C; k += nwarp) {
-    const int n = k / C, c = k % C;
-    double I = 0.0, P = 0.0, Y = 0.0;
-    for (int b = lane; b < nblk; b += 32) {
-      const double* src = part + ((size_t)n * nblk + b) * (3 * C + 2);
-      I += src[c];
-      P += src[C + c];
-      Y += src[2 * C + c];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      I += __shfl_xor_sync(0xffffffffu, I, o);
-      P += __shfl_xor_sync(0xffffffffu, P, o);
-      Y += __shfl_xor_sync(0xffffffffu, Y, o);
-    }
-    if (lane == 0) {
-      red[(size_t)k * 3 + 0] = I;
-      red[(size_t)k * 3 + 1] = P;
-      red[(size_t)k * 3 + 2] = Y;
-      if (c < prm.dice_channels)
-        dice_acc += 1.0 - (2.0 * I + (double)prm.dice_eps_nr) / (P + Y + (double)prm.dice_eps_dr);
-    }
-  }
-  for (int k = threadIdx.x; k < N * nblk; k += blockDim.x) {
-    const double* src = part + (size_t)k * (3 * C + 2);
-    ce_acc += src[3 * C];
-    cnt_acc += src[3 * C + 1];
-  }
-  sh_dice[threadIdx.x] = dice_acc;
-  sh_ce[threadIdx.x] = ce_acc;
-  sh_cnt[threadIdx.x] = cnt_acc;
+  // the last block to get here owns every partial: it combines them (no second launch)
+  __shared__ unsigned int is_last;
+  __threadfence();
   __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      sh_dice[threadIdx.x] += sh_dice[threadIdx.x + s];
-      sh_ce[threadIdx.x] += sh_ce[threadIdx.x + s];
-      sh_cnt[threadIdx.x] += sh_cnt[threadIdx.x + s];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double dice = sh_dice[0] / ((double)N * (double)prm.dice_channels);
-    const double cnt = sh_cnt[0];
-    const double cem = cnt > 0.0 ? sh_ce[0] / cnt : 0.0;
-    tail[0] = sh_ce[0];
-    tail[1] = cnt;
-    tail[2] = dice;
-    tail[3] = (double)prm.w_dice * dice + (double)prm.w_ce * cem;
-    out[0] = (float)tail[3];
-    out[1] = (float)dice;
-    out[2] = (float)cem;
-  }
+  if (threadIdx.x == 0)
+    is_last = atomicAdd(&g_loss_tickets[ticket_slot], 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  dice_ce_finalize_body(ws, (int)gridDim.y, C, nblk, prm, result);
+  if (threadIdx.x == 0) g_loss_tickets[ticket_slot] = 0u;
 }
 
 // dL/dp[n,c,i] = -w_dice/(N*Cd) * (2*y - D_nc)/(Card_nc + eps_dr)  with D = (2I+eps_nr)/(Card+eps_dr)
@@ -359,9 +376,10 @@ extern "C" int mmr_dice_ce_fwd(const float* logits, const int64_t* labels, int N
   MMR_REQUIRE(N * C <= 65536, "N*C too large for the finalize kernel");
   const int64_t HW = (int64_t)H * W;
   dim3 grid(nblk, N);
-  DISPATCH_CP(C, (mmr_launch((dice_ce_fwd_kernel<CP>), grid, kLossThreads, 0, as_stream(stream), logits, labels, C, HW, *p, workspace, nblk)));
-  MMR_CUDA_CHECK(cudaGetLastError());
-  mmr_launch((dice_ce_finalize_kernel), 1, kLossThreads, 0, as_stream(stream), workspace, N, C, nblk, *p, out);
+  // one self-resetting arrival counter per launch in flight: a launch takes the next slot of a ring of 64
+  static std::atomic<unsigned> next_ticket{0};
+  const int slot = (int)(next_ticket.fetch_add(1u) % kLossTickets);
+  DISPATCH_CP(C, (mmr_launch((dice_ce_fwd_kernel<CP>), grid, kLossThreads, 0, as_stream(stream), logits, labels, C, HW, *p, workspace, nblk, out, slot)));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
