@@ -1246,30 +1246,63 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, float scale) {
   return l;
 }
 
-__global__ void upsample_bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
-                                               __nv_bfloat16* __restrict__ out) {
+// Forward: a thread owns one (output column, 8-channel group) and walks down a strip of output rows.  It keeps
+// the horizontally interpolated values of the two source rows of the stencil in registers; moving one output
+// row down advances the stencil by at most one source row, so a strip of `rows` output rows reads
+// rows / 2 + 1 source rows (two 16-byte loads each) instead of four loads per output element, and all index
+// arithmetic but one 32-bit division per thread is block-uniform.  A row of NHWC is contiguous in
+// (x, channel), so consecutive threads store consecutive 16-byte pieces.
+__global__ void __launch_bounds__(kEwThreads)
+upsample_bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int C, int rows,
+                               __nv_bfloat16* __restrict__ out) {
   pdl_prologue();
   const int H2 = 2 * H, W2 = 2 * W;
+  const uint32_t groups = (uint32_t)C / 8;
+  const uint32_t j = blockIdx.x * kEwThreads + threadIdx.x;      // piece of the output row
+  if (j >= (uint32_t)W2 * groups) return;
   const float sy = H2 > 1 ? (float)(H - 1) / (float)(H2 - 1) : 0.f;
   const float sx = W2 > 1 ? (float)(W - 1) / (float)(W2 - 1) : 0.f;
-  const uint32_t groups = (uint32_t)C / 8;
-  const int64_t total = (int64_t)N * H2 * W2 * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)((uint64_t)i % groups) * 8;
-    const int64_t pix = i / groups;
-    const int ox = (int)(pix % W2), oy = (int)((pix / W2) % H2), n = (int)(pix / ((int64_t)W2 * H2));
-    const Lerp ly = lerp_coord(oy, H, sy), lx = lerp_coord(ox, W, sx);
-    const __nv_bfloat16* base = x + (size_t)n * H * W * C + c;
-    float v00[8], v01[8], v10[8], v11[8], o[8];
-    load8(base + ((size_t)ly.i0 * W + lx.i0) * C, v00);
-    load8(base + ((size_t)ly.i0 * W + lx.i1) * C, v01);
-    load8(base + ((size_t)ly.i1 * W + lx.i0) * C, v10);
-    load8(base + ((size_t)ly.i1 * W + lx.i1) * C, v11);
+  const int ox = (int)(j / groups), c = (int)(j % groups) * 8;
+  const Lerp lx = lerp_coord(ox, W, sx);
+  const int n = blockIdx.z;
+  const __nv_bfloat16* src0 = x + (size_t)n * H * W * C + (size_t)lx.i0 * C + c;
+  const __nv_bfloat16* src1 = x + (size_t)n * H * W * C + (size_t)lx.i1 * C + c;
+  __nv_bfloat16* dst = out + (size_t)n * H2 * W2 * C + (size_t)j * 8;
+  const size_t in_row = (size_t)W * C, out_row = (size_t)W2 * C;
+  const int oy0 = blockIdx.y * rows, oy1 = min(H2, oy0 + rows);
+  int rowA = -1, rowB = -1;      // source rows held in hA / hB
+  float hA[8], hB[8];
+  auto hrow = [&](int r, float (&h)[8]) {
+    float a[8], b[8];
+    load8(src0 + (size_t)r * in_row, a);
+    load8(src1 + (size_t)r * in_row, b);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = ly.w0 * (lx.w0 * v00[j] + lx.w1 * v01[j]) + ly.w1 * (lx.w0 * v10[j] + lx.w1 * v11[j]);
-    store8(out + pix * C + c, o);
+    for (int k = 0; k < 8; ++k) h[k] = lx.w0 * a[k] + lx.w1 * b[k];
+  };
+  for (int oy = oy0; oy < oy1; ++oy) {
+    const Lerp ly = lerp_coord(oy, H, sy);
+    if (ly.i0 != rowA) {
+      if (ly.i0 == rowB) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hA[k] = hB[k];
+      } else {
+        hrow(ly.i0, hA);
+      }
+      rowA = ly.i0;
+    }
+    if (ly.i1 != rowB) {
+      if (ly.i1 == rowA) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hB[k] = hA[k];
+      } else {
+        hrow(ly.i1, hB);
+      }
+      rowB = ly.i1;
+    }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = ly.w0 * hA[k] + ly.w1 * hB[k];
+    store8(dst + (size_t)oy * out_row, o);
   }
 }
 
@@ -1291,39 +1324,72 @@ __device__ __forceinline__ void lerp_adjoint_weights(int i, int in, float scale,
   }
 }
 
-__global__ void upsample_bilinear2x_bwd_kernel(ContribList cl, int N, int H, int W, int C,
-                                               __nv_bfloat16* __restrict__ gin) {
+// The adjoint is separable like the forward.  A thread owns one (input column, 8-channel group) and a strip of
+// input rows: it walks down the output rows that touch the strip, takes the horizontal adjoint of each
+// (its <= 5 taps of that row, weights fixed per thread) and adds it, times the row's two vertical weights,
+// to the two input rows of that row's stencil.  Those advance monotonically, so two register accumulators
+// are enough: about 9 loads per input element instead of 16, the vertical weights are block-uniform, and
+// each gradient row is read by one strip (plus the rows shared with its neighbours).
+// SINGLE: one full-resolution contribution (the consumer conv's data gradient), read straight from its pointer.
+template <bool SINGLE>
+__global__ void __launch_bounds__(kEwThreads)
+upsample_bilinear2x_bwd_kernel(ContribList cl, int H, int W, int C, int rows, __nv_bfloat16* __restrict__ gin) {
   pdl_prologue();
   const int H2 = 2 * H, W2 = 2 * W;
+  const uint32_t groups = (uint32_t)C / 8;
+  const uint32_t j = blockIdx.x * kEwThreads + threadIdx.x;      // piece of the input row
+  if (j >= (uint32_t)W * groups) return;
   const float sy = H2 > 1 ? (float)(H - 1) / (float)(H2 - 1) : 0.f;
   const float sx = W2 > 1 ? (float)(W - 1) / (float)(W2 - 1) : 0.f;
-  const uint32_t groups = (uint32_t)C / 8;
-  const int64_t total = (int64_t)N * H * W * groups;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)((uint64_t)i % groups) * 8;
-    const int64_t pix = i / groups;
-    const int xi = (int)(pix % W), yi = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
-    int fy, fx;
-    float wy[6], wx[6];
-    lerp_adjoint_weights(yi, H, sy, fy, wy);
-    lerp_adjoint_weights(xi, W, sx, fx, wx);
-    float acc[8];
+  const int xi = (int)(j / groups), c = (int)(j % groups) * 8;
+  const int n = blockIdx.z;
+  int fx;
+  float wx[6];
+  lerp_adjoint_weights(xi, W, sx, fx, wx);
+  const int y0 = blockIdx.y * rows, y1 = min(H, y0 + rows);
+  const int d0 = max(0, 2 * y0 - 3), d1 = min(H2 - 1, 2 * (y1 - 1) + 4);
+  __nv_bfloat16* dst = gin + (size_t)n * H * W * C + (size_t)j * 8;
+  const size_t in_row = (size_t)W * C;
+  const __nv_bfloat16* g0 = cl.ptr[0] + (size_t)n * H2 * W2 * C + c;
+  int cur = lerp_coord(d0, H, sy).i0;      // accA belongs to input row cur, accB to cur + 1
+  float accA[8], accB[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int ky = 0; ky < 6; ++ky) {
-      if (wy[ky] == 0.f) continue;
-      for (int kx = 0; kx < 6; ++kx) {
-        const float wgt = wy[ky] * wx[kx];
-        if (wgt == 0.f) continue;
-        float g[8];
-        gather8(cl, n, fy + ky, fx + kx, c, H2, W2, C, g);
+  for (int k = 0; k < 8; ++k) accA[k] = accB[k] = 0.f;
+  for (int d = d0; d <= d1; ++d) {
+    const Lerp ly = lerp_coord(d, H, sy);
+    while (ly.i0 > cur) {        // the stencil moved down: row cur is complete
+      if (cur >= y0 && cur < y1) store8(dst + (size_t)cur * in_row, accA);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += wgt * g[j];
+      for (int k = 0; k < 8; ++k) {
+        accA[k] = accB[k];
+        accB[k] = 0.f;
       }
+      ++cur;
     }
-    store8(gin + pix * C + c, acc);
+    float h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (wx[k] == 0.f) continue;      // taps outside the image or outside this column's support
+      float g[8];
+      if (SINGLE)
+        load8(g0 + ((size_t)d * W2 + (fx + k)) * C, g);
+      else
+        gather8(cl, n, d, fx + k, c, H2, W2, C, g);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h[q] += wx[k] * g[q];
+    }
+    const float wa = ly.i1 == ly.i0 ? ly.w0 + ly.w1 : ly.w0;      // last row: both weights land on it
+    const float wb = ly.i1 == ly.i0 ? 0.f : ly.w1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      accA[k] += wa * h[k];
+      accB[k] += wb * h[k];
+    }
   }
+  if (cur >= y0 && cur < y1) store8(dst + (size_t)cur * in_row, accA);
+  if (cur + 1 >= y0 && cur + 1 < y1) store8(dst + (size_t)(cur + 1) * in_row, accB);
 }
 
 // ------------------------------------------------------------------ deep-supervision logits
@@ -1833,11 +1899,22 @@ extern "C" int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int
   return 0;
 }
 
+// Strip length of the row-walking bilinear kernels: as long as possible (the rows a strip shares with its
+// neighbours are read twice) while the launch still fills the SMs several times over.
+static int bilinear_strip_rows(int64_t threads_per_row_set, int H, int longest) {
+  int rows = longest;
+  while (rows > 2 && threads_per_row_set * ((H + rows - 1) / rows) < (int64_t)num_sms() * 2048 * 2) rows /= 2;
+  return rows;
+}
+
 extern "C" int mmr_upsample_bilinear2x_fwd(const void* x, int N, int H, int W, int C, void* out,
                                            mmr_stream_t stream) {
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
-  const int64_t total = (int64_t)N * 4 * H * W * (C / 8);
-  mmr_launch((upsample_bilinear2x_fwd_kernel), ew_blocks(total, 16), kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), N, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+  MMR_REQUIRE(N >= 1 && N <= 65535 && H >= 1 && W >= 1, "bad shape %d x %d x %d", N, H, W);
+  const int64_t pieces = (int64_t)2 * W * (C / 8);
+  const int rows = bilinear_strip_rows(pieces * N, 2 * H, 32);
+  dim3 grid((unsigned)((pieces + kEwThreads - 1) / kEwThreads), (unsigned)((2 * H + rows - 1) / rows), (unsigned)N);
+  mmr_launch((upsample_bilinear2x_fwd_kernel), grid, kEwThreads, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), H, W, C, rows, reinterpret_cast<__nv_bfloat16*>(out));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1845,10 +1922,16 @@ extern "C" int mmr_upsample_bilinear2x_fwd(const void* x, int N, int H, int W, i
 extern "C" int mmr_upsample_bilinear2x_bwd(const MmrContrib* contribs, int ncontrib, int N, int H, int W,
                                            int C, void* gin, mmr_stream_t stream) {
   MMR_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  MMR_REQUIRE(N >= 1 && N <= 65535 && H >= 1 && W >= 1, "bad shape %d x %d x %d", N, H, W);
   ContribList cl;
   if (fill_contribs(cl, contribs, ncontrib)) return -1;
-  const int64_t total = (int64_t)N * H * W * (C / 8);
-  mmr_launch((upsample_bilinear2x_bwd_kernel), ew_blocks(total, 16), kEwThreads, 0, as_stream(stream), cl, N, H, W, C, reinterpret_cast<__nv_bfloat16*>(gin));
+  const int64_t pieces = (int64_t)W * (C / 8);
+  const int rows = bilinear_strip_rows(pieces * N, H, 16);
+  dim3 grid((unsigned)((pieces + kEwThreads - 1) / kEwThreads), (unsigned)((H + rows - 1) / rows), (unsigned)N);
+  if (cl.n == 1 && !cl.pool2[0])
+    mmr_launch((upsample_bilinear2x_bwd_kernel<true>), grid, kEwThreads, 0, as_stream(stream), cl, H, W, C, rows, reinterpret_cast<__nv_bfloat16*>(gin));
+  else
+    mmr_launch((upsample_bilinear2x_bwd_kernel<false>), grid, kEwThreads, 0, as_stream(stream), cl, H, W, C, rows, reinterpret_cast<__nv_bfloat16*>(gin));
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -1,20 +1,21 @@
-"""One process, three U-Net++ train steps at the bench configuration (batch 16 @ 512x512): the
-command that the ncu launch list / full capture under profiles/ are taken from."""
+"""One process, a few train steps at a bench configuration (default c2: U-Net++, batch 16 @ 512x512): the
+command that the ncu launch list / full capture under profiles/ are taken from.
+
+    python scripts/profile_step.py [batch] [steps] [config]"""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-CFG = bench.resolve("c2", 1)
+CFG = bench.resolve(sys.argv[3] if len(sys.argv) > 3 else "c2", 1)
 from mmrseg_b200.losses import DiceCrossEntropyLoss
-from mmrseg_b200.models import UnetPlusPlus
 from mmrseg_b200.optim import FusedAdam
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else CFG["batch"]
+n = int(sys.argv[1]) if len(sys.argv) > 1 and int(sys.argv[1]) > 0 else CFG["batch"]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 torch.manual_seed(6210)
-model = UnetPlusPlus("resnet18", classes=CFG["classes"]).cuda().train()
+model = bench.build_model(CFG, torch.device("cuda", 0)).train()
 crit = DiceCrossEntropyLoss(0.5)
 opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
 x, y = bench.synthetic(CFG, n)

@@ -1,4 +1,6 @@
-"""CUDA-event time of one U-Net++ train step (batch 16 @ 512x512) per C-ABI entry point."""
+"""CUDA-event time of one train step per C-ABI entry point.
+
+    python scripts/step_breakdown.py [batch] [config]      config = c2 (default) | c3 | c4"""
 import ctypes as C
 import os
 import sys
@@ -7,14 +9,13 @@ from collections import defaultdict
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-CFG = bench.resolve("c2", 1)
+CFG = bench.resolve(sys.argv[2] if len(sys.argv) > 2 else "c2", 1)
 from mmrseg_b200.losses import DiceCrossEntropyLoss
-from mmrseg_b200.models import UnetPlusPlus
 from mmrseg_b200.optim import FusedAdam
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else CFG["batch"]
+n = int(sys.argv[1]) if len(sys.argv) > 1 and int(sys.argv[1]) > 0 else CFG["batch"]
 torch.manual_seed(6210)
-model = UnetPlusPlus("resnet18", classes=CFG["classes"]).cuda().train()
+model = bench.build_model(CFG, torch.device("cuda", 0)).train()
 crit = DiceCrossEntropyLoss(0.5)
 opt = FusedAdam(model.parameters(), lr=1e-3, weight_decay=1e-5)
 x, y = bench.synthetic(CFG, n)
