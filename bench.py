@@ -215,7 +215,7 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- our arm
 def kernels_per_call(lib, fn):
-    two = (lib.mmr_wgrad_plan_run, lib.mmr_wgrad_halo_plan_run, lib.mmr_head_grad_prep)
+    two = (lib.mmr_wgrad_plan_run, lib.mmr_wgrad_halo_plan_run, lib.mmr_head_grad_prep, lib.mmr_pointwise_head_bwd)
     if not hasattr(fn, "restype"):      # scheduling marker of the engine's launch lists, not a kernel
         return 0
     return 2 if any(fn is f for f in two) else 1

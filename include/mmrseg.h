@@ -490,6 +490,22 @@ int mmr_dice_ce_bwd(const float* logits, const int64_t* labels, int N, int C, in
 int mmr_head_grad_prep(const float* dlogits, int N, int C, int H, int W, void* out, int cpad,
                        float* dbias, int accumulate, mmr_stream_t stream);
 
+/* 1x1 classification head over a 64-channel bf16 NHWC feature map on the CUDA cores, in fp32 from the fp32
+ * master weights w[Cout][64] (HBM-bound; nothing padded to a tensor-core tile, no repacked weights): replaces the
+ * forward / data-gradient / weight-gradient of `ResNetUNet.conv_last = nn.Conv2d(64, n_class, 1)`
+ * (SU/UArchModel/resnet_unet.py:204, :298).  Cin must be 64, 1 <= Cout <= 16.
+ * fwd: logits fp32 NCHW [N][Cout][H][W] = bias + x . w^T.
+ * bwd: ONE pass over x and dlogits (fp32 NCHW) writes dx bf16 NHWC (times the ReLU mask x > 0 when relu_mask: dx is
+ * then the dz of the conv + bias + ReLU that produced x), dw[Cout][64] and dbias[Cout] of the head and
+ * dbias_producer[64] = column sums of the stored dx (may be NULL); (+)= when accumulate.  workspace: floats for the
+ * per-CTA partial sums, mmr_pointwise_head_bwd_workspace_bytes(Cout) bytes. */
+int mmr_pointwise_head_fwd(const void* x, const float* w, const float* bias, int N, int H, int W, int Cin,
+                           int Cout, float* logits, mmr_stream_t stream);
+int64_t mmr_pointwise_head_bwd_workspace_bytes(int Cout);
+int mmr_pointwise_head_bwd(const float* dlogits, const void* x, const float* w, int N, int H, int W, int Cin,
+                           int Cout, int relu_mask, void* dx, float* dw, float* dbias, float* dbias_producer,
+                           int accumulate, float* workspace, mmr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Sliding-window inference (monai.inferers.sliding_window_inference with mode="constant", called at
  * ED/Main_MMR_SegModel.py:1308-1317, followed by preds.argmax(1) at :1320).  Windows of one frame are

@@ -219,6 +219,9 @@ SIGNATURES = {
     "mmr_dice_ce_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(MmrLossParams), _vp, _f, _vp,
                              _vp, _vp]),
     "mmr_head_grad_prep": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
+    "mmr_pointwise_head_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_pointwise_head_bwd_workspace_bytes": (_i64, [_i]),
+    "mmr_pointwise_head_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "mmr_confusion_from_logits": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mmr_confusion_from_preds": (_i, [_vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp]),
     "mmr_onehot_to_labels": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

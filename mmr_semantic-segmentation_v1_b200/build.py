@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmrseg.so")
 SOURCES = ["common.cu", "conv_gemm.cu", "conv_halo.cu", "conv_wgrad.cu", "conv_wgrad_halo.cu", "elementwise.cu", "loss_metric.cu",
-           "optim.cu", "sliding_window.cu", "hausdorff.cu"]
+           "optim.cu", "sliding_window.cu", "hausdorff.cu", "pointwise_head.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

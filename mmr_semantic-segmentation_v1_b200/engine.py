@@ -33,6 +33,12 @@ class _Act:
         self.producer = None
 
 
+class _PointwisePlan:
+    """Stands where a conv plan would for the launches of csrc/pointwise_head.cu (no handle: CUDA-core kernels)."""
+    handle = None
+    flops = 0
+
+
 class _Arena:
     """Liveness-planned scratch for backward temporaries (g, dz, per-source data gradients)."""
 
@@ -426,7 +432,12 @@ class Engine:
         unit = {"kind": "head" if head else "conv", "op": op, "cout": cout, "cpad": cpad, "k": k, "s": s,
                 "pad": pad, "srcs": srcs, "in_hw": (Hin, Win)}
         sources = [(a.buf, up) for a, up in srcs]
-        halo = self.use_halo and convplan.halo_supported(sources, k, s, pad)
+        # 1x1 head over a 64-channel map at its own resolution (ResNetUNet.conv_last): the CUDA-core fp32 kernels of
+        # csrc/pointwise_head.cu (HBM-bound; one backward pass also applies the producer's ReLU mask)
+        pw = bool(head and k == 1 and len(srcs) == 1 and srcs[0][1] == 1 and cin == 64 and cout <= 16
+                  and op.get("up", 1) == 1 and not os.environ.get("MMR_NO_POINTWISE_HEAD"))
+        unit["pw"] = pw
+        halo = self.use_halo and not pw and convplan.halo_supported(sources, k, s, pad)
         unit["halo"] = halo
         res = self.acts[op["res"]] if (not head and op.get("res")) else None
         unit["res"] = res
@@ -443,13 +454,16 @@ class Engine:
                 unit["dcfg"] = dcfg
                 unit["wd_h"] = self._bf16(convplan.halo_packed_weights_numel(dcfg))
                 self._pack_job(w, unit["wd_h"], cout, cin, 1, dcfg)
-        else:
+        elif not pw:
             unit["wf"] = self._bf16(cpad, taps * cin, zero=True)
             unit["wd"] = self._bf16(cin, taps * cpad, zero=True) if self.training else None
             self._rec(self.repack_calls, "mmr_repack_weights", w, cout, cin, taps, unit["wf"], taps * cin,
                       unit["wd"], taps * cpad, cpad)
 
         def fprop(dst, **kw):
+            if pw:
+                self._rec(fc, "mmr_pointwise_head_fwd", srcs[0][0].buf, w, kw["bias"], n, Ho, Wo, cin, cout, dst)
+                return _PointwisePlan()
             if halo:
                 plan = convplan.build_fprop_halo(sources, w, dst if not head else None, cfg=hcfg,
                                                  packed=unit["wf_h"], out_f32=dst if head else None, **kw)
@@ -527,7 +541,8 @@ class Engine:
                              relu=op["relu"])
         plan.flops = 2 * n * Ho * Wo * cout * taps * cin
         self.conv_flops_fwd += plan.flops
-        unit["fplan"] = plan
+        if not pw:      # "fplan" marks the tensor-core launches (bench roofline, per-layer tables)
+            unit["fplan"] = plan
         unit["out"] = out
         out.producer = unit
         self.acts[op["out"]] = out
@@ -576,9 +591,19 @@ class Engine:
             t_g = t
             if u.get("res") is not None and u["res"].needs_grad and u["res"].producer is not None:
                 t_g = t_of[id(u["res"].producer)]
-            # the weight gradient runs on the side stream and is joined two units later: its dz operand
-            # (g itself when there is no BatchNorm) must not be recycled before that
-            arena.request(("g", id(u)), nbytes(oshape), t, t_g if u.get("bn") else max(t_g, t + 1))
+            if u.get("pw"):
+                # pointwise head: no bf16 copy of dlogits; when its source is a single-reader conv + bias + ReLU the
+                # backward kernel writes that producer's dz itself (ReLU mask applied), which therefore lives from here
+                L = self._pw_fuse_target(u)
+                if L is not None:
+                    L["dz_by_reader"] = t
+                    continue
+            elif u.get("dz_by_reader") is not None:
+                arena.request(("g", id(u)), nbytes(oshape), u["dz_by_reader"], max(t_g, t + 1))
+            else:
+                # the weight gradient runs on the side stream and is joined two units later: its dz operand
+                # (g itself when there is no BatchNorm) must not be recycled before that
+                arena.request(("g", id(u)), nbytes(oshape), t, t_g if u.get("bn") else max(t_g, t + 1))
             if u.get("bn"):
                 arena.request(("dz", id(u)), nbytes(oshape), t, t + 1)
             if kind == "stem":
@@ -611,6 +636,17 @@ class Engine:
                 self._bwd_t = t
                 self._bwd_unit(u, calls, view, int(acc), record_hooks=not acc)
         self.n_launch_bwd = len(self.bwd_calls[False])
+
+    def _pw_fuse_target(self, u):
+        """The conv + bias + ReLU unit (no BatchNorm, no residual) whose 64-channel output only the pointwise head
+        `u` reads: the head's backward kernel then writes that unit's dz and bias gradient.  None otherwise."""
+        src = u["srcs"][0][0]
+        L = src.producer
+        if (L is not None and L.get("kind") == "conv" and not L["op"].get("bn") and L["op"]["relu"]
+                and L.get("res") is None and self.n_readers.get(src.name, 0) == 1
+                and L["cout"] == src.shape[3] == L.get("cpad", L["cout"]) and src.needs_grad):
+            return L
+        return None
 
     def _contrib_array(self, act):
         arr = (MmrContrib * max(1, len(act.contribs)))()
@@ -656,6 +692,32 @@ class Engine:
         oshape = (n, ho, wo, cpad)
         Pn = n * ho * wo
         conv = u["op"]["conv"]
+        if kind == "head" and u.get("pw"):
+            # the loss leaves fp32 NCHW dlogits in u["dlogits"]: one pass gives the head's weight / bias gradients and
+            # the source's data gradient (csrc/pointwise_head.cu)
+            if "dlogits" not in u:
+                u["dlogits"] = self._f32(n, u["cout"], ho, wo, zero=True)
+            src = u["srcs"][0][0]
+            L = self._pw_fuse_target(u)
+            if "pw_ws" not in u:
+                u["pw_ws"] = self._f32(int(self.lib.mmr_pointwise_head_bwd_workspace_bytes(u["cout"])) // 4)
+            names = [conv + ".weight", conv + ".bias"]
+            if L is not None:
+                Lconv = L["op"]["conv"]
+                dx = view(("g", id(L)), L["out"].shape)
+                dbl = self.G[Lconv + ".bias"] if L["op"].get("bias") else None
+                if dbl is not None:
+                    names.append(Lconv + ".bias")
+            else:
+                dx, dbl = view(("dx", id(u), 0), src.shape), None
+                src.contribs.append((dx, 0))
+            self._rec(calls, "mmr_pointwise_head_bwd", u["dlogits"], src.buf, self.P[conv + ".weight"], n, ho, wo,
+                      src.shape[3], u["cout"], int(L is not None), dx, self.G[conv + ".weight"],
+                      self.G[conv + ".bias"], dbl, acc, u["pw_ws"])
+            if record_hooks:
+                self.conv_flops_bwd += 2 * (2 * Pn * u["cout"] * src.shape[3])
+                self.param_ready_hooks.append((len(calls), names))
+            return
         g = view(("g", id(u)), oshape)
         if kind == "head":
             # the loss leaves fp32 NCHW dlogits in u["dlogits"]; convert + bias gradient
@@ -705,6 +767,8 @@ class Engine:
                               u["coef"], u["scale"], u["shift"], Pn, Cc, dz)
                 else:
                     self._rec(calls, "mmr_bn_bwd_apply", g, u["z"], u["mean"], u["invstd"], u["coef"], Pn, Cc, dz)
+            elif u.get("dz_by_reader") is not None:
+                dz = g      # written, masked, by the pointwise head's backward pass (bias gradient included)
             else:
                 has_bias = u["op"].get("bias")
                 self._rec(calls, "mmr_grad_gather", arr, cnt, relu_act, n, ho, wo, Cc, g,

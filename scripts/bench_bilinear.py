@@ -13,6 +13,8 @@ from mmrseg_b200._lib import MmrContrib
 lib = _lib.lib()
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 shapes = [(16, 16, 512), (32, 32, 512), (64, 64, 256), (128, 128, 256), (256, 256, 128)]
+if len(sys.argv) > 2:      # one shape only (for an ncu capture)
+    shapes = [shapes[int(sys.argv[2])]]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 tot = [0.0, 0.0]

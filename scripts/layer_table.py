@@ -1,6 +1,8 @@
 """Per-layer table of the tcgen05 conv kernels at the bench configuration: CUDA-event time of every
 fprop / dgrad / wgrad launch (L2 flushed between launches), algorithmic TFLOP/s and fraction of
-the measured bf16 peak.  Writes profiles/layers_<tag>.csv."""
+the measured bf16 peak.  Writes gpurun_out/layers_<tag>.csv.
+
+    python scripts/layer_table.py [tag] [batch] [config]      config = c2 (default) | c3 | c4"""
 import ctypes as C
 import json
 import os
@@ -9,19 +11,18 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from mmrseg_b200.models import UnetPlusPlus
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-cfg = bench.resolve("c2", 1)
-n = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["batch"]
+cfg = bench.resolve(sys.argv[3] if len(sys.argv) > 3 else "c2", 1)
+n = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else cfg["batch"]
 reps = 3
 torch.manual_seed(6210)
-model = UnetPlusPlus("resnet18", classes=cfg["classes"]).cuda().train()
+model = bench.build_model(cfg, torch.device("cuda", 0)).train()
 x, y = bench.synthetic(cfg, n)
 x = x.cuda()
 eng = model._engine_for(x, training=True)
 eng.forward(x)
-eng.backward(torch.zeros_like(eng.acts["logits"].buf))
+eng.backward(torch.zeros_like(eng.acts["logits"].buf)) if not cfg["ds"] else None
 torch.cuda.synchronize()
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 stream = torch.cuda.current_stream()
@@ -68,5 +69,5 @@ for name, kind, gf, ms, tf, fr in rows:
 for kind, (gf, ms) in tot.items():
     print("%s: %.1f GFLOP in %.3f ms = %.1f TFLOP/s (%.3f of %.1f)" % (kind, gf, ms, gf / ms, gf / ms / pk, pk))
 print("all: %.3f ms" % sum(v[1] for v in tot.values()))
-for r in sorted(rows, key=lambda r: -r[3])[:25]:
+for r in sorted(rows, key=lambda r: -r[3])[:40]:
     print("%-45s %-6s %8.1f GF %8.3f ms %7.1f TF/s %.3f" % r)

@@ -86,7 +86,8 @@ def check_forward(eng, P, x_in, training=True):
             continue
         op = u["op"]
         name = op["out"]
-        W = _r(P[op["conv"] + ".weight"])
+        # the pointwise head (csrc/pointwise_head.cu) multiplies in fp32 by the fp32 master weights
+        W = P[op["conv"] + ".weight"] if u.get("pw") else _r(P[op["conv"] + ".weight"])
         if kind == "stem":
             x, stride, pad = _r(x_in.detach().float().cpu()), 2, 3
         else:
@@ -162,6 +163,28 @@ def check_backward(eng, P, G, x_in):
         out = u["out"]
         n, ho, wo = out.shape[0], out.shape[1], out.shape[2]
         cout, cpad = u["cout"], u.get("cpad", u["cout"])
+        if kind == "head" and u.get("pw"):
+            # one fp32 pass over the fp32 dlogits and the stored bf16 activation: head weight / bias gradients, the
+            # source's data gradient (times its ReLU mask when the head is its only reader: that unit's dz) and the
+            # column sums of the stored gradient (that unit's bias gradient)
+            dl = u["dlogits"].detach().float().cpu()
+            src = u["srcs"][0][0]
+            L = eng._pw_fuse_target(u)
+            x = _nchw(src.buf).requires_grad_(True)
+            W = P[conv + ".weight"].clone().requires_grad_(True)
+            F.conv2d(x, W, None).backward(dl)
+            rows.append((name, "bias grad", "f32", _rel(G[conv + ".bias"], dl.sum((0, 2, 3)))))
+            rows.append((name, "weight grad", "f32", _rel(G[conv + ".weight"], W.grad)))
+            if L is not None:
+                got = _nchw(eng.arena_view(("g", id(L)), src.shape))
+                rows.append((name, "data grad x ReLU mask -> dz of %s" % src.name, "bf16",
+                             _rel(got, _r(x.grad * (x.detach() > 0).float()))))
+                if L["op"].get("bias"):
+                    rows.append((L["op"]["out"], "bias grad", "f32", _rel(G[L["op"]["conv"] + ".bias"], got.sum((0, 2, 3)))))
+            else:
+                rows.append((name, "data grad -> %s" % src.name, "bf16",
+                             _rel(_nchw(eng.arena_view(("dx", id(u), 0), src.shape)), _r(x.grad))))
+            continue
         g_eng = _nchw(eng.arena_view(("g", id(u)), (n, ho, wo, cpad)))[:, :cout]
         if kind == "head":
             dl = u["dlogits"].detach().float().cpu()
@@ -171,6 +194,8 @@ def check_backward(eng, P, G, x_in):
             rows.append((name, "g (bf16 dlogits)", "bf16", _rel(g_eng, _r(dl))))
             rows.append((name, "bias grad", "f32", _rel(G[conv + ".bias"], dl.sum((0, 2, 3)))))
             dz = g_eng
+        elif u.get("dz_by_reader") is not None:
+            dz = g_eng      # written (masked, bias gradient included) by the pointwise head's backward: checked there
         else:
             total = _gathered(out)
             mask = (_nchw(out.buf) > 0).float() if op["relu"] else 1.0
