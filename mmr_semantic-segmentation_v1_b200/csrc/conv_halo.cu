@@ -1043,14 +1043,15 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       float* aff = nullptr;
       if (p.n_ntiles == 1 && p.gpn == 1) {     // the whole channel set is one store group: stage scale / shift once
         aff = reinterpret_cast<float*>(bars + 32);
-        for (int c = m; c < p.sg; c += 128) {
+        for (int c = et; c < p.sg; c += en) {
           const int cc = min(c, p.cout_total - 1);
           aff[c] = p.scale ? __ldg(p.scale + cc) : 1.f;
           aff[p.sg + c] = p.bias ? __ldg(p.bias + cc) : 0.f;
         }
-        epi_bar();
+        epi_bar(en);
       }
-      if (p.sg == 64) epi_fast<64, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, aff);
+      if (p.sg == 64 && p.epi_warps == 8) epi_fast<64, 0, false, 2>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, aff, hf);
+      if (p.sg == 64 && p.epi_warps == 4) epi_fast<64, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, aff);
       if (p.sg == 32) epi_fast<32, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, aff);
       if (p.sg == 16) epi_fast<16, 0, false>(p, tmem_base, out_base, tmem_full, tmem_empty, q, lane, aff);
     } else {
@@ -1288,7 +1289,9 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
 }
 
 // The statistics / BatchNorm-backward families run with eight epilogue warps (384 threads, 168 registers each).
-constexpr int halo_threads(int ek) { return (ek == kEpiStats || ek == kEpiBnBwd) ? kHaloThreads + 128 : kHaloThreads; }
+constexpr int halo_threads(int ek) {
+  return (ek == kEpiStats || ek == kEpiBnBwd || ek == kEpiAffine) ? kHaloThreads + 128 : kHaloThreads;
+}
 
 template <int EK>
 __global__ void __launch_bounds__(halo_threads(EK), 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
@@ -1676,7 +1679,10 @@ extern "C" int mmr_halo_conv_plan_create(const MmrHaloConvDesc* d, void** out_pl
         return fail("pooled store groups need the plain bf16 epilogue (default store mode of the group width)");
       }
     // eight epilogue warps where the epilogue carries per-channel sums of a 64-channel store group
-    p.epi_warps = ((pl->epi_kind == kEpiStats || pl->epi_kind == kEpiBnBwd) && p.sg == 64) ? 8 : 4;
+    // (and the scale / bias / ReLU epilogue of eval-mode and biased convs: MMR_AFFINE_EPI_WARPS=4 is the A/B switch)
+    static const bool affine8 = !(getenv("MMR_AFFINE_EPI_WARPS") && atoi(getenv("MMR_AFFINE_EPI_WARPS")) == 4);
+    p.epi_warps = ((pl->epi_kind == kEpiStats || pl->epi_kind == kEpiBnBwd || (pl->epi_kind == kEpiAffine && affine8)) &&
+                   p.sg == 64) ? 8 : 4;
   }
   {
     const void* fns[kEpiKinds] = {(const void*)conv_halo_kernel<kEpiOther>, (const void*)conv_halo_kernel<kEpiStats>,
@@ -1699,7 +1705,7 @@ extern "C" int mmr_halo_conv_plan_run(void* plan, mmr_stream_t stream) {
     case kEpiStats: mmr_launch((conv_halo_kernel<kEpiStats>), pl->grid, halo_threads(kEpiStats), pl->smem_bytes, as_stream(stream), pl->prm); break;
     case kEpiPlain: mmr_launch((conv_halo_kernel<kEpiPlain>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
     case kEpiBnBwd: mmr_launch((conv_halo_kernel<kEpiBnBwd>), pl->grid, halo_threads(kEpiBnBwd), pl->smem_bytes, as_stream(stream), pl->prm); break;
-    case kEpiAffine: mmr_launch((conv_halo_kernel<kEpiAffine>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
+    case kEpiAffine: mmr_launch((conv_halo_kernel<kEpiAffine>), pl->grid, halo_threads(kEpiAffine), pl->smem_bytes, as_stream(stream), pl->prm); break;
     case kEpiHead: mmr_launch((conv_halo_kernel<kEpiHead>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
     default: mmr_launch((conv_halo_kernel<kEpiOther>), pl->grid, kHaloThreads, pl->smem_bytes, as_stream(stream), pl->prm); break;
   }

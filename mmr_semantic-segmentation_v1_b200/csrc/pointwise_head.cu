@@ -15,10 +15,11 @@
 //             replacing head_grad_prep + a tensor-core dgrad + wgrad (each padded 10 -> 16 channels) + the producer's
 //             grad_gather / bias_grad_finalize: 5.4 GB of traffic -> 2.5 GB at 32 x 512 x 512.
 //
-// Backward kernel: persistent CTAs (two per SM) walk 256-pixel tiles.  Phase A, one thread per pixel: the pixel's
-// 128-byte activation row and its dl values go to shared memory (16-byte chunks XOR-swizzled by the pixel
-// index, so that rows written by a quarter warp and chunk columns read in phase B are both conflict-free), dx is
-// computed, masked, stored to HBM and kept in shared memory.  Phase B, the same threads regrouped as
+// Backward kernel: persistent CTAs (two per SM) walk 256-pixel tiles; a tile's activation rows and dl values arrive
+// by cp.async into double-buffered shared memory while the previous tile is processed (16-byte chunks
+// XOR-swizzled by the pixel index, so that rows accessed by a quarter warp and chunk columns read in phase B are
+// both conflict-free).  Phase A, one thread per pixel: dx is computed, masked and left in shared memory, from
+// where whole rows are copied out per warp instruction.  Phase B, the same threads regrouped as
 // (k half, 8-channel chunk, pixel slice): each accumulates a CO/2 x 8 block of dW over its sixteenth of the
 // tile in registers for the whole launch, plus db and dbL.  At the end a CTA folds its sixteen slices in
 // shared memory and writes ONE partial vector; the finalize kernel adds the partials in a fixed order
@@ -79,7 +80,8 @@ pointwise_head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int cout, int64_t
         for (int j = 0; j < 8; ++j) acc[k] += v[j] * c_pw_w[k * kPwCin + c8 * 8 + j];
       }
     }
-    const int64_t n = p / hw, q = p - n * hw;
+    const int64_t n = npix <= 0x7fffffff ? (int64_t)((uint32_t)p / (uint32_t)hw) : p / hw;
+    const int64_t q = p - n * hw;
     float* o = out + n * cout * hw + q;
 #pragma unroll
     for (int k = 0; k < CO; ++k)
@@ -93,10 +95,15 @@ __host__ __device__ constexpr int pw_partial_floats() { return CO * kPwCin + CO 
 
 template <int CO>
 struct PwSmem {
-  uint4 xs[kPwTile][8];       // activation rows, chunk j of pixel p at [p][j ^ (p & 7)]
+  uint4 xs[2][kPwTile][8];    // activation rows (double-buffered), chunk j of pixel p at [p][j ^ (p & 7)]
   uint4 ds[kPwTile][8];       // masked dx rows, same layout
   float dls[CO][kPwTile];     // dl[k][p]
 };
+
+__device__ __forceinline__ void pw_cp_async16(void* dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;      // 0 source bytes: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
 
 template <int CO>
 __global__ void __launch_bounds__(kPwThreads, 2)
@@ -110,6 +117,9 @@ pointwise_head_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // phase B role: k half, channel chunk, pixel slice (16 slices: pixel p of a tile belongs to slice p % 16)
   const int cc = lane & 7, kh = warp & 1, ps = (warp >> 1) * 4 + (lane >> 3);
+  // tile movers: thread t carries 16-byte chunk t % 8 of pixels t / 8 + 32 i: a warp instruction covers four whole
+  // 128-byte rows (one thread per pixel would touch 32 lines per instruction: 8x the L1 tag cycles)
+  const int mv_chunk = tid & 7, mv_row = tid >> 3;
   float accW[KH][8], accb[KH], accL[8];
 #pragma unroll
   for (int k = 0; k < KH; ++k) {
@@ -120,35 +130,55 @@ pointwise_head_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __r
 #pragma unroll
   for (int j = 0; j < 8; ++j) accL[j] = 0.f;
   const int64_t ntiles = (npix + kPwTile - 1) / kPwTile;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    __syncthreads();      // the previous tile's phase B is done with the shared tiles
-    // ---- phase A: one pixel per thread
+
+  // a tile's x rows come by cp.async into the other buffer; its dl values (this thread's pixel) are prefetched
+  // into registers one tile ahead (two CTAs of 2 x 32 KB + 32 KB + dl tile just fit an SM)
+  auto issue_tile = [&](int64_t tile, int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 32 + mv_row;
+      const int64_t p = tile * kPwTile + r;
+      const bool valid = p < npix;
+      pw_cp_async16(&sm.xs[buf][r][mv_chunk ^ (r & 7)], x + (valid ? p : 0) * kPwCin + mv_chunk * 8, valid);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float dln[CO];
+  auto fetch_dl = [&](int64_t tile) {
     const int64_t p = tile * kPwTile + tid;
     const bool valid = p < npix;
-    uint4 raw[8];
+    const int64_t pp = valid ? p : 0;
+    // 32-bit division where the pixel index allows it (a 64-bit one costs ~100 instructions per tile)
+    const int64_t n = npix <= 0x7fffffff ? (int64_t)((uint32_t)pp / (uint32_t)hw) : pp / hw;
+    const int64_t q = pp - n * hw;
+    const float* d = dl + n * cout * hw + q;
+#pragma unroll
+    for (int k = 0; k < CO; ++k) dln[k] = (valid && k < cout) ? __ldg(d + (int64_t)k * hw) : 0.f;
+  };
+
+  int buf = 0;
+  if ((int64_t)blockIdx.x < ntiles) {
+    issue_tile(blockIdx.x, 0);
+    fetch_dl(blockIdx.x);
+  }
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();      // this tile has landed; the previous tile's phase B and copy-out are done
     float dlv[CO];
-    if (valid) {
-      const uint4* row = reinterpret_cast<const uint4*>(x + p * kPwCin);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) raw[j] = __ldg(row + j);
-      const int64_t n = p / hw, q = p - n * hw;
-      const float* d = dl + n * cout * hw + q;
-#pragma unroll
-      for (int k = 0; k < CO; ++k) dlv[k] = k < cout ? __ldg(d + (int64_t)k * hw) : 0.f;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) raw[j] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int k = 0; k < CO; ++k) dlv[k] = 0.f;
+    for (int k = 0; k < CO; ++k) {
+      dlv[k] = dln[k];
+      sm.dls[k][tid] = dln[k];
     }
-#pragma unroll
-    for (int k = 0; k < CO; ++k) sm.dls[k][tid] = dlv[k];
-    uint4* orow = reinterpret_cast<uint4*>(dx + p * kPwCin);
+    if (tile + gridDim.x < ntiles) {
+      issue_tile(tile + gridDim.x, buf ^ 1);
+      fetch_dl(tile + gridDim.x);
+    }
+    // ---- phase A: one pixel per thread
 #pragma unroll
     for (int c8 = 0; c8 < 8; ++c8) {
-      sm.xs[tid][c8 ^ (tid & 7)] = raw[c8];
       float xv[8], a[8];
-      pw_unpack8(raw[c8], xv);
+      pw_unpack8(sm.xs[buf][tid][c8 ^ (tid & 7)], xv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] = 0.f;
 #pragma unroll
@@ -166,15 +196,21 @@ pointwise_head_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __r
       o.z = pack_bf16x2(a[4], a[5]);
       o.w = pack_bf16x2(a[6], a[7]);
       sm.ds[tid][c8 ^ (tid & 7)] = o;
-      if (valid) orow[c8] = o;
     }
     __syncthreads();
+    // ---- copy the dx tile out, whole rows per warp instruction
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 32 + mv_row;
+      const int64_t p = tile * kPwTile + r;
+      if (p < npix) *reinterpret_cast<uint4*>(dx + p * kPwCin + mv_chunk * 8) = sm.ds[r][mv_chunk ^ (r & 7)];
+    }
     // ---- phase B: dW / db / dbL over this thread's sixteenth of the tile
 #pragma unroll 4
     for (int it = 0; it < kPwTile / 16; ++it) {
       const int q = it * 16 + ps;
       float xv[8];
-      pw_unpack8(sm.xs[q][cc ^ (q & 7)], xv);
+      pw_unpack8(sm.xs[buf][q][cc ^ (q & 7)], xv);
 #pragma unroll
       for (int k = 0; k < KH; ++k) {
         const float d = sm.dls[kh * KH + k][q];
