@@ -1350,7 +1350,17 @@ upsample_bilinear2x_bwd_kernel(ContribList cl, int H, int W, int C, int rows, __
   const int d0 = max(0, 2 * y0 - 3), d1 = min(H2 - 1, 2 * (y1 - 1) + 4);
   __nv_bfloat16* dst = gin + (size_t)n * H * W * C + (size_t)j * 8;
   const size_t in_row = (size_t)W * C;
-  const __nv_bfloat16* g0 = cl.ptr[0] + (size_t)n * H2 * W2 * C + c;
+  // scalars, not an array: the six weights stay in registers (the array went to local memory: 6 LDL per row)
+  const float wx0 = wx[0], wx1 = wx[1], wx2 = wx[2], wx3 = wx[3], wx4 = wx[4], wx5 = wx[5];
+  const size_t out_row = (size_t)W2 * C;
+  // SINGLE: the support of a column is at most five consecutive taps of the six-tap window (an open interval
+  // shorter than 5): they start at tap 0 or tap 1
+  const int t0 = wx0 != 0.f ? 0 : 1;
+  const float tw[5] = {t0 ? wx1 : wx0, t0 ? wx2 : wx1, t0 ? wx3 : wx2, t0 ? wx4 : wx3, t0 ? wx5 : wx4};
+  int tap_off[5];      // element offset of each tap's (clamped) column inside a gradient row
+#pragma unroll
+  for (int k = 0; k < 5; ++k) tap_off[k] = min(max(fx + t0 + k, 0), W2 - 1) * C;
+  const __nv_bfloat16* grow = cl.ptr[0] + (size_t)n * H2 * out_row + c;      // row 0 of this image's gradient
   int cur = lerp_coord(d0, H, sy).i0;      // accA belongs to input row cur, accB to cur + 1
   float accA[8], accB[8];
 #pragma unroll
@@ -1369,16 +1379,37 @@ upsample_bilinear2x_bwd_kernel(ContribList cl, int H, int W, int C, int rows, __
     float h[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) h[k] = 0.f;
+    if (SINGLE) {
+      // all five loads of the row are issued before the first use (a branch per tap serialised them: one load in
+      // flight per thread, 2.8 TB/s); a tap outside the column's support reads a clamped column with weight 0
+      const __nv_bfloat16* rowp = grow + (size_t)d * out_row;
+      uint4 raw[5];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      if (wx[k] == 0.f) continue;      // taps outside the image or outside this column's support
-      float g[8];
-      if (SINGLE)
-        load8(g0 + ((size_t)d * W2 + (fx + k)) * C, g);
-      else
-        gather8(cl, n, d, fx + k, c, H2, W2, C, g);
+      for (int k = 0; k < 5; ++k) raw[k] = __ldg(reinterpret_cast<const uint4*>(rowp + tap_off[k]));
 #pragma unroll
-      for (int q = 0; q < 8; ++q) h[q] += wx[k] * g[q];
+      for (int k = 0; k < 5; ++k) {
+        const uint32_t w[4] = {raw[k].x, raw[k].y, raw[k].z, raw[k].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w[q]);
+          h[2 * q] += tw[k] * f.x;
+          h[2 * q + 1] += tw[k] * f.y;
+        }
+      }
+    } else {
+#define MMR_BILINEAR_TAP(K, WK)                                              \
+      if (WK != 0.f) { /* taps outside the image or outside this column's support carry weight 0 */ \
+        float g[8];                                                          \
+        gather8(cl, n, d, fx + (K), c, H2, W2, C, g);                        \
+        _Pragma("unroll") for (int q = 0; q < 8; ++q) h[q] += WK * g[q];     \
+      }
+      MMR_BILINEAR_TAP(0, wx0)
+      MMR_BILINEAR_TAP(1, wx1)
+      MMR_BILINEAR_TAP(2, wx2)
+      MMR_BILINEAR_TAP(3, wx3)
+      MMR_BILINEAR_TAP(4, wx4)
+      MMR_BILINEAR_TAP(5, wx5)
+#undef MMR_BILINEAR_TAP
     }
     const float wa = ly.i1 == ly.i0 ? ly.w0 + ly.w1 : ly.w0;      // last row: both weights land on it
     const float wb = ly.i1 == ly.i0 ? 0.f : ly.w1;
@@ -1406,6 +1437,30 @@ __global__ void upsample_nearest_f32_kernel(const float* __restrict__ in, int64_
     const int x = (int)(i % W), y = (int)((i / W) % H);
     const int64_t pl = i / ((int64_t)W * H);
     out[i] = __ldg(in + (pl * h + y / f) * w + x / f);
+  }
+}
+// Four output pixels per thread (one 16-byte store; f = 2: two source values, f % 4 == 0: one), 32-bit index
+// arithmetic: the per-element kernel above ran at 0.65 TB/s on the 67 MB logits of config 4's auxiliary heads.
+template <int F2>   // 1: f == 2, 0: f % 4 == 0
+__global__ void __launch_bounds__(kEwThreads)
+upsample_nearest_f32_vec4_kernel(const float* __restrict__ in, uint32_t rows, int h, int w, int f,
+                                 float* __restrict__ out) {
+  pdl_prologue();
+  const uint32_t H = (uint32_t)h * f, wv = (uint32_t)w * f / 4;      // float4 pieces per output row
+  const uint32_t total = rows * wv;
+  for (uint32_t i = blockIdx.x * kEwThreads + threadIdx.x; i < total; i += gridDim.x * kEwThreads) {
+    const uint32_t row = i / wv, xv = i - row * wv;
+    const uint32_t pl = row / H, y = row - pl * H;
+    const float* src = in + ((size_t)pl * h + y / (uint32_t)f) * w;
+    float4 o;
+    if (F2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src) + xv);
+      o = make_float4(v.x, v.x, v.y, v.y);
+    } else {
+      const float v = __ldg(src + (xv * 4) / (uint32_t)f);
+      o = make_float4(v, v, v, v);
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
   }
 }
 __global__ void sumpool_f32_kernel(const float* __restrict__ in, int64_t planes, int h, int w, int f,
@@ -1939,7 +1994,14 @@ extern "C" int mmr_upsample_bilinear2x_bwd(const MmrContrib* contribs, int ncont
 extern "C" int mmr_upsample_nearest_f32_nchw(const float* in, int64_t planes, int h, int w, int f, float* out,
                                              mmr_stream_t stream) {
   MMR_REQUIRE(f >= 1 && f <= 32, "factor must be 1..32");
-  mmr_launch((upsample_nearest_f32_kernel), ew_blocks(planes * h * w * f * f, 16), kEwThreads, 0, as_stream(stream), in, planes, h, w, f, out);
+  const int64_t rows = planes * h * f, vec = rows * ((int64_t)w * f / 4);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) & 7) | (reinterpret_cast<uintptr_t>(out) & 15)) == 0;
+  if (aligned && vec < (int64_t)1 << 31 && f == 2 && w % 2 == 0)
+    mmr_launch((upsample_nearest_f32_vec4_kernel<1>), ew_blocks(vec, 16), kEwThreads, 0, as_stream(stream), in, (uint32_t)rows, h, w, f, out);
+  else if (aligned && vec < (int64_t)1 << 31 && f % 4 == 0)
+    mmr_launch((upsample_nearest_f32_vec4_kernel<0>), ew_blocks(vec, 16), kEwThreads, 0, as_stream(stream), in, (uint32_t)rows, h, w, f, out);
+  else
+    mmr_launch((upsample_nearest_f32_kernel), ew_blocks(planes * h * w * f * f, 16), kEwThreads, 0, as_stream(stream), in, planes, h, w, f, out);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

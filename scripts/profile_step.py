@@ -23,7 +23,8 @@ x, y = x.cuda(), y.cuda()
 for i in range(steps):
     for p in model.parameters():
         p.grad = None
-    loss = crit(model(x), y)
+    out = model(x)
+    loss = sum(crit(o, y) for o in out) / len(out) if isinstance(out, list) else crit(out, y)
     loss.backward()
     opt.step()
 torch.cuda.synchronize()

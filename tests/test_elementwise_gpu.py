@@ -300,3 +300,22 @@ def test_head_grad_prep_layouts(n, classes, h, w):
     L.check(lib.mmr_head_grad_prep(_p(dl), n, classes, h, w, _p(g), 16, _p(db), 1, _s()))
     torch.cuda.synchronize()
     assert torch.allclose(db.double(), 2 * want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("planes,h,w,f", [(6, 16, 24, 2), (4, 8, 8, 4), (2, 4, 6, 8), (3, 5, 7, 2), (2, 6, 5, 3), (5, 7, 9, 1)])
+def test_nearest_f32_upsample_and_sum_pool(planes, h, w, f):
+    """Auxiliary (deep-supervision) logits: fp32 NCHW nearest upsampling by f (vector kernel for f = 2 / f % 4 == 0,
+    scalar one otherwise) is an exact copy; its adjoint sums f x f windows."""
+    L = _lib()
+    lib = L.lib()
+    gen = torch.Generator(device="cuda").manual_seed(planes * 100 + f)
+    x = torch.randn((1, planes, h, w), generator=gen, device="cuda")
+    up = torch.full((1, planes, h * f, w * f), 3.0, device="cuda")
+    L.check(lib.mmr_upsample_nearest_f32_nchw(_p(x), C.c_int64(planes), h, w, f, _p(up), _s()))
+    torch.cuda.synchronize()
+    assert torch.equal(up, F.interpolate(x, scale_factor=f, mode="nearest"))
+    g = torch.randn((1, planes, h * f, w * f), generator=gen, device="cuda")
+    pooled = torch.empty_like(x)
+    L.check(lib.mmr_sumpool_f32_nchw(_p(g), C.c_int64(planes), h, w, f, _p(pooled), _s()))
+    torch.cuda.synchronize()
+    assert torch.allclose(pooled, F.avg_pool2d(g, f) * float(f * f), rtol=1e-5, atol=1e-5)
