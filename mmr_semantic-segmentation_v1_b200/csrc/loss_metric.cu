@@ -103,8 +103,10 @@ __device__ __forceinline__ void dice_ce_finalize_body(double* __restrict__ ws, i
   }
 }
 
+// register cap: the combine step inlined at the end would otherwise set the allocation (98-120 registers for a
+// main loop that needs 40-80) and halve the warps that hide the loop's exp / divide chains
 template <int CP>
-__global__ void __launch_bounds__(kLossThreads)
+__global__ void __launch_bounds__(kLossThreads, CP <= 4 ? 4 : (CP <= 10 ? 3 : 1))
 dice_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int C,
                    int64_t HW, MmrLossParams prm, double* __restrict__ ws, int nblk, float* __restrict__ result,
                    int ticket_slot) {
@@ -116,36 +118,51 @@ dice_ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__
 #pragma unroll
   for (int c = 0; c < CP; ++c) accI[c] = accP[c] = accY[c] = 0.f;
   float ce = 0.f, cnt = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float v[CP];
-    float mx = -INFINITY;
+  // U pixels per iteration, all their loads issued before the first use (one pixel = C + 1 loads in flight per
+  // thread left the 10-class launches latency-bound); the pixels are still accumulated in index order
+  constexpr int U = CP <= 10 ? 2 : 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < HW; i0 += U * stride) {
+    float vv[U][CP];
+    int64_t tt[U];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      v[c] = c < C ? __ldg(lg + (size_t)c * HW + i) : -INFINITY;
-      mx = fmaxf(mx, v[c]);
-    }
-    float se = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool on = i < HW;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      v[c] = c < C ? expf(v[c] - mx) : 0.f;
-      se += v[c];
+      for (int c = 0; c < CP; ++c) vv[u][c] = (on && c < C) ? __ldg(lg + (size_t)c * HW + i) : -INFINITY;
+      tt[u] = on ? __ldg(lb + i) : 0;
     }
-    const float inv = 1.f / se;
-    const int64_t t = __ldg(lb + i);
-    float pt = 0.f;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      const float p = v[c] * inv;
-      const float y = ((int64_t)c == t ? 1.f : 0.f) + prm.onehot_eps;
-      accI[c] += p * y;
-      accP[c] += p;
-      accY[c] += y;
-      if ((int64_t)c == t) pt = p;
-    }
-    if (t != prm.ce_ignore_index && t >= 0 && t < C) {
-      ce += -logf(fmaxf(pt, 1e-38f));
-      cnt += 1.f;
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= HW) break;
+      float (&v)[CP] = vv[u];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) mx = fmaxf(mx, v[c]);
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        v[c] = c < C ? expf(v[c] - mx) : 0.f;
+        se += v[c];
+      }
+      const float inv = 1.f / se;
+      const int64_t t = tt[u];
+      const int ti = (t >= 0 && t < C) ? (int)t : -1;
+      float pt = 0.f;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        const float p = v[c] * inv;
+        const float y = (c == ti ? 1.f : 0.f) + prm.onehot_eps;
+        accI[c] += p * y;
+        accP[c] += p;
+        accY[c] += y;
+        if (c == ti) pt = p;
+      }
+      if (t != prm.ce_ignore_index && ti >= 0) {
+        ce += -logf(fmaxf(pt, 1e-38f));
+        cnt += 1.f;
+      }
     }
   }
   __shared__ float sh[kLossThreads / 32][3 * CP + 2];
@@ -217,39 +234,53 @@ dice_ce_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__
   const float* lg = logits + (size_t)n * C * HW;
   const int64_t* lb = labels + (size_t)n * HW;
   float* dl = dlogits + (size_t)n * C * HW;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float p[CP];
-    float mx = -INFINITY;
+  constexpr int U = CP <= 10 ? 2 : 1;      // as in the forward: U pixels' loads in flight per thread
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < HW; i0 += U * stride) {
+    float pp[U][CP];
+    int64_t tt[U];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      p[c] = c < C ? __ldg(lg + (size_t)c * HW + i) : -INFINITY;
-      mx = fmaxf(mx, p[c]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      const bool on = i < HW;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) pp[u][c] = (on && c < C) ? __ldg(lg + (size_t)c * HW + i) : -INFINITY;
+      tt[u] = on ? __ldg(lb + i) : 0;
     }
-    float se = 0.f;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      p[c] = c < C ? expf(p[c] - mx) : 0.f;
-      se += p[c];
-    }
-    const float inv = 1.f / se;
-    const int64_t t = __ldg(lb + i);
-    float g[CP];
-    float dot = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= HW) break;
+      float (&p)[CP] = pp[u];
+      float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      p[c] *= inv;
-      const float y = ((int64_t)c == t ? 1.f : 0.f) + prm.onehot_eps;
-      g[c] = -coefA[c] * (2.f * y - coefD[c]);
-      dot += g[c] * p[c];
-    }
-    const bool ce_on = t != prm.ce_ignore_index && t >= 0 && t < C;
+      for (int c = 0; c < CP; ++c) mx = fmaxf(mx, p[c]);
+      float se = 0.f;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      if (c < C) {
-        float d = p[c] * (g[c] - dot);
-        if (ce_on) d += ce_w * (p[c] - ((int64_t)c == t ? 1.f : 0.f));
-        dl[(size_t)c * HW + i] = d * grad_scale;
+      for (int c = 0; c < CP; ++c) {
+        p[c] = c < C ? expf(p[c] - mx) : 0.f;
+        se += p[c];
+      }
+      const float inv = 1.f / se;
+      const int64_t t = tt[u];
+      const int ti = (t >= 0 && t < C) ? (int)t : -1;
+      float g[CP];
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        p[c] *= inv;
+        const float y = (c == ti ? 1.f : 0.f) + prm.onehot_eps;
+        g[c] = -coefA[c] * (2.f * y - coefD[c]);
+        dot += g[c] * p[c];
+      }
+      const bool ce_on = t != prm.ce_ignore_index && ti >= 0;
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        if (c < C) {
+          float d = p[c] * (g[c] - dot);
+          if (ce_on) d += ce_w * (p[c] - (c == ti ? 1.f : 0.f));
+          dl[(size_t)c * HW + i] = d * grad_scale;
+        }
       }
     }
   }
@@ -360,6 +391,7 @@ using namespace mmr;
     if ((C) <= 2) { constexpr int CP = 2; CALL; }              \
     else if ((C) <= 4) { constexpr int CP = 4; CALL; }         \
     else if ((C) <= 8) { constexpr int CP = 8; CALL; }         \
+    else if ((C) <= 10) { constexpr int CP = 10; CALL; }       \
     else if ((C) <= 16) { constexpr int CP = 16; CALL; }       \
     else { constexpr int CP = 32; CALL; }                      \
   } while (0)

@@ -1,5 +1,7 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: the launches of ONE train step
-(between two weight-packing launches) aggregated by kernel.  usage: python scripts/launch_summary.py file.csv"""
+(between two weight-packing launches) aggregated by kernel.
+usage: python scripts/launch_summary.py file.csv [k]      k: which step of the file (default 0; the first one of a
+process also holds the one-time fills of freshly allocated buffers)"""
 import collections
 import csv
 import sys
@@ -12,7 +14,9 @@ for x in csv.DictReader(lines):
     seq.append((x["Kernel Name"].split("(")[0].replace("void ", ""), v, x["Grid Size"]))
 marks = [i for i, s in enumerate(seq) if "pack_weights_halo_batch" in s[0]]
 print("launches in file: %d, step boundaries at %s" % (len(seq), marks))
-lo, hi = (marks[0], marks[1]) if len(marks) > 1 else (0, len(seq))
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+k = min(k, max(len(marks) - 2, 0))
+lo, hi = (marks[k], marks[k + 1]) if len(marks) > 1 else (0, len(seq))
 step = seq[lo:hi]
 agg = collections.defaultdict(lambda: [0.0, 0])
 for n, v, g in step:
