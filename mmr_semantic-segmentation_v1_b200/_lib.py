@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmmrseg.so")
+# MMR_LIB: A/B measurements against a variant build (mmrseg_b200.build.build_variant); same C-ABI, still no fallback
+LIB_PATH = os.environ.get("MMR_LIB") or os.path.join(HERE, "libmmrseg.so")
 
 
 class MmrError(RuntimeError):

@@ -70,5 +70,26 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, extra_flags):
+    """A/B builds: libmmrseg_<name>.so with extra nvcc flags (e.g. -DMMR_PDL_LATE=0), loaded through MMR_LIB."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out_dir = os.path.join(HERE, "build", name)
+    os.makedirs(out_dir, exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        procs.append(subprocess.Popen([nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]))
+        objs.append(obj)
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("variant build failed")
+    lib = os.path.join(HERE, "libmmrseg_%s.so" % name)
+    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ["-cudart", "static"])
+    return lib
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

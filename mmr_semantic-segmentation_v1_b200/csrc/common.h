@@ -58,6 +58,30 @@ __device__ __forceinline__ void pdl_prologue() {
   pdl_trigger();
 #endif
 }
+// Late trigger: called by a CTA once its main loop is over (the MMA issuer after its last tcgen05.mma, a
+// streaming kernel after its grid-stride loop).  When every CTA of the grid has got there the next kernel of
+// the stream is launched: its block scheduling, barrier / TMEM set-up (everything it does before its own
+// griddepcontrol.wait) overlap this grid's epilogues and block reductions.  The dependent still blocks in
+// griddepcontrol.wait until this grid has completed, so the placement is a scheduling hint only.
+#ifndef MMR_PDL_LATE
+#define MMR_PDL_LATE 0
+#endif
+__device__ __forceinline__ void pdl_done() {
+#if MMR_PDL_LATE
+  pdl_trigger();
+#endif
+}
+// Conv kernels: set-up that touches no global memory (mbarrier init, TMEM allocation) runs BEFORE the wait.
+__device__ __forceinline__ void pdl_prologue_conv() {
+#if !MMR_PDL_LATE
+  pdl_prologue();
+#endif
+}
+__device__ __forceinline__ void pdl_setup_done() {
+#if MMR_PDL_LATE
+  pdl_wait();
+#endif
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t mmr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {

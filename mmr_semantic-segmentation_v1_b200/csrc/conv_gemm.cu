@@ -119,7 +119,7 @@ __device__ __forceinline__ void store_row16(const ConvParams& p, const MmrOutSeg
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
-  pdl_prologue();
+  pdl_prologue_conv();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: swizzle-128B atoms and the UMMA descriptors assume it.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -157,6 +157,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_setup_done();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -223,6 +224,7 @@ conv_gemm_tc_kernel(const __grid_constant__ ConvParams p) {
           mbar_arrive(&tmem_full[acc]);
       }
     }
+    pdl_done();
   } else if (warp >= 4) {
     // -------------------------------------------------------------- epilogue
     const int q = warp - 4;

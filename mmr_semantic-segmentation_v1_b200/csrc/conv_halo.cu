@@ -868,7 +868,7 @@ enum { kEpiOther = 0, kEpiStats = 1, kEpiPlain = 2, kEpiBnBwd = 3, kEpiAffine = 
 template <int EK>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   if (threadIdx.x == 0) MMR_TRACE(0);
-  pdl_prologue();
+  pdl_prologue_conv();   // late-trigger builds wait after the set-up below (pdl_setup_done)
   if (threadIdx.x == 0) MMR_TRACE(1);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* halo_base = smem;
@@ -912,6 +912,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  pdl_setup_done();      // nothing above reads or writes global memory
   if (threadIdx.x == 0) MMR_TRACE(2);
 
   if ((warp == 0 || warp == 2) && p.cpl) {
@@ -1004,6 +1005,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
 #undef MMR_MMA_CASES_TX
 #undef MMR_MMA_CASE
     if (lane == 0) MMR_TRACE(4);
+    pdl_done();          // every MMA of this CTA is issued: the next kernel's launch overlaps the last epilogue
   } else if (warp >= 4 && warp < 4 + p.epi_warps) {
     // ---------------------------------------------------------------- epilogue
     const int q = (warp - 4) & 3;   // TMEM lane quarter (a warp may only read the lanes 32 (warp % 4) ...)

@@ -65,7 +65,7 @@ __device__ __forceinline__ WgStep wg_decode(const WgParams& p, int it) {
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
-  pdl_prologue();
+  pdl_prologue_conv();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -102,6 +102,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_setup_done();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -164,6 +165,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
       else
         mbar_arrive(tmem_full);
     }
+    pdl_done();
   } else if (warp >= 4) {
     // -------------------------------------------------------------- epilogue
     const int q = warp - 4;

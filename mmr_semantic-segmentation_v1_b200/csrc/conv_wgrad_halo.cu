@@ -89,7 +89,7 @@ __device__ __forceinline__ void wh_view(int cb, int a, int pitch, int& voff_px, 
 
 __global__ void __launch_bounds__(kWhThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
-  pdl_prologue();
+  pdl_prologue_conv();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
   uint64_t* full = bars;
@@ -122,6 +122,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  pdl_setup_done();
   const WhChunk ch = p.chunk[c];
 
   if (warp == 0) {
@@ -210,6 +211,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
         mbar_arrive(tmem_full);
     }
     __syncwarp();
+    pdl_done();
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: fp32 partials
     const int q = warp - 4;
@@ -261,7 +263,7 @@ template <int TX, int BN>
 __global__ void __launch_bounds__(kWhThreads, 1)
 conv_wgrad_kx_kernel(const __grid_constant__ WhParams p) {
   constexpr uint32_t PX = 8 * TX, PZ = 8 * TX + 2, XRB = 128, ZRB = BN * 2, NN = 3 * BN;
-  pdl_prologue();
+  pdl_prologue_conv();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
   uint64_t* full = bars;
@@ -294,6 +296,7 @@ conv_wgrad_kx_kernel(const __grid_constant__ WhParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  pdl_setup_done();
   const WhChunk ch = p.chunk[c];
 
   if (warp == 0) {
@@ -380,6 +383,7 @@ conv_wgrad_kx_kernel(const __grid_constant__ WhParams p) {
         mbar_arrive(tmem_full);
     }
     __syncwarp();
+    pdl_done();
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: fp32 partials [192][NN]
     const int q = warp - 4;
@@ -439,7 +443,7 @@ conv_wgrad_thin_kernel(const __grid_constant__ WhParams p) {
   constexpr uint32_t XPR = PX * CX, ZPR = PZ * CZ;            // chunks per tile row
   constexpr uint32_t XTOT = 18 * XPR, ZTOT = 16 * ZPR;        // chunks per tile
   constexpr uint32_t LIVE = 3 * CB;                           // accumulator rows that belong to a filter row
-  pdl_prologue();
+  pdl_prologue_conv();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
   uint64_t* full = bars;
@@ -472,6 +476,7 @@ conv_wgrad_thin_kernel(const __grid_constant__ WhParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  pdl_setup_done();
   const WhChunk ch = p.chunk[c];
 
   if (warp == 1) {
@@ -518,6 +523,7 @@ conv_wgrad_thin_kernel(const __grid_constant__ WhParams p) {
         mbar_arrive(tmem_full);
     }
     __syncwarp();
+    pdl_done();
   } else if (warp >= 2) {
     // ---------------------------------------------------------------- gather: warps 2 .. 7
     const int pw = warp - 2;

@@ -8,6 +8,7 @@
 namespace mmr {
 
 constexpr int kEwThreads = 256;
+constexpr int kPdlTailIters = 3;  // streaming kernels trigger the next launch this many grid-stride iterations before their end
 constexpr int kMaxContrib = 8;
 
 struct ContribList {
@@ -539,6 +540,7 @@ reduce_rows_kernel(const __nv_bfloat16* __restrict__ z, uint32_t P, int C, doubl
       since_flush = 0;
     }
   }
+  pdl_done();   // the block reduction and the ticket finalisation overlap the next kernel's launch
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sd1[j * kEwThreads + threadIdx.x] += (double)f1[j];
@@ -758,7 +760,9 @@ bn_apply16_kernel(const __nv_bfloat16* __restrict__ z, int64_t total, int C, con
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t gi = (uint32_t)(i % groups);
   const uint32_t gstep = (uint32_t)(stride % groups);
+  const int64_t i_tail = total - kPdlTailIters * stride;
   for (; i < total; i += stride) {
+    if (i >= i_tail) pdl_done();   // last iterations: the next kernel's launch latency hides behind them
     const Words8 zv = ld256(z + i * 16);
     Words8 rv;
     if (RES) rv = ld256(residual + i * 16);
@@ -933,7 +937,9 @@ bn_bwd_apply16_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* 
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t gi = (uint32_t)(i % groups);
   const uint32_t gstep = (uint32_t)(stride % groups);
+  const int64_t i_tail = total - kPdlTailIters * stride;
   for (; i < total; i += stride) {
+    if (i >= i_tail) pdl_done();
     const Words8 gv = ld256(g + i * 16), zv = ld256(z + i * 16);
     const float* k = sc + gi * S;
     Words8 o;
