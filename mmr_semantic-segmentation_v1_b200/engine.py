@@ -563,6 +563,9 @@ class Engine:
         # channel counts of the units whose reduction rides on the consumer's data gradient (MMR_FUSED_BWD_CH: A/B)
         self.fuse_bwd_channels = tuple(int(v) for v in os.environ.get("MMR_FUSED_BWD_CH", "64").split(",") if v)
         self.wgrad_late = os.environ.get("MMR_WGRAD_LATE", "0") == "1"
+        # the main stream waits for the weight gradient of unit t when it reaches unit t + K (and recycles that
+        # unit's dz only then): a deeper K lets the side stream fall further behind instead of stalling the chain
+        K = self.wgrad_join = max(2, int(os.environ.get("MMR_WGRAD_JOIN", "2")))
         self.pool_dgrad = os.environ.get("MMR_POOL_DGRAD", "1") == "1"   # A/B switch
         self.fused_dgrad_handles = set()   # data-gradient plans that also take a BatchNorm-backward reduction
         order = list(reversed(self.units))
@@ -599,13 +602,13 @@ class Engine:
                     L["dz_by_reader"] = t
                     continue
             elif u.get("dz_by_reader") is not None:
-                arena.request(("g", id(u)), nbytes(oshape), u["dz_by_reader"], max(t_g, t + 1))
+                arena.request(("g", id(u)), nbytes(oshape), u["dz_by_reader"], max(t_g, t + K - 1))
             else:
-                # the weight gradient runs on the side stream and is joined two units later: its dz operand
+                # the weight gradient runs on the side stream and is joined K units later: its dz operand
                 # (g itself when there is no BatchNorm) must not be recycled before that
-                arena.request(("g", id(u)), nbytes(oshape), t, t_g if u.get("bn") else max(t_g, t + 1))
+                arena.request(("g", id(u)), nbytes(oshape), t, t_g if u.get("bn") else max(t_g, t + K - 1))
             if u.get("bn"):
-                arena.request(("dz", id(u)), nbytes(oshape), t, t + 1)
+                arena.request(("dz", id(u)), nbytes(oshape), t, t + K - 1)
             if kind == "stem":
                 continue
             Hin, Win = u["in_hw"]
@@ -632,7 +635,7 @@ class Engine:
                 self.acts[name].contribs.append((seed, 0))
             calls = self.bwd_calls[acc]
             for t, u in enumerate(order):
-                calls.append((Engine._mark, ("join", t - 2)))
+                calls.append((Engine._mark, ("join", t - self.wgrad_join)))
                 self._bwd_t = t
                 self._bwd_unit(u, calls, view, int(acc), record_hooks=not acc)
         self.n_launch_bwd = len(self.bwd_calls[False])
