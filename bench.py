@@ -454,7 +454,9 @@ def measure(cfg, args, world, rank, local, dev, full=True):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
         if os.path.exists(tpath) and cfg["name"] == "c2":
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            # DRAM bytes of every conv kernel of one step (ncu) over this line's own launch count, like `achieved`
+            traffic = (tj["dram_read_bytes_per_step"] + tj["dram_write_bytes_per_step"]) / max(roof["launches_per_step"], 1)
         roof["traffic"] = traffic
         line["roofline"] = roof
         line["gpu_launches"] = per_step * steps
