@@ -221,11 +221,11 @@ def kernels_per_call(lib, fn):
     return 2 if any(fn is f for f in two) else 1
 
 
-def conv_kernel_times(eng, n_iter=3):
+def conv_kernel_times(eng, n_iter=8):
     """CUDA-event time of every tcgen05 conv launch of one step (fprop, dgrad and -- training -- wgrad: the
     halo kernels for the 3x3 stride-1 layers and the stem, the first-generation kernels for the strided / 1x1
-    ones), on the launching stream, replaying the step's launch lists serially.  Returns {plan handle: ms}
-    averaged over n_iter - 1 passes."""
+    ones), on the launching stream, replaying the step's launch lists serially.  Returns {plan handle: ms}: the
+    median over n_iter - 1 passes (the SM clock moves under the power cap from pass to pass)."""
     import ctypes as C
     lib = eng.lib
     stream = torch.cuda.current_stream()
@@ -250,8 +250,8 @@ def conv_kernel_times(eng, n_iter=3):
         torch.cuda.synchronize()
         if it > 0:
             for h, e0, e1 in evs:
-                acc[h] = acc.get(h, 0.0) + e0.elapsed_time(e1) / (n_iter - 1)
-    return acc
+                acc.setdefault(h, []).append(e0.elapsed_time(e1))
+    return {h: sorted(v)[len(v) // 2] for h, v in acc.items()}
 
 
 def conv_roofline(eng, pk):

@@ -46,6 +46,9 @@ struct HaloChunk {
 // MMR_HALO_DBG bit 16: per-CTA timestamps of the last conv_halo launch (diagnostic; scripts/halo_trace.py):
 // [0] entry, [1] after griddepcontrol.wait, [2] after setup, [3] MMA warp: first operands landed,
 // [4] MMA warp: last commit issued, [5] epilogue warp 0: last item stored, [6] epilogue: finalisation done, [7] exit
+#ifndef MMR_PREFETCH_DESC
+#define MMR_PREFETCH_DESC 1
+#endif
 constexpr int kTraceSlots = 8;
 __device__ unsigned long long g_halo_trace[256 * kTraceSlots];
 #define MMR_TRACE(slot)                                                                              \
@@ -868,6 +871,19 @@ enum { kEpiOther = 0, kEpiStats = 1, kEpiPlain = 2, kEpiBnBwd = 3, kEpiAffine = 
 template <int EK>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   if (threadIdx.x == 0) MMR_TRACE(0);
+#if MMR_PREFETCH_DESC
+  // the tensor maps live in global memory (plan blob, written at build time): fetch the ones the first loads use
+  // while the barriers / TMEM are being set up -- cold, a descriptor costs an HBM round trip in front of its first load
+  if (!p.cpl && threadIdx.x >= 96 && threadIdx.x <= 96 + (unsigned)min(p.nchunks, 31)) {
+    const int i = (int)threadIdx.x - 96;    // lanes of warp 3: one source chunk each, the last one the weights
+    if (i == min(p.nchunks, 31)) {
+      tma_prefetch_desc(&p.maps[p.wmap]);
+    } else {
+      tma_prefetch_desc(&p.maps[p.chunk[i].map]);
+      if (p.chunk[i].up) tma_prefetch_desc(&p.maps[p.chunk[i].map_edge]);
+    }
+  }
+#endif
   pdl_prologue_conv();   // late-trigger builds wait after the set-up below (pdl_setup_done)
   if (threadIdx.x == 0) MMR_TRACE(1);
   extern __shared__ __align__(1024) uint8_t smem[];

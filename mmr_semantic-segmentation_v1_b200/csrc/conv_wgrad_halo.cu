@@ -24,6 +24,9 @@ constexpr int kWhMaxChunks = 16;
 constexpr int kWhMaxStages = 6;
 constexpr int kWhMaxAcc = 5;
 
+#ifndef MMR_PREFETCH_DESC
+#define MMR_PREFETCH_DESC 1
+#endif
 struct WhChunk {
   int32_t map, map_edge, c0, up, ci0;
   const uint8_t* base;  // mode 2 (cp.async gather): channel c0 of pixel (0, 0, 0) of the source
@@ -89,6 +92,13 @@ __device__ __forceinline__ void wh_view(int cb, int a, int pitch, int& voff_px, 
 
 __global__ void __launch_bounds__(kWhThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ WhParams p) {
+#if MMR_PREFETCH_DESC
+  if (threadIdx.x == 96) {
+    tma_prefetch_desc(&p.maps[p.dzmap + (p.dz_phased ? (int)(blockIdx.x % p.n_ntiles) : 0)]);
+    tma_prefetch_desc(&p.maps[p.chunk[blockIdx.x / p.n_ntiles].map]);
+    if (p.chunk[blockIdx.x / p.n_ntiles].up) tma_prefetch_desc(&p.maps[p.chunk[blockIdx.x / p.n_ntiles].map_edge]);
+  }
+#endif
   pdl_prologue_conv();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
@@ -263,6 +273,13 @@ template <int TX, int BN>
 __global__ void __launch_bounds__(kWhThreads, 1)
 conv_wgrad_kx_kernel(const __grid_constant__ WhParams p) {
   constexpr uint32_t PX = 8 * TX, PZ = 8 * TX + 2, XRB = 128, ZRB = BN * 2, NN = 3 * BN;
+#if MMR_PREFETCH_DESC
+  if (threadIdx.x == 96) {
+    tma_prefetch_desc(&p.maps[p.dzmap + (p.dz_phased ? (int)(blockIdx.x % p.n_ntiles) : 0)]);
+    tma_prefetch_desc(&p.maps[p.chunk[blockIdx.x / p.n_ntiles].map]);
+    if (p.chunk[blockIdx.x / p.n_ntiles].up) tma_prefetch_desc(&p.maps[p.chunk[blockIdx.x / p.n_ntiles].map_edge]);
+  }
+#endif
   pdl_prologue_conv();
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);

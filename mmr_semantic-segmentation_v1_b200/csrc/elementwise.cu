@@ -43,7 +43,10 @@ struct alignas(32) Words8 {
 };
 __device__ __forceinline__ Words8 ld256(const __nv_bfloat16* p) {
   Words8 r;
-  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef MMR_EW_LD_HINT
+#define MMR_EW_LD_HINT ""
+#endif
+  asm volatile("ld.global.L1::no_allocate" MMR_EW_LD_HINT ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
                  "=r"(r.v[7])
                : "l"(p));

@@ -1,0 +1,12 @@
+# A/B of several builds on ONE box: alternating bench runs of c2 (value, ms, e2e, conv frac, target-set frac, MHz)
+# usage: ab_libs.sh <tag> <reps> <lib.so | default> ...
+tag=$1; reps=$2; shift 2
+D=$PWD/mmr_semantic-segmentation_v1_b200
+line() { python -c "
+import json,sys; d=json.load(open(sys.argv[1])); r=d['roofline']; print(sys.argv[1], round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), round(r['frac'],4), round(r['target_set']['frac'],4), d['clocks']['sm_mhz'])" $1; }
+for rep in $(seq 1 $reps); do for lib in "$@"; do
+  name=${lib%.so}; name=${name#libmmrseg_}
+  if [ "$lib" = default ]; then unset MMR_LIB; else export MMR_LIB=$D/$lib; fi
+  python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/${tag}_${name}_$rep.json 2> gpurun_out/${tag}_err.txt || tail -3 gpurun_out/${tag}_err.txt; line gpurun_out/${tag}_${name}_$rep.json
+done; done
+unset MMR_LIB

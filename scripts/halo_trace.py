@@ -16,6 +16,7 @@ N = int(os.environ.get("BATCH", "16"))
 names = sys.argv[1:] or ["layer1", "layer4", "x_3_3.conv2", "x_1_3"]
 lib = _lib.lib()
 gen = torch.Generator(device="cuda").manual_seed(0)
+flush = None
 labels = ["entry", "dep-wait", "setup", "1st operands", "last MMA", "last store", "finalised", "exit"]
 for name, hw, srcs, cout in LAYERS:
     if not any(n in name for n in names):
@@ -37,11 +38,23 @@ for name, hw, srcs, cout in LAYERS:
             plan.run()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
+        if os.environ.get("FLUSH"):
+            # cold operands, as inside a step: 256 MB written between the launches, ONE traced launch
+            if flush is None:
+                flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+            flush.zero_()
+            e0.record()
             plan.run()
-        e1.record()
-        torch.cuda.synchronize()
+            e1.record()
+            torch.cuda.synchronize()
+            e0.elapsed_time(e1)
+            e1 = e0   # the per-launch figure below is meaningless for a single cold launch
+        else:
+            e0.record()
+            for _ in range(5):
+                plan.run()
+            e1.record()
+            torch.cuda.synchronize()
         n_ctas = min(148, plan.cfg.get("total_items", 148)) if isinstance(plan.cfg, dict) else 148
         buf = np.zeros((256, 8), dtype=np.uint64)
         _lib.check(lib.mmr_debug_halo_trace(buf.ctypes.data_as(C.c_void_p), 256))
