@@ -234,7 +234,9 @@ typedef struct {
   int32_t O, I, mode, cb, bn, n_ntiles, nchunks;
   int32_t layout; /* order of the 9 taps inside a chunk: 0 = ky*3+kx; 1 = [kx][ky = 2,1,0] (rph > 1) */
 } MmrPackJob;
-/* total_blocks = sum over the jobs of ceil(n_ntiles * nchunks * bn * cb / 1024) (the host built the table). */
+/* total_blocks = sum over the jobs of ceil(n_ntiles * nchunks * bn * cb / mmr_pack_items_per_block()) (the host
+ * built the table). */
+int mmr_pack_items_per_block(void);
 int mmr_pack_weights_halo_batch(const MmrPackJob* jobs_dev, int njobs, int64_t total_blocks, mmr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

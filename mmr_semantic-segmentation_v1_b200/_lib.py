@@ -170,6 +170,7 @@ SIGNATURES = {
     "mmr_halo_conv_plan_destroy": (_i, [_vp]),
     "mmr_debug_halo_trace": (_i, [_vp, _i]),
     "mmr_pack_weights_halo": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mmr_pack_items_per_block": (_i, []),
     "mmr_pack_weights_halo_batch": (_i, [_vp, _i, _i64, _vp]),
     "mmr_wgrad_halo_partial_floats": (_i64, [_i, _i, _i, _i, _i]),
     "mmr_wgrad_kx_partial_floats": (_i64, [_i, _i, _i, _i]),

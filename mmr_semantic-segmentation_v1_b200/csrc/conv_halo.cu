@@ -1350,15 +1350,17 @@ __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int O, int
 }
 
 // Every layer's packing in one launch.  A block owns kPackPerBlock consecutive (N tile, chunk, row, k) items
-// of one job and finds its job by walking the job sizes (staged in shared memory); a thread reads the nine
-// contiguous taps of its (output channel, input channel) pair once and writes them to the nine tap planes,
-// so consecutive lanes (consecutive k) read one contiguous stretch of the fp32 master in the fprop layout.
-constexpr int kPackPerBlock = 256 * 4;
+// of one job and finds its job by walking the job sizes (staged in shared memory); a thread takes eight
+// consecutive k of one row: in the fprop layout those are 72 consecutive floats of the fp32 master (eighteen
+// 16-byte loads), in the dgrad layout eight 36-byte records; either way nine 16-byte stores, one per tap plane
+// (one thread per (row, k) with 2-byte stores took 96 us per step for 190 MB).
+constexpr int kPackThreads = 128, kPackIters = 8;
+constexpr int kPackPerBlock = kPackThreads * 8 * kPackIters;   // 8192 items: the job walk is paid once per 16 KB written
 constexpr int kMaxPackJobs = 512;
 __device__ __forceinline__ int64_t pack_items(const MmrPackJob& j) {
   return (int64_t)j.n_ntiles * j.nchunks * j.bn * j.cb;
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPackThreads)
 pack_weights_halo_batch_kernel(const MmrPackJob* __restrict__ jobs, int njobs) {
   pdl_prologue();
   __shared__ int64_t totals[kMaxPackJobs];
@@ -1377,27 +1379,66 @@ pack_weights_halo_batch_kernel(const MmrPackJob* __restrict__ jobs, int njobs) {
   const float* __restrict__ w = j.w_oihw;
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(j.out);
   const uint32_t cb = (uint32_t)j.cb, bn = (uint32_t)j.bn, nch = (uint32_t)j.nchunks;
-  const int64_t end = min(total, (b + 1) * kPackPerBlock);
-  for (int64_t idx = b * kPackPerBlock + threadIdx.x; idx < end; idx += 256) {
-    uint32_t t = (uint32_t)idx;
-    const uint32_t k = t % cb;
-    t /= cb;
-    const uint32_t r = t % bn;
-    t /= bn;
-    const uint32_t c = t % nch, nt = t / nch;
-    const int nidx = (int)(nt * bn + r), kidx = (int)(c * cb + k);
-    float v[9];
-    const bool live = j.mode == 0 ? (nidx < j.O && kidx < j.I) : (kidx < j.O && nidx < j.I);
-    const float* src = j.mode == 0 ? w + ((size_t)nidx * j.I + kidx) * 9 : w + ((size_t)kidx * j.I + nidx) * 9;
+  // one thread and iteration = eight consecutive k of one (N tile, chunk, row): nine 16-byte stores, one per tap plane
+  for (int it = 0; it < kPackIters; ++it) {
+  const int64_t idx = b * kPackPerBlock + ((int64_t)it * kPackThreads + threadIdx.x) * 8;
+  if (idx >= total) return;
+  uint32_t t = (uint32_t)idx;
+  const uint32_t k0 = t % cb;
+  t /= cb;
+  const uint32_t r = t % bn;
+  t /= bn;
+  const uint32_t c = t % nch, nt = t / nch;
+  const int nidx = (int)(nt * bn + r), kidx0 = (int)(c * cb + k0);
+  float v[8][9];
+  if (j.mode == 0) {
+    // fprop: the eight (output channel nidx, input channel kidx0 + q) records are 72 consecutive floats
+    const float* src = w + ((size_t)nidx * j.I + kidx0) * 9;
+    if (nidx < j.O && kidx0 + 8 <= j.I && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      float f[72];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) v[q] = live ? __ldg(src + q) : 0.f;
-    // out[((nt*nchunks + c)*9 + slot)*bn + r][k], slot -> filter tap by layout, mirrored for dgrad
-    __nv_bfloat16* dst = out + ((size_t)(nt * nch + c) * 9 * bn + r) * cb + k;
+      for (int q = 0; q < 18; ++q) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(src) + q);
+        f[4 * q] = x.x, f[4 * q + 1] = x.y, f[4 * q + 2] = x.z, f[4 * q + 3] = x.w;
+      }
 #pragma unroll
-    for (int slot = 0; slot < 9; ++slot) {
-      const int tap = pack_tap(slot, j.layout);
-      dst[(size_t)slot * bn * cb] = __float2bfloat16(v[j.mode == 0 ? tap : 8 - tap]);
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) v[q][tp] = f[q * 9 + tp];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool live = nidx < j.O && kidx0 + q < j.I;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) v[q][tp] = live ? __ldg(src + q * 9 + tp) : 0.f;
+      }
     }
+  } else {
+    // dgrad: N index = input channel, K index = output channel, taps mirrored below
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const bool live = kidx0 + q < j.O && nidx < j.I;
+      const float* src = w + ((size_t)(kidx0 + q) * j.I + nidx) * 9;
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) v[q][tp] = live ? __ldg(src + tp) : 0.f;
+    }
+  }
+  // out[((nt*nchunks + c)*9 + slot)*bn + r][k], slot -> filter tap by layout, mirrored for dgrad
+  __nv_bfloat16* dst = out + ((size_t)(nt * nch + c) * 9 * bn + r) * cb + k0;
+  // walk the SOURCE taps (static register indices) and compute the slot each one goes to: the inverse of
+  // pack_tap (layout 1: slot = kx * 3 + (2 - ky)), after the mirror for dgrad
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+    const int tap = j.mode == 0 ? tp : 8 - tp;
+    const int slot = j.layout ? (tap % 3) * 3 + (2 - tap / 3) : tap;
+    uint32_t pk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q][tp], v[2 * q + 1][tp]);
+      pk[q] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)slot * bn * cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
   }
 }
 
@@ -1760,11 +1801,13 @@ extern "C" int mmr_pack_weights_halo(const float* w_oihw, int O, int I, int mode
   return 0;
 }
 
+extern "C" int mmr_pack_items_per_block(void) { return mmr::kPackPerBlock; }
+
 extern "C" int mmr_pack_weights_halo_batch(const MmrPackJob* jobs_dev, int njobs, int64_t total_blocks,
                                            mmr_stream_t stream) {
   MMR_REQUIRE(jobs_dev && njobs > 0 && njobs <= kMaxPackJobs && total_blocks > 0 && total_blocks < ((int64_t)1 << 31),
               "bad argument (at most %d jobs)", kMaxPackJobs);
-  mmr_launch((pack_weights_halo_batch_kernel), (unsigned)total_blocks, 256, 0, as_stream(stream), jobs_dev, njobs);
+  mmr_launch((pack_weights_halo_batch_kernel), (unsigned)total_blocks, kPackThreads, 0, as_stream(stream), jobs_dev, njobs);
   MMR_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

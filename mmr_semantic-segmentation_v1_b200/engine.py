@@ -239,7 +239,8 @@ class Engine:
             arr = (_lib.MmrPackJob * len(self.pack_jobs))(*self.pack_jobs)
             raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
             self.pack_jobs_dev = raw.to(self.dev)
-            blocks = sum(-(-(j.n_ntiles * j.nchunks * j.bn * j.cb) // 1024) for j in self.pack_jobs)
+            per = self.lib.mmr_pack_items_per_block()
+            blocks = sum(-(-(j.n_ntiles * j.nchunks * j.bn * j.cb) // per) for j in self.pack_jobs)
             self.repack_calls.append((self.lib.mmr_pack_weights_halo_batch,
                                       (C.c_void_p(self.pack_jobs_dev.data_ptr()), len(self.pack_jobs),
                                        C.c_int64(blocks))))
