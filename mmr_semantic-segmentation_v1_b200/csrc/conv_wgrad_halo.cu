@@ -908,7 +908,14 @@ extern "C" int mmr_wgrad_halo_plan_create(const MmrWgradHaloDesc* d, void** out_
   if (thin)  // the M tile stacks 128 / cb filter rows: the discarded ones read up to tile row 15 + 128 / cb - 1
     p.x_stage_bytes = ((uint32_t)((16 + 128 / d->cb) * p.pitch[0] * p.xrb) + 1023) / 1024 * 1024;
   p.stage_bytes = p.x_stage_bytes + (p.z_tx_bytes + 1023) / 1024 * 1024;
-  int stages = (int)((224 * 1024) / p.stage_bytes);
+  // The stage ring takes 128 KB, not all of shared memory: the weight gradient runs on the side stream beside the
+  // BatchNorm-backward passes of the main stream (HBM-bound, 32 KB of shared memory per reduction CTA), and those
+  // can only become resident on an SM whose weight-gradient CTA leaves them room.  With 224 KB (five stages of the
+  // TX = 1 kernels) the two streams merely took turns on the SMs: step 10.75 -> 10.47 ms, c3 27.11 -> 26.74 ms,
+  // c4 156.3 -> 153.4 ms; the kernel alone is as fast with two stages (MMR_WGRAD_SMEM_KB: A/B knob).
+  static const int budget_kb = getenv("MMR_WGRAD_SMEM_KB") ? atoi(getenv("MMR_WGRAD_SMEM_KB")) : 128;
+  int stages = (int)(((size_t)budget_kb * 1024) / p.stage_bytes);
+  if (stages < 2) stages = 2;
   if (stages > kWhMaxStages) stages = kWhMaxStages;
   MMR_REQUIRE(stages >= 2, "wgrad: stage of %u bytes does not fit twice in shared memory", p.stage_bytes);
   p.stages = stages;
