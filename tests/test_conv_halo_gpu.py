@@ -312,3 +312,55 @@ def test_wgrad_matches_autograd(case):
     plan.run(accumulate=True)
     torch.cuda.synchronize()
     assert (dst - 2 * ref).abs().max().item() <= 4e-3 * max(rms, 1e-6) * 8
+
+
+# (O, I, cb, bn, n_ntiles, nchunks): full tiles, a ragged N tile, ragged K (I = 3 in a 16-channel chunk, I = 40 in 64-channel
+# chunks: the scalar path of the batch kernel), narrow rows
+PACK_CASES = [(64, 64, 64, 64, 1, 1), (128, 192, 64, 128, 1, 3), (96, 64, 64, 64, 2, 1), (64, 3, 16, 64, 1, 1),
+              (32, 40, 64, 32, 1, 1), (16, 32, 32, 16, 1, 1), (2, 16, 16, 16, 1, 1)]
+
+
+def test_pack_weights_batch_matches_reference_layout():
+    """mmr_pack_weights_halo_batch (eight k per thread, 16-byte stores) against the packed layout written out in
+    PyTorch -- out[((nt*nchunks + c)*9 + slot)*bn + r][k], fprop and dgrad (mirrored taps, O and I swapped), both tap
+    orders -- and against the one-job kernel mmr_pack_weights_halo: bit-exact (one fp32 -> bf16 rounding either way)."""
+    import ctypes as C
+    from mmrseg_b200 import _lib
+    lib = _lib.lib()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    jobs, outs, want, singles = [], [], [], []
+    keep = []
+    for (O, I, cb, bn, nnt, nch) in PACK_CASES:
+        w = torch.randn((O, I, 3, 3), generator=gen, device="cuda")
+        keep.append(w)
+        for mode in (0, 1):
+            for layout in (0, 1):
+                n_rows, n_k = (O, I) if mode == 0 else (I, O)
+                # a dgrad job tiles the INPUT channels over N and the OUTPUT channels over K
+                nnt_m = nnt if mode == 0 else -(-n_rows // bn)
+                nch_m = nch if mode == 0 else -(-n_k // cb)
+                out = torch.full((nnt_m * nch_m * 9 * bn * cb,), -1.0, device="cuda", dtype=torch.bfloat16)
+                jobs.append(_lib.MmrPackJob(w.data_ptr(), out.data_ptr(), O, I, mode, cb, bn, nnt_m, nch_m, layout))
+                outs.append(out)
+                # reference layout in PyTorch
+                ww = w if mode == 0 else w.flip(2, 3).permute(1, 0, 2, 3)      # [rows][k][ky][kx], taps mirrored for dgrad
+                pad = torch.zeros((nnt_m * bn, nch_m * cb, 3, 3), device="cuda")
+                pad[:n_rows, :n_k] = ww
+                taps = pad.reshape(nnt_m, bn, nch_m, cb, 9)
+                order = [(2 - t % 3) * 3 + t // 3 for t in range(9)] if layout else list(range(9))
+                ref = taps[..., order].permute(0, 2, 4, 1, 3).contiguous().to(torch.bfloat16).reshape(-1)
+                want.append(ref)
+                single = torch.full_like(out, -1.0)
+                _lib.check(lib.mmr_pack_weights_halo(C.c_void_p(w.data_ptr()), O, I, mode, cb, bn, nnt_m, nch_m, layout,
+                                                     C.c_void_p(single.data_ptr()), stream))
+                singles.append(single)
+    arr = (_lib.MmrPackJob * len(jobs))(*jobs)
+    dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().cuda()
+    per = lib.mmr_pack_items_per_block()
+    blocks = sum(-(-(j.n_ntiles * j.nchunks * j.bn * j.cb) // per) for j in jobs)
+    _lib.check(lib.mmr_pack_weights_halo_batch(C.c_void_p(dev.data_ptr()), len(jobs), C.c_int64(blocks), stream))
+    torch.cuda.synchronize()
+    for i, (got, ref, single) in enumerate(zip(outs, want, singles)):
+        assert torch.equal(got.view(torch.int16), ref.view(torch.int16)), ("batch vs layout", i, PACK_CASES[i // 4])
+        assert torch.equal(single.view(torch.int16), ref.view(torch.int16)), ("single vs layout", i, PACK_CASES[i // 4])
