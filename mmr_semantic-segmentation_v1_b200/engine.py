@@ -927,7 +927,12 @@ class Engine:
                 self._graphs[key] = False          # seen once: capture on the next use
             elif g is False:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                # MMR_MAIN_PRIO=1 (A/B): capture on a high-priority stream, so the kernel nodes of the main chain carry a
+                # higher launch priority than the weight-gradient branch (side stream, default priority)
+                cap = None
+                if os.environ.get("MMR_MAIN_PRIO"):
+                    cap = self._cap_stream = getattr(self, "_cap_stream", None) or torch.cuda.Stream(device=self.dev, priority=-1)
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
                     self._launch(calls, torch.cuda.current_stream().cuda_stream, lo, hi, lanes=True)
                 self._graphs[key] = g
                 g.replay()
