@@ -314,7 +314,9 @@ class _PlanModel(nn.Module):
         out = torch.ops.mmrseg.plan_forward(x.contiguous(), self._handle, self.training, params)
         if out.shape[0] > 1:        # deep supervision (training): [main, aux...] at full resolution
             return [self._finish(t) for t in out.unbind(0)]
-        return self._finish(out[0])
+        # a view, not out[0]: the backward of a select zero-fills a [1, N, C, H, W] tensor and copies the gradient into
+        # it (two more passes over the logits: 0.67 GB at BASELINE config 3) before plan_backward sees it
+        return self._finish(out.view(out.shape[1:]))
 
 
     @torch.no_grad()
